@@ -1,0 +1,134 @@
+"""Pins the CPU oracle (oracle/) to vectors produced by the reference's own code
+(oracle/make_golden.py -> tests/golden/*.npz).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+
+
+def rel_l2(a, b):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    return np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-300)
+
+
+@pytest.fixture(scope="module")
+def helpers(golden_dir):
+    return np.load(os.path.join(golden_dir, "ref_helpers.npz"))
+
+
+@pytest.fixture(scope="module")
+def speech(golden_dir):
+    return np.load(os.path.join(golden_dir, "ref_speech_excerpt.npz"))
+
+
+@pytest.fixture(scope="module")
+def learned(golden_dir):
+    return np.load(os.path.join(golden_dir, "ref_learned_chunk.npz"))
+
+
+def test_reference_constants(helpers):
+    # masked_mvdr.py:9-18
+    assert helpers["constants_masked_mvdr"].tolist() == [16000, 0.01, 343.0, 90.0, 2, 1e-7, 512, 256]
+
+
+def test_steering_vectors(helpers):
+    for args, ref, ref2 in zip(helpers["sv_args"], helpers["sv_out"], helpers["sv_full_out"]):
+        got = O.steering_vector(*args)
+        assert np.array_equal(got, ref)
+        assert np.array_equal(got, ref2)
+    f = helpers["asv_f_bins"]
+    assert np.array_equal(O.all_steering_vectors(f, 90.0, 0.04, 343.0)[:, :, None], helpers["asv_out"])
+    assert np.array_equal(O.all_steering_vectors(f, 40.0, 0.04, 343.0)[:, :, None], helpers["asv_out_40"])
+
+
+def test_geometric_mask_bit_exact(helpers):
+    got = O.geometric_phase_mask(helpers["geo_Y"].astype(np.complex128))
+    assert np.array_equal(got, helpers["geo_mask"])
+    assert set(np.unique(got)) == {0.01, 1.0}
+
+
+def test_batch_mvdr(helpers):
+    f = helpers["asv_f_bins"]
+    Y = helpers["bm_Y"].astype(np.complex128)
+    m = helpers["bm_mask"].astype(np.float64)
+    for ang, sig, key in ((90.0, 1e-5, "bm_out"), (40.0, 1e-3, "bm_out_40")):
+        d = O.all_steering_vectors(f, ang, 0.04, 343.0)[:, :, None]
+        got = O.batch_mvdr_vec(Y, m, f, d, sig)
+        assert rel_l2(got, helpers[key]) < 1e-13
+    # the loop form with the tf_lite constants is the same arithmetic
+    cfg = O.PRESETS["tf_lite"]
+    S = O.mvdr_oracle._mvdr_from_noise_weight(Y, 1.0 - m, cfg)
+    assert rel_l2(S, helpers["bm_out"]) < 1e-12
+
+
+def test_scores(helpers):
+    est, t, i = helpers["score_in"].astype(np.float64)
+    assert np.allclose(O.osinr_osir(est, t, i), helpers["score_osinr_osir"], rtol=0, atol=1e-12)
+    assert np.allclose(O.sir_sdr_unit_output(est, t, i), helpers["score_sdr_sir"], rtol=0, atol=1e-12)
+    # full_audio.../inference.py:77-85 returns the SIR twice; same projection, eps 1e-6 on the norms
+    assert abs(O.sir_sdr_unit_output(est, t, i)[1] - helpers["score_full_manual"][0]) < 1e-6
+
+
+def test_far_field_mixer_parts(helpers):
+    got = np.array([O.far_field_delays(a, 0.04, 343.0) for a in helpers["ffd_angles"]])
+    assert np.array_equal(got, helpers["ffd_out"])
+    assert np.array_equal(O.fractional_delay(helpers["fd_in"], 3.3e-5, 16000), helpers["fd_out"])
+
+
+@pytest.mark.parametrize("n_fft,hop,L", [(512, 128, 80000), (512, 256, 32000), (1024, 512, 32000), (512, 128, 1000),
+                                           (512, 128, 64001), (256, 64, 777)])
+def test_stft_restatement_matches_scipy(n_fft, hop, L):
+    rng = np.random.default_rng(L)
+    x = rng.standard_normal((2, L))
+    Z = O.stft_scipy(x, n_fft, hop)
+    assert Z.shape == (2, n_fft // 2 + 1, O.n_frames(L, n_fft, hop))
+    assert rel_l2(O.stft_np(x, n_fft, hop), Z) < 1e-14
+    S = Z[0] * (1 + 0.3j)                    # non-Hermitian-consistent DC/Nyquist imaginary parts
+    xr = O.istft_scipy(S, n_fft, hop)
+    assert xr.shape == ((Z.shape[-1] - 1) * hop,)
+    assert rel_l2(O.istft_np(S, n_fft, hop), xr) < 1e-13
+    # round trip (COLA): istft(stft(x)) == x on the first L samples
+    assert rel_l2(O.istft_scipy(Z[1], n_fft, hop)[:L], x[1]) < 1e-13
+
+
+def _pcm(a):
+    return a.astype(np.float64) / 32768.0
+
+
+def test_oracle_debug_main(speech):
+    """oracle_debug.main() unmodified (hop 256) on the real-speech excerpt."""
+    mix, tgt, itf = _pcm(speech["mix_pcm"]).T, _pcm(speech["tgt_pcm"]), _pcm(speech["int_pcm"])
+    got = O.oracle_mask_mvdr(mix, tgt, itf, O.PRESETS["oracle_debug"])
+    ref64 = speech["oracle_debug_out_f64read"]
+    assert got.shape == ref64.shape
+    assert rel_l2(got, ref64) < 1e-12
+    # the reference as shipped reads float32 (complex64 STFT inside scipy): same thing to ~1e-6
+    assert rel_l2(got, speech["oracle_debug_out_f32read"]) < 2e-5
+
+
+def test_masked_mvdr_main(speech):
+    mix = _pcm(speech["mix_pcm"]).T
+    got = O.geometric_mask_mvdr(mix, O.PRESETS["masked_mvdr"])
+    assert rel_l2(got, speech["masked_mvdr_out_f64read"]) < 1e-9
+    assert rel_l2(got, speech["masked_mvdr_out_f32read"]) < 1e-2   # sigma=1e-7: ill-conditioned, f32 STFT moves it
+
+
+def test_process_chunk_and_main_deploy(speech, learned):
+    L = int(learned["L"])
+    mix = _pcm(speech["mix_pcm"])[:L].astype(np.float32)    # the reference reads float32
+    masks = learned["masks"]
+    out0 = O.learned_mask_mvdr_chunk(mix[:32000], lambda X: masks[0], O.PRESETS["full_audio"])
+    assert out0.shape == learned["chunk0_out"].shape == (32256,)
+    assert rel_l2(out0, learned["chunk0_out"]) < 2e-5         # reference STFT is complex64 here
+    it = iter(masks)
+    full = O.chunked_enhance(mix, lambda X: next(it), O.PRESETS["full_audio"], win=32000)
+    assert full.shape == learned["main_deploy_out"].shape == (L,)
+    assert rel_l2(full, learned["main_deploy_out"]) < 2e-5
+
+
+def test_hybrid_null_golden_present(helpers):
+    # Final_pipeline/src/inference.py:28-98 is a "next" row; vector kept for it.
+    assert helpers["hn_out"].shape == (513, 64)
