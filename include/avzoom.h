@@ -1,0 +1,155 @@
+/*
+ * avzoom.h -- C ABI of libavzoom.so: the B200 (sm_100a) mask-driven 2-mic MVDR hot path.
+ *
+ * The reference (Senpai-sama06/real-time-audio-visual-zooming, pure Python) has no FFI of its own;
+ * each entry point below replaces one inline numpy/scipy block of it and says which (paths are
+ * relative to the reference root).  A reference-side binding is a ctypes stub.
+ *
+ * Conventions
+ *   - every pointer is a caller-owned DEVICE buffer unless the name ends in _host; nothing is
+ *     allocated per call (per-(device, n_fft) constant tables are created once, see avz_init);
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it and re-entrant;
+ *   - return value: 0 on success, a negative AVZ_E* code otherwise; avz_last_error() gives the
+ *     thread-local message.  Nothing throws or exits across this boundary;
+ *   - layouts follow the reference: spectra (M, F, T) with T contiguous, masks (F, T), batch
+ *     dimension prepended; complex numbers are interleaved float pairs (re, im);
+ *   - F = n_fft/2 + 1, T = avz_num_frames(L, n_fft, hop) = ceil(L/hop) + 1 for hop | n_fft,
+ *     iSTFT length = (T - 1) * hop  (scipy.signal.stft/istft, boundary='zeros', padded=True).
+ *   - supported: n_fft in {256, 512, 1024, 2048}, hop with n_fft % hop == 0 and 2 <= n_fft/hop <= 8,
+ *     L >= n_fft.
+ */
+#ifndef AVZOOM_H_
+#define AVZOOM_H_
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define AVZ_API __attribute__((visibility("default")))
+#else
+#define AVZ_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVZ_VERSION 100
+
+#define AVZ_OK 0
+#define AVZ_EINVAL (-1)   /* bad argument (shape, n_fft, hop, null pointer) */
+#define AVZ_ECUDA (-2)    /* CUDA runtime error; message has cudaGetErrorString */
+#define AVZ_ENOGPU (-3)   /* no sm_100 device / kernels not loadable on this device */
+
+/* post-filter applied to the beamformed spectrum */
+#define AVZ_POST_NONE 0            /* masked_mvdr.py:124-127                                  */
+#define AVZ_POST_ONE_MINUS_NOISE 1 /* oracle_debug.py:84-90     S * (1 - noise_mask)           */
+#define AVZ_POST_FLOOR 2           /* full_audio.../inference.py:116   S * max(mask, floor)    */
+#define AVZ_POST_MASK 3            /* Final_pipeline/src/inference.py:219   S * mask           */
+
+/* what bins below the high-pass do (SURVEY 8-A2 "bins below the high-pass") */
+#define AVZ_HP_NONE 0 /* tf_lite_version/inference.py batch_mvdr: no high-pass   */
+#define AVZ_HP_ZERO 1 /* oracle_debug.py:69  `continue` -> bin stays 0           */
+#define AVZ_HP_MIC0 2 /* Final_pipeline/src/inference.py:51-53  pass mic 0       */
+
+/* feature layouts */
+#define AVZ_FEAT_LOGMAG_IPD 0         /* (2,F,T): ln(|Y0|+1e-7), angle(Y0)-angle(Y1); full_audio.../inference.py:91-94 */
+#define AVZ_FEAT_LOGMAG_IPD_WRAPPED 1 /* same, IPD wrapped to (-pi, pi]; notebook cell7:130-137                          */
+#define AVZ_FEAT_PHYSICS_NHWC 2       /* (F,T,4): logmag, sin ipd, cos ipd, k/(F-1); Final_pipeline/src/inference.py:117-128 */
+
+/* Every constant in which the reference's call sites differ (SURVEY 8-A2 variant table). */
+typedef struct AvzMvdrCfg {
+  float sigma;      /* diagonal loading:            oracle_debug.py:24,70 (1), masked_mvdr.py:16 (1e-7), .../inference.py:25 (1e-5) */
+  float norm_eps;   /* sum(mask) + norm_eps:        oracle_debug.py:64 (1e-6)                                                        */
+  float sqrt_eps;   /* sqrt(mask + sqrt_eps):       tf_lite_version/inference.py:111 (1e-10), 0 elsewhere                            */
+  float w_eps;      /* d^H u + w_eps:               oracle_debug.py:77 (1e-10)                                                       */
+  int32_t hp_bins;  /* number of leading bins with f < hp_hz (4 for 100 Hz at 512/16k)                                               */
+  int32_t hp_mode;  /* AVZ_HP_*                                                                                                      */
+  int32_t post_mode;/* AVZ_POST_*                                                                                                    */
+  float post_floor; /* 0.05 at full_audio.../inference.py:116                                                                        */
+} AvzMvdrCfg;
+
+AVZ_API int avz_version(void);
+AVZ_API const char* avz_last_error(void);
+
+/* Create the per-device constant tables (window, twiddles) for n_fft ahead of time (optional;
+ * otherwise done on first use).  Do this before capturing calls into a CUDA graph. */
+AVZ_API int avz_init(int n_fft);
+
+/* scipy.signal.stft frame count (boundary='zeros', padded=True). */
+AVZ_API int64_t avz_num_frames(int64_t L, int n_fft, int hop);
+
+/* ---- STFT: replaces scipy.signal.stft(x, fs, nperseg=n_fft, noverlap=n_fft-hop) at
+ * oracle_debug.py:42-44, masked_mvdr.py:76, full_audio.../inference.py:90.
+ * x [B, C, L] f32  ->  Y [B, C, F, T] complex64. */
+AVZ_API int avz_stft_f32(const float* x, int B, int C, int64_t L, int n_fft, int hop, float* Y, void* stream);
+
+/* ---- iSTFT + overlap-add: replaces scipy.signal.istft at oracle_debug.py:93, masked_mvdr.py:127.
+ * S [B, F, T] complex64 -> x [B, (T-1)*hop] f32.  If peak != NULL, peak[b] receives max|x[b,:]|
+ * (peak must be zeroed by the caller). */
+AVZ_API int avz_istft_f32(const float* S, int B, int T, int n_fft, int hop, float* x, float* peak, void* stream);
+
+/* ---- x[b,:] /= (peak[b] + peak_eps): oracle_debug.py:94 (eps 0), masked_mvdr.py:128 (1e-6). */
+AVZ_API int avz_peak_normalise_f32(float* x, int B, int64_t n, const float* peak, float peak_eps, void* stream);
+
+/* ---- fused pass A of the oracle path: STFT(tgt), STFT(int), STFT(mix) -> IBM -> masked covariance,
+ * without materialising any spectrum.  Replaces oracle_debug.py:42-64.
+ * mix [B,2,L], tgt [B,L], itf [B,L] f32.
+ * ibm_bits [B, T, ceil(F/32)] u32: bit (k & 31) of word (k >> 5) of frame t = (|S_int| > |S_tgt|) at bin k.
+ * R [B, F, 4] f32 = (R00, R11, Re R01, Im R01) of  sum_t m y y^H / (sum_t m + norm_eps);  msum [B, F] = sum_t m.
+ * ws: workspace of avz_ibm_cov_ws_bytes() bytes (partial sums of frame chunks). */
+AVZ_API int64_t avz_ibm_cov_ws_bytes(int B, int64_t L, int n_fft, int hop);
+AVZ_API int avz_ibm_cov_f32(const float* mix, const float* tgt, const float* itf, int B, int64_t L, int n_fft, int hop,
+                    float norm_eps, uint32_t* ibm_bits, float* R, float* msum, void* ws, void* stream);
+
+/* ---- masked covariance from a waveform and a given (target-probability) mask, learned-mask path:
+ * replaces full_audio.../inference.py:90,102-108 / tf_lite_version/inference.py:97-127.
+ * mask [B, F, T] f32 is the TARGET probability; the noise weight is (1 - mask). */
+AVZ_API int avz_wave_mask_cov_f32(const float* mix, const float* mask, int B, int64_t L, int n_fft, int hop,
+                          float sqrt_eps, float norm_eps, float* R, float* msum, void* ws, void* stream);
+
+/* ---- masked covariance from a given spectrum: generic form of oracle_debug.py:56-64.
+ * Y [B,2,F,T] complex64, noise_w [B,F,T] f32 (the weight itself, not 1 - mask). */
+AVZ_API int avz_spec_mask_cov_f32(const float* Y, const float* noise_w, int B, int F, int T, float sqrt_eps, float norm_eps,
+                          float* R, float* msum, void* stream);
+
+/* ---- closed-form 2x2 MVDR weights: replaces oracle_debug.py:68-79 (np.linalg.solve per bin).
+ * R [B,F,4], dvec [F,2] complex64 (steering vectors), -> w [B,F,2] complex64.
+ * bins k < cfg->hp_bins get w = 0 (AVZ_HP_ZERO) or [1,0] (AVZ_HP_MIC0); det == 0 -> [1,0]. */
+AVZ_API int avz_mvdr_weights_f32(const float* R, const float* dvec, int B, int F, const AvzMvdrCfg* cfg, float* w, void* stream);
+
+/* ---- beamform a given spectrum: oracle_debug.py:80.  w [B,F,2], Y [B,2,F,T] -> S [B,F,T] complex64. */
+AVZ_API int avz_beamform_f32(const float* w, const float* Y, int B, int F, int T, float* S, void* stream);
+
+/* ---- fused pass B: STFT(mix) -> w^H y -> post-filter -> iSTFT/overlap-add (+ per-utterance peak).
+ * Replaces oracle_debug.py:80-93 / full_audio.../inference.py:114-117.
+ * Exactly one of ibm_bits / mask may be non-NULL (both NULL only with AVZ_POST_NONE).
+ * out [B, (T-1)*hop] f32; peak [B] (zeroed by caller) or NULL. */
+AVZ_API int avz_mvdr_apply_f32(const float* mix, const float* w, const uint32_t* ibm_bits, const float* mask, int B, int64_t L,
+                       int n_fft, int hop, const AvzMvdrCfg* cfg, float* out, float* peak, void* stream);
+
+/* ---- IBM from given spectra: oracle_debug.py:49-53 (noise polarity) / model_training.py:90 (target polarity).
+ * a, b [n] complex64 -> out [n] f32 = (|a| > |b|) ? 1 : 0, compared exactly (float64 squares). */
+AVZ_API int avz_mag_greater_f32(const float* a, const float* b, int64_t n, float* out, void* stream);
+
+/* ---- geometric phase mask: masked_mvdr.py:37-46.  Y [B,2,F,T] -> mask [B,F,T] in {0.01, 1}. */
+AVZ_API int avz_geometric_mask_f32(const float* Y, int B, int F, int T, float* mask, void* stream);
+
+/* ---- unpack ibm_bits [B,T,ceil(F/32)] to a float mask [B,F,T] of {0,1}. */
+AVZ_API int avz_ibm_unpack_f32(const uint32_t* ibm_bits, int B, int F, int T, float* mask, void* stream);
+
+/* ---- features from a spectrum: full_audio.../inference.py:91-94.  Y [B,2,F,T] -> X (mode layout). */
+AVZ_API int avz_features_f32(const float* Y, int B, int F, int T, int mode, float* X, void* stream);
+
+/* ---- features straight from the waveform (STFT fused, no spectrum written): mix [B,2,L] -> X. */
+AVZ_API int avz_wave_features_f32(const float* mix, int B, int64_t L, int n_fft, int hop, int mode, float* X, void* stream);
+
+/* ---- projection scores: Final_pipeline/src/metrics.py:102-123 and scripts/run_metrics.py:6-36.
+ * est [B, n_est], tgt [B, n_ref], itf [B, n_ref]; uses the first min(n_est, n_ref) samples.
+ * scores [B,4] f32 = (OSINR, OSIR, SDR_unit_output, SIR_unit_output) in dB. */
+AVZ_API int avz_sir_f32(const float* est, const float* tgt, const float* itf, int B, int64_t n_est, int64_t n_ref,
+                float* scores, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVZOOM_H_ */

@@ -1,0 +1,181 @@
+// Shared device/host helpers for libavzoom (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "avzoom.h"
+
+namespace avz {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+// Per-(device, n_fft) constant tables, created once by tables_for().
+struct Tables {
+  const float2* tw;     // [n]  exp(-2 pi i k / n), rounded from float64
+  const float* win;     // [n]  periodic Hann, rounded from float64
+  const double2* tw_d;  // [n]  same twiddles in float64 (exact-tie path of the IBM)
+  const double* win_d;  // [n]
+};
+
+int set_error(int code, const char* fmt, ...);
+int tables_for(int n_fft, Tables* out);
+int check_fft_args(int n_fft, int hop, int64_t L);
+int num_sms();
+
+#define AVZ_CUDA_OK(expr)                                                                   \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) return avz::set_error(AVZ_ECUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define AVZ_LAUNCH_OK(name)                                                                 \
+  do {                                                                                      \
+    cudaError_t _e = cudaGetLastError();                                                    \
+    if (_e != cudaSuccess) return avz::set_error(AVZ_ECUDA, "launch %s: %s", name, cudaGetErrorString(_e)); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// complex helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+// a * conj(b)
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {
+  return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+}
+__device__ __forceinline__ float cabs2(float2 a) { return fmaf(a.x, a.x, a.y * a.y); }
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// Generic warp-level FFT in shared memory (any power-of-two N >= 64).  One warp transforms one
+// length-N complex sequence with Stockham autosort passes (radix 4, plus one radix-2 pass when
+// log2 N is odd), ping-ponging between two N-element buffers.  Returns the buffer that holds the
+// result in natural order.  `tw` is exp(-2 pi i k / N) (shared or global memory).
+// The specialised register-resident 512-point transform lives in avz_fft512.cuh.
+// ------------------------------------------------------------------------------------------
+template <int N, bool INV>
+__device__ __forceinline__ float2* warp_fft_smem(float2* a, float2* b, const float2* __restrict__ tw, int lane) {
+  float2* in = a;
+  float2* out = b;
+  int Ns = 1;
+#pragma unroll 1
+  for (; Ns * 4 <= N; Ns *= 4) {
+    const int tstep = N / (4 * Ns);
+    for (int j = lane; j < N / 4; j += kWarp) {
+      const int k = j & (Ns - 1);
+      float2 v0 = in[j];
+      float2 v1 = in[j + N / 4];
+      float2 v2 = in[j + N / 2];
+      float2 v3 = in[j + 3 * N / 4];
+      if (Ns > 1) {
+        float2 w1 = tw[k * tstep];
+        float2 w2 = tw[2 * k * tstep];
+        float2 w3 = tw[3 * k * tstep];
+        if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
+        v1 = cmul(v1, w1);
+        v2 = cmul(v2, w2);
+        v3 = cmul(v3, w3);
+      }
+      const float2 t0 = cadd(v0, v2);
+      const float2 t1 = csub(v0, v2);
+      const float2 t2 = cadd(v1, v3);
+      float2 t3 = csub(v1, v3);
+      t3 = INV ? make_float2(-t3.y, t3.x) : make_float2(t3.y, -t3.x);  // * (+i) inverse, * (-i) forward
+      const int base = (j - k) * 4 + k;
+      out[base] = cadd(t0, t2);
+      out[base + Ns] = cadd(t1, t3);
+      out[base + 2 * Ns] = csub(t0, t2);
+      out[base + 3 * Ns] = csub(t1, t3);
+    }
+    __syncwarp();
+    float2* tmp = in; in = out; out = tmp;
+  }
+  if (Ns < N) {  // one radix-2 pass, Ns == N/2
+    for (int j = lane; j < N / 2; j += kWarp) {
+      float2 w1 = tw[j];  // k = j (Ns = N/2), angle -2 pi k / N
+      if (INV) w1.y = -w1.y;
+      const float2 v0 = in[j];
+      const float2 v1 = cmul(in[j + N / 2], w1);
+      out[j] = cadd(v0, v1);
+      out[j + N / 2] = csub(v0, v1);
+    }
+    __syncwarp();
+    float2* tmp = in; in = out; out = tmp;
+  }
+  return in;
+}
+
+// Load frame t of a pair of real signals (sb may be null) as one complex sequence, windowed:
+// buf[n] = win[n] * scale * (sa[i] + i sb[i]),  i = t*hop - N/2 + n, zero outside [0, L).
+// This is scipy's zero extension (boundary='zeros') and tail padding (padded=True).
+// Returns this lane's share of sum |buf|^2 (for the IBM tie tolerance).
+template <int N>
+__device__ __forceinline__ float load_frame_pair(float2* buf, const float* __restrict__ sa, const float* __restrict__ sb,
+                                                 int64_t L, int64_t start, const float* __restrict__ win, float scale,
+                                                 int lane) {
+  float e = 0.f;
+#pragma unroll 4
+  for (int n = lane; n < N; n += kWarp) {
+    const int64_t i = start + n;
+    float xa = 0.f, xb = 0.f;
+    if (i >= 0 && i < L) {
+      xa = __ldg(sa + i);
+      if (sb) xb = __ldg(sb + i);
+    }
+    const float w = win[n] * scale;
+    const float2 v = make_float2(xa * w, xb * w);
+    e = fmaf(v.x, v.x, fmaf(v.y, v.y, e));
+    buf[n] = v;
+  }
+  return e;
+}
+
+// Split the transform Z of (a + i b), a and b real, at bin k (0 <= k <= N/2):
+//   A[k] = (Z[k] + conj Z[N-k]) / 2 ,  B[k] = -i (Z[k] - conj Z[N-k]) / 2
+__device__ __forceinline__ void unpack_pair(float2 zk, float2 zm, float2& A, float2& B) {
+  A = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+  B = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+}
+
+// log-magnitude + inter-channel phase difference of one TF bin (full_audio.../inference.py:91-94):
+// np.abs is hypot; np.log / np.angle run in float64 there and float32 here (far inside the 1e-4 budget).
+__device__ __forceinline__ void feature_values(float2 y0, float2 y1, float& logmag, float& ipd) {
+  logmag = logf(hypotf(y0.x, y0.y) + 1e-7f);
+  ipd = atan2f(y0.y, y0.x) - atan2f(y1.y, y1.x);
+}
+
+// Store one bin's features in the layout `mode` asks for (AVZ_FEAT_*).
+__device__ __forceinline__ void store_features(float* __restrict__ X, int mode, int b, int k, int t, int F, int T,
+                                               float lm, float ipd) {
+  if (mode == AVZ_FEAT_PHYSICS_NHWC) {
+    float s, c;
+    sincosf(ipd, &s, &c);
+    reinterpret_cast<float4*>(X)[((int64_t)b * F + k) * T + t] =
+        make_float4(lm, s, c, (float)((double)k / (double)(F - 1)));
+  } else {
+    if (mode == AVZ_FEAT_LOGMAG_IPD_WRAPPED) {
+      const float two_pi = 6.28318530717958647692f;
+      ipd = ipd - two_pi * rintf(ipd / two_pi);  // wrap to [-pi, pi]
+    }
+    X[(((int64_t)b * 2 + 0) * F + k) * T + t] = lm;
+    X[(((int64_t)b * 2 + 1) * F + k) * T + t] = ipd;
+  }
+}
+
+}  // namespace avz

@@ -1,0 +1,607 @@
+// Generic-size (n_fft in {256, 512, 1024}) fused kernels: one warp per frame, shared-memory FFT.
+//
+//   k_stft         frame + window + FFT (two real channels per complex transform) -> spectrum
+//   k_cov          pass A: spectra of (tgt, int) -> IBM bits (exact-tie path in float64), spectra of the
+//                  two mics -> mask-weighted 2x2 Hermitian covariance partial sums (no spectrum stored)
+//   k_synth        pass B / iSTFT: [STFT(mix) -> w^H y -> post-filter | given spectrum] -> inverse FFT ->
+//                  window -> deterministic overlap-add -> / sum w^2 -> trimmed output (+ running peak)
+//
+// Reference blocks replaced: rt_av_zoom/core/oracle_debug.py:42-94 (see include/avzoom.h per entry).
+#include "avz_common.cuh"
+
+namespace avz {
+
+template <int N>
+struct Geo {
+  static constexpr int F = N / 2 + 1;
+  static constexpr int FW = N / 64 + 1;                 // 32-bit words per frame of IBM bits
+  static constexpr int BINS_PER_LANE = N / 64 + 1;      // bins k = lane + 32 i, i < BINS_PER_LANE, k <= N/2
+  static constexpr int FP = (F + 31) / 32 * 32;         // padded bin count for partial sums
+  static constexpr int WARPS = (N <= 512) ? 8 : 4;
+};
+
+__host__ __device__ inline int cov_chunks(int B, int T, int warps, int sms) {
+  // enough (utterance, frame-chunk) blocks to fill the machine twice; whole utterances when B is large
+  int chunks = 1;
+  if (B < 2 * sms) chunks = (2 * sms + B - 1) / B;
+  int max_chunks = T / (2 * warps);
+  if (max_chunks < 1) max_chunks = 1;
+  if (chunks > max_chunks) chunks = max_chunks;
+  return chunks;
+}
+
+// ------------------------------------------------------------------------------------------
+// STFT
+// ------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(Geo<N>::WARPS * 32)
+k_stft(const float* __restrict__ x, int C, int64_t L, int T, int hop, float2* __restrict__ Y, Tables tb,
+       int frames_per_block) {
+  constexpr int WARPS = Geo<N>::WARPS;
+  constexpr int F = Geo<N>::F;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* s_tw = reinterpret_cast<float2*>(smem_raw);
+  float* s_win = reinterpret_cast<float*>(s_tw + N);
+  float2* bufs = reinterpret_cast<float2*>(s_win + N);
+  for (int i = threadIdx.x; i < N; i += WARPS * 32) {
+    s_tw[i] = tb.tw[i];
+    s_win[i] = tb.win[i];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, c0 = 2 * blockIdx.y;
+  const bool has_b = (c0 + 1) < C;
+  const float* sa = x + ((int64_t)b * C + c0) * L;
+  const float* sb = has_b ? sa + L : nullptr;
+  float2* b0 = bufs + (size_t)warp * 2 * N;
+  float2* b1 = b0 + N;
+  float2* Ya = Y + ((int64_t)b * C + c0) * F * (int64_t)T;
+  float2* Yb = Ya + (int64_t)F * T;
+  const int t_begin = blockIdx.x * frames_per_block;
+  const int t_end = min(T, t_begin + frames_per_block);
+  for (int t = t_begin + warp; t < t_end; t += WARPS) {
+    load_frame_pair<N>(b0, sa, sb, L, (int64_t)t * hop - N / 2, s_win, 2.0f / N, lane);
+    __syncwarp();
+    const float2* z = warp_fft_smem<N, false>(b0, b1, s_tw, lane);
+    for (int k = lane; k <= N / 2; k += kWarp) {
+      float2 A, Bv;
+      unpack_pair(z[k], z[(N - k) & (N - 1)], A, Bv);
+      Ya[(int64_t)k * T + t] = A;
+      if (has_b) Yb[(int64_t)k * T + t] = Bv;
+    }
+    __syncwarp();
+  }
+}
+
+// Features straight from the waveform: STFT of the two mics fused with log-magnitude + IPD
+// (full_audio.../inference.py:90-94); the spectrum is never written.
+template <int N>
+__global__ void __launch_bounds__(Geo<N>::WARPS * 32)
+k_wave_features(const float* __restrict__ mix, int64_t L, int T, int hop, int mode, float* __restrict__ X, Tables tb,
+                int frames_per_block) {
+  constexpr int WARPS = Geo<N>::WARPS;
+  constexpr int F = Geo<N>::F;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* s_tw = reinterpret_cast<float2*>(smem_raw);
+  float* s_win = reinterpret_cast<float*>(s_tw + N);
+  float2* bufs = reinterpret_cast<float2*>(s_win + N);
+  for (int i = threadIdx.x; i < N; i += WARPS * 32) {
+    s_tw[i] = tb.tw[i];
+    s_win[i] = tb.win[i];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const float* m0 = mix + (int64_t)b * 2 * L;
+  const float* m1 = m0 + L;
+  float2* b0 = bufs + (size_t)warp * 2 * N;
+  float2* b1 = b0 + N;
+  const int t_begin = blockIdx.x * frames_per_block;
+  const int t_end = min(T, t_begin + frames_per_block);
+  for (int t = t_begin + warp; t < t_end; t += WARPS) {
+    load_frame_pair<N>(b0, m0, m1, L, (int64_t)t * hop - N / 2, s_win, 2.0f / N, lane);
+    __syncwarp();
+    const float2* z = warp_fft_smem<N, false>(b0, b1, s_tw, lane);
+    for (int k = lane; k <= N / 2; k += kWarp) {
+      float2 Y0, Y1;
+      unpack_pair(z[k], z[(N - k) & (N - 1)], Y0, Y1);
+      float lm, ipd;
+      feature_values(Y0, Y1, lm, ipd);
+      store_features(X, mode, b, k, t, F, T, lm, ipd);
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// pass A: IBM + masked covariance partial sums
+// ------------------------------------------------------------------------------------------
+// Exact decision |S_int[k]| > |S_tgt[k]| for one frame in float64 (direct DFT, whole warp cooperates).
+template <int N>
+__device__ __forceinline__ bool ibm_exact(const float* __restrict__ tgt, const float* __restrict__ itf, int64_t L,
+                                          int64_t start, int k, const Tables& tb, int lane) {
+  double tr = 0, ti = 0, ir = 0, ii = 0;
+  for (int n = lane; n < N; n += kWarp) {
+    const int64_t i = start + n;
+    if (i >= 0 && i < L) {
+      const double w = tb.win_d[n];
+      const double2 e = tb.tw_d[(n * k) & (N - 1)];
+      const double a = w * (double)__ldg(tgt + i);
+      const double c = w * (double)__ldg(itf + i);
+      tr = fma(a, e.x, tr);
+      ti = fma(a, e.y, ti);
+      ir = fma(c, e.x, ir);
+      ii = fma(c, e.y, ii);
+    }
+  }
+  tr = warp_sum(tr);
+  ti = warp_sum(ti);
+  ir = warp_sum(ir);
+  ii = warp_sum(ii);
+  return (ir * ir + ii * ii) > (tr * tr + ti * ti);
+}
+
+enum { COV_IBM = 0, COV_MASK = 1 };
+
+// part layout: [B][chunks][5][FP] = (R00, R11, Re R01, Im R01, sum m), un-normalised.
+template <int N, int MODE>
+__global__ void __launch_bounds__(Geo<N>::WARPS * 32)
+k_cov(const float* __restrict__ mix, const float* __restrict__ tgt, const float* __restrict__ itf,
+      const float* __restrict__ mask, int64_t L, int T, int hop, int frames_per_chunk, float sqrt_eps,
+      uint32_t* __restrict__ ibm_bits, float* __restrict__ part, Tables tb) {
+  constexpr int WARPS = Geo<N>::WARPS;
+  constexpr int F = Geo<N>::F;
+  constexpr int FW = Geo<N>::FW;
+  constexpr int BPL = Geo<N>::BINS_PER_LANE;
+  constexpr int FP = Geo<N>::FP;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* s_tw = reinterpret_cast<float2*>(smem_raw);
+  float* s_win = reinterpret_cast<float*>(s_tw + N);
+  float2* bufs = reinterpret_cast<float2*>(s_win + N);
+  float* s_acc = reinterpret_cast<float*>(bufs + (size_t)WARPS * 2 * N);  // [WARPS][5][FP]
+  for (int i = threadIdx.x; i < N; i += WARPS * 32) {
+    s_tw[i] = tb.tw[i];
+    s_win[i] = tb.win[i];
+  }
+  for (int i = threadIdx.x; i < WARPS * 5 * FP; i += WARPS * 32) s_acc[i] = 0.f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
+  const float* m0 = mix + (int64_t)b * 2 * L;
+  const float* m1 = m0 + L;
+  const float* tg = (MODE == COV_IBM) ? tgt + (int64_t)b * L : nullptr;
+  const float* it = (MODE == COV_IBM) ? itf + (int64_t)b * L : nullptr;
+  float2* b0 = bufs + (size_t)warp * 2 * N;
+  float2* b1 = b0 + N;
+  float* acc = s_acc + (size_t)warp * 5 * FP;
+  const int t_begin = chunk * frames_per_chunk;
+  const int t_end = min(T, t_begin + frames_per_chunk);
+
+  for (int t = t_begin + warp; t < t_end; t += WARPS) {
+    const int64_t start = (int64_t)t * hop - N / 2;
+    float wgt[BPL];  // noise weight of this lane's bins in this frame
+    if (MODE == COV_IBM) {
+      float e2 = load_frame_pair<N>(b0, tg, it, L, start, s_win, 2.0f / N, lane);
+      e2 = warp_sum(e2);
+      __syncwarp();
+      const float2* z = warp_fft_smem<N, false>(b0, b1, s_tw, lane);
+      const float delta = 4e-6f * sqrtf(e2);  // bound on the float32 FFT error of one bin
+      uint32_t* bits_t = ibm_bits + ((int64_t)b * T + t) * FW;
+#pragma unroll
+      for (int i = 0; i < BPL; ++i) {
+        const int k = lane + 32 * i;
+        bool bit = false, amb = false;
+        if (k <= N / 2) {
+          float2 St, Si;
+          unpack_pair(z[k], z[(N - k) & (N - 1)], St, Si);
+          const float pt = cabs2(St), pi = cabs2(Si);
+          bit = pi > pt;
+          const float mx = fmaxf(pt, pi);
+          // too close to call in float32 (but not the exact 0 == 0 tie of silence): redo in float64
+          amb = (mx > 0.f) && (fabsf(pi - pt) <= 4.f * delta * sqrtf(mx) + 2.f * delta * delta);
+        }
+        unsigned am = __ballot_sync(kFull, amb);
+        while (am) {
+          const int src = __ffs(am) - 1;
+          const bool r = ibm_exact<N>(tg, it, L, start, src + 32 * i, tb, lane);
+          if (lane == src) bit = r;
+          am &= am - 1;
+        }
+        const unsigned word = __ballot_sync(kFull, bit);
+        if (lane == 0) bits_t[i] = word;
+        wgt[i] = bit ? 1.f : 0.f;
+      }
+      __syncwarp();
+    } else {
+#pragma unroll
+      for (int i = 0; i < BPL; ++i) {
+        const int k = lane + 32 * i;
+        wgt[i] = (k <= N / 2) ? 1.f - __ldg(mask + ((int64_t)b * F + k) * T + t) : 0.f;
+      }
+    }
+    load_frame_pair<N>(b0, m0, m1, L, start, s_win, 2.0f / N, lane);
+    __syncwarp();
+    const float2* z = warp_fft_smem<N, false>(b0, b1, s_tw, lane);
+#pragma unroll
+    for (int i = 0; i < BPL; ++i) {
+      const int k = lane + 32 * i;
+      if (k <= N / 2) {
+        float2 Y0, Y1;
+        unpack_pair(z[k], z[(N - k) & (N - 1)], Y0, Y1);
+        const float m = wgt[i];
+        const float ms = (MODE == COV_MASK) ? m + sqrt_eps : m;
+        const float2 c01 = cmulc(Y0, Y1);
+        acc[0 * FP + k] = fmaf(ms, cabs2(Y0), acc[0 * FP + k]);
+        acc[1 * FP + k] = fmaf(ms, cabs2(Y1), acc[1 * FP + k]);
+        acc[2 * FP + k] = fmaf(ms, c01.x, acc[2 * FP + k]);
+        acc[3 * FP + k] = fmaf(ms, c01.y, acc[3 * FP + k]);
+        acc[4 * FP + k] += m;
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  float* dst = part + ((int64_t)b * chunks + chunk) * 5 * FP;
+  for (int i = threadIdx.x; i < 5 * FP; i += WARPS * 32) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) s += s_acc[(size_t)w * 5 * FP + i];  // fixed order: bit-stable reruns
+    dst[i] = s;
+  }
+}
+
+// Sum the chunk partials (float64), normalise: R = sum / (sum m + norm_eps).
+__global__ void k_cov_finalize(const float* __restrict__ part, int B, int F, int FP, int chunks, float norm_eps,
+                               float4* __restrict__ R, float* __restrict__ msum) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * F) return;
+  const int b = idx / F, k = idx - b * F;
+  double s[5] = {0, 0, 0, 0, 0};
+  for (int c = 0; c < chunks; ++c) {
+    const float* p = part + ((int64_t)b * chunks + c) * 5 * FP;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) s[j] += (double)p[j * FP + k];
+  }
+  const double inv = 1.0 / (s[4] + (double)norm_eps);
+  R[idx] = make_float4((float)(s[0] * inv), (float)(s[1] * inv), (float)(s[2] * inv), (float)(s[3] * inv));
+  msum[idx] = (float)s[4];
+}
+
+// ------------------------------------------------------------------------------------------
+// pass B / iSTFT: synthesis with deterministic overlap-add
+// ------------------------------------------------------------------------------------------
+enum { SRC_SPEC = 0, SRC_MIX = 1 };
+enum { GAIN_NONE = 0, GAIN_BITS = 1, GAIN_FLOOR = 2, GAIN_MASK = 3 };
+
+template <int N, int SRC>
+__global__ void __launch_bounds__(Geo<N>::WARPS * 32)
+k_synth(const float* __restrict__ mix, const float2* __restrict__ spec, const float2* __restrict__ w,
+        const uint32_t* __restrict__ ibm_bits, const float* __restrict__ mask, int gain_mode, float post_floor,
+        int64_t L, int T, int hop, int blocks_per_chunk, float* __restrict__ out, float* __restrict__ peak,
+        Tables tb) {
+  constexpr int WARPS = Geo<N>::WARPS;
+  constexpr int F = Geo<N>::F;
+  constexpr int FW = Geo<N>::FW;
+  constexpr int RING = WARPS + 8;  // >= WARPS + R - 1 for every supported overlap factor R <= 8
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* s_tw = reinterpret_cast<float2*>(smem_raw);
+  float* s_win = reinterpret_cast<float*>(s_tw + N);
+  float2* bufs = reinterpret_cast<float2*>(s_win + N);
+  float* s_ring = reinterpret_cast<float*>(bufs + (size_t)WARPS * 2 * N);  // [RING][N] windowed frames
+  float2* s_a = reinterpret_cast<float2*>(s_ring + (size_t)RING * N);      // [F] beamform coefficients
+  float2* s_b = s_a + F;
+  __shared__ float s_peak[WARPS];
+
+  const int R = N / hop;
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < N; i += WARPS * 32) {
+    s_tw[i] = tb.tw[i];
+    s_win[i] = tb.win[i];
+  }
+  if (SRC == SRC_MIX) {
+    // S[k] = conj(w0) Y0 + conj(w1) Y1 with Y0 = (Z[k] + conj Z[N-k])/2, Y1 = -i (Z[k] - conj Z[N-k])/2
+    //      = a[k] Z[k] + b[k] conj(Z[N-k]),  a = (conj w0 - i conj w1)/2,  b = (conj w0 + i conj w1)/2
+    for (int k = threadIdx.x; k < F; k += WARPS * 32) {
+      const float2 w0 = w[((int64_t)b * F + k) * 2 + 0];
+      const float2 w1 = w[((int64_t)b * F + k) * 2 + 1];
+      // conj w0 = (w0.x, -w0.y);  i conj w1 = (w1.y, w1.x)
+      s_a[k] = make_float2(0.5f * (w0.x - w1.y), 0.5f * (-w0.y - w1.x));
+      s_b[k] = make_float2(0.5f * (w0.x + w1.y), 0.5f * (-w0.y + w1.x));
+    }
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float2* b0 = bufs + (size_t)warp * 2 * N;
+  float2* b1 = b0 + N;
+  const float* m0 = (SRC == SRC_MIX) ? mix + (int64_t)b * 2 * L : nullptr;
+  const float* m1 = (SRC == SRC_MIX) ? m0 + L : nullptr;
+  const float2* Sb = (SRC == SRC_SPEC) ? spec + (int64_t)b * F * (int64_t)T : nullptr;
+
+  // Output hop-blocks in extended (untrimmed) coordinates: block g covers [g*hop, (g+1)*hop); the trimmed
+  // output is blocks [R/2, R/2 + T - 1).  Block g sums frames t in [g-R+1, g] intersected with [0, T-1].
+  const int g_lo = R / 2, g_hi = R / 2 + T - 1;
+  const int g0 = g_lo + blockIdx.x * blocks_per_chunk;
+  const int g1 = min(g_hi, g0 + blocks_per_chunk);
+  const int64_t out_len = (int64_t)(T - 1) * hop;
+  float* ob = out + (int64_t)b * out_len;
+  float my_peak = 0.f;
+  const int t_first = max(0, g0 - R + 1);
+
+  for (int tile = t_first; tile < g1; tile += WARPS) {
+    const int t = tile + warp;
+    if (t < T && t < g1) {
+      float2* g;  // spectrum to invert, Hermitian-filled
+      if (SRC == SRC_MIX) {
+        load_frame_pair<N>(b0, m0, m1, L, (int64_t)t * hop - N / 2, s_win, 2.0f / N, lane);
+        __syncwarp();
+        float2* z = warp_fft_smem<N, false>(b0, b1, s_tw, lane);
+        g = (z == b0) ? b1 : b0;
+        for (int k = lane; k <= N / 2; k += kWarp) {
+          const float2 zk = z[k], zm = z[(N - k) & (N - 1)];
+          float2 s = cadd(cmul(s_a[k], zk), cmulc(s_b[k], zm));
+          float gain = 1.f;
+          if (gain_mode == GAIN_BITS) {
+            const uint32_t word = __ldg(ibm_bits + ((int64_t)b * T + t) * FW + (k >> 5));
+            gain = ((word >> (k & 31)) & 1u) ? 0.f : 1.f;  // 1 - noise mask
+          } else if (gain_mode == GAIN_FLOOR) {
+            gain = fmaxf(__ldg(mask + ((int64_t)b * F + k) * T + t), post_floor);
+          } else if (gain_mode == GAIN_MASK) {
+            gain = __ldg(mask + ((int64_t)b * F + k) * T + t);
+          }
+          s.x *= gain;
+          s.y *= gain;
+          if (k == 0 || k == N / 2) {
+            g[k] = make_float2(s.x, 0.f);  // c2r transforms ignore Im(DC), Im(Nyquist)
+          } else {
+            g[k] = s;
+            g[N - k] = make_float2(s.x, -s.y);
+          }
+        }
+        __syncwarp();
+        float2* other = (g == b0) ? b1 : b0;
+        const float2* xr = warp_fft_smem<N, true>(g, other, s_tw, lane);
+        float* slot = s_ring + (size_t)(t % RING) * N;
+        for (int n = lane; n < N; n += kWarp) slot[n] = xr[n].x * 0.5f * s_win[n];  // irfft * sum(w) = 0.5 * sum
+      } else {
+        for (int k = lane; k <= N / 2; k += kWarp) {
+          const float2 s = __ldg(Sb + (int64_t)k * T + t);
+          if (k == 0 || k == N / 2) {
+            b0[k] = make_float2(s.x, 0.f);
+          } else {
+            b0[k] = s;
+            b0[N - k] = make_float2(s.x, -s.y);
+          }
+        }
+        __syncwarp();
+        const float2* xr = warp_fft_smem<N, true>(b0, b1, s_tw, lane);
+        float* slot = s_ring + (size_t)(t % RING) * N;
+        for (int n = lane; n < N; n += kWarp) slot[n] = xr[n].x * 0.5f * s_win[n];
+      }
+    }
+    __syncthreads();
+    // emit the blocks completed by this tile
+    const int e0 = max(g0, tile);
+    const int e1 = min(g1, tile + WARPS);
+    for (int idx = threadIdx.x; idx < (e1 - e0) * hop; idx += WARPS * 32) {
+      const int gi = idx / hop, p = idx - gi * hop;
+      const int gblk = e0 + gi;
+      float acc = 0.f, nrm = 0.f;
+      for (int q = R - 1; q >= 0; --q) {  // ascending frame index, like the reference's loop
+        const int tq = gblk - q;
+        if (tq >= 0 && tq < T) {
+          const float wv = s_win[q * hop + p];
+          acc += s_ring[(size_t)(tq % RING) * N + q * hop + p];
+          nrm = fmaf(wv, wv, nrm);
+        }
+      }
+      const float v = acc / (nrm > 1e-10f ? nrm : 1.0f);
+      ob[(int64_t)(gblk - g_lo) * hop + p] = v;
+      my_peak = fmaxf(my_peak, fabsf(v));
+    }
+    __syncthreads();
+  }
+  if (peak != nullptr) {
+    my_peak = warp_max(my_peak);
+    if (lane == 0) s_peak[warp] = my_peak;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float m = 0.f;
+      for (int i = 0; i < WARPS; ++i) m = fmaxf(m, s_peak[i]);
+      // non-negative floats order like their bit patterns; max is order-independent -> deterministic
+      atomicMax(reinterpret_cast<unsigned int*>(peak + b), __float_as_uint(m));
+    }
+  }
+}
+
+__global__ void k_peak_normalise(float* __restrict__ x, int64_t n, const float* __restrict__ peak, float peak_eps) {
+  const int b = blockIdx.y;
+  const float inv = 1.0f / (peak[b] + peak_eps);
+  float* xb = x + (int64_t)b * n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    xb[i] *= inv;
+}
+
+// ------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------
+template <int N>
+static size_t smem_base() {
+  return (size_t)N * sizeof(float2) + (size_t)N * sizeof(float) + (size_t)Geo<N>::WARPS * 2 * N * sizeof(float2);
+}
+
+template <int N>
+static int launch_stft(const float* x, int B, int C, int64_t L, int hop, float* Y, cudaStream_t st) {
+  Tables tb;
+  int rc = tables_for(N, &tb);
+  if (rc) return rc;
+  const int T = (int)avz_num_frames(L, N, hop);
+  const size_t smem = smem_base<N>();
+  AVZ_CUDA_OK(cudaFuncSetAttribute(k_stft<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int fpb = Geo<N>::WARPS * 4;
+  dim3 grid((T + fpb - 1) / fpb, (C + 1) / 2, B);
+  k_stft<N><<<grid, Geo<N>::WARPS * 32, smem, st>>>(x, C, L, T, hop, reinterpret_cast<float2*>(Y), tb, fpb);
+  AVZ_LAUNCH_OK("k_stft");
+  return AVZ_OK;
+}
+
+template <int N>
+static int launch_wave_features(const float* mix, int B, int64_t L, int hop, int mode, float* X, cudaStream_t st) {
+  Tables tb;
+  int rc = tables_for(N, &tb);
+  if (rc) return rc;
+  const int T = (int)avz_num_frames(L, N, hop);
+  const size_t smem = smem_base<N>();
+  AVZ_CUDA_OK(cudaFuncSetAttribute(k_wave_features<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int fpb = Geo<N>::WARPS * 4;
+  dim3 grid((T + fpb - 1) / fpb, B);
+  k_wave_features<N><<<grid, Geo<N>::WARPS * 32, smem, st>>>(mix, L, T, hop, mode, X, tb, fpb);
+  AVZ_LAUNCH_OK("k_wave_features");
+  return AVZ_OK;
+}
+
+template <int N, int MODE>
+static int launch_cov(const float* mix, const float* tgt, const float* itf, const float* mask, int B, int64_t L,
+                      int hop, float sqrt_eps, float norm_eps, uint32_t* ibm_bits, float* R, float* msum, void* ws,
+                      cudaStream_t st) {
+  Tables tb;
+  int rc = tables_for(N, &tb);
+  if (rc) return rc;
+  const int T = (int)avz_num_frames(L, N, hop);
+  const int chunks = cov_chunks(B, T, Geo<N>::WARPS, num_sms());
+  const int fpc = (T + chunks - 1) / chunks;
+  const size_t smem = smem_base<N>() + (size_t)Geo<N>::WARPS * 5 * Geo<N>::FP * sizeof(float);
+  AVZ_CUDA_OK(cudaFuncSetAttribute(k_cov<N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(chunks, B);
+  k_cov<N, MODE><<<grid, Geo<N>::WARPS * 32, smem, st>>>(mix, tgt, itf, mask, L, T, hop, fpc, sqrt_eps, ibm_bits,
+                                                         (float*)ws, tb);
+  AVZ_LAUNCH_OK("k_cov");
+  const int F = Geo<N>::F;
+  k_cov_finalize<<<(B * F + 255) / 256, 256, 0, st>>>((const float*)ws, B, F, Geo<N>::FP, chunks, norm_eps,
+                                                      reinterpret_cast<float4*>(R), msum);
+  AVZ_LAUNCH_OK("k_cov_finalize");
+  return AVZ_OK;
+}
+
+template <int N, int SRC>
+static int launch_synth(const float* mix, const float* spec, const float* w, const uint32_t* ibm_bits,
+                        const float* mask, int gain_mode, float post_floor, int B, int64_t L, int T, int hop,
+                        float* out, float* peak, cudaStream_t st) {
+  Tables tb;
+  int rc = tables_for(N, &tb);
+  if (rc) return rc;
+  constexpr int WARPS = Geo<N>::WARPS;
+  const int n_blocks = T - 1;  // output hop-blocks per utterance
+  if (n_blocks <= 0) return AVZ_OK;
+  int chunks = cov_chunks(B, n_blocks, WARPS, num_sms());
+  const int bpc = (n_blocks + chunks - 1) / chunks;
+  chunks = (n_blocks + bpc - 1) / bpc;
+  const size_t smem = smem_base<N>() + (size_t)(WARPS + 8) * N * sizeof(float) + 2 * (size_t)Geo<N>::F * sizeof(float2);
+  AVZ_CUDA_OK(cudaFuncSetAttribute(k_synth<N, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(chunks, B);
+  k_synth<N, SRC><<<grid, WARPS * 32, smem, st>>>(mix, reinterpret_cast<const float2*>(spec),
+                                                  reinterpret_cast<const float2*>(w), ibm_bits, mask, gain_mode,
+                                                  post_floor, L, T, hop, bpc, out, peak, tb);
+  AVZ_LAUNCH_OK("k_synth");
+  return AVZ_OK;
+}
+
+#define AVZ_DISPATCH_N(n_fft, CALL)                                      \
+  switch (n_fft) {                                                       \
+    case 256: { constexpr int N_ = 256; return CALL; }                   \
+    case 512: { constexpr int N_ = 512; return CALL; }                   \
+    case 1024: { constexpr int N_ = 1024; return CALL; }                 \
+    default: return avz::set_error(AVZ_EINVAL, "n_fft=%d unsupported", n_fft); \
+  }
+
+}  // namespace avz
+
+using namespace avz;
+
+extern "C" {
+
+int avz_stft_f32(const float* x, int B, int C, int64_t L, int n_fft, int hop, float* Y, void* stream) {
+  if (!x || !Y || B <= 0 || C <= 0) return set_error(AVZ_EINVAL, "avz_stft_f32: null pointer or empty batch");
+  int rc = check_fft_args(n_fft, hop, L);
+  if (rc) return rc;
+  AVZ_DISPATCH_N(n_fft, (launch_stft<N_>(x, B, C, L, hop, Y, (cudaStream_t)stream)));
+}
+
+int avz_istft_f32(const float* S, int B, int T, int n_fft, int hop, float* x, float* peak, void* stream) {
+  if (!S || !x || B <= 0 || T < 2) return set_error(AVZ_EINVAL, "avz_istft_f32: null pointer, empty batch or T < 2");
+  int rc = check_fft_args(n_fft, hop, n_fft);
+  if (rc) return rc;
+  AVZ_DISPATCH_N(n_fft, (launch_synth<N_, SRC_SPEC>(nullptr, S, nullptr, nullptr, nullptr, GAIN_NONE, 0.f, B, 0, T, hop,
+                                                    x, peak, (cudaStream_t)stream)));
+}
+
+int avz_peak_normalise_f32(float* x, int B, int64_t n, const float* peak, float peak_eps, void* stream) {
+  if (!x || !peak || B <= 0 || n <= 0) return set_error(AVZ_EINVAL, "avz_peak_normalise_f32: bad argument");
+  int gx = (int)((n + 1023) / 1024);
+  if (gx > 64) gx = 64;
+  k_peak_normalise<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(x, n, peak, peak_eps);
+  AVZ_LAUNCH_OK("k_peak_normalise");
+  return AVZ_OK;
+}
+
+int avz_wave_features_f32(const float* mix, int B, int64_t L, int n_fft, int hop, int mode, float* X, void* stream) {
+  if (!mix || !X || B <= 0 || mode < 0 || mode > 2) return set_error(AVZ_EINVAL, "avz_wave_features_f32: bad argument");
+  int rc = check_fft_args(n_fft, hop, L);
+  if (rc) return rc;
+  AVZ_DISPATCH_N(n_fft, (launch_wave_features<N_>(mix, B, L, hop, mode, X, (cudaStream_t)stream)));
+}
+
+int64_t avz_ibm_cov_ws_bytes(int B, int64_t L, int n_fft, int hop) {
+  if (B <= 0 || check_fft_args(n_fft, hop, L)) return -1;
+  const int T = (int)avz_num_frames(L, n_fft, hop);
+  const int warps = (n_fft <= 512) ? 8 : 4;
+  const int chunks = cov_chunks(B, T, warps, num_sms());
+  const int FP = ((n_fft / 2 + 1) + 31) / 32 * 32;
+  return (int64_t)B * chunks * 5 * FP * (int64_t)sizeof(float);
+}
+
+int avz_ibm_cov_f32(const float* mix, const float* tgt, const float* itf, int B, int64_t L, int n_fft, int hop,
+                    float norm_eps, uint32_t* ibm_bits, float* R, float* msum, void* ws, void* stream) {
+  if (!mix || !tgt || !itf || !ibm_bits || !R || !msum || !ws || B <= 0)
+    return set_error(AVZ_EINVAL, "avz_ibm_cov_f32: null pointer or empty batch");
+  int rc = check_fft_args(n_fft, hop, L);
+  if (rc) return rc;
+  AVZ_DISPATCH_N(n_fft, (launch_cov<N_, COV_IBM>(mix, tgt, itf, nullptr, B, L, hop, 0.f, norm_eps, ibm_bits, R, msum,
+                                                 ws, (cudaStream_t)stream)));
+}
+
+int avz_wave_mask_cov_f32(const float* mix, const float* mask, int B, int64_t L, int n_fft, int hop, float sqrt_eps,
+                          float norm_eps, float* R, float* msum, void* ws, void* stream) {
+  if (!mix || !mask || !R || !msum || !ws || B <= 0)
+    return set_error(AVZ_EINVAL, "avz_wave_mask_cov_f32: null pointer or empty batch");
+  int rc = check_fft_args(n_fft, hop, L);
+  if (rc) return rc;
+  AVZ_DISPATCH_N(n_fft, (launch_cov<N_, COV_MASK>(mix, nullptr, nullptr, mask, B, L, hop, sqrt_eps, norm_eps, nullptr,
+                                                  R, msum, ws, (cudaStream_t)stream)));
+}
+
+int avz_mvdr_apply_f32(const float* mix, const float* w, const uint32_t* ibm_bits, const float* mask, int B, int64_t L,
+                       int n_fft, int hop, const AvzMvdrCfg* cfg, float* out, float* peak, void* stream) {
+  if (!mix || !w || !cfg || !out || B <= 0) return set_error(AVZ_EINVAL, "avz_mvdr_apply_f32: null pointer or empty batch");
+  int rc = check_fft_args(n_fft, hop, L);
+  if (rc) return rc;
+  int gain = GAIN_NONE;
+  switch (cfg->post_mode) {
+    case AVZ_POST_NONE: gain = GAIN_NONE; break;
+    case AVZ_POST_ONE_MINUS_NOISE:
+      if (!ibm_bits) return set_error(AVZ_EINVAL, "AVZ_POST_ONE_MINUS_NOISE needs ibm_bits");
+      gain = GAIN_BITS;
+      break;
+    case AVZ_POST_FLOOR:
+    case AVZ_POST_MASK:
+      if (!mask) return set_error(AVZ_EINVAL, "AVZ_POST_FLOOR / AVZ_POST_MASK need a float mask");
+      gain = cfg->post_mode == AVZ_POST_FLOOR ? GAIN_FLOOR : GAIN_MASK;
+      break;
+    default: return set_error(AVZ_EINVAL, "post_mode=%d unknown", cfg->post_mode);
+  }
+  const int T = (int)avz_num_frames(L, n_fft, hop);
+  AVZ_DISPATCH_N(n_fft, (launch_synth<N_, SRC_MIX>(mix, nullptr, w, ibm_bits, mask, gain, cfg->post_floor, B, L, T, hop,
+                                                   out, peak, (cudaStream_t)stream)));
+}
+
+}  // extern "C"

@@ -1,0 +1,379 @@
+"""Tensor-level wrappers over the C ABI (include/avzoom.h).
+
+Every function takes CUDA `torch.Tensor`s (or numpy arrays, which are copied to the current CUDA device
+and whose results are copied back - the reference's calling convention) and launches hand-written
+sm_100a kernels on torch's current stream.  PyTorch is used only for device memory and streams.
+Shapes follow the reference: spectra `(..., M, F, T)`, masks `(..., F, T)`; any leading dimensions are
+the batch.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import MvdrConfig, PRESETS
+
+__all__ = [
+    "num_frames", "stft", "istft", "ibm", "ibm_target_label", "geometric_mask", "masked_covariance",
+    "steering_vectors", "mvdr_weights", "beamform", "logmag_ipd", "physics_features", "sir_scores",
+    "ibm_covariance", "wave_masked_covariance", "mvdr_apply", "peak_normalise", "unpack_ibm",
+    "oracle_mask_mvdr", "learned_mask_mvdr", "covariance_to_matrix",
+]
+
+
+# ------------------------------------------------------------------------------------------ helpers
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+class _Io:
+    """Remembers whether the caller handed numpy (-> give numpy back) and moves data to the GPU."""
+
+    def __init__(self):
+        self.numpy = False
+
+    def take(self, x, dtype) -> torch.Tensor:
+        if isinstance(x, np.ndarray):
+            self.numpy = True
+            x = torch.from_numpy(np.ascontiguousarray(x))
+        if not isinstance(x, torch.Tensor):
+            x = torch.as_tensor(x)
+        if not x.is_cuda:
+            if not torch.cuda.is_available():
+                raise _lib.AvzError("avzoom needs a CUDA device (sm_100a); there is no CPU fallback")
+            x = x.cuda(non_blocking=True)
+        if x.dtype != dtype:
+            x = x.to(dtype)
+        return x.contiguous()
+
+    def give(self, t: torch.Tensor):
+        return t.cpu().numpy() if self.numpy else t
+
+
+def num_frames(length: int, n_fft: int, hop: int) -> int:
+    """Frame count of scipy.signal.stft(boundary='zeros', padded=True): ceil(L/hop) + 1 when hop | n_fft."""
+    return int(_lib.load().avz_num_frames(int(length), int(n_fft), int(hop)))
+
+
+def _as_real_view(z: torch.Tensor) -> torch.Tensor:
+    return torch.view_as_real(z)
+
+
+# ------------------------------------------------------------------------------------------ STFT / iSTFT
+def stft(x, n_fft: int = 512, hop: int = 128):
+    """scipy.signal.stft(x, fs, nperseg=n_fft, noverlap=n_fft-hop)[2] (oracle_debug.py:42-44).
+    x (..., L) float32 -> (..., F, T) complex64.  Pairs of rows along the second-to-last axis share one
+    complex transform."""
+    io = _Io()
+    x = io.take(x, torch.float32)
+    lead = x.shape[:-1]
+    L = x.shape[-1]
+    if x.dim() == 1:
+        B, Cn = 1, 1
+    else:
+        Cn = x.shape[-2]
+        B = int(np.prod(x.shape[:-2])) if x.dim() > 2 else 1
+    F, T = n_fft // 2 + 1, num_frames(L, n_fft, hop)
+    Y = torch.empty((B, Cn, F, T), dtype=torch.complex64, device=x.device)
+    lib = _lib.load()
+    _lib.check(lib.avz_stft_f32(_ptr(x), B, Cn, L, n_fft, hop, _ptr(Y), _stream()), "avz_stft_f32")
+    return io.give(Y.reshape(*lead, F, T))
+
+
+def istft(S, n_fft: int = 512, hop: int = 128, return_peak: bool = False):
+    """scipy.signal.istft(S, fs, nperseg=n_fft, noverlap=n_fft-hop)[1] (oracle_debug.py:93).
+    S (..., F, T) complex64 -> (..., (T-1)*hop) float32."""
+    io = _Io()
+    S = io.take(S, torch.complex64)
+    F, T = S.shape[-2], S.shape[-1]
+    if F != n_fft // 2 + 1:
+        raise ValueError(f"spectrum has {F} bins, n_fft={n_fft} needs {n_fft // 2 + 1}")
+    lead = S.shape[:-2]
+    B = int(np.prod(lead)) if lead else 1
+    out = torch.empty((B, (T - 1) * hop), dtype=torch.float32, device=S.device)
+    peak = torch.zeros((B,), dtype=torch.float32, device=S.device) if return_peak else None
+    lib = _lib.load()
+    _lib.check(lib.avz_istft_f32(_ptr(S), B, T, n_fft, hop, _ptr(out), _ptr(peak), _stream()), "avz_istft_f32")
+    out = out.reshape(*lead, (T - 1) * hop)
+    if return_peak:
+        return io.give(out), io.give(peak.reshape(lead))
+    return io.give(out)
+
+
+def peak_normalise(x: torch.Tensor, peak: torch.Tensor, peak_eps: float) -> torch.Tensor:
+    """In place x[b] /= (peak[b] + peak_eps)  (oracle_debug.py:94)."""
+    B, n = x.shape
+    _lib.check(_lib.load().avz_peak_normalise_f32(_ptr(x), B, n, _ptr(peak), float(peak_eps), _stream()),
+               "avz_peak_normalise_f32")
+    return x
+
+
+# ------------------------------------------------------------------------------------------ masks
+def _mag_greater(a, b):
+    io = _Io()
+    a = io.take(a, torch.complex64)
+    b = io.take(b, torch.complex64)
+    if a.shape != b.shape:
+        raise ValueError("spectra differ in shape")
+    out = torch.empty(a.shape, dtype=torch.float32, device=a.device)
+    _lib.check(_lib.load().avz_mag_greater_f32(_ptr(a), _ptr(b), a.numel(), _ptr(out), _stream()), "avz_mag_greater_f32")
+    return io.give(out)
+
+
+def ibm(S_tgt, S_int):
+    """Noise-polarity Ideal Binary Mask: where(|S_int| > |S_tgt|, 1, 0)  (oracle_debug.py:49-53)."""
+    return _mag_greater(S_int, S_tgt)
+
+
+def ibm_target_label(S_tgt, S_int):
+    """Training-label polarity: (|S_t| > |S_i|) as float  (model_training.py:90)."""
+    return _mag_greater(S_tgt, S_int)
+
+
+def geometric_mask(Y):
+    """compute_hard_geometric_mask (masked_mvdr.py:37-46).  Y (..., 2, F, T) -> (..., F, T) in {0.01, 1}."""
+    io = _Io()
+    Y = io.take(Y, torch.complex64)
+    F, T = Y.shape[-2], Y.shape[-1]
+    lead = Y.shape[:-3]
+    B = int(np.prod(lead)) if lead else 1
+    out = torch.empty((B, F, T), dtype=torch.float32, device=Y.device)
+    _lib.check(_lib.load().avz_geometric_mask_f32(_ptr(Y), B, F, T, _ptr(out), _stream()), "avz_geometric_mask_f32")
+    return io.give(out.reshape(*lead, F, T))
+
+
+def unpack_ibm(bits: torch.Tensor, F: int) -> torch.Tensor:
+    """ibm_bits [B, T, ceil(F/32)] int32 -> float mask [B, F, T]."""
+    B, T, _ = bits.shape
+    out = torch.empty((B, F, T), dtype=torch.float32, device=bits.device)
+    _lib.check(_lib.load().avz_ibm_unpack_f32(_ptr(bits), B, F, T, _ptr(out), _stream()), "avz_ibm_unpack_f32")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ covariance / weights
+def covariance_to_matrix(Rp: torch.Tensor) -> torch.Tensor:
+    """Packed (..., F, 4) = (R00, R11, Re R01, Im R01) -> Hermitian (..., F, 2, 2) complex64."""
+    r01 = torch.complex(Rp[..., 2], Rp[..., 3])
+    z = torch.zeros_like(Rp[..., 0])
+    row0 = torch.stack([torch.complex(Rp[..., 0], z), r01], dim=-1)
+    row1 = torch.stack([r01.conj(), torch.complex(Rp[..., 1], z)], dim=-1)
+    return torch.stack([row0, row1], dim=-2)
+
+
+def _pack_covariance(R: torch.Tensor) -> torch.Tensor:
+    if R.shape[-1] == 4 and not R.is_complex():
+        return R.to(torch.float32).contiguous()
+    R = R.to(torch.complex64)
+    return torch.stack([R[..., 0, 0].real, R[..., 1, 1].real, R[..., 0, 1].real, R[..., 0, 1].imag], dim=-1).contiguous()
+
+
+def masked_covariance(Y, noise_w, sqrt_eps: float = 0.0, norm_eps: float = 1e-6, packed: bool = False):
+    """R[f] = sum_t (m + sqrt_eps) y y^H / (sum_t m + norm_eps)  (oracle_debug.py:56-64).
+    Y (..., 2, F, T), noise_w (..., F, T) -> (..., F, 2, 2) complex64."""
+    io = _Io()
+    Y = io.take(Y, torch.complex64)
+    m = io.take(noise_w, torch.float32)
+    F, T = Y.shape[-2], Y.shape[-1]
+    lead = Y.shape[:-3]
+    B = int(np.prod(lead)) if lead else 1
+    Rp = torch.empty((B, F, 4), dtype=torch.float32, device=Y.device)
+    ms = torch.empty((B, F), dtype=torch.float32, device=Y.device)
+    _lib.check(_lib.load().avz_spec_mask_cov_f32(_ptr(Y), _ptr(m), B, F, T, float(sqrt_eps), float(norm_eps), _ptr(Rp),
+                                                 _ptr(ms), _stream()), "avz_spec_mask_cov_f32")
+    Rp = Rp.reshape(*lead, F, 4)
+    return io.give(Rp if packed else covariance_to_matrix(Rp))
+
+
+_SV_CACHE = {}
+
+
+def steering_vectors(cfg: MvdrConfig, device=None, f_bins=None) -> torch.Tensor:
+    """get_steering_vector for every bin (masked_mvdr.py:22-35), float64 on the host, (F, 2) complex64."""
+    key = (cfg.angle_deg, cfg.mic_dist, cfg.c, cfg.fs, cfg.n_fft, str(device), None if f_bins is None else tuple(f_bins))
+    if key not in _SV_CACHE:
+        f = cfg.freqs() if f_bins is None else np.asarray(f_bins, dtype=np.float64)
+        th = np.deg2rad(cfg.angle_deg)
+        tau1 = (cfg.mic_dist / 2) * np.cos(0.0) * np.cos(th - 0) / cfg.c
+        tau2 = (cfg.mic_dist / 2) * np.cos(0.0) * np.cos(th - np.pi) / cfg.c
+        om = 2 * np.pi * f
+        d = np.stack([np.exp(-1j * om * tau1), np.exp(-1j * om * tau2)], axis=1).astype(np.complex64)
+        _SV_CACHE[key] = torch.from_numpy(d).to(device if device is not None else "cuda")
+    return _SV_CACHE[key]
+
+
+def mvdr_weights(R, d, cfg: MvdrConfig = PRESETS["baseline_oracle"]):
+    """w = u / (d^H u + w_eps), u = solve(R + sigma I, d)  (oracle_debug.py:68-79), closed form in float64.
+    R (..., F, 2, 2) complex or packed (..., F, 4); d (F, 2) or (F, 2, 1) -> w (..., F, 2) complex64.
+    Bins below cfg.hp_hz get w = 0 ('zero') or [1, 0] ('mic0')."""
+    io = _Io()
+    if isinstance(R, np.ndarray):
+        r_dtype = torch.complex64 if np.iscomplexobj(R) else torch.float32
+    else:
+        r_dtype = torch.complex64 if R.is_complex() else torch.float32
+    R = io.take(R, r_dtype)
+    Rp = _pack_covariance(R)
+    d = io.take(d, torch.complex64).reshape(-1, 2).contiguous()
+    F = Rp.shape[-2]
+    lead = Rp.shape[:-2]
+    B = int(np.prod(lead)) if lead else 1
+    w = torch.empty((B, F, 2), dtype=torch.complex64, device=Rp.device)
+    cc = cfg.to_c()
+    _lib.check(_lib.load().avz_mvdr_weights_f32(_ptr(Rp), _ptr(d), B, F, C.byref(cc), _ptr(w), _stream()),
+               "avz_mvdr_weights_f32")
+    return io.give(w.reshape(*lead, F, 2))
+
+
+def beamform(w, Y):
+    """S[f,t] = w[f]^H Y[:,f,t]  (oracle_debug.py:80).  w (..., F, 2), Y (..., 2, F, T) -> (..., F, T)."""
+    io = _Io()
+    w = io.take(w, torch.complex64)
+    Y = io.take(Y, torch.complex64)
+    F, T = Y.shape[-2], Y.shape[-1]
+    lead = Y.shape[:-3]
+    B = int(np.prod(lead)) if lead else 1
+    S = torch.empty((B, F, T), dtype=torch.complex64, device=Y.device)
+    _lib.check(_lib.load().avz_beamform_f32(_ptr(w), _ptr(Y), B, F, T, _ptr(S), _stream()), "avz_beamform_f32")
+    return io.give(S.reshape(*lead, F, T))
+
+
+# ------------------------------------------------------------------------------------------ features / scores
+def _features(Y, mode: int):
+    io = _Io()
+    Y = io.take(Y, torch.complex64)
+    F, T = Y.shape[-2], Y.shape[-1]
+    lead = Y.shape[:-3]
+    B = int(np.prod(lead)) if lead else 1
+    if mode == _lib.FEAT_PHYSICS_NHWC:
+        X = torch.empty((B, F, T, 4), dtype=torch.float32, device=Y.device)
+        shape = (*lead, F, T, 4)
+    else:
+        X = torch.empty((B, 2, F, T), dtype=torch.float32, device=Y.device)
+        shape = (*lead, 2, F, T)
+    _lib.check(_lib.load().avz_features_f32(_ptr(Y), B, F, T, mode, _ptr(X), _stream()), "avz_features_f32")
+    return io.give(X.reshape(shape))
+
+
+def logmag_ipd(Y, wrapped: bool = False):
+    """stack[ln(|Y0| + 1e-7), angle(Y0) - angle(Y1)]  (full_audio.../inference.py:91-94) -> (..., 2, F, T) f32."""
+    return _features(Y, _lib.FEAT_LOGMAG_IPD_WRAPPED if wrapped else _lib.FEAT_LOGMAG_IPD)
+
+
+def physics_features(Y):
+    """[logmag, sin ipd, cos ipd, k/(F-1)] NHWC  (Final_pipeline/src/inference.py:117-128) -> (..., F, T, 4)."""
+    return _features(Y, _lib.FEAT_PHYSICS_NHWC)
+
+
+def sir_scores(est, tgt, itf):
+    """Projection scores per utterance -> (..., 4) float32 = (OSINR, OSIR, SDR, SIR) dB:
+    columns 0-1 follow Final_pipeline/src/metrics.py:102-123, columns 2-3 scripts/run_metrics.py:6-36."""
+    io = _Io()
+    est = io.take(est, torch.float32)
+    tgt = io.take(tgt, torch.float32)
+    itf = io.take(itf, torch.float32)
+    lead = est.shape[:-1]
+    B = int(np.prod(lead)) if lead else 1
+    sc = torch.empty((B, 4), dtype=torch.float32, device=est.device)
+    _lib.check(_lib.load().avz_sir_f32(_ptr(est), _ptr(tgt), _ptr(itf), B, est.shape[-1], tgt.shape[-1], _ptr(sc),
+                                       _stream()), "avz_sir_f32")
+    return io.give(sc.reshape(*lead, 4))
+
+
+# ------------------------------------------------------------------------------------------ fused passes
+def ibm_covariance(mix: torch.Tensor, tgt: torch.Tensor, itf: torch.Tensor, cfg: MvdrConfig):
+    """Pass A (oracle_debug.py:42-64) without storing any spectrum.
+    mix [B,2,L], tgt [B,L], itf [B,L] -> (ibm_bits [B,T,ceil(F/32)] int32, R packed [B,F,4], msum [B,F])."""
+    lib = _lib.load()
+    B, _, L = mix.shape
+    F, T = cfg.n_freq, num_frames(L, cfg.n_fft, cfg.hop)
+    dev = mix.device
+    bits = torch.empty((B, T, (F + 31) // 32), dtype=torch.int32, device=dev)
+    Rp = torch.empty((B, F, 4), dtype=torch.float32, device=dev)
+    ms = torch.empty((B, F), dtype=torch.float32, device=dev)
+    nws = lib.avz_ibm_cov_ws_bytes(B, L, cfg.n_fft, cfg.hop)
+    if nws < 0:
+        _lib.check(-1, "avz_ibm_cov_ws_bytes")
+    ws = torch.empty((max(int(nws), 4),), dtype=torch.uint8, device=dev)
+    _lib.check(lib.avz_ibm_cov_f32(_ptr(mix), _ptr(tgt), _ptr(itf), B, L, cfg.n_fft, cfg.hop, float(cfg.norm_eps),
+                                   _ptr(bits), _ptr(Rp), _ptr(ms), _ptr(ws), _stream()), "avz_ibm_cov_f32")
+    return bits, Rp, ms
+
+
+def wave_masked_covariance(mix: torch.Tensor, mask: torch.Tensor, cfg: MvdrConfig):
+    """Learned-mask pass A (full_audio.../inference.py:90,102-108): mix [B,2,L], target-probability mask [B,F,T]
+    -> (R packed [B,F,4], msum [B,F]); noise weight = 1 - mask."""
+    lib = _lib.load()
+    B, _, L = mix.shape
+    F = cfg.n_freq
+    dev = mix.device
+    Rp = torch.empty((B, F, 4), dtype=torch.float32, device=dev)
+    ms = torch.empty((B, F), dtype=torch.float32, device=dev)
+    nws = lib.avz_ibm_cov_ws_bytes(B, L, cfg.n_fft, cfg.hop)
+    ws = torch.empty((max(int(nws), 4),), dtype=torch.uint8, device=dev)
+    _lib.check(lib.avz_wave_mask_cov_f32(_ptr(mix), _ptr(mask), B, L, cfg.n_fft, cfg.hop, float(cfg.sqrt_eps),
+                                         float(cfg.norm_eps), _ptr(Rp), _ptr(ms), _ptr(ws), _stream()),
+               "avz_wave_mask_cov_f32")
+    return Rp, ms
+
+
+def mvdr_apply(mix: torch.Tensor, w: torch.Tensor, cfg: MvdrConfig, ibm_bits: Optional[torch.Tensor] = None,
+               mask: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Pass B (oracle_debug.py:80-93): STFT(mix) -> w^H y -> post-filter -> iSTFT/OLA.
+    -> (out [B,(T-1)*hop] un-normalised, peak [B])."""
+    B, _, L = mix.shape
+    T = num_frames(L, cfg.n_fft, cfg.hop)
+    out = torch.empty((B, (T - 1) * cfg.hop), dtype=torch.float32, device=mix.device)
+    peak = torch.zeros((B,), dtype=torch.float32, device=mix.device)
+    cc = cfg.to_c()
+    _lib.check(_lib.load().avz_mvdr_apply_f32(_ptr(mix), _ptr(w), _ptr(ibm_bits), _ptr(mask), B, L, cfg.n_fft, cfg.hop,
+                                              C.byref(cc), _ptr(out), _ptr(peak), _stream()), "avz_mvdr_apply_f32")
+    return out, peak
+
+
+def _batchify(mix, tgt, itf, io: _Io):
+    mix = io.take(mix, torch.float32)
+    single = mix.dim() == 2
+    if single:
+        mix = mix[None]
+    tgt = None if tgt is None else io.take(tgt, torch.float32).reshape(mix.shape[0], -1)
+    itf = None if itf is None else io.take(itf, torch.float32).reshape(mix.shape[0], -1)
+    return mix.contiguous(), tgt, itf, single
+
+
+def oracle_mask_mvdr(mix, tgt, itf, cfg: MvdrConfig = PRESETS["baseline_oracle"], return_parts: bool = False):
+    """Oracle IBM mask-MVDR end to end (oracle_debug.py:42-94), fused into two passes over the waveforms.
+    mix (B,2,L) or (2,L); tgt, itf (B,L) or (L,) -> waveform (B,(T-1)*hop) float32 (peak-normalised per
+    utterance when cfg.peak_eps is not None)."""
+    io = _Io()
+    mix, tgt, itf, single = _batchify(mix, tgt, itf, io)
+    bits, Rp, ms = ibm_covariance(mix, tgt, itf, cfg)
+    w = mvdr_weights(Rp, steering_vectors(cfg, mix.device), cfg)
+    out, peak = mvdr_apply(mix, w, cfg, ibm_bits=bits if cfg.post == "one_minus_noise" else None)
+    parts = None
+    if return_parts:
+        parts = {"ibm_bits": bits, "R": Rp, "msum": ms, "w": w, "x_raw": out.clone(), "peak": peak}
+    if cfg.peak_eps is not None:
+        peak_normalise(out, peak, cfg.peak_eps)
+    res = io.give(out[0] if single else out)
+    return (res, parts) if return_parts else res
+
+
+def learned_mask_mvdr(mix, mask, cfg: MvdrConfig = PRESETS["baseline_learned"]):
+    """Learned-mask MVDR given the mask (process_chunk after the model call,
+    full_audio.../inference.py:99-117).  mix (B,2,L), mask (B,F,T) target probability -> (B,(T-1)*hop)."""
+    io = _Io()
+    mix, _, _, single = _batchify(mix, None, None, io)
+    mask = io.take(mask, torch.float32).reshape(mix.shape[0], cfg.n_freq, -1).contiguous()
+    Rp, _ = wave_masked_covariance(mix, mask, cfg)
+    w = mvdr_weights(Rp, steering_vectors(cfg, mix.device), cfg)
+    out, peak = mvdr_apply(mix, w, cfg, mask=mask if cfg.post in ("floor", "mask") else None)
+    if cfg.peak_eps is not None:
+        peak_normalise(out, peak, cfg.peak_eps)
+    return io.give(out[0] if single else out)

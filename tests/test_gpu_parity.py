@@ -1,0 +1,271 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the float64 oracle on the same inputs.
+
+Bars: IBM / mask outputs bit-exact; waveforms within 1e-4 relative L2 of the
+numpy/scipy float64 path; SIR within 0.05 dB.  Run on the B200 box with `pytest -m gpu`.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+WAVE_TOL = 1e-4   # relative L2, BASELINE.json north_star
+SIR_TOL_DB = 0.05
+
+
+@pytest.fixture(scope="module")
+def az():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import avzoom
+    avzoom._lib.load()
+    return avzoom
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.complex128 if np.iscomplexobj(a) or np.iscomplexobj(b) else np.float64)
+    b = np.asarray(b)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-300))
+
+
+def to_oracle_cfg(cfg):
+    return O.PathConfig(fs=cfg.fs, n_fft=cfg.n_fft, hop=cfg.hop, mic_dist=cfg.mic_dist, c=cfg.c, angle_deg=cfg.angle_deg,
+                        sigma=cfg.sigma, hp_hz=cfg.hp_hz, hp_mode=cfg.hp_mode, sqrt_eps=cfg.sqrt_eps,
+                        norm_eps=cfg.norm_eps, w_eps=cfg.w_eps, post=cfg.post, post_floor=cfg.post_floor,
+                        peak_eps=cfg.peak_eps)
+
+
+def synth(config_id, n_utt, dur, n_int, start=0):
+    from avzoom import synth as S
+    return S.make_batch(config_id, n_utt, dur, n_int, start=start)
+
+
+# --------------------------------------------------------------------------------------------- STFT / iSTFT
+@pytest.mark.parametrize("n_fft,hop,shape", [
+    (512, 128, (2, 80000)), (512, 256, (2, 32000)), (1024, 512, (2, 32000)), (256, 64, (1, 5001)),
+    (512, 128, (3, 2, 16000)), (512, 128, (3, 9999)), (512, 128, (700,)), (1024, 256, (2, 1024)),
+])
+def test_stft_matches_scipy(az, n_fft, hop, shape):
+    rng = np.random.default_rng(sum(shape) + n_fft)
+    x = rng.standard_normal(shape).astype(np.float32)
+    Y = az.stft(x, n_fft, hop)
+    ref = O.stft_scipy(x, n_fft, hop)
+    assert Y.shape == ref.shape and Y.dtype == np.complex64
+    assert rel_l2(Y, ref) < 1e-6
+
+
+@pytest.mark.parametrize("n_fft,hop,T", [(512, 128, 626), (512, 256, 126), (1024, 512, 64), (256, 64, 17), (512, 128, 2)])
+def test_istft_matches_scipy(az, n_fft, hop, T):
+    rng = np.random.default_rng(T)
+    F = n_fft // 2 + 1
+    S = (rng.standard_normal((2, F, T)) + 1j * rng.standard_normal((2, F, T))).astype(np.complex64)
+    x, peak = az.istft(S, n_fft, hop, return_peak=True)
+    ref = O.istft_scipy(S, n_fft, hop)
+    assert x.shape == ref.shape == (2, (T - 1) * hop)
+    assert rel_l2(x, ref) < 1e-6
+    assert np.allclose(peak, np.abs(x).max(axis=-1), rtol=0, atol=0)
+
+
+def test_stft_istft_round_trip(az):
+    rng = np.random.default_rng(5)
+    x = torch.from_numpy(rng.standard_normal((4, 2, 64000)).astype(np.float32)).cuda()
+    Y = az.stft(x, 512, 128)
+    xr = az.istft(Y, 512, 128)
+    assert xr.shape == (4, 2, 64000)
+    assert float((xr - x).norm() / x.norm()) < 1e-6
+
+
+def test_stft_edge_and_errors(az):
+    with pytest.raises(az._lib.AvzError):
+        az.stft(np.zeros((2, 100), np.float32), 512, 128)       # shorter than n_fft (scipy would shrink nperseg)
+    with pytest.raises(az._lib.AvzError):
+        az.stft(np.zeros((2, 4000), np.float32), 500, 125)      # unsupported n_fft
+    Y = az.stft(np.zeros((2, 4000), np.float32), 512, 128)      # silence -> exact zeros
+    assert not Y.any()
+
+
+# --------------------------------------------------------------------------------------------- masks
+def test_ibm_from_spectra_bit_exact(az):
+    rng = np.random.default_rng(1)
+    a = (rng.standard_normal((257, 300)) + 1j * rng.standard_normal((257, 300))).astype(np.complex64)
+    b = (rng.standard_normal((257, 300)) + 1j * rng.standard_normal((257, 300))).astype(np.complex64)
+    b[:10] = a[:10]                     # exact ties -> 0 in both polarities
+    b[10:20] = 0
+    a[15:20] = 0                        # 0 vs 0
+    b[20, :50] = a[20, :50] * np.float32(1.0000001)
+    got = az.ibm(a, b)                  # noise polarity: |S_int| > |S_tgt| with (S_tgt, S_int) = (a, b)
+    ref = O.ibm_noise_mask(a.astype(np.complex128), b.astype(np.complex128))
+    assert np.array_equal(got, ref.astype(np.float32))
+    got_t = az.ibm_target_label(a, b)
+    assert np.array_equal(got_t, O.ibm_target_label(a.astype(np.complex128), b.astype(np.complex128)))
+    assert not np.any((got == 1) & (got_t == 1))
+
+
+def test_geometric_mask_bit_exact(az, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ref_helpers.npz"))
+    got = az.geometric_mask(g["geo_Y"])
+    assert np.array_equal(got, g["geo_mask"].astype(np.float32))
+
+
+# --------------------------------------------------------------------------------------------- pieces vs oracle
+def test_masked_covariance_weights_beamform(az, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ref_helpers.npz"))
+    Y, mask, f = g["bm_Y"], g["bm_mask"], g["asv_f_bins"]
+    cfg = az.PRESETS["tf_lite"]
+    R = az.masked_covariance(Y, 1.0 - mask, sqrt_eps=1e-10, norm_eps=1e-6)
+    Rref = O.masked_covariance_vec(Y.astype(np.complex128), 1.0 - mask.astype(np.float64), 1e-10, 1e-6)
+    assert R.shape == (513, 2, 2) and rel_l2(R, Rref) < 1e-6
+    d = O.all_steering_vectors(f, 90.0, 0.04, 343.0)
+    w = az.mvdr_weights(Rref.astype(np.complex64), d.astype(np.complex64), cfg)
+    wref = O.mvdr_weights(Rref.astype(np.complex64).astype(np.complex128), d.astype(np.complex64), cfg.sigma, cfg.w_eps)
+    assert rel_l2(w, wref) < 1e-6
+    S = az.beamform(w, Y)
+    assert rel_l2(S, O.beamform(w.astype(np.complex128), Y.astype(np.complex128))) < 1e-6
+    # the reference's own batch_mvdr output (golden) through our three ops
+    w2 = az.mvdr_weights(R, d.astype(np.complex64), cfg)
+    assert rel_l2(az.beamform(w2, Y), g["bm_out"]) < 2e-5
+
+
+def test_features(az):
+    mix, _, _ = synth(3, 1, 2.0, 3)
+    Yref = O.stft_scipy(mix[0], 1024, 512)
+    Y = az.stft(mix[0], 1024, 512)
+    X = az.logmag_ipd(Y)
+    Xref = O.logmag_ipd(Yref)
+    assert X.shape == Xref.shape == (2, 513, 64)
+    assert np.max(np.abs(X[0] - Xref[0])) < 1e-3          # log of tiny magnitudes amplifies f32 STFT noise
+    d_ipd = np.abs(X[1] - Xref[1])
+    strong = np.abs(Yref).min(axis=0) > 1e-4 * np.abs(Yref).max()
+    assert np.max(d_ipd[strong]) < 1e-3
+    P = az.physics_features(Y)
+    Pref = O.physics_features(Yref, 1024)
+    assert P.shape == Pref.shape == (513, 64, 4)
+    assert np.array_equal(P[..., 3], Pref[..., 3])
+    assert np.max(np.abs(P[..., 1:3][strong] - Pref[..., 1:3][strong])) < 1e-3
+
+
+def test_sir_scores_match_reference_golden(az, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ref_helpers.npz"))
+    est, t, i = g["score_in"]
+    sc = az.sir_scores(est, t, i)
+    assert np.allclose(sc[:2], g["score_osinr_osir"], atol=1e-4, rtol=0)
+    assert np.allclose(sc[2:], g["score_sdr_sir"], atol=1e-4, rtol=0)
+
+
+# --------------------------------------------------------------------------------------------- fused oracle path
+def _check_oracle_path(az, mix, tgt, itf, cfg, wave_tol=WAVE_TOL):
+    ocfg = to_oracle_cfg(cfg)
+    out, parts = az.oracle_mask_mvdr(torch.from_numpy(mix).cuda(), torch.from_numpy(tgt).cuda(),
+                                     torch.from_numpy(itf).cuda(), cfg, return_parts=True)
+    F = cfg.n_freq
+    masks = az.unpack_ibm(parts["ibm_bits"], F).cpu().numpy()
+    out = out.cpu().numpy()
+    raw = parts["x_raw"].cpu().numpy()
+    for b in range(mix.shape[0]):
+        ref, rp = O.oracle_mask_mvdr(mix[b], tgt[b], itf[b], ocfg, return_parts=True)
+        assert np.array_equal(masks[b], rp["mask_noise"].astype(np.float32)), f"IBM differs for utterance {b}"
+        assert rel_l2(raw[b], rp["x_raw"]) < wave_tol
+        assert rel_l2(out[b], ref) < wave_tol
+        n = min(len(ref), tgt.shape[1])
+        sir_ref = O.osinr_osir(ref[:n], tgt[b, :n], itf[b, :n])[1]
+        sir_got = O.osinr_osir(out[b, :n], tgt[b, :n], itf[b, :n])[1]
+        assert abs(sir_ref - sir_got) < SIR_TOL_DB
+
+
+def test_oracle_path_config1(az):
+    """BASELINE config 1: 5 s, 1 target + 2 interferers, n_fft 512 / hop 128."""
+    mix, tgt, itf = synth(1, 2, 5.0, 2)
+    _check_oracle_path(az, mix, tgt, itf, az.PRESETS["baseline_oracle"])
+
+
+def test_oracle_path_config2_sample(az):
+    """BASELINE config 2 shape (4 s, 3 interferers), a sample of utterances checked in full."""
+    mix, tgt, itf = synth(2, 4, 4.0, 3)
+    _check_oracle_path(az, mix, tgt, itf, az.PRESETS["baseline_oracle"])
+
+
+def test_oracle_path_hop256_and_ragged(az):
+    mix, tgt, itf = synth(7, 2, 1.37, 2)      # L = 21920: not a multiple of the hop
+    _check_oracle_path(az, mix, tgt, itf, az.PRESETS["oracle_debug"])
+    _check_oracle_path(az, mix, tgt, itf, az.PRESETS["baseline_oracle"])
+
+
+def test_oracle_path_real_speech_golden(az, golden_dir):
+    """The reference's oracle_debug.main() run unmodified on a real-speech excerpt (tests/golden)."""
+    g = np.load(os.path.join(golden_dir, "ref_speech_excerpt.npz"))
+    mix = (g["mix_pcm"].astype(np.float32) / 32768.0).T[None].copy()
+    tgt = (g["tgt_pcm"].astype(np.float32) / 32768.0)[None].copy()
+    itf = (g["int_pcm"].astype(np.float32) / 32768.0)[None].copy()
+    cfg = az.PRESETS["oracle_debug"]
+    _check_oracle_path(az, mix, tgt, itf, cfg)
+    out = az.oracle_mask_mvdr(mix, tgt, itf, cfg)
+    assert rel_l2(out[0], g["oracle_debug_out_f64read"]) < WAVE_TOL
+    # silence-padded input: zero frames give an all-zero IBM row and do not poison the covariance
+    mixz = np.concatenate([mix, np.zeros_like(mix)], axis=-1)
+    tz = np.concatenate([tgt, np.zeros_like(tgt)], axis=-1)
+    iz = np.concatenate([itf, np.zeros_like(itf)], axis=-1)
+    _check_oracle_path(az, mixz, tz, iz, az.PRESETS["baseline_oracle"])
+
+
+def test_learned_mask_path_golden(az, golden_dir):
+    """process_chunk of the reference (full_audio.../inference.py:88-118) with the mask its seeded U-Net
+    produced; reference run with float32 reads."""
+    g = np.load(os.path.join(golden_dir, "ref_speech_excerpt.npz"))
+    lc = np.load(os.path.join(golden_dir, "ref_learned_chunk.npz"))
+    mix = (g["mix_pcm"].astype(np.float32) / 32768.0)[:32000].T[None].copy()
+    cfg = az.PRESETS["full_audio"]
+    out = az.learned_mask_mvdr(mix, lc["masks"][:1], cfg)
+    assert out.shape == (1, 32256)
+    ref = O.learned_mask_mvdr_chunk(mix[0].T, lambda X: lc["masks"][0], to_oracle_cfg(cfg))
+    assert rel_l2(out[0], ref) < WAVE_TOL
+    assert rel_l2(out[0], lc["chunk0_out"]) < WAVE_TOL
+
+
+def test_geometric_mask_mvdr_pieces(az, golden_dir):
+    """masked_mvdr.main's arithmetic (masked_mvdr.py:76-128) assembled from the public ops."""
+    g = np.load(os.path.join(golden_dir, "ref_speech_excerpt.npz"))
+    mix = (g["mix_pcm"].astype(np.float32) / 32768.0).T.copy()
+    cfg = az.PRESETS["masked_mvdr"]
+    Y = az.stft(torch.from_numpy(mix).cuda(), cfg.n_fft, cfg.hop)
+    Yref = O.stft_scipy(mix, cfg.n_fft, cfg.hop)
+    m = az.geometric_mask(Y)
+    mref = O.geometric_phase_mask(Yref)
+    # angle ties are decided on the float32 spectrum here and the float64 one there: only exact silences tie
+    assert np.mean(m.cpu().numpy() != mref.astype(np.float32)) < 1e-3
+    R = az.masked_covariance(Y, m, packed=True)
+    w = az.mvdr_weights(R, az.steering_vectors(cfg, Y.device), cfg)
+    x = az.istft(az.beamform(w, Y), cfg.n_fft, cfg.hop)
+    x = x / (x.abs().max() + 1e-6)
+    ref = O.geometric_mask_mvdr(mix, to_oracle_cfg(cfg))
+    # sigma = 1e-7 on a near-rank-1 covariance: the reference itself moves by ~1e-3 between f32 and f64 reads
+    assert rel_l2(x.cpu().numpy(), ref) < 5e-3
+
+
+# --------------------------------------------------------------------------------------------- full-size properties
+def test_config2_full_size_properties(az):
+    """1024 x 4 s through the fused path: shape, per-utterance peak == 1, distortionless weights, and
+    permutation equivariance (utterances are independent - the sharding invariant)."""
+    B = 1024
+    mix8, tgt8, itf8 = synth(2, 8, 4.0, 3)
+    reps = B // 8
+    mix = torch.from_numpy(np.tile(mix8, (reps, 1, 1))).cuda()
+    tgt = torch.from_numpy(np.tile(tgt8, (reps, 1))).cuda()
+    itf = torch.from_numpy(np.tile(itf8, (reps, 1))).cuda()
+    cfg = az.PRESETS["baseline_oracle"]
+    out, parts = az.oracle_mask_mvdr(mix, tgt, itf, cfg, return_parts=True)
+    assert out.shape == (B, 64000)
+    assert torch.all(out.abs().amax(dim=1) == 1.0)
+    # copies of the same utterance anywhere in the batch give bit-identical results
+    assert torch.equal(out[:8], out[-8:]) and torch.equal(out[8:16], out[:8])
+    # d^H w = 1 above the high-pass (MVDR distortionless constraint), w = 0 below it
+    d = az.steering_vectors(cfg, mix.device)
+    resp = (d.conj()[None] * parts["w"]).sum(-1)
+    hp = cfg.hp_bins()
+    assert torch.all(parts["w"][:, :hp] == 0)
+    assert float((resp[:, hp:] - 1).abs().max()) < 1e-5
+    ref = O.oracle_mask_mvdr(mix8[3], tgt8[3], itf8[3], to_oracle_cfg(cfg))
+    assert rel_l2(out[3].cpu().numpy(), ref) < WAVE_TOL
