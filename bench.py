@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""Benchmark of the mask-driven MVDR hot path (BASELINE.json metric: audio-seconds per second).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE config 2): per GPU 1024 synthetic far-field 2-mic mixtures of 4 s at 16 kHz, 1 target +
+3 interferers, oracle-IBM mask-MVDR at n_fft 512 / hop 128.  A "step" is one pass of the fused path
+(IBM + covariance -> weights -> beamform + post-filter + iSTFT -> peak normalisation) over that batch.
+Utterances are independent, so ranks shard them with no data-path collective (weak scaling); NCCL only
+all-gathers the per-utterance scores in the end-to-end leg.
+
+`value` is measured with the inputs resident in HBM; `e2e` is the same metric through the public host-buffer
+API (pinned host memory -> device every step, enhanced waveforms + scores back to the host).
+`--impl reference` times the reference's CPU algorithm (oracle port, float64, all host cores) on a bounded
+sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FS = 16000
+DUR_S = 4.0
+N_INTERF = 3
+UTT_PER_GPU = 1024
+CONFIG_ID = 2
+ALGO_BYTES_PER_SAMPLE = 20.0        # read mix 2L + tgt L + int L, write out L, float32
+METRIC = "audio-sec/sec mask-MVDR (2-mic,16kHz)"
+UNIT = "audio-s/s"
+
+
+# ------------------------------------------------------------------------------------------ CPU baseline
+def _oracle_one(seed_args):
+    import oracle as O
+    from avzoom import synth
+    mix, tgt, itf = synth.make_mixture(*seed_args)
+    t0 = time.perf_counter()
+    O.oracle_mask_mvdr(mix, tgt, itf, O.PRESETS["baseline_oracle"])
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(n_utt: int | None = None):
+    """The reference's algorithm (oracle port of rt_av_zoom/core/oracle_debug.py:42-94, float64, per-bin python
+    loops as written) over a bounded sample of the workload, one process per host core."""
+    import multiprocessing as mp
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    os.environ.setdefault("MKL_NUM_THREADS", "1")
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    cores = os.cpu_count() or 1
+    if n_utt is None:
+        n_utt = max(256, 4 * cores)
+    L = int(DUR_S * FS)
+    args = [(1_000_003 * CONFIG_ID + u, L, N_INTERF) for u in range(n_utt)]
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_oracle_one, args[:cores])            # warm the workers (imports, FFT plans)
+        t0 = time.perf_counter()
+        per = pool.map(_oracle_one, args, chunksize=max(1, n_utt // (cores * 4)))
+        wall = time.perf_counter() - t0
+    # wall includes generating the inputs in the workers; the algorithm's own time is `per`
+    algo_cpu_s = float(sum(per))
+    eff_wall = algo_cpu_s / cores
+    return {
+        "value": n_utt * DUR_S / eff_wall,
+        "unit": UNIT,
+        "cores": cores,
+        "kind": "port",
+        "sample": f"{n_utt} utterances x {DUR_S:g} s of config 2, float64 numpy/scipy oracle, {cores} processes x 1 thread; "
+                  f"{algo_cpu_s:.1f} CPU-s of algorithm time (single core: {n_utt * DUR_S / algo_cpu_s:.1f} audio-s/s)",
+        "wall_s_incl_input_generation": wall,
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t_all = time.perf_counter()
+    vals = []
+    last = None
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_baseline(64)
+    for _ in range(max(1, min(args.steps, 3))):
+        last = cpu_baseline()
+        vals.append(last["value"])
+    v = statistics.median(vals)
+    last["value"] = v
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
+        "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "BASELINE config 2 (bounded sample): 4 s 2-ch mixtures, 3 interferers, oracle IBM mask-MVDR, "
+                               "n_fft 512 hop 128", "utterance_s": DUR_S},
+        "cpu_baseline": last,
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "total_s": time.perf_counter() - t_all,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu_index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append((time.perf_counter(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ts, ln in self.rows:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                clk, mx = float(parts[1]), float(parts[2])
+            except ValueError:
+                continue
+            smax = mx
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                sm.append(clk)
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ ours
+def load_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import avzoom
+    from avzoom import synth, pipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = avzoom.PRESETS["baseline_oracle"]
+    L = int(DUR_S * FS)
+
+    # ---- synthetic inputs: this rank's shard of the utterance index space
+    cores = os.cpu_count() or 1
+    workers = max(1, min(32, cores // max(1, world)))
+    distinct = UTT_PER_GPU if workers >= 8 else 256
+    t_gen = time.perf_counter()
+    mix_h, tgt_h, itf_h = synth.make_batch(CONFIG_ID, distinct, DUR_S, N_INTERF, start=rank * UTT_PER_GPU, workers=workers)
+    reps = UTT_PER_GPU // distinct
+    if reps > 1:
+        mix_h, tgt_h, itf_h = np.tile(mix_h, (reps, 1, 1)), np.tile(tgt_h, (reps, 1)), np.tile(itf_h, (reps, 1))
+    t_gen = time.perf_counter() - t_gen
+    mix_p = torch.from_numpy(mix_h).pin_memory()
+    tgt_p = torch.from_numpy(tgt_h).pin_memory()
+    itf_p = torch.from_numpy(itf_h).pin_memory()
+    mix, tgt, itf = mix_p.to(dev), tgt_p.to(dev), itf_p.to(dev)
+    B = UTT_PER_GPU
+    audio_s_per_step = B * DUR_S * world
+
+    enh = pipeline.OracleMvdr(cfg, B, L, dev)      # pre-allocated buffers, no per-step allocation
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput
+    for _ in range(args.warmup):
+        enh.run(mix, tgt, itf)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        enh.run(mix, tgt, itf)
+    e1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    ms_per_step = ms_total / args.steps
+    value = audio_s_per_step / (ms_per_step * 1e-3)
+
+    # ---- per-kernel timing for the roofline (CUDA events on the launching stream, same resident inputs)
+    ktimes = enh.time_kernels(mix, tgt, itf, iters=max(3, min(args.steps, 10)))
+    peak_gbs, peak_src = load_peak()
+    samples = B * L
+    algo = {"k_cov (pass A: STFT x4 + IBM + covariance)": 16.0 * samples,      # read mix 2L, tgt L, int L
+            "k_synth (pass B: STFT + beamform + iSTFT)": 12.0 * samples}       # read mix 2L, write out L
+    dom = max(ktimes, key=lambda k: ktimes[k] if k in algo else -1)
+    achieved = algo[dom] / (ktimes[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algo[dom], "kernel_ms": ktimes,
+                "path_frac_of_hbm_roofline": (value / world) * FS * ALGO_BYTES_PER_SAMPLE / (peak_gbs * 1e9)}
+
+    # ---- end to end through the public host-buffer API
+    e2e_steps = max(2, min(args.steps, 5))
+    host = pipeline.HostPipeline(enh, world)
+    host.run(mix_p, tgt_p, itf_p)                       # warm-up (allocates pinned result buffers)
+    barrier()
+    t0 = time.perf_counter()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(e2e_steps):
+        out_h, scores_h = host.run(mix_p, tgt_p, itf_p)
+    g1.record()
+    barrier()
+    e2e_ms = max_over_ranks(g0.elapsed_time(g1)) / e2e_steps
+    e2e = {"value": audio_s_per_step / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": int(mix_p.numel() + tgt_p.numel() + itf_p.numel()) * 4,
+           "d2h_bytes_per_step": int(out_h.numel() + scores_h.numel()) * 4,
+           "api": "avzoom.pipeline.HostPipeline.run(pinned mix, tgt, itf) -> (enhanced waveforms, all-gathered scores)"}
+    sir_mean = float(scores_h[:, 1].mean())
+    sir_in = float(avzoom.sir_scores(mix[:, 0, :].contiguous(), tgt, itf)[:, 1].mean())
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline()
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE config 2: 1024 synthetic 4 s 2-ch far-field mixtures per GPU, 1 target + 3 "
+                                   "interferers, oracle IBM mask-MVDR, n_fft 512 hop 128",
+                       "utterances_per_gpu": B, "distinct_utterances_per_gpu": distinct, "samples_per_utterance": L,
+                       "l2_policy": "inputs (1.05 GB per GPU) larger than the 126 MB L2; no flush needed",
+                       "input_generation_s": round(t_gen, 2)},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": enh.launches_per_step * args.steps, "clocks": clocks,
+            "dSIR_dB": {"output_sir_mean": sir_mean, "mic1_sir_mean": sir_in, "improvement": sir_mean - sir_in},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.gpus > 1 and "RANK" not in os.environ:
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__), "--gpus", str(args.gpus),
+                   "--steps", str(args.steps), "--warmup", str(args.warmup)]
+            sys.exit(subprocess.call(cmd))
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -150,7 +150,7 @@ __device__ __forceinline__ float load_frame_pair(float2* buf, const float* __res
 //   A[k] = (Z[k] + conj Z[N-k]) / 2 ,  B[k] = -i (Z[k] - conj Z[N-k]) / 2
 __device__ __forceinline__ void unpack_pair(float2 zk, float2 zm, float2& A, float2& B) {
   A = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
-  B = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+  B = make_float2(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x));  // (zm.x - zk.x): DC/Nyquist give +0, like rfft
 }
 
 // log-magnitude + inter-channel phase difference of one TF bin (full_audio.../inference.py:91-94):

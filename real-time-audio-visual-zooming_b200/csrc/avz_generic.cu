@@ -416,10 +416,10 @@ k_synth(const float* __restrict__ mix, const float2* __restrict__ spec, const fl
 
 __global__ void k_peak_normalise(float* __restrict__ x, int64_t n, const float* __restrict__ peak, float peak_eps) {
   const int b = blockIdx.y;
-  const float inv = 1.0f / (peak[b] + peak_eps);
+  const float den = peak[b] + peak_eps;  // true division, like `s_out /= np.max(np.abs(s_out))`: the peak maps to 1.0
   float* xb = x + (int64_t)b * n;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    xb[i] *= inv;
+    xb[i] = __fdiv_rn(xb[i], den);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -1,0 +1,164 @@
+"""Batch drivers around the fused kernels: a pre-allocated oracle-mask MVDR engine (no per-step allocation, so a
+step is exactly the kernel launches) and a host-buffer pipeline that overlaps PCIe copies with compute.
+
+Utterances are independent (each has its own covariance), so a multi-GPU run shards them by contiguous blocks
+of the utterance index and never exchanges waveform data; the only collective is an all-gather of the
+per-utterance scores.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Tuple
+
+import torch
+
+from . import _lib
+from .config import MvdrConfig
+from .ops import _ptr, _stream, num_frames, steering_vectors
+
+
+class OracleMvdr:
+    """Oracle-IBM mask-MVDR (rt_av_zoom/core/oracle_debug.py:42-94) for a fixed batch shape."""
+
+    launches_per_step = 5  # k_cov, k_cov_finalize, k_mvdr_weights, k_synth, k_peak_normalise (+1 memset of `peak`)
+
+    def __init__(self, cfg: MvdrConfig, B: int, L: int, device):
+        self.cfg, self.B, self.L, self.device = cfg, B, L, device
+        self.lib = _lib.load()
+        self.F = cfg.n_freq
+        self.T = num_frames(L, cfg.n_fft, cfg.hop)
+        self.out_len = (self.T - 1) * cfg.hop
+        f32 = dict(dtype=torch.float32, device=device)
+        self.bits = torch.empty((B, self.T, (self.F + 31) // 32), dtype=torch.int32, device=device)
+        self.R = torch.empty((B, self.F, 4), **f32)
+        self.msum = torch.empty((B, self.F), **f32)
+        self.w = torch.empty((B, self.F, 2), dtype=torch.complex64, device=device)
+        self.out = torch.empty((B, self.out_len), **f32)
+        self.peak = torch.zeros((B,), **f32)
+        nws = self.lib.avz_ibm_cov_ws_bytes(B, L, cfg.n_fft, cfg.hop)
+        if nws < 0:
+            _lib.check(-1, "avz_ibm_cov_ws_bytes")
+        self.ws = torch.empty((max(int(nws), 4),), dtype=torch.uint8, device=device)
+        self.d = steering_vectors(cfg, device)
+        self.cc = cfg.to_c()
+        _lib.check(self.lib.avz_init(cfg.n_fft), "avz_init")
+
+    # individual stages (each one C-ABI call) ---------------------------------------------------
+    def pass_a(self, mix, tgt, itf):
+        c = self.cfg
+        _lib.check(self.lib.avz_ibm_cov_f32(_ptr(mix), _ptr(tgt), _ptr(itf), self.B, self.L, c.n_fft, c.hop,
+                                            float(c.norm_eps), _ptr(self.bits), _ptr(self.R), _ptr(self.msum),
+                                            _ptr(self.ws), _stream()), "avz_ibm_cov_f32")
+
+    def weights(self):
+        _lib.check(self.lib.avz_mvdr_weights_f32(_ptr(self.R), _ptr(self.d), self.B, self.F, C.byref(self.cc),
+                                                 _ptr(self.w), _stream()), "avz_mvdr_weights_f32")
+
+    def pass_b(self, mix):
+        c = self.cfg
+        self.peak.zero_()
+        bits = self.bits if c.post == "one_minus_noise" else None
+        _lib.check(self.lib.avz_mvdr_apply_f32(_ptr(mix), _ptr(self.w), _ptr(bits), _ptr(None), self.B, self.L, c.n_fft,
+                                               c.hop, C.byref(self.cc), _ptr(self.out), _ptr(self.peak), _stream()),
+                   "avz_mvdr_apply_f32")
+
+    def normalise(self):
+        if self.cfg.peak_eps is not None:
+            _lib.check(self.lib.avz_peak_normalise_f32(_ptr(self.out), self.B, self.out_len, _ptr(self.peak),
+                                                       float(self.cfg.peak_eps), _stream()), "avz_peak_normalise_f32")
+
+    def run(self, mix: torch.Tensor, tgt: torch.Tensor, itf: torch.Tensor) -> torch.Tensor:
+        """One step over device-resident inputs mix [B,2,L], tgt [B,L], itf [B,L] -> out [B,(T-1)*hop]."""
+        self.pass_a(mix, tgt, itf)
+        self.weights()
+        self.pass_b(mix)
+        self.normalise()
+        return self.out
+
+    def time_kernels(self, mix, tgt, itf, iters: int = 5) -> Dict[str, float]:
+        """Average device time (ms) of each stage, CUDA events on the launching stream."""
+        stages = [("k_cov (pass A: STFT x4 + IBM + covariance)", lambda: self.pass_a(mix, tgt, itf)),
+                  ("k_mvdr_weights", self.weights),
+                  ("k_synth (pass B: STFT + beamform + iSTFT)", lambda: self.pass_b(mix)),
+                  ("k_peak_normalise", self.normalise)]
+        self.run(mix, tgt, itf)
+        torch.cuda.synchronize()
+        res = {}
+        for name, fn in stages:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            res[name] = e0.elapsed_time(e1) / iters
+        return res
+
+
+class HostPipeline:
+    """End-to-end leg: pinned host waveforms in, enhanced waveforms + scores out, every step.
+
+    The batch is cut into sub-batches; host->device copies, kernels and device->host copies of consecutive
+    sub-batches run on three streams so PCIe transfers overlap compute.  Scores (OSINR, OSIR, SDR, SIR per
+    utterance) are all-gathered across ranks with NCCL when torch.distributed is initialised."""
+
+    def __init__(self, engine: OracleMvdr, world: int = 1, sub_batches: int = 8):
+        self.e = engine
+        self.world = world
+        B = engine.B
+        self.nsub = sub_batches if B % sub_batches == 0 and B >= sub_batches else 1
+        self.sb = B // self.nsub
+        dev = engine.device
+        self.sub = OracleMvdr(engine.cfg, self.sb, engine.L, dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.d_mix = [torch.empty((self.sb, 2, engine.L), **f32) for _ in range(2)]
+        self.d_tgt = [torch.empty((self.sb, engine.L), **f32) for _ in range(2)]
+        self.d_itf = [torch.empty((self.sb, engine.L), **f32) for _ in range(2)]
+        self.d_out = [torch.empty((self.sb, engine.out_len), **f32) for _ in range(2)]
+        self.scores = torch.empty((B, 4), **f32)
+        self.scores_all = torch.empty((B * world, 4), **f32)
+        self.h_out = torch.empty((B, engine.out_len), dtype=torch.float32).pin_memory()
+        self.h_scores = torch.empty((B * world, 4), dtype=torch.float32).pin_memory()
+        self.s_in, self.s_cmp, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def run(self, mix_h: torch.Tensor, tgt_h: torch.Tensor, itf_h: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        lib = _lib.load()
+        cur = torch.cuda.current_stream()
+        for s in (self.s_in, self.s_cmp, self.s_out):
+            s.wait_stream(cur)
+        ev_in = [None, None]
+        ev_cmp = [None, None]
+        ev_out = [None, None]
+        for c in range(self.nsub):
+            slot = c & 1
+            lo, hi = c * self.sb, (c + 1) * self.sb
+            with torch.cuda.stream(self.s_in):
+                if ev_cmp[slot] is not None:
+                    self.s_in.wait_event(ev_cmp[slot])       # previous user of this slot's inputs has finished
+                self.d_mix[slot].copy_(mix_h[lo:hi], non_blocking=True)
+                self.d_tgt[slot].copy_(tgt_h[lo:hi], non_blocking=True)
+                self.d_itf[slot].copy_(itf_h[lo:hi], non_blocking=True)
+                ev_in[slot] = self.s_in.record_event()
+            with torch.cuda.stream(self.s_cmp):
+                self.s_cmp.wait_event(ev_in[slot])
+                if ev_out[slot] is not None:
+                    self.s_cmp.wait_event(ev_out[slot])      # previous output of this slot has left the device
+                out = self.sub.run(self.d_mix[slot], self.d_tgt[slot], self.d_itf[slot])
+                _lib.check(lib.avz_sir_f32(_ptr(out), _ptr(self.d_tgt[slot]), _ptr(self.d_itf[slot]), self.sb,
+                                           self.sub.out_len, self.sub.L, _ptr(self.scores[lo:hi]), _stream()), "avz_sir_f32")
+                self.d_out[slot].copy_(out, non_blocking=True)
+                ev_cmp[slot] = self.s_cmp.record_event()
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(ev_cmp[slot])
+                self.h_out[lo:hi].copy_(self.d_out[slot], non_blocking=True)
+                ev_out[slot] = self.s_out.record_event()
+        cur.wait_stream(self.s_cmp)
+        cur.wait_stream(self.s_out)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self.scores_all, self.scores)
+        else:
+            self.scores_all.copy_(self.scores)
+        self.h_scores.copy_(self.scores_all, non_blocking=True)
+        cur.synchronize()
+        return self.h_out, self.h_scores
