@@ -101,6 +101,12 @@ AVZ_API int64_t avz_ibm_cov_ws_bytes(int B, int64_t L, int n_fft, int hop);
 AVZ_API int avz_ibm_cov_f32(const float* mix, const float* tgt, const float* itf, int B, int64_t L, int n_fft, int hop,
                     float norm_eps, uint32_t* ibm_bits, float* R, float* msum, void* ws, void* stream);
 
+/* ---- the IBM of oracle_debug.py:42-53 with every bin decided in float64 (direct DFT): slow reference form of the
+ * mask avz_ibm_cov_f32 produces, for checking it at sizes a CPU cannot reach.  n_fft = 512 only.
+ * ibm_bits [B, T, 9] u32 as above; ws16: 16 bytes of device scratch. */
+AVZ_API int avz_ibm_exact_f32(const float* tgt, const float* itf, int B, int64_t L, int n_fft, int hop, uint32_t* ibm_bits,
+                      void* ws16, void* stream);
+
 /* ---- masked covariance from a waveform and a given (target-probability) mask, learned-mask path:
  * replaces full_audio.../inference.py:90,102-108 / tf_lite_version/inference.py:97-127.
  * mask [B, F, T] f32 is the TARGET probability; the noise weight is (1 - mask). */

@@ -51,6 +51,7 @@ SIGNATURES = {
     "avz_peak_normalise_f32": (_i, [_p, _i, _l, _p, _f, _p]),
     "avz_ibm_cov_ws_bytes": (_l, [_i, _l, _i, _i]),
     "avz_ibm_cov_f32": (_i, [_p, _p, _p, _i, _l, _i, _i, _f, _p, _p, _p, _p, _p]),
+    "avz_ibm_exact_f32": (_i, [_p, _p, _i, _l, _i, _i, _p, _p, _p]),
     "avz_wave_mask_cov_f32": (_i, [_p, _p, _i, _l, _i, _i, _f, _f, _p, _p, _p, _p]),
     "avz_spec_mask_cov_f32": (_i, [_p, _p, _i, _i, _i, _f, _f, _p, _p, _p]),
     "avz_mvdr_weights_f32": (_i, [_p, _p, _i, _i, C.POINTER(AvzMvdrCfg), _p, _p]),

@@ -9,7 +9,33 @@
 // Reference blocks replaced: rt_av_zoom/core/oracle_debug.py:42-94 (see include/avzoom.h per entry).
 #include "avz_common.cuh"
 
+#include <cstdlib>
+
 namespace avz {
+
+// n_fft = 512 fast path (avz_opt512.cu)
+namespace o512 {
+int cov_chunks512(int B, int T);
+int64_t ws_bytes512(int B, int T);
+int launch_ibm_exact(const float* tgt, const float* itf, int B, int64_t L, int hop, uint32_t* ibm_bits, void* ws16,
+                     cudaStream_t st);
+template <int HOP>
+int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const float* mask, int B, int64_t L,
+                   float sqrt_eps, uint32_t* ibm_bits, float* part, int* chunks_out, cudaStream_t st);
+template <int HOP>
+int launch_apply(const float* mix, const float* w, const uint32_t* ibm_bits, const float* mask, int gain_mode,
+                 float post_floor, int B, int64_t L, float* out, float* peak, cudaStream_t st);
+}  // namespace o512
+
+// The register-resident 512-point path serves n_fft 512 with hop 128 / 256 unless AVZ_FORCE_GENERIC=1
+// (kept for A/B checks of the two implementations against each other).
+static bool use_opt512(int n_fft, int hop) {
+  static const bool forced = [] {
+    const char* e = getenv("AVZ_FORCE_GENERIC");
+    return e && e[0] == '1';
+  }();
+  return !forced && n_fft == 512 && (hop == 128 || hop == 256);
+}
 
 template <int N>
 struct Geo {
@@ -483,6 +509,21 @@ static int launch_cov(const float* mix, const float* tgt, const float* itf, cons
   return AVZ_OK;
 }
 
+// fast path: IBM + covariance (or mask covariance) for n_fft 512, then the shared finalize kernel
+static int launch_cov512(const float* mix, const float* tgt, const float* itf, const float* mask, int B, int64_t L,
+                         int hop, float sqrt_eps, float norm_eps, uint32_t* ibm_bits, float* R, float* msum, void* ws,
+                         cudaStream_t st) {
+  int chunks = 0;
+  int rc = (hop == 128) ? o512::launch_ibm_cov<128>(mix, tgt, itf, mask, B, L, sqrt_eps, ibm_bits, (float*)ws, &chunks, st)
+                        : o512::launch_ibm_cov<256>(mix, tgt, itf, mask, B, L, sqrt_eps, ibm_bits, (float*)ws, &chunks, st);
+  if (rc) return rc;
+  const int F = 257;
+  k_cov_finalize<<<(B * F + 255) / 256, 256, 0, st>>>((const float*)ws, B, F, Geo<512>::FP, chunks, norm_eps,
+                                                      reinterpret_cast<float4*>(R), msum);
+  AVZ_LAUNCH_OK("k_cov_finalize");
+  return AVZ_OK;
+}
+
 template <int N, int SRC>
 static int launch_synth(const float* mix, const float* spec, const float* w, const uint32_t* ibm_bits,
                         const float* mask, int gain_mode, float post_floor, int B, int64_t L, int T, int hop,
@@ -555,9 +596,12 @@ int64_t avz_ibm_cov_ws_bytes(int B, int64_t L, int n_fft, int hop) {
   if (B <= 0 || check_fft_args(n_fft, hop, L)) return -1;
   const int T = (int)avz_num_frames(L, n_fft, hop);
   const int warps = (n_fft <= 512) ? 8 : 4;
-  const int chunks = cov_chunks(B, T, warps, num_sms());
+  int chunks = cov_chunks(B, T, warps, num_sms());
+  if (n_fft == 512) chunks = max(chunks, o512::cov_chunks512(B, T));
   const int FP = ((n_fft / 2 + 1) + 31) / 32 * 32;
-  return (int64_t)B * chunks * 5 * FP * (int64_t)sizeof(float);
+  int64_t bytes = (int64_t)B * chunks * 5 * FP * (int64_t)sizeof(float);
+  if (n_fft == 512) bytes = max(bytes, o512::ws_bytes512(B, T));
+  return bytes;
 }
 
 int avz_ibm_cov_f32(const float* mix, const float* tgt, const float* itf, int B, int64_t L, int n_fft, int hop,
@@ -566,8 +610,19 @@ int avz_ibm_cov_f32(const float* mix, const float* tgt, const float* itf, int B,
     return set_error(AVZ_EINVAL, "avz_ibm_cov_f32: null pointer or empty batch");
   int rc = check_fft_args(n_fft, hop, L);
   if (rc) return rc;
+  if (use_opt512(n_fft, hop))
+    return launch_cov512(mix, tgt, itf, nullptr, B, L, hop, 0.f, norm_eps, ibm_bits, R, msum, ws, (cudaStream_t)stream);
   AVZ_DISPATCH_N(n_fft, (launch_cov<N_, COV_IBM>(mix, tgt, itf, nullptr, B, L, hop, 0.f, norm_eps, ibm_bits, R, msum,
                                                  ws, (cudaStream_t)stream)));
+}
+
+int avz_ibm_exact_f32(const float* tgt, const float* itf, int B, int64_t L, int n_fft, int hop, uint32_t* ibm_bits,
+                      void* ws16, void* stream) {
+  if (!tgt || !itf || !ibm_bits || !ws16 || B <= 0) return set_error(AVZ_EINVAL, "avz_ibm_exact_f32: bad argument");
+  int rc = check_fft_args(n_fft, hop, L);
+  if (rc) return rc;
+  if (n_fft != 512) return set_error(AVZ_EINVAL, "avz_ibm_exact_f32: n_fft must be 512");
+  return o512::launch_ibm_exact(tgt, itf, B, L, hop, ibm_bits, ws16, (cudaStream_t)stream);
 }
 
 int avz_wave_mask_cov_f32(const float* mix, const float* mask, int B, int64_t L, int n_fft, int hop, float sqrt_eps,
@@ -576,6 +631,9 @@ int avz_wave_mask_cov_f32(const float* mix, const float* mask, int B, int64_t L,
     return set_error(AVZ_EINVAL, "avz_wave_mask_cov_f32: null pointer or empty batch");
   int rc = check_fft_args(n_fft, hop, L);
   if (rc) return rc;
+  if (use_opt512(n_fft, hop))
+    return launch_cov512(mix, nullptr, nullptr, mask, B, L, hop, sqrt_eps, norm_eps, nullptr, R, msum, ws,
+                         (cudaStream_t)stream);
   AVZ_DISPATCH_N(n_fft, (launch_cov<N_, COV_MASK>(mix, nullptr, nullptr, mask, B, L, hop, sqrt_eps, norm_eps, nullptr,
                                                   R, msum, ws, (cudaStream_t)stream)));
 }
@@ -600,6 +658,12 @@ int avz_mvdr_apply_f32(const float* mix, const float* w, const uint32_t* ibm_bit
     default: return set_error(AVZ_EINVAL, "post_mode=%d unknown", cfg->post_mode);
   }
   const int T = (int)avz_num_frames(L, n_fft, hop);
+  if (use_opt512(n_fft, hop)) {
+    return (hop == 128) ? o512::launch_apply<128>(mix, w, ibm_bits, mask, gain, cfg->post_floor, B, L, out, peak,
+                                                  (cudaStream_t)stream)
+                        : o512::launch_apply<256>(mix, w, ibm_bits, mask, gain, cfg->post_floor, B, L, out, peak,
+                                                  (cudaStream_t)stream);
+  }
   AVZ_DISPATCH_N(n_fft, (launch_synth<N_, SRC_MIX>(mix, nullptr, w, ibm_bits, mask, gain, cfg->post_floor, B, L, T, hop,
                                                    out, peak, (cudaStream_t)stream)));
 }

@@ -1,0 +1,719 @@
+// n_fft = 512 fast path (the BASELINE shape: 512 / hop 128, also hop 256): register-resident warp FFTs
+// (avz_fft512.cuh), one warp per run of consecutive frames, no block-level barrier on the per-frame path.
+//
+//   k512_ibm     STFT(tgt), STFT(int) packed in one complex transform -> IBM bits (float64 recheck of near ties)
+//   k512_cov     STFT(mic0), STFT(mic1) packed -> mask-weighted 2x2 covariance partial sums in registers
+//   k512_apply   STFT(mix) -> beamform + post-filter -> two frames per inverse transform -> window ->
+//                overlap-add in registers -> / sum w^2 -> coalesced stores (+ per-utterance peak)
+//
+// Each lane keeps a sliding window of raw samples in registers: a new frame costs HOP/32 coalesced 128-byte
+// loads per channel, every input sample is fetched once per warp run, and nothing is staged in shared memory
+// except the single FFT transposition.  Replaces rt_av_zoom/core/oracle_debug.py:42-94.
+#include <cstdlib>
+
+#include "avz_common.cuh"
+#include "avz_fft512.cuh"
+
+namespace avz {
+namespace o512 {
+
+using f512::Lane;
+
+constexpr int kN = 512;
+constexpr int kF = 257;
+constexpr int kFW = 9;
+constexpr int kFP = 288;     // padded bins for partial sums (matches Geo<512>::FP)
+constexpr int kWarps = 4;    // warps per CTA
+
+// sample of row r (0..15) of frame t for this lane, zero outside the signal (scipy boundary='zeros', padded=True)
+__device__ __forceinline__ float ld_sample(const float* __restrict__ x, int64_t L, int64_t idx) {
+  return (idx >= 0 && idx < L) ? __ldg(x + idx) : 0.f;
+}
+
+// Sliding window of raw samples of two signals (16 rows of 32 lanes = one 512-sample frame each).
+template <int HOP>
+struct Window2 {
+  static constexpr int NR = HOP / 32;   // new rows per frame
+  float a[16], b[16];
+  float na[NR], nb[NR];                 // prefetched rows of the next frame
+
+  __device__ __forceinline__ void load_all(const float* __restrict__ xa, const float* __restrict__ xb, int64_t L,
+                                           int64_t t, int lane) {
+    const int64_t base = t * HOP - kN / 2 + lane;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      a[r] = ld_sample(xa, L, base + 32 * r);
+      b[r] = ld_sample(xb, L, base + 32 * r);
+    }
+  }
+  // issue the loads of the rows that frame t_next adds (rows 16-NR..15 of that frame)
+  __device__ __forceinline__ void prefetch(const float* __restrict__ xa, const float* __restrict__ xb, int64_t L,
+                                           int64_t t_next, int lane) {
+    const int64_t base = t_next * HOP - kN / 2 + lane + 32 * (16 - NR);
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      na[i] = ld_sample(xa, L, base + 32 * i);
+      nb[i] = ld_sample(xb, L, base + 32 * i);
+    }
+  }
+  __device__ __forceinline__ void advance() {
+#pragma unroll
+    for (int r = 0; r < 16 - NR; ++r) {
+      a[r] = a[r + NR];
+      b[r] = b[r + NR];
+    }
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      a[16 - NR + i] = na[i];
+      b[16 - NR + i] = nb[i];
+    }
+  }
+  // windowed complex frame a + i b
+  __device__ __forceinline__ void frame(float2 (&v)[16], const float (&w)[16]) const {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = make_float2(a[r] * w[r], b[r] * w[r]);
+  }
+};
+
+__device__ __forceinline__ void load_window(float (&w)[16], const float* __restrict__ win, float scale, int lane) {
+#pragma unroll
+  for (int r = 0; r < 16; ++r) w[r] = win[32 * r + lane] * scale;
+}
+
+// bin of lo[j] for this lane
+__device__ __forceinline__ int bin_lo(const Lane& ln, int j) { return ln.k1 + 16 * j + 128 * ln.h; }
+
+// ------------------------------------------------------------------------------------------
+// IBM bits
+// ------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ bool ibm_exact512(const float* __restrict__ tgt, const float* __restrict__ itf, int64_t L,
+                                             int64_t start, int k, const Tables& tb, int lane) {
+  double tr = 0, ti = 0, ir = 0, ii = 0;
+  for (int n = lane; n < N; n += kWarp) {
+    const int64_t i = start + n;
+    if (i >= 0 && i < L) {
+      const double w = tb.win_d[n];
+      const double2 e = tb.tw_d[(n * k) & (N - 1)];
+      const double a = w * (double)__ldg(tgt + i);
+      const double c = w * (double)__ldg(itf + i);
+      tr = fma(a, e.x, tr);
+      ti = fma(a, e.y, ti);
+      ir = fma(c, e.x, ir);
+      ii = fma(c, e.y, ii);
+    }
+  }
+  tr = warp_sum(tr);
+  ti = warp_sum(ti);
+  ir = warp_sum(ir);
+  ii = warp_sum(ii);
+  return (ir * ir + ii * ii) > (tr * tr + ti * ti);
+}
+
+// Near-ties are not resolved inline: the kernel records the float32 decision and appends (b, t, k) to a list;
+// k512_ibm_fixup then recomputes exactly those bins in float64 (one warp per entry, massively parallel) and
+// flips the bits that differ.  If the list overflows, the fix-up kernel rechecks every bin instead.
+struct AmbList {
+  unsigned long long* entries;  // (b << 32) | (t << 9) | k
+  unsigned int* count;
+  unsigned int cap;
+};
+
+template <int HOP>
+__global__ void __launch_bounds__(kWarps * 32)
+k512_ibm(const float* __restrict__ tgt, const float* __restrict__ itf, int64_t L, int T, int frames_per_cta,
+         uint32_t* __restrict__ ibm_bits, AmbList amb_list, float tol2, Tables tb) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* sm = reinterpret_cast<float2*>(smem_raw) + (size_t)(threadIdx.x >> 5) * f512::kSmemComplex;
+  Lane ln;
+  ln.init(tb.tw);
+  const int lane = ln.lane, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const float* tg = tgt + (int64_t)b * L;
+  const float* it = itf + (int64_t)b * L;
+  float w[16];
+  load_window(w, tb.win, 2.0f / kN, lane);
+
+  const int c0 = blockIdx.x * frames_per_cta, c1 = min(T, c0 + frames_per_cta);
+  const int per = (c1 - c0 + kWarps - 1) / kWarps;
+  const int ta = c0 + warp * per, tb_ = min(c1, ta + per);
+  if (ta >= tb_) return;
+
+  Window2<HOP> win;
+  win.load_all(tg, it, L, ta, lane);
+  for (int t = ta; t < tb_; ++t) {
+    if (t + 1 < tb_) win.prefetch(tg, it, L, t + 1, lane);
+    float2 v[16];
+    win.frame(v, w);
+    float e2 = 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) e2 = fmaf(v[r].x, v[r].x, fmaf(v[r].y, v[r].y, e2));
+    e2 = warp_sum(e2);
+    f512::forward(v, sm, ln);
+    float2 mir[8];
+    f512::mirror_of_low(v, mir, ln);
+    // float32 FFT error bound of one bin: delta = tol * sqrt(e2), e2 = sum |frame|^2 (= mean |Z[k]|^2).
+    // |pi - pt| <= 4 delta sqrt(mx) + 2 delta^2 is implied by diff^2 <= 32 delta^2 mx + 8 delta^4 (no sqrt).
+    const float d2 = tol2 * e2;
+    unsigned ballots[8], ambb[8];
+    unsigned tot = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float2 St, Si;
+      unpack_pair(v[j], mir[j], St, Si);
+      const float pt = cabs2(St), pi = cabs2(Si);
+      const float mx = fmaxf(pt, pi), diff = pi - pt;
+      // exact zeros on both sides (silence) are a true tie, not an ambiguity
+      const bool amb = (mx > 0.f) && (diff * diff <= d2 * (32.f * mx + 8.f * d2));
+      ballots[j] = __ballot_sync(kFull, pi > pt);
+      ambb[j] = __ballot_sync(kFull, amb);
+      tot += __popc(ambb[j]);
+    }
+    // Nyquist bin 256 = hi[0] of lane 0 (self-mirrored): S_tgt = Re, S_int = Im
+    unsigned ny, ny_amb;
+    {
+      const float pt = v[8].x * v[8].x, pi = v[8].y * v[8].y;
+      const float mx = fmaxf(pt, pi), diff = pi - pt;
+      const bool amb = (mx > 0.f) && (diff * diff <= d2 * (32.f * mx + 8.f * d2));
+      ny = __ballot_sync(kFull, pi > pt) & 1u;
+      ny_amb = __ballot_sync(kFull, amb) & 1u;
+      tot += ny_amb;
+    }
+    if (tot) {  // warp-uniform
+      unsigned base = 0;
+      if (lane == 0) base = atomicAdd(amb_list.count, tot);
+      base = __shfl_sync(kFull, base, 0);
+      const unsigned long long hdr = ((unsigned long long)b << 32) | ((unsigned long long)t << 9);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if ((ambb[j] >> lane) & 1u) {
+          const unsigned slot = base + __popc(ambb[j] & ((1u << lane) - 1u));
+          if (slot < amb_list.cap) amb_list.entries[slot] = hdr | (unsigned)bin_lo(ln, j);
+        }
+        base += __popc(ambb[j]);
+      }
+      if (ny_amb && lane == 0 && base < amb_list.cap) amb_list.entries[base] = hdr | 256u;
+    }
+    if (lane == 0) {
+      uint32_t* o = ibm_bits + ((int64_t)b * T + t) * kFW;
+#pragma unroll
+      for (int wd = 0; wd < 4; ++wd) {
+        o[wd] = (ballots[2 * wd] & 0xffffu) | (ballots[2 * wd + 1] << 16);
+        o[4 + wd] = (ballots[2 * wd] >> 16) | (ballots[2 * wd + 1] & 0xffff0000u);
+      }
+      o[8] = ny;
+    }
+    if (t + 1 < tb_) win.advance();
+  }
+}
+
+// One warp per listed bin: exact float64 decision; flip the stored bit if the float32 one was wrong.
+__global__ void __launch_bounds__(256)
+k512_ibm_fixup(const float* __restrict__ tgt, const float* __restrict__ itf, int64_t L, int T, int hop, int B,
+               uint32_t* __restrict__ ibm_bits, AmbList amb_list, Tables tb) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long gw = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const unsigned long long nw = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+  const unsigned int n = *amb_list.count;
+  const bool overflow = n > amb_list.cap;
+  const unsigned long long total = overflow ? (unsigned long long)B * T * kF : n;
+  for (unsigned long long i = gw; i < total; i += nw) {
+    int b, t, k;
+    if (!overflow) {
+      const unsigned long long e = amb_list.entries[i];
+      b = (int)(e >> 32);
+      t = (int)((e >> 9) & 0x7fffffu);
+      k = (int)(e & 511u);
+    } else {
+      k = (int)(i % kF);
+      t = (int)((i / kF) % T);
+      b = (int)(i / ((unsigned long long)kF * T));
+    }
+    const bool exact = ibm_exact512<kN>(tgt + (int64_t)b * L, itf + (int64_t)b * L, L, (int64_t)t * hop - kN / 2, k, tb,
+                                        lane);
+    if (lane == 0) {
+      uint32_t* wp = ibm_bits + ((int64_t)b * T + t) * kFW + (k >> 5);
+      const bool cur = ((*wp) >> (k & 31)) & 1u;
+      if (cur != exact) atomicXor(wp, 1u << (k & 31));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// masked covariance partial sums
+// ------------------------------------------------------------------------------------------
+enum { W_BITS = 0, W_MASK = 1 };
+
+template <int HOP, int WMODE>
+__global__ void __launch_bounds__(kWarps * 32)
+k512_cov(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, const float* __restrict__ mask, int64_t L,
+         int T, int frames_per_cta, float sqrt_eps, float* __restrict__ part, Tables tb) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* sm_all = reinterpret_cast<float2*>(smem_raw);
+  float2* sm = sm_all + (size_t)(threadIdx.x >> 5) * f512::kSmemComplex;
+  Lane ln;
+  ln.init(tb.tw);
+  const int lane = ln.lane, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
+  const float* m0 = mix + (int64_t)b * 2 * L;
+  const float* m1 = m0 + L;
+  float w[16];
+  load_window(w, tb.win, 2.0f / kN, lane);
+
+  // accumulators of this lane's 8 low bins (+ Nyquist on lane 0): R00, R11, Re R01, Im R01, sum m.
+  // Sums are of the un-halved spectra (Y0' = 2 Y0, Y1' = 2 Y1): scaled by 1/4 when written.
+  float a00[8], a11[8], are[8], aim[8], am_[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a00[j] = a11[j] = are[j] = aim[j] = am_[j] = 0.f;
+  float n00 = 0.f, n11 = 0.f, nre = 0.f, nm = 0.f;
+
+  const int c0 = chunk * frames_per_cta, c1 = min(T, c0 + frames_per_cta);
+  const int per = (c1 - c0 + kWarps - 1) / kWarps;
+  const int ta = c0 + warp * per, tb_ = min(c1, ta + per);
+
+  if (ta < tb_) {
+    Window2<HOP> win;
+    win.load_all(m0, m1, L, ta, lane);
+    for (int t = ta; t < tb_; ++t) {
+      if (t + 1 < tb_) win.prefetch(m0, m1, L, t + 1, lane);
+      // noise weights of this lane's bins
+      float mw[8], mny;
+      if (WMODE == W_BITS) {
+        const uint32_t* bw = ibm_bits + ((int64_t)b * T + t) * kFW;
+        uint32_t wd[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) wd[i] = __ldg(bw + 4 * ln.h + i);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mw[j] = ((wd[j >> 1] >> (ln.k1 + 16 * (j & 1))) & 1u) ? 1.f : 0.f;
+        mny = (__ldg(bw + 8) & 1u) ? 1.f : 0.f;
+      } else {
+        const float* mk = mask + (int64_t)b * kF * T + t;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mw[j] = 1.f - __ldg(mk + (int64_t)bin_lo(ln, j) * T);
+        mny = 1.f - __ldg(mk + (int64_t)256 * T);
+      }
+      float2 v[16];
+      win.frame(v, w);
+      f512::forward(v, sm, ln);
+      float2 mir[8];
+      f512::mirror_of_low(v, mir, ln);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        // Y0' = Z[k] + conj Z[N-k] = 2 Y0 ;  Y1' = -i (Z[k] - conj Z[N-k]) = 2 Y1
+        const float2 y0 = make_float2(v[j].x + mir[j].x, v[j].y - mir[j].y);
+        const float2 y1 = make_float2(v[j].y + mir[j].y, mir[j].x - v[j].x);
+        const float m = mw[j];
+        const float ms = (WMODE == W_MASK) ? m + sqrt_eps : m;
+        const float t0 = ms * y0.x, t1 = ms * y0.y;
+        a00[j] = fmaf(t0, y0.x, fmaf(t1, y0.y, a00[j]));
+        are[j] = fmaf(t0, y1.x, fmaf(t1, y1.y, are[j]));   // Re(y0 conj y1)
+        aim[j] = fmaf(t1, y1.x, fmaf(-t0, y1.y, aim[j]));  // Im(y0 conj y1)
+        const float u0 = ms * y1.x, u1 = ms * y1.y;
+        a11[j] = fmaf(u0, y1.x, fmaf(u1, y1.y, a11[j]));
+        am_[j] += m;
+      }
+      {  // Nyquist (meaningful on lane 0 only): Y0 = Re hi[0], Y1 = Im hi[0]
+        const float ms = (WMODE == W_MASK) ? mny + sqrt_eps : mny;
+        n00 = fmaf(ms * v[8].x, v[8].x, n00);
+        n11 = fmaf(ms * v[8].y, v[8].y, n11);
+        nre = fmaf(ms * v[8].x, v[8].y, nre);
+        nm += mny;
+      }
+      if (t + 1 < tb_) win.advance();
+    }
+  }
+  // per-warp sums -> shared -> fixed-order CTA reduction -> partial buffer [B][chunks][5][kFP]
+  __syncthreads();  // every warp is done with its FFT scratch; reuse it
+  float* s_acc = reinterpret_cast<float*>(sm_all + (size_t)kWarps * f512::kSmemComplex);  // [kWarps][5][kFP]
+  float* mine = s_acc + (size_t)warp * 5 * kFP;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = bin_lo(ln, j);
+    mine[0 * kFP + k] = 0.25f * a00[j];
+    mine[1 * kFP + k] = 0.25f * a11[j];
+    mine[2 * kFP + k] = 0.25f * are[j];
+    mine[3 * kFP + k] = 0.25f * aim[j];
+    mine[4 * kFP + k] = am_[j];
+  }
+  if (lane == 0) {
+    mine[0 * kFP + 256] = n00;
+    mine[1 * kFP + 256] = n11;
+    mine[2 * kFP + 256] = nre;
+    mine[3 * kFP + 256] = 0.f;
+    mine[4 * kFP + 256] = nm;
+  }
+  __syncthreads();
+  float* dst = part + ((int64_t)b * chunks + chunk) * 5 * kFP;
+  for (int i = threadIdx.x; i < 5 * kFP; i += kWarps * 32) {
+    const int k = i % kFP;
+    float s = 0.f;
+    if (k < kF) {
+#pragma unroll
+      for (int ww = 0; ww < kWarps; ++ww) s += s_acc[(size_t)ww * 5 * kFP + i];
+    }
+    dst[i] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// beamform + post-filter + inverse + overlap-add
+// ------------------------------------------------------------------------------------------
+enum { GAIN_NONE = 0, GAIN_BITS = 1, GAIN_FLOOR = 2, GAIN_MASK = 3 };
+
+template <int HOP>
+__global__ void __launch_bounds__(kWarps * 32)
+k512_apply(const float* __restrict__ mix, const float2* __restrict__ wgt, const uint32_t* __restrict__ ibm_bits,
+           const float* __restrict__ mask, int gain_mode, float post_floor, int64_t L, int T, int blocks_per_cta,
+           float* __restrict__ out, float* __restrict__ peak, Tables tb) {
+  constexpr int R = kN / HOP;        // frames overlapping one hop-block
+  constexpr int NR = HOP / 32;       // rows per hop-block
+  constexpr int TAIL = 16 - NR;      // rows still open after a frame's first block is emitted
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* sm_all = reinterpret_cast<float2*>(smem_raw);
+  float2* sm = sm_all + (size_t)(threadIdx.x >> 5) * f512::kSmemComplex;
+  float4* s_ab = reinterpret_cast<float4*>(sm_all + (size_t)kWarps * f512::kSmemComplex);  // [kF] (a.x,a.y,b.x,b.y)
+  float* s_head = reinterpret_cast<float*>(s_ab + 260);         // [kWarps][TAIL][32] first open blocks of a run
+  float* s_tail = s_head + kWarps * TAIL * 32;                  // [kWarps][TAIL][32] blocks left open at its end
+  __shared__ float s_peak[kWarps];
+
+  Lane ln;
+  ln.init(tb.tw);
+  const int lane = ln.lane, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const float* m0 = mix + (int64_t)b * 2 * L;
+  const float* m1 = m0 + L;
+  // S[k] = conj(w0) Y0 + conj(w1) Y1 = a[k] Z[k] + b[k] conj(Z[N-k]),  a = (conj w0 - i conj w1)/2, b = (conj w0 + i conj w1)/2
+  for (int k = threadIdx.x; k < kF; k += kWarps * 32) {
+    const float2 w0 = wgt[((int64_t)b * kF + k) * 2 + 0];
+    const float2 w1 = wgt[((int64_t)b * kF + k) * 2 + 1];
+    s_ab[k] = make_float4(0.5f * (w0.x - w1.y), 0.5f * (-w0.y - w1.x), 0.5f * (w0.x + w1.y), 0.5f * (-w0.y + w1.x));
+  }
+  __syncthreads();
+
+  float wf[16];   // forward window (Hann * 2/N)
+  float wi[16];   // synthesis window: irfft * sum(w) * w = 0.5 * (unnormalised inverse) * w
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const float h_ = tb.win[32 * r + lane];
+    wf[r] = h_ * (2.0f / kN);
+    wi[r] = 0.5f * h_;
+  }
+  // 1 / sum over the R overlapping frames of w^2, for a block with all R frames present
+  float inv_full[NR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      const float h_ = 2.f * wi[r + NR * q];
+      s = fmaf(h_, h_, s);
+    }
+    inv_full[r] = 1.0f / s;
+  }
+
+  // Hop-blocks in extended coordinates: block g covers [g HOP, (g+1) HOP); the output is blocks
+  // [R/2, R/2 + T - 1); block g sums frames g-R+1 .. g (those that exist).  This CTA owns [G0, G1), split
+  // into contiguous runs per warp.  Warp 0 recomputes the R-1 frames before G0 (warm-up); later warps start
+  // cold and their first R-1 blocks are completed at the end from the previous warp's open tail.
+  const int g_lo = R / 2, g_hi = R / 2 + T - 1;
+  const int G0 = g_lo + blockIdx.x * blocks_per_cta, G1 = min(g_hi, G0 + blocks_per_cta);
+  // runs are at least R-1 blocks long so that a head block only ever needs the previous warp's tail
+  const int per = max(R - 1, (G1 - G0 + kWarps - 1) / kWarps);
+  const int ga = min(G1, G0 + warp * per), gb = min(G1, ga + per);
+  const int64_t out_len = (int64_t)(T - 1) * HOP;
+  float* ob = out + (int64_t)b * out_len;
+  float my_peak = 0.f;
+  const bool cold = (warp > 0);
+  const int n_head = cold ? min(R - 1, gb - ga) : 0;   // blocks whose sums wait for the previous warp's tail
+
+  float o[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) o[r] = 0.f;
+
+  auto emit = [&](int g) {
+    // block g is complete in o[0..NR-1] (unless it is one of this warp's head blocks)
+    const bool interior = (g >= R - 1) && (g <= T - 1);
+    const int64_t n0 = (int64_t)(g - g_lo) * HOP + lane;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      float val;
+      if (interior) {
+        val = o[r] * inv_full[r];
+      } else {
+        float nrm = 0.f;
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+          const int tq = g - q;
+          const float h_ = 2.f * wi[r + NR * q];
+          if (tq >= 0 && tq <= T - 1) nrm = fmaf(h_, h_, nrm);
+        }
+        val = o[r] / (nrm > 1e-10f ? nrm : 1.0f);
+      }
+      ob[n0 + 32 * r] = val;
+      my_peak = fmaxf(my_peak, fabsf(val));
+    }
+  };
+  auto shift = [&]() {
+#pragma unroll
+    for (int r = 0; r < TAIL; ++r) o[r] = o[r + NR];
+#pragma unroll
+    for (int r = TAIL; r < 16; ++r) o[r] = 0.f;
+  };
+  // after frame g has been added: close block g
+  auto close_block = [&](int g) {
+    if (g >= ga && g < gb) {
+      if (cold && g - ga < n_head) {
+        float* hd = s_head + ((size_t)warp * TAIL + (size_t)(g - ga) * NR) * 32 + lane;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) hd[32 * r] = o[r];
+      } else {
+        emit(g);
+      }
+    }
+    shift();
+  };
+
+  if (ga < gb) {
+    const int t_first = cold ? ga : max(0, ga - (R - 1));
+    Window2<HOP> win;
+    if (t_first <= T - 1) win.load_all(m0, m1, L, t_first, lane);
+    float2 Sa[8], Sb[8];
+    float2 ny;
+
+    auto analyse = [&](int t, float2 (&S)[8], float& s_ny) {
+      // frame t: forward transform, beamform, post-filter -> S at this lane's low bins, Nyquist (lane 0)
+      float gj[8], gny;
+      if (gain_mode == GAIN_BITS) {
+        const uint32_t* bw = ibm_bits + ((int64_t)b * T + t) * kFW;
+        uint32_t wd[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) wd[i] = __ldg(bw + 4 * ln.h + i);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gj[j] = ((wd[j >> 1] >> (ln.k1 + 16 * (j & 1))) & 1u) ? 0.f : 1.f;
+        gny = (__ldg(bw + 8) & 1u) ? 0.f : 1.f;
+      } else if (gain_mode == GAIN_NONE) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gj[j] = 1.f;
+        gny = 1.f;
+      } else {
+        const float* mk = mask + (int64_t)b * kF * T + t;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float mv = __ldg(mk + (int64_t)bin_lo(ln, j) * T);
+          gj[j] = (gain_mode == GAIN_FLOOR) ? fmaxf(mv, post_floor) : mv;
+        }
+        const float mv = __ldg(mk + (int64_t)256 * T);
+        gny = (gain_mode == GAIN_FLOOR) ? fmaxf(mv, post_floor) : mv;
+      }
+      float2 v[16];
+      win.frame(v, wf);
+      f512::forward(v, sm, ln);
+      float2 mir[8];
+      f512::mirror_of_low(v, mir, ln);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 ab = s_ab[bin_lo(ln, j)];
+        // a * z + b * conj(m)
+        float2 s;
+        s.x = fmaf(ab.x, v[j].x, -ab.y * v[j].y) + fmaf(ab.z, mir[j].x, ab.w * mir[j].y);
+        s.y = fmaf(ab.x, v[j].y, ab.y * v[j].x) + fmaf(ab.w, mir[j].x, -ab.z * mir[j].y);
+        S[j] = make_float2(s.x * gj[j], s.y * gj[j]);
+      }
+      const float4 abn = s_ab[256];
+      // Re(a z + b conj z), z = hi[0] (lane 0)
+      s_ny = gny * ((abn.x + abn.z) * v[8].x + (abn.w - abn.y) * v[8].y);
+    };
+
+    for (int g = t_first; g < gb; g += 2) {
+      const bool va = (g <= T - 1);
+      const bool vb = (g + 1 <= T - 1) && (g + 1 < gb);
+      if (va) {
+        if (g + 1 <= T - 1) win.prefetch(m0, m1, L, g + 1, lane);
+        analyse(g, Sa, ny.x);
+        if (g + 1 <= T - 1) win.advance();
+      }
+      if (vb) {
+        if (g + 2 <= T - 1) win.prefetch(m0, m1, L, g + 2, lane);
+        analyse(g + 1, Sb, ny.y);
+        if (g + 2 <= T - 1) win.advance();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) Sb[j] = make_float2(0.f, 0.f);
+        ny.y = 0.f;
+      }
+      if (va) {
+        float2 v[16];
+        f512::hermitian_pack(Sa, Sb, ny, v, ln);
+        f512::inverse(v, sm, ln);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) o[r] = fmaf(wi[r], v[r].x, o[r]);
+        close_block(g);
+        if (g + 1 < gb) {
+#pragma unroll
+          for (int r = 0; r < 16; ++r) o[r] = fmaf(wi[r], v[r].y, o[r]);
+          close_block(g + 1);
+        }
+      } else {  // past the last frame: only flush the blocks still open
+        close_block(g);
+        if (g + 1 < gb) close_block(g + 1);
+      }
+    }
+  }
+  // Blocks t_first .. gb-1 are closed; o[0..TAIL-1] is this run's contribution to the R-1 blocks from gb on:
+  // hand it to the next warp (zeros if this warp had no run).
+  {
+    float* tl = s_tail + (size_t)warp * TAIL * 32 + lane;
+#pragma unroll
+    for (int r = 0; r < TAIL; ++r) tl[32 * r] = (ga < gb) ? o[r] : 0.f;
+  }
+  __syncthreads();
+  if (cold && ga < gb) {
+    // complete this warp's head blocks: own partial sums + the previous warp's tail
+    const float* prev = s_tail + (size_t)(warp - 1) * TAIL * 32 + lane;
+    const float* hd = s_head + (size_t)warp * TAIL * 32 + lane;
+    for (int i = 0; i < n_head; ++i) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) o[r] = hd[32 * (i * NR + r)] + prev[32 * (i * NR + r)];
+      emit(ga + i);
+    }
+  }
+  if (peak != nullptr) {
+    my_peak = warp_max(my_peak);
+    if (lane == 0) s_peak[warp] = my_peak;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float m = 0.f;
+      for (int i = 0; i < kWarps; ++i) m = fmaxf(m, s_peak[i]);
+      atomicMax(reinterpret_cast<unsigned int*>(peak + b), __float_as_uint(m));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int frames_per_cta(int B, int T, int sms) {
+  // aim for >= ~20 CTAs per SM (3 resident) so that the tail of the last wave is short
+  int per_utt = (20 * sms + B - 1) / B;
+  if (per_utt < 1) per_utt = 1;
+  int fpc = (T + per_utt - 1) / per_utt;
+  if (fpc < 8 * kWarps) fpc = 8 * kWarps;
+  if (fpc > T) fpc = T;
+  return fpc;
+}
+
+int cov_chunks512(int B, int T) {
+  const int fpc = frames_per_cta(B, T, num_sms());
+  return (T + fpc - 1) / fpc;
+}
+
+// workspace layout: [partial sums: B * chunks * 5 * kFP floats][pad to 16][count: 4 x u32][entries: cap x u64]
+static size_t part_bytes(int B, int chunks) {
+  return (((size_t)B * chunks * 5 * kFP * sizeof(float)) + 15) / 16 * 16;
+}
+static unsigned amb_cap(int B, int T) {
+  const unsigned long long c = (unsigned long long)B * T * 8ull;   // 8 near-ties per frame on average
+  return (unsigned)(c > (1ull << 26) ? (1ull << 26) : c);
+}
+int64_t ws_bytes512(int B, int T) {
+  return (int64_t)(part_bytes(B, cov_chunks512(B, T)) + 16 + (size_t)amb_cap(B, T) * 8);
+}
+
+static float ibm_tol2() {
+  // (relative float32 FFT error bound)^2; AVZ_IBM_TOL overrides the bound for experiments
+  static const float t2 = [] {
+    double tol = 1e-6;
+    if (const char* e = getenv("AVZ_IBM_TOL")) tol = atof(e);
+    return (float)(tol * tol);
+  }();
+  return t2;
+}
+
+template <int HOP>
+int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const float* mask, int B, int64_t L,
+                   float sqrt_eps, uint32_t* ibm_bits, float* part, int* chunks_out, cudaStream_t st) {
+  Tables tb;
+  int rc = tables_for(kN, &tb);
+  if (rc) return rc;
+  const int T = (int)avz_num_frames(L, kN, HOP);
+  const int fpc = frames_per_cta(B, T, num_sms());
+  const int chunks = (T + fpc - 1) / fpc;
+  *chunks_out = chunks;
+  dim3 grid(chunks, B);
+  const size_t smem_fft = (size_t)kWarps * f512::kSmemComplex * sizeof(float2);
+  if (mask == nullptr) {
+    unsigned char* wsb = reinterpret_cast<unsigned char*>(part) + part_bytes(B, chunks);
+    AmbList al;
+    al.count = reinterpret_cast<unsigned int*>(wsb);
+    al.entries = reinterpret_cast<unsigned long long*>(wsb + 16);
+    al.cap = amb_cap(B, T);
+    AVZ_CUDA_OK(cudaMemsetAsync(al.count, 0, 16, st));
+    AVZ_CUDA_OK(cudaFuncSetAttribute(k512_ibm<HOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
+    k512_ibm<HOP><<<grid, kWarps * 32, smem_fft, st>>>(tgt, itf, L, T, fpc, ibm_bits, al, ibm_tol2(), tb);
+    AVZ_LAUNCH_OK("k512_ibm");
+    k512_ibm_fixup<<<num_sms() * 8, 256, 0, st>>>(tgt, itf, L, T, HOP, B, ibm_bits, al, tb);
+    AVZ_LAUNCH_OK("k512_ibm_fixup");
+  }
+  const size_t smem_cov = smem_fft + (size_t)kWarps * 5 * kFP * sizeof(float);
+  if (mask == nullptr) {
+    AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov<HOP, W_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
+    k512_cov<HOP, W_BITS><<<grid, kWarps * 32, smem_cov, st>>>(mix, ibm_bits, nullptr, L, T, fpc, 0.f, part, tb);
+  } else {
+    AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov<HOP, W_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
+    k512_cov<HOP, W_MASK><<<grid, kWarps * 32, smem_cov, st>>>(mix, nullptr, mask, L, T, fpc, sqrt_eps, part, tb);
+  }
+  AVZ_LAUNCH_OK("k512_cov");
+  return AVZ_OK;
+}
+
+template <int HOP>
+int launch_apply(const float* mix, const float* w, const uint32_t* ibm_bits, const float* mask, int gain_mode,
+                 float post_floor, int B, int64_t L, float* out, float* peak, cudaStream_t st) {
+  Tables tb;
+  int rc = tables_for(kN, &tb);
+  if (rc) return rc;
+  const int T = (int)avz_num_frames(L, kN, HOP);
+  const int n_blocks = T - 1;
+  if (n_blocks <= 0) return AVZ_OK;
+  int bpc = frames_per_cta(B, n_blocks, num_sms());
+  const int chunks = (n_blocks + bpc - 1) / bpc;
+  constexpr int TAIL = 16 - HOP / 32;
+  const size_t smem = (size_t)kWarps * f512::kSmemComplex * sizeof(float2) + 260 * sizeof(float4) +
+                      2 * (size_t)kWarps * TAIL * 32 * sizeof(float);
+  AVZ_CUDA_OK(cudaFuncSetAttribute(k512_apply<HOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(chunks, B);
+  k512_apply<HOP><<<grid, kWarps * 32, smem, st>>>(mix, reinterpret_cast<const float2*>(w), ibm_bits, mask, gain_mode,
+                                                   post_floor, L, T, bpc, out, peak, tb);
+  AVZ_LAUNCH_OK("k512_apply");
+  return AVZ_OK;
+}
+
+// Every bin decided in float64 (slow; the checker for the float32 + fix-up path at sizes the CPU oracle cannot reach).
+int launch_ibm_exact(const float* tgt, const float* itf, int B, int64_t L, int hop, uint32_t* ibm_bits, void* ws16,
+                     cudaStream_t st) {
+  Tables tb;
+  int rc = tables_for(kN, &tb);
+  if (rc) return rc;
+  const int T = (int)avz_num_frames(L, kN, hop);
+  AVZ_CUDA_OK(cudaMemsetAsync(ibm_bits, 0, (size_t)B * T * kFW * sizeof(uint32_t), st));
+  AVZ_CUDA_OK(cudaMemsetAsync(ws16, 0xff, 16, st));   // count = 0xffffffff > cap = 0: "overflow" -> scan all bins
+  AmbList al;
+  al.count = reinterpret_cast<unsigned int*>(ws16);
+  al.entries = nullptr;
+  al.cap = 0;
+  k512_ibm_fixup<<<num_sms() * 8, 256, 0, st>>>(tgt, itf, L, T, hop, B, ibm_bits, al, tb);
+  AVZ_LAUNCH_OK("k512_ibm_fixup(exact)");
+  return AVZ_OK;
+}
+
+template int launch_ibm_cov<128>(const float*, const float*, const float*, const float*, int, int64_t, float, uint32_t*,
+                                 float*, int*, cudaStream_t);
+template int launch_ibm_cov<256>(const float*, const float*, const float*, const float*, int, int64_t, float, uint32_t*,
+                                 float*, int*, cudaStream_t);
+template int launch_apply<128>(const float*, const float*, const uint32_t*, const float*, int, float, int, int64_t,
+                               float*, float*, cudaStream_t);
+template int launch_apply<256>(const float*, const float*, const uint32_t*, const float*, int, float, int, int64_t,
+                               float*, float*, cudaStream_t);
+
+}  // namespace o512
+}  // namespace avz

@@ -21,7 +21,7 @@ __all__ = [
     "num_frames", "stft", "istft", "ibm", "ibm_target_label", "geometric_mask", "masked_covariance",
     "steering_vectors", "mvdr_weights", "beamform", "logmag_ipd", "physics_features", "sir_scores",
     "ibm_covariance", "wave_masked_covariance", "mvdr_apply", "peak_normalise", "unpack_ibm",
-    "oracle_mask_mvdr", "learned_mask_mvdr", "covariance_to_matrix",
+    "oracle_mask_mvdr", "learned_mask_mvdr", "covariance_to_matrix", "ibm_exact_bits",
 ]
 
 
@@ -304,6 +304,18 @@ def ibm_covariance(mix: torch.Tensor, tgt: torch.Tensor, itf: torch.Tensor, cfg:
     _lib.check(lib.avz_ibm_cov_f32(_ptr(mix), _ptr(tgt), _ptr(itf), B, L, cfg.n_fft, cfg.hop, float(cfg.norm_eps),
                                    _ptr(bits), _ptr(Rp), _ptr(ms), _ptr(ws), _stream()), "avz_ibm_cov_f32")
     return bits, Rp, ms
+
+
+def ibm_exact_bits(tgt: torch.Tensor, itf: torch.Tensor, cfg: MvdrConfig) -> torch.Tensor:
+    """The IBM of oracle_debug.py:42-53 with every bin decided in float64 on the GPU (slow reference form).
+    tgt, itf [B,L] -> ibm_bits [B,T,9] int32."""
+    B, L = tgt.shape
+    T = num_frames(L, cfg.n_fft, cfg.hop)
+    bits = torch.empty((B, T, (cfg.n_freq + 31) // 32), dtype=torch.int32, device=tgt.device)
+    ws = torch.empty((16,), dtype=torch.uint8, device=tgt.device)
+    _lib.check(_lib.load().avz_ibm_exact_f32(_ptr(tgt), _ptr(itf), B, L, cfg.n_fft, cfg.hop, _ptr(bits), _ptr(ws),
+                                             _stream()), "avz_ibm_exact_f32")
+    return bits
 
 
 def wave_masked_covariance(mix: torch.Tensor, mask: torch.Tensor, cfg: MvdrConfig):

@@ -254,6 +254,28 @@ def test_geometric_mask_mvdr_pieces(az, golden_dir):
     assert rel_l2(x.cpu().numpy(), ref) < 5e-3
 
 
+def test_ibm_bit_exact_at_scale(az):
+    """IBM of the fused float32 path (near ties re-decided in float64) against the all-float64 GPU reference over
+    ~16 M bins, the latter pinned to the CPU oracle on one utterance; plus degenerate inputs (identical references:
+    every bin is an exact tie -> all zeros; the near-tie list overflows and the full recheck must still be right)."""
+    cfg = az.PRESETS["baseline_oracle"]
+    mix, tgt, itf = synth(2, 128, 4.0, 3, start=5000)
+    mix_d, tgt_d, itf_d = (torch.from_numpy(a).cuda() for a in (mix, tgt, itf))
+    bits, _, _ = az.ibm_covariance(mix_d, tgt_d, itf_d, cfg)
+    ref_bits = az.ibm_exact_bits(tgt_d, itf_d, cfg)
+    assert torch.equal(bits, ref_bits), f"{int((bits != ref_bits).sum())} IBM words differ"
+    m = az.unpack_ibm(ref_bits[:1], cfg.n_freq).cpu().numpy()[0]
+    mo = O.ibm_noise_mask(O.stft_scipy(tgt[0], 512, 128), O.stft_scipy(itf[0], 512, 128))
+    assert np.array_equal(m, mo.astype(np.float32))
+    # identical references
+    bits2, _, _ = az.ibm_covariance(mix_d[:4], tgt_d[:4], tgt_d[:4].clone(), cfg)
+    assert int(bits2.abs().sum()) == 0
+    # scaled copy: |S_int| = 1.0000001 |S_tgt| everywhere they are non-zero -> all ones except exact-zero bins
+    it2 = (tgt_d[:2].double() * 1.0000001).float()
+    b3, _, _ = az.ibm_covariance(mix_d[:2], tgt_d[:2], it2, cfg)
+    assert torch.equal(b3, az.ibm_exact_bits(tgt_d[:2], it2, cfg))
+
+
 # --------------------------------------------------------------------------------------------- full-size properties
 def test_config2_full_size_properties(az):
     """1024 x 4 s through the fused path: shape, per-utterance peak == 1, distortionless weights, and
