@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libavzoom.so")
+LIB_PATH = os.environ.get("AVZ_LIB") or os.path.join(_HERE, "libavzoom.so")  # AVZ_LIB: A/B builds of the same ABI
 
 _lib = None
 

@@ -25,12 +25,6 @@ constexpr int kN = 512;
 constexpr int kRow = 42;                  // complex elements per shared-memory row
 constexpr int kSmemComplex = 16 * kRow;   // per warp
 
-// cos / sin of 2 pi m / 16 and 2 pi m / 32
-__device__ __constant__ const float kC16[16] = {1.f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f,
-                                                0.f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f,
-                                                -1.f, -0.92387953251128674f, -0.70710678118654752f, -0.38268343236508977f,
-                                                0.f, 0.38268343236508977f, 0.70710678118654752f, 0.92387953251128674f};
-
 template <int M16>
 struct W16 {  // exp(-2 pi i M16 / 16), compile-time
   static constexpr float c() {
@@ -114,39 +108,52 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
 }
 
 // Per-lane constants of the transform.
+//
+// The transposition twiddle of element k (0..15) of lane L is W512^(L k).  With k = k1 + 4 k2 it factors into
+// ta[k1] * tb[k2], ta[k1] = W512^(L k1), tb[k2] = W512^(4 L k2): 6 complex registers instead of 15, at the price
+// of 9 extra complex multiplies per transform (registers, not flops, limit occupancy here).
+// Lanes L = 3 (mod 4) must also negate their 16 values (this rotates the second-stage outputs of the odd lanes
+// by 8 so that the radix-2 exchange needs no register selects); callers fold that `sign` into the analysis /
+// synthesis window they multiply with anyway.
 struct Lane {
-  float2 tw[16];   // tw[k1] = sign * exp(-2 pi i L k1 / 512); tw[0] = (sign, 0); sign = -1 on lanes L = 3 (mod 4)
+  float2 ta[4], tb[4];   // [0] unused (= 1)
+  float sign;            // -1 on lanes L = 3 (mod 4), else +1: multiply the time-domain side by it
   int lane, k1, h, mirror;
-  bool k0;         // k1 == 0: the mirrored bins sit one slot further (see header comment)
-  float rot;       // h ? -1 : +1
-  int wr_off;      // shared-memory column this lane writes in the forward transposition
-  int rd_off;      // first element this lane reads
+  bool k0;               // k1 == 0: the mirrored bins sit one slot further (see header comment)
+  float rot;             // h ? -1 : +1
+  int wr_off;            // shared-memory column this lane writes in the forward transposition
+  int rd_off;            // first element this lane reads
 
-  __device__ __forceinline__ void init(const float2* __restrict__ tw512 /* exp(-2 pi i k/512), global or shared */) {
+  __device__ __forceinline__ void init(const float2* __restrict__ tw512 /* exp(-2 pi i k/512) */) {
     lane = threadIdx.x & 31;
     k1 = lane & 15;
     h = lane >> 4;
     mirror = ((16 - k1) & 15) + 16 * (1 - h);
     k0 = (k1 == 0);
     rot = h ? -1.f : 1.f;
-    const float sign = ((lane & 3) == 3) ? -1.f : 1.f;
+    sign = ((lane & 3) == 3) ? -1.f : 1.f;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float2 w = tw512[(lane * i) & 511];
-      tw[i] = make_float2(sign * w.x, sign * w.y);
+    for (int i = 1; i < 4; ++i) {
+      ta[i] = tw512[(lane * i) & 511];
+      tb[i] = tw512[(lane * 4 * i) & 511];
     }
+    ta[0] = tb[0] = make_float2(1.f, 0.f);
     wr_off = (lane & 1) * 24 + (lane >> 1);
     rd_off = k1 * kRow + 24 * h;
   }
 };
 
-// Forward transform.  In: v[r] = x[32 r + lane].  Out: v[j] = lo[j], v[8 + j] = hi[j] (spectrum layout).
+// Forward transform.  In: v[r] = sign * x[32 r + lane].  Out: v[j] = lo[j], v[8 + j] = hi[j] (spectrum layout).
 __device__ __forceinline__ void forward(float2 (&v)[16], float2* __restrict__ sm, const Lane& ln) {
   fft16<false>(v);
-  v[0].x *= ln.tw[0].x;
-  v[0].y *= ln.tw[0].x;
 #pragma unroll
-  for (int i = 1; i < 16; ++i) v[i] = cmul(v[i], ln.tw[i]);
+  for (int a = 1; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[a + 4 * c] = cmul(v[a + 4 * c], ln.ta[a]);
+#pragma unroll
+  for (int c = 1; c < 4; ++c)
+#pragma unroll
+    for (int a = 0; a < 4; ++a) v[a + 4 * c] = cmul(v[a + 4 * c], ln.tb[c]);
   float2* wp = sm + ln.wr_off;
 #pragma unroll
   for (int i = 0; i < 16; ++i) wp[i * kRow] = v[i];
@@ -185,7 +192,7 @@ __device__ __forceinline__ void forward(float2 (&v)[16], float2* __restrict__ sm
   }
 }
 
-// Unnormalised inverse transform.  In: v[j] = lo[j], v[8 + j] = hi[j].  Out: v[r] = x[32 r + lane] * 512.
+// Unnormalised inverse transform.  In: v[j] = lo[j], v[8 + j] = hi[j].  Out: v[r] = sign * 512 * x[32 r + lane].
 __device__ __forceinline__ void inverse(float2 (&v)[16], float2* __restrict__ sm, const Lane& ln) {
   const bool hh = ln.h != 0;
 #pragma unroll
@@ -221,10 +228,14 @@ __device__ __forceinline__ void inverse(float2 (&v)[16], float2* __restrict__ sm
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = rp[i * kRow];
   __syncwarp();
-  v[0].x *= ln.tw[0].x;
-  v[0].y *= ln.tw[0].x;
 #pragma unroll
-  for (int i = 1; i < 16; ++i) v[i] = cmulc(v[i], ln.tw[i]);
+  for (int a = 1; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[a + 4 * c] = cmulc(v[a + 4 * c], ln.ta[a]);
+#pragma unroll
+  for (int c = 1; c < 4; ++c)
+#pragma unroll
+    for (int a = 0; a < 4; ++a) v[a + 4 * c] = cmulc(v[a + 4 * c], ln.tb[c]);
   fft16<true>(v);
 }
 

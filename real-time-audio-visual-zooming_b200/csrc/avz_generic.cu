@@ -224,7 +224,7 @@ k_cov(const float* __restrict__ mix, const float* __restrict__ tgt, const float*
           bit = pi > pt;
           const float mx = fmaxf(pt, pi);
           // too close to call in float32 (but not the exact 0 == 0 tie of silence): redo in float64
-          amb = (mx > 0.f) && (fabsf(pi - pt) <= 4.f * delta * sqrtf(mx) + 2.f * delta * delta);
+          amb = (e2 > 0.f) && (fabsf(pi - pt) <= 4.f * delta * sqrtf(mx) + 2.f * delta * delta);
         }
         unsigned am = __ballot_sync(kFull, amb);
         while (am) {

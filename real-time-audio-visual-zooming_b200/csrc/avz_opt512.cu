@@ -1,10 +1,12 @@
 // n_fft = 512 fast path (the BASELINE shape: 512 / hop 128, also hop 256): register-resident warp FFTs
 // (avz_fft512.cuh), one warp per run of consecutive frames, no block-level barrier on the per-frame path.
 //
-//   k512_ibm     STFT(tgt), STFT(int) packed in one complex transform -> IBM bits (float64 recheck of near ties)
-//   k512_cov     STFT(mic0), STFT(mic1) packed -> mask-weighted 2x2 covariance partial sums in registers
-//   k512_apply   STFT(mix) -> beamform + post-filter -> two frames per inverse transform -> window ->
-//                overlap-add in registers -> / sum w^2 -> coalesced stores (+ per-utterance peak)
+//   k512_ibm        STFT(tgt), STFT(int) packed in one complex transform -> IBM bits (float32 decision; near
+//                   ties appended to a list)
+//   k512_ibm_fixup  one warp per listed bin: float64 direct DFT, flips the bits float32 got wrong
+//   k512_cov        STFT(mic0), STFT(mic1) packed -> mask-weighted 2x2 covariance partial sums in registers
+//   k512_apply      STFT(mix) -> beamform + post-filter -> two frames per inverse transform -> window ->
+//                   overlap-add in registers -> / sum w^2 -> coalesced stores (+ per-utterance peak)
 //
 // Each lane keeps a sliding window of raw samples in registers: a new frame costs HOP/32 coalesced 128-byte
 // loads per channel, every input sample is fetched once per warp run, and nothing is staged in shared memory
@@ -24,36 +26,56 @@ constexpr int kF = 257;
 constexpr int kFW = 9;
 constexpr int kFP = 288;     // padded bins for partial sums (matches Geo<512>::FP)
 constexpr int kWarps = 4;    // warps per CTA
-
-// sample of row r (0..15) of frame t for this lane, zero outside the signal (scipy boundary='zeros', padded=True)
-__device__ __forceinline__ float ld_sample(const float* __restrict__ x, int64_t L, int64_t idx) {
-  return (idx >= 0 && idx < L) ? __ldg(x + idx) : 0.f;
-}
+#ifndef AVZ_MINB_IBM
+#define AVZ_MINB_IBM 4
+#endif
+#ifndef AVZ_MINB_COV
+#define AVZ_MINB_COV 3
+#endif
+#ifndef AVZ_MINB_APPLY
+#define AVZ_MINB_APPLY 2
+#endif
 
 // Sliding window of raw samples of two signals (16 rows of 32 lanes = one 512-sample frame each).
+// Sample index of row r of frame t for this lane: t * HOP - 256 + 32 r + lane; outside [0, L) it reads as zero
+// (scipy boundary='zeros' and padded=True).  L < 2^31 (checked on the host).
 template <int HOP>
 struct Window2 {
   static constexpr int NR = HOP / 32;   // new rows per frame
   float a[16], b[16];
   float na[NR], nb[NR];                 // prefetched rows of the next frame
 
-  __device__ __forceinline__ void load_all(const float* __restrict__ xa, const float* __restrict__ xb, int64_t L,
-                                           int64_t t, int lane) {
-    const int64_t base = t * HOP - kN / 2 + lane;
+  __device__ __forceinline__ void load_all(const float* __restrict__ xa, const float* __restrict__ xb, int L, int t,
+                                           int lane) {
+    const int base = t * HOP - kN / 2 + lane;
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
-      a[r] = ld_sample(xa, L, base + 32 * r);
-      b[r] = ld_sample(xb, L, base + 32 * r);
+      const int i = base + 32 * r;
+      const bool ok = (unsigned)i < (unsigned)L;
+      a[r] = ok ? __ldg(xa + i) : 0.f;
+      b[r] = ok ? __ldg(xb + i) : 0.f;
     }
   }
   // issue the loads of the rows that frame t_next adds (rows 16-NR..15 of that frame)
-  __device__ __forceinline__ void prefetch(const float* __restrict__ xa, const float* __restrict__ xb, int64_t L,
-                                           int64_t t_next, int lane) {
-    const int64_t base = t_next * HOP - kN / 2 + lane + 32 * (16 - NR);
+  __device__ __forceinline__ void prefetch(const float* __restrict__ xa, const float* __restrict__ xb, int L,
+                                           int t_next, int lane) {
+    const int s0 = t_next * HOP + kN / 2 - HOP;   // first sample of the new hop
+    if (s0 >= 0 && s0 + HOP <= L) {               // warp-uniform: the whole hop is inside the signal
+      const float* pa = xa + s0 + lane;
+      const float* pb = xb + s0 + lane;
 #pragma unroll
-    for (int i = 0; i < NR; ++i) {
-      na[i] = ld_sample(xa, L, base + 32 * i);
-      nb[i] = ld_sample(xb, L, base + 32 * i);
+      for (int i = 0; i < NR; ++i) {
+        na[i] = __ldg(pa + 32 * i);
+        nb[i] = __ldg(pb + 32 * i);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        const int idx = s0 + lane + 32 * i;
+        const bool ok = (unsigned)idx < (unsigned)L;
+        na[i] = ok ? __ldg(xa + idx) : 0.f;
+        nb[i] = ok ? __ldg(xb + idx) : 0.f;
+      }
     }
   }
   __device__ __forceinline__ void advance() {
@@ -75,17 +97,31 @@ struct Window2 {
   }
 };
 
-__device__ __forceinline__ void load_window(float (&w)[16], const float* __restrict__ win, float scale, int lane) {
+// Window of this lane's 16 rows, times the lane sign the transform wants on its time-domain side.
+// The analysis scale 1/sum(w) = 2/N is NOT applied here: it is folded into whatever consumes the spectrum.
+__device__ __forceinline__ void load_window(float (&w)[16], const float* __restrict__ win, const Lane& ln) {
 #pragma unroll
-  for (int r = 0; r < 16; ++r) w[r] = win[32 * r + lane] * scale;
+  for (int r = 0; r < 16; ++r) w[r] = win[32 * r + ln.lane] * ln.sign;
 }
 
 // bin of lo[j] for this lane
 __device__ __forceinline__ int bin_lo(const Lane& ln, int j) { return ln.k1 + 16 * j + 128 * ln.h; }
 
+// This lane's 8 mask bits (+ Nyquist) of one frame: words 4h .. 4h+3 hold bins 128 h .. 128 h + 127.
+struct FrameBits {
+  uint32_t w[4], ny;
+  __device__ __forceinline__ void load(const uint32_t* __restrict__ bits_t, int h) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[i] = __ldg(bits_t + 4 * h + i);
+    ny = __ldg(bits_t + 8);
+  }
+  __device__ __forceinline__ bool bit(int j, int k1) const { return (w[j >> 1] >> (k1 + 16 * (j & 1))) & 1u; }
+};
+
 // ------------------------------------------------------------------------------------------
 // IBM bits
 // ------------------------------------------------------------------------------------------
+// Exact decision |S_int[k]| > |S_tgt[k]| of one frame in float64 (direct DFT; the whole warp cooperates).
 template <int N>
 __device__ __forceinline__ bool ibm_exact512(const float* __restrict__ tgt, const float* __restrict__ itf, int64_t L,
                                              int64_t start, int k, const Tables& tb, int lane) {
@@ -119,9 +155,22 @@ struct AmbList {
   unsigned int cap;
 };
 
+// With Z = FFT(tgt + i int):  |S_int|^2 - |S_tgt|^2 = -Re(Z[k] Z[N-k])  (S_tgt = (Z[k] + conj Z[N-k])/2,
+// S_int = -i (Z[k] - conj Z[N-k])/2), so the IBM bit is  Re(Z[k] Z[N-k]) < 0  - no unpacking needed.
+// c carries an error of at most delta (|Z[k]| + |Z[N-k]|) + delta^2 when each bin is off by at most delta, hence
+// "too close to call" is  c^2 <= delta^2 (4 (|Z[k]|^2 + |Z[N-k]|^2) + 2 delta^2).  Only a frame whose INPUT is
+// exactly zero (`live` false) is a true tie everywhere (bit 0, nothing to recheck); a bin that merely comes out
+// as 0 + 0i in float32 (cancellation at the rounding floor) is as uncertain as any other small value.
+__device__ __forceinline__ void ibm_decide(float2 z, float2 m, float d2, bool live, bool& bit, bool& amb) {
+  const float c = fmaf(z.x, m.x, -z.y * m.y);
+  const float s = fmaf(z.x, z.x, fmaf(z.y, z.y, fmaf(m.x, m.x, m.y * m.y)));
+  bit = c < 0.f;
+  amb = live && (c * c <= d2 * fmaf(4.f, s, 2.f * d2));
+}
+
 template <int HOP>
-__global__ void __launch_bounds__(kWarps * 32)
-k512_ibm(const float* __restrict__ tgt, const float* __restrict__ itf, int64_t L, int T, int frames_per_cta,
+__global__ void __launch_bounds__(kWarps * 32, AVZ_MINB_IBM)
+k512_ibm(const float* __restrict__ tgt, const float* __restrict__ itf, int L, int T, int frames_per_cta,
          uint32_t* __restrict__ ibm_bits, AmbList amb_list, float tol2, Tables tb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* sm = reinterpret_cast<float2*>(smem_raw) + (size_t)(threadIdx.x >> 5) * f512::kSmemComplex;
@@ -132,7 +181,7 @@ k512_ibm(const float* __restrict__ tgt, const float* __restrict__ itf, int64_t L
   const float* tg = tgt + (int64_t)b * L;
   const float* it = itf + (int64_t)b * L;
   float w[16];
-  load_window(w, tb.win, 2.0f / kN, lane);
+  load_window(w, tb.win, ln);
 
   const int c0 = blockIdx.x * frames_per_cta, c1 = min(T, c0 + frames_per_cta);
   const int per = (c1 - c0 + kWarps - 1) / kWarps;
@@ -141,6 +190,7 @@ k512_ibm(const float* __restrict__ tgt, const float* __restrict__ itf, int64_t L
 
   Window2<HOP> win;
   win.load_all(tg, it, L, ta, lane);
+#pragma unroll 1
   for (int t = ta; t < tb_; ++t) {
     if (t + 1 < tb_) win.prefetch(tg, it, L, t + 1, lane);
     float2 v[16];
@@ -152,47 +202,44 @@ k512_ibm(const float* __restrict__ tgt, const float* __restrict__ itf, int64_t L
     f512::forward(v, sm, ln);
     float2 mir[8];
     f512::mirror_of_low(v, mir, ln);
-    // float32 FFT error bound of one bin: delta = tol * sqrt(e2), e2 = sum |frame|^2 (= mean |Z[k]|^2).
-    // |pi - pt| <= 4 delta sqrt(mx) + 2 delta^2 is implied by diff^2 <= 32 delta^2 mx + 8 delta^4 (no sqrt).
+    // float32 FFT error bound of one bin: delta = tol * sqrt(e2)  (e2 = sum |frame|^2, so 512 e2 = sum |Z|^2
+    // and sqrt(e2) is the rms bin magnitude; the spectrum here is unscaled).
     const float d2 = tol2 * e2;
-    unsigned ballots[8], ambb[8];
-    unsigned tot = 0;
+    const bool live = e2 > 0.f;   // any non-zero input sample in either reference
+    unsigned ballots[8];
+    unsigned my_amb = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float2 St, Si;
-      unpack_pair(v[j], mir[j], St, Si);
-      const float pt = cabs2(St), pi = cabs2(Si);
-      const float mx = fmaxf(pt, pi), diff = pi - pt;
-      // exact zeros on both sides (silence) are a true tie, not an ambiguity
-      const bool amb = (mx > 0.f) && (diff * diff <= d2 * (32.f * mx + 8.f * d2));
-      ballots[j] = __ballot_sync(kFull, pi > pt);
-      ambb[j] = __ballot_sync(kFull, amb);
-      tot += __popc(ambb[j]);
+      bool bit, amb;
+      ibm_decide(v[j], mir[j], d2, live, bit, amb);
+      ballots[j] = __ballot_sync(kFull, bit);
+      my_amb |= amb ? (1u << j) : 0u;
     }
-    // Nyquist bin 256 = hi[0] of lane 0 (self-mirrored): S_tgt = Re, S_int = Im
-    unsigned ny, ny_amb;
-    {
-      const float pt = v[8].x * v[8].x, pi = v[8].y * v[8].y;
-      const float mx = fmaxf(pt, pi), diff = pi - pt;
-      const bool amb = (mx > 0.f) && (diff * diff <= d2 * (32.f * mx + 8.f * d2));
-      ny = __ballot_sync(kFull, pi > pt) & 1u;
-      ny_amb = __ballot_sync(kFull, amb) & 1u;
-      tot += ny_amb;
-    }
-    if (tot) {  // warp-uniform
-      unsigned base = 0;
-      if (lane == 0) base = atomicAdd(amb_list.count, tot);
-      base = __shfl_sync(kFull, base, 0);
-      const unsigned long long hdr = ((unsigned long long)b << 32) | ((unsigned long long)t << 9);
+    // Nyquist bin 256 = hi[0] of lane 0, its own mirror: same formula with m = z
+    bool ny_bit, ny_a;
+    ibm_decide(v[8], v[8], d2, live, ny_bit, ny_a);
+    const unsigned ny = __ballot_sync(kFull, ny_bit) & 1u;
+    if (lane == 0 && ny_a) my_amb |= 1u << 8;
+    if (__any_sync(kFull, my_amb != 0u)) {  // warp-uniform, taken for a minority of frames
+      const int cnt = __popc(my_amb);
+      int incl = cnt;                        // inclusive prefix sum over lanes
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if ((ambb[j] >> lane) & 1u) {
-          const unsigned slot = base + __popc(ambb[j] & ((1u << lane) - 1u));
-          if (slot < amb_list.cap) amb_list.entries[slot] = hdr | (unsigned)bin_lo(ln, j);
-        }
-        base += __popc(ambb[j]);
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += up;
       }
-      if (ny_amb && lane == 0 && base < amb_list.cap) amb_list.entries[base] = hdr | 256u;
+      const int tot = __shfl_sync(kFull, incl, 31);
+      unsigned base = 0;
+      if (lane == 31) base = atomicAdd(amb_list.count, (unsigned)tot);
+      base = __shfl_sync(kFull, base, 31) + (unsigned)(incl - cnt);
+      const unsigned long long hdr = ((unsigned long long)b << 32) | ((unsigned long long)t << 9);
+      unsigned m = my_amb;
+      while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        if (base < amb_list.cap) amb_list.entries[base] = hdr | (unsigned)(j == 8 ? 256 : bin_lo(ln, j));
+        ++base;
+      }
     }
     if (lane == 0) {
       uint32_t* o = ibm_bits + ((int64_t)b * T + t) * kFW;
@@ -245,8 +292,8 @@ k512_ibm_fixup(const float* __restrict__ tgt, const float* __restrict__ itf, int
 enum { W_BITS = 0, W_MASK = 1 };
 
 template <int HOP, int WMODE>
-__global__ void __launch_bounds__(kWarps * 32)
-k512_cov(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, const float* __restrict__ mask, int64_t L,
+__global__ void __launch_bounds__(kWarps * 32, AVZ_MINB_COV)
+k512_cov(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, const float* __restrict__ mask, int L,
          int T, int frames_per_cta, float sqrt_eps, float* __restrict__ part, Tables tb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* sm_all = reinterpret_cast<float2*>(smem_raw);
@@ -258,10 +305,10 @@ k512_cov(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, c
   const float* m0 = mix + (int64_t)b * 2 * L;
   const float* m1 = m0 + L;
   float w[16];
-  load_window(w, tb.win, 2.0f / kN, lane);
+  load_window(w, tb.win, ln);
 
   // accumulators of this lane's 8 low bins (+ Nyquist on lane 0): R00, R11, Re R01, Im R01, sum m.
-  // Sums are of the un-halved spectra (Y0' = 2 Y0, Y1' = 2 Y1): scaled by 1/4 when written.
+  // The spectra here are unscaled (x N/2) and un-halved (Y0' = 2 Y0): products are scaled by 1/N^2 at the end.
   float a00[8], a11[8], are[8], aim[8], am_[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) a00[j] = a11[j] = are[j] = aim[j] = am_[j] = 0.f;
@@ -274,23 +321,41 @@ k512_cov(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, c
   if (ta < tb_) {
     Window2<HOP> win;
     win.load_all(m0, m1, L, ta, lane);
+    // noise weights of this lane's bins, fetched one frame ahead
+    FrameBits nb;
+    float nmask[9];
+    const uint32_t* bw = (WMODE == W_BITS) ? ibm_bits + ((int64_t)b * T + ta) * kFW : nullptr;
+    const float* mk = (WMODE == W_MASK) ? mask + (int64_t)b * kF * T + ta : nullptr;
+    if (WMODE == W_BITS) {
+      nb.load(bw, ln.h);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) nmask[j] = __ldg(mk + (int64_t)bin_lo(ln, j) * T);
+      nmask[8] = __ldg(mk + (int64_t)256 * T);
+    }
+#pragma unroll 1
     for (int t = ta; t < tb_; ++t) {
-      if (t + 1 < tb_) win.prefetch(m0, m1, L, t + 1, lane);
-      // noise weights of this lane's bins
       float mw[8], mny;
       if (WMODE == W_BITS) {
-        const uint32_t* bw = ibm_bits + ((int64_t)b * T + t) * kFW;
-        uint32_t wd[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) wd[i] = __ldg(bw + 4 * ln.h + i);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) mw[j] = ((wd[j >> 1] >> (ln.k1 + 16 * (j & 1))) & 1u) ? 1.f : 0.f;
-        mny = (__ldg(bw + 8) & 1u) ? 1.f : 0.f;
+        for (int j = 0; j < 8; ++j) mw[j] = nb.bit(j, ln.k1) ? 1.f : 0.f;
+        mny = (nb.ny & 1u) ? 1.f : 0.f;
       } else {
-        const float* mk = mask + (int64_t)b * kF * T + t;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) mw[j] = 1.f - __ldg(mk + (int64_t)bin_lo(ln, j) * T);
-        mny = 1.f - __ldg(mk + (int64_t)256 * T);
+        for (int j = 0; j < 8; ++j) mw[j] = 1.f - nmask[j];
+        mny = 1.f - nmask[8];
+      }
+      if (t + 1 < tb_) {
+        win.prefetch(m0, m1, L, t + 1, lane);
+        if (WMODE == W_BITS) {
+          bw += kFW;
+          nb.load(bw, ln.h);
+        } else {
+          mk += 1;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) nmask[j] = __ldg(mk + (int64_t)bin_lo(ln, j) * T);
+          nmask[8] = __ldg(mk + (int64_t)256 * T);
+        }
       }
       float2 v[16];
       win.frame(v, w);
@@ -312,7 +377,7 @@ k512_cov(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, c
         a11[j] = fmaf(u0, y1.x, fmaf(u1, y1.y, a11[j]));
         am_[j] += m;
       }
-      {  // Nyquist (meaningful on lane 0 only): Y0 = Re hi[0], Y1 = Im hi[0]
+      {  // Nyquist (meaningful on lane 0 only): Y0 = Re hi[0], Y1 = Im hi[0] (not doubled)
         const float ms = (WMODE == W_MASK) ? mny + sqrt_eps : mny;
         n00 = fmaf(ms * v[8].x, v[8].x, n00);
         n11 = fmaf(ms * v[8].y, v[8].y, n11);
@@ -323,22 +388,23 @@ k512_cov(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, c
     }
   }
   // per-warp sums -> shared -> fixed-order CTA reduction -> partial buffer [B][chunks][5][kFP]
-  __syncthreads();  // every warp is done with its FFT scratch; reuse it
+  const float sc = 1.0f / ((float)kN * (float)kN);      // (2/N)^2 analysis scale x 1/4 for the un-halved products
+  const float sc_ny = 4.0f / ((float)kN * (float)kN);   // Nyquist values were not doubled
   float* s_acc = reinterpret_cast<float*>(sm_all + (size_t)kWarps * f512::kSmemComplex);  // [kWarps][5][kFP]
   float* mine = s_acc + (size_t)warp * 5 * kFP;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int k = bin_lo(ln, j);
-    mine[0 * kFP + k] = 0.25f * a00[j];
-    mine[1 * kFP + k] = 0.25f * a11[j];
-    mine[2 * kFP + k] = 0.25f * are[j];
-    mine[3 * kFP + k] = 0.25f * aim[j];
+    mine[0 * kFP + k] = sc * a00[j];
+    mine[1 * kFP + k] = sc * a11[j];
+    mine[2 * kFP + k] = sc * are[j];
+    mine[3 * kFP + k] = sc * aim[j];
     mine[4 * kFP + k] = am_[j];
   }
   if (lane == 0) {
-    mine[0 * kFP + 256] = n00;
-    mine[1 * kFP + 256] = n11;
-    mine[2 * kFP + 256] = nre;
+    mine[0 * kFP + 256] = sc_ny * n00;
+    mine[1 * kFP + 256] = sc_ny * n11;
+    mine[2 * kFP + 256] = sc_ny * nre;
     mine[3 * kFP + 256] = 0.f;
     mine[4 * kFP + 256] = nm;
   }
@@ -361,9 +427,9 @@ k512_cov(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, c
 enum { GAIN_NONE = 0, GAIN_BITS = 1, GAIN_FLOOR = 2, GAIN_MASK = 3 };
 
 template <int HOP>
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(kWarps * 32, AVZ_MINB_APPLY)
 k512_apply(const float* __restrict__ mix, const float2* __restrict__ wgt, const uint32_t* __restrict__ ibm_bits,
-           const float* __restrict__ mask, int gain_mode, float post_floor, int64_t L, int T, int blocks_per_cta,
+           const float* __restrict__ mask, int gain_mode, float post_floor, int L, int T, int blocks_per_cta,
            float* __restrict__ out, float* __restrict__ peak, Tables tb) {
   constexpr int R = kN / HOP;        // frames overlapping one hop-block
   constexpr int NR = HOP / 32;       // rows per hop-block
@@ -382,44 +448,43 @@ k512_apply(const float* __restrict__ mix, const float2* __restrict__ wgt, const 
   const int b = blockIdx.y;
   const float* m0 = mix + (int64_t)b * 2 * L;
   const float* m1 = m0 + L;
-  // S[k] = conj(w0) Y0 + conj(w1) Y1 = a[k] Z[k] + b[k] conj(Z[N-k]),  a = (conj w0 - i conj w1)/2, b = (conj w0 + i conj w1)/2
-  for (int k = threadIdx.x; k < kF; k += kWarps * 32) {
-    const float2 w0 = wgt[((int64_t)b * kF + k) * 2 + 0];
-    const float2 w1 = wgt[((int64_t)b * kF + k) * 2 + 1];
-    s_ab[k] = make_float4(0.5f * (w0.x - w1.y), 0.5f * (-w0.y - w1.x), 0.5f * (w0.x + w1.y), 0.5f * (-w0.y + w1.x));
+  // S[k] = conj(w0) Y0 + conj(w1) Y1 = a[k] Z[k] + b[k] conj(Z[N-k]),  a = (conj w0 - i conj w1)/2,
+  // b = (conj w0 + i conj w1)/2.  The transforms here are unscaled: the analysis scale 2/N and the synthesis
+  // factor (irfft's 1/N times sum(w) = N/2, i.e. 1/2) are folded into a and b: overall 1/N.
+  {
+    const float sc = 0.5f / (float)kN;
+    for (int k = threadIdx.x; k < kF; k += kWarps * 32) {
+      const float2 w0 = wgt[((int64_t)b * kF + k) * 2 + 0];
+      const float2 w1 = wgt[((int64_t)b * kF + k) * 2 + 1];
+      s_ab[k] = make_float4(sc * (w0.x - w1.y), sc * (-w0.y - w1.x), sc * (w0.x + w1.y), sc * (-w0.y + w1.x));
+    }
   }
   __syncthreads();
 
-  float wf[16];   // forward window (Hann * 2/N)
-  float wi[16];   // synthesis window: irfft * sum(w) * w = 0.5 * (unnormalised inverse) * w
-#pragma unroll
-  for (int r = 0; r < 16; ++r) {
-    const float h_ = tb.win[32 * r + lane];
-    wf[r] = h_ * (2.0f / kN);
-    wi[r] = 0.5f * h_;
-  }
+  float hw[16];   // Hann x lane sign: analysis and synthesis window (sign^2 = 1 in the normaliser)
+  load_window(hw, tb.win, ln);
   // 1 / sum over the R overlapping frames of w^2, for a block with all R frames present
   float inv_full[NR];
 #pragma unroll
   for (int r = 0; r < NR; ++r) {
     float s = 0.f;
 #pragma unroll
-    for (int q = 0; q < R; ++q) {
-      const float h_ = 2.f * wi[r + NR * q];
-      s = fmaf(h_, h_, s);
-    }
+    for (int q = 0; q < R; ++q) s = fmaf(hw[r + NR * q], hw[r + NR * q], s);
     inv_full[r] = 1.0f / s;
   }
 
   // Hop-blocks in extended coordinates: block g covers [g HOP, (g+1) HOP); the output is blocks
   // [R/2, R/2 + T - 1); block g sums frames g-R+1 .. g (those that exist).  This CTA owns [G0, G1), split
-  // into contiguous runs per warp.  Warp 0 recomputes the R-1 frames before G0 (warm-up); later warps start
-  // cold and their first R-1 blocks are completed at the end from the previous warp's open tail.
+  // into contiguous runs per warp.  Warp 0 recomputes the R-1 frames before G0 (warm-up) and gets a shorter
+  // run to balance that; later warps start cold and their first R-1 blocks are completed at the end from the
+  // previous warp's open tail.  Runs are at least R-1 blocks long so a head block only needs one tail.
   const int g_lo = R / 2, g_hi = R / 2 + T - 1;
   const int G0 = g_lo + blockIdx.x * blocks_per_cta, G1 = min(g_hi, G0 + blocks_per_cta);
-  // runs are at least R-1 blocks long so that a head block only ever needs the previous warp's tail
-  const int per = max(R - 1, (G1 - G0 + kWarps - 1) / kWarps);
-  const int ga = min(G1, G0 + warp * per), gb = min(G1, ga + per);
+  const int nblk = G1 - G0;
+  const int per = max(R - 1, (nblk + (R - 1) + kWarps - 1) / kWarps);   // frames per warp incl. warp 0's warm-up
+  const int first = max(min(nblk, R - 1), min(nblk, per - (R - 1)));    // warp 0's blocks
+  const int ga = (warp == 0) ? G0 : min(G1, G0 + first + (warp - 1) * per);
+  const int gb = (warp == 0) ? G0 + first : min(G1, ga + per);
   const int64_t out_len = (int64_t)(T - 1) * HOP;
   float* ob = out + (int64_t)b * out_len;
   float my_peak = 0.f;
@@ -431,9 +496,8 @@ k512_apply(const float* __restrict__ mix, const float2* __restrict__ wgt, const 
   for (int r = 0; r < 16; ++r) o[r] = 0.f;
 
   auto emit = [&](int g) {
-    // block g is complete in o[0..NR-1] (unless it is one of this warp's head blocks)
     const bool interior = (g >= R - 1) && (g <= T - 1);
-    const int64_t n0 = (int64_t)(g - g_lo) * HOP + lane;
+    float* op = ob + (int64_t)(g - g_lo) * HOP + lane;
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
       float val;
@@ -444,24 +508,17 @@ k512_apply(const float* __restrict__ mix, const float2* __restrict__ wgt, const 
 #pragma unroll
         for (int q = 0; q < R; ++q) {
           const int tq = g - q;
-          const float h_ = 2.f * wi[r + NR * q];
-          if (tq >= 0 && tq <= T - 1) nrm = fmaf(h_, h_, nrm);
+          if (tq >= 0 && tq <= T - 1) nrm = fmaf(hw[r + NR * q], hw[r + NR * q], nrm);
         }
         val = o[r] / (nrm > 1e-10f ? nrm : 1.0f);
       }
-      ob[n0 + 32 * r] = val;
+      op[32 * r] = val;
       my_peak = fmaxf(my_peak, fabsf(val));
     }
   };
-  auto shift = [&]() {
-#pragma unroll
-    for (int r = 0; r < TAIL; ++r) o[r] = o[r + NR];
-#pragma unroll
-    for (int r = TAIL; r < 16; ++r) o[r] = 0.f;
-  };
-  // after frame g has been added: close block g
+  // after frame g has been added: close block g (emit it, or park it if it still waits for a tail), shift
   auto close_block = [&](int g) {
-    if (g >= ga && g < gb) {
+    if (g >= ga) {
       if (cold && g - ga < n_head) {
         float* hd = s_head + ((size_t)warp * TAIL + (size_t)(g - ga) * NR) * 32 + lane;
 #pragma unroll
@@ -470,92 +527,113 @@ k512_apply(const float* __restrict__ mix, const float2* __restrict__ wgt, const 
         emit(g);
       }
     }
-    shift();
+#pragma unroll
+    for (int r = 0; r < TAIL; ++r) o[r] = o[r + NR];
+#pragma unroll
+    for (int r = TAIL; r < 16; ++r) o[r] = 0.f;
   };
 
   if (ga < gb) {
     const int t_first = cold ? ga : max(0, ga - (R - 1));
     Window2<HOP> win;
     if (t_first <= T - 1) win.load_all(m0, m1, L, t_first, lane);
-    float2 Sa[8], Sb[8];
-    float2 ny;
-
-    auto analyse = [&](int t, float2 (&S)[8], float& s_ny) {
-      // frame t: forward transform, beamform, post-filter -> S at this lane's low bins, Nyquist (lane 0)
-      float gj[8], gny;
+    // post-filter gains of the frame about to be analysed, fetched one frame ahead
+    FrameBits nb;
+    float nmask[9];
+    const uint32_t* bw = ibm_bits + ((int64_t)b * T + t_first) * kFW;
+    const float* mk = mask + (int64_t)b * kF * T + t_first;
+    auto fetch_gain = [&]() {
       if (gain_mode == GAIN_BITS) {
-        const uint32_t* bw = ibm_bits + ((int64_t)b * T + t) * kFW;
-        uint32_t wd[4];
+        nb.load(bw, ln.h);
+      } else if (gain_mode != GAIN_NONE) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) wd[i] = __ldg(bw + 4 * ln.h + i);
+        for (int j = 0; j < 8; ++j) nmask[j] = __ldg(mk + (int64_t)bin_lo(ln, j) * T);
+        nmask[8] = __ldg(mk + (int64_t)256 * T);
+      }
+    };
+    if (t_first <= T - 1) fetch_gain();
+
+    float2 Sa[8];
+    float ny_a = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) gj[j] = ((wd[j >> 1] >> (ln.k1 + 16 * (j & 1))) & 1u) ? 0.f : 1.f;
-        gny = (__ldg(bw + 8) & 1u) ? 0.f : 1.f;
-      } else if (gain_mode == GAIN_NONE) {
+    for (int j = 0; j < 8; ++j) Sa[j] = make_float2(0.f, 0.f);
+
+#pragma unroll 1
+    for (int g = t_first; g < gb; ++g) {
+      const bool is_first = ((g - t_first) & 1) == 0;
+      float2 S[8];
+      float s_ny = 0.f;
+      if (g <= T - 1) {
+        // ---- frame g: forward transform, beamform, post-filter -> S at this lane's low bins (+ Nyquist, lane 0)
+        float gj[8], gny;
+        if (gain_mode == GAIN_BITS) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) gj[j] = 1.f;
-        gny = 1.f;
-      } else {
-        const float* mk = mask + (int64_t)b * kF * T + t;
+          for (int j = 0; j < 8; ++j) gj[j] = nb.bit(j, ln.k1) ? 0.f : 1.f;   // 1 - noise mask
+          gny = (nb.ny & 1u) ? 0.f : 1.f;
+        } else if (gain_mode == GAIN_NONE) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gj[j] = 1.f;
+          gny = 1.f;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gj[j] = (gain_mode == GAIN_FLOOR) ? fmaxf(nmask[j], post_floor) : nmask[j];
+          gny = (gain_mode == GAIN_FLOOR) ? fmaxf(nmask[8], post_floor) : nmask[8];
+        }
+        if (g + 1 <= T - 1) {
+          win.prefetch(m0, m1, L, g + 1, lane);
+          bw += kFW;
+          mk += 1;
+          fetch_gain();
+        }
+        float2 v[16];
+        win.frame(v, hw);
+        f512::forward(v, sm, ln);
+        float2 mir[8];
+        f512::mirror_of_low(v, mir, ln);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float mv = __ldg(mk + (int64_t)bin_lo(ln, j) * T);
-          gj[j] = (gain_mode == GAIN_FLOOR) ? fmaxf(mv, post_floor) : mv;
+          const float4 ab = s_ab[bin_lo(ln, j)];
+          // a * z + b * conj(m)
+          const float sx = fmaf(ab.x, v[j].x, -ab.y * v[j].y) + fmaf(ab.z, mir[j].x, ab.w * mir[j].y);
+          const float sy = fmaf(ab.x, v[j].y, ab.y * v[j].x) + fmaf(ab.w, mir[j].x, -ab.z * mir[j].y);
+          S[j] = make_float2(sx * gj[j], sy * gj[j]);
         }
-        const float mv = __ldg(mk + (int64_t)256 * T);
-        gny = (gain_mode == GAIN_FLOOR) ? fmaxf(mv, post_floor) : mv;
-      }
-      float2 v[16];
-      win.frame(v, wf);
-      f512::forward(v, sm, ln);
-      float2 mir[8];
-      f512::mirror_of_low(v, mir, ln);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 ab = s_ab[bin_lo(ln, j)];
-        // a * z + b * conj(m)
-        float2 s;
-        s.x = fmaf(ab.x, v[j].x, -ab.y * v[j].y) + fmaf(ab.z, mir[j].x, ab.w * mir[j].y);
-        s.y = fmaf(ab.x, v[j].y, ab.y * v[j].x) + fmaf(ab.w, mir[j].x, -ab.z * mir[j].y);
-        S[j] = make_float2(s.x * gj[j], s.y * gj[j]);
-      }
-      const float4 abn = s_ab[256];
-      // Re(a z + b conj z), z = hi[0] (lane 0)
-      s_ny = gny * ((abn.x + abn.z) * v[8].x + (abn.w - abn.y) * v[8].y);
-    };
-
-    for (int g = t_first; g < gb; g += 2) {
-      const bool va = (g <= T - 1);
-      const bool vb = (g + 1 <= T - 1) && (g + 1 < gb);
-      if (va) {
-        if (g + 1 <= T - 1) win.prefetch(m0, m1, L, g + 1, lane);
-        analyse(g, Sa, ny.x);
+        const float4 abn = s_ab[256];
+        // Re(a z + b conj z), z = hi[0] of lane 0
+        s_ny = gny * ((abn.x + abn.z) * v[8].x + (abn.w - abn.y) * v[8].y);
         if (g + 1 <= T - 1) win.advance();
-      }
-      if (vb) {
-        if (g + 2 <= T - 1) win.prefetch(m0, m1, L, g + 2, lane);
-        analyse(g + 1, Sb, ny.y);
-        if (g + 2 <= T - 1) win.advance();
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) Sb[j] = make_float2(0.f, 0.f);
-        ny.y = 0.f;
+        for (int j = 0; j < 8; ++j) S[j] = make_float2(0.f, 0.f);
       }
-      if (va) {
-        float2 v[16];
-        f512::hermitian_pack(Sa, Sb, ny, v, ln);
-        f512::inverse(v, sm, ln);
+      if (is_first && g + 1 < gb) {   // hold it; the next frame shares its inverse transform
 #pragma unroll
-        for (int r = 0; r < 16; ++r) o[r] = fmaf(wi[r], v[r].x, o[r]);
-        close_block(g);
-        if (g + 1 < gb) {
+        for (int j = 0; j < 8; ++j) Sa[j] = S[j];
+        ny_a = s_ny;
+        continue;
+      }
+      // ---- one inverse transform for the pair (g-1, g), or for g alone when it is the last of the run
+      float2 v[16];
+      if (is_first) {
+        float2 Z0[8];
 #pragma unroll
-          for (int r = 0; r < 16; ++r) o[r] = fmaf(wi[r], v[r].y, o[r]);
-          close_block(g + 1);
-        }
-      } else {  // past the last frame: only flush the blocks still open
+        for (int j = 0; j < 8; ++j) Z0[j] = make_float2(0.f, 0.f);
+        f512::hermitian_pack(S, Z0, make_float2(s_ny, 0.f), v, ln);
+      } else {
+        f512::hermitian_pack(Sa, S, make_float2(ny_a, s_ny), v, ln);
+      }
+      f512::inverse(v, sm, ln);
+      if (!is_first) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) o[r] = fmaf(hw[r], v[r].x, o[r]);
+        close_block(g - 1);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) o[r] = fmaf(hw[r], v[r].y, o[r]);
         close_block(g);
-        if (g + 1 < gb) close_block(g + 1);
+      } else {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) o[r] = fmaf(hw[r], v[r].x, o[r]);
+        close_block(g);
       }
     }
   }
@@ -593,7 +671,7 @@ k512_apply(const float* __restrict__ mix, const float2* __restrict__ wgt, const 
 // host side
 // ------------------------------------------------------------------------------------------
 static int frames_per_cta(int B, int T, int sms) {
-  // aim for >= ~20 CTAs per SM (3 resident) so that the tail of the last wave is short
+  // aim for >= ~20 CTAs per SM so that the tail of the last wave is short
   int per_utt = (20 * sms + B - 1) / B;
   if (per_utt < 1) per_utt = 1;
   int fpc = (T + per_utt - 1) / per_utt;
@@ -620,7 +698,8 @@ int64_t ws_bytes512(int B, int T) {
 }
 
 static float ibm_tol2() {
-  // (relative float32 FFT error bound)^2; AVZ_IBM_TOL overrides the bound for experiments
+  // (relative float32 FFT error bound)^2, relative to the rms bin magnitude of the frame; AVZ_IBM_TOL overrides
+  // the bound for experiments.  Measured worst case of this transform: see DESIGN.md.
   static const float t2 = [] {
     double tol = 1e-6;
     if (const char* e = getenv("AVZ_IBM_TOL")) tol = atof(e);
@@ -635,6 +714,7 @@ int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const f
   Tables tb;
   int rc = tables_for(kN, &tb);
   if (rc) return rc;
+  if (L >= (1ll << 30)) return set_error(AVZ_EINVAL, "L=%lld too long for the 512-point fast path", (long long)L);
   const int T = (int)avz_num_frames(L, kN, HOP);
   const int fpc = frames_per_cta(B, T, num_sms());
   const int chunks = (T + fpc - 1) / fpc;
@@ -649,7 +729,7 @@ int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const f
     al.cap = amb_cap(B, T);
     AVZ_CUDA_OK(cudaMemsetAsync(al.count, 0, 16, st));
     AVZ_CUDA_OK(cudaFuncSetAttribute(k512_ibm<HOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
-    k512_ibm<HOP><<<grid, kWarps * 32, smem_fft, st>>>(tgt, itf, L, T, fpc, ibm_bits, al, ibm_tol2(), tb);
+    k512_ibm<HOP><<<grid, kWarps * 32, smem_fft, st>>>(tgt, itf, (int)L, T, fpc, ibm_bits, al, ibm_tol2(), tb);
     AVZ_LAUNCH_OK("k512_ibm");
     k512_ibm_fixup<<<num_sms() * 8, 256, 0, st>>>(tgt, itf, L, T, HOP, B, ibm_bits, al, tb);
     AVZ_LAUNCH_OK("k512_ibm_fixup");
@@ -657,10 +737,10 @@ int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const f
   const size_t smem_cov = smem_fft + (size_t)kWarps * 5 * kFP * sizeof(float);
   if (mask == nullptr) {
     AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov<HOP, W_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
-    k512_cov<HOP, W_BITS><<<grid, kWarps * 32, smem_cov, st>>>(mix, ibm_bits, nullptr, L, T, fpc, 0.f, part, tb);
+    k512_cov<HOP, W_BITS><<<grid, kWarps * 32, smem_cov, st>>>(mix, ibm_bits, nullptr, (int)L, T, fpc, 0.f, part, tb);
   } else {
     AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov<HOP, W_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
-    k512_cov<HOP, W_MASK><<<grid, kWarps * 32, smem_cov, st>>>(mix, nullptr, mask, L, T, fpc, sqrt_eps, part, tb);
+    k512_cov<HOP, W_MASK><<<grid, kWarps * 32, smem_cov, st>>>(mix, nullptr, mask, (int)L, T, fpc, sqrt_eps, part, tb);
   }
   AVZ_LAUNCH_OK("k512_cov");
   return AVZ_OK;
@@ -672,6 +752,7 @@ int launch_apply(const float* mix, const float* w, const uint32_t* ibm_bits, con
   Tables tb;
   int rc = tables_for(kN, &tb);
   if (rc) return rc;
+  if (L >= (1ll << 30)) return set_error(AVZ_EINVAL, "L=%lld too long for the 512-point fast path", (long long)L);
   const int T = (int)avz_num_frames(L, kN, HOP);
   const int n_blocks = T - 1;
   if (n_blocks <= 0) return AVZ_OK;
@@ -683,7 +764,7 @@ int launch_apply(const float* mix, const float* w, const uint32_t* ibm_bits, con
   AVZ_CUDA_OK(cudaFuncSetAttribute(k512_apply<HOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(chunks, B);
   k512_apply<HOP><<<grid, kWarps * 32, smem, st>>>(mix, reinterpret_cast<const float2*>(w), ibm_bits, mask, gain_mode,
-                                                   post_floor, L, T, bpc, out, peak, tb);
+                                                   post_floor, (int)L, T, bpc, out, peak, tb);
   AVZ_LAUNCH_OK("k512_apply");
   return AVZ_OK;
 }
