@@ -137,6 +137,10 @@ AVZ_API int avz_mvdr_apply_f32(const float* mix, const float* w, const uint32_t*
  * a, b [n] complex64 -> out [n] f32 = (|a| > |b|) ? 1 : 0, compared exactly (float64 squares). */
 AVZ_API int avz_mag_greater_f32(const float* a, const float* b, int64_t n, float* out, void* stream);
 
+/* ---- soft (ideal-ratio) post-filter mask: oracle_reverb.py:143-147.
+ * s_tgt, s_int [n] complex64 -> out [n] f32 = sqrt(|s_tgt|^2 / (|s_tgt|^2 + |s_int|^2 + 1e-10)). */
+AVZ_API int avz_irm_f32(const float* s_tgt, const float* s_int, int64_t n, float* out, void* stream);
+
 /* ---- geometric phase mask: masked_mvdr.py:37-46.  Y [B,2,F,T] -> mask [B,F,T] in {0.01, 1}. */
 AVZ_API int avz_geometric_mask_f32(const float* Y, int B, int F, int T, float* mask, void* stream);
 

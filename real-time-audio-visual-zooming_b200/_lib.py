@@ -58,6 +58,7 @@ SIGNATURES = {
     "avz_beamform_f32": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "avz_mvdr_apply_f32": (_i, [_p, _p, _p, _p, _i, _l, _i, _i, C.POINTER(AvzMvdrCfg), _p, _p, _p]),
     "avz_mag_greater_f32": (_i, [_p, _p, _l, _p, _p]),
+    "avz_irm_f32": (_i, [_p, _p, _l, _p, _p]),
     "avz_geometric_mask_f32": (_i, [_p, _i, _i, _i, _p, _p]),
     "avz_ibm_unpack_f32": (_i, [_p, _i, _i, _i, _p, _p]),
     "avz_features_f32": (_i, [_p, _i, _i, _i, _i, _p, _p]),

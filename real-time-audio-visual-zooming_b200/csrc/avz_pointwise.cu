@@ -80,6 +80,14 @@ __global__ void k_mag_greater(const float2* __restrict__ a, const float2* __rest
   }
 }
 
+// oracle_reverb.py:143-147: soft mask sqrt(Pt / (Pt + Pi + 1e-10)), P = |S|^2.
+__global__ void k_irm(const float2* __restrict__ a, const float2* __restrict__ b, int64_t n, float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float pt = cabs2(a[i]), pi = cabs2(b[i]);
+    out[i] = sqrtf(pt / (pt + pi + 1e-10f));
+  }
+}
+
 // masked_mvdr.py:37-46: 1 where |angle(Y0) - angle(Y1)| > 0 else 0.01.  The difference of two atan2 values
 // is zero exactly when the two angles are the same float64 number; float32 inputs are promoted first.
 __global__ void k_geometric_mask(const float2* __restrict__ Y, int F, int T, int64_t n_per_b, float* __restrict__ mask) {
@@ -251,6 +259,14 @@ int avz_mag_greater_f32(const float* a, const float* b, int64_t n, float* out, v
   k_mag_greater<<<grid1d(n, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float2*>(a), reinterpret_cast<const float2*>(b), n, out);
   AVZ_LAUNCH_OK("k_mag_greater");
+  return AVZ_OK;
+}
+
+int avz_irm_f32(const float* s_tgt, const float* s_int, int64_t n, float* out, void* stream) {
+  if (!s_tgt || !s_int || !out || n <= 0) return set_error(AVZ_EINVAL, "avz_irm_f32: bad argument");
+  k_irm<<<grid1d(n, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float2*>(s_tgt), reinterpret_cast<const float2*>(s_int), n, out);
+  AVZ_LAUNCH_OK("k_irm");
   return AVZ_OK;
 }
 

@@ -21,7 +21,7 @@ __all__ = [
     "num_frames", "stft", "istft", "ibm", "ibm_target_label", "geometric_mask", "masked_covariance",
     "steering_vectors", "mvdr_weights", "beamform", "logmag_ipd", "physics_features", "sir_scores",
     "ibm_covariance", "wave_masked_covariance", "mvdr_apply", "peak_normalise", "unpack_ibm",
-    "oracle_mask_mvdr", "learned_mask_mvdr", "covariance_to_matrix", "ibm_exact_bits",
+    "oracle_mask_mvdr", "learned_mask_mvdr", "covariance_to_matrix", "ibm_exact_bits", "irm", "wave_features",
 ]
 
 
@@ -136,6 +136,18 @@ def ibm(S_tgt, S_int):
 def ibm_target_label(S_tgt, S_int):
     """Training-label polarity: (|S_t| > |S_i|) as float  (model_training.py:90)."""
     return _mag_greater(S_tgt, S_int)
+
+
+def irm(S_tgt, S_int):
+    """Soft post-filter mask sqrt(Pt / (Pt + Pi + 1e-10))  (oracle_reverb.py:143-147)."""
+    io = _Io()
+    a = io.take(S_tgt, torch.complex64)
+    b = io.take(S_int, torch.complex64)
+    if a.shape != b.shape:
+        raise ValueError("spectra differ in shape")
+    out = torch.empty(a.shape, dtype=torch.float32, device=a.device)
+    _lib.check(_lib.load().avz_irm_f32(_ptr(a), _ptr(b), a.numel(), _ptr(out), _stream()), "avz_irm_f32")
+    return io.give(out)
 
 
 def geometric_mask(Y):
@@ -269,6 +281,24 @@ def logmag_ipd(Y, wrapped: bool = False):
 def physics_features(Y):
     """[logmag, sin ipd, cos ipd, k/(F-1)] NHWC  (Final_pipeline/src/inference.py:117-128) -> (..., F, T, 4)."""
     return _features(Y, _lib.FEAT_PHYSICS_NHWC)
+
+
+def wave_features(mix, n_fft: int = 1024, hop: int = 512, mode: str = "logmag_ipd"):
+    """Features straight from the waveform, STFT fused (no spectrum written): full_audio.../inference.py:90-94.
+    mix (..., 2, L) -> (..., 2, F, T) f32 ('logmag_ipd', 'logmag_ipd_wrapped') or (..., F, T, 4) ('physics')."""
+    io = _Io()
+    mix = io.take(mix, torch.float32)
+    lead = mix.shape[:-2]
+    B = int(np.prod(lead)) if lead else 1
+    L = mix.shape[-1]
+    F, T = n_fft // 2 + 1, num_frames(L, n_fft, hop)
+    m = {"logmag_ipd": _lib.FEAT_LOGMAG_IPD, "logmag_ipd_wrapped": _lib.FEAT_LOGMAG_IPD_WRAPPED,
+         "physics": _lib.FEAT_PHYSICS_NHWC}[mode]
+    shape = (B, F, T, 4) if m == _lib.FEAT_PHYSICS_NHWC else (B, 2, F, T)
+    X = torch.empty(shape, dtype=torch.float32, device=mix.device)
+    _lib.check(_lib.load().avz_wave_features_f32(_ptr(mix), B, L, n_fft, hop, m, _ptr(X), _stream()),
+               "avz_wave_features_f32")
+    return io.give(X.reshape(*lead, *shape[1:]))
 
 
 def sir_scores(est, tgt, itf):

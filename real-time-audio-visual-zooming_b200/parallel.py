@@ -1,0 +1,40 @@
+"""Multi-GPU plumbing: utterances are independent, so ranks take contiguous blocks of the utterance index and the
+hot path moves no data between GPUs.  The one collective is an all-gather of the per-utterance score rows
+(SURVEY.md 8-E).  Works with the `nccl` backend on GPUs and with `gloo` on CPU tensors (used by the tests)."""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous block [lo, hi) of rank `rank`: sizes differ by at most one, earlier ranks get the larger blocks."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_scores(local: torch.Tensor, n_total: int) -> torch.Tensor:
+    """All-gather score rows [n_local, K] of every rank into [n_total, K], in utterance order on every rank."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return local
+    world, rank = dist.get_world_size(), dist.get_rank()
+    K = local.shape[1]
+    base, rem = divmod(n_total, world)
+    if rem == 0:
+        out = torch.empty((n_total, K), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous())
+        return out
+    # ragged shards: pad every block to the largest size, gather, then cut the padding out
+    big = base + 1
+    padded = torch.zeros((big, K), dtype=local.dtype, device=local.device)
+    padded[:local.shape[0]] = local
+    buf = torch.empty((world * big, K), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(buf, padded)
+    parts = []
+    for r in range(world):
+        lo, hi = shard_range(n_total, r, world)
+        parts.append(buf[r * big:r * big + (hi - lo)])
+    return torch.cat(parts, dim=0)
