@@ -133,6 +133,19 @@ AVZ_API int avz_beamform_f32(const float* w, const float* Y, int B, int F, int T
 AVZ_API int avz_mvdr_apply_f32(const float* mix, const float* w, const uint32_t* ibm_bits, const float* mask, int B, int64_t L,
                        int n_fft, int hop, const AvzMvdrCfg* cfg, float* out, float* peak, void* stream);
 
+/* ---- "kept spectrum" variants of the two fused passes (n_fft 512, hop 128 / 256).
+ * The path is fp32-issue-bound, not HBM-bound, so pass A can keep the packed two-mic spectrum of
+ * every frame (4096 B per frame in `spec`, avz_spec_ws_bytes() bytes in total; 0 = not supported for this shape) and
+ * pass B then skips its forward transform: ~25 % fewer instructions for 64 B/sample of otherwise idle HBM bandwidth.
+ * Results are bit-identical to the recomputing variants (same transform, same arithmetic order). */
+AVZ_API int64_t avz_spec_ws_bytes(int B, int64_t L, int n_fft, int hop);
+AVZ_API int avz_ibm_cov_keep_f32(const float* mix, const float* tgt, const float* itf, int B, int64_t L, int n_fft, int hop,
+                         float norm_eps, uint32_t* ibm_bits, float* R, float* msum, void* ws, void* spec, void* stream);
+AVZ_API int avz_wave_mask_cov_keep_f32(const float* mix, const float* mask, int B, int64_t L, int n_fft, int hop,
+                               float sqrt_eps, float norm_eps, float* R, float* msum, void* ws, void* spec, void* stream);
+AVZ_API int avz_mvdr_apply_kept_f32(const void* spec, const float* w, const uint32_t* ibm_bits, const float* mask, int B,
+                            int64_t L, int n_fft, int hop, const AvzMvdrCfg* cfg, float* out, float* peak, void* stream);
+
 /* ---- IBM from given spectra: oracle_debug.py:49-53 (noise polarity) / model_training.py:90 (target polarity).
  * a, b [n] complex64 -> out [n] f32 = (|a| > |b|) ? 1 : 0, compared exactly (float64 squares). */
 AVZ_API int avz_mag_greater_f32(const float* a, const float* b, int64_t n, float* out, void* stream);

@@ -153,6 +153,44 @@ __device__ __forceinline__ void unpack_pair(float2 zk, float2 zm, float2& A, flo
   B = make_float2(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x));  // (zm.x - zk.x): DC/Nyquist give +0, like rfft
 }
 
+// ------------------------------------------------------------------------------------------
+// TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers: asynchronous global -> shared staging of
+// contiguous 16-byte-aligned blocks, completion signalled as transaction bytes on an mbarrier.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+}
+// make barrier initialisation visible to the async proxy
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// order this thread's generic-proxy accesses to shared memory before later async-proxy (TMA) accesses
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy of `bytes` (multiple of 16; both addresses 16-byte aligned)
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// wait until the phase with the given parity has completed; traps instead of hanging if it never does
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (spin > (1u << 26)) __trap();
+  }
+}
+
 // log-magnitude + inter-channel phase difference of one TF bin (full_audio.../inference.py:91-94):
 // np.abs is hypot; np.log / np.angle run in float64 there and float32 here (far inside the 1e-4 budget).
 __device__ __forceinline__ void feature_values(float2 y0, float2 y1, float& logmag, float& ipd) {

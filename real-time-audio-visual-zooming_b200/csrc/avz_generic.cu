@@ -21,10 +21,10 @@ int launch_ibm_exact(const float* tgt, const float* itf, int B, int64_t L, int h
                      cudaStream_t st);
 template <int HOP>
 int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const float* mask, int B, int64_t L,
-                   float sqrt_eps, uint32_t* ibm_bits, float* part, int* chunks_out, cudaStream_t st);
+                   float sqrt_eps, uint32_t* ibm_bits, float* part, int* chunks_out, void* spec, cudaStream_t st);
 template <int HOP>
-int launch_apply(const float* mix, const float* w, const uint32_t* ibm_bits, const float* mask, int gain_mode,
-                 float post_floor, int B, int64_t L, float* out, float* peak, cudaStream_t st);
+int launch_apply(const float* mix, const void* spec, const float* w, const uint32_t* ibm_bits, const float* mask,
+                 int gain_mode, float post_floor, int B, int64_t L, float* out, float* peak, cudaStream_t st);
 }  // namespace o512
 
 // The register-resident 512-point path serves n_fft 512 with hop 128 / 256 unless AVZ_FORCE_GENERIC=1
@@ -444,8 +444,30 @@ __global__ void k_peak_normalise(float* __restrict__ x, int64_t n, const float* 
   const int b = blockIdx.y;
   const float den = peak[b] + peak_eps;  // true division, like `s_out /= np.max(np.abs(s_out))`: the peak maps to 1.0
   float* xb = x + (int64_t)b * n;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    xb[i] = __fdiv_rn(xb[i], den);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(xb) & 15) == 0) {
+    // 16-byte accesses, four independent loads in flight per thread (the kernel is pure HBM streaming)
+    float4* x4 = reinterpret_cast<float4*>(xb);
+    const int64_t n4 = n >> 2;
+    int64_t i = tid;
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = x4[i + u * stride];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        v[u] = make_float4(__fdiv_rn(v[u].x, den), __fdiv_rn(v[u].y, den), __fdiv_rn(v[u].z, den), __fdiv_rn(v[u].w, den));
+        x4[i + u * stride] = v[u];
+      }
+    }
+    for (; i < n4; i += stride) {
+      float4 v = x4[i];
+      x4[i] = make_float4(__fdiv_rn(v.x, den), __fdiv_rn(v.y, den), __fdiv_rn(v.z, den), __fdiv_rn(v.w, den));
+    }
+  } else {
+    for (int64_t i = tid; i < n; i += stride) xb[i] = __fdiv_rn(xb[i], den);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -512,10 +534,11 @@ static int launch_cov(const float* mix, const float* tgt, const float* itf, cons
 // fast path: IBM + covariance (or mask covariance) for n_fft 512, then the shared finalize kernel
 static int launch_cov512(const float* mix, const float* tgt, const float* itf, const float* mask, int B, int64_t L,
                          int hop, float sqrt_eps, float norm_eps, uint32_t* ibm_bits, float* R, float* msum, void* ws,
-                         cudaStream_t st) {
+                         void* spec, cudaStream_t st) {
   int chunks = 0;
-  int rc = (hop == 128) ? o512::launch_ibm_cov<128>(mix, tgt, itf, mask, B, L, sqrt_eps, ibm_bits, (float*)ws, &chunks, st)
-                        : o512::launch_ibm_cov<256>(mix, tgt, itf, mask, B, L, sqrt_eps, ibm_bits, (float*)ws, &chunks, st);
+  int rc = (hop == 128)
+               ? o512::launch_ibm_cov<128>(mix, tgt, itf, mask, B, L, sqrt_eps, ibm_bits, (float*)ws, &chunks, spec, st)
+               : o512::launch_ibm_cov<256>(mix, tgt, itf, mask, B, L, sqrt_eps, ibm_bits, (float*)ws, &chunks, spec, st);
   if (rc) return rc;
   const int F = 257;
   k_cov_finalize<<<(B * F + 255) / 256, 256, 0, st>>>((const float*)ws, B, F, Geo<512>::FP, chunks, norm_eps,
@@ -578,8 +601,9 @@ int avz_istft_f32(const float* S, int B, int T, int n_fft, int hop, float* x, fl
 
 int avz_peak_normalise_f32(float* x, int B, int64_t n, const float* peak, float peak_eps, void* stream) {
   if (!x || !peak || B <= 0 || n <= 0) return set_error(AVZ_EINVAL, "avz_peak_normalise_f32: bad argument");
-  int gx = (int)((n + 1023) / 1024);
+  int gx = (int)((n / 4 + 1023) / 1024);   // ~4 float4 per thread
   if (gx > 64) gx = 64;
+  if (gx < 1) gx = 1;
   k_peak_normalise<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(x, n, peak, peak_eps);
   AVZ_LAUNCH_OK("k_peak_normalise");
   return AVZ_OK;
@@ -611,7 +635,8 @@ int avz_ibm_cov_f32(const float* mix, const float* tgt, const float* itf, int B,
   int rc = check_fft_args(n_fft, hop, L);
   if (rc) return rc;
   if (use_opt512(n_fft, hop))
-    return launch_cov512(mix, tgt, itf, nullptr, B, L, hop, 0.f, norm_eps, ibm_bits, R, msum, ws, (cudaStream_t)stream);
+    return launch_cov512(mix, tgt, itf, nullptr, B, L, hop, 0.f, norm_eps, ibm_bits, R, msum, ws, nullptr,
+                         (cudaStream_t)stream);
   AVZ_DISPATCH_N(n_fft, (launch_cov<N_, COV_IBM>(mix, tgt, itf, nullptr, B, L, hop, 0.f, norm_eps, ibm_bits, R, msum,
                                                  ws, (cudaStream_t)stream)));
 }
@@ -632,10 +657,65 @@ int avz_wave_mask_cov_f32(const float* mix, const float* mask, int B, int64_t L,
   int rc = check_fft_args(n_fft, hop, L);
   if (rc) return rc;
   if (use_opt512(n_fft, hop))
-    return launch_cov512(mix, nullptr, nullptr, mask, B, L, hop, sqrt_eps, norm_eps, nullptr, R, msum, ws,
+    return launch_cov512(mix, nullptr, nullptr, mask, B, L, hop, sqrt_eps, norm_eps, nullptr, R, msum, ws, nullptr,
                          (cudaStream_t)stream);
   AVZ_DISPATCH_N(n_fft, (launch_cov<N_, COV_MASK>(mix, nullptr, nullptr, mask, B, L, hop, sqrt_eps, norm_eps, nullptr,
                                                   R, msum, ws, (cudaStream_t)stream)));
+}
+
+// ---- "kept spectrum" variants of the fused passes (n_fft 512 fast path only) ---------------------------------
+int64_t avz_spec_ws_bytes(int B, int64_t L, int n_fft, int hop) {
+  if (B <= 0 || check_fft_args(n_fft, hop, L) || !use_opt512(n_fft, hop)) return 0;
+  return (int64_t)B * avz_num_frames(L, n_fft, hop) * 4096;
+}
+
+int avz_ibm_cov_keep_f32(const float* mix, const float* tgt, const float* itf, int B, int64_t L, int n_fft, int hop,
+                         float norm_eps, uint32_t* ibm_bits, float* R, float* msum, void* ws, void* spec, void* stream) {
+  if (!mix || !tgt || !itf || !ibm_bits || !R || !msum || !ws || !spec || B <= 0)
+    return set_error(AVZ_EINVAL, "avz_ibm_cov_keep_f32: null pointer or empty batch");
+  int rc = check_fft_args(n_fft, hop, L);
+  if (rc) return rc;
+  if (!use_opt512(n_fft, hop)) return set_error(AVZ_EINVAL, "avz_ibm_cov_keep_f32: n_fft 512, hop 128/256 only");
+  return launch_cov512(mix, tgt, itf, nullptr, B, L, hop, 0.f, norm_eps, ibm_bits, R, msum, ws, spec,
+                       (cudaStream_t)stream);
+}
+
+int avz_wave_mask_cov_keep_f32(const float* mix, const float* mask, int B, int64_t L, int n_fft, int hop, float sqrt_eps,
+                               float norm_eps, float* R, float* msum, void* ws, void* spec, void* stream) {
+  if (!mix || !mask || !R || !msum || !ws || !spec || B <= 0)
+    return set_error(AVZ_EINVAL, "avz_wave_mask_cov_keep_f32: null pointer or empty batch");
+  int rc = check_fft_args(n_fft, hop, L);
+  if (rc) return rc;
+  if (!use_opt512(n_fft, hop)) return set_error(AVZ_EINVAL, "avz_wave_mask_cov_keep_f32: n_fft 512, hop 128/256 only");
+  return launch_cov512(mix, nullptr, nullptr, mask, B, L, hop, sqrt_eps, norm_eps, nullptr, R, msum, ws, spec,
+                       (cudaStream_t)stream);
+}
+
+int avz_mvdr_apply_kept_f32(const void* spec, const float* w, const uint32_t* ibm_bits, const float* mask, int B,
+                            int64_t L, int n_fft, int hop, const AvzMvdrCfg* cfg, float* out, float* peak, void* stream) {
+  if (!spec || !w || !cfg || !out || B <= 0)
+    return set_error(AVZ_EINVAL, "avz_mvdr_apply_kept_f32: null pointer or empty batch");
+  int rc = check_fft_args(n_fft, hop, L);
+  if (rc) return rc;
+  if (!use_opt512(n_fft, hop)) return set_error(AVZ_EINVAL, "avz_mvdr_apply_kept_f32: n_fft 512, hop 128/256 only");
+  int gain = GAIN_NONE;
+  switch (cfg->post_mode) {
+    case AVZ_POST_NONE: gain = GAIN_NONE; break;
+    case AVZ_POST_ONE_MINUS_NOISE:
+      if (!ibm_bits) return set_error(AVZ_EINVAL, "AVZ_POST_ONE_MINUS_NOISE needs ibm_bits");
+      gain = GAIN_BITS;
+      break;
+    case AVZ_POST_FLOOR:
+    case AVZ_POST_MASK:
+      if (!mask) return set_error(AVZ_EINVAL, "AVZ_POST_FLOOR / AVZ_POST_MASK need a float mask");
+      gain = cfg->post_mode == AVZ_POST_FLOOR ? GAIN_FLOOR : GAIN_MASK;
+      break;
+    default: return set_error(AVZ_EINVAL, "post_mode=%d unknown", cfg->post_mode);
+  }
+  return (hop == 128) ? o512::launch_apply<128>(nullptr, spec, w, ibm_bits, mask, gain, cfg->post_floor, B, L, out, peak,
+                                                (cudaStream_t)stream)
+                      : o512::launch_apply<256>(nullptr, spec, w, ibm_bits, mask, gain, cfg->post_floor, B, L, out, peak,
+                                                (cudaStream_t)stream);
 }
 
 int avz_mvdr_apply_f32(const float* mix, const float* w, const uint32_t* ibm_bits, const float* mask, int B, int64_t L,
@@ -659,9 +739,9 @@ int avz_mvdr_apply_f32(const float* mix, const float* w, const uint32_t* ibm_bit
   }
   const int T = (int)avz_num_frames(L, n_fft, hop);
   if (use_opt512(n_fft, hop)) {
-    return (hop == 128) ? o512::launch_apply<128>(mix, w, ibm_bits, mask, gain, cfg->post_floor, B, L, out, peak,
+    return (hop == 128) ? o512::launch_apply<128>(mix, nullptr, w, ibm_bits, mask, gain, cfg->post_floor, B, L, out, peak,
                                                   (cudaStream_t)stream)
-                        : o512::launch_apply<256>(mix, w, ibm_bits, mask, gain, cfg->post_floor, B, L, out, peak,
+                        : o512::launch_apply<256>(mix, nullptr, w, ibm_bits, mask, gain, cfg->post_floor, B, L, out, peak,
                                                   (cudaStream_t)stream);
   }
   AVZ_DISPATCH_N(n_fft, (launch_synth<N_, SRC_MIX>(mix, nullptr, w, ibm_bits, mask, gain, cfg->post_floor, B, L, T, hop,

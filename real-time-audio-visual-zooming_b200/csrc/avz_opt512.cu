@@ -35,6 +35,9 @@ constexpr int kWarps = 4;    // warps per CTA
 #ifndef AVZ_MINB_APPLY
 #define AVZ_MINB_APPLY 2
 #endif
+#ifndef AVZ_MINB_APPLY_KEPT
+#define AVZ_MINB_APPLY_KEPT 3
+#endif
 
 // Sliding window of raw samples of two signals (16 rows of 32 lanes = one 512-sample frame each).
 // Sample index of row r of frame t for this lane: t * HOP - 256 + 32 r + lane; outside [0, L) it reads as zero
@@ -172,7 +175,7 @@ template <int HOP>
 __global__ void __launch_bounds__(kWarps * 32, AVZ_MINB_IBM)
 k512_ibm(const float* __restrict__ tgt, const float* __restrict__ itf, int L, int T, int frames_per_cta,
          uint32_t* __restrict__ ibm_bits, AmbList amb_list, float tol2, Tables tb) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   float2* sm = reinterpret_cast<float2*>(smem_raw) + (size_t)(threadIdx.x >> 5) * f512::kSmemComplex;
   Lane ln;
   ln.init(tb.tw);
@@ -291,11 +294,15 @@ k512_ibm_fixup(const float* __restrict__ tgt, const float* __restrict__ itf, int
 // ------------------------------------------------------------------------------------------
 enum { W_BITS = 0, W_MASK = 1 };
 
+// `spec` (optional): the packed two-mic spectrum of every frame is kept for pass B, so that pass B does not repeat
+// the forward transform: [B][T][8][32] float4 = (lo[i].x, lo[i].y, mir[i].x, mir[i].y) of lane l (lane 0's i = 0
+// slot carries (DC, Nyquist): its mirror is itself).  Each store instruction writes 512 contiguous bytes.
+// This trades 64 B/sample of spare HBM bandwidth for ~30 % fewer instructions on an issue-bound path.
 template <int HOP, int WMODE>
 __global__ void __launch_bounds__(kWarps * 32, AVZ_MINB_COV)
 k512_cov(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, const float* __restrict__ mask, int L,
-         int T, int frames_per_cta, float sqrt_eps, float* __restrict__ part, Tables tb) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+         int T, int frames_per_cta, float sqrt_eps, float* __restrict__ part, float4* __restrict__ spec, Tables tb) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   float2* sm_all = reinterpret_cast<float2*>(smem_raw);
   float2* sm = sm_all + (size_t)(threadIdx.x >> 5) * f512::kSmemComplex;
   Lane ln;
@@ -362,6 +369,18 @@ k512_cov(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, c
       f512::forward(v, sm, ln);
       float2 mir[8];
       f512::mirror_of_low(v, mir, ln);
+      if (spec != nullptr) {
+        float4* sp = spec + ((int64_t)b * T + t) * 256 + lane;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 q = make_float4(v[j].x, v[j].y, mir[j].x, mir[j].y);
+          if (j == 0 && lane == 0) {  // (DC, Nyquist)
+            q.z = v[8].x;
+            q.w = v[8].y;
+          }
+          __stcs(sp + 32 * j, q);     // streaming store: read once by pass B, no reuse before that
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         // Y0' = Z[k] + conj Z[N-k] = 2 Y0 ;  Y1' = -i (Z[k] - conj Z[N-k]) = 2 Y1
@@ -426,20 +445,42 @@ k512_cov(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, c
 // ------------------------------------------------------------------------------------------
 enum { GAIN_NONE = 0, GAIN_BITS = 1, GAIN_FLOOR = 2, GAIN_MASK = 3 };
 
+#ifndef AVZ_STAGES
+#define AVZ_STAGES 2
+#endif
+constexpr int kStages = AVZ_STAGES;   // frames of kept spectrum in flight per warp (TMA ring)
 template <int HOP>
-__global__ void __launch_bounds__(kWarps * 32, AVZ_MINB_APPLY)
-k512_apply(const float* __restrict__ mix, const float2* __restrict__ wgt, const uint32_t* __restrict__ ibm_bits,
-           const float* __restrict__ mask, int gain_mode, float post_floor, int L, int T, int blocks_per_cta,
-           float* __restrict__ out, float* __restrict__ peak, Tables tb) {
+__host__ __device__ constexpr size_t apply_fixed_smem() {
+  return (size_t)kWarps * f512::kSmemComplex * sizeof(float2) + 260 * sizeof(float4) +
+         2 * (size_t)kWarps * (16 - HOP / 32) * 32 * sizeof(float);
+}
+template <int HOP, bool KEPT>
+__host__ __device__ constexpr size_t apply_smem_bytes() {
+  return KEPT ? (apply_fixed_smem<HOP>() + 127) / 128 * 128 + (size_t)kWarps * kStages * (4096 + 8)
+              : apply_fixed_smem<HOP>();
+}
+
+// KEPT: the packed mix spectrum of every frame was stored by k512_cov (`spec`); no forward transform here: frames
+// are staged into a per-warp shared-memory ring by TMA bulk copies (cp.async.bulk + mbarrier), kStages deep.
+template <int HOP, bool KEPT>
+__global__ void __launch_bounds__(kWarps * 32, KEPT ? AVZ_MINB_APPLY_KEPT : AVZ_MINB_APPLY)
+k512_apply(const float* __restrict__ mix, const float4* __restrict__ spec, const float2* __restrict__ wgt,
+           const uint32_t* __restrict__ ibm_bits, const float* __restrict__ mask, int gain_mode, float post_floor, int L,
+           int T, int blocks_per_cta, float* __restrict__ out, float* __restrict__ peak, Tables tb) {
   constexpr int R = kN / HOP;        // frames overlapping one hop-block
   constexpr int NR = HOP / 32;       // rows per hop-block
   constexpr int TAIL = 16 - NR;      // rows still open after a frame's first block is emitted
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   float2* sm_all = reinterpret_cast<float2*>(smem_raw);
   float2* sm = sm_all + (size_t)(threadIdx.x >> 5) * f512::kSmemComplex;
   float4* s_ab = reinterpret_cast<float4*>(sm_all + (size_t)kWarps * f512::kSmemComplex);  // [kF] (a.x,a.y,b.x,b.y)
   float* s_head = reinterpret_cast<float*>(s_ab + 260);         // [kWarps][TAIL][32] first open blocks of a run
   float* s_tail = s_head + kWarps * TAIL * 32;                  // [kWarps][TAIL][32] blocks left open at its end
+  // KEPT: per-warp ring of kStages frames of kept spectrum (4096 B each), filled by TMA bulk copies
+  constexpr size_t kRingOff = (apply_fixed_smem<HOP>() + 127) / 128 * 128;
+  float4* s_ring = reinterpret_cast<float4*>(smem_raw + kRingOff) + (size_t)(threadIdx.x >> 5) * kStages * 256;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + kRingOff + (size_t)kWarps * kStages * 4096) +
+                    (size_t)(threadIdx.x >> 5) * kStages;
   __shared__ float s_peak[kWarps];
 
   Lane ln;
@@ -458,6 +499,11 @@ k512_apply(const float* __restrict__ mix, const float2* __restrict__ wgt, const 
       const float2 w1 = wgt[((int64_t)b * kF + k) * 2 + 1];
       s_ab[k] = make_float4(sc * (w0.x - w1.y), sc * (-w0.y - w1.x), sc * (w0.x + w1.y), sc * (-w0.y + w1.x));
     }
+  }
+  if (KEPT && lane == 0) {
+#pragma unroll
+    for (int st = 0; st < kStages; ++st) mbar_init(s_bar + st, 1);
+    mbar_fence_init();
   }
   __syncthreads();
 
@@ -536,7 +582,22 @@ k512_apply(const float* __restrict__ mix, const float2* __restrict__ wgt, const 
   if (ga < gb) {
     const int t_first = cold ? ga : max(0, ga - (R - 1));
     Window2<HOP> win;
-    if (t_first <= T - 1) win.load_all(m0, m1, L, t_first, lane);
+    // KEPT: frames t_first .. t_last of the kept spectrum stream through the ring; frame t lives in stage
+    // (t - t_first) % kStages and is the ((t - t_first) / kStages)-th use of that stage's barrier.
+    const int t_last = min(gb - 1, T - 1);
+    const float4* sp = KEPT ? spec + ((int64_t)b * T + t_first) * 256 : nullptr;
+    if (KEPT) {
+      if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < kStages; ++st)
+          if (t_first + st <= t_last) {
+            mbar_arrive_expect_tx(s_bar + st, 4096);
+            tma_load_1d(s_ring + st * 256, sp + (size_t)st * 256, 4096, s_bar + st);
+          }
+      }
+    } else if (t_first <= T - 1) {
+      win.load_all(m0, m1, L, t_first, lane);
+    }
     // post-filter gains of the frame about to be analysed, fetched one frame ahead
     FrameBits nb;
     float nmask[9];
@@ -579,29 +640,57 @@ k512_apply(const float* __restrict__ mix, const float2* __restrict__ wgt, const 
           for (int j = 0; j < 8; ++j) gj[j] = (gain_mode == GAIN_FLOOR) ? fmaxf(nmask[j], post_floor) : nmask[j];
           gny = (gain_mode == GAIN_FLOOR) ? fmaxf(nmask[8], post_floor) : nmask[8];
         }
-        if (g + 1 <= T - 1) {
-          win.prefetch(m0, m1, L, g + 1, lane);
-          bw += kFW;
-          mk += 1;
-          fetch_gain();
+        float2 zlo[8], mir[8], zny;
+        if (KEPT) {
+          const int use = g - t_first, st = use % kStages;
+          mbar_wait(s_bar + st, (uint32_t)(use / kStages) & 1u);
+          const float4* fr = s_ring + st * 256 + lane;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 q = fr[32 * j];
+            zlo[j] = make_float2(q.x, q.y);
+            mir[j] = make_float2(q.z, q.w);
+          }
+          zny = mir[0];                       // lane 0: slot (0).zw is the Nyquist bin ...
+          if (lane == 0) mir[0] = zlo[0];     // ... and DC is its own mirror
+          __syncwarp();                       // every lane has read the stage: refill it with frame g + kStages
+          if (lane == 0 && g + kStages <= t_last) {
+            fence_proxy_async();
+            mbar_arrive_expect_tx(s_bar + st, 4096);
+            tma_load_1d(s_ring + st * 256, sp + (size_t)(use + kStages) * 256, 4096, s_bar + st);
+          }
+          if (g + 1 <= T - 1) {
+            bw += kFW;
+            mk += 1;
+            fetch_gain();
+          }
+        } else {
+          if (g + 1 <= T - 1) {
+            win.prefetch(m0, m1, L, g + 1, lane);
+            bw += kFW;
+            mk += 1;
+            fetch_gain();
+          }
+          float2 v[16];
+          win.frame(v, hw);
+          f512::forward(v, sm, ln);
+          f512::mirror_of_low(v, mir, ln);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) zlo[j] = v[j];
+          zny = v[8];
         }
-        float2 v[16];
-        win.frame(v, hw);
-        f512::forward(v, sm, ln);
-        float2 mir[8];
-        f512::mirror_of_low(v, mir, ln);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 ab = s_ab[bin_lo(ln, j)];
           // a * z + b * conj(m)
-          const float sx = fmaf(ab.x, v[j].x, -ab.y * v[j].y) + fmaf(ab.z, mir[j].x, ab.w * mir[j].y);
-          const float sy = fmaf(ab.x, v[j].y, ab.y * v[j].x) + fmaf(ab.w, mir[j].x, -ab.z * mir[j].y);
+          const float sx = fmaf(ab.x, zlo[j].x, -ab.y * zlo[j].y) + fmaf(ab.z, mir[j].x, ab.w * mir[j].y);
+          const float sy = fmaf(ab.x, zlo[j].y, ab.y * zlo[j].x) + fmaf(ab.w, mir[j].x, -ab.z * mir[j].y);
           S[j] = make_float2(sx * gj[j], sy * gj[j]);
         }
         const float4 abn = s_ab[256];
-        // Re(a z + b conj z), z = hi[0] of lane 0
-        s_ny = gny * ((abn.x + abn.z) * v[8].x + (abn.w - abn.y) * v[8].y);
-        if (g + 1 <= T - 1) win.advance();
+        // Re(a z + b conj z), z = Nyquist bin (lane 0)
+        s_ny = gny * ((abn.x + abn.z) * zny.x + (abn.w - abn.y) * zny.y);
+        if (!KEPT && g + 1 <= T - 1) win.advance();
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) S[j] = make_float2(0.f, 0.f);
@@ -710,7 +799,7 @@ static float ibm_tol2() {
 
 template <int HOP>
 int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const float* mask, int B, int64_t L,
-                   float sqrt_eps, uint32_t* ibm_bits, float* part, int* chunks_out, cudaStream_t st) {
+                   float sqrt_eps, uint32_t* ibm_bits, float* part, int* chunks_out, void* spec, cudaStream_t st) {
   Tables tb;
   int rc = tables_for(kN, &tb);
   if (rc) return rc;
@@ -737,18 +826,20 @@ int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const f
   const size_t smem_cov = smem_fft + (size_t)kWarps * 5 * kFP * sizeof(float);
   if (mask == nullptr) {
     AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov<HOP, W_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
-    k512_cov<HOP, W_BITS><<<grid, kWarps * 32, smem_cov, st>>>(mix, ibm_bits, nullptr, (int)L, T, fpc, 0.f, part, tb);
+    k512_cov<HOP, W_BITS><<<grid, kWarps * 32, smem_cov, st>>>(mix, ibm_bits, nullptr, (int)L, T, fpc, 0.f, part,
+                                                               reinterpret_cast<float4*>(spec), tb);
   } else {
     AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov<HOP, W_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
-    k512_cov<HOP, W_MASK><<<grid, kWarps * 32, smem_cov, st>>>(mix, nullptr, mask, (int)L, T, fpc, sqrt_eps, part, tb);
+    k512_cov<HOP, W_MASK><<<grid, kWarps * 32, smem_cov, st>>>(mix, nullptr, mask, (int)L, T, fpc, sqrt_eps, part,
+                                                               reinterpret_cast<float4*>(spec), tb);
   }
   AVZ_LAUNCH_OK("k512_cov");
   return AVZ_OK;
 }
 
 template <int HOP>
-int launch_apply(const float* mix, const float* w, const uint32_t* ibm_bits, const float* mask, int gain_mode,
-                 float post_floor, int B, int64_t L, float* out, float* peak, cudaStream_t st) {
+int launch_apply(const float* mix, const void* spec, const float* w, const uint32_t* ibm_bits, const float* mask,
+                 int gain_mode, float post_floor, int B, int64_t L, float* out, float* peak, cudaStream_t st) {
   Tables tb;
   int rc = tables_for(kN, &tb);
   if (rc) return rc;
@@ -758,13 +849,18 @@ int launch_apply(const float* mix, const float* w, const uint32_t* ibm_bits, con
   if (n_blocks <= 0) return AVZ_OK;
   int bpc = frames_per_cta(B, n_blocks, num_sms());
   const int chunks = (n_blocks + bpc - 1) / bpc;
-  constexpr int TAIL = 16 - HOP / 32;
-  const size_t smem = (size_t)kWarps * f512::kSmemComplex * sizeof(float2) + 260 * sizeof(float4) +
-                      2 * (size_t)kWarps * TAIL * 32 * sizeof(float);
-  AVZ_CUDA_OK(cudaFuncSetAttribute(k512_apply<HOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = (spec != nullptr) ? apply_smem_bytes<HOP, true>() : apply_smem_bytes<HOP, false>();
   dim3 grid(chunks, B);
-  k512_apply<HOP><<<grid, kWarps * 32, smem, st>>>(mix, reinterpret_cast<const float2*>(w), ibm_bits, mask, gain_mode,
-                                                   post_floor, (int)L, T, bpc, out, peak, tb);
+  if (spec != nullptr) {
+    AVZ_CUDA_OK(cudaFuncSetAttribute(k512_apply<HOP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k512_apply<HOP, true><<<grid, kWarps * 32, smem, st>>>(nullptr, reinterpret_cast<const float4*>(spec),
+                                                           reinterpret_cast<const float2*>(w), ibm_bits, mask, gain_mode,
+                                                           post_floor, (int)L, T, bpc, out, peak, tb);
+  } else {
+    AVZ_CUDA_OK(cudaFuncSetAttribute(k512_apply<HOP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k512_apply<HOP, false><<<grid, kWarps * 32, smem, st>>>(mix, nullptr, reinterpret_cast<const float2*>(w), ibm_bits,
+                                                            mask, gain_mode, post_floor, (int)L, T, bpc, out, peak, tb);
+  }
   AVZ_LAUNCH_OK("k512_apply");
   return AVZ_OK;
 }
@@ -788,13 +884,13 @@ int launch_ibm_exact(const float* tgt, const float* itf, int B, int64_t L, int h
 }
 
 template int launch_ibm_cov<128>(const float*, const float*, const float*, const float*, int, int64_t, float, uint32_t*,
-                                 float*, int*, cudaStream_t);
+                                 float*, int*, void*, cudaStream_t);
 template int launch_ibm_cov<256>(const float*, const float*, const float*, const float*, int, int64_t, float, uint32_t*,
-                                 float*, int*, cudaStream_t);
-template int launch_apply<128>(const float*, const float*, const uint32_t*, const float*, int, float, int, int64_t,
-                               float*, float*, cudaStream_t);
-template int launch_apply<256>(const float*, const float*, const uint32_t*, const float*, int, float, int, int64_t,
-                               float*, float*, cudaStream_t);
+                                 float*, int*, void*, cudaStream_t);
+template int launch_apply<128>(const float*, const void*, const float*, const uint32_t*, const float*, int, float, int,
+                               int64_t, float*, float*, cudaStream_t);
+template int launch_apply<256>(const float*, const void*, const float*, const uint32_t*, const float*, int, float, int,
+                               int64_t, float*, float*, cudaStream_t);
 
 }  // namespace o512
 }  // namespace avz

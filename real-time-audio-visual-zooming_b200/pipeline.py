@@ -22,7 +22,7 @@ class OracleMvdr:
 
     launches_per_step = 5  # k_cov, k_cov_finalize, k_mvdr_weights, k_synth, k_peak_normalise (+1 memset of `peak`)
 
-    def __init__(self, cfg: MvdrConfig, B: int, L: int, device):
+    def __init__(self, cfg: MvdrConfig, B: int, L: int, device, keep_spectrum: bool = True):
         self.cfg, self.B, self.L, self.device = cfg, B, L, device
         self.lib = _lib.load()
         self.F = cfg.n_freq
@@ -39,6 +39,9 @@ class OracleMvdr:
         if nws < 0:
             _lib.check(-1, "avz_ibm_cov_ws_bytes")
         self.ws = torch.empty((max(int(nws), 4),), dtype=torch.uint8, device=device)
+        # pass A may keep the packed mix spectrum so that pass B skips its forward transform (fast path only)
+        nspec = self.lib.avz_spec_ws_bytes(B, L, cfg.n_fft, cfg.hop) if keep_spectrum else 0
+        self.spec = torch.empty((int(nspec),), dtype=torch.uint8, device=device) if nspec > 0 else None
         self.d = steering_vectors(cfg, device)
         self.cc = cfg.to_c()
         _lib.check(self.lib.avz_init(cfg.n_fft), "avz_init")
@@ -46,6 +49,11 @@ class OracleMvdr:
     # individual stages (each one C-ABI call) ---------------------------------------------------
     def pass_a(self, mix, tgt, itf):
         c = self.cfg
+        if self.spec is not None:
+            _lib.check(self.lib.avz_ibm_cov_keep_f32(_ptr(mix), _ptr(tgt), _ptr(itf), self.B, self.L, c.n_fft, c.hop,
+                                                     float(c.norm_eps), _ptr(self.bits), _ptr(self.R), _ptr(self.msum),
+                                                     _ptr(self.ws), _ptr(self.spec), _stream()), "avz_ibm_cov_keep_f32")
+            return
         _lib.check(self.lib.avz_ibm_cov_f32(_ptr(mix), _ptr(tgt), _ptr(itf), self.B, self.L, c.n_fft, c.hop,
                                             float(c.norm_eps), _ptr(self.bits), _ptr(self.R), _ptr(self.msum),
                                             _ptr(self.ws), _stream()), "avz_ibm_cov_f32")
@@ -58,6 +66,11 @@ class OracleMvdr:
         c = self.cfg
         self.peak.zero_()
         bits = self.bits if c.post == "one_minus_noise" else None
+        if self.spec is not None:
+            _lib.check(self.lib.avz_mvdr_apply_kept_f32(_ptr(self.spec), _ptr(self.w), _ptr(bits), _ptr(None), self.B,
+                                                        self.L, c.n_fft, c.hop, C.byref(self.cc), _ptr(self.out),
+                                                        _ptr(self.peak), _stream()), "avz_mvdr_apply_kept_f32")
+            return
         _lib.check(self.lib.avz_mvdr_apply_f32(_ptr(mix), _ptr(self.w), _ptr(bits), _ptr(None), self.B, self.L, c.n_fft,
                                                c.hop, C.byref(self.cc), _ptr(self.out), _ptr(self.peak), _stream()),
                    "avz_mvdr_apply_f32")
