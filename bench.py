@@ -241,8 +241,9 @@ def run_ours(args):
     ktimes = enh.time_kernels(mix, tgt, itf, iters=max(3, min(args.steps, 10)))
     peak_gbs, peak_src = load_peak()
     samples = B * L
-    algo = {"k_cov (pass A: STFT x4 + IBM + covariance)": 16.0 * samples,      # read mix 2L, tgt L, int L
-            "k_synth (pass B: STFT + beamform + iSTFT)": 12.0 * samples}       # read mix 2L, write out L
+    # algorithmic (compulsory) bytes of each pass: A reads mix 2L + tgt L + int L; B reads mix 2L and writes out L
+    algo = {"pass A (k512_ibm + k512_ibm_fixup + k512_cov + k_cov_finalize)": 16.0 * samples,
+            "pass B (k512_apply)": 12.0 * samples}
     dom = max(ktimes, key=lambda k: ktimes[k] if k in algo else -1)
     achieved = algo[dom] / (ktimes[dom] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",

@@ -20,7 +20,9 @@ from .ops import _ptr, _stream, num_frames, steering_vectors
 class OracleMvdr:
     """Oracle-IBM mask-MVDR (rt_av_zoom/core/oracle_debug.py:42-94) for a fixed batch shape."""
 
-    launches_per_step = 5  # k_cov, k_cov_finalize, k_mvdr_weights, k_synth, k_peak_normalise (+1 memset of `peak`)
+    # k512_ibm, k512_ibm_fixup, k512_cov, k_cov_finalize, k_mvdr_weights, k512_apply, k_peak_normalise
+    # (+ two small memsets: the near-tie counter and `peak`)
+    launches_per_step = 7
 
     def __init__(self, cfg: MvdrConfig, B: int, L: int, device, keep_spectrum: bool = True):
         self.cfg, self.B, self.L, self.device = cfg, B, L, device
@@ -90,9 +92,9 @@ class OracleMvdr:
 
     def time_kernels(self, mix, tgt, itf, iters: int = 5) -> Dict[str, float]:
         """Average device time (ms) of each stage, CUDA events on the launching stream."""
-        stages = [("k_cov (pass A: STFT x4 + IBM + covariance)", lambda: self.pass_a(mix, tgt, itf)),
+        stages = [("pass A (k512_ibm + k512_ibm_fixup + k512_cov + k_cov_finalize)", lambda: self.pass_a(mix, tgt, itf)),
                   ("k_mvdr_weights", self.weights),
-                  ("k_synth (pass B: STFT + beamform + iSTFT)", lambda: self.pass_b(mix)),
+                  ("pass B (k512_apply)", lambda: self.pass_b(mix)),
                   ("k_peak_normalise", self.normalise)]
         self.run(mix, tgt, itf)
         torch.cuda.synchronize()
