@@ -15,8 +15,8 @@
  *     dimension prepended; complex numbers are interleaved float pairs (re, im);
  *   - F = n_fft/2 + 1, T = avz_num_frames(L, n_fft, hop) = ceil(L/hop) + 1 for hop | n_fft,
  *     iSTFT length = (T - 1) * hop  (scipy.signal.stft/istft, boundary='zeros', padded=True).
- *   - supported: n_fft in {256, 512, 1024, 2048}, hop with n_fft % hop == 0 and 2 <= n_fft/hop <= 8,
- *     L >= n_fft.
+ *   - supported: n_fft in {256, 512, 1024}, hop with n_fft % hop == 0 and 2 <= n_fft/hop <= 8, L >= n_fft.
+ *     n_fft 512 with hop 128 or 256 (every BASELINE shape) runs on the register-resident fast path.
  */
 #ifndef AVZOOM_H_
 #define AVZOOM_H_
@@ -145,6 +145,19 @@ AVZ_API int avz_wave_mask_cov_keep_f32(const float* mix, const float* mask, int 
                                float sqrt_eps, float norm_eps, float* R, float* msum, void* ws, void* spec, void* stream);
 AVZ_API int avz_mvdr_apply_kept_f32(const void* spec, const float* w, const uint32_t* ibm_bits, const float* mask, int B,
                             int64_t L, int n_fft, int hop, const AvzMvdrCfg* cfg, float* out, float* peak, void* stream);
+
+/* ---- streaming mode (BASELINE config 4; NOT in the reference - defined by this project, parity unpinned):
+ *   R_t = lambda R_{t-1} + (1-lambda) m_t y_t y_t^H,  n_t = lambda n_{t-1} + (1-lambda) m_t,
+ *   w_t = mvdr(R_t/(n_t+norm_eps) + sigma I),  S_t = w_t^H y_t,  same 512/128 framing and overlap-add as the batch path.
+ * One call consumes one hop (128 new samples per mic) of n_streams independent streams and emits 128 output samples
+ * per stream.  Call number h (0, 1, ...) carries t = h - 1 (the scipy frame completed by this hop) and returns the
+ * output samples [(h-3)*128, (h-2)*128): ignore the first three returns; after the last input hop feed three zero hops
+ * with t_end = number of frames (= input hops + 1) to flush.  t_end = INT_MAX while the stream is open.
+ * state: avz_stream_state_bytes(n_streams) bytes, zeroed by the caller before the first hop.
+ * hop_in [S,2,128] f32, noise_w [S,257] f32 (noise weight m_t of this frame) or NULL (= 1), dvec [257,2] complex64. */
+AVZ_API int64_t avz_stream_state_bytes(int n_streams);
+AVZ_API int avz_stream_step_f32(float* state, const float* hop_in, const float* noise_w, const float* dvec, int n_streams,
+                        int t, int t_end, float lambda, const AvzMvdrCfg* cfg, float* hop_out, void* stream);
 
 /* ---- IBM from given spectra: oracle_debug.py:49-53 (noise polarity) / model_training.py:90 (target polarity).
  * a, b [n] complex64 -> out [n] f32 = (|a| > |b|) ? 1 : 0, compared exactly (float64 squares). */

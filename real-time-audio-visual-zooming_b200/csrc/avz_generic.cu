@@ -17,6 +17,8 @@ namespace avz {
 namespace o512 {
 int cov_chunks512(int B, int T);
 int64_t ws_bytes512(int B, int T);
+int launch_stream_step(float* state, const float* hop_in, const float* noise_w, const float* dvec, int n_streams,
+                       int t, int t_end, float lam, const AvzMvdrCfg* cfg, float* hop_out, cudaStream_t st);
 int launch_ibm_exact(const float* tgt, const float* itf, int B, int64_t L, int hop, uint32_t* ibm_bits, void* ws16,
                      cudaStream_t st);
 template <int HOP>
@@ -716,6 +718,20 @@ int avz_mvdr_apply_kept_f32(const void* spec, const float* w, const uint32_t* ib
                                                 (cudaStream_t)stream)
                       : o512::launch_apply<256>(nullptr, spec, w, ibm_bits, mask, gain, cfg->post_floor, B, L, out, peak,
                                                 (cudaStream_t)stream);
+}
+
+// ---- streaming (n_fft 512 / hop 128): one hop per call for n_streams independent 2-mic streams ---------------
+int64_t avz_stream_state_bytes(int n_streams) {
+  return n_streams > 0 ? (int64_t)n_streams * (2 * 384 + 384 + 5 * 288) * (int64_t)sizeof(float) : 0;
+}
+
+int avz_stream_step_f32(float* state, const float* hop_in, const float* noise_w, const float* dvec, int n_streams, int t,
+                        int t_end, float lambda, const AvzMvdrCfg* cfg, float* hop_out, void* stream) {
+  if (!state || !hop_in || !dvec || !cfg || !hop_out || n_streams <= 0)
+    return set_error(AVZ_EINVAL, "avz_stream_step_f32: null pointer or no streams");
+  if (!(lambda >= 0.f && lambda < 1.f)) return set_error(AVZ_EINVAL, "avz_stream_step_f32: lambda must be in [0, 1)");
+  return o512::launch_stream_step(state, hop_in, noise_w, dvec, n_streams, t, t_end, lambda, cfg, hop_out,
+                                  (cudaStream_t)stream);
 }
 
 int avz_mvdr_apply_f32(const float* mix, const float* w, const uint32_t* ibm_bits, const float* mask, int B, int64_t L,

@@ -894,3 +894,191 @@ template int launch_apply<256>(const float*, const void*, const float*, const ui
 
 }  // namespace o512
 }  // namespace avz
+
+// ------------------------------------------------------------------------------------------
+// Streaming step (BASELINE config 4).  NOT IN THE REFERENCE - this project's definition:
+//   R_t = lam R_{t-1} + (1 - lam) m_t y_t y_t^H ,  n_t = lam n_{t-1} + (1 - lam) m_t
+//   w_t = mvdr(R_t / (n_t + norm_eps) + sigma I) ,  S_t = w_t^H y_t  (bins below the high-pass -> 0 / mic 0)
+// with the same 512 / 128 STFT framing and overlap-add as the batch path, one hop of 128 new samples per call.
+// One warp per stream.  Per stream state: the last 384 input samples of both mics, the 384 open output samples,
+// and (R00, R11, Re R01, Im R01, n) per bin in the lane layout of the transform.
+// ------------------------------------------------------------------------------------------
+namespace avz {
+namespace o512 {
+
+constexpr int kStreamStateFloats = 2 * 384 + 384 + 5 * 288;   // hist, tail, cov (8 x 32 + Nyquist row, padded to 288)
+
+__global__ void __launch_bounds__(kWarps * 32, 3)
+k512_stream_step(float* __restrict__ state, const float* __restrict__ hop_in, const float* __restrict__ noise_w,
+                 const float2* __restrict__ dvec, int n_streams, int t, int t_end, float lam, AvzMvdrCfg cfg,
+                 float* __restrict__ hop_out, Tables tb) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2* sm = reinterpret_cast<float2*>(smem_raw) + (size_t)(threadIdx.x >> 5) * f512::kSmemComplex;
+  Lane ln;
+  ln.init(tb.tw);
+  const int lane = ln.lane;
+  const int s = blockIdx.x * kWarps + (threadIdx.x >> 5);
+  if (s >= n_streams) return;
+  float* st = state + (size_t)s * kStreamStateFloats;
+  float* hist = st;                 // [2][384]
+  float* tail = st + 768;           // [384]  open output blocks t+1 .. t+3 before this call's frame is added
+  float* cov = st + 1152;           // [5][288]
+  const float* xin = hop_in + (size_t)s * 256;   // [2][128]
+  float hw[16];
+  load_window(hw, tb.win, ln);
+
+  // frame t = [history (rows 0..11) | new hop (rows 12..15)], then slide the history
+  float a[16], b[16];
+#pragma unroll
+  for (int r = 0; r < 12; ++r) {
+    a[r] = hist[32 * r + lane];
+    b[r] = hist[384 + 32 * r + lane];
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    a[12 + r] = xin[32 * r + lane];
+    b[12 + r] = xin[128 + 32 * r + lane];
+  }
+#pragma unroll
+  for (int r = 0; r < 12; ++r) {
+    hist[32 * r + lane] = a[r + 4];
+    hist[384 + 32 * r + lane] = b[r + 4];
+  }
+  const bool frame_valid = (t >= 0) && (t < t_end);
+  float o[16];
+#pragma unroll
+  for (int r = 0; r < 12; ++r) o[r] = tail[32 * r + lane];
+#pragma unroll
+  for (int r = 12; r < 16; ++r) o[r] = 0.f;
+
+  if (frame_valid) {
+    float2 v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = make_float2(a[r] * hw[r], b[r] * hw[r]);
+    f512::forward(v, sm, ln);
+    float2 mir[8];
+    f512::mirror_of_low(v, mir, ln);
+    const float sc = 1.0f / ((float)kN * (float)kN);   // spectra are unscaled (x N/2) and un-halved (x 2)
+    const float one_m = 1.f - lam;
+    float2 S[8];
+    float s_ny = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = bin_lo(ln, j);
+      const float2 y0 = make_float2(v[j].x + mir[j].x, v[j].y - mir[j].y);   // 2 Y0 (x N/2)
+      const float2 y1 = make_float2(v[j].y + mir[j].y, mir[j].x - v[j].x);   // 2 Y1
+      const float m = noise_w ? noise_w[(size_t)s * kF + k] : 1.f;
+      const int ci = 32 * j + lane;
+      const float r00 = fmaf(lam, cov[0 * 288 + ci], one_m * m * sc * cabs2(y0));
+      const float r11 = fmaf(lam, cov[1 * 288 + ci], one_m * m * sc * cabs2(y1));
+      const float2 c01 = cmulc(y0, y1);
+      const float rre = fmaf(lam, cov[2 * 288 + ci], one_m * m * sc * c01.x);
+      const float rim = fmaf(lam, cov[3 * 288 + ci], one_m * m * sc * c01.y);
+      const float nn = fmaf(lam, cov[4 * 288 + ci], one_m * m);
+      cov[0 * 288 + ci] = r00;
+      cov[1 * 288 + ci] = r11;
+      cov[2 * 288 + ci] = rre;
+      cov[3 * 288 + ci] = rim;
+      cov[4 * 288 + ci] = nn;
+      float2 w0 = make_float2(0.f, 0.f), w1 = make_float2(0.f, 0.f);
+      if (k < cfg.hp_bins && cfg.hp_mode != AVZ_HP_NONE) {
+        if (cfg.hp_mode == AVZ_HP_MIC0) w0.x = 1.f;
+      } else {
+        // closed-form 2x2 solve in float64 (as k_mvdr_weights)
+        const double inv = 1.0 / ((double)nn + (double)cfg.norm_eps);
+        const double aa = (double)r00 * inv + (double)cfg.sigma, cc = (double)r11 * inv + (double)cfg.sigma;
+        const double bx = (double)rre * inv, by = (double)rim * inv;
+        const double2 d0 = make_double2((double)dvec[2 * k].x, (double)dvec[2 * k].y);
+        const double2 d1 = make_double2((double)dvec[2 * k + 1].x, (double)dvec[2 * k + 1].y);
+        const double det = aa * cc - (bx * bx + by * by);
+        if (det == 0.0 || !isfinite(det)) {
+          w0.x = 1.f;
+        } else {
+          // u0 = (c d0 - b d1)/det, u1 = (a d1 - conj(b) d0)/det
+          const double u0x = (cc * d0.x - (bx * d1.x - by * d1.y)) / det, u0y = (cc * d0.y - (bx * d1.y + by * d1.x)) / det;
+          const double u1x = (aa * d1.x - (bx * d0.x + by * d0.y)) / det, u1y = (aa * d1.y - (bx * d0.y - by * d0.x)) / det;
+          // den = conj(d0) u0 + conj(d1) u1 + w_eps
+          const double dx = d0.x * u0x + d0.y * u0y + d1.x * u1x + d1.y * u1y + (double)cfg.w_eps;
+          const double dy = d0.x * u0y - d0.y * u0x + d1.x * u1y - d1.y * u1x;
+          const double dd = dx * dx + dy * dy;
+          w0 = make_float2((float)((u0x * dx + u0y * dy) / dd), (float)((u0y * dx - u0x * dy) / dd));
+          w1 = make_float2((float)((u1x * dx + u1y * dy) / dd), (float)((u1y * dx - u1x * dy) / dd));
+        }
+      }
+      // S = conj(w0) Y0 + conj(w1) Y1 with Y = y' / N (analysis 2/N, halved); synthesis factor 1/2 folded below
+      const float2 sv = cadd(cmulc(y0, w0), cmulc(y1, w1));
+      S[j] = make_float2(sv.x * (0.5f / (float)kN), sv.y * (0.5f / (float)kN));
+    }
+    // Nyquist bin (lane 0): Y0 = Re hi[0], Y1 = Im hi[0] (x N/2, not doubled)
+    {
+      const float scn = 4.0f / ((float)kN * (float)kN);
+      const float m = noise_w ? noise_w[(size_t)s * kF + 256] : 1.f;
+      const int ci = 256 + lane;    // row 8 of the cov block: only lane 0's entry is meaningful
+      const float r00 = fmaf(lam, cov[0 * 288 + ci], one_m * m * scn * v[8].x * v[8].x);
+      const float r11 = fmaf(lam, cov[1 * 288 + ci], one_m * m * scn * v[8].y * v[8].y);
+      const float rre = fmaf(lam, cov[2 * 288 + ci], one_m * m * scn * v[8].x * v[8].y);
+      const float nn = fmaf(lam, cov[4 * 288 + ci], one_m * m);
+      cov[0 * 288 + ci] = r00;
+      cov[1 * 288 + ci] = r11;
+      cov[2 * 288 + ci] = rre;
+      cov[4 * 288 + ci] = nn;
+      const double inv = 1.0 / ((double)nn + (double)cfg.norm_eps);
+      const double aa = (double)r00 * inv + (double)cfg.sigma, cc = (double)r11 * inv + (double)cfg.sigma;
+      const double bx = (double)rre * inv;
+      const double2 d0 = make_double2((double)dvec[512].x, (double)dvec[512].y);
+      const double2 d1 = make_double2((double)dvec[513].x, (double)dvec[513].y);
+      const double det = aa * cc - bx * bx;
+      double w0x = 1.0, w0y = 0.0, w1x = 0.0, w1y = 0.0;
+      if (det != 0.0 && isfinite(det)) {
+        const double u0x = (cc * d0.x - bx * d1.x) / det, u0y = (cc * d0.y - bx * d1.y) / det;
+        const double u1x = (aa * d1.x - bx * d0.x) / det, u1y = (aa * d1.y - bx * d0.y) / det;
+        const double dx = d0.x * u0x + d0.y * u0y + d1.x * u1x + d1.y * u1y + (double)cfg.w_eps;
+        const double dy = d0.x * u0y - d0.y * u0x + d1.x * u1y - d1.y * u1x;
+        const double dd = dx * dx + dy * dy;
+        w0x = (u0x * dx + u0y * dy) / dd; w0y = (u0y * dx - u0x * dy) / dd;
+        w1x = (u1x * dx + u1y * dy) / dd; w1y = (u1y * dx - u1x * dy) / dd;
+      }
+      (void)w0y; (void)w1y;
+      // Re(conj(w0) Y0 + conj(w1) Y1) for real Y0, Y1; (2/N) analysis x 1/2 synthesis = 1/N
+      s_ny = (float)(w0x * (double)v[8].x + w1x * (double)v[8].y) * (1.0f / (float)kN);
+      if (256 < cfg.hp_bins && cfg.hp_mode == AVZ_HP_ZERO) s_ny = 0.f;
+    }
+    float2 Z0[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) Z0[j] = make_float2(0.f, 0.f);
+    float2 x[16];
+    f512::hermitian_pack(S, Z0, make_float2(s_ny, 0.f), x, ln);
+    f512::inverse(x, sm, ln);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) o[r] = fmaf(hw[r], x[r].x, o[r]);
+  }
+  // block g = t is complete: normalise by the sum of w^2 over the frames t-3..t that exist, emit, keep the rest open
+  float* yo = hop_out + (size_t)s * 128;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    float nrm = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int tq = t - q;
+      if (tq >= 0 && tq < t_end) nrm = fmaf(hw[r + 4 * q], hw[r + 4 * q], nrm);
+    }
+    yo[32 * r + lane] = o[r] / (nrm > 1e-10f ? nrm : 1.0f);
+  }
+#pragma unroll
+  for (int r = 0; r < 12; ++r) tail[32 * r + lane] = o[r + 4];
+}
+
+int launch_stream_step(float* state, const float* hop_in, const float* noise_w, const float* dvec, int n_streams,
+                       int t, int t_end, float lam, const AvzMvdrCfg* cfg, float* hop_out, cudaStream_t st) {
+  Tables tb;
+  int rc = tables_for(kN, &tb);
+  if (rc) return rc;
+  const size_t smem = (size_t)kWarps * f512::kSmemComplex * sizeof(float2);
+  k512_stream_step<<<(n_streams + kWarps - 1) / kWarps, kWarps * 32, smem, st>>>(
+      state, hop_in, noise_w, reinterpret_cast<const float2*>(dvec), n_streams, t, t_end, lam, *cfg, hop_out, tb);
+  AVZ_LAUNCH_OK("k512_stream_step");
+  return AVZ_OK;
+}
+
+}  // namespace o512
+}  // namespace avz
