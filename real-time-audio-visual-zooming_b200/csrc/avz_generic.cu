@@ -19,6 +19,8 @@ int cov_chunks512(int B, int T);
 int64_t ws_bytes512(int B, int T);
 int launch_stream_step(float* state, const float* hop_in, const float* noise_w, const float* dvec, int n_streams,
                        int t, int t_end, float lam, const AvzMvdrCfg* cfg, float* hop_out, cudaStream_t st);
+template <int HOP>
+int launch_features(const float* mix, int B, int64_t L, int wrapped, float* X, cudaStream_t st);
 int launch_ibm_exact(const float* tgt, const float* itf, int B, int64_t L, int hop, uint32_t* ibm_bits, void* ws16,
                      cudaStream_t st);
 template <int HOP>
@@ -615,6 +617,11 @@ int avz_wave_features_f32(const float* mix, int B, int64_t L, int n_fft, int hop
   if (!mix || !X || B <= 0 || mode < 0 || mode > 2) return set_error(AVZ_EINVAL, "avz_wave_features_f32: bad argument");
   int rc = check_fft_args(n_fft, hop, L);
   if (rc) return rc;
+  if (use_opt512(n_fft, hop) && mode != AVZ_FEAT_PHYSICS_NHWC) {
+    const int wrapped = (mode == AVZ_FEAT_LOGMAG_IPD_WRAPPED);
+    return (hop == 128) ? o512::launch_features<128>(mix, B, L, wrapped, X, (cudaStream_t)stream)
+                        : o512::launch_features<256>(mix, B, L, wrapped, X, (cudaStream_t)stream);
+  }
   AVZ_DISPATCH_N(n_fft, (launch_wave_features<N_>(mix, B, L, hop, mode, X, (cudaStream_t)stream)));
 }
 

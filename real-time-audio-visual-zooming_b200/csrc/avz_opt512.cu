@@ -1082,3 +1082,101 @@ int launch_stream_step(float* state, const float* hop_in, const float* noise_w, 
 
 }  // namespace o512
 }  // namespace avz
+
+// ------------------------------------------------------------------------------------------
+// Features straight from the waveform (full_audio.../inference.py:90-94) on the fast path: STFT of the two mics,
+// ln(|Y0| + 1e-7) and angle(Y0) - angle(Y1); the spectrum is never written.  A CTA covers 32 consecutive frames
+// (8 per warp, sliding window), stages the two feature planes in shared memory [2][257][33] and writes every
+// (feature, bin) row as one coalesced 128-byte run along time - the reference layout (2, F, T) has T contiguous.
+// ------------------------------------------------------------------------------------------
+namespace avz {
+namespace o512 {
+
+constexpr int kFeatTile = 32;                       // frames per CTA
+constexpr int kFeatPitch = kFeatTile + 1;           // floats per (feature, bin) row in shared memory
+
+template <int HOP>
+__global__ void __launch_bounds__(kWarps * 32, 3)
+k512_features(const float* __restrict__ mix, int L, int T, int wrapped, float* __restrict__ X, Tables tb) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float2* sm = reinterpret_cast<float2*>(smem_raw) + (size_t)(threadIdx.x >> 5) * f512::kSmemComplex;
+  float* tile = reinterpret_cast<float*>(reinterpret_cast<float2*>(smem_raw) + (size_t)kWarps * f512::kSmemComplex);
+  Lane ln;
+  ln.init(tb.tw);
+  const int lane = ln.lane, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * kFeatTile;
+  const float* m0 = mix + (int64_t)b * 2 * L;
+  const float* m1 = m0 + L;
+  float w[16];
+  load_window(w, tb.win, ln);
+  constexpr int per = kFeatTile / kWarps;
+  const int ta = t0 + warp * per, tb_ = min(T, ta + per);
+  if (ta < tb_) {
+    Window2<HOP> win;
+    win.load_all(m0, m1, L, ta, lane);
+#pragma unroll 1
+    for (int t = ta; t < tb_; ++t) {
+      if (t + 1 < tb_) win.prefetch(m0, m1, L, t + 1, lane);
+      float2 v[16];
+      win.frame(v, w);
+      f512::forward(v, sm, ln);
+      float2 mir[8];
+      f512::mirror_of_low(v, mir, ln);
+      const int tl = t - t0;
+      const float sc = 1.0f / (float)kN;   // un-halved, unscaled spectra -> true values
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        float2 y0, y1;
+        int k;
+        if (j < 8) {
+          k = bin_lo(ln, j);
+          y0 = make_float2(sc * (v[j].x + mir[j].x), sc * (v[j].y - mir[j].y));
+          y1 = make_float2(sc * (v[j].y + mir[j].y), sc * (mir[j].x - v[j].x));
+        } else {  // Nyquist, lane 0: real spectra (imaginary parts +0 as rfft gives)
+          k = 256;
+          y0 = make_float2(2.f * sc * v[8].x, 0.f);
+          y1 = make_float2(2.f * sc * v[8].y, 0.f);
+        }
+        if (j < 8 || lane == 0) {
+          float lm, ipd;
+          feature_values(y0, y1, lm, ipd);
+          if (wrapped) {
+            const float two_pi = 6.28318530717958647692f;
+            ipd = ipd - two_pi * rintf(ipd / two_pi);
+          }
+          tile[(0 * kF + k) * kFeatPitch + tl] = lm;
+          tile[(1 * kF + k) * kFeatPitch + tl] = ipd;
+        }
+      }
+      if (t + 1 < tb_) win.advance();
+    }
+  }
+  __syncthreads();
+  const int nt = min(kFeatTile, T - t0);
+  // rows (feature c, bin k): 32 consecutive frames each; one warp writes one row per iteration
+  for (int row = warp; row < 2 * kF; row += kWarps) {
+    const int c = row / kF, k = row - c * kF;
+    if (lane < nt) X[(((int64_t)b * 2 + c) * kF + k) * T + t0 + lane] = tile[row * kFeatPitch + lane];
+  }
+}
+
+template <int HOP>
+int launch_features(const float* mix, int B, int64_t L, int wrapped, float* X, cudaStream_t st) {
+  Tables tb;
+  int rc = tables_for(kN, &tb);
+  if (rc) return rc;
+  if (L >= (1ll << 30)) return set_error(AVZ_EINVAL, "L=%lld too long for the 512-point fast path", (long long)L);
+  const int T = (int)avz_num_frames(L, kN, HOP);
+  const size_t smem = (size_t)kWarps * f512::kSmemComplex * sizeof(float2) + (size_t)2 * kF * kFeatPitch * sizeof(float);
+  AVZ_CUDA_OK(cudaFuncSetAttribute(k512_features<HOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((T + kFeatTile - 1) / kFeatTile, B);
+  k512_features<HOP><<<grid, kWarps * 32, smem, st>>>(mix, (int)L, T, wrapped, X, tb);
+  AVZ_LAUNCH_OK("k512_features");
+  return AVZ_OK;
+}
+template int launch_features<128>(const float*, int, int64_t, int, float*, cudaStream_t);
+template int launch_features<256>(const float*, int, int64_t, int, float*, cudaStream_t);
+
+}  // namespace o512
+}  // namespace avz

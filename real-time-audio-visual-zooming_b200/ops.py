@@ -21,7 +21,7 @@ __all__ = [
     "num_frames", "stft", "istft", "ibm", "ibm_target_label", "geometric_mask", "masked_covariance",
     "steering_vectors", "mvdr_weights", "beamform", "logmag_ipd", "physics_features", "sir_scores",
     "ibm_covariance", "wave_masked_covariance", "mvdr_apply", "peak_normalise", "unpack_ibm",
-    "oracle_mask_mvdr", "learned_mask_mvdr", "covariance_to_matrix", "ibm_exact_bits", "irm", "wave_features",
+    "oracle_mask_mvdr", "learned_mask_mvdr", "covariance_to_matrix", "ibm_exact_bits", "irm", "wave_features", "alloc_kept_spectrum",
 ]
 
 
@@ -317,8 +317,17 @@ def sir_scores(est, tgt, itf):
 
 
 # ------------------------------------------------------------------------------------------ fused passes
-def ibm_covariance(mix: torch.Tensor, tgt: torch.Tensor, itf: torch.Tensor, cfg: MvdrConfig):
-    """Pass A (oracle_debug.py:42-64) without storing any spectrum.
+def alloc_kept_spectrum(mix: torch.Tensor, cfg: MvdrConfig) -> Optional[torch.Tensor]:
+    """Workspace in which pass A keeps the packed mix spectrum for pass B (fast path shapes only, else None)."""
+    B, _, L = mix.shape
+    n = _lib.load().avz_spec_ws_bytes(B, L, cfg.n_fft, cfg.hop)
+    return torch.empty((int(n),), dtype=torch.uint8, device=mix.device) if n > 0 else None
+
+
+def ibm_covariance(mix: torch.Tensor, tgt: torch.Tensor, itf: torch.Tensor, cfg: MvdrConfig,
+                   spec: Optional[torch.Tensor] = None):
+    """Pass A (oracle_debug.py:42-64) without storing any spectrum - or, with `spec` (alloc_kept_spectrum), keeping
+    the packed mix spectrum so that pass B can skip its forward transform.
     mix [B,2,L], tgt [B,L], itf [B,L] -> (ibm_bits [B,T,ceil(F/32)] int32, R packed [B,F,4], msum [B,F])."""
     lib = _lib.load()
     B, _, L = mix.shape
@@ -331,8 +340,13 @@ def ibm_covariance(mix: torch.Tensor, tgt: torch.Tensor, itf: torch.Tensor, cfg:
     if nws < 0:
         _lib.check(-1, "avz_ibm_cov_ws_bytes")
     ws = torch.empty((max(int(nws), 4),), dtype=torch.uint8, device=dev)
-    _lib.check(lib.avz_ibm_cov_f32(_ptr(mix), _ptr(tgt), _ptr(itf), B, L, cfg.n_fft, cfg.hop, float(cfg.norm_eps),
-                                   _ptr(bits), _ptr(Rp), _ptr(ms), _ptr(ws), _stream()), "avz_ibm_cov_f32")
+    if spec is not None:
+        _lib.check(lib.avz_ibm_cov_keep_f32(_ptr(mix), _ptr(tgt), _ptr(itf), B, L, cfg.n_fft, cfg.hop,
+                                            float(cfg.norm_eps), _ptr(bits), _ptr(Rp), _ptr(ms), _ptr(ws), _ptr(spec),
+                                            _stream()), "avz_ibm_cov_keep_f32")
+    else:
+        _lib.check(lib.avz_ibm_cov_f32(_ptr(mix), _ptr(tgt), _ptr(itf), B, L, cfg.n_fft, cfg.hop, float(cfg.norm_eps),
+                                       _ptr(bits), _ptr(Rp), _ptr(ms), _ptr(ws), _stream()), "avz_ibm_cov_f32")
     return bits, Rp, ms
 
 
@@ -348,7 +362,8 @@ def ibm_exact_bits(tgt: torch.Tensor, itf: torch.Tensor, cfg: MvdrConfig) -> tor
     return bits
 
 
-def wave_masked_covariance(mix: torch.Tensor, mask: torch.Tensor, cfg: MvdrConfig):
+def wave_masked_covariance(mix: torch.Tensor, mask: torch.Tensor, cfg: MvdrConfig,
+                           spec: Optional[torch.Tensor] = None):
     """Learned-mask pass A (full_audio.../inference.py:90,102-108): mix [B,2,L], target-probability mask [B,F,T]
     -> (R packed [B,F,4], msum [B,F]); noise weight = 1 - mask."""
     lib = _lib.load()
@@ -359,23 +374,34 @@ def wave_masked_covariance(mix: torch.Tensor, mask: torch.Tensor, cfg: MvdrConfi
     ms = torch.empty((B, F), dtype=torch.float32, device=dev)
     nws = lib.avz_ibm_cov_ws_bytes(B, L, cfg.n_fft, cfg.hop)
     ws = torch.empty((max(int(nws), 4),), dtype=torch.uint8, device=dev)
-    _lib.check(lib.avz_wave_mask_cov_f32(_ptr(mix), _ptr(mask), B, L, cfg.n_fft, cfg.hop, float(cfg.sqrt_eps),
-                                         float(cfg.norm_eps), _ptr(Rp), _ptr(ms), _ptr(ws), _stream()),
-               "avz_wave_mask_cov_f32")
+    if spec is not None:
+        _lib.check(lib.avz_wave_mask_cov_keep_f32(_ptr(mix), _ptr(mask), B, L, cfg.n_fft, cfg.hop, float(cfg.sqrt_eps),
+                                                  float(cfg.norm_eps), _ptr(Rp), _ptr(ms), _ptr(ws), _ptr(spec),
+                                                  _stream()), "avz_wave_mask_cov_keep_f32")
+    else:
+        _lib.check(lib.avz_wave_mask_cov_f32(_ptr(mix), _ptr(mask), B, L, cfg.n_fft, cfg.hop, float(cfg.sqrt_eps),
+                                             float(cfg.norm_eps), _ptr(Rp), _ptr(ms), _ptr(ws), _stream()),
+                   "avz_wave_mask_cov_f32")
     return Rp, ms
 
 
 def mvdr_apply(mix: torch.Tensor, w: torch.Tensor, cfg: MvdrConfig, ibm_bits: Optional[torch.Tensor] = None,
-               mask: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Pass B (oracle_debug.py:80-93): STFT(mix) -> w^H y -> post-filter -> iSTFT/OLA.
-    -> (out [B,(T-1)*hop] un-normalised, peak [B])."""
+               mask: Optional[torch.Tensor] = None, spec: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Pass B (oracle_debug.py:80-93): STFT(mix) (or the spectrum pass A kept in `spec`) -> w^H y -> post-filter ->
+    iSTFT/OLA.  -> (out [B,(T-1)*hop] un-normalised, peak [B])."""
     B, _, L = mix.shape
     T = num_frames(L, cfg.n_fft, cfg.hop)
     out = torch.empty((B, (T - 1) * cfg.hop), dtype=torch.float32, device=mix.device)
     peak = torch.zeros((B,), dtype=torch.float32, device=mix.device)
     cc = cfg.to_c()
-    _lib.check(_lib.load().avz_mvdr_apply_f32(_ptr(mix), _ptr(w), _ptr(ibm_bits), _ptr(mask), B, L, cfg.n_fft, cfg.hop,
-                                              C.byref(cc), _ptr(out), _ptr(peak), _stream()), "avz_mvdr_apply_f32")
+    if spec is not None:
+        _lib.check(_lib.load().avz_mvdr_apply_kept_f32(_ptr(spec), _ptr(w), _ptr(ibm_bits), _ptr(mask), B, L, cfg.n_fft,
+                                                       cfg.hop, C.byref(cc), _ptr(out), _ptr(peak), _stream()),
+                   "avz_mvdr_apply_kept_f32")
+    else:
+        _lib.check(_lib.load().avz_mvdr_apply_f32(_ptr(mix), _ptr(w), _ptr(ibm_bits), _ptr(mask), B, L, cfg.n_fft,
+                                                  cfg.hop, C.byref(cc), _ptr(out), _ptr(peak), _stream()),
+                   "avz_mvdr_apply_f32")
     return out, peak
 
 
@@ -395,9 +421,10 @@ def oracle_mask_mvdr(mix, tgt, itf, cfg: MvdrConfig = PRESETS["baseline_oracle"]
     utterance when cfg.peak_eps is not None)."""
     io = _Io()
     mix, tgt, itf, single = _batchify(mix, tgt, itf, io)
-    bits, Rp, ms = ibm_covariance(mix, tgt, itf, cfg)
+    spec = alloc_kept_spectrum(mix, cfg)
+    bits, Rp, ms = ibm_covariance(mix, tgt, itf, cfg, spec)
     w = mvdr_weights(Rp, steering_vectors(cfg, mix.device), cfg)
-    out, peak = mvdr_apply(mix, w, cfg, ibm_bits=bits if cfg.post == "one_minus_noise" else None)
+    out, peak = mvdr_apply(mix, w, cfg, ibm_bits=bits if cfg.post == "one_minus_noise" else None, spec=spec)
     parts = None
     if return_parts:
         parts = {"ibm_bits": bits, "R": Rp, "msum": ms, "w": w, "x_raw": out.clone(), "peak": peak}
@@ -413,9 +440,10 @@ def learned_mask_mvdr(mix, mask, cfg: MvdrConfig = PRESETS["baseline_learned"]):
     io = _Io()
     mix, _, _, single = _batchify(mix, None, None, io)
     mask = io.take(mask, torch.float32).reshape(mix.shape[0], cfg.n_freq, -1).contiguous()
-    Rp, _ = wave_masked_covariance(mix, mask, cfg)
+    spec = alloc_kept_spectrum(mix, cfg)
+    Rp, _ = wave_masked_covariance(mix, mask, cfg, spec)
     w = mvdr_weights(Rp, steering_vectors(cfg, mix.device), cfg)
-    out, peak = mvdr_apply(mix, w, cfg, mask=mask if cfg.post in ("floor", "mask") else None)
+    out, peak = mvdr_apply(mix, w, cfg, mask=mask if cfg.post in ("floor", "mask") else None, spec=spec)
     if cfg.peak_eps is not None:
         peak_normalise(out, peak, cfg.peak_eps)
     return io.give(out[0] if single else out)

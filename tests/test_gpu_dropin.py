@@ -128,6 +128,28 @@ def test_wave_features_equal_spectrum_features(az):
     assert torch.equal(p, az.physics_features(az.stft(x, 1024, 512)))
 
 
+def test_fast_path_features_512(az):
+    """n_fft 512 features come from the register-FFT kernel with shared-memory staged, coalesced stores; compare with
+    the oracle (float64) on well-conditioned bins, and with the spectrum-based op."""
+    from avzoom import synth
+    mix, _, _ = synth.make_batch(3, 3, 1.1, 3)            # T = 139: ragged last tile of 32 frames
+    x = torch.from_numpy(mix).cuda()
+    X = az.wave_features(x, 512, 128).cpu().numpy()
+    assert X.shape == (3, 2, 257, 139)
+    for b in range(3):
+        Yref = O.stft_scipy(mix[b], 512, 128)
+        Xref = O.logmag_ipd(Yref)
+        strong = np.abs(Yref).min(axis=0) > 1e-4 * np.abs(Yref).max()
+        assert np.max(np.abs(X[b, 0] - Xref[0])[strong]) < 1e-3
+        d = (X[b, 1] - Xref[1]).astype(np.float64)
+        assert np.max(np.abs((d + np.pi) % (2 * np.pi) - np.pi)[strong]) < 1e-3
+        assert np.mean(np.abs(d[strong]) > 1.0) < 2e-3
+    Xw = az.wave_features(x, 512, 128, "logmag_ipd_wrapped")
+    assert float(Xw[:, 1].abs().max()) <= np.pi + 1e-6
+    Xh = az.wave_features(x, 512, 256)                    # hop 256 variant of the same kernel
+    assert Xh.shape == (3, 2, 257, 70) and bool(torch.isfinite(Xh).all())
+
+
 def test_oracle_reverb_main(az, golden_dir, tmp_path):
     """oracle_reverb.main(args): IBM covariance, MVDR with --sigma/--hp, soft (IRM) post-filter, against the oracle
     assembled from the same pieces."""
