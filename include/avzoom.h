@@ -123,6 +123,15 @@ AVZ_API int avz_spec_mask_cov_f32(const float* Y, const float* noise_w, int B, i
  * bins k < cfg->hp_bins get w = 0 (AVZ_HP_ZERO) or [1,0] (AVZ_HP_MIC0); det == 0 -> [1,0]. */
 AVZ_API int avz_mvdr_weights_f32(const float* R, const float* dvec, int B, int F, const AvzMvdrCfg* cfg, float* w, void* stream);
 
+/* ---- hybrid hard-null weights: replaces Final_pipeline/src/inference.py:56-94 (eigh + cond + solve per bin) with a
+ * closed form in float64.  R [B,F,4] is the interference covariance sum m y y^H / (sum m + 1e-6), m = 1 - mask
+ * (avz_spec_mask_cov_f32 / avz_wave_mask_cov_f32 with sqrt_eps = 0); dvec [F,2] the un-normalised steering vectors;
+ * bins k < bypass_bins (f < 200 Hz there) get w = [1, 0] (mic 0 passes).  Condition number > 10 -> w = v_tgt / 2.
+ * A bin whose covariance is exactly zero gets delay-and-sum (the reference emits NaN there).  w [B,F,2] complex64,
+ * usable by avz_beamform_f32 and by avz_mvdr_apply_f32 (any weights are "beamformer weights" to pass B). */
+AVZ_API int avz_hybrid_null_weights_f32(const float* R, const float* dvec, int B, int F, int bypass_bins, float* w,
+                                void* stream);
+
 /* ---- beamform a given spectrum: oracle_debug.py:80.  w [B,F,2], Y [B,2,F,T] -> S [B,F,T] complex64. */
 AVZ_API int avz_beamform_f32(const float* w, const float* Y, int B, int F, int T, float* S, void* stream);
 

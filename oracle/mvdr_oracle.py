@@ -25,7 +25,7 @@ __all__ = [
     "beamform", "post_filter", "peak_normalise", "oracle_mask_mvdr", "geometric_mask_mvdr",
     "learned_mask_mvdr_chunk", "chunked_enhance", "batch_mvdr_vec", "logmag_ipd", "physics_features",
     "sir_sdr_unit_output", "osinr_osir", "far_field_delays", "fractional_delay", "mix_far_field",
-    "streaming_mvdr",
+    "streaming_mvdr", "hybrid_hard_null",
 ]
 
 
@@ -315,6 +315,45 @@ def batch_mvdr_vec(Y, mask, f_bins, d_vectors, sigma: float) -> np.ndarray:
     denom = np.matmul(np.transpose(dv.conj(), (0, 2, 1)), u) + 1e-10
     w = u / denom
     return np.matmul(np.transpose(w.conj(), (0, 2, 1)), np.transpose(Y, (1, 0, 2)))[:, 0, :]
+
+
+def hybrid_hard_null(Y, mask, f_bins, mic_dist: float = 0.08, c: float = 343.0, angle_deg: float = 90.0) -> np.ndarray:
+    """Final_pipeline/src/inference.py:28-98 (`hybrid_hard_null_bf`) restated: per bin, interference covariance
+    R = (Y m)(Y)^H / (sum m + 1e-6) with m = 1 - mask; principal eigenvector (eigh) phase-normalised to mic 0; target
+    steering vector normalised to mic 0; constraint matrix C = [v_tgt, v_int]; 2-norm condition number > 10 ->
+    delay-and-sum w = v_tgt / 2, else solve C^H w = [1, 0]; bins below 200 Hz pass mic 0.  """
+    Y = np.asarray(Y, dtype=np.complex128)
+    m_int = 1.0 - np.asarray(mask, dtype=np.float64)
+    F, T = Y.shape[1], Y.shape[2]
+    S = np.zeros((F, T), dtype=complex)
+    e1 = np.array([[1], [0]], dtype=np.complex64)
+    for i in range(F):
+        f_hz = f_bins[i]
+        if f_hz < 200:
+            S[i, :] = Y[0, i, :]
+            continue
+        Yv = Y[:, i, :]
+        mv = m_int[i, :]
+        R = (Yv * mv) @ (Yv.conj().T) / (np.sum(mv) + 1e-6)
+        _, vecs = np.linalg.eigh(R)
+        v_int = vecs[:, -1].reshape(2, 1)
+        v_int = v_int / (v_int[0] / (np.abs(v_int[0]) + 1e-10))
+        theta = np.deg2rad(angle_deg)
+        tau1 = (mic_dist / 2) * np.cos(theta) / c
+        tau2 = (mic_dist / 2) * np.cos(theta - np.pi) / c
+        om = 2 * np.pi * f_hz
+        v_tgt = np.array([[np.exp(-1j * om * tau1)], [np.exp(-1j * om * tau2)]])
+        v_tgt = v_tgt / (v_tgt[0] + 1e-10)
+        Cm = np.column_stack((v_tgt, v_int))
+        if np.linalg.cond(Cm) > 10:
+            w = v_tgt / 2
+        else:
+            try:
+                w = np.linalg.solve(Cm.conj().T, e1)
+            except np.linalg.LinAlgError:
+                w = v_tgt / 2
+        S[i, :] = (w.conj().T @ Yv).squeeze()
+    return S
 
 
 # --------------------------------------------------------------------------------------

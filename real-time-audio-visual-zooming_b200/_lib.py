@@ -55,6 +55,7 @@ SIGNATURES = {
     "avz_wave_mask_cov_f32": (_i, [_p, _p, _i, _l, _i, _i, _f, _f, _p, _p, _p, _p]),
     "avz_spec_mask_cov_f32": (_i, [_p, _p, _i, _i, _i, _f, _f, _p, _p, _p]),
     "avz_mvdr_weights_f32": (_i, [_p, _p, _i, _i, C.POINTER(AvzMvdrCfg), _p, _p]),
+    "avz_hybrid_null_weights_f32": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "avz_beamform_f32": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "avz_mvdr_apply_f32": (_i, [_p, _p, _p, _p, _i, _l, _i, _i, C.POINTER(AvzMvdrCfg), _p, _p, _p]),
     "avz_spec_ws_bytes": (_l, [_i, _l, _i, _i]),

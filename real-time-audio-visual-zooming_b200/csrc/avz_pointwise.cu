@@ -53,6 +53,76 @@ __global__ void k_mvdr_weights(const float4* __restrict__ R, const float2* __res
   w[2 * (int64_t)idx + 1] = w1;
 }
 
+// ------------------------------------------------------------------------------------------
+// Hybrid hard-null weights.  Replaces Final_pipeline/src/inference.py:56-94 per bin, closed form in float64:
+// principal eigenvector of the Hermitian 2x2 interference covariance (np.linalg.eigh), phase-normalised to mic 0;
+// target steering vector normalised to mic 0; C = [v_tgt, v_int]; cond_2(C) > 10 -> delay-and-sum v_tgt / 2, else
+// w solves C^H w = [1, 0].  Bins k < bypass_bins pass mic 0 (w = [1, 0]).
+// ------------------------------------------------------------------------------------------
+__global__ void k_hybrid_null_weights(const float4* __restrict__ R, const float2* __restrict__ dvec, int B, int F,
+                                      int bypass_bins, float2* __restrict__ w) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * F) return;
+  const int k = idx % F;
+  cd w0 = {1.0, 0.0}, w1 = {0.0, 0.0};
+  if (k >= bypass_bins) {
+    const float4 r = R[idx];
+    const double a = r.x, c = r.y;
+    const cd b = {(double)r.z, (double)r.w};
+    // target steering vector, normalised to mic 0: v / (v[0] + 1e-10)
+    const cd d0 = {(double)dvec[2 * k].x, (double)dvec[2 * k].y};
+    const cd d1 = {(double)dvec[2 * k + 1].x, (double)dvec[2 * k + 1].y};
+    const cd den = {d0.x + 1e-10, d0.y};
+    const cd vt0 = cddiv(d0, den), vt1 = cddiv(d1, den);
+    w0 = {0.5 * vt0.x, 0.5 * vt0.y};   // delay-and-sum default
+    w1 = {0.5 * vt1.x, 0.5 * vt1.y};
+    // principal eigenvector of [[a, b], [conj b, c]]
+    const double half = 0.5 * (a - c), bb = b.x * b.x + b.y * b.y;
+    const double rad = sqrt(half * half + bb);
+    cd v0, v1;
+    if (half >= 0.0) {          // lambda - c = half + rad is the well-conditioned difference
+      v0 = {half + rad, 0.0};
+      v1 = {b.x, -b.y};
+    } else {                    // lambda - a = rad - half
+      v0 = b;
+      v1 = {rad - half, 0.0};
+    }
+    const double nrm = sqrt(v0.x * v0.x + v0.y * v0.y + v1.x * v1.x + v1.y * v1.y);
+    const double m0 = sqrt(v0.x * v0.x + v0.y * v0.y) / (nrm > 0.0 ? nrm : 1.0);   // |v_int[0]| of the unit vector
+    if (nrm > 0.0 && m0 > 0.0) {
+      // v_int = v / (v0 / (|v0| + 1e-10)):  v_int[0] = |v0| + 1e-10 (real), v_int[1] = v1 (|v0| + 1e-10) / v0
+      const cd u0 = {v0.x / nrm, v0.y / nrm}, u1 = {v1.x / nrm, v1.y / nrm};
+      const double s = m0 + 1e-10;
+      const cd vi0 = {s, 0.0};
+      const cd q = cddiv(u1, u0);
+      const cd vi1 = {q.x * s, q.y * s};
+      // cond_2 of C = [v_tgt, v_int] from the Gram matrix G = C^H C
+      const double g00 = vt0.x * vt0.x + vt0.y * vt0.y + vt1.x * vt1.x + vt1.y * vt1.y;
+      const double g11 = vi0.x * vi0.x + vi1.x * vi1.x + vi1.y * vi1.y;
+      const cd g01 = {vt0.x * vi0.x + vt1.x * vi1.x + vt1.y * vi1.y, -vt0.y * vi0.x + vt1.x * vi1.y - vt1.y * vi1.x};
+      const double T = g00 + g11, D = g00 * g11 - (g01.x * g01.x + g01.y * g01.y);
+      const double disc = sqrt(fmax(T * T - 4.0 * D, 0.0));
+      const double smax2 = 0.5 * (T + disc), smin2 = D / smax2;   // smin^2 = D / smax^2 avoids cancellation
+      const bool ok = (D > 0.0) && (smax2 <= 100.0 * smin2);      // cond <= 10
+      if (ok) {
+        // C^H w = [1, 0]:  [[conj vt0, conj vt1], [conj vi0, conj vi1]] w = e1
+        const cd p = {vt0.x, -vt0.y}, qq = {vt1.x, -vt1.y}, rr = {vi0.x, -vi0.y}, ss = {vi1.x, -vi1.y};
+        const cd ps = cdmul(p, ss), qr = cdmul(qq, rr);
+        const cd det = {ps.x - qr.x, ps.y - qr.y};
+        if (det.x != 0.0 || det.y != 0.0) {
+          w0 = cddiv(ss, det);
+          const cd t = cddiv(rr, det);
+          w1 = {-t.x, -t.y};
+        }
+      }
+    }
+    // an exactly zero covariance (no interference-dominated frame in this bin) has no principal direction; the
+    // reference divides by zero there and emits NaN - delay-and-sum is kept instead (documented deviation)
+  }
+  w[2 * (int64_t)idx] = make_float2((float)w0.x, (float)w0.y);
+  w[2 * (int64_t)idx + 1] = make_float2((float)w1.x, (float)w1.y);
+}
+
 // S[b,k,t] = conj(w0) Y0 + conj(w1) Y1
 __global__ void k_beamform(const float2* __restrict__ w, const float2* __restrict__ Y, int F, int T,
                            float2* __restrict__ S) {
@@ -242,6 +312,16 @@ int avz_mvdr_weights_f32(const float* R, const float* dvec, int B, int F, const 
   k_mvdr_weights<<<(B * F + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float4*>(R), reinterpret_cast<const float2*>(dvec), B, F, *cfg, reinterpret_cast<float2*>(w));
   AVZ_LAUNCH_OK("k_mvdr_weights");
+  return AVZ_OK;
+}
+
+int avz_hybrid_null_weights_f32(const float* R, const float* dvec, int B, int F, int bypass_bins, float* w, void* stream) {
+  if (!R || !dvec || !w || B <= 0 || F <= 0 || bypass_bins < 0)
+    return set_error(AVZ_EINVAL, "avz_hybrid_null_weights_f32: bad argument");
+  k_hybrid_null_weights<<<(B * F + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(R), reinterpret_cast<const float2*>(dvec), B, F, bypass_bins,
+      reinterpret_cast<float2*>(w));
+  AVZ_LAUNCH_OK("k_hybrid_null_weights");
   return AVZ_OK;
 }
 

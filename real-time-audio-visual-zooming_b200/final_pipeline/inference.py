@@ -1,19 +1,21 @@
-"""Mirror of Final_pipeline/src/inference.py: `get_steering_vector_single` (:16-26) and
-`enhance_audio(run_name, input_path, model_path)` (:144-238).
+"""Mirror of Final_pipeline/src/inference.py: `get_steering_vector_single` (:16-26), `hybrid_hard_null_bf` (:28-98)
+and `enhance_audio(run_name, input_path, model_path)` (:144-238).
 
 The chunk loop (2 s windows, 50 % overlap, count-averaged OLA clipped to the input length, peak normalisation with
-1e-9) is the reference's; the per-chunk beamformer here is the mask-driven MVDR of this project's hot path with the
-Final_pipeline constants (n_fft 1024 / hop 512, d = 0.08, mic-0 pass-through below 200 Hz, post-filter S * mask).
-The reference's `hybrid_hard_null_bf` (:28-98, an eigenvector null-steering beamformer, not MVDR) is the next row of
-the scope table and is not built yet; calling it raises NotImplementedError."""
+1e-9), the hybrid hard-null beamformer (interference covariance -> principal eigenvector -> 2x2 constraint solve with
+a condition-number fallback to delay-and-sum, mic-0 pass-through below 200 Hz) and the post-filter S * mask are the
+reference's; all windows of a recording run as one batch through the fused kernels.  The mask estimator is a torch
+module ((B,2,F,T) log-mag + IPD features -> (B,F,T)) because the reference's `.tflite` blob is not shipped
+(.MISSING_LARGE_BLOBS); its 4-channel "physics" feature layout is available as `ops.wave_features(..., 'physics')`."""
 from __future__ import annotations
 
 import os
 import time
 
 import numpy as np
+import torch
 
-from .. import wavio
+from .. import ops, wavio
 from ..config import MvdrConfig
 from ..core import chunked
 from . import config
@@ -22,8 +24,10 @@ ANGLE_TARGET = 90.0
 FREQ_BINS = (config.N_FFT // 2) + 1
 N_MICS = 2
 
+# constants of Final_pipeline/src/inference.py as one record: no diagonal loading / MVDR here, the weights come from
+# the hybrid null solve; pass B only needs the STFT shape and the post-filter (S * mask, :219)
 FINAL_CFG = MvdrConfig(fs=config.FS, n_fft=config.N_FFT, hop=config.HOP_LEN, mic_dist=config.MIC_DIST, c=config.C_SPEED,
-                       sigma=1e-5, hp_hz=200.0, hp_mode="mic0", post="mask", peak_eps=None)
+                       angle_deg=ANGLE_TARGET, sigma=0.0, hp_hz=200.0, hp_mode="mic0", post="mask", peak_eps=None)
 
 
 def get_steering_vector_single(f, angle_deg, d, c):
@@ -36,9 +40,40 @@ def get_steering_vector_single(f, angle_deg, d, c):
     return v / (v[0] + 1e-10)
 
 
+def _steering(f_bins, device):
+    f = np.asarray(f_bins, dtype=np.float64)
+    th = np.deg2rad(ANGLE_TARGET)
+    tau1 = (config.MIC_DIST / 2) * np.cos(th) / config.C_SPEED
+    tau2 = (config.MIC_DIST / 2) * np.cos(th - np.pi) / config.C_SPEED
+    om = 2 * np.pi * f
+    d = np.stack([np.exp(-1j * om * tau1), np.exp(-1j * om * tau2)], axis=1).astype(np.complex64)
+    return torch.from_numpy(d).to(device)
+
+
 def hybrid_hard_null_bf(Y, mask, f_bins):
-    raise NotImplementedError("hybrid hard-null beamformer (Final_pipeline/src/inference.py:28-98): next scope row, "
-                              "see DESIGN.md; enhance_audio uses mask-driven MVDR")
+    """Y (M=2, F, T) complex STFT, mask (F, T) target probabilities, f_bins (F,) Hz -> beamformed (F, T) complex.
+    numpy in -> numpy out; CUDA tensors in -> CUDA tensor out."""
+    is_np = isinstance(Y, np.ndarray)
+    Yt = torch.as_tensor(Y).to("cuda", torch.complex64) if is_np else Y.to(torch.complex64)
+    mt = torch.as_tensor(mask).to(Yt.device, torch.float32)
+    f = np.asarray(f_bins, dtype=np.float64)
+    R = ops.masked_covariance(Yt, 1.0 - mt, sqrt_eps=0.0, norm_eps=1e-6, packed=True)
+    w = ops.hybrid_null_weights(R, _steering(f, Yt.device), int(np.sum(f < 200)))
+    S = ops.beamform(w, Yt)
+    return S.cpu().numpy() if is_np else S
+
+
+def enhance_chunks(chunks: torch.Tensor, model, cfg: MvdrConfig = FINAL_CFG) -> torch.Tensor:
+    """One batch of 2 s windows (n, 2, win) -> (n, iSTFT length): features (STFT fused) -> mask model -> interference
+    covariance (STFT fused) -> hybrid-null weights -> beamform + S * mask + iSTFT (fused)."""
+    X = ops.wave_features(chunks, cfg.n_fft, cfg.hop, "logmag_ipd")
+    with torch.no_grad():
+        mask = model(X).float().contiguous()
+    spec = ops.alloc_kept_spectrum(chunks, cfg)
+    Rp, _ = ops.wave_masked_covariance(chunks, mask, cfg, spec)
+    w = ops.hybrid_null_weights(Rp, _steering(cfg.freqs(), chunks.device), cfg.hp_bins())
+    out, _ = ops.mvdr_apply(chunks, w, cfg, mask=mask, spec=spec)
+    return out
 
 
 def enhance_audio(run_name, input_path, model_path, model=None):
@@ -61,7 +96,10 @@ def enhance_audio(run_name, input_path, model_path, model=None):
             print(f"Failed to load mask model: {e}")
             return
     start_time = time.time()
-    final = chunked.enhance_waveform(y, model, FINAL_CFG, win=config.WIN_SIZE, buf_extra=0)
+    yt = torch.as_tensor(np.asarray(y, dtype=np.float32)).cuda()
+    chunks, stride = chunked.split_chunks(yt, config.WIN_SIZE)
+    outs = enhance_chunks(chunks, model, FINAL_CFG)
+    final = chunked.overlap_add_chunks(outs, yt.shape[0], config.WIN_SIZE, stride, buf_extra=0).cpu().numpy()
     print(f"Total processing time: {time.time() - start_time:.3f}s")
     final = final / (np.max(np.abs(final)) + 1e-9)
     wavio.write(output_path, final, config.FS)

@@ -19,7 +19,7 @@ from .config import MvdrConfig, PRESETS
 
 __all__ = [
     "num_frames", "stft", "istft", "ibm", "ibm_target_label", "geometric_mask", "masked_covariance",
-    "steering_vectors", "mvdr_weights", "beamform", "logmag_ipd", "physics_features", "sir_scores",
+    "steering_vectors", "mvdr_weights", "hybrid_null_weights", "beamform", "logmag_ipd", "physics_features", "sir_scores",
     "ibm_covariance", "wave_masked_covariance", "mvdr_apply", "peak_normalise", "unpack_ibm",
     "oracle_mask_mvdr", "learned_mask_mvdr", "covariance_to_matrix", "ibm_exact_bits", "irm", "wave_features", "alloc_kept_spectrum",
 ]
@@ -240,6 +240,26 @@ def mvdr_weights(R, d, cfg: MvdrConfig = PRESETS["baseline_oracle"]):
     cc = cfg.to_c()
     _lib.check(_lib.load().avz_mvdr_weights_f32(_ptr(Rp), _ptr(d), B, F, C.byref(cc), _ptr(w), _stream()),
                "avz_mvdr_weights_f32")
+    return io.give(w.reshape(*lead, F, 2))
+
+
+def hybrid_null_weights(R, d, bypass_bins: int):
+    """Hybrid hard-null weights (Final_pipeline/src/inference.py:56-94) from the interference covariance.
+    R (..., F, 2, 2) complex or packed (..., F, 4); d (F, 2) un-normalised steering vectors -> w (..., F, 2) complex64;
+    bins below `bypass_bins` pass mic 0."""
+    io = _Io()
+    if isinstance(R, np.ndarray):
+        r_dtype = torch.complex64 if np.iscomplexobj(R) else torch.float32
+    else:
+        r_dtype = torch.complex64 if R.is_complex() else torch.float32
+    Rp = _pack_covariance(io.take(R, r_dtype))
+    d = io.take(d, torch.complex64).reshape(-1, 2).contiguous()
+    F = Rp.shape[-2]
+    lead = Rp.shape[:-2]
+    B = int(np.prod(lead)) if lead else 1
+    w = torch.empty((B, F, 2), dtype=torch.complex64, device=Rp.device)
+    _lib.check(_lib.load().avz_hybrid_null_weights_f32(_ptr(Rp), _ptr(d), B, F, int(bypass_bins), _ptr(w), _stream()),
+               "avz_hybrid_null_weights_f32")
     return io.give(w.reshape(*lead, F, 2))
 
 

@@ -129,6 +129,9 @@ def test_process_chunk_and_main_deploy(speech, learned):
     assert rel_l2(full, learned["main_deploy_out"]) < 2e-5
 
 
-def test_hybrid_null_golden_present(helpers):
-    # Final_pipeline/src/inference.py:28-98 is a "next" row; vector kept for it.
-    assert helpers["hn_out"].shape == (513, 64)
+def test_hybrid_hard_null(helpers):
+    # Final_pipeline/src/inference.py:28-98: the reference's own output on seeded inputs
+    got = O.hybrid_hard_null(helpers["bm_Y"].astype(np.complex128), helpers["bm_mask"].astype(np.float64),
+                             helpers["asv_f_bins"])
+    assert got.shape == (513, 64)
+    assert rel_l2(got, helpers["hn_out"]) < 1e-12
