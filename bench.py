@@ -238,17 +238,29 @@ def run_ours(args):
     value = audio_s_per_step / (ms_per_step * 1e-3)
 
     # ---- per-kernel timing for the roofline (CUDA events on the launching stream, same resident inputs)
-    ktimes = enh.time_kernels(mix, tgt, itf, iters=max(3, min(args.steps, 10)))
+    ktimes = enh.time_each_kernel(mix, tgt, itf, iters=max(3, min(args.steps, 10)))
     peak_gbs, peak_src = load_peak()
     samples = B * L
-    # algorithmic (compulsory) bytes of each pass: A reads mix 2L + tgt L + int L; B reads mix 2L and writes out L
-    algo = {"pass A (k512_ibm + k512_ibm_fixup + k512_cov + k_cov_finalize)": 16.0 * samples,
-            "pass B (k512_apply)": 12.0 * samples}
-    dom = max(ktimes, key=lambda k: ktimes[k] if k in algo else -1)
+    # Algorithmic (compulsory) bytes each kernel must move per launch: k512_ibm reads tgt L + int L,
+    # k512_cov reads mix 2L, k512_apply writes out L (its input is the spectrum pass A kept: not compulsory traffic;
+    # the recomputing variant would read mix 2L), k_peak_normalise reads and writes out L.  The path as a whole:
+    # 20 B/sample (ALGO_BYTES_PER_SAMPLE).
+    algo = {"k512_ibm": 8.0 * samples, "k512_cov": 8.0 * samples, "k512_apply": 4.0 * samples,
+            "k_peak_normalise": 8.0 * samples}
+    dom = max(algo, key=lambda k: ktimes.get(k, 0.0))
     achieved = algo[dom] / (ktimes[dom] * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    try:  # DRAM bytes per launch of that kernel from the committed ncu --set full capture of the same shape
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+        traffic = tj["per_launch"][dom]["dram_read_bytes"] + tj["per_launch"][dom]["dram_write_bytes"]
+        traffic_src = "profiles/r1_ncu_traffic.json (" + tj["source"] + ")"
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak_gbs, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo[dom], "kernel_ms": ktimes,
+                "note": "fp32-issue-bound path (DESIGN.md 3.1): ~2700 warp-instructions per frame set the time, not HBM",
+                "path_achieved_GBps": (value / world) * FS * ALGO_BYTES_PER_SAMPLE / 1e9,
                 "path_frac_of_hbm_roofline": (value / world) * FS * ALGO_BYTES_PER_SAMPLE / (peak_gbs * 1e9)}
 
     # ---- end to end through the public host-buffer API

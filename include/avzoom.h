@@ -75,6 +75,14 @@ AVZ_API const char* avz_last_error(void);
  * otherwise done on first use).  Do this before capturing calls into a CUDA graph. */
 AVZ_API int avz_init(int n_fft);
 
+/* Per-kernel timing of the fused fast path, for benchmarks: while enabled, CUDA events are recorded on the launching
+ * stream around each kernel; avz_profile_get() waits for them and returns the device time (ms) of the LAST launch of
+ * each slot: 0 k512_ibm, 1 k512_ibm_fixup, 2 k512_cov, 3 k_cov_finalize, 4 k_mvdr_weights, 5 k512_apply,
+ * 6 k_peak_normalise (-1 if that kernel has not run since enabling).  ms_host: host array of >= 7 floats.
+ * Not thread-safe; meant for single-stream measurement runs. */
+AVZ_API int avz_profile_enable(int on);
+AVZ_API int avz_profile_get(float* ms_host, int n);
+
 /* scipy.signal.stft frame count (boundary='zeros', padded=True). */
 AVZ_API int64_t avz_num_frames(int64_t L, int n_fft, int hop);
 

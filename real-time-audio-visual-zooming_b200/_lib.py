@@ -45,6 +45,8 @@ SIGNATURES = {
     "avz_version": (_i, []),
     "avz_last_error": (C.c_char_p, []),
     "avz_init": (_i, [_i]),
+    "avz_profile_enable": (_i, [_i]),
+    "avz_profile_get": (_i, [C.POINTER(C.c_float), _i]),
     "avz_num_frames": (_l, [_l, _i, _i]),
     "avz_stft_f32": (_i, [_p, _i, _i, _l, _i, _i, _p, _p]),
     "avz_istft_f32": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),

@@ -24,6 +24,12 @@ int tables_for(int n_fft, Tables* out);
 int check_fft_args(int n_fft, int hop, int64_t L);
 int num_sms();
 
+// Optional per-kernel timing for bench.py (avz_profile_enable / avz_profile_get): CUDA events recorded on the
+// launching stream right before and after each kernel of the fused path.
+enum ProfSlot { PROF_IBM = 0, PROF_FIXUP, PROF_COV, PROF_FINALIZE, PROF_WEIGHTS, PROF_APPLY, PROF_NORMALISE, PROF_COUNT };
+void prof_begin(int slot, cudaStream_t st);
+void prof_end(int slot, cudaStream_t st);
+
 #define AVZ_CUDA_OK(expr)                                                                   \
   do {                                                                                      \
     cudaError_t _e = (expr);                                                                \

@@ -545,8 +545,10 @@ static int launch_cov512(const float* mix, const float* tgt, const float* itf, c
                : o512::launch_ibm_cov<256>(mix, tgt, itf, mask, B, L, sqrt_eps, ibm_bits, (float*)ws, &chunks, spec, st);
   if (rc) return rc;
   const int F = 257;
+  prof_begin(PROF_FINALIZE, st);
   k_cov_finalize<<<(B * F + 255) / 256, 256, 0, st>>>((const float*)ws, B, F, Geo<512>::FP, chunks, norm_eps,
                                                       reinterpret_cast<float4*>(R), msum);
+  prof_end(PROF_FINALIZE, st);
   AVZ_LAUNCH_OK("k_cov_finalize");
   return AVZ_OK;
 }
@@ -608,7 +610,9 @@ int avz_peak_normalise_f32(float* x, int B, int64_t n, const float* peak, float 
   int gx = (int)((n / 4 + 1023) / 1024);   // ~4 float4 per thread
   if (gx > 64) gx = 64;
   if (gx < 1) gx = 1;
+  prof_begin(PROF_NORMALISE, (cudaStream_t)stream);
   k_peak_normalise<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(x, n, peak, peak_eps);
+  prof_end(PROF_NORMALISE, (cudaStream_t)stream);
   AVZ_LAUNCH_OK("k_peak_normalise");
   return AVZ_OK;
 }

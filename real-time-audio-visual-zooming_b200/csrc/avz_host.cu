@@ -83,6 +83,21 @@ int tables_for(int n_fft, Tables* out) {
   return AVZ_OK;
 }
 
+static bool g_prof_on = false;
+static cudaEvent_t g_prof_ev[PROF_COUNT][2];
+static bool g_prof_made = false;
+static bool g_prof_hit[PROF_COUNT];
+
+void prof_begin(int slot, cudaStream_t st) {
+  if (!g_prof_on) return;
+  cudaEventRecord(g_prof_ev[slot][0], st);
+}
+void prof_end(int slot, cudaStream_t st) {
+  if (!g_prof_on) return;
+  cudaEventRecord(g_prof_ev[slot][1], st);
+  g_prof_hit[slot] = true;
+}
+
 int check_fft_args(int n_fft, int hop, int64_t L) {
   if (n_fft != 256 && n_fft != 512 && n_fft != 1024)
     return set_error(AVZ_EINVAL, "n_fft=%d unsupported (256, 512, 1024)", n_fft);
@@ -107,6 +122,31 @@ int avz_init(int n_fft) {
   if (n_fft != 256 && n_fft != 512 && n_fft != 1024) return avz::set_error(AVZ_EINVAL, "n_fft=%d unsupported", n_fft);
   avz::Tables t;
   return avz::tables_for(n_fft, &t);
+}
+
+int avz_profile_enable(int on) {
+  using namespace avz;
+  if (on && !g_prof_made) {
+    for (int i = 0; i < PROF_COUNT; ++i)
+      for (int j = 0; j < 2; ++j) AVZ_CUDA_OK(cudaEventCreate(&g_prof_ev[i][j]));
+    g_prof_made = true;
+  }
+  for (int i = 0; i < PROF_COUNT; ++i) g_prof_hit[i] = false;
+  g_prof_on = on != 0;
+  return AVZ_OK;
+}
+
+int avz_profile_get(float* ms_host, int n) {
+  using namespace avz;
+  if (!ms_host || n < PROF_COUNT) return set_error(AVZ_EINVAL, "avz_profile_get: need room for %d floats", (int)PROF_COUNT);
+  for (int i = 0; i < PROF_COUNT; ++i) {
+    ms_host[i] = -1.f;
+    if (g_prof_made && g_prof_hit[i]) {
+      AVZ_CUDA_OK(cudaEventSynchronize(g_prof_ev[i][1]));
+      AVZ_CUDA_OK(cudaEventElapsedTime(&ms_host[i], g_prof_ev[i][0], g_prof_ev[i][1]));
+    }
+  }
+  return AVZ_OK;
 }
 
 int64_t avz_num_frames(int64_t L, int n_fft, int hop) {

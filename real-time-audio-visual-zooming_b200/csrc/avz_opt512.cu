@@ -818,12 +818,17 @@ int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const f
     al.cap = amb_cap(B, T);
     AVZ_CUDA_OK(cudaMemsetAsync(al.count, 0, 16, st));
     AVZ_CUDA_OK(cudaFuncSetAttribute(k512_ibm<HOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
+    prof_begin(PROF_IBM, st);
     k512_ibm<HOP><<<grid, kWarps * 32, smem_fft, st>>>(tgt, itf, (int)L, T, fpc, ibm_bits, al, ibm_tol2(), tb);
+    prof_end(PROF_IBM, st);
     AVZ_LAUNCH_OK("k512_ibm");
+    prof_begin(PROF_FIXUP, st);
     k512_ibm_fixup<<<num_sms() * 8, 256, 0, st>>>(tgt, itf, L, T, HOP, B, ibm_bits, al, tb);
+    prof_end(PROF_FIXUP, st);
     AVZ_LAUNCH_OK("k512_ibm_fixup");
   }
   const size_t smem_cov = smem_fft + (size_t)kWarps * 5 * kFP * sizeof(float);
+  prof_begin(PROF_COV, st);
   if (mask == nullptr) {
     AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov<HOP, W_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
     k512_cov<HOP, W_BITS><<<grid, kWarps * 32, smem_cov, st>>>(mix, ibm_bits, nullptr, (int)L, T, fpc, 0.f, part,
@@ -833,6 +838,7 @@ int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const f
     k512_cov<HOP, W_MASK><<<grid, kWarps * 32, smem_cov, st>>>(mix, nullptr, mask, (int)L, T, fpc, sqrt_eps, part,
                                                                reinterpret_cast<float4*>(spec), tb);
   }
+  prof_end(PROF_COV, st);
   AVZ_LAUNCH_OK("k512_cov");
   return AVZ_OK;
 }
@@ -851,6 +857,7 @@ int launch_apply(const float* mix, const void* spec, const float* w, const uint3
   const int chunks = (n_blocks + bpc - 1) / bpc;
   const size_t smem = (spec != nullptr) ? apply_smem_bytes<HOP, true>() : apply_smem_bytes<HOP, false>();
   dim3 grid(chunks, B);
+  prof_begin(PROF_APPLY, st);
   if (spec != nullptr) {
     AVZ_CUDA_OK(cudaFuncSetAttribute(k512_apply<HOP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k512_apply<HOP, true><<<grid, kWarps * 32, smem, st>>>(nullptr, reinterpret_cast<const float4*>(spec),
@@ -861,6 +868,7 @@ int launch_apply(const float* mix, const void* spec, const float* w, const uint3
     k512_apply<HOP, false><<<grid, kWarps * 32, smem, st>>>(mix, nullptr, reinterpret_cast<const float2*>(w), ibm_bits,
                                                             mask, gain_mode, post_floor, (int)L, T, bpc, out, peak, tb);
   }
+  prof_end(PROF_APPLY, st);
   AVZ_LAUNCH_OK("k512_apply");
   return AVZ_OK;
 }

@@ -309,8 +309,10 @@ extern "C" {
 
 int avz_mvdr_weights_f32(const float* R, const float* dvec, int B, int F, const AvzMvdrCfg* cfg, float* w, void* stream) {
   if (!R || !dvec || !cfg || !w || B <= 0 || F <= 0) return set_error(AVZ_EINVAL, "avz_mvdr_weights_f32: bad argument");
+  prof_begin(PROF_WEIGHTS, (cudaStream_t)stream);
   k_mvdr_weights<<<(B * F + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float4*>(R), reinterpret_cast<const float2*>(dvec), B, F, *cfg, reinterpret_cast<float2*>(w));
+  prof_end(PROF_WEIGHTS, (cudaStream_t)stream);
   AVZ_LAUNCH_OK("k_mvdr_weights");
   return AVZ_OK;
 }

@@ -90,6 +90,27 @@ class OracleMvdr:
         self.normalise()
         return self.out
 
+    KERNELS = ("k512_ibm", "k512_ibm_fixup", "k512_cov", "k_cov_finalize", "k_mvdr_weights", "k512_apply",
+               "k_peak_normalise")
+
+    def time_each_kernel(self, mix, tgt, itf, iters: int = 5) -> Dict[str, float]:
+        """Average device time (ms) of every kernel of a step, from CUDA events the library records on the launching
+        stream around each launch (avz_profile_enable / avz_profile_get)."""
+        self.run(mix, tgt, itf)
+        torch.cuda.synchronize()
+        _lib.check(self.lib.avz_profile_enable(1), "avz_profile_enable")
+        acc = [0.0] * len(self.KERNELS)
+        buf = (C.c_float * len(self.KERNELS))()
+        try:
+            for _ in range(iters):
+                self.run(mix, tgt, itf)
+                _lib.check(self.lib.avz_profile_get(buf, len(self.KERNELS)), "avz_profile_get")
+                for i in range(len(self.KERNELS)):
+                    acc[i] += max(0.0, float(buf[i]))
+        finally:
+            self.lib.avz_profile_enable(0)
+        return {k: acc[i] / iters for i, k in enumerate(self.KERNELS)}
+
     def time_kernels(self, mix, tgt, itf, iters: int = 5) -> Dict[str, float]:
         """Average device time (ms) of each stage, CUDA events on the launching stream."""
         stages = [("pass A (k512_ibm + k512_ibm_fixup + k512_cov + k_cov_finalize)", lambda: self.pass_a(mix, tgt, itf)),
