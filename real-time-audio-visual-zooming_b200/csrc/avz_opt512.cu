@@ -129,6 +129,7 @@ template <int N>
 __device__ __forceinline__ bool ibm_exact512(const float* __restrict__ tgt, const float* __restrict__ itf, int64_t L,
                                              int64_t start, int k, const Tables& tb, int lane) {
   double tr = 0, ti = 0, ir = 0, ii = 0;
+#pragma unroll   // N / 32 = 16 independent iterations: all their loads in flight at once (the kernel is latency-bound)
   for (int n = lane; n < N; n += kWarp) {
     const int64_t i = start + n;
     if (i >= 0 && i < L) {
@@ -257,7 +258,13 @@ k512_ibm(const float* __restrict__ tgt, const float* __restrict__ itf, int L, in
   }
 }
 
-// One warp per listed bin: exact float64 decision; flip the stored bit if the float32 one was wrong.
+// Exact float64 decisions for the listed bins; a stored bit is flipped where float32 got it wrong.
+// Each warp takes blocks of kFixBlock consecutive list entries.  Entries of one frame are contiguous in the list (they
+// were appended by one warp in one reservation), so the frame's windowed samples are converted to float64 once, kept
+// in registers (lane holds samples n = lane + 32 r), and reused for every listed bin of that frame: per bin only the
+// 16 twiddle loads, 64 DFMA and the warp reduction remain.
+constexpr int kFixBlock = 2;   // short blocks + many warps: the kernel is a latency chain per entry, so spread it wide
+
 __global__ void __launch_bounds__(256)
 k512_ibm_fixup(const float* __restrict__ tgt, const float* __restrict__ itf, int64_t L, int T, int hop, int B,
                uint32_t* __restrict__ ibm_bits, AmbList amb_list, Tables tb) {
@@ -267,24 +274,63 @@ k512_ibm_fixup(const float* __restrict__ tgt, const float* __restrict__ itf, int
   const unsigned int n = *amb_list.count;
   const bool overflow = n > amb_list.cap;
   const unsigned long long total = overflow ? (unsigned long long)B * T * kF : n;
-  for (unsigned long long i = gw; i < total; i += nw) {
-    int b, t, k;
-    if (!overflow) {
-      const unsigned long long e = amb_list.entries[i];
-      b = (int)(e >> 32);
-      t = (int)((e >> 9) & 0x7fffffu);
-      k = (int)(e & 511u);
-    } else {
-      k = (int)(i % kF);
-      t = (int)((i / kF) % T);
-      b = (int)(i / ((unsigned long long)kF * T));
-    }
-    const bool exact = ibm_exact512<kN>(tgt + (int64_t)b * L, itf + (int64_t)b * L, L, (int64_t)t * hop - kN / 2, k, tb,
-                                        lane);
-    if (lane == 0) {
-      uint32_t* wp = ibm_bits + ((int64_t)b * T + t) * kFW + (k >> 5);
-      const bool cur = ((*wp) >> (k & 31)) & 1u;
-      if (cur != exact) atomicXor(wp, 1u << (k & 31));
+  double xt[16], xi[16];
+  int cur_b = -1, cur_t = -1;
+  for (unsigned long long i0 = gw * kFixBlock; i0 < total; i0 += nw * kFixBlock) {
+    const unsigned long long i1 = (i0 + kFixBlock < total) ? i0 + kFixBlock : total;
+    for (unsigned long long i = i0; i < i1; ++i) {
+      int b, t, k;
+      if (!overflow) {
+        const unsigned long long e = amb_list.entries[i];
+        b = (int)(e >> 32);
+        t = (int)((e >> 9) & 0x7fffffu);
+        k = (int)(e & 511u);
+      } else {
+        k = (int)(i % kF);
+        t = (int)((i / kF) % T);
+        b = (int)(i / ((unsigned long long)kF * T));
+      }
+      if (b != cur_b || t != cur_t) {   // warp-uniform
+        cur_b = b;
+        cur_t = t;
+        const float* tg = tgt + (int64_t)b * L;
+        const float* it = itf + (int64_t)b * L;
+        const int64_t start = (int64_t)t * hop - kN / 2;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const int nn = lane + 32 * r;
+          const int64_t idx = start + nn;
+          const bool ok = idx >= 0 && idx < L;
+          const double w = tb.win_d[nn];
+          xt[r] = ok ? w * (double)__ldg(tg + idx) : 0.0;
+          xi[r] = ok ? w * (double)__ldg(it + idx) : 0.0;
+        }
+      }
+      // exp(-2 pi i (lane + 32 r) k / N) = base * step^r: one gathered and one broadcast table load per entry instead
+      // of 16 gathers (random 16-byte gathers cost up to 32 L1 wavefronts each and were this kernel's bottleneck);
+      // the recurrence adds ~16 ulp of float64 rounding, far inside the decision margin.
+      double2 e = tb.tw_d[(lane * k) & (kN - 1)];
+      const double2 stp = tb.tw_d[(32 * k) & (kN - 1)];
+      double tr = 0, ti = 0, ir = 0, ii = 0;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        tr = fma(xt[r], e.x, tr);
+        ti = fma(xt[r], e.y, ti);
+        ir = fma(xi[r], e.x, ir);
+        ii = fma(xi[r], e.y, ii);
+        const double nx = fma(e.x, stp.x, -e.y * stp.y), ny = fma(e.x, stp.y, e.y * stp.x);
+        e = make_double2(nx, ny);
+      }
+      tr = warp_sum(tr);
+      ti = warp_sum(ti);
+      ir = warp_sum(ir);
+      ii = warp_sum(ii);
+      const bool exact = (ir * ir + ii * ii) > (tr * tr + ti * ti);
+      if (lane == 0) {
+        uint32_t* wp = ibm_bits + ((int64_t)b * T + t) * kFW + (k >> 5);
+        const bool cur = ((*wp) >> (k & 31)) & 1u;
+        if (cur != exact) atomicXor(wp, 1u << (k & 31));
+      }
     }
   }
 }
@@ -759,9 +805,18 @@ k512_apply(const float* __restrict__ mix, const float4* __restrict__ spec, const
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
+static int ctas_per_sm_target() {
+  // CTAs per SM a launch should have at least, so that the tail of the last wave is short (AVZ_CTAS_PER_SM overrides)
+  static const int v = [] {
+    int t = 20;
+    if (const char* e = getenv("AVZ_CTAS_PER_SM")) t = atoi(e);
+    return t < 1 ? 1 : t;
+  }();
+  return v;
+}
+
 static int frames_per_cta(int B, int T, int sms) {
-  // aim for >= ~20 CTAs per SM so that the tail of the last wave is short
-  int per_utt = (20 * sms + B - 1) / B;
+  int per_utt = (ctas_per_sm_target() * sms + B - 1) / B;
   if (per_utt < 1) per_utt = 1;
   int fpc = (T + per_utt - 1) / per_utt;
   if (fpc < 8 * kWarps) fpc = 8 * kWarps;
@@ -823,7 +878,7 @@ int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const f
     prof_end(PROF_IBM, st);
     AVZ_LAUNCH_OK("k512_ibm");
     prof_begin(PROF_FIXUP, st);
-    k512_ibm_fixup<<<num_sms() * 8, 256, 0, st>>>(tgt, itf, L, T, HOP, B, ibm_bits, al, tb);
+    k512_ibm_fixup<<<num_sms() * 32, 256, 0, st>>>(tgt, itf, L, T, HOP, B, ibm_bits, al, tb);
     prof_end(PROF_FIXUP, st);
     AVZ_LAUNCH_OK("k512_ibm_fixup");
   }
