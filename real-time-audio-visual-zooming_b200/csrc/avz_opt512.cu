@@ -30,7 +30,7 @@ constexpr int kWarps = 4;    // warps per CTA
 #define AVZ_MINB_IBM 4
 #endif
 #ifndef AVZ_MINB_COV
-#define AVZ_MINB_COV 3
+#define AVZ_MINB_COV 2
 #endif
 #ifndef AVZ_MINB_APPLY
 #define AVZ_MINB_APPLY 2
@@ -46,8 +46,32 @@ template <int HOP>
 struct Window2 {
   static constexpr int NR = HOP / 32;   // new rows per frame
   float a[16], b[16];
-  float na[NR], nb[NR];                 // prefetched rows of the next frame
+  float na[NR], nb[NR];                 // rows of the next frame (t + 1), already requested
+  float fa[NR], fb[NR];                 // rows of the frame after that (t + 2): loads are kept two frames ahead because
+                                        // under load a DRAM round trip outlasts one frame of this warp's compute
 
+  __device__ __forceinline__ void load_rows(float (&ra)[NR], float (&rb)[NR], const float* __restrict__ xa,
+                                            const float* __restrict__ xb, int L, int t_new, int lane) {
+    const int s0 = t_new * HOP + kN / 2 - HOP;    // first sample of the hop that frame t_new adds
+    if (s0 >= 0 && s0 + HOP <= L) {               // warp-uniform: the whole hop is inside the signal
+      const float* pa = xa + s0 + lane;
+      const float* pb = xb + s0 + lane;
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        ra[i] = __ldg(pa + 32 * i);
+        rb[i] = __ldg(pb + 32 * i);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NR; ++i) {
+        const int idx = s0 + lane + 32 * i;
+        const bool ok = (unsigned)idx < (unsigned)L;
+        ra[i] = ok ? __ldg(xa + idx) : 0.f;
+        rb[i] = ok ? __ldg(xb + idx) : 0.f;
+      }
+    }
+  }
+  // all 16 rows of frame t, and the request for frame t + 1
   __device__ __forceinline__ void load_all(const float* __restrict__ xa, const float* __restrict__ xb, int L, int t,
                                            int lane) {
     const int base = t * HOP - kN / 2 + lane;
@@ -58,29 +82,14 @@ struct Window2 {
       a[r] = ok ? __ldg(xa + i) : 0.f;
       b[r] = ok ? __ldg(xb + i) : 0.f;
     }
+    load_rows(na, nb, xa, xb, L, t + 1, lane);
   }
-  // issue the loads of the rows that frame t_next adds (rows 16-NR..15 of that frame)
+  // while frame t is being processed: request the rows frame t + 2 will add (t_next = t + 1 is already in flight)
   __device__ __forceinline__ void prefetch(const float* __restrict__ xa, const float* __restrict__ xb, int L,
                                            int t_next, int lane) {
-    const int s0 = t_next * HOP + kN / 2 - HOP;   // first sample of the new hop
-    if (s0 >= 0 && s0 + HOP <= L) {               // warp-uniform: the whole hop is inside the signal
-      const float* pa = xa + s0 + lane;
-      const float* pb = xb + s0 + lane;
-#pragma unroll
-      for (int i = 0; i < NR; ++i) {
-        na[i] = __ldg(pa + 32 * i);
-        nb[i] = __ldg(pb + 32 * i);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < NR; ++i) {
-        const int idx = s0 + lane + 32 * i;
-        const bool ok = (unsigned)idx < (unsigned)L;
-        na[i] = ok ? __ldg(xa + idx) : 0.f;
-        nb[i] = ok ? __ldg(xb + idx) : 0.f;
-      }
-    }
+    load_rows(fa, fb, xa, xb, L, t_next + 1, lane);
   }
+  // move on to frame t + 1
   __device__ __forceinline__ void advance() {
 #pragma unroll
     for (int r = 0; r < 16 - NR; ++r) {
@@ -91,6 +100,8 @@ struct Window2 {
     for (int i = 0; i < NR; ++i) {
       a[16 - NR + i] = na[i];
       b[16 - NR + i] = nb[i];
+      na[i] = fa[i];
+      nb[i] = fb[i];
     }
   }
   // windowed complex frame a + i b
