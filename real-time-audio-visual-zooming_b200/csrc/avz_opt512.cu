@@ -758,27 +758,26 @@ k512_apply(const float* __restrict__ mix, const float4* __restrict__ spec, const
         ny_a = s_ny;
         continue;
       }
-      // ---- one inverse transform for the pair (g-1, g), or for g alone when it is the last of the run
-      float2 v[16];
+      // ---- one inverse transform for the pair (g-1, g); a lone last frame of the run is the pair (g, nothing)
       if (is_first) {
-        float2 Z0[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) Z0[j] = make_float2(0.f, 0.f);
-        f512::hermitian_pack(S, Z0, make_float2(s_ny, 0.f), v, ln);
-      } else {
-        f512::hermitian_pack(Sa, S, make_float2(ny_a, s_ny), v, ln);
+        for (int j = 0; j < 8; ++j) {
+          Sa[j] = S[j];
+          S[j] = make_float2(0.f, 0.f);
+        }
+        ny_a = s_ny;
+        s_ny = 0.f;
       }
+      const int g_a = is_first ? g : g - 1;
+      float2 v[16];
+      f512::hermitian_pack(Sa, S, make_float2(ny_a, s_ny), v, ln);
       f512::inverse(v, sm, ln);
+#pragma unroll
+      for (int r = 0; r < 16; ++r) o[r] = fmaf(hw[r], v[r].x, o[r]);
+      close_block(g_a);
       if (!is_first) {
 #pragma unroll
-        for (int r = 0; r < 16; ++r) o[r] = fmaf(hw[r], v[r].x, o[r]);
-        close_block(g - 1);
-#pragma unroll
         for (int r = 0; r < 16; ++r) o[r] = fmaf(hw[r], v[r].y, o[r]);
-        close_block(g);
-      } else {
-#pragma unroll
-        for (int r = 0; r < 16; ++r) o[r] = fmaf(hw[r], v[r].x, o[r]);
         close_block(g);
       }
     }
