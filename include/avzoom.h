@@ -163,6 +163,13 @@ AVZ_API int avz_wave_mask_cov_keep_f32(const float* mix, const float* mask, int 
 AVZ_API int avz_mvdr_apply_kept_f32(const void* spec, const float* w, const uint32_t* ibm_bits, const float* mask, int B,
                             int64_t L, int n_fft, int hop, const AvzMvdrCfg* cfg, float* out, float* peak, void* stream);
 
+/* Same as avz_mvdr_apply_kept_f32 plus the peak normalisation of oracle_debug.py:94 fused in: the thread block that
+ * finishes an utterance last divides it by (peak[b] + peak_eps) in place while it is still in L2 (no second kernel,
+ * no second trip to HBM).  Bit-identical to apply followed by avz_peak_normalise_f32.  peak [B] zeroed by the caller. */
+AVZ_API int avz_mvdr_apply_kept_norm_f32(const void* spec, const float* w, const uint32_t* ibm_bits, const float* mask, int B,
+                                 int64_t L, int n_fft, int hop, const AvzMvdrCfg* cfg, float peak_eps, float* out,
+                                 float* peak, void* stream);
+
 /* ---- streaming mode (BASELINE config 4; NOT in the reference - defined by this project, parity unpinned):
  *   R_t = lambda R_{t-1} + (1-lambda) m_t y_t y_t^H,  n_t = lambda n_{t-1} + (1-lambda) m_t,
  *   w_t = mvdr(R_t/(n_t+norm_eps) + sigma I),  S_t = w_t^H y_t,  same 512/128 framing and overlap-add as the batch path.

@@ -28,7 +28,8 @@ int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const f
                    float sqrt_eps, uint32_t* ibm_bits, float* part, int* chunks_out, void* spec, cudaStream_t st);
 template <int HOP>
 int launch_apply(const float* mix, const void* spec, const float* w, const uint32_t* ibm_bits, const float* mask,
-                 int gain_mode, float post_floor, int B, int64_t L, float* out, float* peak, cudaStream_t st);
+                 int gain_mode, float post_floor, int B, int64_t L, float* out, float* peak, int fuse_norm,
+                 float peak_eps, cudaStream_t st);
 }  // namespace o512
 
 // The register-resident 512-point path serves n_fft 512 with hop 128 / 256 unless AVZ_FORCE_GENERIC=1
@@ -679,7 +680,7 @@ int avz_wave_mask_cov_f32(const float* mix, const float* mask, int B, int64_t L,
 // ---- "kept spectrum" variants of the fused passes (n_fft 512 fast path only) ---------------------------------
 int64_t avz_spec_ws_bytes(int B, int64_t L, int n_fft, int hop) {
   if (B <= 0 || check_fft_args(n_fft, hop, L) || !use_opt512(n_fft, hop)) return 0;
-  return (int64_t)B * avz_num_frames(L, n_fft, hop) * 4096;
+  return (int64_t)B * avz_num_frames(L, n_fft, hop) * 4096 + (int64_t)B * 4;   // + per-utterance completion counters
 }
 
 int avz_ibm_cov_keep_f32(const float* mix, const float* tgt, const float* itf, int B, int64_t L, int n_fft, int hop,
@@ -704,8 +705,9 @@ int avz_wave_mask_cov_keep_f32(const float* mix, const float* mask, int B, int64
                        (cudaStream_t)stream);
 }
 
-int avz_mvdr_apply_kept_f32(const void* spec, const float* w, const uint32_t* ibm_bits, const float* mask, int B,
-                            int64_t L, int n_fft, int hop, const AvzMvdrCfg* cfg, float* out, float* peak, void* stream) {
+static int apply_kept(const void* spec, const float* w, const uint32_t* ibm_bits, const float* mask, int B, int64_t L,
+                      int n_fft, int hop, const AvzMvdrCfg* cfg, float* out, float* peak, int fuse_norm, float peak_eps,
+                      void* stream) {
   if (!spec || !w || !cfg || !out || B <= 0)
     return set_error(AVZ_EINVAL, "avz_mvdr_apply_kept_f32: null pointer or empty batch");
   int rc = check_fft_args(n_fft, hop, L);
@@ -726,9 +728,21 @@ int avz_mvdr_apply_kept_f32(const void* spec, const float* w, const uint32_t* ib
     default: return set_error(AVZ_EINVAL, "post_mode=%d unknown", cfg->post_mode);
   }
   return (hop == 128) ? o512::launch_apply<128>(nullptr, spec, w, ibm_bits, mask, gain, cfg->post_floor, B, L, out, peak,
-                                                (cudaStream_t)stream)
+                                                fuse_norm, peak_eps, (cudaStream_t)stream)
                       : o512::launch_apply<256>(nullptr, spec, w, ibm_bits, mask, gain, cfg->post_floor, B, L, out, peak,
-                                                (cudaStream_t)stream);
+                                                fuse_norm, peak_eps, (cudaStream_t)stream);
+}
+
+int avz_mvdr_apply_kept_f32(const void* spec, const float* w, const uint32_t* ibm_bits, const float* mask, int B,
+                            int64_t L, int n_fft, int hop, const AvzMvdrCfg* cfg, float* out, float* peak, void* stream) {
+  return apply_kept(spec, w, ibm_bits, mask, B, L, n_fft, hop, cfg, out, peak, 0, 0.f, stream);
+}
+
+int avz_mvdr_apply_kept_norm_f32(const void* spec, const float* w, const uint32_t* ibm_bits, const float* mask, int B,
+                                 int64_t L, int n_fft, int hop, const AvzMvdrCfg* cfg, float peak_eps, float* out,
+                                 float* peak, void* stream) {
+  if (!peak) return set_error(AVZ_EINVAL, "avz_mvdr_apply_kept_norm_f32: peak buffer required");
+  return apply_kept(spec, w, ibm_bits, mask, B, L, n_fft, hop, cfg, out, peak, 1, peak_eps, stream);
 }
 
 // ---- streaming (n_fft 512 / hop 128): one hop per call for n_streams independent 2-mic streams ---------------
@@ -767,9 +781,9 @@ int avz_mvdr_apply_f32(const float* mix, const float* w, const uint32_t* ibm_bit
   const int T = (int)avz_num_frames(L, n_fft, hop);
   if (use_opt512(n_fft, hop)) {
     return (hop == 128) ? o512::launch_apply<128>(mix, nullptr, w, ibm_bits, mask, gain, cfg->post_floor, B, L, out, peak,
-                                                  (cudaStream_t)stream)
+                                                  0, 0.f, (cudaStream_t)stream)
                         : o512::launch_apply<256>(mix, nullptr, w, ibm_bits, mask, gain, cfg->post_floor, B, L, out, peak,
-                                                  (cudaStream_t)stream);
+                                                  0, 0.f, (cudaStream_t)stream);
   }
   AVZ_DISPATCH_N(n_fft, (launch_synth<N_, SRC_MIX>(mix, nullptr, w, ibm_bits, mask, gain, cfg->post_floor, B, L, T, hop,
                                                    out, peak, (cudaStream_t)stream)));

@@ -523,7 +523,8 @@ template <int HOP, bool KEPT>
 __global__ void __launch_bounds__(kWarps * 32, KEPT ? AVZ_MINB_APPLY_KEPT : AVZ_MINB_APPLY)
 k512_apply(const float* __restrict__ mix, const float4* __restrict__ spec, const float2* __restrict__ wgt,
            const uint32_t* __restrict__ ibm_bits, const float* __restrict__ mask, int gain_mode, float post_floor, int L,
-           int T, int blocks_per_cta, float* __restrict__ out, float* __restrict__ peak, Tables tb) {
+           int T, int blocks_per_cta, float* __restrict__ out, float* __restrict__ peak, unsigned int* __restrict__ done,
+           float peak_eps, Tables tb) {
   constexpr int R = kN / HOP;        // frames overlapping one hop-block
   constexpr int NR = HOP / 32;       // rows per hop-block
   constexpr int TAIL = 16 - NR;      // rows still open after a frame's first block is emitted
@@ -809,6 +810,29 @@ k512_apply(const float* __restrict__ mix, const float4* __restrict__ spec, const
       for (int i = 0; i < kWarps; ++i) m = fmaxf(m, s_peak[i]);
       atomicMax(reinterpret_cast<unsigned int*>(peak + b), __float_as_uint(m));
     }
+    // Fused peak normalisation (oracle_debug.py:94): the CTA that finishes an utterance last rescales it in place
+    // while its samples are still in L2 - no extra kernel, no second trip to HBM.
+    if (done != nullptr) {
+      __shared__ int s_last;
+      __threadfence();                 // this thread's output stores are visible device-wide ...
+      __syncthreads();
+      if (threadIdx.x == 0) {          // ... before the CTA signals completion (the atomicMax above precedes it too)
+        __threadfence();
+        s_last = (atomicAdd(done + b, 1u) == gridDim.x - 1);
+      }
+      __syncthreads();
+      if (s_last) {
+        __threadfence();
+        const float den = __ldcg(peak + b) + peak_eps;
+        float4* o4 = reinterpret_cast<float4*>(ob);
+        const int n4 = (int)(out_len >> 2);   // out_len = (T-1) * HOP, a multiple of 128
+        for (int i = threadIdx.x; i < n4; i += kWarps * 32) {
+          float4 v = __ldcg(o4 + i);
+          v = make_float4(__fdiv_rn(v.x, den), __fdiv_rn(v.y, den), __fdiv_rn(v.z, den), __fdiv_rn(v.w, den));
+          o4[i] = v;
+        }
+      }
+    }
   }
 }
 
@@ -910,7 +934,8 @@ int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const f
 
 template <int HOP>
 int launch_apply(const float* mix, const void* spec, const float* w, const uint32_t* ibm_bits, const float* mask,
-                 int gain_mode, float post_floor, int B, int64_t L, float* out, float* peak, cudaStream_t st) {
+                 int gain_mode, float post_floor, int B, int64_t L, float* out, float* peak, int fuse_norm,
+                 float peak_eps, cudaStream_t st) {
   Tables tb;
   int rc = tables_for(kN, &tb);
   if (rc) return rc;
@@ -924,14 +949,23 @@ int launch_apply(const float* mix, const void* spec, const float* w, const uint3
   dim3 grid(chunks, B);
   prof_begin(PROF_APPLY, st);
   if (spec != nullptr) {
+    // per-utterance completion counters live behind the kept spectrum (avz_spec_ws_bytes accounts for them)
+    unsigned int* done = nullptr;
+    if (fuse_norm) {
+      if (peak == nullptr) return set_error(AVZ_EINVAL, "fused normalisation needs the peak buffer");
+      done = reinterpret_cast<unsigned int*>(const_cast<unsigned char*>(static_cast<const unsigned char*>(spec)) +
+                                             (size_t)B * T * 4096);
+      AVZ_CUDA_OK(cudaMemsetAsync(done, 0, (size_t)B * sizeof(unsigned int), st));
+    }
     AVZ_CUDA_OK(cudaFuncSetAttribute(k512_apply<HOP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k512_apply<HOP, true><<<grid, kWarps * 32, smem, st>>>(nullptr, reinterpret_cast<const float4*>(spec),
                                                            reinterpret_cast<const float2*>(w), ibm_bits, mask, gain_mode,
-                                                           post_floor, (int)L, T, bpc, out, peak, tb);
+                                                           post_floor, (int)L, T, bpc, out, peak, done, peak_eps, tb);
   } else {
     AVZ_CUDA_OK(cudaFuncSetAttribute(k512_apply<HOP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k512_apply<HOP, false><<<grid, kWarps * 32, smem, st>>>(mix, nullptr, reinterpret_cast<const float2*>(w), ibm_bits,
-                                                            mask, gain_mode, post_floor, (int)L, T, bpc, out, peak, tb);
+                                                            mask, gain_mode, post_floor, (int)L, T, bpc, out, peak, nullptr,
+                                                            0.f, tb);
   }
   prof_end(PROF_APPLY, st);
   AVZ_LAUNCH_OK("k512_apply");
@@ -961,9 +995,9 @@ template int launch_ibm_cov<128>(const float*, const float*, const float*, const
 template int launch_ibm_cov<256>(const float*, const float*, const float*, const float*, int, int64_t, float, uint32_t*,
                                  float*, int*, void*, cudaStream_t);
 template int launch_apply<128>(const float*, const void*, const float*, const uint32_t*, const float*, int, float, int,
-                               int64_t, float*, float*, cudaStream_t);
+                               int64_t, float*, float*, int, float, cudaStream_t);
 template int launch_apply<256>(const float*, const void*, const float*, const uint32_t*, const float*, int, float, int,
-                               int64_t, float*, float*, cudaStream_t);
+                               int64_t, float*, float*, int, float, cudaStream_t);
 
 }  // namespace o512
 }  // namespace avz

@@ -24,7 +24,7 @@ class OracleMvdr:
     # (+ two small memsets: the near-tie counter and `peak`)
     launches_per_step = 7
 
-    def __init__(self, cfg: MvdrConfig, B: int, L: int, device, keep_spectrum: bool = True):
+    def __init__(self, cfg: MvdrConfig, B: int, L: int, device, keep_spectrum: bool = True, fused_norm: bool = False):
         self.cfg, self.B, self.L, self.device = cfg, B, L, device
         self.lib = _lib.load()
         self.F = cfg.n_freq
@@ -44,6 +44,11 @@ class OracleMvdr:
         # pass A may keep the packed mix spectrum so that pass B skips its forward transform (fast path only)
         nspec = self.lib.avz_spec_ws_bytes(B, L, cfg.n_fft, cfg.hop) if keep_spectrum else 0
         self.spec = torch.empty((int(nspec),), dtype=torch.uint8, device=device) if nspec > 0 else None
+        # fused_norm: the last thread block of an utterance rescales it in L2 (one launch and one HBM round trip less).
+        # Measured on B200 at config 2 it LOSES (pass B 0.54 -> 0.76 ms vs 0.09 ms for the separate streaming kernel):
+        # a single 4-warp block rescaling 256 KB is latency-bound and lengthens the tail.  Kept as an option, off.
+        self.fused_norm = fused_norm and cfg.peak_eps is not None and self.spec is not None
+        self.launches_per_step = 6 if self.fused_norm else 7
         self.d = steering_vectors(cfg, device)
         self.cc = cfg.to_c()
         _lib.check(self.lib.avz_init(cfg.n_fft), "avz_init")
@@ -68,6 +73,13 @@ class OracleMvdr:
         c = self.cfg
         self.peak.zero_()
         bits = self.bits if c.post == "one_minus_noise" else None
+        if self.spec is not None and self.fused_norm:
+            # peak normalisation fused into pass B: the last thread block of an utterance rescales it in L2
+            _lib.check(self.lib.avz_mvdr_apply_kept_norm_f32(_ptr(self.spec), _ptr(self.w), _ptr(bits), _ptr(None),
+                                                             self.B, self.L, c.n_fft, c.hop, C.byref(self.cc),
+                                                             float(c.peak_eps), _ptr(self.out), _ptr(self.peak),
+                                                             _stream()), "avz_mvdr_apply_kept_norm_f32")
+            return
         if self.spec is not None:
             _lib.check(self.lib.avz_mvdr_apply_kept_f32(_ptr(self.spec), _ptr(self.w), _ptr(bits), _ptr(None), self.B,
                                                         self.L, c.n_fft, c.hop, C.byref(self.cc), _ptr(self.out),
@@ -78,7 +90,7 @@ class OracleMvdr:
                    "avz_mvdr_apply_f32")
 
     def normalise(self):
-        if self.cfg.peak_eps is not None:
+        if self.cfg.peak_eps is not None and not (self.spec is not None and self.fused_norm):
             _lib.check(self.lib.avz_peak_normalise_f32(_ptr(self.out), self.B, self.out_len, _ptr(self.peak),
                                                        float(self.cfg.peak_eps), _stream()), "avz_peak_normalise_f32")
 

@@ -264,7 +264,8 @@ def test_engine_kept_spectrum_equals_recompute(az, preset, B, dur):
     mix_d, tgt_d, itf_d = (torch.from_numpy(a).cuda() for a in (mix, tgt, itf))
     e_keep = pipeline.OracleMvdr(cfg, B, mix.shape[-1], mix_d.device, keep_spectrum=True)
     e_reco = pipeline.OracleMvdr(cfg, B, mix.shape[-1], mix_d.device, keep_spectrum=False)
-    assert e_keep.spec is not None and e_reco.spec is None
+    e_sep = pipeline.OracleMvdr(cfg, B, mix.shape[-1], mix_d.device, keep_spectrum=True, fused_norm=True)
+    assert e_keep.spec is not None and e_reco.spec is None and not e_keep.fused_norm and e_sep.fused_norm
     def same(x, y):
         # an all-silent output is 0 / 0 = NaN after peak normalisation (as `s_out /= np.max(np.abs(s_out))` gives in
         # the reference); NaN patterns must agree, everything else bit for bit
@@ -273,6 +274,7 @@ def test_engine_kept_spectrum_equals_recompute(az, preset, B, dur):
     a = e_keep.run(mix_d, tgt_d, itf_d).clone()
     b = e_reco.run(mix_d, tgt_d, itf_d).clone()
     assert same(a, b)
+    assert same(a, e_sep.run(mix_d, tgt_d, itf_d))          # fused vs separate peak normalisation
     assert torch.equal(e_keep.bits, e_reco.bits) and torch.equal(e_keep.R, e_reco.R)
     assert torch.equal(e_keep.peak, e_reco.peak)
     c = az.oracle_mask_mvdr(mix_d, tgt_d, itf_d, cfg)
