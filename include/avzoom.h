@@ -209,6 +209,23 @@ AVZ_API int avz_wave_features_f32(const float* mix, int B, int64_t L, int n_fft,
 AVZ_API int avz_sir_f32(const float* est, const float* tgt, const float* itf, int B, int64_t n_est, int64_t n_ref,
                 float* scores, void* stream);
 
+/* ---- far-field 2-mic mixer: rt_av_zoom/core/tf_lite_version/world_building.py:46-52 (apply_frac_delay: whole-signal
+ * rFFT, phase ramp exp(-2 pi i f tau), irfft) and :61-93 (mix_and_save: per-source delays to both mics, references =
+ * the mic-1 images, everything divided by max|mix| + peak_eps).
+ * src [B,S,L] (source 0 is the target, the others interferers); delays_host [S][2] seconds (mic 1, mic 2) is a HOST
+ * pointer read during the call.  mix [B,2,L], tgt [B,L], itf [B,L].  peak_eps < 0 skips the division (plain delays).
+ * L = N1*N2 with N1 the largest power of two <= 512 dividing L and N2 <= 1024 (64000 = 512*125, 80000 = 128*625);
+ * other lengths return AVZ_EINVAL.  1 <= S <= 8.  ws: avz_farfield_mix_ws_bytes(B,S,L) bytes of device scratch. */
+AVZ_API int64_t avz_farfield_mix_ws_bytes(int B, int S, int64_t L);
+AVZ_API int avz_farfield_mix_f32(const float* src, const double* delays_host, int B, int S, int64_t L, double fs,
+                         float peak_eps, float* mix, float* tgt, float* itf, void* ws, void* stream);
+
+/* ---- PCM16 wire format (soundfile semantics, oracle_debug.py:35-39,96): read = int16 / 32768 (exact in float32);
+ * write = libsndfile's default PCM_16 conversion, round-half-even(x * 32767) (0x7FFF), clipped to [-32768, 32767].
+ * n elements, any layout; the device-side halves of a PCM16 host<->device transfer (half the PCIe bytes of float32). */
+AVZ_API int avz_pcm16_to_f32(const int16_t* pcm, int64_t n, float* out, void* stream);
+AVZ_API int avz_f32_to_pcm16(const float* x, int64_t n, int16_t* pcm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

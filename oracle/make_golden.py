@@ -127,6 +127,44 @@ def main():
                                 os.path.join(REF, "rt_av_zoom/core/full_audio_generating_pipeline"))
     ref_rm = load_file_module("ref_run_metrics", os.path.join(REF, "scripts/run_metrics.py"), REF)
 
+    # ---------------------------------------------------------------- 4. far-field mixer
+    def gen_mixer():
+        """world_building.mix_and_save run unmodified on three PCM16 'files' (lengths the GPU mixer's two-factor
+        transform supports: 8000 = 2^6 * 125), plus apply_frac_delay at L = 4000."""
+        r4 = np.random.default_rng(20261019)
+        m = {}
+        L4 = 8000
+        src_pcm = np.clip(np.rint(r4.standard_normal((3, L4)) * 6000.0), -32768, 32767).astype("<i2")
+        m["src_pcm"] = src_pcm
+        with tempfile.TemporaryDirectory() as td:
+            old = os.getcwd()
+            os.chdir(td)
+            try:
+                files = []
+                for i in range(3):
+                    fn = os.path.join(td, f"src{i}.wav")
+                    write_wav_pcm16(fn, src_pcm[i])
+                    files.append(fn)
+                sf.written.clear()
+                with contextlib.redirect_stdout(io.StringIO()):
+                    ref_wb.mix_and_save(files, "g")
+                m["mix"] = sf.written["mixture_g.wav"]            # (L, 2)
+                m["tgt"] = sf.written["target_ref_g.wav"]
+                m["itf"] = sf.written["interf_ref_g.wav"]
+            finally:
+                os.chdir(old)
+        m["angles"] = np.array([ref_wb.ANGLE_TARGET, ref_wb.ANGLE_INTERFERER_A, ref_wb.ANGLE_INTERFERER_B], dtype=np.float64)
+        m["d_c_fs"] = np.array([ref_wb.D, ref_wb.C, ref_wb.FS], dtype=np.float64)
+        yd2 = r4.standard_normal(4000).astype(np.float32)
+        m["fd2_in"] = yd2
+        m["fd2_out"] = ref_wb.apply_frac_delay(yd2.astype(np.float64), -4.1e-5, 16000)
+        np.savez_compressed(os.path.join(OUT, "ref_mixer.npz"), **m)
+
+    if "--only-mixer" in sys.argv:
+        gen_mixer()
+        print("ref_mixer.npz", os.path.getsize(os.path.join(OUT, "ref_mixer.npz")))
+        return
+
     rng = np.random.default_rng(20261018)
 
     # ---------------------------------------------------------------- 1. importable helpers
@@ -258,6 +296,8 @@ def main():
             os.chdir(old)
     c["L"] = np.array(L3)
     np.savez_compressed(os.path.join(OUT, "ref_learned_chunk.npz"), **c)
+
+    gen_mixer()
 
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))

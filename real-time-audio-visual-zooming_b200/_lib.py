@@ -74,6 +74,10 @@ SIGNATURES = {
     "avz_features_f32": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "avz_wave_features_f32": (_i, [_p, _i, _l, _i, _i, _i, _p, _p]),
     "avz_sir_f32": (_i, [_p, _p, _p, _i, _l, _l, _p, _p]),
+    "avz_farfield_mix_ws_bytes": (_l, [_i, _i, _l]),
+    "avz_farfield_mix_f32": (_i, [_p, C.POINTER(C.c_double), _i, _i, _l, C.c_double, _f, _p, _p, _p, _p, _p]),
+    "avz_pcm16_to_f32": (_i, [_p, _l, _p, _p]),
+    "avz_f32_to_pcm16": (_i, [_p, _l, _p, _p]),
 }
 
 

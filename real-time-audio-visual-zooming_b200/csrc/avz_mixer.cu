@@ -1,0 +1,466 @@
+// On-device far-field 2-mic mixer and the PCM16 wire-format converters (8-F rank 4).
+//
+// Reference: rt_av_zoom/core/tf_lite_version/world_building.py:46-52 (apply_frac_delay) and :61-93 (mix_and_save).
+// The reference delays every source with a whole-signal real FFT of length L (pocketfft handles any L), a phase ramp
+// and an inverse real FFT, once per source and microphone.  Here the mixture is formed in the frequency domain:
+//
+//   pass 1+2  forward length-L FFT of the sources, two real sources packed into one complex transform
+//   pass 3    per bin: unpack the sources, apply the 2S phase ramps, sum into mic 1 / mic 2 / target image /
+//             interferer image, re-pack as (mic1 + i mic2) and (target + i interferer) Hermitian pairs
+//   pass 4+5  inverse length-L FFT of the two packed outputs, 1/L, running max|mix|
+//   pass 6    divide everything by max|mix| + eps
+//
+// so S sources cost ceil(S/2) + 2 complex transforms instead of the reference's 3S real ones.
+//
+// The length-L transform is a two-factor Cooley-Tukey split L = N1*N2 (N1 = 2^a <= 512, N2 <= 1024 arbitrary):
+// with n = N2 n1 + n2 and k = k1 + N1 k2,
+//   X[k1 + N1 k2] = sum_n2 W_N2^{n2 k2} * [ W_L^{n2 k1} * sum_n1 x[N2 n1 + n2] W_N1^{n1 k1} ]
+// "cols" kernels do the power-of-two part over n1 (16 adjacent n2 columns per block so that global accesses are
+// 64/128-byte runs; radix-2 in shared memory, DIF forward / DIT inverse so that no bit-reversal pass is needed),
+// "rows" kernels do the length-N2 part as a direct DFT on contiguous rows (N2 = 125 for 4 s at 16 kHz).
+// Spectra stay in the [k1][k2] order between the passes; the inverse runs the two factors in the opposite order and
+// lands in natural time order, so no transposition is ever materialised.  All twiddles come from one table
+// W_L[j] = exp(-2 pi i j / L) rounded from float64 (W_N1^j = W_L[j N2], W_N2^j = W_L[j N1]).
+#include <mutex>
+#include <vector>
+
+#include "avz_common.cuh"
+
+namespace avz {
+namespace {
+
+constexpr int kMaxSrc = 8;
+constexpr int kCols = 16;        // n2 columns per block in the power-of-two passes
+constexpr int kColThreads = 256;
+constexpr int kRowsPer = 4;      // rows sharing one twiddle fetch in the direct-DFT passes
+constexpr int kMaxN1 = 512;
+constexpr int kMaxN2 = 1024;
+
+struct MixTable {
+  int device;
+  int64_t n;
+  const float2* w;
+};
+std::mutex g_mix_mu;
+std::vector<MixTable> g_mix_tables;
+
+int mix_table_for(int64_t n, const float2** out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return set_error(AVZ_ENOGPU, "cudaGetDevice: %s", cudaGetErrorString(e));
+  std::lock_guard<std::mutex> lk(g_mix_mu);
+  for (const auto& t : g_mix_tables)
+    if (t.device == dev && t.n == n) {
+      *out = t.w;
+      return AVZ_OK;
+    }
+  std::vector<float2> w((size_t)n);
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int64_t j = 0; j < n; ++j) {
+    double c = cos(two_pi * (double)j / (double)n), s = -sin(two_pi * (double)j / (double)n);
+    if ((4 * j) % n == 0) {  // exact quadrant points
+      const int q = (int)((4 * j) / n);
+      c = (q == 0) ? 1.0 : (q == 2 ? -1.0 : 0.0);
+      s = (q == 1) ? -1.0 : (q == 3 ? 1.0 : 0.0);
+    }
+    w[(size_t)j] = make_float2((float)c, (float)s);
+  }
+  void* p = nullptr;
+  AVZ_CUDA_OK(cudaMalloc(&p, (size_t)n * sizeof(float2)));
+  AVZ_CUDA_OK(cudaMemcpy(p, w.data(), (size_t)n * sizeof(float2), cudaMemcpyHostToDevice));
+  g_mix_tables.push_back({dev, n, (const float2*)p});
+  *out = (const float2*)p;
+  return AVZ_OK;
+}
+
+// L = N1 * N2: N1 = largest power of two <= kMaxN1 dividing L.
+bool split_length(int64_t L, int* N1, int* log2N1, int* N2) {
+  if (L < 2) return false;
+  int n1 = 1, lg = 0;
+  while (n1 < kMaxN1 && L % (2 * (int64_t)n1) == 0) { n1 *= 2; ++lg; }
+  const int64_t n2 = L / n1;
+  if (n2 > kMaxN2) return false;
+  *N1 = n1;
+  *log2N1 = lg;
+  *N2 = (int)n2;
+  return true;
+}
+
+__device__ __forceinline__ int bitrev(int x, int bits) { return bits ? (int)(__brev((unsigned)x) >> (32 - bits)) : 0; }
+
+// ---- pass 1: pack two sources, power-of-two DIF over n1, twiddle W_L^{n2 k1}; A[b][p][k1][n2] ----
+__global__ void __launch_bounds__(kColThreads)
+k_mix_cols_fwd(const float* __restrict__ src, float2* __restrict__ A, const float2* __restrict__ W, int S, int PP,
+               int N1, int log2N1, int N2, int64_t N) {
+  extern __shared__ float2 sm[];  // [N1][kCols]
+  const int c0 = blockIdx.x * kCols;
+  const int p = blockIdx.y, b = blockIdx.z;
+  const int ncol = min(kCols, N2 - c0);
+  const float* sa = src + ((int64_t)b * S + 2 * p) * N;
+  const bool has_b = 2 * p + 1 < S;
+  const float* sb = sa + N;
+  for (int idx = threadIdx.x; idx < N1 * kCols; idx += kColThreads) {
+    const int c = idx & (kCols - 1), n1 = idx / kCols;
+    float2 z = make_float2(0.f, 0.f);
+    if (c < ncol) {
+      const int64_t g = (int64_t)n1 * N2 + c0 + c;
+      z.x = __ldg(sa + g);
+      if (has_b) z.y = __ldg(sb + g);
+    }
+    sm[idx] = z;
+  }
+  __syncthreads();
+  for (int h = N1 >> 1; h >= 1; h >>= 1) {
+    const int64_t tstep = (int64_t)N2 * (N1 / (2 * h));  // W_{2h}^{pos} = W_L[pos * L / (2h)]
+    for (int idx = threadIdx.x; idx < (N1 / 2) * kCols; idx += kColThreads) {
+      const int c = idx & (kCols - 1), j = idx / kCols;
+      const int pos = j & (h - 1);
+      const int i0 = ((j - pos) << 1) + pos;
+      const float2 a = sm[i0 * kCols + c];
+      const float2 bb = sm[(i0 + h) * kCols + c];
+      const float2 w = __ldg(W + pos * tstep);
+      sm[i0 * kCols + c] = cadd(a, bb);
+      sm[(i0 + h) * kCols + c] = cmul(csub(a, bb), w);
+    }
+    __syncthreads();
+  }
+  float2* out = A + ((int64_t)b * PP + p) * N;
+  for (int idx = threadIdx.x; idx < N1 * kCols; idx += kColThreads) {
+    const int c = idx & (kCols - 1), pos = idx / kCols;
+    if (c < ncol) {
+      const int k1 = bitrev(pos, log2N1);
+      const int n2 = c0 + c;
+      out[(int64_t)k1 * N2 + n2] = cmul(sm[idx], __ldg(W + (int64_t)n2 * k1));
+    }
+  }
+}
+
+// ---- passes 2 and 4: direct length-N2 DFT along contiguous rows, in place.  One thread per output index,
+//      kRowsPer rows share each twiddle fetch. ----
+template <bool INV>
+__global__ void k_mix_rows(float2* __restrict__ Z, const float2* __restrict__ W, int N1, int N2, int64_t N) {
+  extern __shared__ float2 sm[];  // wm[N2] | rows[kRowsPer][N2]
+  float2* wm = sm;
+  float2* rows = sm + N2;
+  for (int j = threadIdx.x; j < N2; j += blockDim.x) {
+    float2 w = __ldg(W + (int64_t)j * N1);
+    if (INV) w.y = -w.y;
+    wm[j] = w;
+  }
+  float2* base = Z + (int64_t)blockIdx.y * N;
+  for (int r0 = blockIdx.x * kRowsPer; r0 < N1; r0 += gridDim.x * kRowsPer) {
+    const int nr = min(kRowsPer, N1 - r0);
+    __syncthreads();
+    for (int j = threadIdx.x; j < kRowsPer * N2; j += blockDim.x)
+      rows[j] = (j < nr * N2) ? base[(int64_t)r0 * N2 + j] : make_float2(0.f, 0.f);
+    __syncthreads();
+    const int k2 = threadIdx.x;
+    if (k2 < N2) {
+      float2 acc[kRowsPer];
+#pragma unroll
+      for (int r = 0; r < kRowsPer; ++r) acc[r] = make_float2(0.f, 0.f);
+      int idx = 0;
+      for (int n2 = 0; n2 < N2; ++n2) {
+        const float2 w = wm[idx];
+#pragma unroll
+        for (int r = 0; r < kRowsPer; ++r) {
+          const float2 v = rows[r * N2 + n2];
+          acc[r].x = fmaf(v.x, w.x, fmaf(-v.y, w.y, acc[r].x));
+          acc[r].y = fmaf(v.x, w.y, fmaf(v.y, w.x, acc[r].y));
+        }
+        idx += k2;
+        if (idx >= N2) idx -= N2;
+      }
+#pragma unroll
+      for (int r = 0; r < kRowsPer; ++r)
+        if (r < nr) base[(int64_t)(r0 + r) * N2 + k2] = acc[r];
+    }
+  }
+}
+
+struct MixParams {
+  int S;
+  double c1[kMaxSrc];  // tau(s, mic 1) * fs / L  (cycles per bin)
+  double c2[kMaxSrc];
+};
+
+__device__ __forceinline__ float2 ramp(double cyc_per_bin, int64_t k) {
+  float s, c;
+  sincospif((float)(2.0 * (double)k * cyc_per_bin), &s, &c);
+  return make_float2(c, -s);  // exp(-2 pi i k c)
+}
+
+// ---- pass 3: unpack sources, phase ramps, sum, re-pack.  In place on the spectra: the thread that owns the pair
+//      (k, L-k) is the only one that touches those two positions of any plane. ----
+__global__ void k_mix_combine(float2* __restrict__ Z, MixParams prm, int PP, int N1, int N2, int64_t N) {
+  const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= N) return;
+  const int b = blockIdx.y;
+  const int k1 = (int)(o / N2), k2 = (int)(o % N2);
+  const int64_t k = k1 + (int64_t)N1 * k2;
+  const int64_t km = (N - k) % N;
+  if (k > km) return;
+  const int64_t om = (km % N1) * N2 + km / N1;
+  float2* zb = Z + (int64_t)b * PP * N;
+  float2 m1 = make_float2(0.f, 0.f), m2 = m1, tg = m1;
+  const int P = (prm.S + 1) / 2;
+  for (int p = 0; p < P; ++p) {
+    const float2 zk = zb[(int64_t)p * N + o];
+    const float2 zm = zb[(int64_t)p * N + om];
+    const float2 a = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+    const float2 bv = make_float2(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x));
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int s = 2 * p + h;
+      if (s < prm.S) {
+        const float2 v = h ? bv : a;
+        const float2 d1 = cmul(v, ramp(prm.c1[s], k));
+        const float2 d2 = cmul(v, ramp(prm.c2[s], k));
+        m1 = cadd(m1, d1);
+        m2 = cadd(m2, d2);
+        if (s == 0) tg = d1;
+      }
+    }
+  }
+  float2 in = csub(m1, tg);
+  if (k == km) {  // DC and (even L) Nyquist: the real inverse transform ignores the imaginary part
+    m1.y = 0.f; m2.y = 0.f; tg.y = 0.f; in.y = 0.f;
+  }
+  // x + i y for two real signals x, y: bin k holds X + iY, bin L-k holds conj(X) + i conj(Y)
+  zb[o] = make_float2(m1.x - m2.y, m1.y + m2.x);
+  zb[N + o] = make_float2(tg.x - in.y, tg.y + in.x);
+  if (om != o) {
+    zb[om] = make_float2(m1.x + m2.y, m2.x - m1.y);
+    zb[N + om] = make_float2(tg.x + in.y, in.x - tg.y);
+  }
+}
+
+// ---- pass 5: twiddle conj(W_L^{n2 k1}), power-of-two DIT over k1, 1/L, write the four real signals ----
+__global__ void __launch_bounds__(kColThreads)
+k_mix_cols_inv(const float2* __restrict__ Q, const float2* __restrict__ W, float* __restrict__ mix,
+               float* __restrict__ tgt, float* __restrict__ itf, unsigned* __restrict__ peak_bits, int PP, int N1,
+               int log2N1, int N2, int64_t N) {
+  extern __shared__ float2 sm[];
+  __shared__ float s_max[kColThreads / 32];
+  const int c0 = blockIdx.x * kCols;
+  const int q = blockIdx.y, b = blockIdx.z;
+  const int ncol = min(kCols, N2 - c0);
+  const float2* in = Q + ((int64_t)b * PP + q) * N;
+  for (int idx = threadIdx.x; idx < N1 * kCols; idx += kColThreads) {
+    const int c = idx & (kCols - 1), k1 = idx / kCols;
+    float2 z = make_float2(0.f, 0.f);
+    if (c < ncol) {
+      const int n2 = c0 + c;
+      z = cmulc(in[(int64_t)k1 * N2 + n2], __ldg(W + (int64_t)n2 * k1));
+    }
+    sm[bitrev(k1, log2N1) * kCols + c] = z;
+  }
+  __syncthreads();
+  for (int h = 1; h < N1; h <<= 1) {
+    const int64_t tstep = (int64_t)N2 * (N1 / (2 * h));
+    for (int idx = threadIdx.x; idx < (N1 / 2) * kCols; idx += kColThreads) {
+      const int c = idx & (kCols - 1), j = idx / kCols;
+      const int pos = j & (h - 1);
+      const int i0 = ((j - pos) << 1) + pos;
+      const float2 a = sm[i0 * kCols + c];
+      const float2 bb = cmulc(sm[(i0 + h) * kCols + c], __ldg(W + pos * tstep));
+      sm[i0 * kCols + c] = cadd(a, bb);
+      sm[(i0 + h) * kCols + c] = csub(a, bb);
+    }
+    __syncthreads();
+  }
+  const float inv_n = (float)(1.0 / (double)N);
+  float* o_re = q == 0 ? mix + (int64_t)b * 2 * N : tgt + (int64_t)b * N;
+  float* o_im = q == 0 ? mix + ((int64_t)b * 2 + 1) * N : itf + (int64_t)b * N;
+  float mx = 0.f;
+  for (int idx = threadIdx.x; idx < N1 * kCols; idx += kColThreads) {
+    const int c = idx & (kCols - 1), n1 = idx / kCols;
+    if (c < ncol) {
+      const int64_t g = (int64_t)n1 * N2 + c0 + c;
+      const float2 v = sm[idx];
+      const float re = v.x * inv_n, im = v.y * inv_n;
+      o_re[g] = re;
+      o_im[g] = im;
+      mx = fmaxf(mx, fmaxf(fabsf(re), fabsf(im)));
+    }
+  }
+  if (q == 0) {  // uniform per block
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < kColThreads / 32; ++w) mx = fmaxf(mx, s_max[w]);
+      atomicMax(peak_bits + b, __float_as_uint(mx));  // non-negative floats order like their bit patterns
+    }
+  }
+}
+
+// ---- pass 6: divide mix / tgt / itf by max|mix| + eps (world_building.py:86-91) ----
+__global__ void k_mix_scale(float* __restrict__ mix, float* __restrict__ tgt, float* __restrict__ itf,
+                            const unsigned* __restrict__ peak_bits, float peak_eps, int64_t N) {
+  const int b = blockIdx.y;
+  const float den = __uint_as_float(peak_bits[b]) + peak_eps;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 4 * N; i += (int64_t)gridDim.x * blockDim.x) {
+    float* p = i < 2 * N ? mix + (int64_t)b * 2 * N + i : (i < 3 * N ? tgt + (int64_t)b * N + (i - 2 * N)
+                                                                      : itf + (int64_t)b * N + (i - 3 * N));
+    *p = __fdiv_rn(*p, den);
+  }
+}
+
+__global__ void k_pcm16_to_f32(const int16_t* __restrict__ pcm, int64_t n, float* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n8 = n / 8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const int4 raw = __ldcs(reinterpret_cast<const int4*>(pcm) + i);
+    const int w[4] = {raw.x, raw.y, raw.z, raw.w};
+    float4 lo, hi;
+    lo.x = (float)(short)(w[0] & 0xffff) * (1.f / 32768.f);
+    lo.y = (float)(short)(w[0] >> 16) * (1.f / 32768.f);
+    lo.z = (float)(short)(w[1] & 0xffff) * (1.f / 32768.f);
+    lo.w = (float)(short)(w[1] >> 16) * (1.f / 32768.f);
+    hi.x = (float)(short)(w[2] & 0xffff) * (1.f / 32768.f);
+    hi.y = (float)(short)(w[2] >> 16) * (1.f / 32768.f);
+    hi.z = (float)(short)(w[3] & 0xffff) * (1.f / 32768.f);
+    hi.w = (float)(short)(w[3] >> 16) * (1.f / 32768.f);
+    reinterpret_cast<float4*>(out)[2 * i] = lo;
+    reinterpret_cast<float4*>(out)[2 * i + 1] = hi;
+  }
+  for (int64_t i = n8 * 8 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = (float)pcm[i] * (1.f / 32768.f);
+}
+
+__device__ __forceinline__ int to_pcm(float x) {
+  // libsndfile f2s: lrintf(x * 0x7FFF); NaN -> 0; clipped instead of wrapping
+  const float v = x * 32767.f;
+  if (!(v == v)) return 0;
+  return max(-32768, min(32767, __float2int_rn(fminf(fmaxf(v, -40000.f), 40000.f))));
+}
+
+__global__ void k_f32_to_pcm16(const float* __restrict__ x, int64_t n, int16_t* __restrict__ pcm) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n8 = n / 8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const float4 lo = __ldcs(reinterpret_cast<const float4*>(x) + 2 * i);
+    const float4 hi = __ldcs(reinterpret_cast<const float4*>(x) + 2 * i + 1);
+    int4 o;
+    o.x = (int)((unsigned)(to_pcm(lo.x) & 0xffff) | ((unsigned)to_pcm(lo.y) << 16));
+    o.y = (int)((unsigned)(to_pcm(lo.z) & 0xffff) | ((unsigned)to_pcm(lo.w) << 16));
+    o.z = (int)((unsigned)(to_pcm(hi.x) & 0xffff) | ((unsigned)to_pcm(hi.y) << 16));
+    o.w = (int)((unsigned)(to_pcm(hi.z) & 0xffff) | ((unsigned)to_pcm(hi.w) << 16));
+    reinterpret_cast<int4*>(pcm)[i] = o;
+  }
+  for (int64_t i = n8 * 8 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    pcm[i] = (int16_t)to_pcm(x[i]);
+}
+
+}  // namespace
+}  // namespace avz
+
+extern "C" {
+
+int64_t avz_farfield_mix_ws_bytes(int B, int S, int64_t L) {
+  using namespace avz;
+  int N1, lg, N2;
+  if (B <= 0 || S < 1 || S > kMaxSrc || !split_length(L, &N1, &lg, &N2)) return 0;
+  const int PP = ((S + 1) / 2 > 2) ? (S + 1) / 2 : 2;
+  return (int64_t)B * PP * L * (int64_t)sizeof(float2) + (int64_t)B * 16;
+}
+
+int avz_farfield_mix_f32(const float* src, const double* delays_host, int B, int S, int64_t L, double fs,
+                         float peak_eps, float* mix, float* tgt, float* itf, void* ws, void* stream) {
+  using namespace avz;
+  if (!src || !delays_host || !mix || !tgt || !itf || !ws) return set_error(AVZ_EINVAL, "avz_farfield_mix_f32: null pointer");
+  if (S < 1 || S > kMaxSrc) return set_error(AVZ_EINVAL, "avz_farfield_mix_f32: S=%d out of range (1..%d)", S, kMaxSrc);
+  int N1, lg, N2;
+  if (!split_length(L, &N1, &lg, &N2))
+    return set_error(AVZ_EINVAL,
+                     "avz_farfield_mix_f32: L=%lld unsupported (need L = 2^a * N2 with the odd-or-leftover factor "
+                     "N2 <= %d after taking 2^a <= %d)", (long long)L, kMaxN2, kMaxN1);
+  if (!(fs > 0.0)) return set_error(AVZ_EINVAL, "avz_farfield_mix_f32: fs must be positive");
+  const float2* W = nullptr;
+  int rc = mix_table_for(L, &W);
+  if (rc != AVZ_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int P = (S + 1) / 2;
+  const int PP = P > 2 ? P : 2;
+  if (B <= 0 || (int64_t)B * PP > 65535)
+    return set_error(AVZ_EINVAL, "avz_farfield_mix_f32: B=%d out of range (B * max(2, ceil(S/2)) <= 65535)", B);
+  float2* Z = (float2*)ws;
+  unsigned* peak = (unsigned*)((char*)ws + (int64_t)B * PP * L * (int64_t)sizeof(float2));
+  MixParams prm;
+  prm.S = S;
+  for (int s = 0; s < kMaxSrc; ++s) {
+    prm.c1[s] = s < S ? delays_host[2 * s] * fs / (double)L : 0.0;
+    prm.c2[s] = s < S ? delays_host[2 * s + 1] * fs / (double)L : 0.0;
+  }
+  const size_t col_smem = (size_t)N1 * kCols * sizeof(float2);
+  const size_t row_smem = (size_t)(1 + kRowsPer) * N2 * sizeof(float2);
+  static std::mutex attr_mu;
+  {
+    std::lock_guard<std::mutex> lk(attr_mu);
+    AVZ_CUDA_OK(cudaFuncSetAttribute(k_mix_cols_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)col_smem));
+    AVZ_CUDA_OK(cudaFuncSetAttribute(k_mix_cols_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)col_smem));
+  }
+  const int col_blocks = (N2 + kCols - 1) / kCols;
+  const int row_threads = ((N2 + 31) / 32) * 32;
+  const int row_blocks = (N1 + kRowsPer - 1) / kRowsPer;
+  AVZ_CUDA_OK(cudaMemsetAsync(peak, 0, (size_t)B * sizeof(unsigned), st));
+  k_mix_cols_fwd<<<dim3(col_blocks, P, B), kColThreads, col_smem, st>>>(src, Z, W, S, PP, N1, lg, N2, L);
+  AVZ_LAUNCH_OK("k_mix_cols_fwd");
+  if (N2 > 1) {
+    if (P == PP) {
+      k_mix_rows<false><<<dim3(row_blocks, B * PP), row_threads, row_smem, st>>>(Z, W, N1, N2, L);
+    } else {  // P == 1 < PP == 2: only plane 0 of each utterance holds data; stride 2 planes
+      k_mix_rows<false><<<dim3(row_blocks, B), row_threads, row_smem, st>>>(Z, W, N1, N2, 2 * L);
+    }
+    AVZ_LAUNCH_OK("k_mix_rows<fwd>");
+  }
+  k_mix_combine<<<dim3((unsigned)((L + 255) / 256), B), 256, 0, st>>>(Z, prm, PP, N1, N2, L);
+  AVZ_LAUNCH_OK("k_mix_combine");
+  if (N2 > 1) {
+    if (PP == 2) {
+      k_mix_rows<true><<<dim3(row_blocks, B * 2), row_threads, row_smem, st>>>(Z, W, N1, N2, L);
+      AVZ_LAUNCH_OK("k_mix_rows<inv>");
+    } else {  // planes 0 and 1 of each utterance, utterance stride PP planes
+      for (int q = 0; q < 2; ++q) {
+        k_mix_rows<true><<<dim3(row_blocks, B), row_threads, row_smem, st>>>(Z + (int64_t)q * L, W, N1, N2, (int64_t)PP * L);
+        AVZ_LAUNCH_OK("k_mix_rows<inv>");
+      }
+    }
+  }
+  k_mix_cols_inv<<<dim3(col_blocks, 2, B), kColThreads, col_smem, st>>>(Z, W, mix, tgt, itf, peak, PP, N1, lg, N2, L);
+  AVZ_LAUNCH_OK("k_mix_cols_inv");
+  if (peak_eps >= 0.f) {
+    k_mix_scale<<<dim3(64, B), 256, 0, st>>>(mix, tgt, itf, peak, peak_eps, L);
+    AVZ_LAUNCH_OK("k_mix_scale");
+  }
+  return AVZ_OK;
+}
+
+int avz_pcm16_to_f32(const int16_t* pcm, int64_t n, float* out, void* stream) {
+  using namespace avz;
+  if (!pcm || !out) return set_error(AVZ_EINVAL, "avz_pcm16_to_f32: null pointer");
+  if (n < 0) return set_error(AVZ_EINVAL, "avz_pcm16_to_f32: n < 0");
+  if (n == 0) return AVZ_OK;
+  if (((uintptr_t)pcm & 15) || ((uintptr_t)out & 15)) return set_error(AVZ_EINVAL, "avz_pcm16_to_f32: buffers must be 16-byte aligned");
+  const int64_t want = (n / 8 + 255) / 256 + 1;
+  const int grid = (int)(want < (int64_t)num_sms() * 16 ? want : (int64_t)num_sms() * 16);
+  k_pcm16_to_f32<<<grid, 256, 0, (cudaStream_t)stream>>>(pcm, n, out);
+  AVZ_LAUNCH_OK("k_pcm16_to_f32");
+  return AVZ_OK;
+}
+
+int avz_f32_to_pcm16(const float* x, int64_t n, int16_t* pcm, void* stream) {
+  using namespace avz;
+  if (!pcm || !x) return set_error(AVZ_EINVAL, "avz_f32_to_pcm16: null pointer");
+  if (n < 0) return set_error(AVZ_EINVAL, "avz_f32_to_pcm16: n < 0");
+  if (n == 0) return AVZ_OK;
+  if (((uintptr_t)pcm & 15) || ((uintptr_t)x & 15)) return set_error(AVZ_EINVAL, "avz_f32_to_pcm16: buffers must be 16-byte aligned");
+  const int64_t want = (n / 8 + 255) / 256 + 1;
+  const int grid = (int)(want < (int64_t)num_sms() * 16 ? want : (int64_t)num_sms() * 16);
+  k_f32_to_pcm16<<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, pcm);
+  AVZ_LAUNCH_OK("k_f32_to_pcm16");
+  return AVZ_OK;
+}
+
+}  // extern "C"

@@ -22,6 +22,7 @@ __all__ = [
     "steering_vectors", "mvdr_weights", "hybrid_null_weights", "beamform", "logmag_ipd", "physics_features", "sir_scores",
     "ibm_covariance", "wave_masked_covariance", "mvdr_apply", "peak_normalise", "unpack_ibm",
     "oracle_mask_mvdr", "learned_mask_mvdr", "covariance_to_matrix", "ibm_exact_bits", "irm", "wave_features", "alloc_kept_spectrum",
+    "far_field_mix", "fractional_delay", "pcm16_to_float", "float_to_pcm16",
 ]
 
 
@@ -334,6 +335,66 @@ def sir_scores(est, tgt, itf):
     _lib.check(_lib.load().avz_sir_f32(_ptr(est), _ptr(tgt), _ptr(itf), B, est.shape[-1], tgt.shape[-1], _ptr(sc),
                                        _stream()), "avz_sir_f32")
     return io.give(sc.reshape(*lead, 4))
+
+
+# ------------------------------------------------------------------------------------------ mixer / wire format
+def far_field_mix(sources, delays_s, fs: float = 16000.0, peak_eps: Optional[float] = 1e-9):
+    """Far-field 2-mic mixtures on the device (tf_lite_version/world_building.py:61-93 without the file I/O).
+
+    sources (B,S,L) or (S,L) float32, source 0 = target; delays_s (S,2) seconds per source and microphone
+    (`world_building.calculate_far_field_delays`).  -> mix (B,2,L), tgt (B,L), itf (B,L) float32, all divided by
+    max|mix| + peak_eps per utterance (peak_eps=None: no division)."""
+    io = _Io()
+    src = io.take(sources, torch.float32)
+    single = src.dim() == 2
+    if single:
+        src = src.unsqueeze(0)
+    B, S, L = src.shape
+    dl = np.ascontiguousarray(np.asarray(delays_s, dtype=np.float64).reshape(S, 2))
+    lib = _lib.load()
+    nbytes = lib.avz_farfield_mix_ws_bytes(B, S, L)
+    if nbytes <= 0:
+        raise _lib.AvzError(f"far_field_mix: unsupported shape B={B} S={S} L={L} (see include/avzoom.h)")
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=src.device)
+    mix = torch.empty((B, 2, L), dtype=torch.float32, device=src.device)
+    tgt = torch.empty((B, L), dtype=torch.float32, device=src.device)
+    itf = torch.empty((B, L), dtype=torch.float32, device=src.device)
+    _lib.check(lib.avz_farfield_mix_f32(_ptr(src), dl.ctypes.data_as(C.POINTER(C.c_double)), B, S, L, float(fs),
+                                        -1.0 if peak_eps is None else float(peak_eps), _ptr(mix), _ptr(tgt), _ptr(itf),
+                                        _ptr(ws), _stream()), "avz_farfield_mix_f32")
+    if single:
+        mix, tgt, itf = mix[0], tgt[0], itf[0]
+    return io.give(mix), io.give(tgt), io.give(itf)
+
+
+def fractional_delay(y, delay_sec: float, fs: float = 16000.0):
+    """world_building.py:46-52 `apply_frac_delay`: whole-signal phase-ramp delay of (..., L) signals."""
+    io = _Io()
+    y = io.take(y, torch.float32)
+    lead = y.shape[:-1]
+    src = y.reshape(-1, 1, y.shape[-1])
+    _, out, _ = far_field_mix(src, [[delay_sec, delay_sec]], fs, peak_eps=None)
+    return io.give(out.reshape(*lead, y.shape[-1]))
+
+
+def pcm16_to_float(pcm: torch.Tensor) -> torch.Tensor:
+    """int16 CUDA tensor -> float32 = pcm / 32768 (what `soundfile.read(dtype='float32')` returns; oracle_debug.py:35-39)."""
+    if pcm.dtype != torch.int16 or not pcm.is_cuda:
+        raise _lib.AvzError("pcm16_to_float needs an int16 CUDA tensor")
+    pcm = pcm.contiguous()
+    out = torch.empty(pcm.shape, dtype=torch.float32, device=pcm.device)
+    _lib.check(_lib.load().avz_pcm16_to_f32(_ptr(pcm), pcm.numel(), _ptr(out), _stream()), "avz_pcm16_to_f32")
+    return out
+
+
+def float_to_pcm16(x: torch.Tensor) -> torch.Tensor:
+    """float32 CUDA tensor -> int16 as `soundfile.write` stores PCM_16 (round(x * 32767), clipped; oracle_debug.py:96)."""
+    if x.dtype != torch.float32 or not x.is_cuda:
+        raise _lib.AvzError("float_to_pcm16 needs a float32 CUDA tensor")
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=torch.int16, device=x.device)
+    _lib.check(_lib.load().avz_f32_to_pcm16(_ptr(x), x.numel(), _ptr(out), _stream()), "avz_f32_to_pcm16")
+    return out
 
 
 # ------------------------------------------------------------------------------------------ fused passes

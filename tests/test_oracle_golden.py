@@ -78,6 +78,20 @@ def test_far_field_mixer_parts(helpers):
     assert np.array_equal(O.fractional_delay(helpers["fd_in"], 3.3e-5, 16000), helpers["fd_out"])
 
 
+def test_far_field_mixer_matches_reference_mix_and_save(golden_dir):
+    """world_building.mix_and_save run unmodified on three PCM16 sources (oracle/make_golden.py section 4).  The
+    reference reads float32 and numpy >= 2 then transforms in single precision, so its own output carries ~3e-8 of
+    float32 FFT noise against the float64 restatement."""
+    z = np.load(os.path.join(golden_dir, "ref_mixer.npz"))
+    src = z["src_pcm"].astype(np.float64) / 32768.0
+    d, c, fs = z["d_c_fs"]
+    mix, tgt, itf = O.mix_far_field(list(src), list(z["angles"]), d, c, fs)
+    assert np.abs(mix.T - z["mix"]).max() < 2e-7
+    assert np.abs(tgt - z["tgt"]).max() < 2e-7
+    assert np.abs(itf - z["itf"]).max() < 2e-7
+    assert np.array_equal(O.fractional_delay(z["fd2_in"].astype(np.float64), -4.1e-5, 16000), z["fd2_out"])
+
+
 @pytest.mark.parametrize("n_fft,hop,L", [(512, 128, 80000), (512, 256, 32000), (1024, 512, 32000), (512, 128, 1000),
                                            (512, 128, 64001), (256, 64, 777)])
 def test_stft_restatement_matches_scipy(n_fft, hop, L):
