@@ -61,7 +61,7 @@ def cpu_baseline(n_utt: int | None = None):
     os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
     cores = os.cpu_count() or 1
     if n_utt is None:
-        n_utt = max(256, 4 * cores)
+        n_utt = UTT_PER_GPU                              # the whole config-2 batch: ~25-30 CPU-s of algorithm time
     L = int(DUR_S * FS)
     args = [(1_000_003 * CONFIG_ID + u, L, N_INTERF) for u in range(n_utt)]
     with mp.get_context("fork").Pool(cores) as pool:
@@ -281,6 +281,25 @@ def run_ours(args):
            "d2h_bytes_per_step": int(out_h.numel() + scores_h.numel()) * 4,
            "api": "avzoom.pipeline.HostPipeline.run(pinned mix, tgt, itf) -> (enhanced waveforms, all-gathered scores)"}
     sir_mean = float(scores_h[:, 1].mean())
+    # same leg with the reference's on-disk sample format (PCM16 WAV, oracle_debug.py:35-39,96) on the wire: int16 in
+    # both directions, converted on the device.  Informational: the headline e2e above moves float32.
+    del host
+    to_pcm = lambda a: torch.from_numpy(np.clip(np.rint(a * 32767.0), -32768, 32767).astype(np.int16)).pin_memory()
+    mix_w, tgt_w, itf_w = to_pcm(mix_h), to_pcm(tgt_h), to_pcm(itf_h)
+    host_w = pipeline.HostPipeline(enh, world, wire="pcm16")
+    host_w.run(mix_w, tgt_w, itf_w)
+    barrier()
+    g0.record()
+    for _ in range(e2e_steps):
+        out_w, scores_w = host_w.run(mix_w, tgt_w, itf_w)
+    g1.record()
+    barrier()
+    w_ms = max_over_ranks(g0.elapsed_time(g1)) / e2e_steps
+    e2e["pcm16_wire"] = {"value": audio_s_per_step / (w_ms * 1e-3), "unit": UNIT, "ms_per_step": w_ms,
+                         "h2d_bytes_per_step": int(mix_w.numel() + tgt_w.numel() + itf_w.numel()) * 2,
+                         "d2h_bytes_per_step": int(out_w.numel()) * 2 + int(scores_w.numel()) * 4,
+                         "output_sir_mean": float(scores_w[:, 1].mean())}
+    del host_w, mix_w, tgt_w, itf_w
     sir_in = float(avzoom.sir_scores(mix[:, 0, :].contiguous(), tgt, itf)[:, 1].mean())
 
     cpu = None

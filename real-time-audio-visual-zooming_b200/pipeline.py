@@ -148,10 +148,17 @@ class HostPipeline:
 
     The batch is cut into sub-batches; host->device copies, kernels and device->host copies of consecutive
     sub-batches run on three streams so PCIe transfers overlap compute.  Scores (OSINR, OSIR, SDR, SIR per
-    utterance) are all-gathered across ranks with NCCL when torch.distributed is initialised."""
+    utterance) are all-gathered across ranks with NCCL when torch.distributed is initialised.
 
-    def __init__(self, engine: OracleMvdr, world: int = 1, sub_batches: int = 8):
+    wire="pcm16": the host buffers are int16 (what the reference's WAV files hold, oracle_debug.py:35-39,96); samples
+    cross PCIe as int16 in both directions and are converted on the device (read = /32768 like soundfile, write =
+    round(x*32767) like libsndfile), halving the transfer that bounds this leg."""
+
+    def __init__(self, engine: OracleMvdr, world: int = 1, sub_batches: int = 8, wire: str = "f32"):
+        if wire not in ("f32", "pcm16"):
+            raise ValueError("wire must be 'f32' or 'pcm16'")
         self.e = engine
+        self.wire = wire
         self.world = world
         B = engine.B
         self.nsub = sub_batches if B % sub_batches == 0 and B >= sub_batches else 1
@@ -165,12 +172,23 @@ class HostPipeline:
         self.d_out = [torch.empty((self.sb, engine.out_len), **f32) for _ in range(2)]
         self.scores = torch.empty((B, 4), **f32)
         self.scores_all = torch.empty((B * world, 4), **f32)
-        self.h_out = torch.empty((B, engine.out_len), dtype=torch.float32).pin_memory()
+        if wire == "pcm16":
+            i16 = dict(dtype=torch.int16, device=dev)
+            self.w_mix = [torch.empty((self.sb, 2, engine.L), **i16) for _ in range(2)]
+            self.w_tgt = [torch.empty((self.sb, engine.L), **i16) for _ in range(2)]
+            self.w_itf = [torch.empty((self.sb, engine.L), **i16) for _ in range(2)]
+            self.w_out = [torch.empty((self.sb, engine.out_len), **i16) for _ in range(2)]
+        self.h_out = torch.empty((B, engine.out_len), dtype=torch.int16 if wire == "pcm16" else torch.float32).pin_memory()
         self.h_scores = torch.empty((B * world, 4), dtype=torch.float32).pin_memory()
         self.s_in, self.s_cmp, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
 
     def run(self, mix_h: torch.Tensor, tgt_h: torch.Tensor, itf_h: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         lib = _lib.load()
+        pcm = self.wire == "pcm16"
+        want = torch.int16 if pcm else torch.float32
+        if mix_h.dtype != want or tgt_h.dtype != want or itf_h.dtype != want:
+            raise _lib.AvzError(f"HostPipeline(wire={self.wire!r}) needs {want} host buffers")
+        i_mix, i_tgt, i_itf = (self.w_mix, self.w_tgt, self.w_itf) if pcm else (self.d_mix, self.d_tgt, self.d_itf)
         cur = torch.cuda.current_stream()
         for s in (self.s_in, self.s_cmp, self.s_out):
             s.wait_stream(cur)
@@ -183,22 +201,28 @@ class HostPipeline:
             with torch.cuda.stream(self.s_in):
                 if ev_cmp[slot] is not None:
                     self.s_in.wait_event(ev_cmp[slot])       # previous user of this slot's inputs has finished
-                self.d_mix[slot].copy_(mix_h[lo:hi], non_blocking=True)
-                self.d_tgt[slot].copy_(tgt_h[lo:hi], non_blocking=True)
-                self.d_itf[slot].copy_(itf_h[lo:hi], non_blocking=True)
+                i_mix[slot].copy_(mix_h[lo:hi], non_blocking=True)
+                i_tgt[slot].copy_(tgt_h[lo:hi], non_blocking=True)
+                i_itf[slot].copy_(itf_h[lo:hi], non_blocking=True)
                 ev_in[slot] = self.s_in.record_event()
             with torch.cuda.stream(self.s_cmp):
                 self.s_cmp.wait_event(ev_in[slot])
                 if ev_out[slot] is not None:
                     self.s_cmp.wait_event(ev_out[slot])      # previous output of this slot has left the device
+                if pcm:
+                    for w, d in ((i_mix[slot], self.d_mix[slot]), (i_tgt[slot], self.d_tgt[slot]), (i_itf[slot], self.d_itf[slot])):
+                        _lib.check(lib.avz_pcm16_to_f32(_ptr(w), w.numel(), _ptr(d), _stream()), "avz_pcm16_to_f32")
                 out = self.sub.run(self.d_mix[slot], self.d_tgt[slot], self.d_itf[slot])
                 _lib.check(lib.avz_sir_f32(_ptr(out), _ptr(self.d_tgt[slot]), _ptr(self.d_itf[slot]), self.sb,
                                            self.sub.out_len, self.sub.L, _ptr(self.scores[lo:hi]), _stream()), "avz_sir_f32")
-                self.d_out[slot].copy_(out, non_blocking=True)
+                if pcm:
+                    _lib.check(lib.avz_f32_to_pcm16(_ptr(out), out.numel(), _ptr(self.w_out[slot]), _stream()), "avz_f32_to_pcm16")
+                else:
+                    self.d_out[slot].copy_(out, non_blocking=True)
                 ev_cmp[slot] = self.s_cmp.record_event()
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(ev_cmp[slot])
-                self.h_out[lo:hi].copy_(self.d_out[slot], non_blocking=True)
+                self.h_out[lo:hi].copy_((self.w_out if pcm else self.d_out)[slot], non_blocking=True)
                 ev_out[slot] = self.s_out.record_event()
         cur.wait_stream(self.s_cmp)
         cur.wait_stream(self.s_out)

@@ -127,3 +127,27 @@ def test_pcm16_wire_format(az, n):
     # what soundfile does: write then read is idempotent after the first quantisation
     again = az.ops.float_to_pcm16(az.ops.pcm16_to_float(torch.from_numpy(got).cuda()) * (32768.0 / 32767.0))
     assert np.abs(again.cpu().numpy().astype(np.int32) - got.astype(np.int32)).max() <= 1
+
+
+def test_host_pipeline_pcm16_wire(az):
+    """HostPipeline(wire='pcm16'): int16 host buffers in and out equal the float path run on pcm/32768 and quantised
+    like soundfile.write does."""
+    from avzoom import pipeline, synth
+    cfg = az.PRESETS["baseline_oracle"]
+    dev = torch.device("cuda", 0)
+    mix, tgt, itf = synth.make_batch(2, 8, 1.0, 3)
+    q = lambda a: np.clip(np.rint(a * 32767.0), -32768, 32767).astype(np.int16)
+    mw, tw, iw = q(mix), q(tgt), q(itf)
+    eng = pipeline.OracleMvdr(cfg, 8, 16000, dev)
+    hp = pipeline.HostPipeline(eng, 1, sub_batches=4, wire="pcm16")
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    out, sc = hp.run(pin(mw), pin(tw), pin(iw))
+    assert out.dtype == torch.int16 and out.shape == (8, eng.out_len)
+    f = lambda a: torch.from_numpy(a.astype(np.float32) / 32768.0).cuda()
+    ref = az.ops.oracle_mask_mvdr(f(mw), f(tw), f(iw))
+    want = az.ops.float_to_pcm16(ref).cpu().numpy().astype(np.int32)
+    assert np.abs(out.numpy().astype(np.int32) - want).max() <= 1
+    ref_sc = az.ops.sir_scores(ref, f(tw), f(iw)).cpu().numpy()
+    assert np.allclose(sc.numpy(), ref_sc, atol=1e-3)
+    with pytest.raises(az._lib.AvzError):
+        hp.run(pin(mix), pin(tgt), pin(itf))                # float buffers on the int16 wire

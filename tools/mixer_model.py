@@ -47,11 +47,24 @@ def cols_fwd(z, W, N1, lg, N2):
 
 
 def rows(A, W, N1, N2, inv):
+    """Two-level DFT of every row, as k_mix_rows does it: N2 = Na*Nb, n = Nb na + nb, k = ka + Na kb."""
     wm = W[np.arange(N2) * N1]
     if inv:
         wm = wm.conj()
-    idx = np.outer(np.arange(N2), np.arange(N2)) % N2  # [k2][n2]
-    return A @ wm[idx].T
+    Na = max(a for a in range(1, int(N2 ** 0.5) + 1) if N2 % a == 0)
+    Nb = N2 // Na
+    out = np.zeros_like(A)
+    for r in range(A.shape[0]):
+        x = A[r]
+        tb = np.zeros(N2, complex)
+        for t in range(N2):
+            ka, nb = divmod(t, Nb)
+            acc = sum(x[Nb * na + nb] * wm[((na * ka) % Na) * Nb] for na in range(Na))
+            tb[t] = acc * wm[nb * ka]
+        for t in range(N2):
+            ka, kb = divmod(t, Nb)
+            out[r, ka + Na * kb] = sum(tb[ka * Nb + nb] * wm[((nb * kb) % Nb) * Na] for nb in range(Nb))
+    return out
 
 
 def cols_inv(Q, W, N1, lg, N2):
