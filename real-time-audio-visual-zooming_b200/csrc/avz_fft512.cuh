@@ -117,6 +117,7 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
 // synthesis window they multiply with anyway.
 struct Lane {
   float2 ta[4], tb[4];   // [0] unused (= 1)
+  float2 tf[16];         // all 15 products ta[k1] * tb[k2] (init_full(); only kernels with registers to spare use them)
   float sign;            // -1 on lanes L = 3 (mod 4), else +1: multiply the time-domain side by it
   int lane, k1, h, mirror;
   bool k0;               // k1 == 0: the mirrored bins sit one slot further (see header comment)
@@ -141,7 +142,25 @@ struct Lane {
     wr_off = (lane & 1) * 24 + (lane >> 1);
     rd_off = k1 * kRow + 24 * h;
   }
+
+  // the unfactored twiddles W512^(lane k), k = 1..15: 18 more registers, 9 fewer complex multiplies per transform
+  __device__ __forceinline__ void init_full(const float2* __restrict__ tw512) {
+#pragma unroll
+    for (int k = 1; k < 16; ++k) tf[k] = tw512[(lane * k) & 511];
+    tf[0] = make_float2(1.f, 0.f);
+  }
 };
+
+// Second half of the forward transform (after the transposition twiddles have been applied).
+__device__ __forceinline__ void forward_tail(float2 (&v)[16], float2* __restrict__ sm, const Lane& ln);
+
+// Forward transform with the 15 unfactored twiddles (Lane::init_full).
+__device__ __forceinline__ void forward_full(float2 (&v)[16], float2* __restrict__ sm, const Lane& ln) {
+  fft16<false>(v);
+#pragma unroll
+  for (int k = 1; k < 16; ++k) v[k] = cmul(v[k], ln.tf[k]);
+  forward_tail(v, sm, ln);
+}
 
 // Forward transform.  In: v[r] = sign * x[32 r + lane].  Out: v[j] = lo[j], v[8 + j] = hi[j] (spectrum layout).
 __device__ __forceinline__ void forward(float2 (&v)[16], float2* __restrict__ sm, const Lane& ln) {
@@ -154,6 +173,10 @@ __device__ __forceinline__ void forward(float2 (&v)[16], float2* __restrict__ sm
   for (int c = 1; c < 4; ++c)
 #pragma unroll
     for (int a = 0; a < 4; ++a) v[a + 4 * c] = cmul(v[a + 4 * c], ln.tb[c]);
+  forward_tail(v, sm, ln);
+}
+
+__device__ __forceinline__ void forward_tail(float2 (&v)[16], float2* __restrict__ sm, const Lane& ln) {
   float2* wp = sm + ln.wr_off;
 #pragma unroll
   for (int i = 0; i < 16; ++i) wp[i * kRow] = v[i];

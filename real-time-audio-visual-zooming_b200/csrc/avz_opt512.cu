@@ -26,6 +26,9 @@ constexpr int kF = 257;
 constexpr int kFW = 9;
 constexpr int kFP = 288;     // padded bins for partial sums (matches Geo<512>::FP)
 constexpr int kWarps = 4;    // warps per CTA
+#ifndef AVZ_COV_FULLTW
+#define AVZ_COV_FULLTW 1     // k512_cov: 15 unfactored transposition twiddles (+18 registers, -36 instructions per frame)
+#endif
 #ifndef AVZ_MINB_IBM
 #define AVZ_MINB_IBM 4
 #endif
@@ -364,6 +367,9 @@ k512_cov(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, c
   float2* sm = sm_all + (size_t)(threadIdx.x >> 5) * f512::kSmemComplex;
   Lane ln;
   ln.init(tb.tw);
+#if AVZ_COV_FULLTW
+  ln.init_full(tb.tw);   // this kernel runs 2 CTAs/SM on its accumulators anyway: spend spare registers on twiddles
+#endif
   const int lane = ln.lane, warp = threadIdx.x >> 5;
   const int b = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
   const float* m0 = mix + (int64_t)b * 2 * L;
@@ -423,7 +429,11 @@ k512_cov(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, c
       }
       float2 v[16];
       win.frame(v, w);
+#if AVZ_COV_FULLTW
+      f512::forward_full(v, sm, ln);
+#else
       f512::forward(v, sm, ln);
+#endif
       float2 mir[8];
       f512::mirror_of_low(v, mir, ln);
       if (spec != nullptr) {
@@ -543,6 +553,9 @@ k512_apply(const float* __restrict__ mix, const float4* __restrict__ spec, const
 
   Lane ln;
   ln.init(tb.tw);
+#if AVZ_COV_FULLTW
+  if (!KEPT) ln.init_full(tb.tw);   // same twiddles as k512_cov: recomputed and kept spectra are bit-identical
+#endif
   const int lane = ln.lane, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
   const float* m0 = mix + (int64_t)b * 2 * L;
@@ -731,7 +744,11 @@ k512_apply(const float* __restrict__ mix, const float4* __restrict__ spec, const
           }
           float2 v[16];
           win.frame(v, hw);
+#if AVZ_COV_FULLTW
+          f512::forward_full(v, sm, ln);
+#else
           f512::forward(v, sm, ln);
+#endif
           f512::mirror_of_low(v, mir, ln);
 #pragma unroll
           for (int j = 0; j < 8; ++j) zlo[j] = v[j];
