@@ -118,6 +118,7 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
 struct Lane {
   float2 ta[4], tb[4];   // [0] unused (= 1)
   float2 tf[16];         // all 15 products ta[k1] * tb[k2] (init_full(); only kernels with registers to spare use them)
+  float rc[8], rs[8];    // radix-2 twiddles W32^j * (-i)^h as per-lane constants (init_full(); [0] unused)
   float sign;            // -1 on lanes L = 3 (mod 4), else +1: multiply the time-domain side by it
   int lane, k1, h, mirror;
   bool k0;               // k1 == 0: the mirrored bins sit one slot further (see header comment)
@@ -148,10 +149,18 @@ struct Lane {
 #pragma unroll
     for (int k = 1; k < 16; ++k) tf[k] = tw512[(lane * k) & 511];
     tf[0] = make_float2(1.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {   // W32^j = tw512[16 j] = (c, -s);  h = 1: (c', s') = (-s, c)
+      const float2 w = tw512[16 * j];
+      rc[j] = h ? w.y : w.x;
+      rs[j] = h ? w.x : -w.y;
+    }
   }
 };
 
-// Second half of the forward transform (after the transposition twiddles have been applied).
+// Second half of the forward transform (after the transposition twiddles have been applied).  LANEC: the radix-2
+// twiddles come from Lane::rc/rs (14 registers) instead of immediates + 2 selects + 1 multiply per j.
+template <bool LANEC>
 __device__ __forceinline__ void forward_tail(float2 (&v)[16], float2* __restrict__ sm, const Lane& ln);
 
 // Forward transform with the 15 unfactored twiddles (Lane::init_full).
@@ -159,7 +168,7 @@ __device__ __forceinline__ void forward_full(float2 (&v)[16], float2* __restrict
   fft16<false>(v);
 #pragma unroll
   for (int k = 1; k < 16; ++k) v[k] = cmul(v[k], ln.tf[k]);
-  forward_tail(v, sm, ln);
+  forward_tail<true>(v, sm, ln);
 }
 
 // Forward transform.  In: v[r] = sign * x[32 r + lane].  Out: v[j] = lo[j], v[8 + j] = hi[j] (spectrum layout).
@@ -173,9 +182,10 @@ __device__ __forceinline__ void forward(float2 (&v)[16], float2* __restrict__ sm
   for (int c = 1; c < 4; ++c)
 #pragma unroll
     for (int a = 0; a < 4; ++a) v[a + 4 * c] = cmul(v[a + 4 * c], ln.tb[c]);
-  forward_tail(v, sm, ln);
+  forward_tail<false>(v, sm, ln);
 }
 
+template <bool LANEC>
 __device__ __forceinline__ void forward_tail(float2 (&v)[16], float2* __restrict__ sm, const Lane& ln) {
   float2* wp = sm + ln.wr_off;
 #pragma unroll
@@ -197,6 +207,13 @@ __device__ __forceinline__ void forward_tail(float2 (&v)[16], float2* __restrict
     const float ry = __shfl_xor_sync(kFull, v[8 + j].y, 16);
     const float2 E = hh ? make_float2(rx, ry) : v[j];
     const float2 O = hh ? v[j] : make_float2(rx, ry);
+    if (LANEC && j > 0) {   // (p, q) = O * W32^j * (-i)^h with this lane's constants
+      const float p = fmaf(O.x, ln.rc[j], O.y * ln.rs[j]);
+      const float q = fmaf(O.y, ln.rc[j], -O.x * ln.rs[j]);
+      v[j] = make_float2(E.x + p, E.y + q);
+      v[8 + j] = make_float2(E.x - p, E.y - q);
+      continue;
+    }
     // t = O * W32^j ; for h = 1 the twiddle is W32^(j+8) = -i W32^j
     float2 t;
     if (j == 0) {

@@ -26,11 +26,14 @@ constexpr int kF = 257;
 constexpr int kFW = 9;
 constexpr int kFP = 288;     // padded bins for partial sums (matches Geo<512>::FP)
 constexpr int kWarps = 4;    // warps per CTA
+#ifndef AVZ_IBM_FULLTW
+#define AVZ_IBM_FULLTW 1     // k512_ibm: unfactored twiddles + per-lane radix-2 constants; needs AVZ_MINB_IBM <= 3 (168 registers)
+#endif
 #ifndef AVZ_COV_FULLTW
 #define AVZ_COV_FULLTW 1     // k512_cov: 15 unfactored transposition twiddles (+18 registers, -36 instructions per frame)
 #endif
 #ifndef AVZ_MINB_IBM
-#define AVZ_MINB_IBM 4
+#define AVZ_MINB_IBM 3
 #endif
 #ifndef AVZ_MINB_COV
 #define AVZ_MINB_COV 2
@@ -194,6 +197,9 @@ k512_ibm(const float* __restrict__ tgt, const float* __restrict__ itf, int L, in
   float2* sm = reinterpret_cast<float2*>(smem_raw) + (size_t)(threadIdx.x >> 5) * f512::kSmemComplex;
   Lane ln;
   ln.init(tb.tw);
+#if AVZ_IBM_FULLTW
+  ln.init_full(tb.tw);
+#endif
   const int lane = ln.lane, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
   const float* tg = tgt + (int64_t)b * L;
@@ -217,7 +223,11 @@ k512_ibm(const float* __restrict__ tgt, const float* __restrict__ itf, int L, in
 #pragma unroll
     for (int r = 0; r < 16; ++r) e2 = fmaf(v[r].x, v[r].x, fmaf(v[r].y, v[r].y, e2));
     e2 = warp_sum(e2);
+#if AVZ_IBM_FULLTW
+    f512::forward_full(v, sm, ln);
+#else
     f512::forward(v, sm, ln);
+#endif
     float2 mir[8];
     f512::mirror_of_low(v, mir, ln);
     // float32 FFT error bound of one bin: delta = tol * sqrt(e2)  (e2 = sum |frame|^2, so 512 e2 = sum |Z|^2
