@@ -233,6 +233,8 @@ __device__ __forceinline__ void forward_tail(float2 (&v)[16], float2* __restrict
 }
 
 // Unnormalised inverse transform.  In: v[j] = lo[j], v[8 + j] = hi[j].  Out: v[r] = sign * 512 * x[32 r + lane].
+// FULL: the 15 unfactored twiddles of Lane::init_full instead of the 6 factored ones.
+template <bool FULL = false>
 __device__ __forceinline__ void inverse(float2 (&v)[16], float2* __restrict__ sm, const Lane& ln) {
   const bool hh = ln.h != 0;
 #pragma unroll
@@ -268,14 +270,19 @@ __device__ __forceinline__ void inverse(float2 (&v)[16], float2* __restrict__ sm
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = rp[i * kRow];
   __syncwarp();
+  if (FULL) {
 #pragma unroll
-  for (int a = 1; a < 4; ++a)
+    for (int k = 1; k < 16; ++k) v[k] = cmulc(v[k], ln.tf[k]);
+  } else {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) v[a + 4 * c] = cmulc(v[a + 4 * c], ln.ta[a]);
+    for (int a = 1; a < 4; ++a)
 #pragma unroll
-  for (int c = 1; c < 4; ++c)
+      for (int c = 0; c < 4; ++c) v[a + 4 * c] = cmulc(v[a + 4 * c], ln.ta[a]);
 #pragma unroll
-    for (int a = 0; a < 4; ++a) v[a + 4 * c] = cmulc(v[a + 4 * c], ln.tb[c]);
+    for (int c = 1; c < 4; ++c)
+#pragma unroll
+      for (int a = 0; a < 4; ++a) v[a + 4 * c] = cmulc(v[a + 4 * c], ln.tb[c]);
+  }
   fft16<true>(v);
 }
 

@@ -29,6 +29,9 @@ constexpr int kWarps = 4;    // warps per CTA
 #ifndef AVZ_IBM_FULLTW
 #define AVZ_IBM_FULLTW 1     // k512_ibm: unfactored twiddles + per-lane radix-2 constants; needs AVZ_MINB_IBM <= 3 (168 registers)
 #endif
+#ifndef AVZ_APPLY_FULLTW
+#define AVZ_APPLY_FULLTW 0   // k512_apply<KEPT>: unfactored twiddles in the inverse transform (needs AVZ_MINB_APPLY_KEPT 2)
+#endif
 #ifndef AVZ_COV_FULLTW
 #define AVZ_COV_FULLTW 1     // k512_cov: 15 unfactored transposition twiddles (+18 registers, -36 instructions per frame)
 #endif
@@ -564,7 +567,7 @@ k512_apply(const float* __restrict__ mix, const float4* __restrict__ spec, const
   Lane ln;
   ln.init(tb.tw);
 #if AVZ_COV_FULLTW
-  if (!KEPT) ln.init_full(tb.tw);   // same twiddles as k512_cov: recomputed and kept spectra are bit-identical
+  if (!KEPT || AVZ_APPLY_FULLTW) ln.init_full(tb.tw);   // !KEPT: same twiddles as k512_cov, so recomputed and kept spectra are bit-identical
 #endif
   const int lane = ln.lane, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
@@ -799,7 +802,7 @@ k512_apply(const float* __restrict__ mix, const float4* __restrict__ spec, const
       const int g_a = is_first ? g : g - 1;
       float2 v[16];
       f512::hermitian_pack(Sa, S, make_float2(ny_a, s_ny), v, ln);
-      f512::inverse(v, sm, ln);
+      f512::inverse<(AVZ_APPLY_FULLTW != 0)>(v, sm, ln);
 #pragma unroll
       for (int r = 0; r < 16; ++r) o[r] = fmaf(hw[r], v[r].x, o[r]);
       close_block(g_a);
