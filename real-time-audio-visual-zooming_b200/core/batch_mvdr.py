@@ -46,6 +46,25 @@ def batch_mvdr(Y, mask, f_bins, d_vectors, sigma):
     return S.cpu().numpy() if is_np else S
 
 
+class TFLiteBeamformer:
+    """Name and call contract of tf_lite_version/inference.py:185-241: `predict_mask(log_mag (F,T), ipd (F,T)) -> (F,T)`.
+    The interpreter is a torch module (`model=`, or a TorchScript file at `model_path`) that receives the reference's
+    input tensor (1, F, T, 2) float32 NHWC = [log_mag, ipd]."""
+
+    def __init__(self, model_path="mask_estimator.tflite", model=None):
+        if model is None:
+            model = torch.jit.load(model_path, map_location="cuda" if torch.cuda.is_available() else "cpu")
+        self.model = model
+
+    def predict_mask(self, log_mag, ipd):
+        is_np = isinstance(log_mag, np.ndarray)
+        lm = torch.as_tensor(log_mag, dtype=torch.float32)
+        x = torch.stack([lm, torch.as_tensor(ipd, dtype=torch.float32).to(lm.device)], dim=-1)[None]
+        with torch.no_grad():
+            out = self.model(x).float().squeeze()
+        return out.cpu().numpy() if is_np else out
+
+
 def process_audio_file(input_path, output_path, model=None, model_path=None):
     """Chunked enhancement of a WAV file (:245-391): 2 s windows, 50 % overlap, count-averaged overlap-add, peak
     normalisation with 1e-9.  `model` is a torch mask estimator ((B,2,F,T) -> (B,F,T))."""

@@ -63,6 +63,35 @@ def hybrid_hard_null_bf(Y, mask, f_bins):
     return S.cpu().numpy() if is_np else S
 
 
+class TFLiteBeamformer:
+    """Name and call contract of the reference's physics-aware wrapper (Final_pipeline/src/inference.py:102-141):
+    `TFLiteBeamformer(model_path).predict_mask(log_mag (F,T), raw_ipd (F,T)) -> (F,T)`.
+
+    The TFLite interpreter is replaced by a torch module: `model_path` is a TorchScript file (`torch.jit.load`), or
+    pass `model=` directly; it receives the reference's input tensor, (1, F, T, 4) float32 NHWC =
+    [log_mag, sin ipd, cos ipd, linspace(0,1,F) tiled over T], and returns the mask in any shape that squeezes to
+    (F, T).  A missing file raises FileNotFoundError like the reference.  (Batches of windows take the fused kernel
+    instead: `ops.wave_features(chunks, n_fft, hop, 'physics')` builds the same tensor straight from the waveform.)"""
+
+    def __init__(self, model_path, model=None):
+        if model is None:
+            if not os.path.exists(model_path):
+                raise FileNotFoundError(f"Model file not found: {model_path}")
+            model = torch.jit.load(model_path, map_location="cuda" if torch.cuda.is_available() else "cpu")
+        self.model = model
+        self.freq_map = np.linspace(0, 1, FREQ_BINS, dtype=np.float32)[:, np.newaxis]
+
+    def predict_mask(self, log_mag, raw_ipd):
+        is_np = isinstance(log_mag, np.ndarray)
+        lm = torch.as_tensor(log_mag, dtype=torch.float32)
+        ipd = torch.as_tensor(raw_ipd, dtype=torch.float32).to(lm.device)
+        fmap = torch.linspace(0, 1, lm.shape[0], dtype=torch.float32, device=lm.device)[:, None].expand(-1, lm.shape[1])
+        x = torch.stack([lm, torch.sin(ipd), torch.cos(ipd), fmap], dim=-1)[None]
+        with torch.no_grad():
+            out = self.model(x).float().squeeze()
+        return out.cpu().numpy() if is_np else out
+
+
 def enhance_chunks(chunks: torch.Tensor, model, cfg: MvdrConfig = FINAL_CFG) -> torch.Tensor:
     """One batch of 2 s windows (n, 2, win) -> (n, iSTFT length): features (STFT fused) -> mask model -> interference
     covariance (STFT fused) -> hybrid-null weights -> beamform + S * mask + iSTFT (fused)."""

@@ -87,3 +87,43 @@ def test_chunk_split_matches_reference_windows():
     outs = torch.ones((3, 32256))
     full = chunked.overlap_add_chunks(outs, L, win, stride, buf_extra=win)
     assert full.shape == (L,) and torch.allclose(full, torch.ones(L))
+
+
+def test_tflite_beamformer_wrappers_keep_the_reference_contract(tmp_path):
+    """TFLiteBeamformer.predict_mask (Final_pipeline/src/inference.py:117-141, tf_lite_version/inference.py:205-241):
+    the model sees the reference's NHWC input tensor and the result squeezes to (F, T)."""
+    from avzoom.final_pipeline import inference as fin
+    from avzoom.core import batch_mvdr as tfl
+    rng = np.random.default_rng(3)
+    F, T = fin.FREQ_BINS, 7
+    lm = rng.standard_normal((F, T)).astype(np.float32)
+    ipd = rng.uniform(-6, 6, (F, T)).astype(np.float32)
+    seen = {}
+
+    def model4(x):
+        seen["x4"] = x.clone()
+        return torch.sigmoid(x[..., 0] + x[..., 3])[..., None]
+
+    out = fin.TFLiteBeamformer("unused", model=model4).predict_mask(lm, ipd)
+    want = np.stack([lm, np.sin(ipd), np.cos(ipd), np.tile(np.linspace(0, 1, F, dtype=np.float32)[:, None], (1, T))], axis=-1)[None]
+    assert isinstance(out, np.ndarray) and out.shape == (F, T)
+    assert seen["x4"].shape == (1, F, T, 4) and np.allclose(seen["x4"].numpy(), want, atol=1e-6)
+    with pytest.raises(FileNotFoundError):
+        fin.TFLiteBeamformer(str(tmp_path / "missing.tflite"))
+
+    def model2(x):
+        seen["x2"] = x.clone()
+        return x[..., 1]
+
+    out2 = tfl.TFLiteBeamformer(model=model2).predict_mask(lm, ipd)
+    assert seen["x2"].shape == (1, F, T, 2) and np.array_equal(out2, ipd)
+    # a TorchScript file stands in for the .tflite blob
+    class M(torch.nn.Module):
+        def forward(self, x):
+            return torch.sigmoid(x[..., 0])
+    path = str(tmp_path / "mask.pt")
+    torch.jit.script(M()).save(path)
+    bf = tfl.TFLiteBeamformer(path)
+    x = torch.from_numpy(lm).to(next(iter([torch.device("cuda" if torch.cuda.is_available() else "cpu")])))
+    got = bf.predict_mask(x, torch.from_numpy(ipd).to(x.device))
+    assert torch.allclose(got.cpu(), torch.sigmoid(torch.from_numpy(lm)), atol=1e-6)
