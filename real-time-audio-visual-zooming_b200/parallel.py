@@ -3,7 +3,8 @@ hot path moves no data between GPUs.  The one collective is an all-gather of the
 (SURVEY.md 8-E).  Works with the `nccl` backend on GPUs and with `gloo` on CPU tensors (used by the tests)."""
 from __future__ import annotations
 
-from typing import Tuple
+import os
+from typing import List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -38,3 +39,27 @@ def gather_scores(local: torch.Tensor, n_total: int) -> torch.Tensor:
         lo, hi = shard_range(n_total, r, world)
         parts.append(buf[r * big:r * big + (hi - lo)])
     return torch.cat(parts, dim=0)
+
+
+def bind_to_gpu_numa(gpu_index: int) -> Optional[List[int]]:
+    """Pin this process to the CPUs NVML reports as local to GPU `gpu_index`, so that pinned host buffers allocated
+    afterwards (first touch) sit on the GPU's own NUMA node and host<->device copies do not cross sockets.  Only the
+    host-buffer leg cares (the hot path never touches the host).  Returns the CPU list, or None if NVML has no answer."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            n_cpu = os.cpu_count() or 1
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        finally:
+            pynvml.nvmlShutdown()
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
