@@ -276,10 +276,21 @@ def run_ours(args):
     dom = max(algo, key=lambda k: ktimes.get(k, 0.0))
     achieved = algo[dom] / (ktimes[dom] * 1e-3) / 1e9
     traffic, traffic_src = None, None
+    issue = None
     try:  # DRAM bytes per launch of that kernel from the committed ncu --set full capture of the same shape
         tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
         traffic = tj["per_launch"][dom]["dram_read_bytes"] + tj["per_launch"][dom]["dram_write_bytes"]
         traffic_src = "profiles/r1_ncu_traffic.json (" + tj["source"] + ")"
+        # what actually bounds the transform kernels: warp-instruction issue slots (4 schedulers per SM, one
+        # instruction per clock each).  Instruction counts from the same ncu capture, times live.
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        clk_hz = 1e6 * (((clocks or {}).get("sm_mhz")) or 1965.0)
+        slots_per_s = sms * 4 * clk_hz
+        issue = {"unit": "fraction of warp-instruction issue slots", "peak_slots_per_s": slots_per_s, "kernels": {
+            k: (tj["per_launch"][k]["warp_instructions"] * B / 1024.0) / (ktimes[k] * 1e-3) / slots_per_s
+            for k in ("k512_ibm", "k512_cov", "k512_apply") if ktimes.get(k)},
+            "note": "instruction counts per launch from profiles/r1_ncu_traffic.json (ncu smsp__inst_executed.sum at "
+                    "B = 1024), divided by the CUDA-event kernel time measured in this run"}
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
@@ -287,7 +298,8 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": algo[dom], "kernel_ms": ktimes,
                 "note": "fp32-issue-bound path (DESIGN.md 3.1): ~2540 warp-instructions per frame set the time, not HBM",
                 "path_achieved_GBps": (value / world) * FS * ALGO_BYTES_PER_SAMPLE / 1e9,
-                "path_frac_of_hbm_roofline": (value / world) * FS * ALGO_BYTES_PER_SAMPLE / (peak_gbs * 1e9)}
+                "path_frac_of_hbm_roofline": (value / world) * FS * ALGO_BYTES_PER_SAMPLE / (peak_gbs * 1e9),
+                "issue_slots": issue}
 
     # ---- end to end through the public host-buffer API
     e2e_steps = max(2, min(args.steps, 5))

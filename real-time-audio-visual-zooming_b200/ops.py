@@ -64,11 +64,6 @@ def num_frames(length: int, n_fft: int, hop: int) -> int:
     return int(_lib.load().avz_num_frames(int(length), int(n_fft), int(hop)))
 
 
-def _as_real_view(z: torch.Tensor) -> torch.Tensor:
-    return torch.view_as_real(z)
-
-
-# ------------------------------------------------------------------------------------------ STFT / iSTFT
 def stft(x, n_fft: int = 512, hop: int = 128):
     """scipy.signal.stft(x, fs, nperseg=n_fft, noverlap=n_fft-hop)[2] (oracle_debug.py:42-44).
     x (..., L) float32 -> (..., F, T) complex64.  Pairs of rows along the second-to-last axis share one

@@ -40,7 +40,7 @@ for r in rows[2:]:
     inst = get(r, "smsp__inst_executed.sum")
     st = [get(r, "smsp__average_warps_issue_stalled_%s_per_issue_active.ratio" % s)
           for s in ("long_scoreboard", "wait", "not_selected", "short_scoreboard")]
-    per[short] = {"dram_read_bytes": rd, "dram_write_bytes": wr, "ncu_duration_us": us}
+    per[short] = {"dram_read_bytes": rd, "dram_write_bytes": wr, "ncu_duration_us": us, "warp_instructions": inst}
     ipf = "%.0f" % (inst / frames) if short.startswith("k512") and "fixup" not in short else "-"
     print("| `%s` | %.0f | %d | %s | %.0f %% | %.3f / %.3f | %.0f (%.0f %%) | %.2f / %.2f / %.2f / %.2f |" % (
         short, us, get(r, "launch__registers_per_thread"), ipf,
