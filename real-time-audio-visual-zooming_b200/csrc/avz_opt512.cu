@@ -909,7 +909,7 @@ static float ibm_tol2() {
   // (relative float32 FFT error bound)^2, relative to the rms bin magnitude of the frame; AVZ_IBM_TOL overrides
   // the bound for experiments.  Measured worst case of this transform: see DESIGN.md.
   static const float t2 = [] {
-    double tol = 1e-6;
+    double tol = 5e-7;   // 5x the level where the first float32 decision errors appear
     if (const char* e = getenv("AVZ_IBM_TOL")) tol = atof(e);
     return (float)(tol * tol);
   }();
