@@ -1045,24 +1045,85 @@ namespace o512 {
 
 constexpr int kStreamStateFloats = 2 * 384 + 384 + 5 * 288;   // hist, tail, cov (8 x 32 + Nyquist row, padded to 288)
 
+// The stream's whole state (10 KB) and its new hop are brought into shared memory by two TMA bulk copies issued at
+// kernel entry, so the ~600 ns trip to L2/HBM overlaps the per-lane set-up instead of stalling every dependent load
+// (the kernel is one long dependent chain per warp; ncu before this change: 3 long-scoreboard stalls per issue).
+constexpr int kStreamStageFloats = kStreamStateFloats + 256;   // state + new hop [2][128]
+constexpr size_t kStreamSmem = (size_t)kWarps * f512::kSmemComplex * sizeof(float2) +
+                               (size_t)kWarps * kStreamStageFloats * sizeof(float) + (size_t)kWarps * sizeof(uint64_t);
+
+// MVDR weights of one bin from the recursive statistics, float64, one division.  With nne = n + norm_eps,
+// A' = R00 + sigma nne, C' = R11 + sigma nne, b' = R01 (all "times nne"), det' = A' C' - |b'|^2, u' = adj(.) d:
+//   w = u / (d^H u + w_eps),  u = (R/nne + sigma I)^-1 d = u' nne / det'   =>   w = u' nne / (d^H u' nne + w_eps det')
+// An exactly singular (or non-finite) system gives w = [1, 0] like the batch kernel (masked_mvdr.py:120-122).
+__device__ __forceinline__ void stream_weights(float r00, float r11, float rre, float rim, float nn, float2 d0f,
+                                               float2 d1f, const AvzMvdrCfg& cfg, float2& w0, float2& w1) {
+  const double nne = (double)nn + (double)cfg.norm_eps;
+  const double sg = (double)cfg.sigma * nne;
+  const double aa = (double)r00 + sg, cc = (double)r11 + sg, bx = (double)rre, by = (double)rim;
+  const double d0x = (double)d0f.x, d0y = (double)d0f.y, d1x = (double)d1f.x, d1y = (double)d1f.y;
+  const double det = aa * cc - (bx * bx + by * by);
+  w0 = make_float2(1.f, 0.f);
+  w1 = make_float2(0.f, 0.f);
+  if (det == 0.0 || !isfinite(det)) return;
+  // u0' = C' d0 - b' d1,  u1' = A' d1 - conj(b') d0
+  const double u0x = cc * d0x - (bx * d1x - by * d1y), u0y = cc * d0y - (bx * d1y + by * d1x);
+  const double u1x = aa * d1x - (bx * d0x + by * d0y), u1y = aa * d1y - (bx * d0y - by * d0x);
+  // D = nne (conj(d0) u0' + conj(d1) u1') + w_eps det'
+  const double dx = nne * (d0x * u0x + d0y * u0y + d1x * u1x + d1y * u1y) + (double)cfg.w_eps * det;
+  const double dy = nne * (d0x * u0y - d0y * u0x + d1x * u1y - d1y * u1x);
+  const double r = nne / (dx * dx + dy * dy);
+  w0 = make_float2((float)((u0x * dx + u0y * dy) * r), (float)((u0y * dx - u0x * dy) * r));
+  w1 = make_float2((float)((u1x * dx + u1y * dy) * r), (float)((u1y * dx - u1x * dy) * r));
+}
+
 __global__ void __launch_bounds__(kWarps * 32, 3)
 k512_stream_step(float* __restrict__ state, const float* __restrict__ hop_in, const float* __restrict__ noise_w,
                  const float2* __restrict__ dvec, int n_streams, int t, int t_end, float lam, AvzMvdrCfg cfg,
                  float* __restrict__ hop_out, Tables tb) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float2* sm = reinterpret_cast<float2*>(smem_raw) + (size_t)(threadIdx.x >> 5) * f512::kSmemComplex;
+  const int warp = threadIdx.x >> 5;
+  float2* sm = reinterpret_cast<float2*>(smem_raw) + (size_t)warp * f512::kSmemComplex;
+  float* stage = reinterpret_cast<float*>(smem_raw + (size_t)kWarps * f512::kSmemComplex * sizeof(float2)) +
+                 (size_t)warp * kStreamStageFloats;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kWarps * f512::kSmemComplex * sizeof(float2) +
+                                              (size_t)kWarps * kStreamStageFloats * sizeof(float)) + warp;
+  const int s = blockIdx.x * kWarps + warp;
+  if (s >= n_streams) return;
+  float* st = state + (size_t)s * kStreamStateFloats;
+  const float* xin_g = hop_in + (size_t)s * 256;   // [2][128]
+  if ((threadIdx.x & 31) == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+    mbar_arrive_expect_tx(bar, kStreamStageFloats * sizeof(float));
+    tma_load_1d(stage, st, kStreamStateFloats * sizeof(float), bar);
+    tma_load_1d(stage + kStreamStateFloats, xin_g, 256 * sizeof(float), bar);
+  }
   Lane ln;
   ln.init(tb.tw);
   const int lane = ln.lane;
-  const int s = blockIdx.x * kWarps + (threadIdx.x >> 5);
-  if (s >= n_streams) return;
-  float* st = state + (size_t)s * kStreamStateFloats;
-  float* hist = st;                 // [2][384]
-  float* tail = st + 768;           // [384]  open output blocks t+1 .. t+3 before this call's frame is added
-  float* cov = st + 1152;           // [5][288]
-  const float* xin = hop_in + (size_t)s * 256;   // [2][128]
   float hw[16];
   load_window(hw, tb.win, ln);
+  const bool frame_valid = (t >= 0) && (t < t_end);
+  // this lane's noise weights and steering vectors: requested now, used after the forward transform
+  float mk[9];
+  float2 dv0[8], dv1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = bin_lo(ln, j);
+    mk[j] = noise_w ? __ldg(noise_w + (size_t)s * kF + k) : 1.f;
+    dv0[j] = __ldg(dvec + 2 * k);
+    dv1[j] = __ldg(dvec + 2 * k + 1);
+  }
+  mk[8] = noise_w ? __ldg(noise_w + (size_t)s * kF + 256) : 1.f;
+  __syncwarp();
+  mbar_wait(bar, 0);
+
+  const float* hist = stage;                       // [2][384]
+  const float* tail = stage + 768;                 // [384]  open output blocks t+1 .. t+3 before this frame is added
+  const float* cov = stage + 1152;                 // [5][288]
+  const float* xin = stage + kStreamStateFloats;   // [2][128]
+  float* cov_g = st + 1152;
 
   // frame t = [history (rows 0..11) | new hop (rows 12..15)], then slide the history
   float a[16], b[16];
@@ -1078,10 +1139,9 @@ k512_stream_step(float* __restrict__ state, const float* __restrict__ hop_in, co
   }
 #pragma unroll
   for (int r = 0; r < 12; ++r) {
-    hist[32 * r + lane] = a[r + 4];
-    hist[384 + 32 * r + lane] = b[r + 4];
+    st[32 * r + lane] = a[r + 4];
+    st[384 + 32 * r + lane] = b[r + 4];
   }
-  const bool frame_valid = (t >= 0) && (t < t_end);
   float o[16];
 #pragma unroll
   for (int r = 0; r < 12; ++r) o[r] = tail[32 * r + lane];
@@ -1104,7 +1164,7 @@ k512_stream_step(float* __restrict__ state, const float* __restrict__ hop_in, co
       const int k = bin_lo(ln, j);
       const float2 y0 = make_float2(v[j].x + mir[j].x, v[j].y - mir[j].y);   // 2 Y0 (x N/2)
       const float2 y1 = make_float2(v[j].y + mir[j].y, mir[j].x - v[j].x);   // 2 Y1
-      const float m = noise_w ? noise_w[(size_t)s * kF + k] : 1.f;
+      const float m = mk[j];
       const int ci = 32 * j + lane;
       const float r00 = fmaf(lam, cov[0 * 288 + ci], one_m * m * sc * cabs2(y0));
       const float r11 = fmaf(lam, cov[1 * 288 + ci], one_m * m * sc * cabs2(y1));
@@ -1112,72 +1172,38 @@ k512_stream_step(float* __restrict__ state, const float* __restrict__ hop_in, co
       const float rre = fmaf(lam, cov[2 * 288 + ci], one_m * m * sc * c01.x);
       const float rim = fmaf(lam, cov[3 * 288 + ci], one_m * m * sc * c01.y);
       const float nn = fmaf(lam, cov[4 * 288 + ci], one_m * m);
-      cov[0 * 288 + ci] = r00;
-      cov[1 * 288 + ci] = r11;
-      cov[2 * 288 + ci] = rre;
-      cov[3 * 288 + ci] = rim;
-      cov[4 * 288 + ci] = nn;
+      cov_g[0 * 288 + ci] = r00;
+      cov_g[1 * 288 + ci] = r11;
+      cov_g[2 * 288 + ci] = rre;
+      cov_g[3 * 288 + ci] = rim;
+      cov_g[4 * 288 + ci] = nn;
       float2 w0 = make_float2(0.f, 0.f), w1 = make_float2(0.f, 0.f);
       if (k < cfg.hp_bins && cfg.hp_mode != AVZ_HP_NONE) {
         if (cfg.hp_mode == AVZ_HP_MIC0) w0.x = 1.f;
       } else {
-        // closed-form 2x2 solve in float64 (as k_mvdr_weights)
-        const double inv = 1.0 / ((double)nn + (double)cfg.norm_eps);
-        const double aa = (double)r00 * inv + (double)cfg.sigma, cc = (double)r11 * inv + (double)cfg.sigma;
-        const double bx = (double)rre * inv, by = (double)rim * inv;
-        const double2 d0 = make_double2((double)dvec[2 * k].x, (double)dvec[2 * k].y);
-        const double2 d1 = make_double2((double)dvec[2 * k + 1].x, (double)dvec[2 * k + 1].y);
-        const double det = aa * cc - (bx * bx + by * by);
-        if (det == 0.0 || !isfinite(det)) {
-          w0.x = 1.f;
-        } else {
-          // u0 = (c d0 - b d1)/det, u1 = (a d1 - conj(b) d0)/det
-          const double u0x = (cc * d0.x - (bx * d1.x - by * d1.y)) / det, u0y = (cc * d0.y - (bx * d1.y + by * d1.x)) / det;
-          const double u1x = (aa * d1.x - (bx * d0.x + by * d0.y)) / det, u1y = (aa * d1.y - (bx * d0.y - by * d0.x)) / det;
-          // den = conj(d0) u0 + conj(d1) u1 + w_eps
-          const double dx = d0.x * u0x + d0.y * u0y + d1.x * u1x + d1.y * u1y + (double)cfg.w_eps;
-          const double dy = d0.x * u0y - d0.y * u0x + d1.x * u1y - d1.y * u1x;
-          const double dd = dx * dx + dy * dy;
-          w0 = make_float2((float)((u0x * dx + u0y * dy) / dd), (float)((u0y * dx - u0x * dy) / dd));
-          w1 = make_float2((float)((u1x * dx + u1y * dy) / dd), (float)((u1y * dx - u1x * dy) / dd));
-        }
+        stream_weights(r00, r11, rre, rim, nn, dv0[j], dv1[j], cfg, w0, w1);
       }
       // S = conj(w0) Y0 + conj(w1) Y1 with Y = y' / N (analysis 2/N, halved); synthesis factor 1/2 folded below
       const float2 sv = cadd(cmulc(y0, w0), cmulc(y1, w1));
       S[j] = make_float2(sv.x * (0.5f / (float)kN), sv.y * (0.5f / (float)kN));
     }
-    // Nyquist bin (lane 0): Y0 = Re hi[0], Y1 = Im hi[0] (x N/2, not doubled)
+    // Nyquist bin (meaningful on lane 0): Y0 = Re hi[0], Y1 = Im hi[0] (x N/2, not doubled)
     {
       const float scn = 4.0f / ((float)kN * (float)kN);
-      const float m = noise_w ? noise_w[(size_t)s * kF + 256] : 1.f;
+      const float m = mk[8];
       const int ci = 256 + lane;    // row 8 of the cov block: only lane 0's entry is meaningful
       const float r00 = fmaf(lam, cov[0 * 288 + ci], one_m * m * scn * v[8].x * v[8].x);
       const float r11 = fmaf(lam, cov[1 * 288 + ci], one_m * m * scn * v[8].y * v[8].y);
       const float rre = fmaf(lam, cov[2 * 288 + ci], one_m * m * scn * v[8].x * v[8].y);
       const float nn = fmaf(lam, cov[4 * 288 + ci], one_m * m);
-      cov[0 * 288 + ci] = r00;
-      cov[1 * 288 + ci] = r11;
-      cov[2 * 288 + ci] = rre;
-      cov[4 * 288 + ci] = nn;
-      const double inv = 1.0 / ((double)nn + (double)cfg.norm_eps);
-      const double aa = (double)r00 * inv + (double)cfg.sigma, cc = (double)r11 * inv + (double)cfg.sigma;
-      const double bx = (double)rre * inv;
-      const double2 d0 = make_double2((double)dvec[512].x, (double)dvec[512].y);
-      const double2 d1 = make_double2((double)dvec[513].x, (double)dvec[513].y);
-      const double det = aa * cc - bx * bx;
-      double w0x = 1.0, w0y = 0.0, w1x = 0.0, w1y = 0.0;
-      if (det != 0.0 && isfinite(det)) {
-        const double u0x = (cc * d0.x - bx * d1.x) / det, u0y = (cc * d0.y - bx * d1.y) / det;
-        const double u1x = (aa * d1.x - bx * d0.x) / det, u1y = (aa * d1.y - bx * d0.y) / det;
-        const double dx = d0.x * u0x + d0.y * u0y + d1.x * u1x + d1.y * u1y + (double)cfg.w_eps;
-        const double dy = d0.x * u0y - d0.y * u0x + d1.x * u1y - d1.y * u1x;
-        const double dd = dx * dx + dy * dy;
-        w0x = (u0x * dx + u0y * dy) / dd; w0y = (u0y * dx - u0x * dy) / dd;
-        w1x = (u1x * dx + u1y * dy) / dd; w1y = (u1y * dx - u1x * dy) / dd;
-      }
-      (void)w0y; (void)w1y;
+      cov_g[0 * 288 + ci] = r00;
+      cov_g[1 * 288 + ci] = r11;
+      cov_g[2 * 288 + ci] = rre;
+      cov_g[4 * 288 + ci] = nn;
+      float2 w0, w1;
+      stream_weights(r00, r11, rre, 0.f, nn, __ldg(dvec + 512), __ldg(dvec + 513), cfg, w0, w1);
       // Re(conj(w0) Y0 + conj(w1) Y1) for real Y0, Y1; (2/N) analysis x 1/2 synthesis = 1/N
-      s_ny = (float)(w0x * (double)v[8].x + w1x * (double)v[8].y) * (1.0f / (float)kN);
+      s_ny = (w0.x * v[8].x + w1.x * v[8].y) * (1.0f / (float)kN);
       if (256 < cfg.hp_bins && cfg.hp_mode == AVZ_HP_ZERO) s_ny = 0.f;
     }
     float2 Z0[8];
@@ -1202,7 +1228,7 @@ k512_stream_step(float* __restrict__ state, const float* __restrict__ hop_in, co
     yo[32 * r + lane] = o[r] / (nrm > 1e-10f ? nrm : 1.0f);
   }
 #pragma unroll
-  for (int r = 0; r < 12; ++r) tail[32 * r + lane] = o[r + 4];
+  for (int r = 0; r < 12; ++r) st[768 + 32 * r + lane] = o[r + 4];
 }
 
 int launch_stream_step(float* state, const float* hop_in, const float* noise_w, const float* dvec, int n_streams,
@@ -1210,7 +1236,8 @@ int launch_stream_step(float* state, const float* hop_in, const float* noise_w, 
   Tables tb;
   int rc = tables_for(kN, &tb);
   if (rc) return rc;
-  const size_t smem = (size_t)kWarps * f512::kSmemComplex * sizeof(float2);
+  const size_t smem = kStreamSmem;
+  AVZ_CUDA_OK(cudaFuncSetAttribute(k512_stream_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k512_stream_step<<<(n_streams + kWarps - 1) / kWarps, kWarps * 32, smem, st>>>(
       state, hop_in, noise_w, reinterpret_cast<const float2*>(dvec), n_streams, t, t_end, lam, *cfg, hop_out, tb);
   AVZ_LAUNCH_OK("k512_stream_step");
