@@ -154,7 +154,9 @@ AVZ_API int avz_mvdr_apply_f32(const float* mix, const float* w, const uint32_t*
  * The path is fp32-issue-bound, not HBM-bound, so pass A can keep the packed two-mic spectrum of
  * every frame (4096 B per frame in `spec`, avz_spec_ws_bytes() bytes in total; 0 = not supported for this shape) and
  * pass B then skips its forward transform: ~25 % fewer instructions for 64 B/sample of otherwise idle HBM bandwidth.
- * Results are bit-identical to the recomputing variants (same transform, same arithmetic order). */
+ * Results are bit-identical to the recomputing variants (same transform, same arithmetic order).
+ * The buffer also has room for per-utterance completion counters and for a transposed copy (B, T, 264) of the mask:
+ * the mask variants re-lay the caller's (B, F, T) mask there first, so that a frame's 257 weights are contiguous. */
 AVZ_API int64_t avz_spec_ws_bytes(int B, int64_t L, int n_fft, int hop);
 AVZ_API int avz_ibm_cov_keep_f32(const float* mix, const float* tgt, const float* itf, int B, int64_t L, int n_fft, int hop,
                          float norm_eps, uint32_t* ibm_bits, float* R, float* msum, void* ws, void* spec, void* stream);

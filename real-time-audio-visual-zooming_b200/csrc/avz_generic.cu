@@ -17,6 +17,7 @@ namespace avz {
 namespace o512 {
 int cov_chunks512(int B, int T);
 int64_t ws_bytes512(int B, int T);
+int64_t spec_ws_bytes512(int B, int T);
 int launch_stream_step(float* state, const float* hop_in, const float* noise_w, const float* dvec, int n_streams,
                        int t, int t_end, float lam, const AvzMvdrCfg* cfg, float* hop_out, cudaStream_t st);
 template <int HOP>
@@ -288,6 +289,7 @@ __global__ void k_cov_finalize(const float* __restrict__ part, int B, int F, int
   if (idx >= B * F) return;
   const int b = idx / F, k = idx - b * F;
   double s[5] = {0, 0, 0, 0, 0};
+#pragma unroll 4   // independent loads: keep several chunks in flight (the kernel is pure load latency)
   for (int c = 0; c < chunks; ++c) {
     const float* p = part + ((int64_t)b * chunks + c) * 5 * FP;
 #pragma unroll
@@ -530,7 +532,7 @@ static int launch_cov(const float* mix, const float* tgt, const float* itf, cons
                                                          (float*)ws, tb);
   AVZ_LAUNCH_OK("k_cov");
   const int F = Geo<N>::F;
-  k_cov_finalize<<<(B * F + 255) / 256, 256, 0, st>>>((const float*)ws, B, F, Geo<N>::FP, chunks, norm_eps,
+  k_cov_finalize<<<(B * F + 63) / 64, 64, 0, st>>>((const float*)ws, B, F, Geo<N>::FP, chunks, norm_eps,
                                                       reinterpret_cast<float4*>(R), msum);
   AVZ_LAUNCH_OK("k_cov_finalize");
   return AVZ_OK;
@@ -547,7 +549,7 @@ static int launch_cov512(const float* mix, const float* tgt, const float* itf, c
   if (rc) return rc;
   const int F = 257;
   prof_begin(PROF_FINALIZE, st);
-  k_cov_finalize<<<(B * F + 255) / 256, 256, 0, st>>>((const float*)ws, B, F, Geo<512>::FP, chunks, norm_eps,
+  k_cov_finalize<<<(B * F + 63) / 64, 64, 0, st>>>((const float*)ws, B, F, Geo<512>::FP, chunks, norm_eps,
                                                       reinterpret_cast<float4*>(R), msum);
   prof_end(PROF_FINALIZE, st);
   AVZ_LAUNCH_OK("k_cov_finalize");
@@ -680,7 +682,7 @@ int avz_wave_mask_cov_f32(const float* mix, const float* mask, int B, int64_t L,
 // ---- "kept spectrum" variants of the fused passes (n_fft 512 fast path only) ---------------------------------
 int64_t avz_spec_ws_bytes(int B, int64_t L, int n_fft, int hop) {
   if (B <= 0 || check_fft_args(n_fft, hop, L) || !use_opt512(n_fft, hop)) return 0;
-  return (int64_t)B * avz_num_frames(L, n_fft, hop) * 4096 + (int64_t)B * 4;   // + per-utterance completion counters
+  return o512::spec_ws_bytes512(B, (int)avz_num_frames(L, n_fft, hop));
 }
 
 int avz_ibm_cov_keep_f32(const float* mix, const float* tgt, const float* itf, int B, int64_t L, int n_fft, int hop,

@@ -367,14 +367,45 @@ k512_ibm_fixup(const float* __restrict__ tgt, const float* __restrict__ itf, int
 // ------------------------------------------------------------------------------------------
 enum { W_BITS = 0, W_MASK = 1 };
 
+// Where mask[b][k][t] lives: the reference layout (B, F, T) has T contiguous, which makes the per-frame reads of a
+// warp (one bin per lane) 32 separate sectors per load.  When the kept-spectrum buffer is available its tail holds a
+// transposed copy (B, T, kMaskPitch) made by k_mask_transpose, and a frame's 257 weights are 9 contiguous runs.
+struct MaskLayout {
+  int64_t sb;   // floats between utterances
+  int sf;       // floats between bins
+  int st;       // floats between frames
+};
+constexpr int kMaskPitch = 264;   // 257 bins padded to a multiple of 8 floats (32-byte rows)
+
+__global__ void __launch_bounds__(256)
+k_mask_transpose(const float* __restrict__ mask, float* __restrict__ mask_t, int T) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, k0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const float* src = mask + (int64_t)b * kF * T;
+  float* dst = mask_t + (int64_t)b * T * kMaskPitch;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = k0 + ty + 8 * i, t = t0 + tx;
+    tile[ty + 8 * i][tx] = (k < kF && t < T) ? __ldg(src + (int64_t)k * T + t) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int t = t0 + ty + 8 * i, k = k0 + tx;
+    if (t < T && k < kMaskPitch) dst[(int64_t)t * kMaskPitch + k] = tile[tx][ty + 8 * i];
+  }
+}
+
 // `spec` (optional): the packed two-mic spectrum of every frame is kept for pass B, so that pass B does not repeat
 // the forward transform: [B][T][8][32] float4 = (lo[i].x, lo[i].y, mir[i].x, mir[i].y) of lane l (lane 0's i = 0
 // slot carries (DC, Nyquist): its mirror is itself).  Each store instruction writes 512 contiguous bytes.
 // This trades 64 B/sample of spare HBM bandwidth for ~30 % fewer instructions on an issue-bound path.
 template <int HOP, int WMODE>
 __global__ void __launch_bounds__(kWarps * 32, AVZ_MINB_COV)
-k512_cov(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, const float* __restrict__ mask, int L,
-         int T, int frames_per_cta, float sqrt_eps, float* __restrict__ part, float4* __restrict__ spec, Tables tb) {
+k512_cov(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, const float* __restrict__ mask,
+         MaskLayout ml, int L, int T, int frames_per_cta, float sqrt_eps, float* __restrict__ part,
+         float4* __restrict__ spec, Tables tb) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float2* sm_all = reinterpret_cast<float2*>(smem_raw);
   float2* sm = sm_all + (size_t)(threadIdx.x >> 5) * f512::kSmemComplex;
@@ -408,13 +439,13 @@ k512_cov(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, c
     FrameBits nb;
     float nmask[9];
     const uint32_t* bw = (WMODE == W_BITS) ? ibm_bits + ((int64_t)b * T + ta) * kFW : nullptr;
-    const float* mk = (WMODE == W_MASK) ? mask + (int64_t)b * kF * T + ta : nullptr;
+    const float* mk = (WMODE == W_MASK) ? mask + (int64_t)b * ml.sb + (int64_t)ta * ml.st : nullptr;
     if (WMODE == W_BITS) {
       nb.load(bw, ln.h);
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) nmask[j] = __ldg(mk + (int64_t)bin_lo(ln, j) * T);
-      nmask[8] = __ldg(mk + (int64_t)256 * T);
+      for (int j = 0; j < 8; ++j) nmask[j] = __ldg(mk + (int64_t)bin_lo(ln, j) * ml.sf);
+      nmask[8] = __ldg(mk + (int64_t)256 * ml.sf);
     }
 #pragma unroll 1
     for (int t = ta; t < tb_; ++t) {
@@ -434,10 +465,10 @@ k512_cov(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, c
           bw += kFW;
           nb.load(bw, ln.h);
         } else {
-          mk += 1;
+          mk += ml.st;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) nmask[j] = __ldg(mk + (int64_t)bin_lo(ln, j) * T);
-          nmask[8] = __ldg(mk + (int64_t)256 * T);
+          for (int j = 0; j < 8; ++j) nmask[j] = __ldg(mk + (int64_t)bin_lo(ln, j) * ml.sf);
+          nmask[8] = __ldg(mk + (int64_t)256 * ml.sf);
         }
       }
       float2 v[16];
@@ -545,9 +576,9 @@ __host__ __device__ constexpr size_t apply_smem_bytes() {
 template <int HOP, bool KEPT>
 __global__ void __launch_bounds__(kWarps * 32, KEPT ? AVZ_MINB_APPLY_KEPT : AVZ_MINB_APPLY)
 k512_apply(const float* __restrict__ mix, const float4* __restrict__ spec, const float2* __restrict__ wgt,
-           const uint32_t* __restrict__ ibm_bits, const float* __restrict__ mask, int gain_mode, float post_floor, int L,
-           int T, int blocks_per_cta, float* __restrict__ out, float* __restrict__ peak, unsigned int* __restrict__ done,
-           float peak_eps, Tables tb) {
+           const uint32_t* __restrict__ ibm_bits, const float* __restrict__ mask, MaskLayout ml, int gain_mode,
+           float post_floor, int L, int T, int blocks_per_cta, float* __restrict__ out, float* __restrict__ peak,
+           unsigned int* __restrict__ done, float peak_eps, Tables tb) {
   constexpr int R = kN / HOP;        // frames overlapping one hop-block
   constexpr int NR = HOP / 32;       // rows per hop-block
   constexpr int TAIL = 16 - NR;      // rows still open after a frame's first block is emitted
@@ -686,14 +717,14 @@ k512_apply(const float* __restrict__ mix, const float4* __restrict__ spec, const
     FrameBits nb;
     float nmask[9];
     const uint32_t* bw = ibm_bits + ((int64_t)b * T + t_first) * kFW;
-    const float* mk = mask + (int64_t)b * kF * T + t_first;
+    const float* mk = mask + (int64_t)b * ml.sb + (int64_t)t_first * ml.st;
     auto fetch_gain = [&]() {
       if (gain_mode == GAIN_BITS) {
         nb.load(bw, ln.h);
       } else if (gain_mode != GAIN_NONE) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) nmask[j] = __ldg(mk + (int64_t)bin_lo(ln, j) * T);
-        nmask[8] = __ldg(mk + (int64_t)256 * T);
+        for (int j = 0; j < 8; ++j) nmask[j] = __ldg(mk + (int64_t)bin_lo(ln, j) * ml.sf);
+        nmask[8] = __ldg(mk + (int64_t)256 * ml.sf);
       }
     };
     if (t_first <= T - 1) fetch_gain();
@@ -745,14 +776,14 @@ k512_apply(const float* __restrict__ mix, const float4* __restrict__ spec, const
           }
           if (g + 1 <= T - 1) {
             bw += kFW;
-            mk += 1;
+            mk += ml.st;
             fetch_gain();
           }
         } else {
           if (g + 1 <= T - 1) {
             win.prefetch(m0, m1, L, g + 1, lane);
             bw += kFW;
-            mk += 1;
+            mk += ml.st;
             fetch_gain();
           }
           float2 v[16];
@@ -905,6 +936,26 @@ int64_t ws_bytes512(int B, int T) {
   return (int64_t)(part_bytes(B, cov_chunks512(B, T)) + 16 + (size_t)amb_cap(B, T) * 8);
 }
 
+// kept-spectrum buffer: [B*T frames x 4096 B][per-utterance completion counters, padded to 256 B][transposed mask]
+static size_t spec_mask_offset(int B, int T) {
+  return (size_t)B * T * 4096 + (((size_t)B * sizeof(unsigned int)) + 255) / 256 * 256;
+}
+int64_t spec_ws_bytes512(int B, int T) {
+  return (int64_t)(spec_mask_offset(B, T) + (size_t)B * T * kMaskPitch * sizeof(float));
+}
+// Mask reads of the fused kernels: transposed copy behind the kept spectrum when there is one, else the caller's.
+static const float* stage_mask(const float* mask, const void* spec, int B, int T, MaskLayout* ml, cudaStream_t st) {
+  if (mask == nullptr || spec == nullptr) {
+    *ml = MaskLayout{(int64_t)kF * T, T, 1};
+    return mask;
+  }
+  float* mask_t = reinterpret_cast<float*>(const_cast<unsigned char*>(static_cast<const unsigned char*>(spec)) +
+                                           spec_mask_offset(B, T));
+  k_mask_transpose<<<dim3((T + 31) / 32, (kMaskPitch + 31) / 32, B), 256, 0, st>>>(mask, mask_t, T);
+  *ml = MaskLayout{(int64_t)T * kMaskPitch, 1, kMaskPitch};
+  return mask_t;
+}
+
 static float ibm_tol2() {
   // (relative float32 FFT error bound)^2, relative to the rms bin magnitude of the frame; AVZ_IBM_TOL overrides
   // the bound for experiments.  Measured worst case of this transform: see DESIGN.md.
@@ -950,11 +1001,14 @@ int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const f
   prof_begin(PROF_COV, st);
   if (mask == nullptr) {
     AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov<HOP, W_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
-    k512_cov<HOP, W_BITS><<<grid, kWarps * 32, smem_cov, st>>>(mix, ibm_bits, nullptr, (int)L, T, fpc, 0.f, part,
-                                                               reinterpret_cast<float4*>(spec), tb);
+    k512_cov<HOP, W_BITS><<<grid, kWarps * 32, smem_cov, st>>>(mix, ibm_bits, nullptr, MaskLayout{0, 0, 0}, (int)L, T, fpc,
+                                                               0.f, part, reinterpret_cast<float4*>(spec), tb);
   } else {
     AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov<HOP, W_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
-    k512_cov<HOP, W_MASK><<<grid, kWarps * 32, smem_cov, st>>>(mix, nullptr, mask, (int)L, T, fpc, sqrt_eps, part,
+    MaskLayout ml;
+    const float* mptr = stage_mask(mask, spec, B, T, &ml, st);
+    AVZ_LAUNCH_OK("k_mask_transpose");
+    k512_cov<HOP, W_MASK><<<grid, kWarps * 32, smem_cov, st>>>(mix, nullptr, mptr, ml, (int)L, T, fpc, sqrt_eps, part,
                                                                reinterpret_cast<float4*>(spec), tb);
   }
   prof_end(PROF_COV, st);
@@ -977,6 +1031,9 @@ int launch_apply(const float* mix, const void* spec, const float* w, const uint3
   const int chunks = (n_blocks + bpc - 1) / bpc;
   const size_t smem = (spec != nullptr) ? apply_smem_bytes<HOP, true>() : apply_smem_bytes<HOP, false>();
   dim3 grid(chunks, B);
+  MaskLayout ml;
+  const float* mptr = stage_mask((gain_mode == GAIN_FLOOR || gain_mode == GAIN_MASK) ? mask : nullptr, spec, B, T, &ml, st);
+  AVZ_LAUNCH_OK("k_mask_transpose");
   prof_begin(PROF_APPLY, st);
   if (spec != nullptr) {
     // per-utterance completion counters live behind the kept spectrum (avz_spec_ws_bytes accounts for them)
@@ -989,13 +1046,14 @@ int launch_apply(const float* mix, const void* spec, const float* w, const uint3
     }
     AVZ_CUDA_OK(cudaFuncSetAttribute(k512_apply<HOP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k512_apply<HOP, true><<<grid, kWarps * 32, smem, st>>>(nullptr, reinterpret_cast<const float4*>(spec),
-                                                           reinterpret_cast<const float2*>(w), ibm_bits, mask, gain_mode,
-                                                           post_floor, (int)L, T, bpc, out, peak, done, peak_eps, tb);
+                                                           reinterpret_cast<const float2*>(w), ibm_bits, mptr, ml,
+                                                           gain_mode, post_floor, (int)L, T, bpc, out, peak, done, peak_eps,
+                                                           tb);
   } else {
     AVZ_CUDA_OK(cudaFuncSetAttribute(k512_apply<HOP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k512_apply<HOP, false><<<grid, kWarps * 32, smem, st>>>(mix, nullptr, reinterpret_cast<const float2*>(w), ibm_bits,
-                                                            mask, gain_mode, post_floor, (int)L, T, bpc, out, peak, nullptr,
-                                                            0.f, tb);
+                                                            mptr, ml, gain_mode, post_floor, (int)L, T, bpc, out, peak,
+                                                            nullptr, 0.f, tb);
   }
   prof_end(PROF_APPLY, st);
   AVZ_LAUNCH_OK("k512_apply");
