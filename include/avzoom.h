@@ -165,9 +165,11 @@ AVZ_API int avz_wave_mask_cov_keep_f32(const float* mix, const float* mask, int 
 AVZ_API int avz_mvdr_apply_kept_f32(const void* spec, const float* w, const uint32_t* ibm_bits, const float* mask, int B,
                             int64_t L, int n_fft, int hop, const AvzMvdrCfg* cfg, float* out, float* peak, void* stream);
 
-/* Same as avz_mvdr_apply_kept_f32 plus the peak normalisation of oracle_debug.py:94 fused in: the thread block that
- * finishes an utterance last divides it by (peak[b] + peak_eps) in place while it is still in L2 (no second kernel,
- * no second trip to HBM).  Bit-identical to apply followed by avz_peak_normalise_f32.  peak [B] zeroed by the caller. */
+/* Same as avz_mvdr_apply_kept_f32 plus the peak normalisation of oracle_debug.py:94 fused in: the thread blocks of an
+ * utterance run as one cluster, agree on max|x| through distributed shared memory and divide their own output range
+ * by (peak + peak_eps) while it is still in L2 (more than 8 blocks per utterance: a separate pass follows instead).
+ * Bit-identical to apply followed by avz_peak_normalise_f32; slower than that pair at the BASELINE shapes
+ * (profiles/README.md), offered for callers that want one launch.  peak [B] zeroed by the caller. */
 AVZ_API int avz_mvdr_apply_kept_norm_f32(const void* spec, const float* w, const uint32_t* ibm_bits, const float* mask, int B,
                                  int64_t L, int n_fft, int hop, const AvzMvdrCfg* cfg, float peak_eps, float* out,
                                  float* peak, void* stream);

@@ -14,12 +14,15 @@
 #include <cstdlib>
 
 #include "avz_common.cuh"
+#include <cooperative_groups.h>
+
 #include "avz_fft512.cuh"
 
 namespace avz {
 namespace o512 {
 
 using f512::Lane;
+namespace cg = cooperative_groups;
 
 constexpr int kN = 512;
 constexpr int kF = 257;
@@ -578,7 +581,7 @@ __global__ void __launch_bounds__(kWarps * 32, KEPT ? AVZ_MINB_APPLY_KEPT : AVZ_
 k512_apply(const float* __restrict__ mix, const float4* __restrict__ spec, const float2* __restrict__ wgt,
            const uint32_t* __restrict__ ibm_bits, const float* __restrict__ mask, MaskLayout ml, int gain_mode,
            float post_floor, int L, int T, int blocks_per_cta, float* __restrict__ out, float* __restrict__ peak,
-           unsigned int* __restrict__ done, float peak_eps, Tables tb) {
+           int cluster_norm, float peak_eps, Tables tb) {
   constexpr int R = kN / HOP;        // frames overlapping one hop-block
   constexpr int NR = HOP / 32;       // rows per hop-block
   constexpr int TAIL = 16 - NR;      // rows still open after a frame's first block is emitted
@@ -866,32 +869,40 @@ k512_apply(const float* __restrict__ mix, const float4* __restrict__ spec, const
     my_peak = warp_max(my_peak);
     if (lane == 0) s_peak[warp] = my_peak;
     __syncthreads();
-    if (threadIdx.x == 0) {
-      float m = 0.f;
-      for (int i = 0; i < kWarps; ++i) m = fmaxf(m, s_peak[i]);
-      atomicMax(reinterpret_cast<unsigned int*>(peak + b), __float_as_uint(m));
-    }
-    // Fused peak normalisation (oracle_debug.py:94): the CTA that finishes an utterance last rescales it in place
-    // while its samples are still in L2 - no extra kernel, no second trip to HBM.
-    if (done != nullptr) {
-      __shared__ int s_last;
-      __threadfence();                 // this thread's output stores are visible device-wide ...
-      __syncthreads();
-      if (threadIdx.x == 0) {          // ... before the CTA signals completion (the atomicMax above precedes it too)
-        __threadfence();
-        s_last = (atomicAdd(done + b, 1u) == gridDim.x - 1);
+    float m = 0.f;
+#pragma unroll
+    for (int i = 0; i < kWarps; ++i) m = fmaxf(m, s_peak[i]);
+    if (!cluster_norm) {
+      if (threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned int*>(peak + b), __float_as_uint(m));
+    } else {
+      // Fused peak normalisation (oracle_debug.py:94).  The CTAs of one utterance form a thread-block cluster: they
+      // exchange their maxima through distributed shared memory, then every CTA divides the range it has just written
+      // (still in L2) - no extra kernel and no second trip of the output to HBM.
+      __shared__ float s_cta_peak;
+      if (threadIdx.x == 0) s_cta_peak = m;
+      cg::cluster_group cl = cg::this_cluster();
+      cl.sync();   // every CTA of the utterance has stored its blocks and published its maximum
+      float um = 0.f;
+      for (unsigned r = 0; r < cl.num_blocks(); ++r) um = fmaxf(um, *cl.map_shared_rank(&s_cta_peak, r));
+      cl.sync();   // nobody leaves (and frees its shared memory) while a peer may still be reading it
+      if (cl.block_rank() == 0 && threadIdx.x == 0) peak[b] = um;
+      const float den = um + peak_eps;
+      float4* o4 = reinterpret_cast<float4*>(ob + (int64_t)(G0 - g_lo) * HOP);
+      const int n4 = nblk * (HOP / 4);
+      constexpr int kStep = kWarps * 32;
+      int i = threadIdx.x;
+      for (; i + 3 * kStep < n4; i += 4 * kStep) {   // four loads in flight per thread: the pass is L2 latency
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldcg(o4 + i + u * kStep);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          o4[i + u * kStep] = make_float4(__fdiv_rn(v[u].x, den), __fdiv_rn(v[u].y, den), __fdiv_rn(v[u].z, den),
+                                          __fdiv_rn(v[u].w, den));
       }
-      __syncthreads();
-      if (s_last) {
-        __threadfence();
-        const float den = __ldcg(peak + b) + peak_eps;
-        float4* o4 = reinterpret_cast<float4*>(ob);
-        const int n4 = (int)(out_len >> 2);   // out_len = (T-1) * HOP, a multiple of 128
-        for (int i = threadIdx.x; i < n4; i += kWarps * 32) {
-          float4 v = __ldcg(o4 + i);
-          v = make_float4(__fdiv_rn(v.x, den), __fdiv_rn(v.y, den), __fdiv_rn(v.z, den), __fdiv_rn(v.w, den));
-          o4[i] = v;
-        }
+      for (; i < n4; i += kStep) {
+        const float4 v = __ldcg(o4 + i);
+        o4[i] = make_float4(__fdiv_rn(v.x, den), __fdiv_rn(v.y, den), __fdiv_rn(v.z, den), __fdiv_rn(v.w, den));
       }
     }
   }
@@ -1036,24 +1047,34 @@ int launch_apply(const float* mix, const void* spec, const float* w, const uint3
   AVZ_LAUNCH_OK("k_mask_transpose");
   prof_begin(PROF_APPLY, st);
   if (spec != nullptr) {
-    // per-utterance completion counters live behind the kept spectrum (avz_spec_ws_bytes accounts for them)
-    unsigned int* done = nullptr;
-    if (fuse_norm) {
-      if (peak == nullptr) return set_error(AVZ_EINVAL, "fused normalisation needs the peak buffer");
-      done = reinterpret_cast<unsigned int*>(const_cast<unsigned char*>(static_cast<const unsigned char*>(spec)) +
-                                             (size_t)B * T * 4096);
-      AVZ_CUDA_OK(cudaMemsetAsync(done, 0, (size_t)B * sizeof(unsigned int), st));
-    }
     AVZ_CUDA_OK(cudaFuncSetAttribute(k512_apply<HOP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k512_apply<HOP, true><<<grid, kWarps * 32, smem, st>>>(nullptr, reinterpret_cast<const float4*>(spec),
-                                                           reinterpret_cast<const float2*>(w), ibm_bits, mptr, ml,
-                                                           gain_mode, post_floor, (int)L, T, bpc, out, peak, done, peak_eps,
-                                                           tb);
+    // fused normalisation: the CTAs of an utterance run as one thread-block cluster (portable size limit 8)
+    const int cluster_norm = (fuse_norm && peak != nullptr && chunks <= 8) ? 1 : 0;
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = grid;
+    lc.blockDim = dim3(kWarps * 32);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cluster_norm ? chunks : 1;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    lc.attrs = at;
+    lc.numAttrs = 1;
+    AVZ_CUDA_OK(cudaLaunchKernelEx(&lc, k512_apply<HOP, true>, (const float*)nullptr, reinterpret_cast<const float4*>(spec),
+                                   reinterpret_cast<const float2*>(w), ibm_bits, mptr, ml, gain_mode, post_floor, (int)L, T,
+                                   bpc, out, peak, cluster_norm, peak_eps, tb));
+    if (fuse_norm && !cluster_norm) {   // too many chunks per utterance for a cluster: separate pass
+      prof_end(PROF_APPLY, st);
+      AVZ_LAUNCH_OK("k512_apply");
+      return avz_peak_normalise_f32(out, B, (int64_t)(T - 1) * HOP, peak, peak_eps, st);
+    }
   } else {
     AVZ_CUDA_OK(cudaFuncSetAttribute(k512_apply<HOP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k512_apply<HOP, false><<<grid, kWarps * 32, smem, st>>>(mix, nullptr, reinterpret_cast<const float2*>(w), ibm_bits,
                                                             mptr, ml, gain_mode, post_floor, (int)L, T, bpc, out, peak,
-                                                            nullptr, 0.f, tb);
+                                                            0, 0.f, tb);
   }
   prof_end(PROF_APPLY, st);
   AVZ_LAUNCH_OK("k512_apply");

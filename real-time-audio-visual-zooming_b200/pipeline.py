@@ -44,9 +44,10 @@ class OracleMvdr:
         # pass A may keep the packed mix spectrum so that pass B skips its forward transform (fast path only)
         nspec = self.lib.avz_spec_ws_bytes(B, L, cfg.n_fft, cfg.hop) if keep_spectrum else 0
         self.spec = torch.empty((int(nspec),), dtype=torch.uint8, device=device) if nspec > 0 else None
-        # fused_norm: the last thread block of an utterance rescales it in L2 (one launch and one HBM round trip less).
-        # Measured on B200 at config 2 it LOSES (pass B 0.54 -> 0.76 ms vs 0.09 ms for the separate streaming kernel):
-        # a single 4-warp block rescaling 256 KB is latency-bound and lengthens the tail.  Kept as an option, off.
+        # fused_norm: the thread blocks of an utterance run as one cluster, exchange their maxima through distributed
+        # shared memory and each rescales the range it has just written while it is still in L2 (one launch less,
+        # bit-identical output).  Measured on B200 at config 2 it LOSES: pass B 0.50 -> 0.68 ms against the 0.09 ms of
+        # the separate streaming kernel (L2 round trips at the end of every block + cluster co-scheduling).  Off.
         self.fused_norm = fused_norm and cfg.peak_eps is not None and self.spec is not None
         self.launches_per_step = 6 if self.fused_norm else 7
         self.d = steering_vectors(cfg, device)
@@ -74,7 +75,7 @@ class OracleMvdr:
         self.peak.zero_()
         bits = self.bits if c.post == "one_minus_noise" else None
         if self.spec is not None and self.fused_norm:
-            # peak normalisation fused into pass B: the last thread block of an utterance rescales it in L2
+            # peak normalisation fused into pass B (thread-block cluster per utterance)
             _lib.check(self.lib.avz_mvdr_apply_kept_norm_f32(_ptr(self.spec), _ptr(self.w), _ptr(bits), _ptr(None),
                                                              self.B, self.L, c.n_fft, c.hop, C.byref(self.cc),
                                                              float(c.peak_eps), _ptr(self.out), _ptr(self.peak),
