@@ -234,6 +234,41 @@ def test_learned_mask_path_golden(az, golden_dir):
     assert rel_l2(out[0], lc["chunk0_out"]) < WAVE_TOL
 
 
+@pytest.mark.parametrize("preset,hop", [("baseline_learned", 128), ("baseline_learned", 256), ("tf_lite", 128)])
+def test_learned_mask_fast_path_512(az, preset, hop):
+    """Learned-mask MVDR on the n_fft 512 fast path (BASELINE config 3 shape): random target-probability masks,
+    ragged length, against the float64 oracle; the kept-spectrum variant (mask re-laid (B,T,264) behind the spectrum)
+    and the recomputing variant (mask read in the reference layout) give bit-identical waveforms."""
+    import dataclasses
+    from avzoom import ops
+    cfg = dataclasses.replace(az.PRESETS[preset], n_fft=512, hop=hop)
+    mix, _, _ = synth(3, 3, 1.27, 3)                       # L = 20320: not a multiple of the hop
+    B, L = mix.shape[0], mix.shape[-1]
+    T = O.n_frames(L, 512, hop)
+    rng = np.random.default_rng(hop)
+    mask = rng.random((B, 257, T)).astype(np.float32)
+    mask[0, 7, :] = 1.0                                     # empty noise weight in one bin
+    mask[1, :, 5] = 0.0
+    out = az.learned_mask_mvdr(mix, mask, cfg)
+    assert out.shape == (B, (T - 1) * hop)
+    ocfg = to_oracle_cfg(cfg)
+    for b in range(B):
+        ref = O.learned_mask_mvdr_chunk(mix[b].T.astype(np.float64), lambda X: mask[b], ocfg)
+        ref = O.peak_normalise(ref, ocfg.peak_eps)
+        assert rel_l2(out[b], ref) < WAVE_TOL
+    # kept spectrum (transposed mask) == recompute (reference mask layout), bit for bit
+    mix_d, mask_d = torch.from_numpy(mix).cuda(), torch.from_numpy(mask).cuda()
+    res = []
+    for keep in (True, False):
+        spec = ops.alloc_kept_spectrum(mix_d, cfg) if keep else None
+        Rp, _ = ops.wave_masked_covariance(mix_d, mask_d, cfg, spec)
+        w = ops.mvdr_weights(Rp, ops.steering_vectors(cfg, mix_d.device), cfg)
+        o, pk = ops.mvdr_apply(mix_d, w, cfg, mask=mask_d if cfg.post in ("floor", "mask") else None, spec=spec)
+        res.append((Rp.clone(), o.clone(), pk.clone()))
+    assert res[0][0].shape == res[1][0].shape and torch.equal(res[0][0], res[1][0])
+    assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+
+
 def test_geometric_mask_mvdr_pieces(az, golden_dir):
     """masked_mvdr.main's arithmetic (masked_mvdr.py:76-128) assembled from the public ops."""
     g = np.load(os.path.join(golden_dir, "ref_speech_excerpt.npz"))
