@@ -86,7 +86,32 @@ bool split_length(int64_t L, int* N1, int* log2N1, int* N2) {
   return true;
 }
 
-__device__ __forceinline__ int bitrev(int x, int bits) { return bits ? (int)(__brev((unsigned)x) >> (32 - bits)) : 0; }
+// The power-of-two passes run radix-4 stages (quarter sizes N1/4, N1/16, ...) plus one radix-2 stage when log2 N1 is
+// odd, in place: decimation in frequency leaves bin k at the position whose base-4 digits (and last bit) are k's in
+// reverse order; the inverse places bin k there and runs the stages backwards (decimation in time).
+__device__ __forceinline__ int pos_to_bin(int pos, int N1) {
+  int k = 0, mult = 1, rem = N1, p = pos;
+  while (rem >= 4) {
+    const int q = rem >> 2, d = p / q;
+    p -= d * q;
+    k += d * mult;
+    mult <<= 2;
+    rem = q;
+  }
+  if (rem == 2) k += p * mult;
+  return k;
+}
+__device__ __forceinline__ int bin_to_pos(int k, int N1) {
+  int pos = 0, rem = N1;
+  while (rem >= 4) {
+    const int q = rem >> 2;
+    pos += (k & 3) * q;
+    k >>= 2;
+    rem = q;
+  }
+  if (rem == 2) pos += k & 1;
+  return pos;
+}
 
 // ---- pass 1: pack two sources, power-of-two DIF over n1, twiddle W_L^{n2 k1}; A[b][p][k1][n2] ----
 __global__ void __launch_bounds__(kColThreads)
@@ -110,17 +135,33 @@ k_mix_cols_fwd(const float* __restrict__ src, float2* __restrict__ A, const floa
     sm[idx] = z;
   }
   __syncthreads();
-  for (int h = N1 >> 1; h >= 1; h >>= 1) {
-    const int64_t tstep = (int64_t)N2 * (N1 / (2 * h));  // W_{2h}^{pos} = W_L[pos * L / (2h)]
+  int rem = N1;
+  for (; rem >= 4; rem >>= 2) {   // radix-4 DIF stage on blocks of `rem`
+    const int q = rem >> 2;
+    const int64_t tstep = (int64_t)N2 * (N1 / rem);  // W_rem^j = W_L[j * L / rem]
+    for (int idx = threadIdx.x; idx < (N1 / 4) * kCols; idx += kColThreads) {
+      const int c = idx & (kCols - 1), j = idx / kCols;
+      const int pos = j & (q - 1);
+      const int i0 = ((j - pos) << 2) + pos;
+      float2* x = sm + i0 * kCols + c;
+      const float2 a0 = x[0], a1 = x[q * kCols], a2 = x[2 * q * kCols], a3 = x[3 * q * kCols];
+      const float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3);
+      const float2 d = csub(a1, a3);
+      const float2 t3 = make_float2(d.y, -d.x);   // * (-i)
+      x[0] = cadd(t0, t2);
+      x[q * kCols] = cmul(cadd(t1, t3), __ldg(W + pos * tstep));
+      x[2 * q * kCols] = cmul(csub(t0, t2), __ldg(W + 2 * pos * tstep));
+      x[3 * q * kCols] = cmul(csub(t1, t3), __ldg(W + 3 * pos * tstep));
+    }
+    __syncthreads();
+  }
+  if (rem == 2) {
     for (int idx = threadIdx.x; idx < (N1 / 2) * kCols; idx += kColThreads) {
       const int c = idx & (kCols - 1), j = idx / kCols;
-      const int pos = j & (h - 1);
-      const int i0 = ((j - pos) << 1) + pos;
-      const float2 a = sm[i0 * kCols + c];
-      const float2 bb = sm[(i0 + h) * kCols + c];
-      const float2 w = __ldg(W + pos * tstep);
-      sm[i0 * kCols + c] = cadd(a, bb);
-      sm[(i0 + h) * kCols + c] = cmul(csub(a, bb), w);
+      float2* x = sm + 2 * j * kCols + c;
+      const float2 a = x[0], bb = x[kCols];
+      x[0] = cadd(a, bb);
+      x[kCols] = csub(a, bb);
     }
     __syncthreads();
   }
@@ -128,7 +169,7 @@ k_mix_cols_fwd(const float* __restrict__ src, float2* __restrict__ A, const floa
   for (int idx = threadIdx.x; idx < N1 * kCols; idx += kColThreads) {
     const int c = idx & (kCols - 1), pos = idx / kCols;
     if (c < ncol) {
-      const int k1 = bitrev(pos, log2N1);
+      const int k1 = pos_to_bin(pos, N1);
       const int n2 = c0 + c;
       out[(int64_t)k1 * N2 + n2] = cmul(sm[idx], __ldg(W + (int64_t)n2 * k1));
     }
@@ -282,19 +323,40 @@ k_mix_cols_inv(const float2* __restrict__ Q, const float2* __restrict__ W, float
       const int n2 = c0 + c;
       z = cmulc(in[(int64_t)k1 * N2 + n2], __ldg(W + (int64_t)n2 * k1));
     }
-    sm[bitrev(k1, log2N1) * kCols + c] = z;
+    sm[bin_to_pos(k1, N1) * kCols + c] = z;
   }
   __syncthreads();
-  for (int h = 1; h < N1; h <<= 1) {
-    const int64_t tstep = (int64_t)N2 * (N1 / (2 * h));
+  int rem = (log2N1 & 1) ? 2 : 4;
+  if (rem == 2 && N1 >= 2) {
     for (int idx = threadIdx.x; idx < (N1 / 2) * kCols; idx += kColThreads) {
       const int c = idx & (kCols - 1), j = idx / kCols;
-      const int pos = j & (h - 1);
-      const int i0 = ((j - pos) << 1) + pos;
-      const float2 a = sm[i0 * kCols + c];
-      const float2 bb = cmulc(sm[(i0 + h) * kCols + c], __ldg(W + pos * tstep));
-      sm[i0 * kCols + c] = cadd(a, bb);
-      sm[(i0 + h) * kCols + c] = csub(a, bb);
+      float2* x = sm + 2 * j * kCols + c;
+      const float2 a = x[0], bb = x[kCols];
+      x[0] = cadd(a, bb);
+      x[kCols] = csub(a, bb);
+    }
+    __syncthreads();
+    rem = 8;
+  }
+  for (; rem <= N1; rem <<= 2) {   // radix-4 DIT stage on blocks of `rem`
+    const int q = rem >> 2;
+    const int64_t tstep = (int64_t)N2 * (N1 / rem);
+    for (int idx = threadIdx.x; idx < (N1 / 4) * kCols; idx += kColThreads) {
+      const int c = idx & (kCols - 1), j = idx / kCols;
+      const int pos = j & (q - 1);
+      const int i0 = ((j - pos) << 2) + pos;
+      float2* x = sm + i0 * kCols + c;
+      const float2 b0 = x[0];
+      const float2 b1 = cmulc(x[q * kCols], __ldg(W + pos * tstep));
+      const float2 b2 = cmulc(x[2 * q * kCols], __ldg(W + 2 * pos * tstep));
+      const float2 b3 = cmulc(x[3 * q * kCols], __ldg(W + 3 * pos * tstep));
+      const float2 t0 = cadd(b0, b2), t1 = csub(b0, b2), t2 = cadd(b1, b3);
+      const float2 d = csub(b1, b3);
+      const float2 t3 = make_float2(-d.y, d.x);   // * (+i)
+      x[0] = cadd(t0, t2);
+      x[q * kCols] = cadd(t1, t3);
+      x[2 * q * kCols] = csub(t0, t2);
+      x[3 * q * kCols] = csub(t1, t3);
     }
     __syncthreads();
   }
@@ -325,10 +387,23 @@ k_mix_cols_inv(const float2* __restrict__ Q, const float2* __restrict__ W, float
 }
 
 // ---- pass 6: divide mix / tgt / itf by max|mix| + eps (world_building.py:86-91) ----
-__global__ void k_mix_scale(float* __restrict__ mix, float* __restrict__ tgt, float* __restrict__ itf,
-                            const unsigned* __restrict__ peak_bits, float peak_eps, int64_t N) {
+__global__ void __launch_bounds__(256)
+k_mix_scale(float* __restrict__ mix, float* __restrict__ tgt, float* __restrict__ itf,
+            const unsigned* __restrict__ peak_bits, float peak_eps, int64_t N) {
   const int b = blockIdx.y;
   const float den = __uint_as_float(peak_bits[b]) + peak_eps;
+  // the four signals of an utterance, float4 at a time when N allows it (each signal then starts 16-byte aligned)
+  if ((N & 3) == 0) {
+    const int64_t n4 = N >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 4 * n4; i += (int64_t)gridDim.x * blockDim.x) {
+      float4* p = i < 2 * n4 ? reinterpret_cast<float4*>(mix + (int64_t)b * 2 * N) + i
+                             : (i < 3 * n4 ? reinterpret_cast<float4*>(tgt + (int64_t)b * N) + (i - 2 * n4)
+                                           : reinterpret_cast<float4*>(itf + (int64_t)b * N) + (i - 3 * n4));
+      const float4 v = __ldcs(p);
+      *p = make_float4(__fdiv_rn(v.x, den), __fdiv_rn(v.y, den), __fdiv_rn(v.z, den), __fdiv_rn(v.w, den));
+    }
+    return;
+  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 4 * N; i += (int64_t)gridDim.x * blockDim.x) {
     float* p = i < 2 * N ? mix + (int64_t)b * 2 * N + i : (i < 3 * N ? tgt + (int64_t)b * N + (i - 2 * N)
                                                                       : itf + (int64_t)b * N + (i - 3 * N));

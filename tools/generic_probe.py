@@ -1,0 +1,35 @@
+"""Timing of the generic (n_fft 1024 / hop 512) kernels the reference's learned pipelines use: 512 windows of 2 s.
+python tools/generic_probe.py"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+import avzoom  # noqa: E402
+from avzoom import synth  # noqa: E402
+
+B, L = 512, 32000
+cfg = avzoom.PRESETS["full_audio"]
+mix8, _, _ = synth.make_batch(3, 8, 2.0, 3)
+mix = torch.from_numpy(mix8).cuda().repeat(B // 8, 1, 1).contiguous()
+T = avzoom.num_frames(L, cfg.n_fft, cfg.hop)
+mask = torch.rand((B, cfg.n_freq, T), device="cuda")
+
+
+def timed(fn, iters=5):
+    fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+t_feat = timed(lambda: avzoom.wave_features(mix, cfg.n_fft, cfg.hop))
+t_mvdr = timed(lambda: avzoom.learned_mask_mvdr(mix, mask, cfg))
+audio_s = B * L / 16000.0
+print(f"1024/512 generic path, {B} x 2 s: features {t_feat:.3f} ms, learned-mask MVDR {t_mvdr:.3f} ms "
+      f"-> {audio_s / ((t_feat + t_mvdr) * 1e-3) / 1e6:.3f} M audio-s/s")

@@ -1,4 +1,4 @@
-"""numpy model of csrc/avz_mixer.cu's index algebra (two-factor FFT, DIF/DIT bit reversal, packed Hermitian
+"""numpy model of csrc/avz_mixer.cu's index algebra (two-factor FFT, radix-4 DIF/DIT digit reversal, packed Hermitian
 combine), checked against the float64 oracle mixer.  Design aid, CPU only:  python tools/mixer_model.py
 """
 import os
@@ -18,30 +18,66 @@ def split_length(L, max_n1=512):
     return n1, lg, L // n1
 
 
-def bitrev(x, bits):
-    r = 0
-    for i in range(bits):
-        r |= ((x >> i) & 1) << (bits - 1 - i)
-    return r
+def stages(N1):
+    """Radix-4 stages (quarter sizes N1/4, N1/16, ...) plus one radix-2 stage when log2 N1 is odd."""
+    st, rem = [], N1
+    while rem >= 4:
+        st.append(("r4", rem // 4))
+        rem //= 4
+    if rem == 2:
+        st.append(("r2", 1))
+    return st
+
+
+def pos_to_bin(pos, N1):
+    k, mult, rem, p = 0, 1, N1, pos
+    while rem >= 4:
+        q = rem // 4
+        d = p // q
+        p -= d * q
+        k += d * mult
+        mult *= 4
+        rem = q
+    if rem == 2:
+        k += p * mult
+    return k
+
+
+def bin_to_pos(k, N1):
+    pos, rem = 0, N1
+    while rem >= 4:
+        q = rem // 4
+        pos += (k & 3) * q
+        k >>= 2
+        rem = q
+    if rem == 2:
+        pos += k & 1
+    return pos
 
 
 def cols_fwd(z, W, N1, lg, N2):
-    """z (N,) complex natural order -> A [k1][n2] after DIF over n1 and the W_L^{n2 k1} twiddle."""
+    """z (N,) complex natural order -> A [k1][n2] after the in-place DIF over n1 and the W_L^{n2 k1} twiddle."""
     sm = z.reshape(N1, N2).copy()  # [n1][n2]
-    h = N1 >> 1
-    while h >= 1:
-        tstep = N2 * (N1 // (2 * h))
-        for j in range(N1 // 2):
-            pos = j & (h - 1)
-            i0 = ((j - pos) << 1) + pos
-            a, b = sm[i0].copy(), sm[i0 + h].copy()
-            sm[i0] = a + b
-            sm[i0 + h] = (a - b) * W[pos * tstep]
-        h >>= 1
+    for kind, q in stages(N1):
+        if kind == "r4":
+            ts = N2 * (N1 // (4 * q))
+            for g in range(0, N1, 4 * q):
+                for pos in range(q):
+                    i = g + pos
+                    a0, a1, a2, a3 = sm[i].copy(), sm[i + q].copy(), sm[i + 2 * q].copy(), sm[i + 3 * q].copy()
+                    t0, t1, t2, t3 = a0 + a2, a0 - a2, a1 + a3, (a1 - a3) * (-1j)
+                    sm[i] = t0 + t2
+                    sm[i + q] = (t1 + t3) * W[pos * ts]
+                    sm[i + 2 * q] = (t0 - t2) * W[2 * pos * ts]
+                    sm[i + 3 * q] = (t1 - t3) * W[3 * pos * ts]
+        else:
+            for i in range(0, N1, 2):
+                a, b = sm[i].copy(), sm[i + 1].copy()
+                sm[i], sm[i + 1] = a + b, a - b
     A = np.zeros((N1, N2), complex)
     n2 = np.arange(N2)
     for pos in range(N1):
-        k1 = bitrev(pos, lg)
+        k1 = pos_to_bin(pos, N1)
         A[k1] = sm[pos] * W[n2 * k1]
     return A
 
@@ -71,18 +107,23 @@ def cols_inv(Q, W, N1, lg, N2):
     sm = np.zeros((N1, N2), complex)
     n2 = np.arange(N2)
     for k1 in range(N1):
-        sm[bitrev(k1, lg)] = Q[k1] * W[n2 * k1].conj()
-    h = 1
-    while h < N1:
-        tstep = N2 * (N1 // (2 * h))
-        for j in range(N1 // 2):
-            pos = j & (h - 1)
-            i0 = ((j - pos) << 1) + pos
-            a = sm[i0].copy()
-            b = sm[i0 + h] * W[pos * tstep].conj()
-            sm[i0] = a + b
-            sm[i0 + h] = a - b
-        h <<= 1
+        sm[bin_to_pos(k1, N1)] = Q[k1] * W[n2 * k1].conj()
+    for kind, q in reversed(stages(N1)):
+        if kind == "r2":
+            for i in range(0, N1, 2):
+                a, b = sm[i].copy(), sm[i + 1].copy()
+                sm[i], sm[i + 1] = a + b, a - b
+        else:
+            ts = N2 * (N1 // (4 * q))
+            for g in range(0, N1, 4 * q):
+                for pos in range(q):
+                    i = g + pos
+                    b0 = sm[i].copy()
+                    b1 = sm[i + q] * W[pos * ts].conj()
+                    b2 = sm[i + 2 * q] * W[2 * pos * ts].conj()
+                    b3 = sm[i + 3 * q] * W[3 * pos * ts].conj()
+                    t0, t1, t2, t3 = b0 + b2, b0 - b2, b1 + b3, (b1 - b3) * 1j
+                    sm[i], sm[i + q], sm[i + 2 * q], sm[i + 3 * q] = t0 + t2, t1 + t3, t0 - t2, t1 - t3
     return sm.reshape(-1) / (N1 * N2)
 
 
