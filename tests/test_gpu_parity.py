@@ -203,6 +203,15 @@ def test_oracle_path_hop256_and_ragged(az):
     _check_oracle_path(az, mix, tgt, itf, az.PRESETS["baseline_oracle"])
 
 
+def test_oracle_path_long_utterances(az):
+    """Two 25 s utterances (T = 3126 frames, ~100 frame chunks per utterance: the chunking, warm-up and hand-off logic
+    of both passes at a very different shape from the 4 s benchmark batch), plus a batch of one."""
+    cfg = az.PRESETS["baseline_oracle"]
+    mix, tgt, itf = synth(1, 2, 25.0, 2)
+    _check_oracle_path(az, mix, tgt, itf, cfg)
+    _check_oracle_path(az, mix[:1, :, :70001], tgt[:1, :70001], itf[:1, :70001], cfg)
+
+
 def test_oracle_path_real_speech_golden(az, golden_dir):
     """The reference's oracle_debug.main() run unmodified on a real-speech excerpt (tests/golden)."""
     g = np.load(os.path.join(golden_dir, "ref_speech_excerpt.npz"))
