@@ -397,7 +397,14 @@ def alloc_kept_spectrum(mix: torch.Tensor, cfg: MvdrConfig) -> Optional[torch.Te
     """Workspace in which pass A keeps the packed mix spectrum for pass B (fast path shapes only, else None)."""
     B, _, L = mix.shape
     n = _lib.load().avz_spec_ws_bytes(B, L, cfg.n_fft, cfg.hop)
-    return torch.empty((int(n),), dtype=torch.uint8, device=mix.device) if n > 0 else None
+    if n <= 0:
+        return None
+    # ~34 bytes per input sample: only worth it while it fits comfortably; otherwise pass B recomputes the transform
+    # (bit-identical result, ~8 % slower), so huge batches degrade gracefully instead of running out of memory.
+    free, _ = torch.cuda.mem_get_info(mix.device)
+    if n > free // 2:
+        return None
+    return torch.empty((int(n),), dtype=torch.uint8, device=mix.device)
 
 
 def ibm_covariance(mix: torch.Tensor, tgt: torch.Tensor, itf: torch.Tensor, cfg: MvdrConfig,
