@@ -328,6 +328,35 @@ def test_engine_kept_spectrum_equals_recompute(az, preset, B, dur):
     assert rel_l2(a[0].cpu().numpy(), ref) < WAVE_TOL
 
 
+def test_streamed_engine_equals_single_engine(az):
+    """StreamedOracleMvdr (consecutive batches on alternating CUDA streams / workspaces) returns, for every batch,
+    exactly what one OracleMvdr returns; results stay valid until `depth` further submits."""
+    from avzoom import pipeline
+    cfg = az.PRESETS["baseline_oracle"]
+    batches = []
+    for i in range(5):
+        mix, tgt, itf = synth(2, 6, 0.9, 3, start=10 * i)
+        batches.append(tuple(torch.from_numpy(a).cuda() for a in (mix, tgt, itf)))
+    L = batches[0][0].shape[-1]
+    single = pipeline.OracleMvdr(cfg, 6, L, batches[0][0].device)
+    want = [single.run(*b).clone() for b in batches]
+    loop = pipeline.StreamedOracleMvdr(cfg, 6, L, batches[0][0].device, depth=2)
+    got = []
+    for k, b in enumerate(batches):
+        out = loop.submit(*b)
+        if k >= 1:                       # the previous result is still intact while this one is being computed
+            loop.join()
+            got.append(prev.clone())
+        prev = out
+    loop.join()
+    got.append(prev.clone())
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        pipeline.StreamedOracleMvdr(cfg, 6, L, batches[0][0].device, depth=0)
+
+
 def test_ibm_bit_exact_at_scale(az):
     """IBM of the fused float32 path (near ties re-decided in float64) against the all-float64 GPU reference over
     ~16 M bins, the latter pinned to the CPU oracle on one utterance; plus degenerate inputs (identical references:
