@@ -304,7 +304,8 @@ k512_ibm_fixup(const float* __restrict__ tgt, const float* __restrict__ itf, int
   const unsigned int n = *amb_list.count;
   const bool overflow = n > amb_list.cap;
   const unsigned long long total = overflow ? (unsigned long long)B * T * kF : n;
-  double xt[16], xi[16];
+  float xt[16], xi[16];   // raw samples of the cached frame (float: half the registers of the windowed doubles, so
+                          // twice the warps per SM for a kernel that is one latency chain per entry)
   int cur_b = -1, cur_t = -1;
   for (unsigned long long i0 = gw * kFixBlock; i0 < total; i0 += nw * kFixBlock) {
     const unsigned long long i1 = (i0 + kFixBlock < total) ? i0 + kFixBlock : total;
@@ -331,9 +332,8 @@ k512_ibm_fixup(const float* __restrict__ tgt, const float* __restrict__ itf, int
           const int nn = lane + 32 * r;
           const int64_t idx = start + nn;
           const bool ok = idx >= 0 && idx < L;
-          const double w = tb.win_d[nn];
-          xt[r] = ok ? w * (double)__ldg(tg + idx) : 0.0;
-          xi[r] = ok ? w * (double)__ldg(it + idx) : 0.0;
+          xt[r] = ok ? __ldg(tg + idx) : 0.f;
+          xi[r] = ok ? __ldg(it + idx) : 0.f;
         }
       }
       // exp(-2 pi i (lane + 32 r) k / N) = base * step^r: one gathered and one broadcast table load per entry instead
@@ -344,10 +344,12 @@ k512_ibm_fixup(const float* __restrict__ tgt, const float* __restrict__ itf, int
       double tr = 0, ti = 0, ir = 0, ii = 0;
 #pragma unroll
       for (int r = 0; r < 16; ++r) {
-        tr = fma(xt[r], e.x, tr);
-        ti = fma(xt[r], e.y, ti);
-        ir = fma(xi[r], e.x, ir);
-        ii = fma(xi[r], e.y, ii);
+        const double w = tb.win_d[lane + 32 * r];
+        const double at = w * (double)xt[r], ai = w * (double)xi[r];
+        tr = fma(at, e.x, tr);
+        ti = fma(at, e.y, ti);
+        ir = fma(ai, e.x, ir);
+        ii = fma(ai, e.y, ii);
         const double nx = fma(e.x, stp.x, -e.y * stp.y), ny = fma(e.x, stp.y, e.y * stp.x);
         e = make_double2(nx, ny);
       }
