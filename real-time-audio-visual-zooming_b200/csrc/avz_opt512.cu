@@ -35,6 +35,9 @@ constexpr int kWarps = 4;    // warps per CTA
 #ifndef AVZ_APPLY_FULLTW
 #define AVZ_APPLY_FULLTW 0   // k512_apply<KEPT>: unfactored twiddles in the inverse transform (needs AVZ_MINB_APPLY_KEPT 2)
 #endif
+#ifndef AVZ_MINB_STREAM
+#define AVZ_MINB_STREAM 4
+#endif
 #ifndef AVZ_COV_FULLTW
 #define AVZ_COV_FULLTW 1     // k512_cov: 15 unfactored transposition twiddles (+18 registers, -36 instructions per frame)
 #endif
@@ -1130,8 +1133,11 @@ constexpr int kStreamStateFloats = 2 * 384 + 384 + 5 * 288;   // hist, tail, cov
 // kernel entry, so the ~600 ns trip to L2/HBM overlaps the per-lane set-up instead of stalling every dependent load
 // (the kernel is one long dependent chain per warp; ncu before this change: 3 long-scoreboard stalls per issue).
 constexpr int kStreamStageFloats = kStreamStateFloats + 256;   // state + new hop [2][128]
-constexpr size_t kStreamSmem = (size_t)kWarps * f512::kSmemComplex * sizeof(float2) +
-                               (size_t)kWarps * kStreamStageFloats * sizeof(float) + (size_t)kWarps * sizeof(uint64_t);
+// Per warp: [new hop 256 floats][history 768][open tail 384][covariance 1440].  The first 1408 floats are copied
+// into registers before the transform starts, so the transform's transposition buffer (5376 B) reuses them: 45.6 KB
+// per CTA, four CTAs per SM.
+constexpr size_t kStreamSmem = (size_t)kWarps * kStreamStageFloats * sizeof(float) + (size_t)kWarps * sizeof(uint64_t);
+static_assert((256 + 768 + 384) * sizeof(float) >= f512::kSmemComplex * sizeof(float2), "transposition buffer must fit");
 
 // MVDR weights of one bin from the recursive statistics, float64, one division.  With nne = n + norm_eps,
 // A' = R00 + sigma nne, C' = R11 + sigma nne, b' = R01 (all "times nne"), det' = A' C' - |b'|^2, u' = adj(.) d:
@@ -1158,17 +1164,15 @@ __device__ __forceinline__ void stream_weights(float r00, float r11, float rre, 
   w1 = make_float2((float)((u1x * dx + u1y * dy) * r), (float)((u1y * dx - u1x * dy) * r));
 }
 
-__global__ void __launch_bounds__(kWarps * 32, 3)
+__global__ void __launch_bounds__(kWarps * 32, AVZ_MINB_STREAM)
 k512_stream_step(float* __restrict__ state, const float* __restrict__ hop_in, const float* __restrict__ noise_w,
                  const float2* __restrict__ dvec, int n_streams, int t, int t_end, float lam, AvzMvdrCfg cfg,
                  float* __restrict__ hop_out, Tables tb) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
-  float2* sm = reinterpret_cast<float2*>(smem_raw) + (size_t)warp * f512::kSmemComplex;
-  float* stage = reinterpret_cast<float*>(smem_raw + (size_t)kWarps * f512::kSmemComplex * sizeof(float2)) +
-                 (size_t)warp * kStreamStageFloats;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kWarps * f512::kSmemComplex * sizeof(float2) +
-                                              (size_t)kWarps * kStreamStageFloats * sizeof(float)) + warp;
+  float* stage = reinterpret_cast<float*>(smem_raw) + (size_t)warp * kStreamStageFloats;
+  float2* sm = reinterpret_cast<float2*>(stage);   // reused once hop, history and tail are in registers
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kWarps * kStreamStageFloats * sizeof(float)) + warp;
   const int s = blockIdx.x * kWarps + warp;
   if (s >= n_streams) return;
   float* st = state + (size_t)s * kStreamStateFloats;
@@ -1177,8 +1181,8 @@ k512_stream_step(float* __restrict__ state, const float* __restrict__ hop_in, co
     mbar_init(bar, 1);
     mbar_fence_init();
     mbar_arrive_expect_tx(bar, kStreamStageFloats * sizeof(float));
-    tma_load_1d(stage, st, kStreamStateFloats * sizeof(float), bar);
-    tma_load_1d(stage + kStreamStateFloats, xin_g, 256 * sizeof(float), bar);
+    tma_load_1d(stage, xin_g, 256 * sizeof(float), bar);
+    tma_load_1d(stage + 256, st, kStreamStateFloats * sizeof(float), bar);
   }
   Lane ln;
   ln.init(tb.tw);
@@ -1188,22 +1192,16 @@ k512_stream_step(float* __restrict__ state, const float* __restrict__ hop_in, co
   const bool frame_valid = (t >= 0) && (t < t_end);
   // this lane's noise weights and steering vectors: requested now, used after the forward transform
   float mk[9];
-  float2 dv0[8], dv1[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int k = bin_lo(ln, j);
-    mk[j] = noise_w ? __ldg(noise_w + (size_t)s * kF + k) : 1.f;
-    dv0[j] = __ldg(dvec + 2 * k);
-    dv1[j] = __ldg(dvec + 2 * k + 1);
-  }
+  for (int j = 0; j < 8; ++j) mk[j] = noise_w ? __ldg(noise_w + (size_t)s * kF + bin_lo(ln, j)) : 1.f;
   mk[8] = noise_w ? __ldg(noise_w + (size_t)s * kF + 256) : 1.f;
   __syncwarp();
   mbar_wait(bar, 0);
 
-  const float* hist = stage;                       // [2][384]
-  const float* tail = stage + 768;                 // [384]  open output blocks t+1 .. t+3 before this frame is added
-  const float* cov = stage + 1152;                 // [5][288]
-  const float* xin = stage + kStreamStateFloats;   // [2][128]
+  const float* xin = stage;                        // [2][128]
+  const float* hist = stage + 256;                 // [2][384]
+  const float* tail = stage + 256 + 768;           // [384]  open output blocks t+1 .. t+3 before this frame is added
+  const float* cov = stage + 256 + 1152;           // [5][288]
   float* cov_g = st + 1152;
 
   // frame t = [history (rows 0..11) | new hop (rows 12..15)], then slide the history
@@ -1228,6 +1226,7 @@ k512_stream_step(float* __restrict__ state, const float* __restrict__ hop_in, co
   for (int r = 0; r < 12; ++r) o[r] = tail[32 * r + lane];
 #pragma unroll
   for (int r = 12; r < 16; ++r) o[r] = 0.f;
+  __syncwarp();   // every lane has its hop, history and tail: their shared memory now serves the transposition
 
   if (frame_valid) {
     float2 v[16];
@@ -1262,7 +1261,7 @@ k512_stream_step(float* __restrict__ state, const float* __restrict__ hop_in, co
       if (k < cfg.hp_bins && cfg.hp_mode != AVZ_HP_NONE) {
         if (cfg.hp_mode == AVZ_HP_MIC0) w0.x = 1.f;
       } else {
-        stream_weights(r00, r11, rre, rim, nn, dv0[j], dv1[j], cfg, w0, w1);
+        stream_weights(r00, r11, rre, rim, nn, __ldg(dvec + 2 * k), __ldg(dvec + 2 * k + 1), cfg, w0, w1);
       }
       // S = conj(w0) Y0 + conj(w1) Y1 with Y = y' / N (analysis 2/N, halved); synthesis factor 1/2 folded below
       const float2 sv = cadd(cmulc(y0, w0), cmulc(y1, w1));
