@@ -1336,15 +1336,22 @@ int launch_stream_step(float* state, const float* hop_in, const float* noise_w, 
 namespace avz {
 namespace o512 {
 
+#ifndef AVZ_FEAT_WARPS
+#define AVZ_FEAT_WARPS 8
+#endif
+#ifndef AVZ_MINB_FEAT
+#define AVZ_MINB_FEAT 2
+#endif
+constexpr int kFeatWarps = AVZ_FEAT_WARPS;          // the 68 KB feature tile allows two CTAs per SM: eight warps each
 constexpr int kFeatTile = 32;                       // frames per CTA
 constexpr int kFeatPitch = kFeatTile + 1;           // floats per (feature, bin) row in shared memory
 
 template <int HOP>
-__global__ void __launch_bounds__(kWarps * 32, 3)
+__global__ void __launch_bounds__(kFeatWarps * 32, AVZ_MINB_FEAT)
 k512_features(const float* __restrict__ mix, int L, int T, int wrapped, float* __restrict__ X, Tables tb) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float2* sm = reinterpret_cast<float2*>(smem_raw) + (size_t)(threadIdx.x >> 5) * f512::kSmemComplex;
-  float* tile = reinterpret_cast<float*>(reinterpret_cast<float2*>(smem_raw) + (size_t)kWarps * f512::kSmemComplex);
+  float* tile = reinterpret_cast<float*>(reinterpret_cast<float2*>(smem_raw) + (size_t)kFeatWarps * f512::kSmemComplex);
   Lane ln;
   ln.init(tb.tw);
   const int lane = ln.lane, warp = threadIdx.x >> 5;
@@ -1354,7 +1361,7 @@ k512_features(const float* __restrict__ mix, int L, int T, int wrapped, float* _
   const float* m1 = m0 + L;
   float w[16];
   load_window(w, tb.win, ln);
-  constexpr int per = kFeatTile / kWarps;
+  constexpr int per = kFeatTile / kFeatWarps;
   const int ta = t0 + warp * per, tb_ = min(T, ta + per);
   if (ta < tb_) {
     Window2<HOP> win;
@@ -1399,7 +1406,7 @@ k512_features(const float* __restrict__ mix, int L, int T, int wrapped, float* _
   __syncthreads();
   const int nt = min(kFeatTile, T - t0);
   // rows (feature c, bin k): 32 consecutive frames each; one warp writes one row per iteration
-  for (int row = warp; row < 2 * kF; row += kWarps) {
+  for (int row = warp; row < 2 * kF; row += kFeatWarps) {
     const int c = row / kF, k = row - c * kF;
     if (lane < nt) X[(((int64_t)b * 2 + c) * kF + k) * T + t0 + lane] = tile[row * kFeatPitch + lane];
   }
@@ -1412,10 +1419,10 @@ int launch_features(const float* mix, int B, int64_t L, int wrapped, float* X, c
   if (rc) return rc;
   if (L >= (1ll << 30)) return set_error(AVZ_EINVAL, "L=%lld too long for the 512-point fast path", (long long)L);
   const int T = (int)avz_num_frames(L, kN, HOP);
-  const size_t smem = (size_t)kWarps * f512::kSmemComplex * sizeof(float2) + (size_t)2 * kF * kFeatPitch * sizeof(float);
+  const size_t smem = (size_t)kFeatWarps * f512::kSmemComplex * sizeof(float2) + (size_t)2 * kF * kFeatPitch * sizeof(float);
   AVZ_CUDA_OK(cudaFuncSetAttribute(k512_features<HOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((T + kFeatTile - 1) / kFeatTile, B);
-  k512_features<HOP><<<grid, kWarps * 32, smem, st>>>(mix, (int)L, T, wrapped, X, tb);
+  k512_features<HOP><<<grid, kFeatWarps * 32, smem, st>>>(mix, (int)L, T, wrapped, X, tb);
   AVZ_LAUNCH_OK("k512_features");
   return AVZ_OK;
 }

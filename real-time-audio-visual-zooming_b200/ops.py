@@ -399,12 +399,13 @@ def alloc_kept_spectrum(mix: torch.Tensor, cfg: MvdrConfig) -> Optional[torch.Te
     n = _lib.load().avz_spec_ws_bytes(B, L, cfg.n_fft, cfg.hop)
     if n <= 0:
         return None
-    # ~34 bytes per input sample: only worth it while it fits comfortably; otherwise pass B recomputes the transform
-    # (bit-identical result, ~8 % slower), so huge batches degrade gracefully instead of running out of memory.
-    free, _ = torch.cuda.mem_get_info(mix.device)
-    if n > free // 2:
+    # ~34 bytes per input sample.  If it does not fit, pass B recomputes the transform instead (bit-identical result,
+    # ~8 % slower): huge batches degrade gracefully instead of running out of memory.  (No cudaMemGetInfo here: it
+    # costs milliseconds per call and does not see the blocks torch's caching allocator can reuse.)
+    try:
+        return torch.empty((int(n),), dtype=torch.uint8, device=mix.device)
+    except torch.cuda.OutOfMemoryError:
         return None
-    return torch.empty((int(n),), dtype=torch.uint8, device=mix.device)
 
 
 def ibm_covariance(mix: torch.Tensor, tgt: torch.Tensor, itf: torch.Tensor, cfg: MvdrConfig,
