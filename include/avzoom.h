@@ -218,8 +218,11 @@ AVZ_API int avz_sir_f32(const float* est, const float* tgt, const float* itf, in
  * the mic-1 images, everything divided by max|mix| + peak_eps).
  * src [B,S,L] (source 0 is the target, the others interferers); delays_host [S][2] seconds (mic 1, mic 2) is a HOST
  * pointer read during the call.  mix [B,2,L], tgt [B,L], itf [B,L].  peak_eps < 0 skips the division (plain delays).
- * L = N1*N2 with N1 the largest power of two <= 512 dividing L and N2 <= 1024 (64000 = 512*125, 80000 = 128*625);
- * other lengths return AVZ_EINVAL.  1 <= S <= 8.  ws: avz_farfield_mix_ws_bytes(B,S,L) bytes of device scratch. */
+ * Any L (as pocketfft in the reference): L = N1*N2 with N1 the largest power of two <= 512 dividing L and N2 <= 1024
+ * (64000 = 512*125, 80000 = 128*625) runs the two-factor transform directly; every other length up to 262144 samples
+ * (primes, odd lengths, ...) runs the same passes as a chirp-z (Bluestein) convolution of length M >= 2L-1 (one plan
+ * per (device, L), built on the first call, which synchronises `stream` once).  Longer non-factorable lengths return
+ * AVZ_EINVAL.  1 <= S <= 8.  ws: avz_farfield_mix_ws_bytes(B,S,L) bytes of device scratch (0 = unsupported shape). */
 AVZ_API int64_t avz_farfield_mix_ws_bytes(int B, int S, int64_t L);
 AVZ_API int avz_farfield_mix_f32(const float* src, const double* delays_host, int B, int S, int64_t L, double fs,
                          float peak_eps, float* mix, float* tgt, float* itf, void* ws, void* stream);

@@ -113,24 +113,50 @@ __device__ __forceinline__ int bin_to_pos(int k, int N1) {
   return pos;
 }
 
+// What the forward power-of-two pass reads (the Bluestein variants serve lengths that have no N1*N2 split, see below).
+enum ColLoad {
+  kLoadPair = 0,      // two real sources of length N packed as re + i im
+  kLoadBluePair = 1,  // the same, of length Ls <= N: times the chirp c[n], zero beyond Ls
+  kLoadBlueSpec = 2,  // a complex spectrum of length Ls: conj(Y[k]) * c[k], zero beyond Ls (inverse transform)
+  kLoadPlane = 3      // a complex plane of length N as it is
+};
+// What the inverse power-of-two pass writes.
+enum ColStore {
+  kStoreReal = 0,      // re / im of x / N into two real signals of length N (+ running max|mix|)
+  kStoreBlueSpec = 1,  // conv[k] * c[k] / N for k < Ls into a complex spectrum of length Ls (natural bin order)
+  kStoreBlueReal = 2   // conj(conv[n] * c[n]) / (N Ls) for n < Ls into two real signals of length Ls (+ max|mix|)
+};
+
 // ---- pass 1: pack two sources, power-of-two DIF over n1, twiddle W_L^{n2 k1}; A[b][p][k1][n2] ----
+//      N = N1*N2 is the transform length (= plane stride of A); Ls the signal length (= N unless Bluestein).
+template <int LOAD>
 __global__ void __launch_bounds__(kColThreads)
-k_mix_cols_fwd(const float* __restrict__ src, float2* __restrict__ A, const float2* __restrict__ W, int S, int PP,
-               int N1, int log2N1, int N2, int64_t N) {
+k_mix_cols_fwd(const float* __restrict__ src, const float2* __restrict__ spec, const float2* __restrict__ chirp,
+               float2* __restrict__ A, const float2* __restrict__ W, int S, int PP, int N1, int log2N1, int N2,
+               int64_t N, int64_t Ls) {
   extern __shared__ float2 sm[];  // [N1][kCols]
   const int c0 = blockIdx.x * kCols;
   const int p = blockIdx.y, b = blockIdx.z;
   const int ncol = min(kCols, N2 - c0);
-  const float* sa = src + ((int64_t)b * S + 2 * p) * N;
+  const float* sa = src + ((int64_t)b * S + 2 * p) * Ls;
   const bool has_b = 2 * p + 1 < S;
-  const float* sb = sa + N;
+  const float* sb = sa + Ls;
+  const float2* sp = spec + ((int64_t)b * PP + p) * Ls;
   for (int idx = threadIdx.x; idx < N1 * kCols; idx += kColThreads) {
     const int c = idx & (kCols - 1), n1 = idx / kCols;
     float2 z = make_float2(0.f, 0.f);
-    if (c < ncol) {
-      const int64_t g = (int64_t)n1 * N2 + c0 + c;
-      z.x = __ldg(sa + g);
-      if (has_b) z.y = __ldg(sb + g);
+    const int64_t g = (int64_t)n1 * N2 + c0 + c;
+    if (c < ncol && g < Ls) {
+      if (LOAD == kLoadPair || LOAD == kLoadBluePair) {
+        z.x = __ldg(sa + g);
+        if (has_b) z.y = __ldg(sb + g);
+        if (LOAD == kLoadBluePair) z = cmul(z, __ldg(chirp + g));
+      } else if (LOAD == kLoadBlueSpec) {
+        const float2 y = __ldg(sp + g);
+        z = cmul(make_float2(y.x, -y.y), __ldg(chirp + g));
+      } else {
+        z = __ldg(sp + g);
+      }
     }
     sm[idx] = z;
   }
@@ -181,10 +207,12 @@ k_mix_cols_fwd(const float* __restrict__ src, float2* __restrict__ A, const floa
 //        t[ka][nb] = W_N2^{nb ka} * sum_na x[Nb na + nb] W_Na^{na ka}        (Na terms per output)
 //        X[ka + Na kb] = sum_nb t[ka][nb] W_Nb^{nb kb}                         (Nb terms per output)
 //      i.e. N2*(Na+Nb) instead of N2^2 complex multiply-adds per row (125 = 5*25: 4x fewer).  One thread per output
-//      index, kRowsPer rows share every twiddle fetch; wm[j] = W_N2^j (conjugated for the inverse). ----
+//      index, kRowsPer rows share every twiddle fetch; wm[j] = W_N2^j (conjugated for the inverse).
+//      `mul` (optional, [k1][k2] like the data): every element is multiplied by it on the way in - the Bluestein
+//      convolution kernel's spectrum, applied where the inverse transform starts. ----
 template <bool INV>
-__global__ void k_mix_rows(float2* __restrict__ Z, const float2* __restrict__ W, int N1, int N2, int Na, int Nb,
-                           int64_t N) {
+__global__ void k_mix_rows(float2* __restrict__ Z, const float2* __restrict__ W, const float2* __restrict__ mul, int N1,
+                           int N2, int Na, int Nb, int64_t N) {
   extern __shared__ float2 sm[];  // wm[N2] | rows[kRowsPer][N2] | tb[kRowsPer][N2]
   float2* wm = sm;
   float2* rows = sm + N2;
@@ -200,8 +228,14 @@ __global__ void k_mix_rows(float2* __restrict__ Z, const float2* __restrict__ W,
   for (int r0 = blockIdx.x * kRowsPer; r0 < N1; r0 += gridDim.x * kRowsPer) {
     const int nr = min(kRowsPer, N1 - r0);
     __syncthreads();
-    for (int j = threadIdx.x; j < kRowsPer * N2; j += blockDim.x)
-      rows[j] = (j < nr * N2) ? base[(int64_t)r0 * N2 + j] : make_float2(0.f, 0.f);
+    for (int j = threadIdx.x; j < kRowsPer * N2; j += blockDim.x) {
+      float2 v = make_float2(0.f, 0.f);
+      if (j < nr * N2) {
+        v = base[(int64_t)r0 * N2 + j];
+        if (mul) v = cmul(v, __ldg(mul + (int64_t)r0 * N2 + j));
+      }
+      rows[j] = v;
+    }
     __syncthreads();
     if (t < N2) {  // step A
       float2 acc[kRowsPer];
@@ -306,10 +340,11 @@ __global__ void k_mix_combine(float2* __restrict__ Z, MixParams prm, int PP, int
 }
 
 // ---- pass 5: twiddle conj(W_L^{n2 k1}), power-of-two DIT over k1, 1/L, write the four real signals ----
+template <int STORE>
 __global__ void __launch_bounds__(kColThreads)
-k_mix_cols_inv(const float2* __restrict__ Q, const float2* __restrict__ W, float* __restrict__ mix,
-               float* __restrict__ tgt, float* __restrict__ itf, unsigned* __restrict__ peak_bits, int PP, int N1,
-               int log2N1, int N2, int64_t N) {
+k_mix_cols_inv(const float2* __restrict__ Q, const float2* __restrict__ W, const float2* __restrict__ chirp,
+               float2* __restrict__ spec, float* __restrict__ mix, float* __restrict__ tgt, float* __restrict__ itf,
+               unsigned* __restrict__ peak_bits, int PP, int N1, int log2N1, int N2, int64_t N, int64_t Ls) {
   extern __shared__ float2 sm[];
   __shared__ float s_max[kColThreads / 32];
   const int c0 = blockIdx.x * kCols;
@@ -360,15 +395,32 @@ k_mix_cols_inv(const float2* __restrict__ Q, const float2* __restrict__ W, float
     }
     __syncthreads();
   }
-  const float inv_n = (float)(1.0 / (double)N);
-  float* o_re = q == 0 ? mix + (int64_t)b * 2 * N : tgt + (int64_t)b * N;
-  float* o_im = q == 0 ? mix + ((int64_t)b * 2 + 1) * N : itf + (int64_t)b * N;
+  if (STORE == kStoreBlueSpec) {
+    const float inv_n = (float)(1.0 / (double)N);
+    float2* o = spec + ((int64_t)b * PP + q) * Ls;
+    for (int idx = threadIdx.x; idx < N1 * kCols; idx += kColThreads) {
+      const int c = idx & (kCols - 1), n1 = idx / kCols;
+      const int64_t g = (int64_t)n1 * N2 + c0 + c;
+      if (c < ncol && g < Ls) {
+        const float2 v = cmul(sm[idx], __ldg(chirp + g));
+        o[g] = make_float2(v.x * inv_n, v.y * inv_n);
+      }
+    }
+    return;
+  }
+  const float inv_n = (float)(STORE == kStoreBlueReal ? 1.0 / ((double)N * (double)Ls) : 1.0 / (double)N);
+  float* o_re = q == 0 ? mix + (int64_t)b * 2 * Ls : tgt + (int64_t)b * Ls;
+  float* o_im = q == 0 ? mix + ((int64_t)b * 2 + 1) * Ls : itf + (int64_t)b * Ls;
   float mx = 0.f;
   for (int idx = threadIdx.x; idx < N1 * kCols; idx += kColThreads) {
     const int c = idx & (kCols - 1), n1 = idx / kCols;
-    if (c < ncol) {
-      const int64_t g = (int64_t)n1 * N2 + c0 + c;
-      const float2 v = sm[idx];
+    const int64_t g = (int64_t)n1 * N2 + c0 + c;
+    if (c < ncol && g < Ls) {
+      float2 v = sm[idx];
+      if (STORE == kStoreBlueReal) {
+        v = cmul(v, __ldg(chirp + g));
+        v.y = -v.y;
+      }
       const float re = v.x * inv_n, im = v.y * inv_n;
       o_re[g] = re;
       o_im[g] = im;
@@ -457,6 +509,148 @@ __global__ void k_f32_to_pcm16(const float* __restrict__ x, int64_t n, int16_t* 
     pcm[i] = (int16_t)to_pcm(x[i]);
 }
 
+
+// ---- host side: transform geometry, launch helpers, chirp-z plans ----
+struct Split {
+  int N1 = 1, lg = 0, N2 = 1;
+  int64_t len() const { return (int64_t)N1 * N2; }
+  size_t col_smem() const { return (size_t)N1 * kCols * sizeof(float2); }
+  size_t row_smem() const { return (size_t)(1 + 2 * kRowsPer) * N2 * sizeof(float2); }
+  void row_factors(int* Na, int* Nb) const {
+    int a = 1;
+    for (int d = 1; d * d <= N2; ++d)
+      if (N2 % d == 0) a = d;
+    *Na = a;
+    *Nb = N2 / a;
+  }
+};
+
+// Convolution length for the chirp-z path: M = 2^a * N2 >= 2L-1 with a <= 9, 2 <= N2 <= kMaxN2, chosen to minimise a
+// simple cost model (M * (2 a + Na + Nb): radix stages of the column pass + terms of the two-level row DFT).
+bool bluestein_split(int64_t L, Split* out) {
+  if (L < 1) return false;
+  const int64_t need = 2 * L - 1;
+  if (need > (int64_t)kMaxN1 * kMaxN2) return false;
+  double best = 0.0;
+  bool found = false;
+  for (int a = 0; (1 << a) <= kMaxN1; ++a) {
+    const int64_t n1 = (int64_t)1 << a;
+    int64_t lo = (need + n1 - 1) / n1;
+    if (lo < 2) lo = 2;
+    for (int64_t n2 = lo; n2 <= kMaxN2 && n2 < lo + 48; ++n2) {
+      Split c;
+      c.N1 = (int)n1;
+      c.lg = a;
+      c.N2 = (int)n2;
+      int Na, Nb;
+      c.row_factors(&Na, &Nb);
+      const double cost = (double)c.len() * (2.0 * a + Na + Nb);
+      if (!found || cost < best) {
+        best = cost;
+        *out = c;
+        found = true;
+      }
+    }
+  }
+  return found;
+}
+
+int set_mix_attrs(const Split& sp) {
+  static std::mutex attr_mu;
+  std::lock_guard<std::mutex> lk(attr_mu);
+  const int cs = (int)sp.col_smem(), rs = (int)sp.row_smem();
+  AVZ_CUDA_OK(cudaFuncSetAttribute(k_mix_cols_fwd<kLoadPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, cs));
+  AVZ_CUDA_OK(cudaFuncSetAttribute(k_mix_cols_fwd<kLoadBluePair>, cudaFuncAttributeMaxDynamicSharedMemorySize, cs));
+  AVZ_CUDA_OK(cudaFuncSetAttribute(k_mix_cols_fwd<kLoadBlueSpec>, cudaFuncAttributeMaxDynamicSharedMemorySize, cs));
+  AVZ_CUDA_OK(cudaFuncSetAttribute(k_mix_cols_fwd<kLoadPlane>, cudaFuncAttributeMaxDynamicSharedMemorySize, cs));
+  AVZ_CUDA_OK(cudaFuncSetAttribute(k_mix_cols_inv<kStoreReal>, cudaFuncAttributeMaxDynamicSharedMemorySize, cs));
+  AVZ_CUDA_OK(cudaFuncSetAttribute(k_mix_cols_inv<kStoreBlueSpec>, cudaFuncAttributeMaxDynamicSharedMemorySize, cs));
+  AVZ_CUDA_OK(cudaFuncSetAttribute(k_mix_cols_inv<kStoreBlueReal>, cudaFuncAttributeMaxDynamicSharedMemorySize, cs));
+  AVZ_CUDA_OK(cudaFuncSetAttribute(k_mix_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rs));
+  AVZ_CUDA_OK(cudaFuncSetAttribute(k_mix_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rs));
+  return AVZ_OK;
+}
+
+// Row pass over planes 0 .. used-1 of every utterance (PP planes of sp.len() elements per utterance).
+template <bool INV>
+int launch_rows(float2* Z, const float2* W, const float2* mul, const Split& sp, int B, int used, int PP, cudaStream_t st) {
+  if (sp.N2 <= 1) return AVZ_OK;
+  int Na, Nb;
+  sp.row_factors(&Na, &Nb);
+  const int64_t M = sp.len();
+  const int row_threads = ((sp.N2 + 31) / 32) * 32;
+  const int row_blocks = (sp.N1 + kRowsPer - 1) / kRowsPer;
+  if (used == PP) {
+    k_mix_rows<INV><<<dim3(row_blocks, B * PP), row_threads, sp.row_smem(), st>>>(Z, W, mul, sp.N1, sp.N2, Na, Nb, M);
+    AVZ_LAUNCH_OK("k_mix_rows");
+    return AVZ_OK;
+  }
+  for (int q = 0; q < used; ++q) {  // utterance stride PP planes
+    k_mix_rows<INV><<<dim3(row_blocks, B), row_threads, sp.row_smem(), st>>>(Z + (int64_t)q * M, W, mul, sp.N1, sp.N2, Na,
+                                                                            Nb, (int64_t)PP * M);
+    AVZ_LAUNCH_OK("k_mix_rows");
+  }
+  return AVZ_OK;
+}
+
+// Chirp-z plan of one signal length: c[n] = exp(-i pi n^2 / L) (n^2 reduced mod 2L in integers, angle in float64) and
+// the spectrum of the wrapped kernel conj(c)[|m|], computed once on the device by the native passes, [k1][k2] order.
+struct BluePlan {
+  int device;
+  int64_t L;
+  Split sp;
+  float2* chirp;
+  float2* bhat;
+};
+std::mutex g_blue_mu;
+std::vector<BluePlan*> g_blue_plans;
+
+int blue_plan_for(int64_t L, const Split& sp, cudaStream_t st, const BluePlan** out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return set_error(AVZ_ENOGPU, "cudaGetDevice: %s", cudaGetErrorString(e));
+  std::lock_guard<std::mutex> lk(g_blue_mu);
+  for (const BluePlan* p : g_blue_plans)
+    if (p->device == dev && p->L == L) {
+      *out = p;
+      return AVZ_OK;
+    }
+  const int64_t M = sp.len();
+  const float2* W = nullptr;
+  int rc = mix_table_for(M, &W);
+  if (rc != AVZ_OK) return rc;
+  std::vector<float2> c((size_t)L), kb((size_t)M, make_float2(0.f, 0.f));
+  const double pi = 3.141592653589793238462643383279;
+  for (int64_t n = 0; n < L; ++n) {
+    const int64_t r = (int64_t)(((unsigned long long)n * (unsigned long long)n) % (unsigned long long)(2 * L));
+    const double ang = pi * (double)r / (double)L;
+    const float cr = (float)cos(ang), ci = (float)sin(ang);
+    c[(size_t)n] = make_float2(cr, -ci);
+    kb[(size_t)n] = make_float2(cr, ci);
+    if (n > 0) kb[(size_t)(M - n)] = make_float2(cr, ci);
+  }
+  void *dc = nullptr, *dk = nullptr, *dh = nullptr;
+  AVZ_CUDA_OK(cudaMalloc(&dc, (size_t)L * sizeof(float2)));
+  AVZ_CUDA_OK(cudaMalloc(&dk, (size_t)M * sizeof(float2)));
+  AVZ_CUDA_OK(cudaMalloc(&dh, (size_t)M * sizeof(float2)));
+  AVZ_CUDA_OK(cudaMemcpy(dc, c.data(), (size_t)L * sizeof(float2), cudaMemcpyHostToDevice));
+  AVZ_CUDA_OK(cudaMemcpy(dk, kb.data(), (size_t)M * sizeof(float2), cudaMemcpyHostToDevice));
+  rc = set_mix_attrs(sp);
+  if (rc != AVZ_OK) return rc;
+  const int col_blocks = (sp.N2 + kCols - 1) / kCols;
+  k_mix_cols_fwd<kLoadPlane><<<dim3(col_blocks, 1, 1), kColThreads, sp.col_smem(), st>>>(
+      nullptr, (const float2*)dk, nullptr, (float2*)dh, W, 1, 1, sp.N1, sp.lg, sp.N2, M, M);
+  AVZ_LAUNCH_OK("k_mix_cols_fwd<plane>");
+  rc = launch_rows<false>((float2*)dh, W, nullptr, sp, 1, 1, 1, st);
+  if (rc != AVZ_OK) return rc;
+  AVZ_CUDA_OK(cudaStreamSynchronize(st));   // the plan may be used from any stream afterwards
+  AVZ_CUDA_OK(cudaFree(dk));
+  BluePlan* p = new BluePlan{dev, L, sp, (float2*)dc, (float2*)dh};
+  g_blue_plans.push_back(p);
+  *out = p;
+  return AVZ_OK;
+}
+
 }  // namespace
 }  // namespace avz
 
@@ -464,10 +658,12 @@ extern "C" {
 
 int64_t avz_farfield_mix_ws_bytes(int B, int S, int64_t L) {
   using namespace avz;
-  int N1, lg, N2;
-  if (B <= 0 || S < 1 || S > kMaxSrc || !split_length(L, &N1, &lg, &N2)) return 0;
+  if (B <= 0 || S < 1 || S > kMaxSrc) return 0;
   const int PP = ((S + 1) / 2 > 2) ? (S + 1) / 2 : 2;
-  return (int64_t)B * PP * L * (int64_t)sizeof(float2) + (int64_t)B * 16;
+  Split sp;
+  if (split_length(L, &sp.N1, &sp.lg, &sp.N2)) return (int64_t)B * PP * L * (int64_t)sizeof(float2) + (int64_t)B * 16;
+  if (!bluestein_split(L, &sp)) return 0;
+  return (int64_t)B * PP * (sp.len() + L) * (int64_t)sizeof(float2) + (int64_t)B * 16;
 }
 
 int avz_farfield_mix_f32(const float* src, const double* delays_host, int B, int S, int64_t L, double fs,
@@ -475,71 +671,74 @@ int avz_farfield_mix_f32(const float* src, const double* delays_host, int B, int
   using namespace avz;
   if (!src || !delays_host || !mix || !tgt || !itf || !ws) return set_error(AVZ_EINVAL, "avz_farfield_mix_f32: null pointer");
   if (S < 1 || S > kMaxSrc) return set_error(AVZ_EINVAL, "avz_farfield_mix_f32: S=%d out of range (1..%d)", S, kMaxSrc);
-  int N1, lg, N2;
-  if (!split_length(L, &N1, &lg, &N2))
-    return set_error(AVZ_EINVAL,
-                     "avz_farfield_mix_f32: L=%lld unsupported (need L = 2^a * N2 with the odd-or-leftover factor "
-                     "N2 <= %d after taking 2^a <= %d)", (long long)L, kMaxN2, kMaxN1);
   if (!(fs > 0.0)) return set_error(AVZ_EINVAL, "avz_farfield_mix_f32: fs must be positive");
-  const float2* W = nullptr;
-  int rc = mix_table_for(L, &W);
-  if (rc != AVZ_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int P = (S + 1) / 2;
   const int PP = P > 2 ? P : 2;
   if (B <= 0 || (int64_t)B * PP > 65535)
     return set_error(AVZ_EINVAL, "avz_farfield_mix_f32: B=%d out of range (B * max(2, ceil(S/2)) <= 65535)", B);
-  float2* Z = (float2*)ws;
-  unsigned* peak = (unsigned*)((char*)ws + (int64_t)B * PP * L * (int64_t)sizeof(float2));
+  Split sp;
+  const bool native = split_length(L, &sp.N1, &sp.lg, &sp.N2);
+  const BluePlan* bp = nullptr;
+  if (!native) {
+    if (!bluestein_split(L, &sp))
+      return set_error(AVZ_EINVAL,
+                       "avz_farfield_mix_f32: L=%lld unsupported (neither L = 2^a * N2 with 2^a <= %d, N2 <= %d, nor "
+                       "2L-1 <= %lld for the chirp-z path)", (long long)L, kMaxN1, kMaxN2, (long long)kMaxN1 * kMaxN2);
+    const int rc = blue_plan_for(L, sp, st, &bp);
+    if (rc != AVZ_OK) return rc;
+  }
+  const int64_t M = sp.len();   // transform length (= L on the native path)
+  const float2* W = nullptr;
+  int rc = mix_table_for(M, &W);
+  if (rc != AVZ_OK) return rc;
+  float2* Z = (float2*)ws;                                   // [B][PP][M]
+  float2* SP = native ? Z : Z + (int64_t)B * PP * M;         // Bluestein: spectra [B][PP][L] in natural bin order
+  unsigned* peak = (unsigned*)((char*)ws + (int64_t)B * PP * (native ? L : M + L) * (int64_t)sizeof(float2));
   MixParams prm;
   prm.S = S;
   for (int s = 0; s < kMaxSrc; ++s) {
     prm.c1[s] = s < S ? delays_host[2 * s] * fs / (double)L : 0.0;
     prm.c2[s] = s < S ? delays_host[2 * s + 1] * fs / (double)L : 0.0;
   }
-  const size_t col_smem = (size_t)N1 * kCols * sizeof(float2);
-  const size_t row_smem = (size_t)(1 + 2 * kRowsPer) * N2 * sizeof(float2);
-  int Na = 1;
-  for (int a = 1; a * a <= N2; ++a)
-    if (N2 % a == 0) Na = a;
-  const int Nb = N2 / Na;
-  static std::mutex attr_mu;
-  {
-    std::lock_guard<std::mutex> lk(attr_mu);
-    AVZ_CUDA_OK(cudaFuncSetAttribute(k_mix_cols_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)col_smem));
-    AVZ_CUDA_OK(cudaFuncSetAttribute(k_mix_cols_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)col_smem));
-    AVZ_CUDA_OK(cudaFuncSetAttribute(k_mix_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
-    AVZ_CUDA_OK(cudaFuncSetAttribute(k_mix_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
-  }
-  const int col_blocks = (N2 + kCols - 1) / kCols;
-  const int row_threads = ((N2 + 31) / 32) * 32;
-  const int row_blocks = (N1 + kRowsPer - 1) / kRowsPer;
+  rc = set_mix_attrs(sp);
+  if (rc != AVZ_OK) return rc;
+  const size_t col_smem = sp.col_smem();
+  const int col_blocks = (sp.N2 + kCols - 1) / kCols;
   AVZ_CUDA_OK(cudaMemsetAsync(peak, 0, (size_t)B * sizeof(unsigned), st));
-  k_mix_cols_fwd<<<dim3(col_blocks, P, B), kColThreads, col_smem, st>>>(src, Z, W, S, PP, N1, lg, N2, L);
-  AVZ_LAUNCH_OK("k_mix_cols_fwd");
-  if (N2 > 1) {
-    if (P == PP) {
-      k_mix_rows<false><<<dim3(row_blocks, B * PP), row_threads, row_smem, st>>>(Z, W, N1, N2, Na, Nb, L);
-    } else {  // P == 1 < PP == 2: only plane 0 of each utterance holds data; stride 2 planes
-      k_mix_rows<false><<<dim3(row_blocks, B), row_threads, row_smem, st>>>(Z, W, N1, N2, Na, Nb, 2 * L);
-    }
-    AVZ_LAUNCH_OK("k_mix_rows<fwd>");
+  if (native) {
+    k_mix_cols_fwd<kLoadPair><<<dim3(col_blocks, P, B), kColThreads, col_smem, st>>>(src, nullptr, nullptr, Z, W, S, PP,
+                                                                                    sp.N1, sp.lg, sp.N2, L, L);
+    AVZ_LAUNCH_OK("k_mix_cols_fwd");
+    if ((rc = launch_rows<false>(Z, W, nullptr, sp, B, P, PP, st)) != AVZ_OK) return rc;
+    k_mix_combine<<<dim3((unsigned)((L + 255) / 256), B), 256, 0, st>>>(Z, prm, PP, sp.N1, sp.N2, L);
+    AVZ_LAUNCH_OK("k_mix_combine");
+    if ((rc = launch_rows<true>(Z, W, nullptr, sp, B, 2, PP, st)) != AVZ_OK) return rc;
+    k_mix_cols_inv<kStoreReal><<<dim3(col_blocks, 2, B), kColThreads, col_smem, st>>>(Z, W, nullptr, nullptr, mix, tgt, itf,
+                                                                                     peak, PP, sp.N1, sp.lg, sp.N2, L, L);
+    AVZ_LAUNCH_OK("k_mix_cols_inv");
+  } else {
+    // Chirp-z (Bluestein): DFT_L(u)[k] = c[k] * sum_n (u[n] c[n]) conj(c)[k - n],  c[n] = exp(-i pi n^2 / L); the
+    // convolution runs as a cyclic one of length M >= 2L-1 on the native passes.  Inverse: x = conj(DFT_L(conj Y)) / L.
+    k_mix_cols_fwd<kLoadBluePair><<<dim3(col_blocks, P, B), kColThreads, col_smem, st>>>(src, nullptr, bp->chirp, Z, W, S,
+                                                                                        PP, sp.N1, sp.lg, sp.N2, M, L);
+    AVZ_LAUNCH_OK("k_mix_cols_fwd<chirp>");
+    if ((rc = launch_rows<false>(Z, W, nullptr, sp, B, P, PP, st)) != AVZ_OK) return rc;
+    if ((rc = launch_rows<true>(Z, W, bp->bhat, sp, B, P, PP, st)) != AVZ_OK) return rc;
+    k_mix_cols_inv<kStoreBlueSpec><<<dim3(col_blocks, P, B), kColThreads, col_smem, st>>>(
+        Z, W, bp->chirp, SP, nullptr, nullptr, nullptr, nullptr, PP, sp.N1, sp.lg, sp.N2, M, L);
+    AVZ_LAUNCH_OK("k_mix_cols_inv<spec>");
+    k_mix_combine<<<dim3((unsigned)((L + 255) / 256), B), 256, 0, st>>>(SP, prm, PP, 1, (int)L, L);
+    AVZ_LAUNCH_OK("k_mix_combine");
+    k_mix_cols_fwd<kLoadBlueSpec><<<dim3(col_blocks, 2, B), kColThreads, col_smem, st>>>(nullptr, SP, bp->chirp, Z, W, S,
+                                                                                        PP, sp.N1, sp.lg, sp.N2, M, L);
+    AVZ_LAUNCH_OK("k_mix_cols_fwd<spec>");
+    if ((rc = launch_rows<false>(Z, W, nullptr, sp, B, 2, PP, st)) != AVZ_OK) return rc;
+    if ((rc = launch_rows<true>(Z, W, bp->bhat, sp, B, 2, PP, st)) != AVZ_OK) return rc;
+    k_mix_cols_inv<kStoreBlueReal><<<dim3(col_blocks, 2, B), kColThreads, col_smem, st>>>(
+        Z, W, bp->chirp, nullptr, mix, tgt, itf, peak, PP, sp.N1, sp.lg, sp.N2, M, L);
+    AVZ_LAUNCH_OK("k_mix_cols_inv<real>");
   }
-  k_mix_combine<<<dim3((unsigned)((L + 255) / 256), B), 256, 0, st>>>(Z, prm, PP, N1, N2, L);
-  AVZ_LAUNCH_OK("k_mix_combine");
-  if (N2 > 1) {
-    if (PP == 2) {
-      k_mix_rows<true><<<dim3(row_blocks, B * 2), row_threads, row_smem, st>>>(Z, W, N1, N2, Na, Nb, L);
-      AVZ_LAUNCH_OK("k_mix_rows<inv>");
-    } else {  // planes 0 and 1 of each utterance, utterance stride PP planes
-      for (int q = 0; q < 2; ++q) {
-        k_mix_rows<true><<<dim3(row_blocks, B), row_threads, row_smem, st>>>(Z + (int64_t)q * L, W, N1, N2, Na, Nb, (int64_t)PP * L);
-        AVZ_LAUNCH_OK("k_mix_rows<inv>");
-      }
-    }
-  }
-  k_mix_cols_inv<<<dim3(col_blocks, 2, B), kColThreads, col_smem, st>>>(Z, W, mix, tgt, itf, peak, PP, N1, lg, N2, L);
-  AVZ_LAUNCH_OK("k_mix_cols_inv");
   if (peak_eps >= 0.f) {
     k_mix_scale<<<dim3(64, B), 256, 0, st>>>(mix, tgt, itf, peak, peak_eps, L);
     AVZ_LAUNCH_OK("k_mix_scale");

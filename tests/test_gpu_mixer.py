@@ -85,8 +85,42 @@ def test_apply_frac_delay_dropin(az, golden_dir):
     assert rel_l2(two.cpu().numpy(), ref2) < 2 * MIX_TOL
 
 
+# lengths with no 2^a * (<= 1024) split run the chirp-z (Bluestein) path: primes, odd lengths, 2 * prime, tiny
+@pytest.mark.parametrize("B,S,L", [(1, 3, 4001), (2, 4, 12345), (1, 2, 50001), (2, 1, 6002), (1, 5, 2049), (1, 8, 100003),
+                                     (1, 3, 262143)])
+def test_mixer_arbitrary_length_matches_oracle(az, B, S, L):
+    rng = np.random.default_rng(7000 * S + L % 991)
+    src = rng.standard_normal((B, S, L)).astype(np.float32)
+    delays = [O.far_field_delays(a, 0.04, 343.0) for a in ANGLES[:S]]
+    assert az._lib.load().avz_farfield_mix_ws_bytes(B, S, L) > B * 2 * L * 8 * 2   # chirp-z scratch, not the native one
+    mix, tgt, itf = az.ops.far_field_mix(torch.from_numpy(src).cuda(), delays, 16000.0)
+    assert mix.shape == (B, 2, L) and tgt.shape == (B, L) and itf.shape == (B, L)
+    for b in range(B):
+        rm, rt, ri = O.mix_far_field(list(src[b].astype(np.float64)), ANGLES[:S], 0.04, 343.0, 16000.0)
+        assert rel_l2(mix[b].cpu().numpy(), rm) < MIX_TOL
+        assert rel_l2(tgt[b].cpu().numpy(), rt) < MIX_TOL
+        if S > 1:
+            assert rel_l2(itf[b].cpu().numpy(), ri) < MIX_TOL
+        assert abs(float(mix[b].abs().max()) - 1.0) < 1e-6
+    # the cached plan serves a second call (other stream, other batch) identically
+    with torch.cuda.stream(torch.cuda.Stream()):
+        mix2, _, _ = az.ops.far_field_mix(torch.from_numpy(src[:1]).cuda(), delays, 16000.0)
+    torch.cuda.synchronize()
+    assert torch.equal(mix2[0], mix[0])
+
+
+def test_apply_frac_delay_arbitrary_length(az):
+    from avzoom.core import world_building as wb
+    rng = np.random.default_rng(11)
+    for L in (33333, 16001):
+        y = rng.standard_normal(L).astype(np.float32)
+        got = wb.apply_frac_delay(y, 3.7e-5, 16000)
+        assert isinstance(got, np.ndarray) and got.shape == (L,)
+        assert rel_l2(got, O.fractional_delay(y.astype(np.float64), 3.7e-5, 16000)) < MIX_TOL
+
+
 def test_mixer_rejects_unsupported_shapes(az):
-    x = torch.zeros((1, 3, 4001), device="cuda")            # 4001 is prime: no 2^a * (<=1024) split
+    x = torch.zeros((1, 3, 300001), device="cuda")          # prime and 2L-1 > 512 * 1024: neither path takes it
     with pytest.raises(az._lib.AvzError):
         az.ops.far_field_mix(x, [[0.0, 0.0]] * 3)
     x = torch.zeros((1, 9, 4000), device="cuda")            # more than 8 sources
