@@ -33,6 +33,16 @@ int launch_apply(const float* mix, const void* spec, const float* w, const uint3
                  float peak_eps, cudaStream_t st);
 }  // namespace o512
 
+// n_fft = 1024 / hop 512 fast path (avz_opt1024.cu)
+namespace o1024 {
+int cov_chunks1024(int B, int T);
+int launch_features(const float* mix, int B, int64_t L, int mode, float* X, cudaStream_t st);
+int launch_mask_cov(const float* mix, const float* mask, int B, int64_t L, float sqrt_eps, float* part, int* chunks_out,
+                    cudaStream_t st);
+int launch_apply(const float* mix, const float* w, const float* mask, int gain_mode, float post_floor, int B, int64_t L,
+                 float* out, float* peak, cudaStream_t st);
+}  // namespace o1024
+
 // The register-resident 512-point path serves n_fft 512 with hop 128 / 256 unless AVZ_FORCE_GENERIC=1
 // (kept for A/B checks of the two implementations against each other).
 static bool use_opt512(int n_fft, int hop) {
@@ -41,6 +51,14 @@ static bool use_opt512(int n_fft, int hop) {
     return e && e[0] == '1';
   }();
   return !forced && n_fft == 512 && (hop == 128 || hop == 256);
+}
+// ... and n_fft 1024 / hop 512 (the learned pipelines' shape) on the same 512-point transform (even/odd split).
+static bool use_opt1024(int n_fft, int hop) {
+  static const bool forced = [] {
+    const char* e = getenv("AVZ_FORCE_GENERIC");
+    return e && e[0] == '1';
+  }();
+  return !forced && n_fft == 1024 && hop == 512;
 }
 
 template <int N>
@@ -629,6 +647,7 @@ int avz_wave_features_f32(const float* mix, int B, int64_t L, int n_fft, int hop
     return (hop == 128) ? o512::launch_features<128>(mix, B, L, wrapped, X, (cudaStream_t)stream)
                         : o512::launch_features<256>(mix, B, L, wrapped, X, (cudaStream_t)stream);
   }
+  if (use_opt1024(n_fft, hop)) return o1024::launch_features(mix, B, L, mode, X, (cudaStream_t)stream);
   AVZ_DISPATCH_N(n_fft, (launch_wave_features<N_>(mix, B, L, hop, mode, X, (cudaStream_t)stream)));
 }
 
@@ -638,6 +657,7 @@ int64_t avz_ibm_cov_ws_bytes(int B, int64_t L, int n_fft, int hop) {
   const int warps = (n_fft <= 512) ? 8 : 4;
   int chunks = cov_chunks(B, T, warps, num_sms());
   if (n_fft == 512) chunks = max(chunks, o512::cov_chunks512(B, T));
+  if (n_fft == 1024) chunks = max(chunks, o1024::cov_chunks1024(B, T));
   const int FP = ((n_fft / 2 + 1) + 31) / 32 * 32;
   int64_t bytes = (int64_t)B * chunks * 5 * FP * (int64_t)sizeof(float);
   if (n_fft == 512) bytes = max(bytes, o512::ws_bytes512(B, T));
@@ -675,6 +695,15 @@ int avz_wave_mask_cov_f32(const float* mix, const float* mask, int B, int64_t L,
   if (use_opt512(n_fft, hop))
     return launch_cov512(mix, nullptr, nullptr, mask, B, L, hop, sqrt_eps, norm_eps, nullptr, R, msum, ws, nullptr,
                          (cudaStream_t)stream);
+  if (use_opt1024(n_fft, hop)) {
+    int chunks = 0;
+    rc = o1024::launch_mask_cov(mix, mask, B, L, sqrt_eps, (float*)ws, &chunks, (cudaStream_t)stream);
+    if (rc) return rc;
+    k_cov_finalize<<<(B * 513 + 63) / 64, 64, 0, (cudaStream_t)stream>>>((const float*)ws, B, 513, Geo<1024>::FP, chunks,
+                                                                         norm_eps, reinterpret_cast<float4*>(R), msum);
+    AVZ_LAUNCH_OK("k_cov_finalize");
+    return AVZ_OK;
+  }
   AVZ_DISPATCH_N(n_fft, (launch_cov<N_, COV_MASK>(mix, nullptr, nullptr, mask, B, L, hop, sqrt_eps, norm_eps, nullptr,
                                                   R, msum, ws, (cudaStream_t)stream)));
 }
@@ -787,6 +816,8 @@ int avz_mvdr_apply_f32(const float* mix, const float* w, const uint32_t* ibm_bit
                         : o512::launch_apply<256>(mix, nullptr, w, ibm_bits, mask, gain, cfg->post_floor, B, L, out, peak,
                                                   0, 0.f, (cudaStream_t)stream);
   }
+  if (use_opt1024(n_fft, hop) && gain != GAIN_BITS)
+    return o1024::launch_apply(mix, w, mask, gain, cfg->post_floor, B, L, out, peak, (cudaStream_t)stream);
   AVZ_DISPATCH_N(n_fft, (launch_synth<N_, SRC_MIX>(mix, nullptr, w, ibm_bits, mask, gain, cfg->post_floor, B, L, T, hop,
                                                    out, peak, (cudaStream_t)stream)));
 }

@@ -1,0 +1,495 @@
+// n_fft = 1024 / hop 512 fast path - the STFT shape of the reference's learned pipelines
+// (rt_av_zoom/core/full_audio_generating_pipeline/inference.py:88-117, tf_lite_version/inference.py:85-179,307-349,
+// Final_pipeline/src/inference.py:198-222 with their config.json) - on the register-resident 512-point warp FFT.
+//
+// A real 1024-sample frame x is transformed as ONE 512-point complex FFT of z[n] = x[2n] + i x[2n+1]:
+//   with A = Z[k] + conj Z[512-k],  T = W1024^k * (-i) (Z[k] - conj Z[512-k]):
+//   X[k] = (A + T) / 2,   X[512-k] = conj(A - T) / 2          (k = 0..255; X[256] = conj Z[256])
+// so lane (k1, h) of avz_fft512.cuh, which holds lo bins k = k1 + 16 j + 128 h and (after one shuffle per bin) their
+// mirrors Z[512-k], produces bins k and 512-k of the one-sided spectrum.  The inverse runs the same algebra backwards
+// (E = S[k] + conj S[512-k], O = (S[k] - conj S[512-k]) conj W1024^k, Z = (E + i O) / 2) and one inverse 512-point
+// transform returns the frame as (even, odd) sample pairs, which is also the layout of coalesced 8-byte loads/stores.
+//
+//   k1024_features  STFT(mic0), STFT(mic1) -> ln(|Y0| + 1e-7), angle(Y0) - angle(Y1); NCHW rows leave as runs along T
+//   k1024_cov       STFT of both mics -> (1 - mask)-weighted 2x2 covariance partial sums, accumulators in registers
+//   k1024_apply     STFT of both mics -> w^H y -> post-filter gain -> inverse -> window -> overlap-add of the two
+//                   half-frames in registers -> / sum w^2 -> coalesced stores (+ per-utterance peak)
+//
+// The two per-channel spectra of a frame meet in a per-warp shared-memory buffer in natural bin order (513 + 513
+// complex): the covariance / beamforming arithmetic then runs on bins lane + 32 i, where the mask, the weights and the
+// partial sums are contiguous.  One warp owns a run of consecutive frames; nothing but __syncwarp() on the frame path.
+#include <cstdlib>
+
+#include "avz_common.cuh"
+#include "avz_fft512.cuh"
+
+namespace avz {
+namespace o1024 {
+
+using f512::Lane;
+
+constexpr int kN = 1024;
+constexpr int kHop = 512;
+constexpr int kF = 513;
+constexpr int kFP = 544;      // padded bins of the partial sums (Geo<1024>::FP)
+constexpr int kBPL = 17;      // bins lane + 32 i, i < 17, k <= 512
+constexpr int kWarps = 4;
+constexpr int kYP = 520;      // complex elements per channel plane of the per-warp spectrum buffer
+constexpr int kFeatFrames = 16;
+constexpr int kFeatPitch = kFeatFrames + 1;
+
+enum { GAIN_NONE = 0, GAIN_BITS = 1, GAIN_FLOOR = 2, GAIN_MASK = 3 };   // as avz_generic.cu
+
+#ifndef AVZ_MINB_1024
+#define AVZ_MINB_1024 2
+#endif
+
+struct Ctx {
+  Lane ln;
+  float2 wk[8];   // W1024^k for this lane's lo bins k = k1 + 16 j + 128 h
+  __device__ __forceinline__ void init(const float2* __restrict__ tw512, const float2* __restrict__ tw1024) {
+    ln.init(tw512);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wk[j] = tw1024[ln.k1 + 16 * j + 128 * ln.h];
+  }
+};
+
+// Shared-memory constants of a CTA: analysis window (w[2n], w[2n+1]) * lane sign / 1024 and synthesis window
+// (w[2n], w[2n+1]) * lane sign / 2, both indexed by n = 32 r + lane (the transform's time layout).
+__device__ __forceinline__ void fill_windows(float2* s_wa, float2* s_ws, const float* __restrict__ win) {
+  for (int n = threadIdx.x; n < 512; n += blockDim.x) {
+    const float sg = ((n & 3) == 3) ? -1.f : 1.f;
+    const float a = win[2 * n], b = win[2 * n + 1];
+    s_wa[n] = make_float2(a * sg * (1.f / 1024.f), b * sg * (1.f / 1024.f));
+    if (s_ws) s_ws[n] = make_float2(a * sg * 0.5f, b * sg * 0.5f);
+  }
+}
+
+// Raw samples of frame t of one channel: raw[r] = (x[s + 64 r + 2 lane], x[... + 1]), s = 512 t - 512; zero outside
+// [0, L) (scipy boundary='zeros', padded=True).
+__device__ __forceinline__ void load_frame(float2 (&raw)[16], const float* __restrict__ x, int L, int t, int lane) {
+  const int s = t * kHop - kN / 2;
+  if (s >= 0 && s + kN <= L && (reinterpret_cast<uintptr_t>(x) & 7) == 0) {   // warp-uniform
+    const float2* p = reinterpret_cast<const float2*>(x + s) + lane;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) raw[r] = __ldg(p + 32 * r);
+  } else {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int i = s + 64 * r + 2 * lane;
+      raw[r].x = ((unsigned)i < (unsigned)L) ? __ldg(x + i) : 0.f;
+      raw[r].y = ((unsigned)(i + 1) < (unsigned)L) ? __ldg(x + i + 1) : 0.f;
+    }
+  }
+}
+
+// One channel: window, 512-point transform, even/odd split.  lo[j] = X[k], up[j] = X[512 - k] for this lane's lo bins
+// (scaled by 1 / sum(w) as scipy's stft); mid = X[256] (meaningful on lane 0 only).
+__device__ __forceinline__ void analyse(const float2 (&raw)[16], const float2* __restrict__ s_wa, float2* __restrict__ sm,
+                                        const Ctx& cx, float2 (&lo)[8], float2 (&up)[8], float2& mid) {
+  float2 v[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const float2 w = s_wa[32 * r + cx.ln.lane];
+    v[r] = make_float2(raw[r].x * w.x, raw[r].y * w.y);
+  }
+  f512::forward(v, sm, cx.ln);
+  float2 mir[8];
+  f512::mirror_of_low(v, mir, cx.ln);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float2 z = v[j], m = mir[j];
+    const float2 A = make_float2(z.x + m.x, z.y - m.y);          // Z[k] + conj Z[512-k]
+    const float2 Bv = make_float2(z.y + m.y, m.x - z.x);         // -i (Z[k] - conj Z[512-k])
+    const float2 T = cmul(Bv, cx.wk[j]);
+    lo[j] = make_float2(A.x + T.x, A.y + T.y);
+    up[j] = make_float2(A.x - T.x, T.y - A.y);                    // conj(A - T)
+  }
+  mid = make_float2(2.f * v[8].x, -2.f * v[8].y);                // lane 0: hi[0] = Z[256]; X[256] = conj Z[256]
+}
+
+// ... and into the per-warp buffer in natural bin order.
+__device__ __forceinline__ void spectrum_to_smem(float2* __restrict__ Yc, const float2 (&lo)[8], const float2 (&up)[8],
+                                                 float2 mid, const Lane& ln) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = ln.k1 + 16 * j + 128 * ln.h;
+    Yc[k] = lo[j];
+    Yc[512 - k] = up[j];
+  }
+  if (ln.lane == 0) Yc[256] = mid;
+}
+
+// ------------------------------------------------------------------------------------------
+// features
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarps * 32, 2)
+k1024_features(const float* __restrict__ mix, int L, int T, int mode, float* __restrict__ X, Tables tb512, Tables tb) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* s_wa = reinterpret_cast<float2*>(smem_raw);                        // [512]
+  float2* s_fft = s_wa + 512;                                                // [kWarps][kSmemComplex]
+  float* s_tile = reinterpret_cast<float*>(s_fft + kWarps * f512::kSmemComplex);   // [2][kF][kFeatPitch]
+  fill_windows(s_wa, nullptr, tb.win);
+  __syncthreads();
+  Ctx cx;
+  cx.init(tb512.tw, tb.tw);
+  const int lane = cx.ln.lane, warp = threadIdx.x >> 5;
+  float2* sm = s_fft + (size_t)warp * f512::kSmemComplex;
+  const int b = blockIdx.y;
+  const float* m0 = mix + (int64_t)b * 2 * L;
+  const float* m1 = m0 + L;
+  const int t0 = blockIdx.x * kFeatFrames;
+  const int nt = min(kFeatFrames, T - t0);
+  for (int tl = warp; tl < nt; tl += kWarps) {
+    const int t = t0 + tl;
+    float2 r0[16], r1[16];
+    load_frame(r0, m0, L, t, lane);
+    load_frame(r1, m1, L, t, lane);
+    float2 lo0[8], up0[8], mid0, lo1[8], up1[8], mid1;
+    analyse(r0, s_wa, sm, cx, lo0, up0, mid0);
+    analyse(r1, s_wa, sm, cx, lo1, up1, mid1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = cx.ln.k1 + 16 * j + 128 * cx.ln.h;
+      float lm, ipd;
+      feature_values(lo0[j], lo1[j], lm, ipd);
+      if (mode == AVZ_FEAT_PHYSICS_NHWC) {
+        store_features(X, mode, b, k, t, kF, T, lm, ipd);
+      } else {
+        s_tile[(size_t)k * kFeatPitch + tl] = lm;
+        s_tile[(size_t)(kF + k) * kFeatPitch + tl] = ipd;
+      }
+      feature_values(up0[j], up1[j], lm, ipd);
+      if (mode == AVZ_FEAT_PHYSICS_NHWC) {
+        store_features(X, mode, b, 512 - k, t, kF, T, lm, ipd);
+      } else {
+        s_tile[(size_t)(512 - k) * kFeatPitch + tl] = lm;
+        s_tile[(size_t)(kF + 512 - k) * kFeatPitch + tl] = ipd;
+      }
+    }
+    if (lane == 0) {
+      float lm, ipd;
+      feature_values(mid0, mid1, lm, ipd);
+      if (mode == AVZ_FEAT_PHYSICS_NHWC) {
+        store_features(X, mode, b, 256, t, kF, T, lm, ipd);
+      } else {
+        s_tile[(size_t)256 * kFeatPitch + tl] = lm;
+        s_tile[(size_t)(kF + 256) * kFeatPitch + tl] = ipd;
+      }
+    }
+  }
+  if (mode == AVZ_FEAT_PHYSICS_NHWC) return;
+  __syncthreads();
+  // rows (feature, bin) leave as runs of nt floats along T: 16 consecutive threads per row
+  const bool wrapped = (mode == AVZ_FEAT_LOGMAG_IPD_WRAPPED);
+  for (int idx = threadIdx.x; idx < 2 * kF * kFeatFrames; idx += kWarps * 32) {
+    const int row = idx / kFeatFrames, tl = idx - row * kFeatFrames;
+    if (tl < nt) {
+      float v = s_tile[(size_t)row * kFeatPitch + tl];
+      if (wrapped && row >= kF) {
+        const float two_pi = 6.28318530717958647692f;
+        v = v - two_pi * rintf(v / two_pi);
+      }
+      X[((int64_t)b * 2 * kF + row) * T + t0 + tl] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// mask-weighted covariance partial sums: part[B][chunks][5][kFP] = (R00, R11, Re R01, Im R01, sum m), un-normalised
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarps * 32, AVZ_MINB_1024)
+k1024_cov(const float* __restrict__ mix, const float* __restrict__ mask, int L, int T, int frames_per_cta, float sqrt_eps,
+          float* __restrict__ part, Tables tb512, Tables tb) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* s_wa = reinterpret_cast<float2*>(smem_raw);                        // [512]
+  float2* s_fft = s_wa + 512;                                                // [kWarps][kSmemComplex]
+  float2* s_y = s_fft + kWarps * f512::kSmemComplex;                         // [kWarps][2][kYP]
+  fill_windows(s_wa, nullptr, tb.win);
+  __syncthreads();
+  Ctx cx;
+  cx.init(tb512.tw, tb.tw);
+  const int lane = cx.ln.lane, warp = threadIdx.x >> 5;
+  float2* sm = s_fft + (size_t)warp * f512::kSmemComplex;
+  float2* Y0 = s_y + (size_t)warp * 2 * kYP;
+  float2* Y1 = Y0 + kYP;
+  const int b = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
+  const float* m0 = mix + (int64_t)b * 2 * L;
+  const float* m1 = m0 + L;
+  const float* mk = mask + (int64_t)b * kF * T;
+
+  const int c0 = chunk * frames_per_cta, c1 = min(T, c0 + frames_per_cta);
+  const int per = (c1 - c0 + kWarps - 1) / kWarps;
+  const int ta = c0 + warp * per, tb_ = min(c1, ta + per);
+
+  float acc[5][kBPL];
+#pragma unroll
+  for (int q = 0; q < 5; ++q)
+#pragma unroll
+    for (int i = 0; i < kBPL; ++i) acc[q][i] = 0.f;
+
+  float2 r0[16];
+  if (ta < tb_) load_frame(r0, m0, L, ta, lane);
+#pragma unroll 1
+  for (int t = ta; t < tb_; ++t) {
+    float2 r1[16];
+    load_frame(r1, m1, L, t, lane);
+    float wgt[kBPL];
+#pragma unroll
+    for (int i = 0; i < kBPL; ++i) {
+      const int k = lane + 32 * i;
+      wgt[i] = (k <= 512) ? 1.f - __ldg(mk + (int64_t)k * T + t) : 0.f;
+    }
+    {
+      float2 lo[8], up[8], mid;
+      analyse(r0, s_wa, sm, cx, lo, up, mid);
+      spectrum_to_smem(Y0, lo, up, mid, cx.ln);
+      analyse(r1, s_wa, sm, cx, lo, up, mid);
+      spectrum_to_smem(Y1, lo, up, mid, cx.ln);
+    }
+    if (t + 1 < tb_) load_frame(r0, m0, L, t + 1, lane);   // in flight during the accumulation below
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < kBPL; ++i) {
+      const int k = lane + 32 * i;
+      if (k <= 512) {
+        const float2 y0 = Y0[k], y1 = Y1[k];
+        const float m = wgt[i];
+        const float ms = m + sqrt_eps;
+        const float2 c01 = cmulc(y0, y1);
+        acc[0][i] = fmaf(ms, cabs2(y0), acc[0][i]);
+        acc[1][i] = fmaf(ms, cabs2(y1), acc[1][i]);
+        acc[2][i] = fmaf(ms, c01.x, acc[2][i]);
+        acc[3][i] = fmaf(ms, c01.y, acc[3][i]);
+        acc[4][i] += m;
+      }
+    }
+    __syncwarp();
+  }
+  // fixed-order reduction over the CTA's warps (bit-stable reruns); the staging area reuses the frame buffers
+  __syncthreads();
+  float* s_acc = reinterpret_cast<float*>(s_fft);   // [kWarps][5][kFP]
+#pragma unroll
+  for (int q = 0; q < 5; ++q)
+#pragma unroll
+    for (int i = 0; i < kBPL; ++i) s_acc[((size_t)warp * 5 + q) * kFP + lane + 32 * i] = acc[q][i];
+  __syncthreads();
+  float* dst = part + ((int64_t)b * chunks + chunk) * 5 * kFP;
+  for (int i = threadIdx.x; i < 5 * kFP; i += kWarps * 32) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s += s_acc[(size_t)w * 5 * kFP + i];
+    dst[i] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// beamform + post-filter + inverse + overlap-add
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarps * 32, AVZ_MINB_1024)
+k1024_apply(const float* __restrict__ mix, const float2* __restrict__ w, const float* __restrict__ mask, int gain_mode,
+            float post_floor, int L, int T, int blocks_per_cta, float* __restrict__ out, float* __restrict__ peak,
+            Tables tb512, Tables tb) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2* s_wa = reinterpret_cast<float2*>(smem_raw);                        // [512]
+  float2* s_ws = s_wa + 512;                                                 // [512]
+  float2* s_cw = s_ws + 512;                                                 // [2][kYP]: conj(w0), conj(w1)
+  float2* s_fft = s_cw + 2 * kYP;                                            // [kWarps][kSmemComplex]
+  float2* s_y = s_fft + kWarps * f512::kSmemComplex;                         // [kWarps][2][kYP]
+  __shared__ float s_peak[kWarps];
+  const int b = blockIdx.y;
+  fill_windows(s_wa, s_ws, tb.win);
+  for (int k = threadIdx.x; k < kF; k += kWarps * 32) {
+    const float2 w0 = w[((int64_t)b * kF + k) * 2 + 0];
+    const float2 w1 = w[((int64_t)b * kF + k) * 2 + 1];
+    s_cw[k] = make_float2(w0.x, -w0.y);
+    s_cw[kYP + k] = make_float2(w1.x, -w1.y);
+  }
+  __syncthreads();
+  Ctx cx;
+  cx.init(tb512.tw, tb.tw);
+  const int lane = cx.ln.lane, warp = threadIdx.x >> 5;
+  float2* sm = s_fft + (size_t)warp * f512::kSmemComplex;
+  float2* Y0 = s_y + (size_t)warp * 2 * kYP;
+  float2* Y1 = Y0 + kYP;
+  const float* m0 = mix + (int64_t)b * 2 * L;
+  const float* m1 = m0 + L;
+  const float* mk = (gain_mode == GAIN_FLOOR || gain_mode == GAIN_MASK) ? mask + (int64_t)b * kF * T : nullptr;
+  float* ob = out + (int64_t)b * (int64_t)(T - 1) * kHop;
+
+  // Output block g (1 <= g <= T-1) = second half of frame g-1 + first half of frame g, stored at (g-1) * 512.
+  const int G0 = 1 + blockIdx.x * blocks_per_cta, G1 = min(T, G0 + blocks_per_cta);
+  const int per = (G1 - G0 + kWarps - 1) / kWarps;
+  const int ga = G0 + warp * per, gb = min(G1, ga + per);
+
+  // 1 / (w[p]^2 + w[p+512]^2) is not precomputed: the reference divides, so do we (guard 1e-10 never triggers for Hann)
+  float2 tail[8];
+  float my_peak = 0.f;
+  float2 r0[16];
+  if (ga < gb) load_frame(r0, m0, L, ga - 1, lane);
+#pragma unroll 1
+  for (int t = ga - 1; t < gb && ga < gb; ++t) {
+    float2 r1[16];
+    load_frame(r1, m1, L, t, lane);
+    float gain[kBPL];
+#pragma unroll
+    for (int i = 0; i < kBPL; ++i) {
+      const int k = lane + 32 * i;
+      float g = 1.f;
+      if (mk != nullptr && k <= 512) {
+        g = __ldg(mk + (int64_t)k * T + t);
+        if (gain_mode == GAIN_FLOOR) g = fmaxf(g, post_floor);
+      }
+      gain[i] = g;
+    }
+    {
+      float2 lo[8], up[8], mid;
+      analyse(r0, s_wa, sm, cx, lo, up, mid);
+      spectrum_to_smem(Y0, lo, up, mid, cx.ln);
+      analyse(r1, s_wa, sm, cx, lo, up, mid);
+      spectrum_to_smem(Y1, lo, up, mid, cx.ln);
+    }
+    if (t + 1 < gb) load_frame(r0, m0, L, t + 1, lane);
+    __syncwarp();
+    // S[k] = conj(w0) Y0 + conj(w1) Y1, times the post-filter gain; the c2r transform ignores Im(DC), Im(Nyquist)
+#pragma unroll
+    for (int i = 0; i < kBPL; ++i) {
+      const int k = lane + 32 * i;
+      if (k <= 512) {
+        const float2 s = cadd(cmul(s_cw[k], Y0[k]), cmul(s_cw[kYP + k], Y1[k]));
+        Y0[k] = make_float2(s.x * gain[i], (k == 0 || k == 512) ? 0.f : s.y * gain[i]);
+      }
+    }
+    __syncwarp();
+    float2 v[16];
+    {
+      float2 Sa[8], Sb[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int k = cx.ln.k1 + 16 * j + 128 * cx.ln.h;
+        const float2 a = Y0[k], c = Y0[512 - k];
+        Sa[j] = make_float2(a.x + c.x, a.y - c.y);                               // S[k] + conj S[512-k]
+        Sb[j] = cmulc(make_float2(a.x - c.x, a.y + c.y), cx.wk[j]);              // (S[k] - conj S[512-k]) conj W^k
+      }
+      const float2 s256 = Y0[256];
+      f512::hermitian_pack(Sa, Sb, make_float2(2.f * s256.x, -2.f * s256.y), v, cx.ln);
+    }
+    __syncwarp();
+    f512::inverse(v, sm, cx.ln);
+    // v[r] * s_ws = irfft(S) * sum(w) * w  at samples 64 r + 2 lane, + 1
+    if (t >= ga) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const float2 wa = s_ws[32 * r + lane], wb = s_ws[32 * (r + 8) + lane];   // |.| = w / 2 (sign folded in)
+        const float2 cur = make_float2(v[r].x * wa.x, v[r].y * wa.y);
+        const float nx = 4.f * fmaf(wa.x, wa.x, wb.x * wb.x), ny = 4.f * fmaf(wa.y, wa.y, wb.y * wb.y);
+        float2 o;
+        o.x = (tail[r].x + cur.x) / (nx > 1e-10f ? nx : 1.f);
+        o.y = (tail[r].y + cur.y) / (ny > 1e-10f ? ny : 1.f);
+        *reinterpret_cast<float2*>(ob + (int64_t)(t - 1) * kHop + 64 * r + 2 * lane) = o;
+        my_peak = fmaxf(my_peak, fmaxf(fabsf(o.x), fabsf(o.y)));
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const float2 wb = s_ws[32 * (r + 8) + lane];
+      tail[r] = make_float2(v[r + 8].x * wb.x, v[r + 8].y * wb.y);
+    }
+  }
+  if (peak != nullptr) {
+    my_peak = warp_max(my_peak);
+    if (lane == 0) s_peak[warp] = my_peak;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float m = 0.f;
+#pragma unroll
+      for (int i = 0; i < kWarps; ++i) m = fmaxf(m, s_peak[i]);
+      atomicMax(reinterpret_cast<unsigned int*>(peak + b), __float_as_uint(m));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int units_per_cta(int B, int n, int sms) {
+  int per_utt = (16 * sms + B - 1) / B;   // aim at >= 16 CTAs per SM over the launch
+  if (per_utt < 1) per_utt = 1;
+  int u = (n + per_utt - 1) / per_utt;
+  if (u < 4 * kWarps) u = 4 * kWarps;
+  if (u > n) u = n;
+  return u < 1 ? 1 : u;
+}
+
+int cov_chunks1024(int B, int T) {
+  const int fpc = units_per_cta(B, T, num_sms());
+  return (T + fpc - 1) / fpc;
+}
+
+static constexpr size_t kSmemCov = (512 + (size_t)kWarps * f512::kSmemComplex + (size_t)kWarps * 2 * kYP) * sizeof(float2);
+static constexpr size_t kSmemApply = kSmemCov + (512 + 2 * (size_t)kYP) * sizeof(float2);
+static constexpr size_t kSmemFeat = (512 + (size_t)kWarps * f512::kSmemComplex) * sizeof(float2) +
+                                    2 * (size_t)kF * kFeatPitch * sizeof(float);
+static_assert(kSmemCov - 512 * sizeof(float2) >= (size_t)kWarps * 5 * kFP * sizeof(float), "reduction staging must fit");
+
+static int tables2(Tables* t512, Tables* t1024) {
+  int rc = tables_for(512, t512);
+  if (rc) return rc;
+  return tables_for(kN, t1024);
+}
+
+int launch_features(const float* mix, int B, int64_t L, int mode, float* X, cudaStream_t st) {
+  if (L >= (1ll << 31) - 2 * kN) return set_error(AVZ_EINVAL, "L too large");
+  if (B > 65535) return set_error(AVZ_EINVAL, "B > 65535");
+  Tables t5, t10;
+  int rc = tables2(&t5, &t10);
+  if (rc) return rc;
+  const int T = (int)avz_num_frames(L, kN, kHop);
+  AVZ_CUDA_OK(cudaFuncSetAttribute(k1024_features, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemFeat));
+  k1024_features<<<dim3((T + kFeatFrames - 1) / kFeatFrames, B), kWarps * 32, kSmemFeat, st>>>(mix, (int)L, T, mode, X, t5,
+                                                                                             t10);
+  AVZ_LAUNCH_OK("k1024_features");
+  return AVZ_OK;
+}
+
+int launch_mask_cov(const float* mix, const float* mask, int B, int64_t L, float sqrt_eps, float* part, int* chunks_out,
+                    cudaStream_t st) {
+  if (L >= (1ll << 31) - 2 * kN) return set_error(AVZ_EINVAL, "L too large");
+  if (B > 65535) return set_error(AVZ_EINVAL, "B > 65535");
+  Tables t5, t10;
+  int rc = tables2(&t5, &t10);
+  if (rc) return rc;
+  const int T = (int)avz_num_frames(L, kN, kHop);
+  const int fpc = units_per_cta(B, T, num_sms());
+  const int chunks = (T + fpc - 1) / fpc;
+  *chunks_out = chunks;
+  AVZ_CUDA_OK(cudaFuncSetAttribute(k1024_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCov));
+  prof_begin(PROF_COV, st);
+  k1024_cov<<<dim3(chunks, B), kWarps * 32, kSmemCov, st>>>(mix, mask, (int)L, T, fpc, sqrt_eps, part, t5, t10);
+  prof_end(PROF_COV, st);
+  AVZ_LAUNCH_OK("k1024_cov");
+  return AVZ_OK;
+}
+
+int launch_apply(const float* mix, const float* w, const float* mask, int gain_mode, float post_floor, int B, int64_t L,
+                 float* out, float* peak, cudaStream_t st) {
+  if (L >= (1ll << 31) - 2 * kN) return set_error(AVZ_EINVAL, "L too large");
+  if (B > 65535) return set_error(AVZ_EINVAL, "B > 65535");
+  Tables t5, t10;
+  int rc = tables2(&t5, &t10);
+  if (rc) return rc;
+  const int T = (int)avz_num_frames(L, kN, kHop);
+  if (T < 2) return AVZ_OK;
+  const int bpc = units_per_cta(B, T - 1, num_sms());
+  const int chunks = (T - 1 + bpc - 1) / bpc;
+  AVZ_CUDA_OK(cudaFuncSetAttribute(k1024_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemApply));
+  prof_begin(PROF_APPLY, st);
+  k1024_apply<<<dim3(chunks, B), kWarps * 32, kSmemApply, st>>>(mix, reinterpret_cast<const float2*>(w), mask, gain_mode,
+                                                              post_floor, (int)L, T, bpc, out, peak, t5, t10);
+  prof_end(PROF_APPLY, st);
+  AVZ_LAUNCH_OK("k1024_apply");
+  return AVZ_OK;
+}
+
+}  // namespace o1024
+}  // namespace avz

@@ -120,12 +120,22 @@ def test_wave_features_equal_spectrum_features(az):
     from avzoom import synth
     mix, _, _ = synth.make_batch(3, 2, 2.0, 3)
     x = torch.from_numpy(mix).cuda()
-    a = az.wave_features(x, 1024, 512)
-    b = az.logmag_ipd(az.stft(x, 1024, 512))
-    assert a.shape == b.shape == (2, 2, 513, 64)
+    # n_fft 1024 / hop 256 runs the generic kernels on both sides: same transform, same bits
+    a = az.wave_features(x, 1024, 256)
+    b = az.logmag_ipd(az.stft(x, 1024, 256))
+    assert a.shape == b.shape == (2, 2, 513, 126)
     assert torch.equal(a, b)
-    p = az.wave_features(x, 1024, 512, "physics")
-    assert torch.equal(p, az.physics_features(az.stft(x, 1024, 512)))
+    p = az.wave_features(x, 1024, 256, "physics")
+    assert torch.equal(p, az.physics_features(az.stft(x, 1024, 256)))
+    # 1024 / 512 features come from the register-resident fast path (another transform): equal up to float32 noise
+    a = az.wave_features(x, 1024, 512)
+    Y = az.stft(x, 1024, 512)
+    b = az.logmag_ipd(Y)
+    assert a.shape == b.shape == (2, 2, 513, 64)
+    strong = (Y.abs().amin(dim=1) > 1e-4 * Y.abs().amax()).cpu()
+    assert float((a[:, 0] - b[:, 0]).abs().cpu()[strong].max()) < 1e-3
+    d = (a[:, 1] - b[:, 1]).double().cpu()
+    assert float((torch.remainder(d + np.pi, 2 * np.pi) - np.pi).abs()[strong].max()) < 1e-3
 
 
 def test_fast_path_features_512(az):

@@ -1,5 +1,6 @@
-"""Timing of the generic (n_fft 1024 / hop 512) kernels the reference's learned pipelines use: 512 windows of 2 s.
-python tools/generic_probe.py"""
+"""Timing of the n_fft 1024 / hop 512 kernels the reference's learned pipelines use: 512 windows of 2 s.
+python tools/generic_probe.py                      register-resident fast path (avz_opt1024.cu)
+AVZ_FORCE_GENERIC=1 python tools/generic_probe.py  generic shared-memory FFT kernels (A/B)"""
 import os
 import sys
 
@@ -31,5 +32,6 @@ def timed(fn, iters=5):
 t_feat = timed(lambda: avzoom.wave_features(mix, cfg.n_fft, cfg.hop))
 t_mvdr = timed(lambda: avzoom.learned_mask_mvdr(mix, mask, cfg))
 audio_s = B * L / 16000.0
-print(f"1024/512 generic path, {B} x 2 s: features {t_feat:.3f} ms, learned-mask MVDR {t_mvdr:.3f} ms "
+which = "generic" if os.environ.get("AVZ_FORCE_GENERIC") == "1" else "fast"
+print(f"1024/512 {which} path, {B} x 2 s: features {t_feat:.3f} ms, learned-mask MVDR {t_mvdr:.3f} ms "
       f"-> {audio_s / ((t_feat + t_mvdr) * 1e-3) / 1e6:.3f} M audio-s/s")
