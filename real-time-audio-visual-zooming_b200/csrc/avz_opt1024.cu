@@ -38,10 +38,36 @@ constexpr int kYP = 520;      // complex elements per channel plane of the per-w
 constexpr int kFeatFrames = 16;
 constexpr int kFeatPitch = kFeatFrames + 1;
 
+constexpr int kTileFrames = 16;   // frames per CTA of the mask-reading kernels: their mask tile lives in shared memory
+constexpr int kTilePitch = kTileFrames + 1;
+
 enum { GAIN_NONE = 0, GAIN_BITS = 1, GAIN_FLOOR = 2, GAIN_MASK = 3 };   // as avz_generic.cu
 
-#ifndef AVZ_MINB_1024
-#define AVZ_MINB_1024 2
+// The caller's mask is (B, F, T): one frame's 513 values are 513 different sectors.  Each CTA therefore copies the
+// (513 x <= 16 frames) tile it needs into shared memory once, asynchronously (cp.async, 16 consecutive threads per
+// 64-byte row), and every frame then reads its weights with consecutive lanes on consecutive bins (pitch 17: no bank
+// conflicts).  The copy overlaps the first frame's transforms; tile_ready() is the wait + barrier before first use.
+__device__ __forceinline__ void stage_mask_tile(float* __restrict__ s_tile, const float* __restrict__ mk, int T, int t0,
+                                                int nt) {
+  for (int idx = threadIdx.x; idx < kF * kTileFrames; idx += kWarps * 32) {
+    const int k = idx / kTileFrames, tl = idx - k * kTileFrames;
+    if (tl < nt)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(s_tile + k * kTilePitch + tl)),
+                   "l"(mk + (int64_t)k * T + t0 + tl)
+                   : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tile_ready() {
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+}
+
+#ifndef AVZ_MINB_1024_COV
+#define AVZ_MINB_1024_COV 2
+#endif
+#ifndef AVZ_MINB_1024_APPLY
+#define AVZ_MINB_1024_APPLY 2
 #endif
 
 struct Ctx {
@@ -198,13 +224,17 @@ k1024_features(const float* __restrict__ mix, int L, int T, int mode, float* __r
 // ------------------------------------------------------------------------------------------
 // mask-weighted covariance partial sums: part[B][chunks][5][kFP] = (R00, R11, Re R01, Im R01, sum m), un-normalised
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kWarps * 32, AVZ_MINB_1024)
+__global__ void __launch_bounds__(kWarps * 32, AVZ_MINB_1024_COV)
 k1024_cov(const float* __restrict__ mix, const float* __restrict__ mask, int L, int T, int frames_per_cta, float sqrt_eps,
           float* __restrict__ part, Tables tb512, Tables tb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* s_wa = reinterpret_cast<float2*>(smem_raw);                        // [512]
   float2* s_fft = s_wa + 512;                                                // [kWarps][kSmemComplex]
   float2* s_y = s_fft + kWarps * f512::kSmemComplex;                         // [kWarps][2][kYP]
+  float* s_tile = reinterpret_cast<float*>(s_y + kWarps * 2 * kYP);          // [kF][kTilePitch]
+  const int b = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
+  const int c0 = chunk * frames_per_cta, c1 = min(T, c0 + frames_per_cta);   // frames_per_cta <= kTileFrames
+  stage_mask_tile(s_tile, mask + (int64_t)b * kF * T, T, c0, c1 - c0);
   fill_windows(s_wa, nullptr, tb.win);
   __syncthreads();
   Ctx cx;
@@ -213,12 +243,10 @@ k1024_cov(const float* __restrict__ mix, const float* __restrict__ mask, int L, 
   float2* sm = s_fft + (size_t)warp * f512::kSmemComplex;
   float2* Y0 = s_y + (size_t)warp * 2 * kYP;
   float2* Y1 = Y0 + kYP;
-  const int b = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
   const float* m0 = mix + (int64_t)b * 2 * L;
   const float* m1 = m0 + L;
-  const float* mk = mask + (int64_t)b * kF * T;
+  bool tile_pending = true;
 
-  const int c0 = chunk * frames_per_cta, c1 = min(T, c0 + frames_per_cta);
   const int per = (c1 - c0 + kWarps - 1) / kWarps;
   const int ta = c0 + warp * per, tb_ = min(c1, ta + per);
 
@@ -234,12 +262,6 @@ k1024_cov(const float* __restrict__ mix, const float* __restrict__ mask, int L, 
   for (int t = ta; t < tb_; ++t) {
     float2 r1[16];
     load_frame(r1, m1, L, t, lane);
-    float wgt[kBPL];
-#pragma unroll
-    for (int i = 0; i < kBPL; ++i) {
-      const int k = lane + 32 * i;
-      wgt[i] = (k <= 512) ? 1.f - __ldg(mk + (int64_t)k * T + t) : 0.f;
-    }
     {
       float2 lo[8], up[8], mid;
       analyse(r0, s_wa, sm, cx, lo, up, mid);
@@ -248,6 +270,16 @@ k1024_cov(const float* __restrict__ mix, const float* __restrict__ mask, int L, 
       spectrum_to_smem(Y1, lo, up, mid, cx.ln);
     }
     if (t + 1 < tb_) load_frame(r0, m0, L, t + 1, lane);   // in flight during the accumulation below
+    if (tile_pending) {
+      tile_ready();
+      tile_pending = false;
+    }
+    float wgt[kBPL];
+#pragma unroll
+    for (int i = 0; i < kBPL; ++i) {
+      const int k = lane + 32 * i;
+      wgt[i] = (k <= 512) ? 1.f - s_tile[k * kTilePitch + (t - c0)] : 0.f;
+    }
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < kBPL; ++i) {
@@ -266,6 +298,7 @@ k1024_cov(const float* __restrict__ mix, const float* __restrict__ mask, int L, 
     }
     __syncwarp();
   }
+  if (tile_pending) tile_ready();   // warps without frames still take part in the barrier
   // fixed-order reduction over the CTA's warps (bit-stable reruns); the staging area reuses the frame buffers
   __syncthreads();
   float* s_acc = reinterpret_cast<float*>(s_fft);   // [kWarps][5][kFP]
@@ -286,7 +319,7 @@ k1024_cov(const float* __restrict__ mix, const float* __restrict__ mask, int L, 
 // ------------------------------------------------------------------------------------------
 // beamform + post-filter + inverse + overlap-add
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kWarps * 32, AVZ_MINB_1024)
+__global__ void __launch_bounds__(kWarps * 32, AVZ_MINB_1024_APPLY)
 k1024_apply(const float* __restrict__ mix, const float2* __restrict__ w, const float* __restrict__ mask, int gain_mode,
             float post_floor, int L, int T, int blocks_per_cta, float* __restrict__ out, float* __restrict__ peak,
             Tables tb512, Tables tb) {
@@ -296,8 +329,15 @@ k1024_apply(const float* __restrict__ mix, const float2* __restrict__ w, const f
   float2* s_cw = s_ws + 512;                                                 // [2][kYP]: conj(w0), conj(w1)
   float2* s_fft = s_cw + 2 * kYP;                                            // [kWarps][kSmemComplex]
   float2* s_y = s_fft + kWarps * f512::kSmemComplex;                         // [kWarps][2][kYP]
+  float* s_tile = reinterpret_cast<float*>(s_y + kWarps * 2 * kYP);          // [kF][kTilePitch]
   __shared__ float s_peak[kWarps];
   const int b = blockIdx.y;
+  const bool use_mask = (gain_mode == GAIN_FLOOR || gain_mode == GAIN_MASK);
+  {
+    const int g0 = 1 + blockIdx.x * blocks_per_cta, g1 = min(T, g0 + blocks_per_cta);   // blocks_per_cta < kTileFrames
+    if (use_mask) stage_mask_tile(s_tile, mask + (int64_t)b * kF * T, T, g0 - 1, g1 - g0 + 1);
+  }
+  bool tile_pending = use_mask;
   fill_windows(s_wa, s_ws, tb.win);
   for (int k = threadIdx.x; k < kF; k += kWarps * 32) {
     const float2 w0 = w[((int64_t)b * kF + k) * 2 + 0];
@@ -314,34 +354,27 @@ k1024_apply(const float* __restrict__ mix, const float2* __restrict__ w, const f
   float2* Y1 = Y0 + kYP;
   const float* m0 = mix + (int64_t)b * 2 * L;
   const float* m1 = m0 + L;
-  const float* mk = (gain_mode == GAIN_FLOOR || gain_mode == GAIN_MASK) ? mask + (int64_t)b * kF * T : nullptr;
   float* ob = out + (int64_t)b * (int64_t)(T - 1) * kHop;
 
   // Output block g (1 <= g <= T-1) = second half of frame g-1 + first half of frame g, stored at (g-1) * 512.
+  // The CTA emits blocks [G0, G1), i.e. it transforms frames G0-1 .. G1-1, split into one run of consecutive frames
+  // per warp.  Inside a run the open half-frame stays in registers.  The first block of a run needs the last
+  // half-frame of the previous warp's run: the warp parks its own half in the output buffer, the previous warp leaves
+  // its tail in shared memory (in its spectrum buffer, dead by then), and the sum is completed after one barrier.
+  // Only the CTA's very first frame (G0-1) is a warm-up whose first half is discarded.
   const int G0 = 1 + blockIdx.x * blocks_per_cta, G1 = min(T, G0 + blocks_per_cta);
-  const int per = (G1 - G0 + kWarps - 1) / kWarps;
-  const int ga = G0 + warp * per, gb = min(G1, ga + per);
+  const int F0 = G0 - 1, nf = G1 - G0 + 1;
+  const int per = (nf + kWarps - 1) / kWarps;
+  const int fa = F0 + warp * per, fb = min(F0 + nf, fa + per);
 
-  // 1 / (w[p]^2 + w[p+512]^2) is not precomputed: the reference divides, so do we (guard 1e-10 never triggers for Hann)
   float2 tail[8];
   float my_peak = 0.f;
   float2 r0[16];
-  if (ga < gb) load_frame(r0, m0, L, ga - 1, lane);
+  if (fa < fb) load_frame(r0, m0, L, fa, lane);
 #pragma unroll 1
-  for (int t = ga - 1; t < gb && ga < gb; ++t) {
+  for (int t = fa; t < fb; ++t) {
     float2 r1[16];
     load_frame(r1, m1, L, t, lane);
-    float gain[kBPL];
-#pragma unroll
-    for (int i = 0; i < kBPL; ++i) {
-      const int k = lane + 32 * i;
-      float g = 1.f;
-      if (mk != nullptr && k <= 512) {
-        g = __ldg(mk + (int64_t)k * T + t);
-        if (gain_mode == GAIN_FLOOR) g = fmaxf(g, post_floor);
-      }
-      gain[i] = g;
-    }
     {
       float2 lo[8], up[8], mid;
       analyse(r0, s_wa, sm, cx, lo, up, mid);
@@ -349,15 +382,24 @@ k1024_apply(const float* __restrict__ mix, const float2* __restrict__ w, const f
       analyse(r1, s_wa, sm, cx, lo, up, mid);
       spectrum_to_smem(Y1, lo, up, mid, cx.ln);
     }
-    if (t + 1 < gb) load_frame(r0, m0, L, t + 1, lane);
+    if (t + 1 < fb) load_frame(r0, m0, L, t + 1, lane);
+    if (tile_pending) {
+      tile_ready();
+      tile_pending = false;
+    }
     __syncwarp();
     // S[k] = conj(w0) Y0 + conj(w1) Y1, times the post-filter gain; the c2r transform ignores Im(DC), Im(Nyquist)
 #pragma unroll
     for (int i = 0; i < kBPL; ++i) {
       const int k = lane + 32 * i;
       if (k <= 512) {
+        float g = 1.f;
+        if (use_mask) {
+          g = s_tile[k * kTilePitch + (t - F0)];
+          if (gain_mode == GAIN_FLOOR) g = fmaxf(g, post_floor);
+        }
         const float2 s = cadd(cmul(s_cw[k], Y0[k]), cmul(s_cw[kYP + k], Y1[k]));
-        Y0[k] = make_float2(s.x * gain[i], (k == 0 || k == 512) ? 0.f : s.y * gain[i]);
+        Y0[k] = make_float2(s.x * g, (k == 0 || k == 512) ? 0.f : s.y * g);
       }
     }
     __syncwarp();
@@ -377,23 +419,53 @@ k1024_apply(const float* __restrict__ mix, const float2* __restrict__ w, const f
     __syncwarp();
     f512::inverse(v, sm, cx.ln);
     // v[r] * s_ws = irfft(S) * sum(w) * w  at samples 64 r + 2 lane, + 1
-    if (t >= ga) {
+    if (t > F0) {
+      float2* dst = reinterpret_cast<float2*>(ob + (int64_t)(t - 1) * kHop) + lane;
+      if (t == fa) {   // first frame of a later warp's run: park the half-frame, completed after the barrier
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const float2 wa = s_ws[32 * r + lane], wb = s_ws[32 * (r + 8) + lane];   // |.| = w / 2 (sign folded in)
-        const float2 cur = make_float2(v[r].x * wa.x, v[r].y * wa.y);
-        const float nx = 4.f * fmaf(wa.x, wa.x, wb.x * wb.x), ny = 4.f * fmaf(wa.y, wa.y, wb.y * wb.y);
-        float2 o;
-        o.x = (tail[r].x + cur.x) / (nx > 1e-10f ? nx : 1.f);
-        o.y = (tail[r].y + cur.y) / (ny > 1e-10f ? ny : 1.f);
-        *reinterpret_cast<float2*>(ob + (int64_t)(t - 1) * kHop + 64 * r + 2 * lane) = o;
-        my_peak = fmaxf(my_peak, fmaxf(fabsf(o.x), fabsf(o.y)));
+        for (int r = 0; r < 8; ++r) {
+          const float2 wa = s_ws[32 * r + lane];
+          dst[32 * r] = make_float2(v[r].x * wa.x, v[r].y * wa.y);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const float2 wa = s_ws[32 * r + lane], wb = s_ws[32 * (r + 8) + lane];   // |.| = w / 2 (sign folded in)
+          const float2 cur = make_float2(v[r].x * wa.x, v[r].y * wa.y);
+          const float nx = 4.f * fmaf(wa.x, wa.x, wb.x * wb.x), ny = 4.f * fmaf(wa.y, wa.y, wb.y * wb.y);
+          float2 o;
+          o.x = (tail[r].x + cur.x) / (nx > 1e-10f ? nx : 1.f);
+          o.y = (tail[r].y + cur.y) / (ny > 1e-10f ? ny : 1.f);
+          dst[32 * r] = o;
+          my_peak = fmaxf(my_peak, fmaxf(fabsf(o.x), fabsf(o.y)));
+        }
       }
     }
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       const float2 wb = s_ws[32 * (r + 8) + lane];
       tail[r] = make_float2(v[r + 8].x * wb.x, v[r + 8].y * wb.y);
+    }
+  }
+  if (tile_pending) tile_ready();   // warps without frames still take part in the barrier
+  if (fa < fb) {   // this run's open half-frame, for the next warp
+#pragma unroll
+    for (int r = 0; r < 8; ++r) Y1[32 * r + lane] = tail[r];
+  }
+  __syncthreads();
+  if (fa < fb && fa > F0) {
+    const float2* prev = Y1 - 2 * kYP;   // the previous warp's buffer (its run is not empty when this one is not)
+    float2* dst = reinterpret_cast<float2*>(ob + (int64_t)(fa - 1) * kHop) + lane;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const float2 wa = s_ws[32 * r + lane], wb = s_ws[32 * (r + 8) + lane];
+      const float2 cur = dst[32 * r], tl = prev[32 * r + lane];
+      const float nx = 4.f * fmaf(wa.x, wa.x, wb.x * wb.x), ny = 4.f * fmaf(wa.y, wa.y, wb.y * wb.y);
+      float2 o;
+      o.x = (tl.x + cur.x) / (nx > 1e-10f ? nx : 1.f);
+      o.y = (tl.y + cur.y) / (ny > 1e-10f ? ny : 1.f);
+      dst[32 * r] = o;
+      my_peak = fmaxf(my_peak, fmaxf(fabsf(o.x), fabsf(o.y)));
     }
   }
   if (peak != nullptr) {
@@ -412,25 +484,28 @@ k1024_apply(const float* __restrict__ mix, const float2* __restrict__ w, const f
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-static int units_per_cta(int B, int n, int sms) {
+static int units_per_cta(int B, int n, int sms, int cap) {
   int per_utt = (16 * sms + B - 1) / B;   // aim at >= 16 CTAs per SM over the launch
   if (per_utt < 1) per_utt = 1;
   int u = (n + per_utt - 1) / per_utt;
   if (u < 4 * kWarps) u = 4 * kWarps;
+  if (u > cap) u = cap;
   if (u > n) u = n;
   return u < 1 ? 1 : u;
 }
 
 int cov_chunks1024(int B, int T) {
-  const int fpc = units_per_cta(B, T, num_sms());
+  const int fpc = units_per_cta(B, T, num_sms(), kTileFrames);
   return (T + fpc - 1) / fpc;
 }
 
-static constexpr size_t kSmemCov = (512 + (size_t)kWarps * f512::kSmemComplex + (size_t)kWarps * 2 * kYP) * sizeof(float2);
-static constexpr size_t kSmemApply = kSmemCov + (512 + 2 * (size_t)kYP) * sizeof(float2);
+static constexpr size_t kSmemFrames = (512 + (size_t)kWarps * f512::kSmemComplex + (size_t)kWarps * 2 * kYP) * sizeof(float2);
+static constexpr size_t kSmemTile = (size_t)kF * kTilePitch * sizeof(float);
+static constexpr size_t kSmemCov = kSmemFrames + kSmemTile;
+static constexpr size_t kSmemApply = kSmemFrames + (512 + 2 * (size_t)kYP) * sizeof(float2) + kSmemTile;
 static constexpr size_t kSmemFeat = (512 + (size_t)kWarps * f512::kSmemComplex) * sizeof(float2) +
                                     2 * (size_t)kF * kFeatPitch * sizeof(float);
-static_assert(kSmemCov - 512 * sizeof(float2) >= (size_t)kWarps * 5 * kFP * sizeof(float), "reduction staging must fit");
+static_assert(kSmemFrames - 512 * sizeof(float2) >= (size_t)kWarps * 5 * kFP * sizeof(float), "reduction staging must fit");
 
 static int tables2(Tables* t512, Tables* t1024) {
   int rc = tables_for(512, t512);
@@ -460,7 +535,7 @@ int launch_mask_cov(const float* mix, const float* mask, int B, int64_t L, float
   int rc = tables2(&t5, &t10);
   if (rc) return rc;
   const int T = (int)avz_num_frames(L, kN, kHop);
-  const int fpc = units_per_cta(B, T, num_sms());
+  const int fpc = units_per_cta(B, T, num_sms(), kTileFrames);
   const int chunks = (T + fpc - 1) / fpc;
   *chunks_out = chunks;
   AVZ_CUDA_OK(cudaFuncSetAttribute(k1024_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCov));
@@ -480,7 +555,10 @@ int launch_apply(const float* mix, const float* w, const float* mask, int gain_m
   if (rc) return rc;
   const int T = (int)avz_num_frames(L, kN, kHop);
   if (T < 2) return AVZ_OK;
-  const int bpc = units_per_cta(B, T - 1, num_sms());
+  // frames per CTA = blocks + 1 (one warm-up frame): keep it a multiple of the warp count so the runs are even
+  int bpc = units_per_cta(B, T - 1, num_sms(), kTileFrames - 1);
+  bpc = ((bpc + 1 + kWarps - 1) / kWarps) * kWarps - 1;   // <= kTileFrames - 1: the CTA's mask tile covers its frames
+  if (bpc > T - 1) bpc = T - 1;
   const int chunks = (T - 1 + bpc - 1) / bpc;
   AVZ_CUDA_OK(cudaFuncSetAttribute(k1024_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemApply));
   prof_begin(PROF_APPLY, st);

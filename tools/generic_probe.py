@@ -29,6 +29,15 @@ def timed(fn, iters=5):
     return a.elapsed_time(b) / iters
 
 
+from avzoom import ops  # noqa: E402
+Rp, _ = ops.wave_masked_covariance(mix, mask, cfg, None)
+wts = ops.mvdr_weights(Rp, ops.steering_vectors(cfg, mix.device), cfg)
+t_cov = timed(lambda: ops.wave_masked_covariance(mix, mask, cfg, None), 20)
+t_apply = timed(lambda: ops.mvdr_apply(mix, wts, cfg, mask=mask), 20)
+import dataclasses  # noqa: E402
+t_apply_nomask = timed(lambda: ops.mvdr_apply(mix, wts, dataclasses.replace(cfg, post="none")), 20)
+print(f"  pass B without the post-filter mask reads {t_apply_nomask:.3f} ms")
+print(f"  pass A (covariance + finalize) {t_cov:.3f} ms, pass B (apply) {t_apply:.3f} ms")
 t_feat = timed(lambda: avzoom.wave_features(mix, cfg.n_fft, cfg.hop))
 t_mvdr = timed(lambda: avzoom.learned_mask_mvdr(mix, mask, cfg))
 audio_s = B * L / 16000.0
