@@ -35,7 +35,7 @@ constexpr int kFP = 544;      // padded bins of the partial sums (Geo<1024>::FP)
 constexpr int kBPL = 17;      // bins lane + 32 i, i < 17, k <= 512
 constexpr int kWarps = 4;
 constexpr int kYP = 520;      // complex elements per channel plane of the per-warp spectrum buffer
-constexpr int kFeatFrames = 16;
+constexpr int kFeatFrames = 8;
 constexpr int kFeatPitch = kFeatFrames + 1;
 
 constexpr int kTileFrames = 16;   // frames per CTA of the mask-reading kernels: their mask tile lives in shared memory
@@ -146,78 +146,96 @@ __device__ __forceinline__ void spectrum_to_smem(float2* __restrict__ Yc, const 
   if (ln.lane == 0) Yc[256] = mid;
 }
 
+// Both channels of a frame into Y0 / Y1.  The channel loop is deliberately NOT unrolled: one copy of the transform in
+// the instruction stream instead of two (the first version of these kernels stalled on instruction fetch - ncu
+// "no_instruction" 0.5 to 4.9 stalls per issue - because three to four inlined 512-point transforms do not fit the
+// instruction cache).  ra holds channel 0 on entry and is free afterwards; rb holds channel 1.
+__device__ __forceinline__ void analyse_pair(float2 (&ra)[16], const float2 (&rb)[16], const float2* __restrict__ s_wa,
+                                             float2* __restrict__ sm, const Ctx& cx, float2* __restrict__ Y0,
+                                             float2* __restrict__ Y1) {
+#pragma unroll 1
+  for (int ch = 0; ch < 2; ++ch) {
+    float2 lo[8], up[8], mid;
+    analyse(ra, s_wa, sm, cx, lo, up, mid);
+    spectrum_to_smem(ch ? Y1 : Y0, lo, up, mid, cx.ln);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) ra[r] = rb[r];
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // features
 // ------------------------------------------------------------------------------------------
+// Persistent CTAs loop over (utterance, 8-frame tile) units: windows and lane constants are set up once per CTA.
+__device__ __forceinline__ void feature_bin(const float2* __restrict__ Y0, const float2* __restrict__ Y1, int k, int mode,
+                                            float* __restrict__ X, float* __restrict__ s_tile, int b, int t, int tl, int T) {
+  float lm, ipd;
+  feature_values(Y0[k], Y1[k], lm, ipd);
+  if (mode == AVZ_FEAT_PHYSICS_NHWC) {
+    store_features(X, mode, b, k, t, kF, T, lm, ipd);
+  } else {
+    s_tile[(size_t)k * kFeatPitch + tl] = lm;
+    s_tile[(size_t)(kF + k) * kFeatPitch + tl] = ipd;
+  }
+}
+
 __global__ void __launch_bounds__(kWarps * 32, 2)
-k1024_features(const float* __restrict__ mix, int L, int T, int mode, float* __restrict__ X, Tables tb512, Tables tb) {
+k1024_features(const float* __restrict__ mix, int L, int T, int B, int mode, float* __restrict__ X, Tables tb512,
+               Tables tb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* s_wa = reinterpret_cast<float2*>(smem_raw);                        // [512]
   float2* s_fft = s_wa + 512;                                                // [kWarps][kSmemComplex]
-  float* s_tile = reinterpret_cast<float*>(s_fft + kWarps * f512::kSmemComplex);   // [2][kF][kFeatPitch]
+  float2* s_y = s_fft + kWarps * f512::kSmemComplex;                         // [kWarps][2][kYP]
+  float* s_tile = reinterpret_cast<float*>(s_y + kWarps * 2 * kYP);          // [2][kF][kFeatPitch]
   fill_windows(s_wa, nullptr, tb.win);
   __syncthreads();
   Ctx cx;
   cx.init(tb512.tw, tb.tw);
   const int lane = cx.ln.lane, warp = threadIdx.x >> 5;
   float2* sm = s_fft + (size_t)warp * f512::kSmemComplex;
-  const int b = blockIdx.y;
-  const float* m0 = mix + (int64_t)b * 2 * L;
-  const float* m1 = m0 + L;
-  const int t0 = blockIdx.x * kFeatFrames;
-  const int nt = min(kFeatFrames, T - t0);
-  for (int tl = warp; tl < nt; tl += kWarps) {
-    const int t = t0 + tl;
-    float2 r0[16], r1[16];
-    load_frame(r0, m0, L, t, lane);
-    load_frame(r1, m1, L, t, lane);
-    float2 lo0[8], up0[8], mid0, lo1[8], up1[8], mid1;
-    analyse(r0, s_wa, sm, cx, lo0, up0, mid0);
-    analyse(r1, s_wa, sm, cx, lo1, up1, mid1);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = cx.ln.k1 + 16 * j + 128 * cx.ln.h;
-      float lm, ipd;
-      feature_values(lo0[j], lo1[j], lm, ipd);
-      if (mode == AVZ_FEAT_PHYSICS_NHWC) {
-        store_features(X, mode, b, k, t, kF, T, lm, ipd);
-      } else {
-        s_tile[(size_t)k * kFeatPitch + tl] = lm;
-        s_tile[(size_t)(kF + k) * kFeatPitch + tl] = ipd;
-      }
-      feature_values(up0[j], up1[j], lm, ipd);
-      if (mode == AVZ_FEAT_PHYSICS_NHWC) {
-        store_features(X, mode, b, 512 - k, t, kF, T, lm, ipd);
-      } else {
-        s_tile[(size_t)(512 - k) * kFeatPitch + tl] = lm;
-        s_tile[(size_t)(kF + 512 - k) * kFeatPitch + tl] = ipd;
-      }
-    }
-    if (lane == 0) {
-      float lm, ipd;
-      feature_values(mid0, mid1, lm, ipd);
-      if (mode == AVZ_FEAT_PHYSICS_NHWC) {
-        store_features(X, mode, b, 256, t, kF, T, lm, ipd);
-      } else {
-        s_tile[(size_t)256 * kFeatPitch + tl] = lm;
-        s_tile[(size_t)(kF + 256) * kFeatPitch + tl] = ipd;
-      }
-    }
-  }
-  if (mode == AVZ_FEAT_PHYSICS_NHWC) return;
-  __syncthreads();
-  // rows (feature, bin) leave as runs of nt floats along T: 16 consecutive threads per row
+  float2* Y0 = s_y + (size_t)warp * 2 * kYP;
+  float2* Y1 = Y0 + kYP;
   const bool wrapped = (mode == AVZ_FEAT_LOGMAG_IPD_WRAPPED);
-  for (int idx = threadIdx.x; idx < 2 * kF * kFeatFrames; idx += kWarps * 32) {
-    const int row = idx / kFeatFrames, tl = idx - row * kFeatFrames;
-    if (tl < nt) {
-      float v = s_tile[(size_t)row * kFeatPitch + tl];
-      if (wrapped && row >= kF) {
-        const float two_pi = 6.28318530717958647692f;
-        v = v - two_pi * rintf(v / two_pi);
+  const int tiles_per_utt = (T + kFeatFrames - 1) / kFeatFrames;
+  const int n_tiles = B * tiles_per_utt;
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int b = tile / tiles_per_utt;
+    const int t0 = (tile - b * tiles_per_utt) * kFeatFrames;
+    const int nt = min(kFeatFrames, T - t0);
+    const float* m0 = mix + (int64_t)b * 2 * L;
+    const float* m1 = m0 + L;
+#pragma unroll 1
+    for (int tl = warp; tl < nt; tl += kWarps) {
+      const int t = t0 + tl;
+      float2 r0[16], r1[16];
+      load_frame(r0, m0, L, t, lane);
+      load_frame(r1, m1, L, t, lane);
+      analyse_pair(r0, r1, s_wa, sm, cx, Y0, Y1);
+      __syncwarp();
+#pragma unroll 1
+      for (int i0 = 0; i0 < 16; i0 += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) feature_bin(Y0, Y1, lane + 32 * (i0 + u), mode, X, s_tile, b, t, tl, T);
       }
-      X[((int64_t)b * 2 * kF + row) * T + t0 + tl] = v;
+      if (lane == 0) feature_bin(Y0, Y1, 512, mode, X, s_tile, b, t, tl, T);
+      __syncwarp();
     }
+    if (mode == AVZ_FEAT_PHYSICS_NHWC) continue;
+    __syncthreads();
+    // rows (feature, bin) leave as runs of nt floats along T: kFeatFrames consecutive threads per row
+    for (int idx = threadIdx.x; idx < 2 * kF * kFeatFrames; idx += kWarps * 32) {
+      const int row = idx / kFeatFrames, tl = idx - row * kFeatFrames;
+      if (tl < nt) {
+        float v = s_tile[(size_t)row * kFeatPitch + tl];
+        if (wrapped && row >= kF) {
+          const float two_pi = 6.28318530717958647692f;
+          v = v - two_pi * rintf(v / two_pi);
+        }
+        X[((int64_t)b * 2 * kF + row) * T + t0 + tl] = v;
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -262,13 +280,7 @@ k1024_cov(const float* __restrict__ mix, const float* __restrict__ mask, int L, 
   for (int t = ta; t < tb_; ++t) {
     float2 r1[16];
     load_frame(r1, m1, L, t, lane);
-    {
-      float2 lo[8], up[8], mid;
-      analyse(r0, s_wa, sm, cx, lo, up, mid);
-      spectrum_to_smem(Y0, lo, up, mid, cx.ln);
-      analyse(r1, s_wa, sm, cx, lo, up, mid);
-      spectrum_to_smem(Y1, lo, up, mid, cx.ln);
-    }
+    analyse_pair(r0, r1, s_wa, sm, cx, Y0, Y1);
     if (t + 1 < tb_) load_frame(r0, m0, L, t + 1, lane);   // in flight during the accumulation below
     if (tile_pending) {
       tile_ready();
@@ -375,13 +387,7 @@ k1024_apply(const float* __restrict__ mix, const float2* __restrict__ w, const f
   for (int t = fa; t < fb; ++t) {
     float2 r1[16];
     load_frame(r1, m1, L, t, lane);
-    {
-      float2 lo[8], up[8], mid;
-      analyse(r0, s_wa, sm, cx, lo, up, mid);
-      spectrum_to_smem(Y0, lo, up, mid, cx.ln);
-      analyse(r1, s_wa, sm, cx, lo, up, mid);
-      spectrum_to_smem(Y1, lo, up, mid, cx.ln);
-    }
+    analyse_pair(r0, r1, s_wa, sm, cx, Y0, Y1);
     if (t + 1 < fb) load_frame(r0, m0, L, t + 1, lane);
     if (tile_pending) {
       tile_ready();
@@ -503,7 +509,7 @@ static constexpr size_t kSmemFrames = (512 + (size_t)kWarps * f512::kSmemComplex
 static constexpr size_t kSmemTile = (size_t)kF * kTilePitch * sizeof(float);
 static constexpr size_t kSmemCov = kSmemFrames + kSmemTile;
 static constexpr size_t kSmemApply = kSmemFrames + (512 + 2 * (size_t)kYP) * sizeof(float2) + kSmemTile;
-static constexpr size_t kSmemFeat = (512 + (size_t)kWarps * f512::kSmemComplex) * sizeof(float2) +
+static constexpr size_t kSmemFeat = (512 + (size_t)kWarps * f512::kSmemComplex + (size_t)kWarps * 2 * kYP) * sizeof(float2) +
                                     2 * (size_t)kF * kFeatPitch * sizeof(float);
 static_assert(kSmemFrames - 512 * sizeof(float2) >= (size_t)kWarps * 5 * kFP * sizeof(float), "reduction staging must fit");
 
@@ -521,8 +527,10 @@ int launch_features(const float* mix, int B, int64_t L, int mode, float* X, cuda
   if (rc) return rc;
   const int T = (int)avz_num_frames(L, kN, kHop);
   AVZ_CUDA_OK(cudaFuncSetAttribute(k1024_features, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemFeat));
-  k1024_features<<<dim3((T + kFeatFrames - 1) / kFeatFrames, B), kWarps * 32, kSmemFeat, st>>>(mix, (int)L, T, mode, X, t5,
-                                                                                             t10);
+  const int64_t n_tiles = (int64_t)B * ((T + kFeatFrames - 1) / kFeatFrames);
+  const int64_t resident = 2 * (int64_t)num_sms();
+  k1024_features<<<(unsigned)(n_tiles < resident ? n_tiles : resident), kWarps * 32, kSmemFeat, st>>>(mix, (int)L, T, B, mode,
+                                                                                                    X, t5, t10);
   AVZ_LAUNCH_OK("k1024_features");
   return AVZ_OK;
 }
