@@ -221,11 +221,12 @@ __device__ __forceinline__ float atan2_poly(float y, float x) {
 }
 
 // log-magnitude + inter-channel phase difference of one TF bin (full_audio.../inference.py:91-94).  The reference
-// evaluates np.abs / np.log / np.angle in float64 and casts to float32; here |.| is sqrt(x^2 + y^2), the logarithm is
+// evaluates np.abs / np.log / np.angle in float64 and casts to float32; here |.| is (x^2 + y^2) * rsq(x^2 + y^2), the logarithm is
 // the hardware lg2 (absolute error ~5e-7) and the angles come from atan2_poly: all far inside the float32 STFT noise
 // that the features of weak bins carry anyway (tests: 1e-3 on well-conditioned bins).
 __device__ __forceinline__ void feature_values(float2 y0, float2 y1, float& logmag, float& ipd) {
-  logmag = __logf(sqrtf(fmaf(y0.x, y0.x, y0.y * y0.y)) + 1e-7f);
+  const float p = fmaf(y0.x, y0.x, y0.y * y0.y);
+  logmag = __logf(p * rsqrtf(fmaxf(p, 1e-37f)) + 1e-7f);   // |y| = p / sqrt(p) (hardware rsq); p = 0 gives 0, not NaN
   ipd = atan2_poly(y0.y, y0.x) - atan2_poly(y1.y, y1.x);
 }
 

@@ -66,6 +66,9 @@ __device__ __forceinline__ void tile_ready() {
 #ifndef AVZ_MINB_1024_COV
 #define AVZ_MINB_1024_COV 2
 #endif
+#ifndef AVZ_1024_FEAT_UNROLL
+#define AVZ_1024_FEAT_UNROLL 8
+#endif
 #ifndef AVZ_MINB_1024_APPLY
 #define AVZ_MINB_1024_APPLY 2
 #endif
@@ -167,18 +170,22 @@ __device__ __forceinline__ void analyse_pair(float2 (&ra)[16], const float2 (&rb
 // features
 // ------------------------------------------------------------------------------------------
 // Persistent CTAs loop over (utterance, 8-frame tile) units: windows and lane constants are set up once per CTA.
-__device__ __forceinline__ void feature_bin(const float2* __restrict__ Y0, const float2* __restrict__ Y1, int k, int mode,
+// PHYS: the 4-channel NHWC layout of Final_pipeline/src/inference.py:117-128 (stored straight from the bin loop; its
+// sincosf lives only in that instantiation).
+template <bool PHYS>
+__device__ __forceinline__ void feature_bin(const float2* __restrict__ Y0, const float2* __restrict__ Y1, int k,
                                             float* __restrict__ X, float* __restrict__ s_tile, int b, int t, int tl, int T) {
   float lm, ipd;
   feature_values(Y0[k], Y1[k], lm, ipd);
-  if (mode == AVZ_FEAT_PHYSICS_NHWC) {
-    store_features(X, mode, b, k, t, kF, T, lm, ipd);
+  if (PHYS) {
+    store_features(X, AVZ_FEAT_PHYSICS_NHWC, b, k, t, kF, T, lm, ipd);
   } else {
-    s_tile[(size_t)k * kFeatPitch + tl] = lm;
-    s_tile[(size_t)(kF + k) * kFeatPitch + tl] = ipd;
+    s_tile[k * kFeatPitch + tl] = lm;
+    s_tile[(kF + k) * kFeatPitch + tl] = ipd;
   }
 }
 
+template <bool PHYS>
 __global__ void __launch_bounds__(kWarps * 32, 2)
 k1024_features(const float* __restrict__ mix, int L, int T, int B, int mode, float* __restrict__ X, Tables tb512,
                Tables tb) {
@@ -214,14 +221,15 @@ k1024_features(const float* __restrict__ mix, int L, int T, int B, int mode, flo
       analyse_pair(r0, r1, s_wa, sm, cx, Y0, Y1);
       __syncwarp();
 #pragma unroll 1
-      for (int i0 = 0; i0 < 16; i0 += 4) {
+      for (int i0 = 0; i0 < 16; i0 += AVZ_1024_FEAT_UNROLL) {   // independent bins in flight: the per-bin chain is long
 #pragma unroll
-        for (int u = 0; u < 4; ++u) feature_bin(Y0, Y1, lane + 32 * (i0 + u), mode, X, s_tile, b, t, tl, T);
+        for (int u = 0; u < AVZ_1024_FEAT_UNROLL; ++u)
+          feature_bin<PHYS>(Y0, Y1, lane + 32 * (i0 + u), X, s_tile, b, t, tl, T);
       }
-      if (lane == 0) feature_bin(Y0, Y1, 512, mode, X, s_tile, b, t, tl, T);
+      if (lane == 0) feature_bin<PHYS>(Y0, Y1, 512, X, s_tile, b, t, tl, T);
       __syncwarp();
     }
-    if (mode == AVZ_FEAT_PHYSICS_NHWC) continue;
+    if (PHYS) continue;
     __syncthreads();
     // rows (feature, bin) leave as runs of nt floats along T: kFeatFrames consecutive threads per row
     for (int idx = threadIdx.x; idx < 2 * kF * kFeatFrames; idx += kWarps * 32) {
@@ -526,11 +534,15 @@ int launch_features(const float* mix, int B, int64_t L, int mode, float* X, cuda
   int rc = tables2(&t5, &t10);
   if (rc) return rc;
   const int T = (int)avz_num_frames(L, kN, kHop);
-  AVZ_CUDA_OK(cudaFuncSetAttribute(k1024_features, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemFeat));
+  AVZ_CUDA_OK(cudaFuncSetAttribute(k1024_features<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemFeat));
+  AVZ_CUDA_OK(cudaFuncSetAttribute(k1024_features<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemFeat));
   const int64_t n_tiles = (int64_t)B * ((T + kFeatFrames - 1) / kFeatFrames);
   const int64_t resident = 2 * (int64_t)num_sms();
-  k1024_features<<<(unsigned)(n_tiles < resident ? n_tiles : resident), kWarps * 32, kSmemFeat, st>>>(mix, (int)L, T, B, mode,
-                                                                                                    X, t5, t10);
+  const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
+  if (mode == AVZ_FEAT_PHYSICS_NHWC)
+    k1024_features<true><<<grid, kWarps * 32, kSmemFeat, st>>>(mix, (int)L, T, B, mode, X, t5, t10);
+  else
+    k1024_features<false><<<grid, kWarps * 32, kSmemFeat, st>>>(mix, (int)L, T, B, mode, X, t5, t10);
   AVZ_LAUNCH_OK("k1024_features");
   return AVZ_OK;
 }

@@ -12,7 +12,7 @@ from avzoom import synth  # noqa: E402
 from avzoom.core import models  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 10   # the first iterations pay for the 264 MB output buffers
 cfg = avzoom.PRESETS["baseline_learned"]
 mix8, _, _ = synth.make_batch(3, 8, 4.0, 3)
 mix = torch.from_numpy(mix8).cuda().repeat((B + 7) // 8, 1, 1)[:B].contiguous()
