@@ -300,18 +300,38 @@ k_cov(const float* __restrict__ mix, const float* __restrict__ tgt, const float*
   }
 }
 
-// Sum the chunk partials (float64), normalise: R = sum / (sum m + norm_eps).
-__global__ void k_cov_finalize(const float* __restrict__ part, int B, int F, int FP, int chunks, float norm_eps,
-                               float4* __restrict__ R, float* __restrict__ msum) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * F) return;
-  const int b = idx / F, k = idx - b * F;
+// Sum the chunk partials (float64), normalise: R = sum / (sum m + norm_eps).  The kernel is a pure load-latency chain
+// per thread, so the chunks of a bin are split over kFinSlices threads (slice s takes chunks s, s + kFinSlices, ...)
+// whose float64 sums meet in shared memory in a fixed order: reruns stay bit-identical.
+constexpr int kFinSlices = 4;
+constexpr int kFinBins = 64;
+__global__ void __launch_bounds__(kFinBins * kFinSlices)
+k_cov_finalize(const float* __restrict__ part, int B, int F, int FP, int chunks, float norm_eps,
+               float4* __restrict__ R, float* __restrict__ msum) {
+  __shared__ double s_sum[kFinSlices][5][kFinBins];
+  const int lane64 = threadIdx.x & (kFinBins - 1), slice = threadIdx.x / kFinBins;
+  const int idx = blockIdx.x * kFinBins + lane64;
+  const bool ok = idx < B * F;
+  const int b = ok ? idx / F : 0, k = ok ? idx - b * F : 0;
   double s[5] = {0, 0, 0, 0, 0};
-#pragma unroll 4   // independent loads: keep several chunks in flight (the kernel is pure load latency)
-  for (int c = 0; c < chunks; ++c) {
-    const float* p = part + ((int64_t)b * chunks + c) * 5 * FP;
+  if (ok) {
+#pragma unroll 4   // independent loads: keep several chunks in flight
+    for (int c = slice; c < chunks; c += kFinSlices) {
+      const float* p = part + ((int64_t)b * chunks + c) * 5 * FP;
 #pragma unroll
-    for (int j = 0; j < 5; ++j) s[j] += (double)p[j * FP + k];
+      for (int j = 0; j < 5; ++j) s[j] += (double)p[j * FP + k];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 5; ++j) s_sum[slice][j][lane64] = s[j];
+  __syncthreads();
+  if (slice != 0 || !ok) return;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    double t = s_sum[0][j][lane64];
+#pragma unroll
+    for (int q = 1; q < kFinSlices; ++q) t += s_sum[q][j][lane64];
+    s[j] = t;
   }
   const double inv = 1.0 / (s[4] + (double)norm_eps);
   R[idx] = make_float4((float)(s[0] * inv), (float)(s[1] * inv), (float)(s[2] * inv), (float)(s[3] * inv));
@@ -550,7 +570,7 @@ static int launch_cov(const float* mix, const float* tgt, const float* itf, cons
                                                          (float*)ws, tb);
   AVZ_LAUNCH_OK("k_cov");
   const int F = Geo<N>::F;
-  k_cov_finalize<<<(B * F + 63) / 64, 64, 0, st>>>((const float*)ws, B, F, Geo<N>::FP, chunks, norm_eps,
+  k_cov_finalize<<<(B * F + kFinBins - 1) / kFinBins, kFinBins * kFinSlices, 0, st>>>((const float*)ws, B, F, Geo<N>::FP, chunks, norm_eps,
                                                       reinterpret_cast<float4*>(R), msum);
   AVZ_LAUNCH_OK("k_cov_finalize");
   return AVZ_OK;
@@ -567,7 +587,7 @@ static int launch_cov512(const float* mix, const float* tgt, const float* itf, c
   if (rc) return rc;
   const int F = 257;
   prof_begin(PROF_FINALIZE, st);
-  k_cov_finalize<<<(B * F + 63) / 64, 64, 0, st>>>((const float*)ws, B, F, Geo<512>::FP, chunks, norm_eps,
+  k_cov_finalize<<<(B * F + kFinBins - 1) / kFinBins, kFinBins * kFinSlices, 0, st>>>((const float*)ws, B, F, Geo<512>::FP, chunks, norm_eps,
                                                       reinterpret_cast<float4*>(R), msum);
   prof_end(PROF_FINALIZE, st);
   AVZ_LAUNCH_OK("k_cov_finalize");
@@ -699,7 +719,7 @@ int avz_wave_mask_cov_f32(const float* mix, const float* mask, int B, int64_t L,
     int chunks = 0;
     rc = o1024::launch_mask_cov(mix, mask, B, L, sqrt_eps, (float*)ws, &chunks, (cudaStream_t)stream);
     if (rc) return rc;
-    k_cov_finalize<<<(B * 513 + 63) / 64, 64, 0, (cudaStream_t)stream>>>((const float*)ws, B, 513, Geo<1024>::FP, chunks,
+    k_cov_finalize<<<(B * 513 + kFinBins - 1) / kFinBins, kFinBins * kFinSlices, 0, (cudaStream_t)stream>>>((const float*)ws, B, 513, Geo<1024>::FP, chunks,
                                                                          norm_eps, reinterpret_cast<float4*>(R), msum);
     AVZ_LAUNCH_OK("k_cov_finalize");
     return AVZ_OK;
