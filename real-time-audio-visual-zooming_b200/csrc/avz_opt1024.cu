@@ -231,8 +231,27 @@ k1024_features(const float* __restrict__ mix, int L, int T, int B, int mode, flo
     }
     if (PHYS) continue;
     __syncthreads();
-    // rows (feature, bin) leave as runs of nt floats along T: kFeatFrames consecutive threads per row
-    for (int idx = threadIdx.x; idx < 2 * kF * kFeatFrames; idx += kWarps * 32) {
+    // rows (feature, bin) leave as runs along T.  Full tiles with 16-byte-aligned rows: two threads per row, one
+    // float4 each (a warp writes 16 whole sectors per instruction; the scalar loop below cost 800 instructions per
+    // frame - a fifth of the kernel); ragged tiles / odd T: kFeatFrames consecutive threads per row.
+    const bool vec = (nt == kFeatFrames) && ((T & 3) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+    static_assert(kFeatFrames == 8, "the vector store path assumes two float4 per row");
+    if (vec) {
+      for (int idx = threadIdx.x; idx < 2 * kF * 2; idx += kWarps * 32) {
+        const int row = idx >> 1, half = idx & 1;
+        const float* src = s_tile + row * kFeatPitch + 4 * half;
+        float4 v = make_float4(src[0], src[1], src[2], src[3]);
+        if (wrapped && row >= kF) {
+          const float two_pi = 6.28318530717958647692f;
+          v.x -= two_pi * rintf(v.x / two_pi);
+          v.y -= two_pi * rintf(v.y / two_pi);
+          v.z -= two_pi * rintf(v.z / two_pi);
+          v.w -= two_pi * rintf(v.w / two_pi);
+        }
+        *reinterpret_cast<float4*>(X + ((int64_t)b * 2 * kF + row) * T + t0 + 4 * half) = v;
+      }
+    }
+    for (int idx = vec ? 2 * kF * kFeatFrames : threadIdx.x; idx < 2 * kF * kFeatFrames; idx += kWarps * 32) {
       const int row = idx / kFeatFrames, tl = idx - row * kFeatFrames;
       if (tl < nt) {
         float v = s_tile[(size_t)row * kFeatPitch + tl];
