@@ -37,10 +37,11 @@ int launch_apply(const float* mix, const void* spec, const float* w, const uint3
 namespace o1024 {
 int cov_chunks1024(int B, int T);
 int launch_features(const float* mix, int B, int64_t L, int mode, float* X, cudaStream_t st);
+int64_t spec_ws_bytes1024(int B, int T);
 int launch_mask_cov(const float* mix, const float* mask, int B, int64_t L, float sqrt_eps, float* part, int* chunks_out,
-                    cudaStream_t st);
-int launch_apply(const float* mix, const float* w, const float* mask, int gain_mode, float post_floor, int B, int64_t L,
-                 float* out, float* peak, cudaStream_t st);
+                    void* spec, cudaStream_t st);
+int launch_apply(const float* mix, const void* spec, const float* w, const float* mask, int gain_mode, float post_floor,
+                 int B, int64_t L, float* out, float* peak, cudaStream_t st);
 }  // namespace o1024
 
 // The register-resident 512-point path serves n_fft 512 with hop 128 / 256 unless AVZ_FORCE_GENERIC=1
@@ -706,6 +707,17 @@ int avz_ibm_exact_f32(const float* tgt, const float* itf, int B, int64_t L, int 
   return o512::launch_ibm_exact(tgt, itf, B, L, hop, ibm_bits, ws16, (cudaStream_t)stream);
 }
 
+static int mask_cov1024(const float* mix, const float* mask, int B, int64_t L, float sqrt_eps, float norm_eps, float* R,
+                        float* msum, void* ws, void* spec, cudaStream_t st) {
+  int chunks = 0;
+  int rc = o1024::launch_mask_cov(mix, mask, B, L, sqrt_eps, (float*)ws, &chunks, spec, st);
+  if (rc) return rc;
+  k_cov_finalize<<<(B * 513 + kFinBins - 1) / kFinBins, kFinBins * kFinSlices, 0, st>>>(
+      (const float*)ws, B, 513, Geo<1024>::FP, chunks, norm_eps, reinterpret_cast<float4*>(R), msum);
+  AVZ_LAUNCH_OK("k_cov_finalize");
+  return AVZ_OK;
+}
+
 int avz_wave_mask_cov_f32(const float* mix, const float* mask, int B, int64_t L, int n_fft, int hop, float sqrt_eps,
                           float norm_eps, float* R, float* msum, void* ws, void* stream) {
   if (!mix || !mask || !R || !msum || !ws || B <= 0)
@@ -715,22 +727,17 @@ int avz_wave_mask_cov_f32(const float* mix, const float* mask, int B, int64_t L,
   if (use_opt512(n_fft, hop))
     return launch_cov512(mix, nullptr, nullptr, mask, B, L, hop, sqrt_eps, norm_eps, nullptr, R, msum, ws, nullptr,
                          (cudaStream_t)stream);
-  if (use_opt1024(n_fft, hop)) {
-    int chunks = 0;
-    rc = o1024::launch_mask_cov(mix, mask, B, L, sqrt_eps, (float*)ws, &chunks, (cudaStream_t)stream);
-    if (rc) return rc;
-    k_cov_finalize<<<(B * 513 + kFinBins - 1) / kFinBins, kFinBins * kFinSlices, 0, (cudaStream_t)stream>>>((const float*)ws, B, 513, Geo<1024>::FP, chunks,
-                                                                         norm_eps, reinterpret_cast<float4*>(R), msum);
-    AVZ_LAUNCH_OK("k_cov_finalize");
-    return AVZ_OK;
-  }
+  if (use_opt1024(n_fft, hop))
+    return mask_cov1024(mix, mask, B, L, sqrt_eps, norm_eps, R, msum, ws, nullptr, (cudaStream_t)stream);
   AVZ_DISPATCH_N(n_fft, (launch_cov<N_, COV_MASK>(mix, nullptr, nullptr, mask, B, L, hop, sqrt_eps, norm_eps, nullptr,
                                                   R, msum, ws, (cudaStream_t)stream)));
 }
 
 // ---- "kept spectrum" variants of the fused passes (n_fft 512 fast path only) ---------------------------------
 int64_t avz_spec_ws_bytes(int B, int64_t L, int n_fft, int hop) {
-  if (B <= 0 || check_fft_args(n_fft, hop, L) || !use_opt512(n_fft, hop)) return 0;
+  if (B <= 0 || check_fft_args(n_fft, hop, L)) return 0;
+  if (use_opt1024(n_fft, hop)) return o1024::spec_ws_bytes1024(B, (int)avz_num_frames(L, n_fft, hop));
+  if (!use_opt512(n_fft, hop)) return 0;
   return o512::spec_ws_bytes512(B, (int)avz_num_frames(L, n_fft, hop));
 }
 
@@ -751,7 +758,10 @@ int avz_wave_mask_cov_keep_f32(const float* mix, const float* mask, int B, int64
     return set_error(AVZ_EINVAL, "avz_wave_mask_cov_keep_f32: null pointer or empty batch");
   int rc = check_fft_args(n_fft, hop, L);
   if (rc) return rc;
-  if (!use_opt512(n_fft, hop)) return set_error(AVZ_EINVAL, "avz_wave_mask_cov_keep_f32: n_fft 512, hop 128/256 only");
+  if (use_opt1024(n_fft, hop))
+    return mask_cov1024(mix, mask, B, L, sqrt_eps, norm_eps, R, msum, ws, spec, (cudaStream_t)stream);
+  if (!use_opt512(n_fft, hop))
+    return set_error(AVZ_EINVAL, "avz_wave_mask_cov_keep_f32: n_fft 512 (hop 128/256) or 1024 (hop 512) only");
   return launch_cov512(mix, nullptr, nullptr, mask, B, L, hop, sqrt_eps, norm_eps, nullptr, R, msum, ws, spec,
                        (cudaStream_t)stream);
 }
@@ -763,7 +773,9 @@ static int apply_kept(const void* spec, const float* w, const uint32_t* ibm_bits
     return set_error(AVZ_EINVAL, "avz_mvdr_apply_kept_f32: null pointer or empty batch");
   int rc = check_fft_args(n_fft, hop, L);
   if (rc) return rc;
-  if (!use_opt512(n_fft, hop)) return set_error(AVZ_EINVAL, "avz_mvdr_apply_kept_f32: n_fft 512, hop 128/256 only");
+  const bool fast1024 = use_opt1024(n_fft, hop);
+  if (!fast1024 && !use_opt512(n_fft, hop))
+    return set_error(AVZ_EINVAL, "avz_mvdr_apply_kept_f32: n_fft 512 (hop 128/256) or 1024 (hop 512) only");
   int gain = GAIN_NONE;
   switch (cfg->post_mode) {
     case AVZ_POST_NONE: gain = GAIN_NONE; break;
@@ -777,6 +789,11 @@ static int apply_kept(const void* spec, const float* w, const uint32_t* ibm_bits
       gain = cfg->post_mode == AVZ_POST_FLOOR ? GAIN_FLOOR : GAIN_MASK;
       break;
     default: return set_error(AVZ_EINVAL, "post_mode=%d unknown", cfg->post_mode);
+  }
+  if (fast1024) {
+    if (gain == GAIN_BITS || fuse_norm)
+      return set_error(AVZ_EINVAL, "avz_mvdr_apply_kept_f32: n_fft 1024 takes float masks only, no fused normalisation");
+    return o1024::launch_apply(nullptr, spec, w, mask, gain, cfg->post_floor, B, L, out, peak, (cudaStream_t)stream);
   }
   return (hop == 128) ? o512::launch_apply<128>(nullptr, spec, w, ibm_bits, mask, gain, cfg->post_floor, B, L, out, peak,
                                                 fuse_norm, peak_eps, (cudaStream_t)stream)
@@ -837,7 +854,7 @@ int avz_mvdr_apply_f32(const float* mix, const float* w, const uint32_t* ibm_bit
                                                   0, 0.f, (cudaStream_t)stream);
   }
   if (use_opt1024(n_fft, hop) && gain != GAIN_BITS)
-    return o1024::launch_apply(mix, w, mask, gain, cfg->post_floor, B, L, out, peak, (cudaStream_t)stream);
+    return o1024::launch_apply(mix, nullptr, w, mask, gain, cfg->post_floor, B, L, out, peak, (cudaStream_t)stream);
   AVZ_DISPATCH_N(n_fft, (launch_synth<N_, SRC_MIX>(mix, nullptr, w, ibm_bits, mask, gain, cfg->post_floor, B, L, T, hop,
                                                    out, peak, (cudaStream_t)stream)));
 }

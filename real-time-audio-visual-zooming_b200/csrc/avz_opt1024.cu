@@ -269,9 +269,12 @@ k1024_features(const float* __restrict__ mix, int L, int T, int B, int mode, flo
 // ------------------------------------------------------------------------------------------
 // mask-weighted covariance partial sums: part[B][chunks][5][kFP] = (R00, R11, Re R01, Im R01, sum m), un-normalised
 // ------------------------------------------------------------------------------------------
+// KEEP: both one-sided spectra of every frame are also written to `spec` ([B][T][2][kYP] complex, natural bin order,
+// 8320 B per frame = 16 B per sample) so that pass B starts from them instead of transforming the waveform again.
+template <bool KEEP>
 __global__ void __launch_bounds__(kWarps * 32, AVZ_MINB_1024_COV)
 k1024_cov(const float* __restrict__ mix, const float* __restrict__ mask, int L, int T, int frames_per_cta, float sqrt_eps,
-          float* __restrict__ part, Tables tb512, Tables tb) {
+          float* __restrict__ part, float2* __restrict__ spec, Tables tb512, Tables tb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* s_wa = reinterpret_cast<float2*>(smem_raw);                        // [512]
   float2* s_fft = s_wa + 512;                                                // [kWarps][kSmemComplex]
@@ -325,6 +328,11 @@ k1024_cov(const float* __restrict__ mix, const float* __restrict__ mask, int L, 
       const int k = lane + 32 * i;
       if (k <= 512) {
         const float2 y0 = Y0[k], y1 = Y1[k];
+        if (KEEP) {
+          float2* sp = spec + ((int64_t)b * T + t) * 2 * kYP;
+          __stcs(sp + k, y0);
+          __stcs(sp + kYP + k, y1);
+        }
         const float m = wgt[i];
         const float ms = m + sqrt_eps;
         const float2 c01 = cmulc(y0, y1);
@@ -358,8 +366,11 @@ k1024_cov(const float* __restrict__ mix, const float* __restrict__ mask, int L, 
 // ------------------------------------------------------------------------------------------
 // beamform + post-filter + inverse + overlap-add
 // ------------------------------------------------------------------------------------------
+// KEPT: the spectra come from `spec` (written by k1024_cov<true>) instead of two forward transforms; the arithmetic
+// after that point is the same code, so both variants give bit-identical waveforms.
+template <bool KEPT>
 __global__ void __launch_bounds__(kWarps * 32, AVZ_MINB_1024_APPLY)
-k1024_apply(const float* __restrict__ mix, const float2* __restrict__ w, const float* __restrict__ mask, int gain_mode,
+k1024_apply(const float* __restrict__ mix, const float2* __restrict__ spec, const float2* __restrict__ w, const float* __restrict__ mask, int gain_mode,
             float post_floor, int L, int T, int blocks_per_cta, float* __restrict__ out, float* __restrict__ peak,
             Tables tb512, Tables tb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -408,14 +419,29 @@ k1024_apply(const float* __restrict__ mix, const float2* __restrict__ w, const f
 
   float2 tail[8];
   float my_peak = 0.f;
-  float2 r0[16];
-  if (fa < fb) load_frame(r0, m0, L, fa, lane);
+  float2 r0[16];                 // !KEPT: channel 0 of the frame to come
+  float2 ya[kBPL], yb[kBPL];     // KEPT: both spectra of the frame to come, bins lane + 32 i
+  auto load_kept = [&](int t) {
+    const float2* sp = spec + ((int64_t)b * T + t) * 2 * kYP + lane;
+#pragma unroll
+    for (int i = 0; i < kBPL; ++i) {
+      const bool ok = (i < kBPL - 1) || lane == 0;
+      ya[i] = ok ? __ldcs(sp + 32 * i) : make_float2(0.f, 0.f);
+      yb[i] = ok ? __ldcs(sp + kYP + 32 * i) : make_float2(0.f, 0.f);
+    }
+  };
+  if (fa < fb) {
+    if (KEPT) load_kept(fa);
+    else load_frame(r0, m0, L, fa, lane);
+  }
 #pragma unroll 1
   for (int t = fa; t < fb; ++t) {
-    float2 r1[16];
-    load_frame(r1, m1, L, t, lane);
-    analyse_pair(r0, r1, s_wa, sm, cx, Y0, Y1);
-    if (t + 1 < fb) load_frame(r0, m0, L, t + 1, lane);
+    if (!KEPT) {
+      float2 r1[16];
+      load_frame(r1, m1, L, t, lane);
+      analyse_pair(r0, r1, s_wa, sm, cx, Y0, Y1);
+      if (t + 1 < fb) load_frame(r0, m0, L, t + 1, lane);
+    }
     if (tile_pending) {
       tile_ready();
       tile_pending = false;
@@ -431,10 +457,12 @@ k1024_apply(const float* __restrict__ mix, const float2* __restrict__ w, const f
           g = s_tile[k * kTilePitch + (t - F0)];
           if (gain_mode == GAIN_FLOOR) g = fmaxf(g, post_floor);
         }
-        const float2 s = cadd(cmul(s_cw[k], Y0[k]), cmul(s_cw[kYP + k], Y1[k]));
+        const float2 y0 = KEPT ? ya[i] : Y0[k], y1 = KEPT ? yb[i] : Y1[k];
+        const float2 s = cadd(cmul(s_cw[k], y0), cmul(s_cw[kYP + k], y1));
         Y0[k] = make_float2(s.x * g, (k == 0 || k == 512) ? 0.f : s.y * g);
       }
     }
+    if (KEPT && t + 1 < fb) load_kept(t + 1);   // in flight during the inverse transform below
     __syncwarp();
     float2 v[16];
     {
@@ -566,8 +594,10 @@ int launch_features(const float* mix, int B, int64_t L, int mode, float* X, cuda
   return AVZ_OK;
 }
 
+int64_t spec_ws_bytes1024(int B, int T) { return (int64_t)B * T * 2 * kYP * (int64_t)sizeof(float2); }
+
 int launch_mask_cov(const float* mix, const float* mask, int B, int64_t L, float sqrt_eps, float* part, int* chunks_out,
-                    cudaStream_t st) {
+                    void* spec, cudaStream_t st) {
   if (L >= (1ll << 31) - 2 * kN) return set_error(AVZ_EINVAL, "L too large");
   if (B > 65535) return set_error(AVZ_EINVAL, "B > 65535");
   Tables t5, t10;
@@ -577,16 +607,22 @@ int launch_mask_cov(const float* mix, const float* mask, int B, int64_t L, float
   const int fpc = units_per_cta(B, T, num_sms(), kTileFrames);
   const int chunks = (T + fpc - 1) / fpc;
   *chunks_out = chunks;
-  AVZ_CUDA_OK(cudaFuncSetAttribute(k1024_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCov));
+  AVZ_CUDA_OK(cudaFuncSetAttribute(k1024_cov<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCov));
+  AVZ_CUDA_OK(cudaFuncSetAttribute(k1024_cov<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCov));
   prof_begin(PROF_COV, st);
-  k1024_cov<<<dim3(chunks, B), kWarps * 32, kSmemCov, st>>>(mix, mask, (int)L, T, fpc, sqrt_eps, part, t5, t10);
+  if (spec)
+    k1024_cov<true><<<dim3(chunks, B), kWarps * 32, kSmemCov, st>>>(mix, mask, (int)L, T, fpc, sqrt_eps, part,
+                                                                    (float2*)spec, t5, t10);
+  else
+    k1024_cov<false><<<dim3(chunks, B), kWarps * 32, kSmemCov, st>>>(mix, mask, (int)L, T, fpc, sqrt_eps, part, nullptr,
+                                                                     t5, t10);
   prof_end(PROF_COV, st);
   AVZ_LAUNCH_OK("k1024_cov");
   return AVZ_OK;
 }
 
-int launch_apply(const float* mix, const float* w, const float* mask, int gain_mode, float post_floor, int B, int64_t L,
-                 float* out, float* peak, cudaStream_t st) {
+int launch_apply(const float* mix, const void* spec, const float* w, const float* mask, int gain_mode, float post_floor,
+                 int B, int64_t L, float* out, float* peak, cudaStream_t st) {
   if (L >= (1ll << 31) - 2 * kN) return set_error(AVZ_EINVAL, "L too large");
   if (B > 65535) return set_error(AVZ_EINVAL, "B > 65535");
   Tables t5, t10;
@@ -599,10 +635,16 @@ int launch_apply(const float* mix, const float* w, const float* mask, int gain_m
   bpc = ((bpc + 1 + kWarps - 1) / kWarps) * kWarps - 1;   // <= kTileFrames - 1: the CTA's mask tile covers its frames
   if (bpc > T - 1) bpc = T - 1;
   const int chunks = (T - 1 + bpc - 1) / bpc;
-  AVZ_CUDA_OK(cudaFuncSetAttribute(k1024_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemApply));
+  AVZ_CUDA_OK(cudaFuncSetAttribute(k1024_apply<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemApply));
+  AVZ_CUDA_OK(cudaFuncSetAttribute(k1024_apply<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemApply));
   prof_begin(PROF_APPLY, st);
-  k1024_apply<<<dim3(chunks, B), kWarps * 32, kSmemApply, st>>>(mix, reinterpret_cast<const float2*>(w), mask, gain_mode,
-                                                              post_floor, (int)L, T, bpc, out, peak, t5, t10);
+  if (spec)
+    k1024_apply<true><<<dim3(chunks, B), kWarps * 32, kSmemApply, st>>>(
+        nullptr, reinterpret_cast<const float2*>(spec), reinterpret_cast<const float2*>(w), mask, gain_mode, post_floor,
+        (int)L, T, bpc, out, peak, t5, t10);
+  else
+    k1024_apply<false><<<dim3(chunks, B), kWarps * 32, kSmemApply, st>>>(
+        mix, nullptr, reinterpret_cast<const float2*>(w), mask, gain_mode, post_floor, (int)L, T, bpc, out, peak, t5, t10);
   prof_end(PROF_APPLY, st);
   AVZ_LAUNCH_OK("k1024_apply");
   return AVZ_OK;

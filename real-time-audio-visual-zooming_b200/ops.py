@@ -393,13 +393,17 @@ def float_to_pcm16(x: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------ fused passes
-def alloc_kept_spectrum(mix: torch.Tensor, cfg: MvdrConfig) -> Optional[torch.Tensor]:
-    """Workspace in which pass A keeps the packed mix spectrum for pass B (fast path shapes only, else None)."""
+def alloc_kept_spectrum(mix: torch.Tensor, cfg: MvdrConfig, ibm: bool = False) -> Optional[torch.Tensor]:
+    """Workspace in which pass A keeps the mix spectrum for pass B (fast path shapes only, else None).
+    `ibm`: for the oracle-IBM pass A, which keeps a spectrum at n_fft 512 only (the learned-mask pass A also does at
+    n_fft 1024 / hop 512)."""
     B, _, L = mix.shape
+    if ibm and cfg.n_fft != 512:
+        return None
     n = _lib.load().avz_spec_ws_bytes(B, L, cfg.n_fft, cfg.hop)
     if n <= 0:
         return None
-    # ~34 bytes per input sample.  If it does not fit, pass B recomputes the transform instead (bit-identical result,
+    # ~34 bytes per input sample (n_fft 512; 16 at n_fft 1024).  If it does not fit, pass B recomputes the transform instead (bit-identical result,
     # ~8 % slower): huge batches degrade gracefully instead of running out of memory.  (No cudaMemGetInfo here: it
     # costs milliseconds per call and does not see the blocks torch's caching allocator can reuse.)
     try:
@@ -505,7 +509,7 @@ def oracle_mask_mvdr(mix, tgt, itf, cfg: MvdrConfig = PRESETS["baseline_oracle"]
     utterance when cfg.peak_eps is not None)."""
     io = _Io()
     mix, tgt, itf, single = _batchify(mix, tgt, itf, io)
-    spec = alloc_kept_spectrum(mix, cfg)
+    spec = alloc_kept_spectrum(mix, cfg, ibm=True)
     bits, Rp, ms = ibm_covariance(mix, tgt, itf, cfg, spec)
     w = mvdr_weights(Rp, steering_vectors(cfg, mix.device), cfg)
     out, peak = mvdr_apply(mix, w, cfg, ibm_bits=bits if cfg.post == "one_minus_noise" else None, spec=spec)

@@ -42,7 +42,7 @@ class OracleMvdr:
             _lib.check(-1, "avz_ibm_cov_ws_bytes")
         self.ws = torch.empty((max(int(nws), 4),), dtype=torch.uint8, device=device)
         # pass A may keep the packed mix spectrum so that pass B skips its forward transform (fast path only)
-        nspec = self.lib.avz_spec_ws_bytes(B, L, cfg.n_fft, cfg.hop) if keep_spectrum else 0
+        nspec = self.lib.avz_spec_ws_bytes(B, L, cfg.n_fft, cfg.hop) if keep_spectrum and cfg.n_fft == 512 else 0
         self.spec = torch.empty((int(nspec),), dtype=torch.uint8, device=device) if nspec > 0 else None
         # fused_norm: the thread blocks of an utterance run as one cluster, exchange their maxima through distributed
         # shared memory and each rescales the range it has just written while it is still in L2 (one launch less,

@@ -86,6 +86,16 @@ def test_learned_mask_mvdr_1024(az, preset, dur):
         assert rel_l2(out[b], ref) < WAVE_TOL
     # reruns are bit-identical (fixed-order reductions, no float atomics)
     assert np.array_equal(az.learned_mask_mvdr(mix, mask, cfg), out)
+    # kept spectrum (pass A writes both one-sided spectra, pass B starts from them) == recompute, bit for bit
+    res = []
+    for keep in (True, False):
+        spec = ops.alloc_kept_spectrum(mix_d, cfg) if keep else None
+        assert (spec is not None) == keep
+        Rk, _ = ops.wave_masked_covariance(mix_d, mask_d, cfg, spec)
+        w = ops.mvdr_weights(Rk, ops.steering_vectors(cfg, mix_d.device), cfg)
+        o, pk = ops.mvdr_apply(mix_d, w, cfg, mask=mask_d if cfg.post in ("floor", "mask") else None, spec=spec)
+        res.append((Rk.clone(), o.clone(), pk.clone()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
 
 
 def test_apply_1024_post_modes(az):
