@@ -16,7 +16,8 @@
  *   - F = n_fft/2 + 1, T = avz_num_frames(L, n_fft, hop) = ceil(L/hop) + 1 for hop | n_fft,
  *     iSTFT length = (T - 1) * hop  (scipy.signal.stft/istft, boundary='zeros', padded=True).
  *   - supported: n_fft in {256, 512, 1024}, hop with n_fft % hop == 0 and 2 <= n_fft/hop <= 8, L >= n_fft.
- *     n_fft 512 with hop 128 or 256 (every BASELINE shape) runs on the register-resident fast path.
+ *     n_fft 512 with hop 128 or 256 (every BASELINE shape) runs on the register-resident fast path, and so does
+ *     n_fft 1024 with hop 512 (the learned pipelines' shape: features, mask covariance, apply).
  */
 #ifndef AVZOOM_H_
 #define AVZOOM_H_
@@ -156,7 +157,10 @@ AVZ_API int avz_mvdr_apply_f32(const float* mix, const float* w, const uint32_t*
  * pass B then skips its forward transform: ~25 % fewer instructions for 64 B/sample of otherwise idle HBM bandwidth.
  * Results are bit-identical to the recomputing variants (same transform, same arithmetic order).
  * The buffer also has room for per-utterance completion counters and for a transposed copy (B, T, 264) of the mask:
- * the mask variants re-lay the caller's (B, F, T) mask there first, so that a frame's 257 weights are contiguous. */
+ * the mask variants re-lay the caller's (B, F, T) mask there first, so that a frame's 257 weights are contiguous.
+ * n_fft 1024 / hop 512: the learned-mask pair (avz_wave_mask_cov_keep_f32 -> avz_mvdr_apply_kept_f32, float masks)
+ * keeps both one-sided spectra, 8320 B per frame = 16 B per sample; the IBM variant and the fused normalisation are
+ * n_fft 512 only (AVZ_EINVAL otherwise). */
 AVZ_API int64_t avz_spec_ws_bytes(int B, int64_t L, int n_fft, int hop);
 AVZ_API int avz_ibm_cov_keep_f32(const float* mix, const float* tgt, const float* itf, int B, int64_t L, int n_fft, int hop,
                          float norm_eps, uint32_t* ibm_bits, float* R, float* msum, void* ws, void* spec, void* stream);
