@@ -766,6 +766,23 @@ int avz_wave_mask_cov_keep_f32(const float* mix, const float* mask, int B, int64
                        (cudaStream_t)stream);
 }
 
+// Post-filter of pass B as a kernel gain mode, with the buffer the mode needs checked.
+static int gain_mode_of(const AvzMvdrCfg* cfg, const uint32_t* ibm_bits, const float* mask, int* gain) {
+  switch (cfg->post_mode) {
+    case AVZ_POST_NONE: *gain = GAIN_NONE; return AVZ_OK;
+    case AVZ_POST_ONE_MINUS_NOISE:
+      if (!ibm_bits) return set_error(AVZ_EINVAL, "AVZ_POST_ONE_MINUS_NOISE needs ibm_bits");
+      *gain = GAIN_BITS;
+      return AVZ_OK;
+    case AVZ_POST_FLOOR:
+    case AVZ_POST_MASK:
+      if (!mask) return set_error(AVZ_EINVAL, "AVZ_POST_FLOOR / AVZ_POST_MASK need a float mask");
+      *gain = cfg->post_mode == AVZ_POST_FLOOR ? GAIN_FLOOR : GAIN_MASK;
+      return AVZ_OK;
+    default: return set_error(AVZ_EINVAL, "post_mode=%d unknown", cfg->post_mode);
+  }
+}
+
 static int apply_kept(const void* spec, const float* w, const uint32_t* ibm_bits, const float* mask, int B, int64_t L,
                       int n_fft, int hop, const AvzMvdrCfg* cfg, float* out, float* peak, int fuse_norm, float peak_eps,
                       void* stream) {
@@ -777,19 +794,8 @@ static int apply_kept(const void* spec, const float* w, const uint32_t* ibm_bits
   if (!fast1024 && !use_opt512(n_fft, hop))
     return set_error(AVZ_EINVAL, "avz_mvdr_apply_kept_f32: n_fft 512 (hop 128/256) or 1024 (hop 512) only");
   int gain = GAIN_NONE;
-  switch (cfg->post_mode) {
-    case AVZ_POST_NONE: gain = GAIN_NONE; break;
-    case AVZ_POST_ONE_MINUS_NOISE:
-      if (!ibm_bits) return set_error(AVZ_EINVAL, "AVZ_POST_ONE_MINUS_NOISE needs ibm_bits");
-      gain = GAIN_BITS;
-      break;
-    case AVZ_POST_FLOOR:
-    case AVZ_POST_MASK:
-      if (!mask) return set_error(AVZ_EINVAL, "AVZ_POST_FLOOR / AVZ_POST_MASK need a float mask");
-      gain = cfg->post_mode == AVZ_POST_FLOOR ? GAIN_FLOOR : GAIN_MASK;
-      break;
-    default: return set_error(AVZ_EINVAL, "post_mode=%d unknown", cfg->post_mode);
-  }
+  rc = gain_mode_of(cfg, ibm_bits, mask, &gain);
+  if (rc) return rc;
   if (fast1024) {
     if (gain == GAIN_BITS || fuse_norm)
       return set_error(AVZ_EINVAL, "avz_mvdr_apply_kept_f32: n_fft 1024 takes float masks only, no fused normalisation");
@@ -833,19 +839,8 @@ int avz_mvdr_apply_f32(const float* mix, const float* w, const uint32_t* ibm_bit
   int rc = check_fft_args(n_fft, hop, L);
   if (rc) return rc;
   int gain = GAIN_NONE;
-  switch (cfg->post_mode) {
-    case AVZ_POST_NONE: gain = GAIN_NONE; break;
-    case AVZ_POST_ONE_MINUS_NOISE:
-      if (!ibm_bits) return set_error(AVZ_EINVAL, "AVZ_POST_ONE_MINUS_NOISE needs ibm_bits");
-      gain = GAIN_BITS;
-      break;
-    case AVZ_POST_FLOOR:
-    case AVZ_POST_MASK:
-      if (!mask) return set_error(AVZ_EINVAL, "AVZ_POST_FLOOR / AVZ_POST_MASK need a float mask");
-      gain = cfg->post_mode == AVZ_POST_FLOOR ? GAIN_FLOOR : GAIN_MASK;
-      break;
-    default: return set_error(AVZ_EINVAL, "post_mode=%d unknown", cfg->post_mode);
-  }
+  rc = gain_mode_of(cfg, ibm_bits, mask, &gain);
+  if (rc) return rc;
   const int T = (int)avz_num_frames(L, n_fft, hop);
   if (use_opt512(n_fft, hop)) {
     return (hop == 128) ? o512::launch_apply<128>(mix, nullptr, w, ibm_bits, mask, gain, cfg->post_floor, B, L, out, peak,

@@ -121,6 +121,10 @@ const char* avz_last_error(void) { return avz::g_err; }
 int avz_init(int n_fft) {
   if (n_fft != 256 && n_fft != 512 && n_fft != 1024) return avz::set_error(AVZ_EINVAL, "n_fft=%d unsupported", n_fft);
   avz::Tables t;
+  if (n_fft == 1024) {   // the 1024 / hop 512 fast path runs on the 512-point transform: it needs both tables
+    const int rc = avz::tables_for(512, &t);
+    if (rc) return rc;
+  }
   return avz::tables_for(n_fft, &t);
 }
 
