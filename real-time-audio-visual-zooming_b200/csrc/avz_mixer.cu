@@ -21,6 +21,7 @@
 // Spectra stay in the [k1][k2] order between the passes; the inverse runs the two factors in the opposite order and
 // lands in natural time order, so no transposition is ever materialised.  All twiddles come from one table
 // W_L[j] = exp(-2 pi i j / L) rounded from float64 (W_N1^j = W_L[j N2], W_N2^j = W_L[j N1]).
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -279,6 +280,109 @@ __global__ void k_mix_rows(float2* __restrict__ Z, const float2* __restrict__ W,
     }
     __syncthreads();
     for (int j = threadIdx.x; j < nr * N2; j += blockDim.x) base[(int64_t)r0 * N2 + j] = rows[j];
+  }
+}
+
+// ---- passes 2 and 4, fast variant: when N2 has only prime factors <= 7 the row transform runs as a mixed-radix
+//      Stockham FFT in shared memory (radices <= 8, natural order in and out) instead of the two-level direct DFT:
+//      sum(radix) instead of Na + Nb complex multiply-adds per element (125 = 5*5*5: 15 instead of 30) and - what
+//      matters more, the direct DFT is shared-memory-bandwidth-bound - a butterfly keeps its R inputs of kRowsPer rows
+//      and the R roots of unity in registers: ~0.4 shared-memory loads per multiply-add instead of 1.25. ----
+constexpr int kMaxStages = 12;
+constexpr int kFftRows = 2;        // rows sharing the twiddles of a butterfly thread (register budget: 64 -> full occupancy)
+constexpr int kFftThreads = 256;
+struct RowFftPlan {
+  int n_stages;
+  int radix[kMaxStages];
+};
+
+template <int R>
+__device__ __forceinline__ void row_stage(const float2* __restrict__ in, float2* __restrict__ out,
+                                          const float2* __restrict__ wm, int N2, int Ns, int groups) {
+  const int nb = N2 / R;                 // butterflies per row
+  const int tstep = N2 / (Ns * R);       // W_{Ns R}^{k t} = wm[k t tstep]
+  float2 root[R];                        // W_R^m = wm[m nb]
+#pragma unroll
+  for (int m = 0; m < R; ++m) root[m] = wm[m * nb];
+  for (int idx = threadIdx.x; idx < groups * nb; idx += blockDim.x) {
+    const int g = idx / nb, j = idx - g * nb;
+    const int k = j % Ns;
+    const float2* src = in + (size_t)g * kFftRows * N2 + j;
+    float2 v[kFftRows][R];
+#pragma unroll
+    for (int t = 0; t < R; ++t) {
+      if (t == 0 || Ns == 1) {
+#pragma unroll
+        for (int q = 0; q < kFftRows; ++q) v[q][t] = src[q * N2 + t * nb];
+      } else {
+        const float2 w = wm[k * t * tstep];
+#pragma unroll
+        for (int q = 0; q < kFftRows; ++q) v[q][t] = cmul(src[q * N2 + t * nb], w);
+      }
+    }
+    float2* dst = out + (size_t)g * kFftRows * N2 + (j - k) * R + k;
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+#pragma unroll
+      for (int q = 0; q < kFftRows; ++q) {
+        float2 a = v[q][0];
+#pragma unroll
+        for (int t = 1; t < R; ++t) {
+          const float2 w = root[(t * u) % R];
+          const float2 x = v[q][t];
+          a.x = fmaf(x.x, w.x, fmaf(-x.y, w.y, a.x));
+          a.y = fmaf(x.x, w.y, fmaf(x.y, w.x, a.y));
+        }
+        dst[q * N2 + u * Ns] = a;
+      }
+    }
+  }
+}
+
+template <bool INV>
+__global__ void __launch_bounds__(kFftThreads, 4)
+k_mix_rows_fft(float2* __restrict__ Z, const float2* __restrict__ W, const float2* __restrict__ mul, int N1, int N2,
+               int groups, RowFftPlan plan, int64_t N) {
+  extern __shared__ float2 sm[];  // wm[N2] | bufA[groups*kFftRows][N2] | bufB[same]
+  float2* wm = sm;
+  float2* bufA = sm + N2;
+  float2* bufB = bufA + (size_t)groups * kFftRows * N2;
+  for (int j = threadIdx.x; j < N2; j += blockDim.x) {
+    float2 w = __ldg(W + (int64_t)j * N1);
+    if (INV) w.y = -w.y;
+    wm[j] = w;
+  }
+  float2* base = Z + (int64_t)blockIdx.y * N;
+  const int rows_blk = groups * kFftRows;
+  for (int r0 = blockIdx.x * rows_blk; r0 < N1; r0 += gridDim.x * rows_blk) {
+    const int nr = min(rows_blk, N1 - r0);
+    __syncthreads();
+    for (int j = threadIdx.x; j < rows_blk * N2; j += blockDim.x) {
+      float2 v = make_float2(0.f, 0.f);
+      if (j < nr * N2) {
+        v = base[(int64_t)r0 * N2 + j];
+        if (mul) v = cmul(v, __ldg(mul + (int64_t)r0 * N2 + j));
+      }
+      bufA[j] = v;
+    }
+    __syncthreads();
+    float2* in = bufA;
+    float2* out = bufB;
+    int Ns = 1;
+    for (int s = 0; s < plan.n_stages; ++s) {
+      switch (plan.radix[s]) {
+        case 2: row_stage<2>(in, out, wm, N2, Ns, groups); break;
+        case 3: row_stage<3>(in, out, wm, N2, Ns, groups); break;
+        case 4: row_stage<4>(in, out, wm, N2, Ns, groups); break;
+        case 5: row_stage<5>(in, out, wm, N2, Ns, groups); break;
+        case 7: row_stage<7>(in, out, wm, N2, Ns, groups); break;
+        default: row_stage<8>(in, out, wm, N2, Ns, groups); break;
+      }
+      Ns *= plan.radix[s];
+      __syncthreads();
+      float2* tmp = in; in = out; out = tmp;
+    }
+    for (int j = threadIdx.x; j < nr * N2; j += blockDim.x) base[(int64_t)r0 * N2 + j] = in[j];
   }
 }
 
@@ -571,10 +675,53 @@ int set_mix_attrs(const Split& sp) {
   return AVZ_OK;
 }
 
+// Radices (<= 8) of the mixed-radix row transform, or false when N2 has a prime factor above 7.
+bool row_fft_plan(int N2, RowFftPlan* plan) {
+  int n = N2, ns = 0;
+  const int order[] = {5, 7, 3, 8, 4, 2};
+  for (int r : order)
+    while (n % r == 0 && n > 1) {
+      if (ns == kMaxStages) return false;
+      plan->radix[ns++] = r;
+      n /= r;
+    }
+  plan->n_stages = ns;
+  return n == 1 && ns > 0;
+}
+
 // Row pass over planes 0 .. used-1 of every utterance (PP planes of sp.len() elements per utterance).
 template <bool INV>
 int launch_rows(float2* Z, const float2* W, const float2* mul, const Split& sp, int B, int used, int PP, cudaStream_t st) {
   if (sp.N2 <= 1) return AVZ_OK;
+  RowFftPlan plan;
+  static const bool direct_only = [] {
+    const char* e = getenv("AVZ_MIXER_DIRECT_ROWS");   // A/B: force the two-level direct DFT
+    return e && e[0] == '1';
+  }();
+  if (!direct_only && row_fft_plan(sp.N2, &plan)) {
+    const int64_t M = sp.len();
+    // 16 rows per block when they fit in ~48 KB (4 blocks of 256 threads per SM), fewer for long rows
+    int groups = (int)((48 * 1024 / (int64_t)sizeof(float2) - sp.N2) / (2 * (int64_t)kFftRows * sp.N2));
+    groups = groups < 1 ? 1 : (groups > 8 ? 8 : groups);
+    const size_t smem = ((size_t)sp.N2 + 2 * (size_t)groups * kFftRows * sp.N2) * sizeof(float2);
+    {
+      static std::mutex mu;
+      std::lock_guard<std::mutex> lk(mu);
+      AVZ_CUDA_OK(cudaFuncSetAttribute(k_mix_rows_fft<INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    const int row_blocks = (sp.N1 + groups * kFftRows - 1) / (groups * kFftRows);
+    if (used == PP) {
+      k_mix_rows_fft<INV><<<dim3(row_blocks, B * PP), kFftThreads, smem, st>>>(Z, W, mul, sp.N1, sp.N2, groups, plan, M);
+      AVZ_LAUNCH_OK("k_mix_rows_fft");
+      return AVZ_OK;
+    }
+    for (int q = 0; q < used; ++q) {  // utterance stride PP planes
+      k_mix_rows_fft<INV><<<dim3(row_blocks, B), kFftThreads, smem, st>>>(Z + (int64_t)q * M, W, mul, sp.N1, sp.N2, groups, plan,
+                                                                  (int64_t)PP * M);
+      AVZ_LAUNCH_OK("k_mix_rows_fft");
+    }
+    return AVZ_OK;
+  }
   int Na, Nb;
   sp.row_factors(&Na, &Nb);
   const int64_t M = sp.len();
