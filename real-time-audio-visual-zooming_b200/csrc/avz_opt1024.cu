@@ -10,14 +10,18 @@
 // (E = S[k] + conj S[512-k], O = (S[k] - conj S[512-k]) conj W1024^k, Z = (E + i O) / 2) and one inverse 512-point
 // transform returns the frame as (even, odd) sample pairs, which is also the layout of coalesced 8-byte loads/stores.
 //
-//   k1024_features  STFT(mic0), STFT(mic1) -> ln(|Y0| + 1e-7), angle(Y0) - angle(Y1); NCHW rows leave as runs along T
-//   k1024_cov       STFT of both mics -> (1 - mask)-weighted 2x2 covariance partial sums, accumulators in registers
-//   k1024_apply     STFT of both mics -> w^H y -> post-filter gain -> inverse -> window -> overlap-add of the two
-//                   half-frames in registers -> / sum w^2 -> coalesced stores (+ per-utterance peak)
+//   k1024_features<PHYS>  STFT(mic0), STFT(mic1) -> ln(|Y0| + 1e-7), angle(Y0) - angle(Y1); NCHW rows leave as float4
+//                         runs along T (PHYS: the 4-channel NHWC layout, stored from the bin loop)
+//   k1024_cov<KEEP>       STFT of both mics -> (1 - mask)-weighted 2x2 covariance partial sums, accumulators in
+//                         registers (KEEP: both spectra are also streamed out for pass B)
+//   k1024_apply<KEPT>     STFT of both mics (or the kept spectra) -> w^H y -> post-filter gain -> inverse -> window ->
+//                         overlap-add of the two half-frames in registers -> / sum w^2 -> coalesced stores (+ peak)
 //
 // The two per-channel spectra of a frame meet in a per-warp shared-memory buffer in natural bin order (513 + 513
-// complex): the covariance / beamforming arithmetic then runs on bins lane + 32 i, where the mask, the weights and the
-// partial sums are contiguous.  One warp owns a run of consecutive frames; nothing but __syncwarp() on the frame path.
+// complex): the covariance / beamforming arithmetic then runs on bins lane + 32 i, where the mask tile, the weights and
+// the partial sums are contiguous.  One warp owns a run of consecutive frames; the frame path has only __syncwarp()
+// (plus one block barrier per CTA when the asynchronously staged mask tile is first used).  Measurements and the ncu
+// findings that shaped this file: profiles/r1_ncu_1024.md.
 #include <cstdlib>
 
 #include "avz_common.cuh"
