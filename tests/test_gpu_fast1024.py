@@ -51,7 +51,7 @@ def test_wave_features_1024(az, L):
 
 
 @pytest.mark.parametrize("preset", ["full_audio", "tf_lite"])
-@pytest.mark.parametrize("dur", [2.0, 1.27, 4.0])
+@pytest.mark.parametrize("dur", [2.0, 1.27, 4.0, 0.064, 0.1])   # 0.064 s = one n_fft (T = 3), 0.1 s: T = 5
 def test_learned_mask_mvdr_1024(az, preset, dur):
     """Learned-mask MVDR at 1024/512 (full_audio.../inference.py:88-117; tf_lite_version/inference.py:85-179):
     random target-probability masks against the float64 oracle, pieces and whole."""
