@@ -467,6 +467,14 @@ k1024_apply(const float* __restrict__ mix, const float2* __restrict__ spec, cons
       }
     }
     if (KEPT && t + 1 < fb) load_kept(t + 1);   // in flight during the inverse transform below
+    if (KEPT && t + 2 < fb) {                    // and the frame after that on its way from DRAM to L2 (no registers)
+      const char* nx = reinterpret_cast<const char*>(spec + ((int64_t)b * T + t + 2) * 2 * kYP);
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int off = (lane + 32 * q) * 128;
+        if (off < 2 * kYP * (int)sizeof(float2)) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + off));
+      }
+    }
     __syncwarp();
     float2 v[16];
     {
