@@ -158,6 +158,9 @@ AVZ_API int avz_mvdr_apply_f32(const float* mix, const float* w, const uint32_t*
  * Results are bit-identical to the recomputing variants (same transform, same arithmetic order).
  * The buffer also has room for per-utterance completion counters and for a transposed copy (B, T, 264) of the mask:
  * the mask variants re-lay the caller's (B, F, T) mask there first, so that a frame's 257 weights are contiguous.
+ * avz_mvdr_apply_kept_f32 with a float-mask post-filter (AVZ_POST_FLOOR / AVZ_POST_MASK) and mask == NULL uses that
+ * transposed copy as it stands - valid right after avz_wave_mask_cov_keep_f32 on the same `spec`, and it saves the second
+ * transposition (n_fft 512; with a mask pointer the mask is re-laid again, which is always safe).
  * n_fft 1024 / hop 512: the learned-mask pair (avz_wave_mask_cov_keep_f32 -> avz_mvdr_apply_kept_f32, float masks)
  * keeps both one-sided spectra, 8320 B per frame = 16 B per sample; the IBM variant and the fused normalisation are
  * n_fft 512 only (AVZ_EINVAL otherwise). */

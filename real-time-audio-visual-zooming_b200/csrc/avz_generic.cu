@@ -30,7 +30,7 @@ int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const f
 template <int HOP>
 int launch_apply(const float* mix, const void* spec, const float* w, const uint32_t* ibm_bits, const float* mask,
                  int gain_mode, float post_floor, int B, int64_t L, float* out, float* peak, int fuse_norm,
-                 float peak_eps, cudaStream_t st);
+                 float peak_eps, int mask_staged, cudaStream_t st);
 }  // namespace o512
 
 // n_fft = 1024 / hop 512 fast path (avz_opt1024.cu)
@@ -793,18 +793,26 @@ static int apply_kept(const void* spec, const float* w, const uint32_t* ibm_bits
   const bool fast1024 = use_opt1024(n_fft, hop);
   if (!fast1024 && !use_opt512(n_fft, hop))
     return set_error(AVZ_EINVAL, "avz_mvdr_apply_kept_f32: n_fft 512 (hop 128/256) or 1024 (hop 512) only");
+  // A float-mask post-filter without a mask pointer means: the mask the learned-mask pass A (avz_wave_mask_cov_keep_f32)
+  // re-laid behind the kept spectrum in this same `spec` - pass B then skips its own transposition (n_fft 512 only).
+  const bool needs_mask = cfg->post_mode == AVZ_POST_FLOOR || cfg->post_mode == AVZ_POST_MASK;
+  const int staged = (needs_mask && !mask && !fast1024) ? 1 : 0;
   int gain = GAIN_NONE;
-  rc = gain_mode_of(cfg, ibm_bits, mask, &gain);
-  if (rc) return rc;
+  if (staged) {
+    gain = cfg->post_mode == AVZ_POST_FLOOR ? GAIN_FLOOR : GAIN_MASK;
+  } else {
+    rc = gain_mode_of(cfg, ibm_bits, mask, &gain);
+    if (rc) return rc;
+  }
   if (fast1024) {
     if (gain == GAIN_BITS || fuse_norm)
       return set_error(AVZ_EINVAL, "avz_mvdr_apply_kept_f32: n_fft 1024 takes float masks only, no fused normalisation");
     return o1024::launch_apply(nullptr, spec, w, mask, gain, cfg->post_floor, B, L, out, peak, (cudaStream_t)stream);
   }
   return (hop == 128) ? o512::launch_apply<128>(nullptr, spec, w, ibm_bits, mask, gain, cfg->post_floor, B, L, out, peak,
-                                                fuse_norm, peak_eps, (cudaStream_t)stream)
+                                                fuse_norm, peak_eps, staged, (cudaStream_t)stream)
                       : o512::launch_apply<256>(nullptr, spec, w, ibm_bits, mask, gain, cfg->post_floor, B, L, out, peak,
-                                                fuse_norm, peak_eps, (cudaStream_t)stream);
+                                                fuse_norm, peak_eps, staged, (cudaStream_t)stream);
 }
 
 int avz_mvdr_apply_kept_f32(const void* spec, const float* w, const uint32_t* ibm_bits, const float* mask, int B,
@@ -844,9 +852,9 @@ int avz_mvdr_apply_f32(const float* mix, const float* w, const uint32_t* ibm_bit
   const int T = (int)avz_num_frames(L, n_fft, hop);
   if (use_opt512(n_fft, hop)) {
     return (hop == 128) ? o512::launch_apply<128>(mix, nullptr, w, ibm_bits, mask, gain, cfg->post_floor, B, L, out, peak,
-                                                  0, 0.f, (cudaStream_t)stream)
+                                                  0, 0.f, 0, (cudaStream_t)stream)
                         : o512::launch_apply<256>(mix, nullptr, w, ibm_bits, mask, gain, cfg->post_floor, B, L, out, peak,
-                                                  0, 0.f, (cudaStream_t)stream);
+                                                  0, 0.f, 0, (cudaStream_t)stream);
   }
   if (use_opt1024(n_fft, hop) && gain != GAIN_BITS)
     return o1024::launch_apply(mix, nullptr, w, mask, gain, cfg->post_floor, B, L, out, peak, (cudaStream_t)stream);

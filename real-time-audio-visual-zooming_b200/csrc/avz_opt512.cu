@@ -1035,7 +1035,7 @@ int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const f
 template <int HOP>
 int launch_apply(const float* mix, const void* spec, const float* w, const uint32_t* ibm_bits, const float* mask,
                  int gain_mode, float post_floor, int B, int64_t L, float* out, float* peak, int fuse_norm,
-                 float peak_eps, cudaStream_t st) {
+                 float peak_eps, int mask_staged, cudaStream_t st) {
   Tables tb;
   int rc = tables_for(kN, &tb);
   if (rc) return rc;
@@ -1048,8 +1048,15 @@ int launch_apply(const float* mix, const void* spec, const float* w, const uint3
   const size_t smem = (spec != nullptr) ? apply_smem_bytes<HOP, true>() : apply_smem_bytes<HOP, false>();
   dim3 grid(chunks, B);
   MaskLayout ml;
-  const float* mptr = stage_mask((gain_mode == GAIN_FLOOR || gain_mode == GAIN_MASK) ? mask : nullptr, spec, B, T, &ml, st);
-  AVZ_LAUNCH_OK("k_mask_transpose");
+  const float* mptr;
+  if (mask_staged && spec != nullptr) {
+    // the transposed copy the learned-mask pass A left behind the kept spectrum: no second transposition
+    ml = MaskLayout{(int64_t)T * kMaskPitch, 1, kMaskPitch};
+    mptr = reinterpret_cast<const float*>(static_cast<const unsigned char*>(spec) + spec_mask_offset(B, T));
+  } else {
+    mptr = stage_mask((gain_mode == GAIN_FLOOR || gain_mode == GAIN_MASK) ? mask : nullptr, spec, B, T, &ml, st);
+    AVZ_LAUNCH_OK("k_mask_transpose");
+  }
   prof_begin(PROF_APPLY, st);
   if (spec != nullptr) {
     AVZ_CUDA_OK(cudaFuncSetAttribute(k512_apply<HOP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1109,9 +1116,9 @@ template int launch_ibm_cov<128>(const float*, const float*, const float*, const
 template int launch_ibm_cov<256>(const float*, const float*, const float*, const float*, int, int64_t, float, uint32_t*,
                                  float*, int*, void*, cudaStream_t);
 template int launch_apply<128>(const float*, const void*, const float*, const uint32_t*, const float*, int, float, int,
-                               int64_t, float*, float*, int, float, cudaStream_t);
+                               int64_t, float*, float*, int, float, int, cudaStream_t);
 template int launch_apply<256>(const float*, const void*, const float*, const uint32_t*, const float*, int, float, int,
-                               int64_t, float*, float*, int, float, cudaStream_t);
+                               int64_t, float*, float*, int, float, int, cudaStream_t);
 
 }  // namespace o512
 }  // namespace avz

@@ -101,7 +101,7 @@ def enhance_chunks(chunks: torch.Tensor, model, cfg: MvdrConfig = FINAL_CFG) -> 
     spec = ops.alloc_kept_spectrum(chunks, cfg)
     Rp, _ = ops.wave_masked_covariance(chunks, mask, cfg, spec)
     w = ops.hybrid_null_weights(Rp, _steering(cfg.freqs(), chunks.device), cfg.hp_bins())
-    out, _ = ops.mvdr_apply(chunks, w, cfg, mask=mask, spec=spec)
+    out, _ = ops.mvdr_apply(chunks, w, cfg, mask=mask, spec=spec, mask_staged=True)
     return out
 
 

@@ -474,10 +474,15 @@ def wave_masked_covariance(mix: torch.Tensor, mask: torch.Tensor, cfg: MvdrConfi
 
 
 def mvdr_apply(mix: torch.Tensor, w: torch.Tensor, cfg: MvdrConfig, ibm_bits: Optional[torch.Tensor] = None,
-               mask: Optional[torch.Tensor] = None, spec: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+               mask: Optional[torch.Tensor] = None, spec: Optional[torch.Tensor] = None,
+               mask_staged: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
     """Pass B (oracle_debug.py:80-93): STFT(mix) (or the spectrum pass A kept in `spec`) -> w^H y -> post-filter ->
-    iSTFT/OLA.  -> (out [B,(T-1)*hop] un-normalised, peak [B])."""
+    iSTFT/OLA.  -> (out [B,(T-1)*hop] un-normalised, peak [B]).
+    `mask_staged`: `mask` is the one `wave_masked_covariance(..., spec)` has just been given - at n_fft 512 pass B then
+    reuses the transposed copy that call left in `spec` instead of re-laying the mask a second time."""
     B, _, L = mix.shape
+    if mask_staged and spec is not None and cfg.n_fft == 512 and cfg.post in ("floor", "mask"):
+        mask = None
     T = num_frames(L, cfg.n_fft, cfg.hop)
     out = torch.empty((B, (T - 1) * cfg.hop), dtype=torch.float32, device=mix.device)
     peak = torch.zeros((B,), dtype=torch.float32, device=mix.device)
@@ -531,7 +536,7 @@ def learned_mask_mvdr(mix, mask, cfg: MvdrConfig = PRESETS["baseline_learned"]):
     spec = alloc_kept_spectrum(mix, cfg)
     Rp, _ = wave_masked_covariance(mix, mask, cfg, spec)
     w = mvdr_weights(Rp, steering_vectors(cfg, mix.device), cfg)
-    out, peak = mvdr_apply(mix, w, cfg, mask=mask if cfg.post in ("floor", "mask") else None, spec=spec)
+    out, peak = mvdr_apply(mix, w, cfg, mask=mask if cfg.post in ("floor", "mask") else None, spec=spec, mask_staged=True)
     if cfg.peak_eps is not None:
         peak_normalise(out, peak, cfg.peak_eps)
     return io.give(out[0] if single else out)

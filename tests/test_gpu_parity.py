@@ -276,6 +276,13 @@ def test_learned_mask_fast_path_512(az, preset, hop):
         res.append((Rp.clone(), o.clone(), pk.clone()))
     assert res[0][0].shape == res[1][0].shape and torch.equal(res[0][0], res[1][0])
     assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+    # pass B on the transposed mask pass A staged in `spec` (no second transposition): same bits again
+    if cfg.post in ("floor", "mask"):
+        spec = ops.alloc_kept_spectrum(mix_d, cfg)
+        Rp, _ = ops.wave_masked_covariance(mix_d, mask_d, cfg, spec)
+        w = ops.mvdr_weights(Rp, ops.steering_vectors(cfg, mix_d.device), cfg)
+        o, pk = ops.mvdr_apply(mix_d, w, cfg, mask=mask_d, spec=spec, mask_staged=True)
+        assert torch.equal(o, res[0][1]) and torch.equal(pk, res[0][2])
 
 
 def test_geometric_mask_mvdr_pieces(az, golden_dir):
