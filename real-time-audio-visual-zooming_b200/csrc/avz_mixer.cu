@@ -21,6 +21,7 @@
 // Spectra stay in the [k1][k2] order between the passes; the inverse runs the two factors in the opposite order and
 // lands in natural time order, so no transposition is ever materialised.  All twiddles come from one table
 // W_L[j] = exp(-2 pi i j / L) rounded from float64 (W_N1^j = W_L[j N2], W_N2^j = W_L[j N1]).
+#include <cmath>
 #include <cstdlib>
 #include <mutex>
 #include <vector>
@@ -192,11 +193,15 @@ k_mix_cols_fwd(const float* __restrict__ src, const float2* __restrict__ spec, c
     }
     __syncthreads();
   }
+  // position -> bin once per row of the tile (the digit-reversal loop with its divisions used to run per element)
+  __shared__ unsigned short s_bin[kMaxN1];
+  for (int pos = threadIdx.x; pos < N1; pos += kColThreads) s_bin[pos] = (unsigned short)pos_to_bin(pos, N1);
+  __syncthreads();
   float2* out = A + ((int64_t)b * PP + p) * N;
   for (int idx = threadIdx.x; idx < N1 * kCols; idx += kColThreads) {
     const int c = idx & (kCols - 1), pos = idx / kCols;
     if (c < ncol) {
-      const int k1 = pos_to_bin(pos, N1);
+      const int k1 = s_bin[pos];
       const int n2 = c0 + c;
       out[(int64_t)k1 * N2 + n2] = cmul(sm[idx], __ldg(W + (int64_t)n2 * k1));
     }
@@ -388,6 +393,7 @@ k_mix_rows_fft(float2* __restrict__ Z, const float2* __restrict__ W, const float
 
 struct MixParams {
   int S;
+  int sym[kMaxSrc];    // c2 == -c1 (the two microphones sit symmetrically about the array centre): ramp 2 = conj(ramp 1)
   double c1[kMaxSrc];  // tau(s, mic 1) * fs / L  (cycles per bin)
   double c2[kMaxSrc];
 };
@@ -422,8 +428,10 @@ __global__ void k_mix_combine(float2* __restrict__ Z, MixParams prm, int PP, int
       const int s = 2 * p + h;
       if (s < prm.S) {
         const float2 v = h ? bv : a;
-        const float2 d1 = cmul(v, ramp(prm.c1[s], k));
-        const float2 d2 = cmul(v, ramp(prm.c2[s], k));
+        const float2 r1 = ramp(prm.c1[s], k);
+        const float2 r2 = prm.sym[s] ? make_float2(r1.x, -r1.y) : ramp(prm.c2[s], k);   // sincospif is exactly odd / even
+        const float2 d1 = cmul(v, r1);
+        const float2 d2 = cmul(v, r2);
         m1 = cadd(m1, d1);
         m2 = cadd(m2, d2);
         if (s == 0) tg = d1;
@@ -462,7 +470,7 @@ k_mix_cols_inv(const float2* __restrict__ Q, const float2* __restrict__ W, const
       const int n2 = c0 + c;
       z = cmulc(in[(int64_t)k1 * N2 + n2], __ldg(W + (int64_t)n2 * k1));
     }
-    sm[bin_to_pos(k1, N1) * kCols + c] = z;
+    sm[bin_to_pos(k1, N1) * kCols + c] = z;   // shifts and masks only (a lookup table here measured slower)
   }
   __syncthreads();
   int rem = (log2N1 & 1) ? 2 : 4;
@@ -847,6 +855,9 @@ int avz_farfield_mix_f32(const float* src, const double* delays_host, int B, int
   for (int s = 0; s < kMaxSrc; ++s) {
     prm.c1[s] = s < S ? delays_host[2 * s] * fs / (double)L : 0.0;
     prm.c2[s] = s < S ? delays_host[2 * s + 1] * fs / (double)L : 0.0;
+    // symmetric pair (far-field delays +-(d/2) cos(theta) / c; numpy's cos(theta - pi) and -cos(theta) differ in the last
+    // bit): the phase difference of treating them as exact negatives is < 1e-11 rad at any bin, far below float32
+    prm.sym[s] = (fabs(prm.c2[s] + prm.c1[s]) <= 1e-12 * fabs(prm.c1[s])) ? 1 : 0;
   }
   rc = set_mix_attrs(sp);
   if (rc != AVZ_OK) return rc;
