@@ -294,8 +294,8 @@ __global__ void k_mix_rows(float2* __restrict__ Z, const float2* __restrict__ W,
 //      matters more, the direct DFT is shared-memory-bandwidth-bound - a butterfly keeps its R inputs of kRowsPer rows
 //      and the R roots of unity in registers: ~0.4 shared-memory loads per multiply-add instead of 1.25. ----
 constexpr int kMaxStages = 12;
-constexpr int kFftRows = 2;        // rows sharing the twiddles of a butterfly thread (register budget: 64 -> full occupancy)
-constexpr int kFftThreads = 256;
+constexpr int kFftRows = 2;        // rows sharing the twiddles of a butterfly thread
+constexpr int kFftThreads = 512;
 struct RowFftPlan {
   int n_stages;
   int radix[kMaxStages];
@@ -345,7 +345,7 @@ __device__ __forceinline__ void row_stage(const float2* __restrict__ in, float2*
 }
 
 template <bool INV>
-__global__ void __launch_bounds__(kFftThreads, 4)
+__global__ void __launch_bounds__(kFftThreads, 3)
 k_mix_rows_fft(float2* __restrict__ Z, const float2* __restrict__ W, const float2* __restrict__ mul, int N1, int N2,
                int groups, RowFftPlan plan, int64_t N) {
   extern __shared__ float2 sm[];  // wm[N2] | bufA[groups*kFftRows][N2] | bufB[same]
@@ -708,9 +708,10 @@ int launch_rows(float2* Z, const float2* W, const float2* mul, const Split& sp, 
   }();
   if (!direct_only && row_fft_plan(sp.N2, &plan)) {
     const int64_t M = sp.len();
-    // 16 rows per block when they fit in ~48 KB (4 blocks of 256 threads per SM), fewer for long rows
-    int groups = (int)((48 * 1024 / (int64_t)sizeof(float2) - sp.N2) / (2 * (int64_t)kFftRows * sp.N2));
-    groups = groups < 1 ? 1 : (groups > 8 ? 8 : groups);
+    // 32 rows per block when they fit in ~72 KB (3 blocks of 512 threads per SM = 48 warps: the pass is latency-bound,
+    // occupancy is what moves it - 256 threads x 4 blocks measured 6 % slower end to end), fewer for long rows
+    int groups = (int)((72 * 1024 / (int64_t)sizeof(float2) - sp.N2) / (2 * (int64_t)kFftRows * sp.N2));
+    groups = groups < 1 ? 1 : (groups > 16 ? 16 : groups);
     const size_t smem = ((size_t)sp.N2 + 2 * (size_t)groups * kFftRows * sp.N2) * sizeof(float2);
     {
       static std::mutex mu;
