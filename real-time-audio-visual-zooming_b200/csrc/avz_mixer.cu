@@ -398,7 +398,7 @@ struct MixParams {
   double c2[kMaxSrc];
 };
 
-__device__ __forceinline__ float2 ramp(double cyc_per_bin, int64_t k) {
+__device__ __forceinline__ float2 ramp(double cyc_per_bin, int k) {
   float s, c;
   sincospif((float)(2.0 * (double)k * cyc_per_bin), &s, &c);
   return make_float2(c, -s);  // exp(-2 pi i k c)
@@ -407,14 +407,17 @@ __device__ __forceinline__ float2 ramp(double cyc_per_bin, int64_t k) {
 // ---- pass 3: unpack sources, phase ramps, sum, re-pack.  In place on the spectra: the thread that owns the pair
 //      (k, L-k) is the only one that touches those two positions of any plane. ----
 __global__ void k_mix_combine(float2* __restrict__ Z, MixParams prm, int PP, int N1, int N2, int64_t N) {
-  const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= N) return;
+  // 32-bit index arithmetic (N <= 512 * 1024): the 64-bit divisions of the first version were a third of the kernel
+  const int n = (int)N;
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n) return;
   const int b = blockIdx.y;
-  const int k1 = (int)(o / N2), k2 = (int)(o % N2);
-  const int64_t k = k1 + (int64_t)N1 * k2;
-  const int64_t km = (N - k) % N;
+  const int k1 = o / N2, k2 = o - k1 * N2;
+  const int k = k1 + N1 * k2;
+  const int km = (k == 0) ? 0 : n - k;
   if (k > km) return;
-  const int64_t om = (km % N1) * N2 + km / N1;
+  const int kq = km / N1;
+  const int om = (km - kq * N1) * N2 + kq;
   float2* zb = Z + (int64_t)b * PP * N;
   float2 m1 = make_float2(0.f, 0.f), m2 = m1, tg = m1;
   const int P = (prm.S + 1) / 2;
