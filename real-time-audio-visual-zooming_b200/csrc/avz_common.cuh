@@ -45,14 +45,35 @@ void prof_end(int slot, cudaStream_t st);
 // ------------------------------------------------------------------------------------------
 // complex helpers
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// Packed float32 pairs (Blackwell sm_100: add/mul/fma.rn.f32x2 -> SASS FADD2 / FMUL2 / FFMA2).  A complex value
+// (re, im) is one 64-bit register pair; one packed instruction does the work of two scalar ones in ONE issue slot
+// (the FMA pipe still spends two cycles on it - measured, profiles/r2_f32x2_probe.md - so it is issue slots, not
+// flops, that are saved: exactly what an issue-bound FFT needs).  ptxas folds the pack / unpack moves below into
+// operand modifiers of the packed instruction: half swap (.LO_HI), per-half negation (.NP / .PN) and 32-bit
+// broadcast (Rn.F32), so multiplying by +-i, conjugating and scaling by a real cost no instruction of their own.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float a, float b) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ u64 pk2(float2 a) { return pk2(a.x, a.y); }
+__device__ __forceinline__ float2 up2(u64 v) { float2 r; asm("mov.b64 {%0,%1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return up2(add2(pk2(a), pk2(b))); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return up2(add2(pk2(a), pk2(-b.x, -b.y))); }
+// a + conj(b), a - conj(b)
+__device__ __forceinline__ float2 caddc(float2 a, float2 b) { return up2(add2(pk2(a), pk2(b.x, -b.y))); }
+__device__ __forceinline__ float2 csubc(float2 a, float2 b) { return up2(add2(pk2(a), pk2(-b.x, b.y))); }
+// a * s, a * s + c for a real s
+__device__ __forceinline__ float2 cscale(float2 a, float s) { return up2(mul2(pk2(a), pk2(s, s))); }
+__device__ __forceinline__ float2 cfma_real(float2 a, float s, float2 c) { return up2(fma2(pk2(a), pk2(s, s), pk2(c))); }
+// a * b = (a.x, a.y) b.x + (-a.y, a.x) b.y
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+  return up2(fma2(pk2(-a.y, a.x), pk2(b.y, b.y), mul2(pk2(a), pk2(b.x, b.x))));
 }
-// a * conj(b)
+// a * conj(b) = (a.x, a.y) b.x + (a.y, -a.x) b.y
 __device__ __forceinline__ float2 cmulc(float2 a, float2 b) {
-  return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+  return up2(fma2(pk2(a.y, -a.x), pk2(b.y, b.y), mul2(pk2(a), pk2(b.x, b.x))));
 }
 __device__ __forceinline__ float cabs2(float2 a) { return fmaf(a.x, a.x, a.y * a.y); }
 

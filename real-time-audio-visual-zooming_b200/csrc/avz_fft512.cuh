@@ -61,19 +61,19 @@ __device__ __forceinline__ float2 mul_w16(float2 v) {
   if (m == 12) return INV ? make_float2(v.y, -v.x) : make_float2(-v.y, v.x);
   constexpr float c = W16<m>::c();
   constexpr float s = INV ? -W16<m>::s() : W16<m>::s();  // w = c - i s (forward)
-  // (x + i y)(c - i s) = (x c + y s) + i (y c - x s)
-  return make_float2(fmaf(v.x, c, v.y * s), fmaf(v.y, c, -v.x * s));
+  // (x + i y)(c - i s) = (x, y) c + (y, -x) s : one packed multiply + one packed fma (swap and sign are operand modifiers)
+  return up2(fma2(pk2(v.y, -v.x), pk2(s, s), mul2(pk2(v), pk2(c, c))));
 }
 
 template <bool INV>
 __device__ __forceinline__ void radix4(float2& x0, float2& x1, float2& x2, float2& x3) {
-  const float2 t0 = cadd(x0, x2), t1 = csub(x0, x2), t2 = cadd(x1, x3);
-  float2 t3 = csub(x1, x3);
-  t3 = INV ? make_float2(-t3.y, t3.x) : make_float2(t3.y, -t3.x);
+  const float2 t0 = cadd(x0, x2), t1 = csub(x0, x2), t2 = cadd(x1, x3), t3 = csub(x1, x3);
   x0 = cadd(t0, t2);
-  x1 = cadd(t1, t3);
   x2 = csub(t0, t2);
-  x3 = csub(t1, t3);
+  // t1 -+ i t3 (forward) / t1 +- i t3 (inverse): the rotation by +-i is the half swap + sign of the packed operand
+  const u64 p1 = pk2(t1);
+  x1 = up2(add2(p1, INV ? pk2(-t3.y, t3.x) : pk2(t3.y, -t3.x)));
+  x3 = up2(add2(p1, INV ? pk2(t3.y, -t3.x) : pk2(-t3.y, t3.x)));
 }
 
 // 16-point DFT in registers, natural order in and out (4 x 4 decomposition).
@@ -207,11 +207,10 @@ __device__ __forceinline__ void forward_tail(float2 (&v)[16], float2* __restrict
     const float ry = __shfl_xor_sync(kFull, v[8 + j].y, 16);
     const float2 E = hh ? make_float2(rx, ry) : v[j];
     const float2 O = hh ? v[j] : make_float2(rx, ry);
-    if (LANEC && j > 0) {   // (p, q) = O * W32^j * (-i)^h with this lane's constants
-      const float p = fmaf(O.x, ln.rc[j], O.y * ln.rs[j]);
-      const float q = fmaf(O.y, ln.rc[j], -O.x * ln.rs[j]);
-      v[j] = make_float2(E.x + p, E.y + q);
-      v[8 + j] = make_float2(E.x - p, E.y - q);
+    if (LANEC && j > 0) {   // t = O * W32^j * (-i)^h with this lane's constants: (O.x, O.y) rc + (O.y, -O.x) rs
+      const float2 t = up2(fma2(pk2(O.y, -O.x), pk2(ln.rs[j], ln.rs[j]), mul2(pk2(O), pk2(ln.rc[j], ln.rc[j]))));
+      v[j] = cadd(E, t);
+      v[8 + j] = csub(E, t);
       continue;
     }
     // t = O * W32^j ; for h = 1 the twiddle is W32^(j+8) = -i W32^j
@@ -223,12 +222,12 @@ __device__ __forceinline__ void forward_tail(float2 (&v)[16], float2* __restrict
                     : (j == 5) ? W32<5>::c() : (j == 6) ? W32<6>::c() : W32<7>::c();
       const float s = (j == 1) ? W32<1>::s() : (j == 2) ? W32<2>::s() : (j == 3) ? W32<3>::s() : (j == 4) ? W32<4>::s()
                     : (j == 5) ? W32<5>::s() : (j == 6) ? W32<6>::s() : W32<7>::s();
-      t = make_float2(fmaf(O.x, c, O.y * s), fmaf(O.y, c, -O.x * s));
+      t = up2(fma2(pk2(O.y, -O.x), pk2(s, s), mul2(pk2(O), pk2(c, c))));
     }
     const float p = hh ? t.y : t.x;            // (-i)^h t = (p, q)
     const float q = (hh ? t.x : t.y) * ln.rot;
-    v[j] = make_float2(E.x + p, E.y + q);
-    v[8 + j] = make_float2(E.x - p, E.y - q);
+    v[j] = cadd(E, make_float2(p, q));
+    v[8 + j] = csub(E, make_float2(p, q));
   }
 }
 
@@ -250,8 +249,8 @@ __device__ __forceinline__ void inverse(float2 (&v)[16], float2* __restrict__ sm
                     : (j == 5) ? W32<5>::c() : (j == 6) ? W32<6>::c() : W32<7>::c();
       const float s = (j == 1) ? W32<1>::s() : (j == 2) ? W32<2>::s() : (j == 3) ? W32<3>::s() : (j == 4) ? W32<4>::s()
                     : (j == 5) ? W32<5>::s() : (j == 6) ? W32<6>::s() : W32<7>::s();
-      // (x + i y)(c + i s) = (x c - y s) + i (y c + x s)
-      t = make_float2(fmaf(d.x, c, -d.y * s), fmaf(d.y, c, d.x * s));
+      // (x + i y)(c + i s) = (x, y) c + (-y, x) s
+      t = up2(fma2(pk2(-d.y, d.x), pk2(s, s), mul2(pk2(d), pk2(c, c))));
     }
     // (+i)^h t: h = 1 -> (-t.y, t.x)
     const float2 Op = make_float2((hh ? t.y : t.x) * ln.rot, hh ? t.x : t.y);
@@ -312,8 +311,8 @@ __device__ __forceinline__ void hermitian_pack(const float2 (&Sa)[8], const floa
       a.y = 0.f;
       b.y = 0.f;
     }
-    v[j] = make_float2(a.x - b.y, a.y + b.x);    // Sa + i Sb
-    gm[j] = make_float2(a.x + b.y, b.x - a.y);   // conj(Sa) + i conj(Sb): value at the mirrored bin
+    v[j] = up2(add2(pk2(a), pk2(-b.y, b.x)));          // Sa + i Sb
+    gm[j] = up2(add2(pk2(a.x, -a.y), pk2(b.y, b.x)));  // conj(Sa) + i conj(Sb): value at the mirrored bin
   }
   float2 r[8];
 #pragma unroll

@@ -122,7 +122,7 @@ struct Window2 {
   // windowed complex frame a + i b
   __device__ __forceinline__ void frame(float2 (&v)[16], const float (&w)[16]) const {
 #pragma unroll
-    for (int r = 0; r < 16; ++r) v[r] = make_float2(a[r] * w[r], b[r] * w[r]);
+    for (int r = 0; r < 16; ++r) v[r] = cscale(make_float2(a[r], b[r]), w[r]);
   }
 };
 
@@ -228,10 +228,10 @@ k512_ibm(const float* __restrict__ tgt, const float* __restrict__ itf, int L, in
     if (t + 1 < tb_) win.prefetch(tg, it, L, t + 1, lane);
     float2 v[16];
     win.frame(v, w);
-    float e2 = 0.f;
+    u64 e2p = pk2(0.f, 0.f);
 #pragma unroll
-    for (int r = 0; r < 16; ++r) e2 = fmaf(v[r].x, v[r].x, fmaf(v[r].y, v[r].y, e2));
-    e2 = warp_sum(e2);
+    for (int r = 0; r < 16; ++r) e2p = fma2(pk2(v[r]), pk2(v[r]), e2p);
+    float e2 = warp_sum(up2(e2p).x + up2(e2p).y);
 #if AVZ_IBM_FULLTW
     f512::forward_full(v, sm, ln);
 #else
@@ -503,16 +503,16 @@ k512_cov(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, c
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         // Y0' = Z[k] + conj Z[N-k] = 2 Y0 ;  Y1' = -i (Z[k] - conj Z[N-k]) = 2 Y1
-        const float2 y0 = make_float2(v[j].x + mir[j].x, v[j].y - mir[j].y);
-        const float2 y1 = make_float2(v[j].y + mir[j].y, mir[j].x - v[j].x);
+        const float2 y0 = caddc(v[j], mir[j]);
+        const float2 y1 = up2(add2(pk2(v[j].y, -v[j].x), pk2(mir[j].y, mir[j].x)));
         const float m = mw[j];
         const float ms = (WMODE == W_MASK) ? m + sqrt_eps : m;
-        const float t0 = ms * y0.x, t1 = ms * y0.y;
+        const float2 tt = cscale(y0, ms), uu = cscale(y1, ms);
+        const float t0 = tt.x, t1 = tt.y;
         a00[j] = fmaf(t0, y0.x, fmaf(t1, y0.y, a00[j]));
         are[j] = fmaf(t0, y1.x, fmaf(t1, y1.y, are[j]));   // Re(y0 conj y1)
         aim[j] = fmaf(t1, y1.x, fmaf(-t0, y1.y, aim[j]));  // Im(y0 conj y1)
-        const float u0 = ms * y1.x, u1 = ms * y1.y;
-        a11[j] = fmaf(u0, y1.x, fmaf(u1, y1.y, a11[j]));
+        a11[j] = fmaf(uu.x, y1.x, fmaf(uu.y, y1.y, a11[j]));
         am_[j] += m;
       }
       {  // Nyquist (meaningful on lane 0 only): Y0 = Re hi[0], Y1 = Im hi[0] (not doubled)
@@ -810,9 +810,12 @@ k512_apply(const float* __restrict__ mix, const float4* __restrict__ spec, const
         for (int j = 0; j < 8; ++j) {
           const float4 ab = s_ab[bin_lo(ln, j)];
           // a * z + b * conj(m)
-          const float sx = fmaf(ab.x, zlo[j].x, -ab.y * zlo[j].y) + fmaf(ab.z, mir[j].x, ab.w * mir[j].y);
-          const float sy = fmaf(ab.x, zlo[j].y, ab.y * zlo[j].x) + fmaf(ab.w, mir[j].x, -ab.z * mir[j].y);
-          S[j] = make_float2(sx * gj[j], sy * gj[j]);
+          // (z.x, z.y) a.x + (-z.y, z.x) a.y + (b.x, b.y) m.x + (b.y, -b.x) m.y : four packed multiply-adds
+          u64 s2 = mul2(pk2(zlo[j]), pk2(ab.x, ab.x));
+          s2 = fma2(pk2(-zlo[j].y, zlo[j].x), pk2(ab.y, ab.y), s2);
+          s2 = fma2(pk2(ab.z, ab.w), pk2(mir[j].x, mir[j].x), s2);
+          s2 = fma2(pk2(ab.w, -ab.z), pk2(mir[j].y, mir[j].y), s2);
+          S[j] = up2(mul2(s2, pk2(gj[j], gj[j])));
         }
         const float4 abn = s_ab[256];
         // Re(a z + b conj z), z = Nyquist bin (lane 0)
