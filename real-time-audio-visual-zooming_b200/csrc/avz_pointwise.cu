@@ -126,13 +126,13 @@ __global__ void k_hybrid_null_weights(const float4* __restrict__ R, const float2
 // S[b,k,t] = conj(w0) Y0 + conj(w1) Y1
 __global__ void k_beamform(const float2* __restrict__ w, const float2* __restrict__ Y, int F, int T,
                            float2* __restrict__ S) {
-  const int bk = blockIdx.y;  // b * F + k
+  const int bk = blockIdx.x;  // b * F + k  (on grid.x: B * F exceeds the 65535 limit of grid.y at BASELINE batch sizes)
   const int b = bk / F, k = bk - b * F;
   const float2 w0 = w[2 * (int64_t)bk], w1 = w[2 * (int64_t)bk + 1];
   const float2* y0 = Y + (((int64_t)b * 2 + 0) * F + k) * T;
   const float2* y1 = Y + (((int64_t)b * 2 + 1) * F + k) * T;
   float2* s = S + (int64_t)bk * T;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+  for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < T; t += gridDim.y * blockDim.x) {
     const float2 a = y0[t], c = y1[t];
     // conj(w) * y = cmulc(y, w)
     s[t] = cadd(cmulc(a, w0), cmulc(c, w1));
@@ -160,24 +160,27 @@ __global__ void k_irm(const float2* __restrict__ a, const float2* __restrict__ b
 
 // masked_mvdr.py:37-46: 1 where |angle(Y0) - angle(Y1)| > 0 else 0.01.  The difference of two atan2 values
 // is zero exactly when the two angles are the same float64 number; float32 inputs are promoted first.
-__global__ void k_geometric_mask(const float2* __restrict__ Y, int F, int T, int64_t n_per_b, float* __restrict__ mask) {
-  const int b = blockIdx.y;
-  const float2* y0 = Y + (int64_t)b * 2 * n_per_b;
-  const float2* y1 = y0 + n_per_b;
-  float* m = mask + (int64_t)b * n_per_b;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_per_b; i += (int64_t)gridDim.x * blockDim.x) {
-    const float2 u = y0[i], v = y1[i];
-    const double pa = atan2((double)u.y, (double)u.x), pb = atan2((double)v.y, (double)v.x);
-    m[i] = (fabs(pa - pb) > 0.0) ? 1.0f : 0.01f;
+__global__ void k_geometric_mask(const float2* __restrict__ Y, int B, int64_t n_per_b, float* __restrict__ mask) {
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {   // grid.y is capped at 65535
+    const float2* y0 = Y + (int64_t)b * 2 * n_per_b;
+    const float2* y1 = y0 + n_per_b;
+    float* m = mask + (int64_t)b * n_per_b;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_per_b; i += (int64_t)gridDim.x * blockDim.x) {
+      const float2 u = y0[i], v = y1[i];
+      const double pa = atan2((double)u.y, (double)u.x), pb = atan2((double)v.y, (double)v.x);
+      m[i] = (fabs(pa - pb) > 0.0) ? 1.0f : 0.01f;
+    }
   }
 }
 
-__global__ void k_ibm_unpack(const uint32_t* __restrict__ bits, int F, int T, int FW, float* __restrict__ mask) {
-  const int b = blockIdx.z, k = blockIdx.y;
-  const uint32_t* bb = bits + (int64_t)b * T * FW + (k >> 5);
-  float* m = mask + ((int64_t)b * F + k) * T;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x)
-    m[t] = ((bb[(int64_t)t * FW] >> (k & 31)) & 1u) ? 1.f : 0.f;
+__global__ void k_ibm_unpack(const uint32_t* __restrict__ bits, int B, int F, int T, int FW, float* __restrict__ mask) {
+  const int k = blockIdx.y;
+  for (int b = blockIdx.z; b < B; b += gridDim.z) {   // grid.z is capped at 65535
+    const uint32_t* bb = bits + (int64_t)b * T * FW + (k >> 5);
+    float* m = mask + ((int64_t)b * F + k) * T;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x)
+      m[t] = ((bb[(int64_t)t * FW] >> (k & 31)) & 1u) ? 1.f : 0.f;
+  }
 }
 
 // R[b,k] = sum_t (m + sqrt_eps) y y^H / (sum_t m + norm_eps); one warp per (b, k), float64 accumulation.
@@ -217,14 +220,16 @@ __global__ void k_spec_mask_cov(const float2* __restrict__ Y, const float* __res
 // ------------------------------------------------------------------------------------------
 // features from a spectrum (full_audio.../inference.py:91-94; Final_pipeline/src/inference.py:117-128)
 // ------------------------------------------------------------------------------------------
-__global__ void k_features(const float2* __restrict__ Y, int F, int T, int mode, float* __restrict__ X) {
-  const int b = blockIdx.z, k = blockIdx.y;
-  const float2* y0 = Y + (((int64_t)b * 2 + 0) * F + k) * T;
-  const float2* y1 = Y + (((int64_t)b * 2 + 1) * F + k) * T;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
-    float lm, ipd;
-    feature_values(y0[t], y1[t], lm, ipd);
-    store_features(X, mode, b, k, t, F, T, lm, ipd);
+__global__ void k_features(const float2* __restrict__ Y, int B, int F, int T, int mode, float* __restrict__ X) {
+  const int k = blockIdx.y;
+  for (int b = blockIdx.z; b < B; b += gridDim.z) {   // grid.z is capped at 65535
+    const float2* y0 = Y + (((int64_t)b * 2 + 0) * F + k) * T;
+    const float2* y1 = Y + (((int64_t)b * 2 + 1) * F + k) * T;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+      float lm, ipd;
+      feature_values(y0[t], y1[t], lm, ipd);
+      store_features(X, mode, b, k, t, F, T, lm, ipd);
+    }
   }
 }
 
@@ -329,7 +334,7 @@ int avz_hybrid_null_weights_f32(const float* R, const float* dvec, int B, int F,
 
 int avz_beamform_f32(const float* w, const float* Y, int B, int F, int T, float* S, void* stream) {
   if (!w || !Y || !S || B <= 0 || F <= 0 || T <= 0) return set_error(AVZ_EINVAL, "avz_beamform_f32: bad argument");
-  dim3 grid(grid1d(T, 256, 8), B * F);
+  dim3 grid(B * F, grid1d(T, 256, 8));
   k_beamform<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(w), reinterpret_cast<const float2*>(Y),
                                                      F, T, reinterpret_cast<float2*>(S));
   AVZ_LAUNCH_OK("k_beamform");
@@ -355,16 +360,16 @@ int avz_irm_f32(const float* s_tgt, const float* s_int, int64_t n, float* out, v
 int avz_geometric_mask_f32(const float* Y, int B, int F, int T, float* mask, void* stream) {
   if (!Y || !mask || B <= 0 || F <= 0 || T <= 0) return set_error(AVZ_EINVAL, "avz_geometric_mask_f32: bad argument");
   const int64_t n = (int64_t)F * T;
-  dim3 grid(grid1d(n, 256, 148 * 4), B);
-  k_geometric_mask<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(Y), F, T, n, mask);
+  dim3 grid(grid1d(n, 256, 148 * 4), B < 65535 ? B : 65535);
+  k_geometric_mask<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(Y), B, n, mask);
   AVZ_LAUNCH_OK("k_geometric_mask");
   return AVZ_OK;
 }
 
 int avz_ibm_unpack_f32(const uint32_t* ibm_bits, int B, int F, int T, float* mask, void* stream) {
   if (!ibm_bits || !mask || B <= 0 || F <= 0 || T <= 0) return set_error(AVZ_EINVAL, "avz_ibm_unpack_f32: bad argument");
-  dim3 grid(grid1d(T, 128, 8), F, B);
-  k_ibm_unpack<<<grid, 128, 0, (cudaStream_t)stream>>>(ibm_bits, F, T, (F + 31) / 32, mask);
+  dim3 grid(grid1d(T, 128, 8), F, B < 65535 ? B : 65535);
+  k_ibm_unpack<<<grid, 128, 0, (cudaStream_t)stream>>>(ibm_bits, B, F, T, (F + 31) / 32, mask);
   AVZ_LAUNCH_OK("k_ibm_unpack");
   return AVZ_OK;
 }
@@ -383,8 +388,8 @@ int avz_spec_mask_cov_f32(const float* Y, const float* noise_w, int B, int F, in
 int avz_features_f32(const float* Y, int B, int F, int T, int mode, float* X, void* stream) {
   if (!Y || !X || B <= 0 || F <= 1 || T <= 0 || mode < 0 || mode > 2)
     return set_error(AVZ_EINVAL, "avz_features_f32: bad argument");
-  dim3 grid(grid1d(T, 128, 8), F, B);
-  k_features<<<grid, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(Y), F, T, mode, X);
+  dim3 grid(grid1d(T, 128, 8), F, B < 65535 ? B : 65535);
+  k_features<<<grid, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(Y), B, F, T, mode, X);
   AVZ_LAUNCH_OK("k_features");
   return AVZ_OK;
 }

@@ -70,38 +70,42 @@ class OracleMvdr:
         _lib.check(self.lib.avz_mvdr_weights_f32(_ptr(self.R), _ptr(self.d), self.B, self.F, C.byref(self.cc),
                                                  _ptr(self.w), _stream()), "avz_mvdr_weights_f32")
 
-    def pass_b(self, mix):
+    def pass_b(self, mix, out=None):
         c = self.cfg
         self.peak.zero_()
+        out_t = self.out if out is None else out
         bits = self.bits if c.post == "one_minus_noise" else None
         if self.spec is not None and self.fused_norm:
             # peak normalisation fused into pass B (thread-block cluster per utterance)
             _lib.check(self.lib.avz_mvdr_apply_kept_norm_f32(_ptr(self.spec), _ptr(self.w), _ptr(bits), _ptr(None),
                                                              self.B, self.L, c.n_fft, c.hop, C.byref(self.cc),
-                                                             float(c.peak_eps), _ptr(self.out), _ptr(self.peak),
+                                                             float(c.peak_eps), _ptr(out_t), _ptr(self.peak),
                                                              _stream()), "avz_mvdr_apply_kept_norm_f32")
             return
         if self.spec is not None:
             _lib.check(self.lib.avz_mvdr_apply_kept_f32(_ptr(self.spec), _ptr(self.w), _ptr(bits), _ptr(None), self.B,
-                                                        self.L, c.n_fft, c.hop, C.byref(self.cc), _ptr(self.out),
+                                                        self.L, c.n_fft, c.hop, C.byref(self.cc), _ptr(out_t),
                                                         _ptr(self.peak), _stream()), "avz_mvdr_apply_kept_f32")
             return
         _lib.check(self.lib.avz_mvdr_apply_f32(_ptr(mix), _ptr(self.w), _ptr(bits), _ptr(None), self.B, self.L, c.n_fft,
-                                               c.hop, C.byref(self.cc), _ptr(self.out), _ptr(self.peak), _stream()),
+                                               c.hop, C.byref(self.cc), _ptr(out_t), _ptr(self.peak), _stream()),
                    "avz_mvdr_apply_f32")
 
-    def normalise(self):
+    def normalise(self, out=None):
         if self.cfg.peak_eps is not None and not (self.spec is not None and self.fused_norm):
-            _lib.check(self.lib.avz_peak_normalise_f32(_ptr(self.out), self.B, self.out_len, _ptr(self.peak),
+            _lib.check(self.lib.avz_peak_normalise_f32(_ptr(self.out if out is None else out), self.B, self.out_len, _ptr(self.peak),
                                                        float(self.cfg.peak_eps), _stream()), "avz_peak_normalise_f32")
 
-    def run(self, mix: torch.Tensor, tgt: torch.Tensor, itf: torch.Tensor) -> torch.Tensor:
-        """One step over device-resident inputs mix [B,2,L], tgt [B,L], itf [B,L] -> out [B,(T-1)*hop]."""
+    def run(self, mix: torch.Tensor, tgt: torch.Tensor, itf: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+        """One step over device-resident inputs mix [B,2,L], tgt [B,L], itf [B,L] -> out [B,(T-1)*hop] (the engine's own
+        buffer, or the contiguous float32 tensor `out` of that shape)."""
+        if out is not None and (out.shape != self.out.shape or out.dtype != torch.float32 or not out.is_contiguous()):
+            raise ValueError("out must be a contiguous float32 tensor of shape %s" % (tuple(self.out.shape),))
         self.pass_a(mix, tgt, itf)
         self.weights()
-        self.pass_b(mix)
-        self.normalise()
-        return self.out
+        self.pass_b(mix, out)
+        self.normalise(out)
+        return self.out if out is None else out
 
     KERNELS = ("k512_ibm", "k512_ibm_fixup", "k512_cov", "k_cov_finalize", "k_mvdr_weights", "k512_apply",
                "k_peak_normalise")
