@@ -15,7 +15,11 @@
  *     dimension prepended; complex numbers are interleaved float pairs (re, im);
  *   - F = n_fft/2 + 1, T = avz_num_frames(L, n_fft, hop) = ceil(L/hop) + 1 for hop | n_fft,
  *     iSTFT length = (T - 1) * hop  (scipy.signal.stft/istft, boundary='zeros', padded=True).
- *   - supported: n_fft in {256, 512, 1024}, hop with n_fft % hop == 0 and 2 <= n_fft/hop <= 8, L >= n_fft.
+ *   - supported: n_fft in {256, 512, 1024}, hop with n_fft % hop == 0 and 2 <= n_fft/hop <= 8, L >= n_fft, B <= 65535
+ *     for the fused passes.  L < n_fft returns AVZ_EINVAL: scipy.signal.stft would shrink nperseg to L there (or raise
+ *     "noverlap must be less than nperseg" when L <= n_fft - hop), which changes the number of bins, and every reference
+ *     call site then indexes out of range (oracle_debug.py:60 loops over N_FFT//2 + 1 bins) - the reference has no
+ *     behaviour to reproduce for such inputs.
  *     n_fft 512 with hop 128 or 256 (every BASELINE shape) runs on the register-resident fast path, and so does
  *     n_fft 1024 with hop 512 (the learned pipelines' shape: features, mask covariance, apply).
  */
@@ -136,10 +140,12 @@ AVZ_API int avz_mvdr_weights_f32(const float* R, const float* dvec, int B, int F
  * closed form in float64.  R [B,F,4] is the interference covariance sum m y y^H / (sum m + 1e-6), m = 1 - mask
  * (avz_spec_mask_cov_f32 / avz_wave_mask_cov_f32 with sqrt_eps = 0); dvec [F,2] the un-normalised steering vectors;
  * bins k < bypass_bins (f < 200 Hz there) get w = [1, 0] (mic 0 passes).  Condition number > 10 -> w = v_tgt / 2.
- * A bin whose covariance is exactly zero gets delay-and-sum (the reference emits NaN there).  w [B,F,2] complex64,
+ * A bin whose principal eigenvector has a zero first component (an exactly zero or diagonal covariance with R00 <= R11)
+ * gets delay-and-sum, or - zero_cov_nan != 0 - NaN, which is what the reference's v_int / (v_int[0] / (|v_int[0]| + 1e-10))
+ * evaluates to there (Final_pipeline/src/inference.py:66-68).  w [B,F,2] complex64,
  * usable by avz_beamform_f32 and by avz_mvdr_apply_f32 (any weights are "beamformer weights" to pass B). */
-AVZ_API int avz_hybrid_null_weights_f32(const float* R, const float* dvec, int B, int F, int bypass_bins, float* w,
-                                void* stream);
+AVZ_API int avz_hybrid_null_weights_f32(const float* R, const float* dvec, int B, int F, int bypass_bins, int zero_cov_nan,
+                                float* w, void* stream);
 
 /* ---- beamform a given spectrum: oracle_debug.py:80.  w [B,F,2], Y [B,2,F,T] -> S [B,F,T] complex64. */
 AVZ_API int avz_beamform_f32(const float* w, const float* Y, int B, int F, int T, float* S, void* stream);
@@ -193,6 +199,75 @@ AVZ_API int avz_mvdr_apply_kept_norm_f32(const void* spec, const float* w, const
 AVZ_API int64_t avz_stream_state_bytes(int n_streams);
 AVZ_API int avz_stream_step_f32(float* state, const float* hop_in, const float* noise_w, const float* dvec, int n_streams,
                         int t, int t_end, float lambda, const AvzMvdrCfg* cfg, float* hop_out, void* stream);
+
+/* ---- chunk drivers: main_deploy / process_audio_file / enhance_audio cut a recording into
+ * WIN_SIZE = 32000-sample windows at stride 16000, zero-pad the tail, enhance every window and overlap-add the outputs
+ * with a per-sample count (full_audio.../inference.py:127-156, resnet_model_mvdr/inference.py:226-265,
+ * tf_lite_version/inference.py:267-375, Final_pipeline/src/inference.py:172-235).  Here R planar recordings
+ * rec [R][2][rec_len] are read IN PLACE: window i of recording r is utterance b = r * n_windows + i of the fused
+ * kernels (samples past rec_len read as zero), so no gathered copy of the windows exists, and one gather kernel does
+ * the count-averaged overlap-add.  n_fft 1024 / hop 512 (the STFT shape of all those drivers); R * n_windows <= 65535. */
+typedef struct AvzChunkView {
+  int64_t rec_len;    /* samples per channel of a recording                                   */
+  int32_t n_windows;  /* windows per recording: ceil(rec_len / stride)                          */
+  int32_t stride;     /* samples between window starts (WIN_SIZE / 2 = 16000 in the reference)  */
+} AvzChunkView;
+/* features of every window: X [R*n_windows, ...] in the layout of `mode` (process_chunk, full_audio.../inference.py:90-94) */
+AVZ_API int avz_chunk_features_f32(const float* rec, int R, const AvzChunkView* cv, int64_t win, int n_fft, int hop, int mode,
+                           float* X, void* stream);
+/* learned-mask pass A per window (full_audio.../inference.py:102-108): mask [R*n_windows, F, T] target probabilities ->
+ * Rcov [R*n_windows, F, 4], msum; ws as avz_ibm_cov_ws_bytes(R*n_windows, win, ...); spec (may be NULL) keeps the spectra
+ * (avz_spec_ws_bytes(R*n_windows, win, ...)) for avz_chunk_mvdr_apply_f32. */
+AVZ_API int avz_chunk_mask_cov_f32(const float* rec, const float* mask, int R, const AvzChunkView* cv, int64_t win, int n_fft,
+                           int hop, float sqrt_eps, float norm_eps, float* Rcov, float* msum, void* ws, void* spec,
+                           void* stream);
+/* pass B per window (full_audio.../inference.py:114-117): from `spec` if not NULL, else from the waveform (rec).
+ * out [R*n_windows, (T-1)*hop]; peak [R*n_windows] zeroed by the caller, or NULL. */
+AVZ_API int avz_chunk_mvdr_apply_f32(const float* rec, const void* spec, const float* w, const float* mask, int R,
+                             const AvzChunkView* cv, int64_t win, int n_fft, int hop, const AvzMvdrCfg* cfg, float* out,
+                             float* peak, void* stream);
+/* count-averaged overlap-add of the window outputs: final[r][s] = sum_i outs[r*n_windows+i][s - i*stride] / max(count, 1)
+ * over the windows whose first `use_len` output samples cover s (use_len = min(olen, WIN_SIZE) at
+ * full_audio.../inference.py:151-153, = olen at Final_pipeline/src/inference.py:225-227 where the buffer ends at rec_len),
+ * summed in window order like the reference's loop.  final [R][rec_len]; peak [R] (zeroed by the caller) receives
+ * max|final[r]| for the closing `final / (max|final| + 1e-9)` (avz_peak_normalise_f32), or NULL. */
+AVZ_API int avz_chunk_ola_f32(const float* outs, int R, int n_windows, int64_t olen, int64_t rec_len, int stride,
+                      int64_t use_len, float* final_, float* peak, void* stream);
+/* WAV frames -> planar float32: pcm [R][n][C] interleaved int16 (soundfile.read's (frames, channels)) -> out [R][C][n]
+ * = pcm / 32768 (oracle_debug.py:35-39). */
+AVZ_API int avz_pcm16_frames_to_planar_f32(const int16_t* pcm, int R, int64_t n, int C, float* out, void* stream);
+
+/* ---- float64 forms of the unfused operators.  The reference computes in float64 / complex128 whenever its inputs are
+ * float64 (scipy.signal.stft follows the input dtype; R, w, S are `dtype=complex`, oracle_debug.py:57,67).  Two call
+ * sites are ill-conditioned enough for a float32 STFT to show in the output - masked_mvdr.main (sigma = 1e-7,
+ * masked_mvdr.py:76-128) and hybrid_hard_null_bf (eigenvector + cond threshold + solve, Final_pipeline/src/inference.py:
+ * 28-98) - and run on these.  Same layouts as the _f32 entry points with double / complex128 elements; R is
+ * [B,F,4] doubles, dvec [F,2] complex128, w [B,F,2] complex128.  Not on the throughput path. */
+AVZ_API int avz_stft_f64(const double* x, int B, int C, int64_t L, int n_fft, int hop, double* Y, void* stream);
+AVZ_API int64_t avz_istft_f64_ws_bytes(int B, int T, int n_fft);
+AVZ_API int avz_istft_f64(const double* S, int B, int T, int n_fft, int hop, double* x, void* ws, void* stream);
+/* x[b,:] /= max|x[b,:]| + peak_eps (masked_mvdr.py:128); peak [B] receives the maxima if not NULL. */
+AVZ_API int avz_peak_normalise_f64(double* x, int B, int64_t n, double peak_eps, double* peak, void* stream);
+AVZ_API int avz_geometric_mask_f64(const double* Y, int B, int F, int T, double* mask, void* stream);
+AVZ_API int avz_spec_mask_cov_f64(const double* Y, const double* noise_w, int B, int F, int T, double sqrt_eps,
+                          double norm_eps, double* R, double* msum, void* stream);
+/* Learned-mask covariance in float64 straight from the float32 waveform and target-probability mask (weight 1 - mask):
+ * the ill-conditioned consumers (hybrid hard-null) get full_audio.../inference.py:90,102-108 at the reference's precision.
+ * ws: avz_wave_mask_cov_f64_ws_bytes() bytes (the complex128 spectrum). */
+AVZ_API int64_t avz_wave_mask_cov_f64_ws_bytes(int B, int64_t L, int n_fft, int hop);
+AVZ_API int avz_wave_mask_cov_f64(const float* mix, const float* mask, int B, int64_t L, int n_fft, int hop, double sqrt_eps,
+                          double norm_eps, double* R, double* msum, void* ws, void* stream);
+/* the same for the windows of planar recordings read in place (AvzChunkView above); ws for R * n_windows utterances */
+AVZ_API int avz_chunk_mask_cov_f64(const float* rec, const float* mask, int R, const AvzChunkView* cv, int64_t win, int n_fft,
+                           int hop, double sqrt_eps, double norm_eps, double* Rcov, double* msum, void* ws, void* stream);
+AVZ_API int avz_mvdr_weights_f64(const double* R, const double* dvec, int B, int F, double sigma, double w_eps, int hp_bins,
+                         int hp_mode, double* w, void* stream);
+AVZ_API int avz_hybrid_null_weights_f64(const double* R, const double* dvec, int B, int F, int bypass_bins, int zero_cov_nan,
+                                double* w, void* stream);
+/* float64 arithmetic, weights rounded once to complex64 for the float32 pass B (avz_mvdr_apply_f32 / avz_chunk_mvdr_apply_f32) */
+AVZ_API int avz_hybrid_null_weights_f64_w32(const double* R, const double* dvec, int B, int F, int bypass_bins, int zero_cov_nan,
+                                    float* w, void* stream);
+AVZ_API int avz_beamform_f64(const double* w, const double* Y, int B, int F, int T, double* S, void* stream);
 
 /* ---- IBM from given spectra: oracle_debug.py:49-53 (noise polarity) / model_training.py:90 (target polarity).
  * a, b [n] complex64 -> out [n] f32 = (|a| > |b|) ? 1 : 0, compared exactly (float64 squares). */

@@ -297,6 +297,65 @@ def main():
     c["L"] = np.array(L3)
     np.savez_compressed(os.path.join(OUT, "ref_learned_chunk.npz"), **c)
 
+    # ---------------------------------------------------------------- 5. the TFLite-era chunk drivers (row 9b) and NaN bins
+    # process_audio_file (tf_lite_version/inference.py:245-391) and enhance_audio (Final_pipeline/src/inference.py:144-238)
+    # run unmodified; only their TFLiteBeamformer (a tf.lite interpreter over a blob that is not shipped) is replaced by
+    # an object that replays the masks of section 3, window by window.
+    class ReplayBeamformer:
+        def __init__(self, *a, **k):
+            self.i = 0
+
+        def predict_mask(self, log_mag, ipd):
+            m = c["masks"][self.i]
+            self.i += 1
+            return m
+
+    d5 = {}
+    with tempfile.TemporaryDirectory() as td:
+        old = os.getcwd()
+        os.chdir(td)
+        try:
+            write_wav_pcm16("speech_TEST.wav", mix_pcm[:L3])
+            open("dummy.tflite", "wb").write(b"0" * 1024)
+            saved = (ref_tfl.TFLiteBeamformer, ref_fp_inf.TFLiteBeamformer, ref_fp_inf.config.RESULTS_DIR)
+            ref_tfl.TFLiteBeamformer = ReplayBeamformer
+            ref_fp_inf.TFLiteBeamformer = ReplayBeamformer
+            ref_fp_inf.config.RESULTS_DIR = td
+            for force64, tag in ((False, "f32read"), (True, "f64read")):
+                sf.force_float64 = force64
+                sf.written.clear()
+                with contextlib.redirect_stdout(io.StringIO()):
+                    ref_tfl.process_audio_file("speech_TEST.wav", "paf_out.wav", "dummy.tflite")
+                    ref_fp_inf.enhance_audio("g5", "speech_TEST.wav", "dummy.tflite")
+                d5["process_audio_file_out_" + tag] = sf.written["paf_out.wav"]
+                d5["enhance_audio_out_" + tag] = sf.written["g5_enhanced.wav"]
+            sf.force_float64 = False
+            ref_tfl.TFLiteBeamformer, ref_fp_inf.TFLiteBeamformer, ref_fp_inf.config.RESULTS_DIR = saved
+        finally:
+            os.chdir(old)
+    # hybrid hard-null with an interference covariance that is exactly zero in a bin above the 200 Hz bypass: the
+    # reference divides by zero there (v_int / (v_int[0] / (|v_int[0]| + 1e-10))) and the bin comes out NaN
+    rng5 = np.random.default_rng(20261020)
+    Yn = ((rng5.standard_normal((2, 513, 16)) + 1j * rng5.standard_normal((2, 513, 16))) * 0.01)
+    Yn = Yn.astype(np.complex64).astype(np.complex128)
+    mn = rng5.random((513, 16)).astype(np.float32).astype(np.float64)
+    mn[40, :] = 1.0
+    # (numpy 2.3.5 here: np.linalg.cond of the NaN constraint matrix raises LinAlgError("SVD did not converge"), which
+    # hybrid_hard_null_bf does not catch - the reference's answer to such an input is that exception)
+    try:
+        with np.errstate(all="ignore"):
+            d5["hn_nan_out"] = ref_fp_inf.hybrid_hard_null_bf(Yn, mn, f_bins)
+        d5["hn_nan_raised"] = np.array("")
+    except Exception as ex:                      # noqa: BLE001 - record what the reference does
+        d5["hn_nan_raised"] = np.array(f"{type(ex).__name__}: {ex}")
+    mn2 = mn.copy()
+    mn2[40, :] = rng5.random(16).astype(np.float32).astype(np.float64)
+    d5["hn_ok_out"] = ref_fp_inf.hybrid_hard_null_bf(Yn, mn2, f_bins)    # same input without the empty bin
+    d5["hn_ok_mask"] = mn2.astype(np.float32)
+    d5["hn_nan_Y"] = Yn.astype(np.complex64)
+    d5["hn_nan_mask"] = mn.astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "ref_chunk_drivers.npz"), **d5)
+
     gen_mixer()
 
     for fn in sorted(os.listdir(OUT)):

@@ -25,7 +25,7 @@ __all__ = [
     "beamform", "post_filter", "peak_normalise", "oracle_mask_mvdr", "geometric_mask_mvdr",
     "learned_mask_mvdr_chunk", "chunked_enhance", "batch_mvdr_vec", "logmag_ipd", "physics_features",
     "sir_sdr_unit_output", "osinr_osir", "far_field_delays", "fractional_delay", "mix_far_field",
-    "streaming_mvdr", "hybrid_hard_null",
+    "streaming_mvdr", "hybrid_hard_null", "chunked_enhance_clipped",
 ]
 
 
@@ -197,7 +197,7 @@ def masked_covariance_loop(Y, noise_w, sqrt_eps: float = 0.0, norm_eps: float = 
 def masked_covariance_vec(Y, noise_w, sqrt_eps: float = 0.0, norm_eps: float = 1e-6) -> np.ndarray:
     """tf_lite_version/inference.py:97-127, all bins at once (einsum 'fmt,fnt->fmn')."""
     Y = np.asarray(Y, dtype=np.complex128)
-    noise_w = np.asarray(noise_w, dtype=np.float64)
+    noise_w = np.asarray(noise_w)          # dtype kept: a float32 mask makes sqrt() and sum() float32 in the reference
     Yp = np.transpose(Y, (1, 0, 2))
     Yw = Yp * np.sqrt(noise_w[:, None, :] + sqrt_eps)
     R = np.einsum("fmt,fnt->fmn", Yw, Yw.conj())
@@ -303,7 +303,7 @@ def batch_mvdr_vec(Y, mask, f_bins, d_vectors, sigma: float) -> np.ndarray:
     """tf_lite_version/inference.py:85-179 restated: noise weight 1 - mask, sqrt eps 1e-10,
     norm eps 1e-6, broadcast solve, w eps 1e-10, NO high-pass.  d_vectors (F,2,1) -> (F,T)."""
     Y = np.asarray(Y, dtype=np.complex128)
-    noise_w = 1.0 - np.asarray(mask, dtype=np.float64)
+    noise_w = 1.0 - np.asarray(mask)       # `mask_noise = (1.0 - mask)` in the mask's own dtype (:100)
     R = masked_covariance_vec(Y, noise_w, sqrt_eps=1e-10, norm_eps=1e-6)
     R = R + sigma * np.eye(2)[None]
     dv = np.asarray(d_vectors, dtype=np.complex128)
@@ -323,7 +323,7 @@ def hybrid_hard_null(Y, mask, f_bins, mic_dist: float = 0.08, c: float = 343.0, 
     steering vector normalised to mic 0; constraint matrix C = [v_tgt, v_int]; 2-norm condition number > 10 ->
     delay-and-sum w = v_tgt / 2, else solve C^H w = [1, 0]; bins below 200 Hz pass mic 0.  """
     Y = np.asarray(Y, dtype=np.complex128)
-    m_int = 1.0 - np.asarray(mask, dtype=np.float64)
+    m_int = 1.0 - np.asarray(mask)         # `mask_int = 1.0 - mask` in the mask's own dtype (:43)
     F, T = Y.shape[1], Y.shape[2]
     S = np.zeros((F, T), dtype=complex)
     e1 = np.array([[1], [0]], dtype=np.complex64)
@@ -413,6 +413,42 @@ def chunked_enhance(y_full, mask_fn, cfg: PathConfig = PRESETS["full_audio"], wi
         cnt_buf[s:s + n] += 1.0
     cnt_buf[cnt_buf == 0] = 1.0
     return out_buf[:L] / cnt_buf[:L]
+
+
+def chunked_enhance_clipped(y_full, mask_fn, beamformer: str = "batch_mvdr", win: int = 32000, fs: float = 16000.0,
+                            n_fft: int = 1024, hop: int = 512, mic_dist: float = 0.04, c: float = 343.0,
+                            sigma: float = 1e-5, peak_eps: float = 1e-9) -> np.ndarray:
+    """The TFLite-era chunk drivers restated: `process_audio_file` (tf_lite_version/inference.py:245-391,
+    beamformer='batch_mvdr', post-filter max(mask, 0.05), d = 0.04) and `enhance_audio`
+    (Final_pipeline/src/inference.py:144-238, beamformer='hybrid_null', post-filter mask, MIC_DIST = 0.08).
+    Buffers of len(y): a window adds all its iSTFT samples up to the end of the buffer
+    (w_len = min(len(chunk_out), len(out_buf[start:]))), count-averaged, then / (max|x| + 1e-9).
+    mask_fn(log_mag (F,T), ipd (F,T)) -> (F,T) target-probability mask (the TFLite interpreter's role)."""
+    y_full = np.asarray(y_full)
+    L = y_full.shape[0]
+    stride = win // 2
+    out_buf = np.zeros(L)
+    norm_buf = np.zeros(L)
+    for i in range(int(np.ceil(L / stride))):
+        s = i * stride
+        chunk = y_full[s:s + win]
+        if chunk.shape[0] < win:
+            chunk = np.pad(chunk, ((0, win - chunk.shape[0]), (0, 0)))
+        f_bins, _, Y = scipy.signal.stft(chunk.T, fs=fs, nperseg=n_fft, noverlap=n_fft - hop)
+        mask = np.asarray(mask_fn(np.log(np.abs(Y[0]) + 1e-7), np.angle(Y[0]) - np.angle(Y[1])))
+        if beamformer == "batch_mvdr":
+            d_vecs = all_steering_vectors(f_bins, 90.0, mic_dist, c)[:, :, None]
+            S_final = batch_mvdr_vec(Y, mask, f_bins, d_vecs, sigma) * np.maximum(mask, 0.05)
+        elif beamformer == "hybrid_null":
+            S_final = hybrid_hard_null(Y, mask, f_bins, mic_dist, c) * mask
+        else:
+            raise ValueError(beamformer)
+        _, chunk_out = scipy.signal.istft(S_final, fs=fs, nperseg=n_fft, noverlap=n_fft - hop)
+        w_len = min(len(chunk_out), L - s)
+        out_buf[s:s + w_len] += chunk_out[:w_len]
+        norm_buf[s:s + w_len] += 1.0
+    final = out_buf / np.maximum(norm_buf, 1.0)
+    return final / (np.max(np.abs(final)) + peak_eps)
 
 
 # --------------------------------------------------------------------------------------

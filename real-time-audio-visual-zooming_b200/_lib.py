@@ -31,6 +31,11 @@ class AvzMvdrCfg(C.Structure):
     ]
 
 
+class AvzChunkView(C.Structure):
+    """Mirror of `struct AvzChunkView` (include/avzoom.h)."""
+    _fields_ = [("rec_len", C.c_int64), ("n_windows", C.c_int32), ("stride", C.c_int32)]
+
+
 POST_NONE, POST_ONE_MINUS_NOISE, POST_FLOOR, POST_MASK = 0, 1, 2, 3
 HP_NONE, HP_ZERO, HP_MIC0 = 0, 1, 2
 FEAT_LOGMAG_IPD, FEAT_LOGMAG_IPD_WRAPPED, FEAT_PHYSICS_NHWC = 0, 1, 2
@@ -39,6 +44,7 @@ _p = C.c_void_p
 _i = C.c_int
 _l = C.c_int64
 _f = C.c_float
+_d = C.c_double
 
 # name -> (restype, argtypes); every symbol include/avzoom.h declares
 SIGNATURES = {
@@ -57,7 +63,7 @@ SIGNATURES = {
     "avz_wave_mask_cov_f32": (_i, [_p, _p, _i, _l, _i, _i, _f, _f, _p, _p, _p, _p]),
     "avz_spec_mask_cov_f32": (_i, [_p, _p, _i, _i, _i, _f, _f, _p, _p, _p]),
     "avz_mvdr_weights_f32": (_i, [_p, _p, _i, _i, C.POINTER(AvzMvdrCfg), _p, _p]),
-    "avz_hybrid_null_weights_f32": (_i, [_p, _p, _i, _i, _i, _p, _p]),
+    "avz_hybrid_null_weights_f32": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
     "avz_beamform_f32": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "avz_mvdr_apply_f32": (_i, [_p, _p, _p, _p, _i, _l, _i, _i, C.POINTER(AvzMvdrCfg), _p, _p, _p]),
     "avz_spec_ws_bytes": (_l, [_i, _l, _i, _i]),
@@ -76,6 +82,24 @@ SIGNATURES = {
     "avz_sir_f32": (_i, [_p, _p, _p, _i, _l, _l, _p, _p]),
     "avz_farfield_mix_ws_bytes": (_l, [_i, _i, _l]),
     "avz_farfield_mix_f32": (_i, [_p, C.POINTER(C.c_double), _i, _i, _l, C.c_double, _f, _p, _p, _p, _p, _p]),
+    "avz_chunk_features_f32": (_i, [_p, _i, C.POINTER(AvzChunkView), _l, _i, _i, _i, _p, _p]),
+    "avz_chunk_mask_cov_f32": (_i, [_p, _p, _i, C.POINTER(AvzChunkView), _l, _i, _i, _f, _f, _p, _p, _p, _p, _p]),
+    "avz_chunk_mvdr_apply_f32": (_i, [_p, _p, _p, _p, _i, C.POINTER(AvzChunkView), _l, _i, _i, C.POINTER(AvzMvdrCfg), _p, _p, _p]),
+    "avz_chunk_ola_f32": (_i, [_p, _i, _i, _l, _l, _i, _l, _p, _p, _p]),
+    "avz_pcm16_frames_to_planar_f32": (_i, [_p, _i, _l, _i, _p, _p]),
+    "avz_stft_f64": (_i, [_p, _i, _i, _l, _i, _i, _p, _p]),
+    "avz_istft_f64_ws_bytes": (_l, [_i, _i, _i]),
+    "avz_istft_f64": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
+    "avz_peak_normalise_f64": (_i, [_p, _i, _l, _d, _p, _p]),
+    "avz_geometric_mask_f64": (_i, [_p, _i, _i, _i, _p, _p]),
+    "avz_spec_mask_cov_f64": (_i, [_p, _p, _i, _i, _i, _d, _d, _p, _p, _p]),
+    "avz_wave_mask_cov_f64_ws_bytes": (_l, [_i, _l, _i, _i]),
+    "avz_wave_mask_cov_f64": (_i, [_p, _p, _i, _l, _i, _i, _d, _d, _p, _p, _p, _p]),
+    "avz_chunk_mask_cov_f64": (_i, [_p, _p, _i, C.POINTER(AvzChunkView), _l, _i, _i, _d, _d, _p, _p, _p, _p]),
+    "avz_hybrid_null_weights_f64_w32": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
+    "avz_mvdr_weights_f64": (_i, [_p, _p, _i, _i, _d, _d, _i, _i, _p, _p]),
+    "avz_hybrid_null_weights_f64": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
+    "avz_beamform_f64": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "avz_pcm16_to_f32": (_i, [_p, _l, _p, _p]),
     "avz_f32_to_pcm16": (_i, [_p, _l, _p, _p]),
 }

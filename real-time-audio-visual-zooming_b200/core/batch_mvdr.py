@@ -37,10 +37,14 @@ def batch_mvdr(Y, mask, f_bins, d_vectors, sigma):
     (tf_lite_version/inference.py:97-179).  numpy in -> numpy out, CUDA tensors in -> CUDA tensor out."""
     cfg = dataclasses.replace(PRESETS["tf_lite"], sigma=float(sigma))
     is_np = isinstance(Y, np.ndarray)
-    Yt = torch.as_tensor(Y).to("cuda", torch.complex64) if is_np else Y.to(torch.complex64)
-    mt = torch.as_tensor(mask).to(Yt.device, torch.float32)
-    dv = torch.as_tensor(np.asarray(d_vectors)).to(Yt.device, torch.complex64).reshape(-1, 2)
-    R = ops.masked_covariance(Yt, 1.0 - mt, sqrt_eps=cfg.sqrt_eps, norm_eps=cfg.norm_eps, packed=True)
+    Yt = torch.as_tensor(Y).cuda() if is_np else Y
+    wide = Yt.dtype == torch.complex128            # complex128 in (scipy's STFT of float64 audio) -> float64 operators
+    if not wide:
+        Yt = Yt.to(torch.complex64)
+    mt = torch.as_tensor(mask).to(Yt.device)
+    noise_w = (1.0 - mt).to(torch.float64 if wide else torch.float32)
+    dv = torch.as_tensor(np.asarray(d_vectors)).to(Yt.device, Yt.dtype).reshape(-1, 2)
+    R = ops.masked_covariance(Yt, noise_w, sqrt_eps=cfg.sqrt_eps, norm_eps=cfg.norm_eps, packed=True)
     w = ops.mvdr_weights(R, dv, cfg)
     S = ops.beamform(w, Yt)
     return S.cpu().numpy() if is_np else S
@@ -75,8 +79,11 @@ def process_audio_file(input_path, output_path, model=None, model_path=None):
     if model is None:
         model = chunked.load_mask_model(model_path)
     start = time.time()
-    final = chunked.enhance_waveform(y, model, PRESETS["tf_lite"], win=WIN_SIZE, buf_extra=0)
-    final = final / (np.max(np.abs(final)) + 1e-9)
+    # per-window outputs stay un-normalised (the reference adds the raw iSTFT chunks, :351-373); only the final
+    # waveform is divided by its peak (:375)
+    chunk_cfg = dataclasses.replace(PRESETS["tf_lite"], peak_eps=None)
+    enh = chunked.ChunkedEnhancer(chunk_cfg, WIN_SIZE, clip_to_input=True, final_peak_eps=1e-9)
+    final = enh(chunked.to_planar(y), model)[0].cpu().numpy()
     proc_time = time.time() - start
     wavio.write(output_path, final, FS)
     print("-" * 40)

@@ -36,6 +36,21 @@ def compute_hard_geometric_mask(Y_stft, freqs):
     return ops.geometric_mask(Y_stft)
 
 
+def enhance(y):
+    """The arithmetic of main() (masked_mvdr.py:76-128) on an (L, 2) recording -> peak-normalised (n,) float64 waveform.
+    sigma = 1e-7 on a near-rank-1 covariance amplifies STFT rounding by ~1e4, so this site runs on the float64
+    operators (avz_*_f64), as the reference's complex128 arrays do."""
+    import torch
+    cfg = PRESETS["masked_mvdr"]
+    yt = torch.from_numpy(np.ascontiguousarray(np.asarray(y, dtype=np.float64).T)).cuda()
+    Y = ops.stft(yt, cfg.n_fft, cfg.hop)                                   # complex128
+    mask_noise = ops.geometric_mask(Y)
+    R = ops.masked_covariance(Y, mask_noise, cfg.sqrt_eps, cfg.norm_eps, packed=True)
+    w = ops.mvdr_weights(R, ops.steering_vectors(cfg, Y.device, wide=True), cfg)
+    s_out = ops.istft(ops.beamform(w, Y), cfg.n_fft, cfg.hop)
+    return ops.peak_normalise(s_out[None], None, cfg.peak_eps)[0].cpu().numpy()
+
+
 def main(output_dir_world):
     """masked_mvdr.py:50-135: <dir>/mixture_3_sources.wav -> <dir>/../MVDR_Outputs/output_masked_mvdr.wav."""
     if not output_dir_world or not os.path.exists(output_dir_world):
@@ -50,21 +65,13 @@ def main(output_dir_world):
     mvdr_output_dir = os.path.join(run_root_dir, "MVDR_Outputs")
     os.makedirs(mvdr_output_dir, exist_ok=True)
 
-    import torch
-    cfg = PRESETS["masked_mvdr"]
-    y, fs = wavio.read(input_file, dtype="float32")
-    y = torch.from_numpy(np.ascontiguousarray(y.T)).cuda()
-    Y = ops.stft(y, cfg.n_fft, cfg.hop)
+    y, fs = wavio.read(input_file, dtype="float64")
     print("Calculating Hard Phase Mask...")
-    mask_noise = ops.geometric_mask(Y)
     print("Computing Weighted Noise Covariance...")
-    R = ops.masked_covariance(Y, mask_noise, cfg.sqrt_eps, cfg.norm_eps, packed=True)
     print(f"Beamforming with SIGMA={SIGMA}...")
-    w = ops.mvdr_weights(R, ops.steering_vectors(cfg, Y.device), cfg)
-    s_out, peak = ops.istft(ops.beamform(w, Y), cfg.n_fft, cfg.hop, return_peak=True)
-    s_out = ops.peak_normalise(s_out[None], peak.reshape(1), cfg.peak_eps)[0]
+    s_out = enhance(y)
     wav_out_path = os.path.join(mvdr_output_dir, "output_masked_mvdr.wav")
-    wavio.write(wav_out_path, s_out.cpu().numpy(), fs)
+    wavio.write(wav_out_path, s_out, fs)
     print("Done.")
     print(f"Saved outputs to: {mvdr_output_dir}")
     return wav_out_path

@@ -24,10 +24,27 @@ def get_latest_run_dir():
     return all_runs[0] if all_runs else "simulation_results/latest_run"
 
 
+def enhance(y_mix, s_tgt, s_int, sigma, hp_cutoff):
+    """The arithmetic of main() (oracle_reverb.py:76-160) on arrays: y_mix (2, L), s_tgt (L,), s_int (L,) float32 ->
+    peak-normalised waveform (n,) float32.  IBM covariance, MVDR with sigma / hp, soft post-filter
+    sqrt(Pt / (Pt + Pi + 1e-10)), x / (max|x| + 1e-9)."""
+    import torch
+    cfg = dataclasses.replace(PRESETS["oracle_debug"], sigma=float(sigma), hp_hz=float(hp_cutoff), post="mask",
+                              peak_eps=1e-9)
+    mix = torch.from_numpy(np.ascontiguousarray(y_mix, dtype=np.float32)).cuda()[None]
+    tgt = torch.from_numpy(np.ascontiguousarray(s_tgt, dtype=np.float32)).cuda()[None]
+    itf = torch.from_numpy(np.ascontiguousarray(s_int, dtype=np.float32)).cuda()[None]
+    bits, Rp, _ = ops.ibm_covariance(mix, tgt, itf, cfg)
+    w = ops.mvdr_weights(Rp, ops.steering_vectors(cfg, mix.device), cfg)
+    mask_soft = ops.irm(ops.stft(tgt, cfg.n_fft, cfg.hop), ops.stft(itf, cfg.n_fft, cfg.hop))
+    out, peak = ops.mvdr_apply(mix, w, cfg, mask=mask_soft)
+    ops.peak_normalise(out, peak, cfg.peak_eps)
+    return out[0].cpu().numpy()
+
+
 def main(args):
     """oracle_reverb.py:41-178: IBM covariance on mixture_wpe.wav, MVDR with args.sigma / args.hp, soft post-filter
     sqrt(Pt / (Pt + Pi + 1e-10)), peak normalisation with 1e-9."""
-    import torch
     outdir, sigma, hp_cutoff = args.outdir, args.sigma, args.hp
     print("\n--- ORACLE OPTIMIZATION RUN ---")
     print(f"Directory:  {os.path.basename(outdir)}")
@@ -44,19 +61,10 @@ def main(args):
         y_mix = y_mix.T
     s_tgt, _ = wavio.read(paths[1], dtype="float32")
     s_int, _ = wavio.read(paths[2], dtype="float32")
-    cfg = dataclasses.replace(PRESETS["oracle_debug"], sigma=float(sigma), hp_hz=float(hp_cutoff), post="mask",
-                              peak_eps=1e-9)
-    mix = torch.from_numpy(np.ascontiguousarray(y_mix)).cuda()[None]
-    tgt = torch.from_numpy(s_tgt).cuda()[None]
-    itf = torch.from_numpy(s_int).cuda()[None]
-    bits, Rp, _ = ops.ibm_covariance(mix, tgt, itf, cfg)
     print("Oracle Mask generated (Includes Reverb tails in Interference).")
-    w = ops.mvdr_weights(Rp, ops.steering_vectors(cfg, mix.device), cfg)
-    mask_soft = ops.irm(ops.stft(tgt, cfg.n_fft, cfg.hop), ops.stft(itf, cfg.n_fft, cfg.hop))
-    out, peak = ops.mvdr_apply(mix, w, cfg, mask=mask_soft)
-    ops.peak_normalise(out, peak, cfg.peak_eps)
+    out = enhance(y_mix, s_tgt, s_int, sigma, hp_cutoff)
     out_path = os.path.join(outdir, "output_oracle_reverb.wav")
-    wavio.write(out_path, out[0].cpu().numpy(), FS)
+    wavio.write(out_path, out, FS)
     print(f"Saved: {out_path}")
     print("-----------------------------------")
     return out_path

@@ -218,13 +218,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-// atan2 in (-pi, pi] with numpy's conventions for signed zeros: one fast division, a degree-8 minimax polynomial in
+// atan2 in (-pi, pi] with numpy's conventions for signed zeros: one division, a degree-8 minimax polynomial in
 // t^2 for atan(t)/t on [0, 1] (Remez fit, |error| < 1.2e-7 rad evaluated in float32) and quadrant fix-ups - about a
 // third of the instructions of atan2f, which dominated the feature kernels.
 __device__ __forceinline__ float atan2_poly(float y, float x) {
   const float ax = fabsf(x), ay = fabsf(y);
   const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-  const float t = (mx > 0.f) ? __fdividef(mn, mx) : 0.f;
+  const float t = (mx > 0.f) ? __fdiv_rn(mn, mx) : 0.f;   // correctly rounded: the fast division's 2 ulp would be a third of the error budget
   const float s = t * t;
   float p = 0.0029035559807253364f;
   p = fmaf(p, s, -0.016283021665709413f);
@@ -242,12 +242,15 @@ __device__ __forceinline__ float atan2_poly(float y, float x) {
 }
 
 // log-magnitude + inter-channel phase difference of one TF bin (full_audio.../inference.py:91-94).  The reference
-// evaluates np.abs / np.log / np.angle in float64 and casts to float32; here |.| is (x^2 + y^2) * rsq(x^2 + y^2), the logarithm is
-// the hardware lg2 (absolute error ~5e-7) and the angles come from atan2_poly: all far inside the float32 STFT noise
-// that the features of weak bins carry anyway (tests: 1e-3 on well-conditioned bins).
+// evaluates np.abs / np.log / np.angle in float64 and casts to float32.  Error budget against that, for the SAME
+// spectrum (tests/test_gpu_parity.py::test_features_same_spectrum: log-mag <= 2e-6, IPD <= 1e-6 rad on every non-zero
+// bin): |y| = sqrt.rn(x^2 + y^2) (<= 1 ulp relative = 1.2e-7 absolute in the logarithm), logf (<= 1 ulp of a value of at
+// most 16.2 = 1.9e-6), two atan2_poly angles (1.2e-7 polynomial + 0.6e-7 quotient + 1.2e-7 rounding each) and the
+// rounding of their difference (2.4e-7).  The hardware lg2 / rsq / fast division this replaced were 3 ulp / 2 ulp /
+// 2 ulp and could exceed both bounds on weak bins.
 __device__ __forceinline__ void feature_values(float2 y0, float2 y1, float& logmag, float& ipd) {
   const float p = fmaf(y0.x, y0.x, y0.y * y0.y);
-  logmag = __logf(p * rsqrtf(fmaxf(p, 1e-37f)) + 1e-7f);   // |y| = p / sqrt(p) (hardware rsq); p = 0 gives 0, not NaN
+  logmag = logf(__fsqrt_rn(p) + 1e-7f);
   ipd = atan2_poly(y0.y, y0.x) - atan2_poly(y1.y, y1.x);
 }
 

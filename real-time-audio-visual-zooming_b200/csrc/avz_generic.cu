@@ -36,12 +36,12 @@ int launch_apply(const float* mix, const void* spec, const float* w, const uint3
 // n_fft = 1024 / hop 512 fast path (avz_opt1024.cu)
 namespace o1024 {
 int cov_chunks1024(int B, int T);
-int launch_features(const float* mix, int B, int64_t L, int mode, float* X, cudaStream_t st);
+int launch_features(const float* mix, int B, int64_t L, int mode, float* X, cudaStream_t st, const AvzChunkView* cv = nullptr);
 int64_t spec_ws_bytes1024(int B, int T);
 int launch_mask_cov(const float* mix, const float* mask, int B, int64_t L, float sqrt_eps, float* part, int* chunks_out,
-                    void* spec, cudaStream_t st);
+                    void* spec, cudaStream_t st, const AvzChunkView* cv = nullptr);
 int launch_apply(const float* mix, const void* spec, const float* w, const float* mask, int gain_mode, float post_floor,
-                 int B, int64_t L, float* out, float* peak, cudaStream_t st);
+                 int B, int64_t L, float* out, float* peak, cudaStream_t st, const AvzChunkView* cv = nullptr);
 }  // namespace o1024
 
 // The register-resident 512-point path serves n_fft 512 with hop 128 / 256 unless AVZ_FORCE_GENERIC=1
@@ -633,14 +633,14 @@ using namespace avz;
 extern "C" {
 
 int avz_stft_f32(const float* x, int B, int C, int64_t L, int n_fft, int hop, float* Y, void* stream) {
-  if (!x || !Y || B <= 0 || C <= 0) return set_error(AVZ_EINVAL, "avz_stft_f32: null pointer or empty batch");
+  if (!x || !Y || B <= 0 || B > 65535 || C <= 0) return set_error(AVZ_EINVAL, "avz_stft_f32: null pointer or empty batch");
   int rc = check_fft_args(n_fft, hop, L);
   if (rc) return rc;
   AVZ_DISPATCH_N(n_fft, (launch_stft<N_>(x, B, C, L, hop, Y, (cudaStream_t)stream)));
 }
 
 int avz_istft_f32(const float* S, int B, int T, int n_fft, int hop, float* x, float* peak, void* stream) {
-  if (!S || !x || B <= 0 || T < 2) return set_error(AVZ_EINVAL, "avz_istft_f32: null pointer, empty batch or T < 2");
+  if (!S || !x || B <= 0 || B > 65535 || T < 2) return set_error(AVZ_EINVAL, "avz_istft_f32: null pointer, empty batch or T < 2");
   int rc = check_fft_args(n_fft, hop, n_fft);
   if (rc) return rc;
   AVZ_DISPATCH_N(n_fft, (launch_synth<N_, SRC_SPEC>(nullptr, S, nullptr, nullptr, nullptr, GAIN_NONE, 0.f, B, 0, T, hop,
@@ -648,7 +648,7 @@ int avz_istft_f32(const float* S, int B, int T, int n_fft, int hop, float* x, fl
 }
 
 int avz_peak_normalise_f32(float* x, int B, int64_t n, const float* peak, float peak_eps, void* stream) {
-  if (!x || !peak || B <= 0 || n <= 0) return set_error(AVZ_EINVAL, "avz_peak_normalise_f32: bad argument");
+  if (!x || !peak || B <= 0 || B > 65535 || n <= 0) return set_error(AVZ_EINVAL, "avz_peak_normalise_f32: bad argument");
   int gx = (int)((n / 4 + 1023) / 1024);   // ~4 float4 per thread
   if (gx > 64) gx = 64;
   if (gx < 1) gx = 1;
@@ -660,7 +660,7 @@ int avz_peak_normalise_f32(float* x, int B, int64_t n, const float* peak, float 
 }
 
 int avz_wave_features_f32(const float* mix, int B, int64_t L, int n_fft, int hop, int mode, float* X, void* stream) {
-  if (!mix || !X || B <= 0 || mode < 0 || mode > 2) return set_error(AVZ_EINVAL, "avz_wave_features_f32: bad argument");
+  if (!mix || !X || B <= 0 || B > 65535 || mode < 0 || mode > 2) return set_error(AVZ_EINVAL, "avz_wave_features_f32: bad argument");
   int rc = check_fft_args(n_fft, hop, L);
   if (rc) return rc;
   if (use_opt512(n_fft, hop) && mode != AVZ_FEAT_PHYSICS_NHWC) {
@@ -687,7 +687,7 @@ int64_t avz_ibm_cov_ws_bytes(int B, int64_t L, int n_fft, int hop) {
 
 int avz_ibm_cov_f32(const float* mix, const float* tgt, const float* itf, int B, int64_t L, int n_fft, int hop,
                     float norm_eps, uint32_t* ibm_bits, float* R, float* msum, void* ws, void* stream) {
-  if (!mix || !tgt || !itf || !ibm_bits || !R || !msum || !ws || B <= 0)
+  if (!mix || !tgt || !itf || !ibm_bits || !R || !msum || !ws || B <= 0 || B > 65535)
     return set_error(AVZ_EINVAL, "avz_ibm_cov_f32: null pointer or empty batch");
   int rc = check_fft_args(n_fft, hop, L);
   if (rc) return rc;
@@ -708,9 +708,9 @@ int avz_ibm_exact_f32(const float* tgt, const float* itf, int B, int64_t L, int 
 }
 
 static int mask_cov1024(const float* mix, const float* mask, int B, int64_t L, float sqrt_eps, float norm_eps, float* R,
-                        float* msum, void* ws, void* spec, cudaStream_t st) {
+                        float* msum, void* ws, void* spec, cudaStream_t st, const AvzChunkView* cv = nullptr) {
   int chunks = 0;
-  int rc = o1024::launch_mask_cov(mix, mask, B, L, sqrt_eps, (float*)ws, &chunks, spec, st);
+  int rc = o1024::launch_mask_cov(mix, mask, B, L, sqrt_eps, (float*)ws, &chunks, spec, st, cv);
   if (rc) return rc;
   k_cov_finalize<<<(B * 513 + kFinBins - 1) / kFinBins, kFinBins * kFinSlices, 0, st>>>(
       (const float*)ws, B, 513, Geo<1024>::FP, chunks, norm_eps, reinterpret_cast<float4*>(R), msum);
@@ -720,7 +720,7 @@ static int mask_cov1024(const float* mix, const float* mask, int B, int64_t L, f
 
 int avz_wave_mask_cov_f32(const float* mix, const float* mask, int B, int64_t L, int n_fft, int hop, float sqrt_eps,
                           float norm_eps, float* R, float* msum, void* ws, void* stream) {
-  if (!mix || !mask || !R || !msum || !ws || B <= 0)
+  if (!mix || !mask || !R || !msum || !ws || B <= 0 || B > 65535)
     return set_error(AVZ_EINVAL, "avz_wave_mask_cov_f32: null pointer or empty batch");
   int rc = check_fft_args(n_fft, hop, L);
   if (rc) return rc;
@@ -743,7 +743,7 @@ int64_t avz_spec_ws_bytes(int B, int64_t L, int n_fft, int hop) {
 
 int avz_ibm_cov_keep_f32(const float* mix, const float* tgt, const float* itf, int B, int64_t L, int n_fft, int hop,
                          float norm_eps, uint32_t* ibm_bits, float* R, float* msum, void* ws, void* spec, void* stream) {
-  if (!mix || !tgt || !itf || !ibm_bits || !R || !msum || !ws || !spec || B <= 0)
+  if (!mix || !tgt || !itf || !ibm_bits || !R || !msum || !ws || !spec || B <= 0 || B > 65535)
     return set_error(AVZ_EINVAL, "avz_ibm_cov_keep_f32: null pointer or empty batch");
   int rc = check_fft_args(n_fft, hop, L);
   if (rc) return rc;
@@ -754,7 +754,7 @@ int avz_ibm_cov_keep_f32(const float* mix, const float* tgt, const float* itf, i
 
 int avz_wave_mask_cov_keep_f32(const float* mix, const float* mask, int B, int64_t L, int n_fft, int hop, float sqrt_eps,
                                float norm_eps, float* R, float* msum, void* ws, void* spec, void* stream) {
-  if (!mix || !mask || !R || !msum || !ws || !spec || B <= 0)
+  if (!mix || !mask || !R || !msum || !ws || !spec || B <= 0 || B > 65535)
     return set_error(AVZ_EINVAL, "avz_wave_mask_cov_keep_f32: null pointer or empty batch");
   int rc = check_fft_args(n_fft, hop, L);
   if (rc) return rc;
@@ -786,7 +786,7 @@ static int gain_mode_of(const AvzMvdrCfg* cfg, const uint32_t* ibm_bits, const f
 static int apply_kept(const void* spec, const float* w, const uint32_t* ibm_bits, const float* mask, int B, int64_t L,
                       int n_fft, int hop, const AvzMvdrCfg* cfg, float* out, float* peak, int fuse_norm, float peak_eps,
                       void* stream) {
-  if (!spec || !w || !cfg || !out || B <= 0)
+  if (!spec || !w || !cfg || !out || B <= 0 || B > 65535)
     return set_error(AVZ_EINVAL, "avz_mvdr_apply_kept_f32: null pointer or empty batch");
   int rc = check_fft_args(n_fft, hop, L);
   if (rc) return rc;
@@ -843,7 +843,7 @@ int avz_stream_step_f32(float* state, const float* hop_in, const float* noise_w,
 
 int avz_mvdr_apply_f32(const float* mix, const float* w, const uint32_t* ibm_bits, const float* mask, int B, int64_t L,
                        int n_fft, int hop, const AvzMvdrCfg* cfg, float* out, float* peak, void* stream) {
-  if (!mix || !w || !cfg || !out || B <= 0) return set_error(AVZ_EINVAL, "avz_mvdr_apply_f32: null pointer or empty batch");
+  if (!mix || !w || !cfg || !out || B <= 0 || B > 65535) return set_error(AVZ_EINVAL, "avz_mvdr_apply_f32: null pointer or empty batch");
   int rc = check_fft_args(n_fft, hop, L);
   if (rc) return rc;
   int gain = GAIN_NONE;
@@ -860,6 +860,120 @@ int avz_mvdr_apply_f32(const float* mix, const float* w, const uint32_t* ibm_bit
     return o1024::launch_apply(mix, nullptr, w, mask, gain, cfg->post_floor, B, L, out, peak, (cudaStream_t)stream);
   AVZ_DISPATCH_N(n_fft, (launch_synth<N_, SRC_MIX>(mix, nullptr, w, ibm_bits, mask, gain, cfg->post_floor, B, L, T, hop,
                                                    out, peak, (cudaStream_t)stream)));
+}
+
+}  // extern "C"
+
+// ---- chunk drivers: 2 s windows at 50 % overlap read in place, count-averaged OLA ----
+namespace avz {
+
+// final[r][s] = sum over windows i covering s of outs[r * n_win + i][s - i * stride] / max(count, 1), windows taken in
+// increasing i like the reference's `out_buf[start:start+w] += chunk_out[:w]` loop (full_audio.../inference.py:151-155,
+// Final_pipeline/src/inference.py:225-233).  A window contributes its first `use_len` samples.  Deterministic gather.
+__global__ void __launch_bounds__(256) k_chunk_ola(const float* __restrict__ outs, int n_win, int64_t olen, int64_t rec_len,
+                                                   int stride, int64_t use_len, float* __restrict__ final_,
+                                                   float* __restrict__ peak) {
+  const int r = blockIdx.y;
+  const float* o = outs + (int64_t)r * n_win * olen;
+  float* f = final_ + (int64_t)r * rec_len;
+  float m = 0.f;
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < rec_len; s += (int64_t)gridDim.x * blockDim.x) {
+    int64_t i1 = s / stride;
+    if (i1 > n_win - 1) i1 = n_win - 1;
+    int64_t i0 = (s - use_len) / stride + 1;      // first i with i * stride + use_len > s
+    if (s - use_len < 0) i0 = 0;
+    float acc = 0.f, cnt = 0.f;
+    for (int64_t i = i0; i <= i1; ++i) {
+      acc += o[i * olen + (s - i * stride)];
+      cnt += 1.f;
+    }
+    const float v = acc / (cnt > 0.f ? cnt : 1.f);
+    f[s] = v;
+    m = fmaxf(m, fabsf(v));
+  }
+  if (peak != nullptr) {
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(peak + r), __float_as_uint(m));
+  }
+}
+
+// WAV frames (frames x channels, interleaved PCM16: what soundfile.read hands the reference, oracle_debug.py:35-39) ->
+// planar float32 [R][C][n] = pcm / 32768, the layout the fused kernels read.
+__global__ void __launch_bounds__(256) k_pcm16_frames_to_planar(const int16_t* __restrict__ pcm, int64_t n, int C,
+                                                                float* __restrict__ out) {
+  const int r = blockIdx.y;
+  const int16_t* p = pcm + (int64_t)r * n * C;
+  float* o = out + (int64_t)r * C * n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * C; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = i / n, s = i - c * n;        // consecutive threads write consecutive samples of one channel
+    o[i] = (float)p[s * C + c] * (1.0f / 32768.0f);
+  }
+}
+
+static int check_chunk(const AvzChunkView* cv, int R, int64_t win, int n_fft, int hop, const char* who) {
+  if (!cv || R <= 0 || cv->rec_len <= 0 || cv->stride <= 0 || cv->n_windows <= 0)
+    return set_error(AVZ_EINVAL, "%s: bad chunk view", who);
+  if ((int64_t)R * cv->n_windows > 65535) return set_error(AVZ_EINVAL, "%s: R * n_windows > 65535", who);
+  if (cv->rec_len >= (1ll << 30)) return set_error(AVZ_EINVAL, "%s: recording too long", who);
+  if (!use_opt1024(n_fft, hop))
+    return set_error(AVZ_EINVAL, "%s: the in-place chunk view runs on the n_fft 1024 / hop 512 fast path (the STFT shape "
+                                 "of every chunk driver in the reference)", who);
+  return check_fft_args(n_fft, hop, win);
+}
+
+}  // namespace avz
+
+extern "C" {
+
+int avz_chunk_features_f32(const float* rec, int R, const AvzChunkView* cv, int64_t win, int n_fft, int hop, int mode,
+                           float* X, void* stream) {
+  if (!rec || !X || mode < 0 || mode > 2) return set_error(AVZ_EINVAL, "avz_chunk_features_f32: bad argument");
+  int rc = check_chunk(cv, R, win, n_fft, hop, "avz_chunk_features_f32");
+  if (rc) return rc;
+  return o1024::launch_features(rec, R * cv->n_windows, win, mode, X, (cudaStream_t)stream, cv);
+}
+
+int avz_chunk_mask_cov_f32(const float* rec, const float* mask, int R, const AvzChunkView* cv, int64_t win, int n_fft,
+                           int hop, float sqrt_eps, float norm_eps, float* Rcov, float* msum, void* ws, void* spec,
+                           void* stream) {
+  if (!rec || !mask || !Rcov || !msum || !ws) return set_error(AVZ_EINVAL, "avz_chunk_mask_cov_f32: null pointer");
+  int rc = check_chunk(cv, R, win, n_fft, hop, "avz_chunk_mask_cov_f32");
+  if (rc) return rc;
+  return mask_cov1024(rec, mask, R * cv->n_windows, win, sqrt_eps, norm_eps, Rcov, msum, ws, spec, (cudaStream_t)stream, cv);
+}
+
+int avz_chunk_mvdr_apply_f32(const float* rec, const void* spec, const float* w, const float* mask, int R,
+                             const AvzChunkView* cv, int64_t win, int n_fft, int hop, const AvzMvdrCfg* cfg, float* out,
+                             float* peak, void* stream) {
+  if ((!rec && !spec) || !w || !cfg || !out) return set_error(AVZ_EINVAL, "avz_chunk_mvdr_apply_f32: null pointer");
+  int rc = check_chunk(cv, R, win, n_fft, hop, "avz_chunk_mvdr_apply_f32");
+  if (rc) return rc;
+  int gain = GAIN_NONE;
+  rc = gain_mode_of(cfg, nullptr, mask, &gain);
+  if (rc) return rc;
+  return o1024::launch_apply(spec ? nullptr : rec, spec, w, mask, gain, cfg->post_floor, R * cv->n_windows, win, out, peak,
+                             (cudaStream_t)stream, cv);
+}
+
+int avz_chunk_ola_f32(const float* outs, int R, int n_windows, int64_t olen, int64_t rec_len, int stride, int64_t use_len,
+                      float* final_, float* peak, void* stream) {
+  if (!outs || !final_ || R <= 0 || R > 65535 || n_windows <= 0 || olen <= 0 || rec_len <= 0 || stride <= 0 || use_len <= 0 ||
+      use_len > olen)
+    return set_error(AVZ_EINVAL, "avz_chunk_ola_f32: bad argument");
+  int gx = (int)((rec_len + 1023) / 1024);
+  if (gx > 148 * 8) gx = 148 * 8;
+  k_chunk_ola<<<dim3(gx, R), 256, 0, (cudaStream_t)stream>>>(outs, n_windows, olen, rec_len, stride, use_len, final_, peak);
+  AVZ_LAUNCH_OK("k_chunk_ola");
+  return AVZ_OK;
+}
+
+int avz_pcm16_frames_to_planar_f32(const int16_t* pcm, int R, int64_t n, int C, float* out, void* stream) {
+  if (!pcm || !out || R <= 0 || R > 65535 || n <= 0 || C <= 0) return set_error(AVZ_EINVAL, "avz_pcm16_frames_to_planar_f32: bad argument");
+  int gx = (int)((n * C + 1023) / 1024);
+  if (gx > 148 * 8) gx = 148 * 8;
+  k_pcm16_frames_to_planar<<<dim3(gx, R), 256, 0, (cudaStream_t)stream>>>(pcm, n, C, out);
+  AVZ_LAUNCH_OK("k_pcm16_frames_to_planar");
+  return AVZ_OK;
 }
 
 }  // extern "C"

@@ -47,6 +47,22 @@ constexpr int kTilePitch = kTileFrames + 1;
 
 enum { GAIN_NONE = 0, GAIN_BITS = 1, GAIN_FLOOR = 2, GAIN_MASK = 3 };   // as avz_generic.cu
 
+// Where the two channels of utterance b live and how many of its L samples exist.  A plain batch is [B][2][L]
+// (n_win = 1, rec_stride = 2 L, ch_stride = L, rec_len = L).  The chunk drivers of the reference
+// (full_audio.../inference.py:137-147, Final_pipeline/src/inference.py:186-193) cut a recording into windows of L
+// samples at stride win_stride, zero-padded past its end: here utterance b = r * n_win + i is read IN PLACE from
+// recording r of a planar [R][2][rec_len] buffer - no gathered copy of the windows exists.
+struct WaveView {
+  int64_t rec_stride, ch_stride;
+  int n_win, win_stride, rec_len;
+  __device__ __forceinline__ const float* chan0(const float* base, int b, int L, int& valid) const {
+    const int r = b / n_win, i = b - r * n_win;
+    const int start = i * win_stride;
+    valid = max(0, min(L, rec_len - start));
+    return base + (int64_t)r * rec_stride + start;
+  }
+};
+
 // The caller's mask is (B, F, T): one frame's 513 values are 513 different sectors.  Each CTA therefore copies the
 // (513 x <= 16 frames) tile it needs into shared memory once, asynchronously (cp.async, 16 consecutive threads per
 // 64-byte row), and every frame then reads its weights with consecutive lanes on consecutive bins (pitch 17: no bank
@@ -191,8 +207,8 @@ __device__ __forceinline__ void feature_bin(const float2* __restrict__ Y0, const
 
 template <bool PHYS>
 __global__ void __launch_bounds__(kWarps * 32, 2)
-k1024_features(const float* __restrict__ mix, int L, int T, int B, int mode, float* __restrict__ X, Tables tb512,
-               Tables tb) {
+k1024_features(const float* __restrict__ mix, WaveView vw, int L, int T, int B, int mode, float* __restrict__ X,
+               Tables tb512, Tables tb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* s_wa = reinterpret_cast<float2*>(smem_raw);                        // [512]
   float2* s_fft = s_wa + 512;                                                // [kWarps][kSmemComplex]
@@ -214,14 +230,15 @@ k1024_features(const float* __restrict__ mix, int L, int T, int B, int mode, flo
     const int b = tile / tiles_per_utt;
     const int t0 = (tile - b * tiles_per_utt) * kFeatFrames;
     const int nt = min(kFeatFrames, T - t0);
-    const float* m0 = mix + (int64_t)b * 2 * L;
-    const float* m1 = m0 + L;
+    int Lv;
+    const float* m0 = vw.chan0(mix, b, L, Lv);
+    const float* m1 = m0 + vw.ch_stride;
 #pragma unroll 1
     for (int tl = warp; tl < nt; tl += kWarps) {
       const int t = t0 + tl;
       float2 r0[16], r1[16];
-      load_frame(r0, m0, L, t, lane);
-      load_frame(r1, m1, L, t, lane);
+      load_frame(r0, m0, Lv, t, lane);
+      load_frame(r1, m1, Lv, t, lane);
       analyse_pair(r0, r1, s_wa, sm, cx, Y0, Y1);
       __syncwarp();
 #pragma unroll 1
@@ -277,8 +294,8 @@ k1024_features(const float* __restrict__ mix, int L, int T, int B, int mode, flo
 // 8320 B per frame = 16 B per sample) so that pass B starts from them instead of transforming the waveform again.
 template <bool KEEP>
 __global__ void __launch_bounds__(kWarps * 32, AVZ_MINB_1024_COV)
-k1024_cov(const float* __restrict__ mix, const float* __restrict__ mask, int L, int T, int frames_per_cta, float sqrt_eps,
-          float* __restrict__ part, float2* __restrict__ spec, Tables tb512, Tables tb) {
+k1024_cov(const float* __restrict__ mix, WaveView vw, const float* __restrict__ mask, int L_full, int T, int frames_per_cta,
+          float sqrt_eps, float* __restrict__ part, float2* __restrict__ spec, Tables tb512, Tables tb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* s_wa = reinterpret_cast<float2*>(smem_raw);                        // [512]
   float2* s_fft = s_wa + 512;                                                // [kWarps][kSmemComplex]
@@ -295,8 +312,9 @@ k1024_cov(const float* __restrict__ mix, const float* __restrict__ mask, int L, 
   float2* sm = s_fft + (size_t)warp * f512::kSmemComplex;
   float2* Y0 = s_y + (size_t)warp * 2 * kYP;
   float2* Y1 = Y0 + kYP;
-  const float* m0 = mix + (int64_t)b * 2 * L;
-  const float* m1 = m0 + L;
+  int L;
+  const float* m0 = vw.chan0(mix, b, L_full, L);
+  const float* m1 = m0 + vw.ch_stride;
   bool tile_pending = true;
 
   const int per = (c1 - c0 + kWarps - 1) / kWarps;
@@ -374,9 +392,9 @@ k1024_cov(const float* __restrict__ mix, const float* __restrict__ mask, int L, 
 // after that point is the same code, so both variants give bit-identical waveforms.
 template <bool KEPT>
 __global__ void __launch_bounds__(kWarps * 32, AVZ_MINB_1024_APPLY)
-k1024_apply(const float* __restrict__ mix, const float2* __restrict__ spec, const float2* __restrict__ w, const float* __restrict__ mask, int gain_mode,
-            float post_floor, int L, int T, int blocks_per_cta, float* __restrict__ out, float* __restrict__ peak,
-            Tables tb512, Tables tb) {
+k1024_apply(const float* __restrict__ mix, WaveView vw, const float2* __restrict__ spec, const float2* __restrict__ w,
+            const float* __restrict__ mask, int gain_mode, float post_floor, int L_full, int T, int blocks_per_cta,
+            float* __restrict__ out, float* __restrict__ peak, Tables tb512, Tables tb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* s_wa = reinterpret_cast<float2*>(smem_raw);                        // [512]
   float2* s_ws = s_wa + 512;                                                 // [512]
@@ -406,8 +424,9 @@ k1024_apply(const float* __restrict__ mix, const float2* __restrict__ spec, cons
   float2* sm = s_fft + (size_t)warp * f512::kSmemComplex;
   float2* Y0 = s_y + (size_t)warp * 2 * kYP;
   float2* Y1 = Y0 + kYP;
-  const float* m0 = mix + (int64_t)b * 2 * L;
-  const float* m1 = m0 + L;
+  int L = L_full;
+  const float* m0 = KEPT ? nullptr : vw.chan0(mix, b, L_full, L);
+  const float* m1 = KEPT ? nullptr : m0 + vw.ch_stride;
   float* ob = out + (int64_t)b * (int64_t)(T - 1) * kHop;
 
   // Output block g (1 <= g <= T-1) = second half of frame g-1 + first half of frame g, stored at (g-1) * 512.
@@ -586,7 +605,13 @@ static int tables2(Tables* t512, Tables* t1024) {
   return tables_for(kN, t1024);
 }
 
-int launch_features(const float* mix, int B, int64_t L, int mode, float* X, cudaStream_t st) {
+// plain batch [B][2][L], or windows of planar recordings [R][2][rec_len] read in place (B = R * n_windows)
+static WaveView view_of(const AvzChunkView* cv, int64_t L) {
+  if (cv == nullptr) return WaveView{2 * L, L, 1, 0, (int)L};
+  return WaveView{2 * cv->rec_len, cv->rec_len, cv->n_windows, cv->stride, (int)cv->rec_len};
+}
+
+int launch_features(const float* mix, int B, int64_t L, int mode, float* X, cudaStream_t st, const AvzChunkView* cv) {
   if (L >= (1ll << 31) - 2 * kN) return set_error(AVZ_EINVAL, "L too large");
   if (B > 65535) return set_error(AVZ_EINVAL, "B > 65535");
   Tables t5, t10;
@@ -599,9 +624,9 @@ int launch_features(const float* mix, int B, int64_t L, int mode, float* X, cuda
   const int64_t resident = 2 * (int64_t)num_sms();
   const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
   if (mode == AVZ_FEAT_PHYSICS_NHWC)
-    k1024_features<true><<<grid, kWarps * 32, kSmemFeat, st>>>(mix, (int)L, T, B, mode, X, t5, t10);
+    k1024_features<true><<<grid, kWarps * 32, kSmemFeat, st>>>(mix, view_of(cv, L), (int)L, T, B, mode, X, t5, t10);
   else
-    k1024_features<false><<<grid, kWarps * 32, kSmemFeat, st>>>(mix, (int)L, T, B, mode, X, t5, t10);
+    k1024_features<false><<<grid, kWarps * 32, kSmemFeat, st>>>(mix, view_of(cv, L), (int)L, T, B, mode, X, t5, t10);
   AVZ_LAUNCH_OK("k1024_features");
   return AVZ_OK;
 }
@@ -609,7 +634,7 @@ int launch_features(const float* mix, int B, int64_t L, int mode, float* X, cuda
 int64_t spec_ws_bytes1024(int B, int T) { return (int64_t)B * T * 2 * kYP * (int64_t)sizeof(float2); }
 
 int launch_mask_cov(const float* mix, const float* mask, int B, int64_t L, float sqrt_eps, float* part, int* chunks_out,
-                    void* spec, cudaStream_t st) {
+                    void* spec, cudaStream_t st, const AvzChunkView* cv) {
   if (L >= (1ll << 31) - 2 * kN) return set_error(AVZ_EINVAL, "L too large");
   if (B > 65535) return set_error(AVZ_EINVAL, "B > 65535");
   Tables t5, t10;
@@ -623,18 +648,18 @@ int launch_mask_cov(const float* mix, const float* mask, int B, int64_t L, float
   AVZ_CUDA_OK(cudaFuncSetAttribute(k1024_cov<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCov));
   prof_begin(PROF_COV, st);
   if (spec)
-    k1024_cov<true><<<dim3(chunks, B), kWarps * 32, kSmemCov, st>>>(mix, mask, (int)L, T, fpc, sqrt_eps, part,
-                                                                    (float2*)spec, t5, t10);
+    k1024_cov<true><<<dim3(chunks, B), kWarps * 32, kSmemCov, st>>>(mix, view_of(cv, L), mask, (int)L, T, fpc, sqrt_eps,
+                                                                    part, (float2*)spec, t5, t10);
   else
-    k1024_cov<false><<<dim3(chunks, B), kWarps * 32, kSmemCov, st>>>(mix, mask, (int)L, T, fpc, sqrt_eps, part, nullptr,
-                                                                     t5, t10);
+    k1024_cov<false><<<dim3(chunks, B), kWarps * 32, kSmemCov, st>>>(mix, view_of(cv, L), mask, (int)L, T, fpc, sqrt_eps,
+                                                                     part, nullptr, t5, t10);
   prof_end(PROF_COV, st);
   AVZ_LAUNCH_OK("k1024_cov");
   return AVZ_OK;
 }
 
 int launch_apply(const float* mix, const void* spec, const float* w, const float* mask, int gain_mode, float post_floor,
-                 int B, int64_t L, float* out, float* peak, cudaStream_t st) {
+                 int B, int64_t L, float* out, float* peak, cudaStream_t st, const AvzChunkView* cv) {
   if (L >= (1ll << 31) - 2 * kN) return set_error(AVZ_EINVAL, "L too large");
   if (B > 65535) return set_error(AVZ_EINVAL, "B > 65535");
   Tables t5, t10;
@@ -652,11 +677,12 @@ int launch_apply(const float* mix, const void* spec, const float* w, const float
   prof_begin(PROF_APPLY, st);
   if (spec)
     k1024_apply<true><<<dim3(chunks, B), kWarps * 32, kSmemApply, st>>>(
-        nullptr, reinterpret_cast<const float2*>(spec), reinterpret_cast<const float2*>(w), mask, gain_mode, post_floor,
-        (int)L, T, bpc, out, peak, t5, t10);
+        nullptr, view_of(cv, L), reinterpret_cast<const float2*>(spec), reinterpret_cast<const float2*>(w), mask, gain_mode,
+        post_floor, (int)L, T, bpc, out, peak, t5, t10);
   else
     k1024_apply<false><<<dim3(chunks, B), kWarps * 32, kSmemApply, st>>>(
-        mix, nullptr, reinterpret_cast<const float2*>(w), mask, gain_mode, post_floor, (int)L, T, bpc, out, peak, t5, t10);
+        mix, view_of(cv, L), nullptr, reinterpret_cast<const float2*>(w), mask, gain_mode, post_floor, (int)L, T, bpc, out,
+        peak, t5, t10);
   prof_end(PROF_APPLY, st);
   AVZ_LAUNCH_OK("k1024_apply");
   return AVZ_OK;

@@ -60,7 +60,7 @@ __global__ void k_mvdr_weights(const float4* __restrict__ R, const float2* __res
 // w solves C^H w = [1, 0].  Bins k < bypass_bins pass mic 0 (w = [1, 0]).
 // ------------------------------------------------------------------------------------------
 __global__ void k_hybrid_null_weights(const float4* __restrict__ R, const float2* __restrict__ dvec, int B, int F,
-                                      int bypass_bins, float2* __restrict__ w) {
+                                      int bypass_bins, int zero_cov_nan, float2* __restrict__ w) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * F) return;
   const int k = idx % F;
@@ -80,12 +80,12 @@ __global__ void k_hybrid_null_weights(const float4* __restrict__ R, const float2
     const double half = 0.5 * (a - c), bb = b.x * b.x + b.y * b.y;
     const double rad = sqrt(half * half + bb);
     cd v0, v1;
-    if (half >= 0.0) {          // lambda - c = half + rad is the well-conditioned difference
+    if (half > 0.0 || (half == 0.0 && bb > 0.0)) {   // lambda - c = half + rad is the well-conditioned difference
       v0 = {half + rad, 0.0};
       v1 = {b.x, -b.y};
-    } else {                    // lambda - a = rad - half
+    } else {                    // lambda - a = rad - half; R00 == R11 with R01 == 0: eigh returns the identity, last column [0, 1]
       v0 = b;
-      v1 = {rad - half, 0.0};
+      v1 = {(half == 0.0 && bb == 0.0) ? 1.0 : rad - half, 0.0};
     }
     const double nrm = sqrt(v0.x * v0.x + v0.y * v0.y + v1.x * v1.x + v1.y * v1.y);
     const double m0 = sqrt(v0.x * v0.x + v0.y * v0.y) / (nrm > 0.0 ? nrm : 1.0);   // |v_int[0]| of the unit vector
@@ -116,8 +116,12 @@ __global__ void k_hybrid_null_weights(const float4* __restrict__ R, const float2
         }
       }
     }
-    // an exactly zero covariance (no interference-dominated frame in this bin) has no principal direction; the
-    // reference divides by zero there and emits NaN - delay-and-sum is kept instead (documented deviation)
+    else if (zero_cov_nan) {
+      // no principal direction with a non-zero mic-0 component (exactly zero covariance, or diagonal with R00 <= R11):
+      // the reference divides by zero there and emits NaN; without the flag delay-and-sum is kept instead
+      w0 = {nan(""), nan("")};
+      w1 = {nan(""), nan("")};
+    }
   }
   w[2 * (int64_t)idx] = make_float2((float)w0.x, (float)w0.y);
   w[2 * (int64_t)idx + 1] = make_float2((float)w1.x, (float)w1.y);
@@ -322,11 +326,12 @@ int avz_mvdr_weights_f32(const float* R, const float* dvec, int B, int F, const 
   return AVZ_OK;
 }
 
-int avz_hybrid_null_weights_f32(const float* R, const float* dvec, int B, int F, int bypass_bins, float* w, void* stream) {
+int avz_hybrid_null_weights_f32(const float* R, const float* dvec, int B, int F, int bypass_bins, int zero_cov_nan, float* w,
+                                void* stream) {
   if (!R || !dvec || !w || B <= 0 || F <= 0 || bypass_bins < 0)
     return set_error(AVZ_EINVAL, "avz_hybrid_null_weights_f32: bad argument");
   k_hybrid_null_weights<<<(B * F + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const float4*>(R), reinterpret_cast<const float2*>(dvec), B, F, bypass_bins,
+      reinterpret_cast<const float4*>(R), reinterpret_cast<const float2*>(dvec), B, F, bypass_bins, zero_cov_nan,
       reinterpret_cast<float2*>(w));
   AVZ_LAUNCH_OK("k_hybrid_null_weights");
   return AVZ_OK;

@@ -40,25 +40,41 @@ def get_steering_vector_single(f, angle_deg, d, c):
     return v / (v[0] + 1e-10)
 
 
-def _steering(f_bins, device):
+def _steering(f_bins, device, wide=False):
     f = np.asarray(f_bins, dtype=np.float64)
     th = np.deg2rad(ANGLE_TARGET)
     tau1 = (config.MIC_DIST / 2) * np.cos(th) / config.C_SPEED
     tau2 = (config.MIC_DIST / 2) * np.cos(th - np.pi) / config.C_SPEED
     om = 2 * np.pi * f
-    d = np.stack([np.exp(-1j * om * tau1), np.exp(-1j * om * tau2)], axis=1).astype(np.complex64)
-    return torch.from_numpy(d).to(device)
+    d = np.stack([np.exp(-1j * om * tau1), np.exp(-1j * om * tau2)], axis=1)
+    return torch.from_numpy(d.astype(np.complex128 if wide else np.complex64)).to(device)
 
 
-def hybrid_hard_null_bf(Y, mask, f_bins):
+def hybrid_hard_null_bf(Y, mask, f_bins, degenerate="raise"):
     """Y (M=2, F, T) complex STFT, mask (F, T) target probabilities, f_bins (F,) Hz -> beamformed (F, T) complex.
-    numpy in -> numpy out; CUDA tensors in -> CUDA tensor out."""
+    numpy in -> numpy out; CUDA tensors in -> CUDA tensor out.  The arithmetic follows the dtype of Y like numpy:
+    complex128 (what scipy.signal.stft hands the reference) runs on the float64 operators - the eigenvector, the
+    condition-number threshold and the constraint solve amplify float32 rounding beyond the 1e-4 parity budget.
+
+    `degenerate`: what a bin above the bypass does when its interference covariance has no principal direction with a
+    mic-0 component (e.g. mask == 1 in every frame of the bin).  The reference divides by zero there, its constraint
+    matrix is NaN and np.linalg.cond raises LinAlgError("SVD did not converge") out of the function
+    (Final_pipeline/src/inference.py:66-81; pinned in tests/golden/ref_chunk_drivers.npz): 'raise' does the same,
+    'nan' returns NaN in that bin, 'das' falls back to delay-and-sum (what the batched chunk path does)."""
+    if degenerate not in ("raise", "nan", "das"):
+        raise ValueError("degenerate must be 'raise', 'nan' or 'das'")
     is_np = isinstance(Y, np.ndarray)
-    Yt = torch.as_tensor(Y).to("cuda", torch.complex64) if is_np else Y.to(torch.complex64)
-    mt = torch.as_tensor(mask).to(Yt.device, torch.float32)
+    Yt = torch.as_tensor(Y).cuda() if is_np else Y
+    wide = Yt.dtype == torch.complex128
+    if not wide:
+        Yt = Yt.to(torch.complex64)
+    mt = torch.as_tensor(mask).to(Yt.device)
+    m_int = (1.0 - mt).to(torch.float64 if wide else torch.float32)      # `mask_int = 1.0 - mask` in the mask's own dtype
     f = np.asarray(f_bins, dtype=np.float64)
-    R = ops.masked_covariance(Yt, 1.0 - mt, sqrt_eps=0.0, norm_eps=1e-6, packed=True)
-    w = ops.hybrid_null_weights(R, _steering(f, Yt.device), int(np.sum(f < 200)))
+    R = ops.masked_covariance(Yt, m_int, sqrt_eps=0.0, norm_eps=1e-6, packed=True)
+    w = ops.hybrid_null_weights(R, _steering(f, Yt.device, wide), int(np.sum(f < 200)), zero_cov_nan=(degenerate != "das"))
+    if degenerate == "raise" and bool(torch.isnan(w.real).any()):
+        raise np.linalg.LinAlgError("SVD did not converge")
     S = ops.beamform(w, Yt)
     return S.cpu().numpy() if is_np else S
 
@@ -98,10 +114,11 @@ def enhance_chunks(chunks: torch.Tensor, model, cfg: MvdrConfig = FINAL_CFG) -> 
     X = ops.wave_features(chunks, cfg.n_fft, cfg.hop, "logmag_ipd")
     with torch.no_grad():
         mask = model(X).float().contiguous()
-    spec = ops.alloc_kept_spectrum(chunks, cfg)
-    Rp, _ = ops.wave_masked_covariance(chunks, mask, cfg, spec)
-    w = ops.hybrid_null_weights(Rp, _steering(cfg.freqs(), chunks.device), cfg.hp_bins())
-    out, _ = ops.mvdr_apply(chunks, w, cfg, mask=mask, spec=spec, mask_staged=True)
+    # interference covariance and weights in float64 (the null solve is ill-conditioned); pass B stays on the fused
+    # float32 kernels: rounding w to complex64 moves the output by ~1e-7
+    Rp, _ = ops.wave_masked_covariance(chunks, mask, cfg, wide=True)
+    w = ops.hybrid_null_weights(Rp, _steering(cfg.freqs(), chunks.device, wide=True), cfg.hp_bins(), round_to_f32=True)
+    out, _ = ops.mvdr_apply(chunks, w, cfg, mask=mask)
     return out
 
 
@@ -125,11 +142,9 @@ def enhance_audio(run_name, input_path, model_path, model=None):
             print(f"Failed to load mask model: {e}")
             return
     start_time = time.time()
-    yt = torch.as_tensor(np.asarray(y, dtype=np.float32)).cuda()
-    chunks, stride = chunked.split_chunks(yt, config.WIN_SIZE)
-    outs = enhance_chunks(chunks, model, FINAL_CFG)
-    final = chunked.overlap_add_chunks(outs, yt.shape[0], config.WIN_SIZE, stride, buf_extra=0).cpu().numpy()
+    enh = chunked.ChunkedEnhancer(FINAL_CFG, config.WIN_SIZE, clip_to_input=True, weights="hybrid_null",
+                                  final_peak_eps=1e-9, steering=lambda dev: _steering(FINAL_CFG.freqs(), dev, wide=True))
+    final = enh(chunked.to_planar(y), model)[0].cpu().numpy()
     print(f"Total processing time: {time.time() - start_time:.3f}s")
-    final = final / (np.max(np.abs(final)) + 1e-9)
     wavio.write(output_path, final, config.FS)
     return output_path

@@ -28,6 +28,8 @@ __all__ = [
 
 # ------------------------------------------------------------------------------------------ helpers
 def _stream() -> C.c_void_p:
+    if not torch.cuda.is_available():
+        raise _lib.AvzError("avzoom needs a CUDA device (sm_100a); there is no CPU fallback")
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -59,6 +61,19 @@ class _Io:
         return t.cpu().numpy() if self.numpy else t
 
 
+_WIDE = (np.dtype(np.float64), np.dtype(np.complex128), torch.float64, torch.complex128)
+
+
+def _wide(*xs) -> bool:
+    """True if any argument is float64 / complex128: the call then runs on the float64 kernels (avz_*_f64), as numpy
+    and scipy follow their input dtype (the reference's R, w, S are complex128: oracle_debug.py:57,67)."""
+    for x in xs:
+        dt = getattr(x, "dtype", None)
+        if dt is not None and dt in _WIDE:
+            return True
+    return False
+
+
 def num_frames(length: int, n_fft: int, hop: int) -> int:
     """Frame count of scipy.signal.stft(boundary='zeros', padded=True): ceil(L/hop) + 1 when hop | n_fft."""
     return int(_lib.load().avz_num_frames(int(length), int(n_fft), int(hop)))
@@ -69,7 +84,8 @@ def stft(x, n_fft: int = 512, hop: int = 128):
     x (..., L) float32 -> (..., F, T) complex64.  Pairs of rows along the second-to-last axis share one
     complex transform."""
     io = _Io()
-    x = io.take(x, torch.float32)
+    wide = _wide(x)
+    x = io.take(x, torch.float64 if wide else torch.float32)
     lead = x.shape[:-1]
     L = x.shape[-1]
     if x.dim() == 1:
@@ -78,9 +94,12 @@ def stft(x, n_fft: int = 512, hop: int = 128):
         Cn = x.shape[-2]
         B = int(np.prod(x.shape[:-2])) if x.dim() > 2 else 1
     F, T = n_fft // 2 + 1, num_frames(L, n_fft, hop)
-    Y = torch.empty((B, Cn, F, T), dtype=torch.complex64, device=x.device)
+    Y = torch.empty((B, Cn, F, T), dtype=torch.complex128 if wide else torch.complex64, device=x.device)
     lib = _lib.load()
-    _lib.check(lib.avz_stft_f32(_ptr(x), B, Cn, L, n_fft, hop, _ptr(Y), _stream()), "avz_stft_f32")
+    if wide:    # float64 in -> complex128 out, like scipy
+        _lib.check(lib.avz_stft_f64(_ptr(x), B, Cn, L, n_fft, hop, _ptr(Y), _stream()), "avz_stft_f64")
+    else:
+        _lib.check(lib.avz_stft_f32(_ptr(x), B, Cn, L, n_fft, hop, _ptr(Y), _stream()), "avz_stft_f32")
     return io.give(Y.reshape(*lead, F, T))
 
 
@@ -88,12 +107,22 @@ def istft(S, n_fft: int = 512, hop: int = 128, return_peak: bool = False):
     """scipy.signal.istft(S, fs, nperseg=n_fft, noverlap=n_fft-hop)[1] (oracle_debug.py:93).
     S (..., F, T) complex64 -> (..., (T-1)*hop) float32."""
     io = _Io()
-    S = io.take(S, torch.complex64)
+    wide = _wide(S)
+    S = io.take(S, torch.complex128 if wide else torch.complex64)
     F, T = S.shape[-2], S.shape[-1]
     if F != n_fft // 2 + 1:
         raise ValueError(f"spectrum has {F} bins, n_fft={n_fft} needs {n_fft // 2 + 1}")
     lead = S.shape[:-2]
     B = int(np.prod(lead)) if lead else 1
+    if wide:
+        lib = _lib.load()
+        out = torch.empty((B, (T - 1) * hop), dtype=torch.float64, device=S.device)
+        ws = torch.empty((int(lib.avz_istft_f64_ws_bytes(B, T, n_fft)),), dtype=torch.uint8, device=S.device)
+        _lib.check(lib.avz_istft_f64(_ptr(S), B, T, n_fft, hop, _ptr(out), _ptr(ws), _stream()), "avz_istft_f64")
+        out = out.reshape(*lead, (T - 1) * hop)
+        if return_peak:
+            return io.give(out), io.give(out.abs().amax(dim=-1))
+        return io.give(out)
     out = torch.empty((B, (T - 1) * hop), dtype=torch.float32, device=S.device)
     peak = torch.zeros((B,), dtype=torch.float32, device=S.device) if return_peak else None
     lib = _lib.load()
@@ -105,8 +134,12 @@ def istft(S, n_fft: int = 512, hop: int = 128, return_peak: bool = False):
 
 
 def peak_normalise(x: torch.Tensor, peak: torch.Tensor, peak_eps: float) -> torch.Tensor:
-    """In place x[b] /= (peak[b] + peak_eps)  (oracle_debug.py:94)."""
+    """In place x[b] /= (peak[b] + peak_eps)  (oracle_debug.py:94).  float64 rows find their own maximum (`peak` unused)."""
     B, n = x.shape
+    if x.dtype == torch.float64:
+        _lib.check(_lib.load().avz_peak_normalise_f64(_ptr(x), B, n, float(peak_eps), _ptr(None), _stream()),
+                   "avz_peak_normalise_f64")
+        return x
     _lib.check(_lib.load().avz_peak_normalise_f32(_ptr(x), B, n, _ptr(peak), float(peak_eps), _stream()),
                "avz_peak_normalise_f32")
     return x
@@ -149,12 +182,16 @@ def irm(S_tgt, S_int):
 def geometric_mask(Y):
     """compute_hard_geometric_mask (masked_mvdr.py:37-46).  Y (..., 2, F, T) -> (..., F, T) in {0.01, 1}."""
     io = _Io()
-    Y = io.take(Y, torch.complex64)
+    wide = _wide(Y)
+    Y = io.take(Y, torch.complex128 if wide else torch.complex64)
     F, T = Y.shape[-2], Y.shape[-1]
     lead = Y.shape[:-3]
     B = int(np.prod(lead)) if lead else 1
-    out = torch.empty((B, F, T), dtype=torch.float32, device=Y.device)
-    _lib.check(_lib.load().avz_geometric_mask_f32(_ptr(Y), B, F, T, _ptr(out), _stream()), "avz_geometric_mask_f32")
+    out = torch.empty((B, F, T), dtype=torch.float64 if wide else torch.float32, device=Y.device)
+    if wide:
+        _lib.check(_lib.load().avz_geometric_mask_f64(_ptr(Y), B, F, T, _ptr(out), _stream()), "avz_geometric_mask_f64")
+    else:
+        _lib.check(_lib.load().avz_geometric_mask_f32(_ptr(Y), B, F, T, _ptr(out), _stream()), "avz_geometric_mask_f32")
     return io.give(out.reshape(*lead, F, T))
 
 
@@ -176,10 +213,10 @@ def covariance_to_matrix(Rp: torch.Tensor) -> torch.Tensor:
     return torch.stack([row0, row1], dim=-2)
 
 
-def _pack_covariance(R: torch.Tensor) -> torch.Tensor:
+def _pack_covariance(R: torch.Tensor, wide: bool = False) -> torch.Tensor:
     if R.shape[-1] == 4 and not R.is_complex():
-        return R.to(torch.float32).contiguous()
-    R = R.to(torch.complex64)
+        return R.to(torch.float64 if wide else torch.float32).contiguous()
+    R = R.to(torch.complex128 if wide else torch.complex64)
     return torch.stack([R[..., 0, 0].real, R[..., 1, 1].real, R[..., 0, 1].real, R[..., 0, 1].imag], dim=-1).contiguous()
 
 
@@ -187,15 +224,22 @@ def masked_covariance(Y, noise_w, sqrt_eps: float = 0.0, norm_eps: float = 1e-6,
     """R[f] = sum_t (m + sqrt_eps) y y^H / (sum_t m + norm_eps)  (oracle_debug.py:56-64).
     Y (..., 2, F, T), noise_w (..., F, T) -> (..., F, 2, 2) complex64."""
     io = _Io()
-    Y = io.take(Y, torch.complex64)
-    m = io.take(noise_w, torch.float32)
+    wide = _wide(Y)
+    Y = io.take(Y, torch.complex128 if wide else torch.complex64)
+    m = io.take(noise_w, torch.float64 if wide else torch.float32)
     F, T = Y.shape[-2], Y.shape[-1]
     lead = Y.shape[:-3]
     B = int(np.prod(lead)) if lead else 1
-    Rp = torch.empty((B, F, 4), dtype=torch.float32, device=Y.device)
-    ms = torch.empty((B, F), dtype=torch.float32, device=Y.device)
-    _lib.check(_lib.load().avz_spec_mask_cov_f32(_ptr(Y), _ptr(m), B, F, T, float(sqrt_eps), float(norm_eps), _ptr(Rp),
-                                                 _ptr(ms), _stream()), "avz_spec_mask_cov_f32")
+    if m.numel() != B * F * T:
+        raise ValueError(f"noise weights {tuple(m.shape)} do not match the spectrum {tuple(Y.shape)}")
+    Rp = torch.empty((B, F, 4), dtype=m.dtype, device=Y.device)
+    ms = torch.empty((B, F), dtype=m.dtype, device=Y.device)
+    if wide:
+        _lib.check(_lib.load().avz_spec_mask_cov_f64(_ptr(Y), _ptr(m), B, F, T, float(sqrt_eps), float(norm_eps),
+                                                     _ptr(Rp), _ptr(ms), _stream()), "avz_spec_mask_cov_f64")
+    else:
+        _lib.check(_lib.load().avz_spec_mask_cov_f32(_ptr(Y), _ptr(m), B, F, T, float(sqrt_eps), float(norm_eps), _ptr(Rp),
+                                                     _ptr(ms), _stream()), "avz_spec_mask_cov_f32")
     Rp = Rp.reshape(*lead, F, 4)
     return io.give(Rp if packed else covariance_to_matrix(Rp))
 
@@ -203,18 +247,36 @@ def masked_covariance(Y, noise_w, sqrt_eps: float = 0.0, norm_eps: float = 1e-6,
 _SV_CACHE = {}
 
 
-def steering_vectors(cfg: MvdrConfig, device=None, f_bins=None) -> torch.Tensor:
-    """get_steering_vector for every bin (masked_mvdr.py:22-35), float64 on the host, (F, 2) complex64."""
-    key = (cfg.angle_deg, cfg.mic_dist, cfg.c, cfg.fs, cfg.n_fft, str(device), None if f_bins is None else tuple(f_bins))
+def steering_vectors(cfg: MvdrConfig, device=None, f_bins=None, wide: bool = False) -> torch.Tensor:
+    """get_steering_vector for every bin (masked_mvdr.py:22-35), float64 on the host, (F, 2) complex64 (`wide`: complex128)."""
+    key = (cfg.angle_deg, cfg.mic_dist, cfg.c, cfg.fs, cfg.n_fft, str(device), None if f_bins is None else tuple(f_bins),
+           wide)
     if key not in _SV_CACHE:
         f = cfg.freqs() if f_bins is None else np.asarray(f_bins, dtype=np.float64)
         th = np.deg2rad(cfg.angle_deg)
         tau1 = (cfg.mic_dist / 2) * np.cos(0.0) * np.cos(th - 0) / cfg.c
         tau2 = (cfg.mic_dist / 2) * np.cos(0.0) * np.cos(th - np.pi) / cfg.c
         om = 2 * np.pi * f
-        d = np.stack([np.exp(-1j * om * tau1), np.exp(-1j * om * tau2)], axis=1).astype(np.complex64)
+        d = np.stack([np.exp(-1j * om * tau1), np.exp(-1j * om * tau2)], axis=1).astype(np.complex128 if wide else np.complex64)
         _SV_CACHE[key] = torch.from_numpy(d).to(device if device is not None else "cuda")
     return _SV_CACHE[key]
+
+
+def _take_cov_and_steering(io: "_Io", R, d, wide: bool):
+    """R (..., F, 2, 2) complex or packed (..., F, 4); d (F, 2) or (F, 2, 1) -> packed R, d (F, 2), B, F, lead shape."""
+    cdt, rdt = (torch.complex128, torch.float64) if wide else (torch.complex64, torch.float32)
+    if isinstance(R, np.ndarray):
+        r_dtype = cdt if np.iscomplexobj(R) else rdt
+    else:
+        r_dtype = cdt if R.is_complex() else rdt
+    Rp = _pack_covariance(io.take(R, r_dtype), wide)
+    d = io.take(d, cdt).reshape(-1, 2).contiguous()
+    F = Rp.shape[-2]
+    if d.shape[0] != F:
+        raise ValueError(f"steering vectors cover {d.shape[0]} bins, the covariance {F}")
+    lead = Rp.shape[:-2]
+    B = int(np.prod(lead)) if lead else 1
+    return Rp, d, B, F, lead
 
 
 def mvdr_weights(R, d, cfg: MvdrConfig = PRESETS["baseline_oracle"]):
@@ -222,53 +284,55 @@ def mvdr_weights(R, d, cfg: MvdrConfig = PRESETS["baseline_oracle"]):
     R (..., F, 2, 2) complex or packed (..., F, 4); d (F, 2) or (F, 2, 1) -> w (..., F, 2) complex64.
     Bins below cfg.hp_hz get w = 0 ('zero') or [1, 0] ('mic0')."""
     io = _Io()
-    if isinstance(R, np.ndarray):
-        r_dtype = torch.complex64 if np.iscomplexobj(R) else torch.float32
-    else:
-        r_dtype = torch.complex64 if R.is_complex() else torch.float32
-    R = io.take(R, r_dtype)
-    Rp = _pack_covariance(R)
-    d = io.take(d, torch.complex64).reshape(-1, 2).contiguous()
-    F = Rp.shape[-2]
-    lead = Rp.shape[:-2]
-    B = int(np.prod(lead)) if lead else 1
-    w = torch.empty((B, F, 2), dtype=torch.complex64, device=Rp.device)
+    wide = _wide(R)
+    Rp, d, B, F, lead = _take_cov_and_steering(io, R, d, wide)
+    w = torch.empty((B, F, 2), dtype=torch.complex128 if wide else torch.complex64, device=Rp.device)
     cc = cfg.to_c()
-    _lib.check(_lib.load().avz_mvdr_weights_f32(_ptr(Rp), _ptr(d), B, F, C.byref(cc), _ptr(w), _stream()),
-               "avz_mvdr_weights_f32")
+    if wide:    # sigma and w_eps travel as doubles (1e-7 is not a float32 number)
+        _lib.check(_lib.load().avz_mvdr_weights_f64(_ptr(Rp), _ptr(d), B, F, float(cfg.sigma), float(cfg.w_eps),
+                                                    int(cc.hp_bins), int(cc.hp_mode), _ptr(w), _stream()),
+                   "avz_mvdr_weights_f64")
+    else:
+        _lib.check(_lib.load().avz_mvdr_weights_f32(_ptr(Rp), _ptr(d), B, F, C.byref(cc), _ptr(w), _stream()),
+                   "avz_mvdr_weights_f32")
     return io.give(w.reshape(*lead, F, 2))
 
 
-def hybrid_null_weights(R, d, bypass_bins: int):
+def hybrid_null_weights(R, d, bypass_bins: int, zero_cov_nan: bool = False, round_to_f32: bool = False):
     """Hybrid hard-null weights (Final_pipeline/src/inference.py:56-94) from the interference covariance.
-    R (..., F, 2, 2) complex or packed (..., F, 4); d (F, 2) un-normalised steering vectors -> w (..., F, 2) complex64;
-    bins below `bypass_bins` pass mic 0."""
+    R (..., F, 2, 2) complex or packed (..., F, 4); d (F, 2) un-normalised steering vectors -> w (..., F, 2) complex64
+    (complex128 for float64 / complex128 R); bins below `bypass_bins` pass mic 0.  `zero_cov_nan`: reproduce the
+    reference's NaN for a bin whose principal eigenvector has no mic-0 component (default: delay-and-sum there)."""
     io = _Io()
-    if isinstance(R, np.ndarray):
-        r_dtype = torch.complex64 if np.iscomplexobj(R) else torch.float32
-    else:
-        r_dtype = torch.complex64 if R.is_complex() else torch.float32
-    Rp = _pack_covariance(io.take(R, r_dtype))
-    d = io.take(d, torch.complex64).reshape(-1, 2).contiguous()
-    F = Rp.shape[-2]
-    lead = Rp.shape[:-2]
-    B = int(np.prod(lead)) if lead else 1
-    w = torch.empty((B, F, 2), dtype=torch.complex64, device=Rp.device)
-    _lib.check(_lib.load().avz_hybrid_null_weights_f32(_ptr(Rp), _ptr(d), B, F, int(bypass_bins), _ptr(w), _stream()),
-               "avz_hybrid_null_weights_f32")
+    wide = _wide(R)
+    Rp, d, B, F, lead = _take_cov_and_steering(io, R, d, wide)
+    w = torch.empty((B, F, 2), dtype=torch.complex128 if (wide and not round_to_f32) else torch.complex64, device=Rp.device)
+    lib = _lib.load()
+    # round_to_f32: float64 arithmetic, weights rounded once to complex64 for the float32 pass B
+    fn = (lib.avz_hybrid_null_weights_f64_w32 if round_to_f32 else lib.avz_hybrid_null_weights_f64) if wide \
+        else lib.avz_hybrid_null_weights_f32
+    _lib.check(fn(_ptr(Rp), _ptr(d), B, F, int(bypass_bins), int(bool(zero_cov_nan)), _ptr(w), _stream()),
+               "avz_hybrid_null_weights")
     return io.give(w.reshape(*lead, F, 2))
 
 
 def beamform(w, Y):
     """S[f,t] = w[f]^H Y[:,f,t]  (oracle_debug.py:80).  w (..., F, 2), Y (..., 2, F, T) -> (..., F, T)."""
     io = _Io()
-    w = io.take(w, torch.complex64)
-    Y = io.take(Y, torch.complex64)
+    wide = _wide(w, Y)
+    cdt = torch.complex128 if wide else torch.complex64
+    w = io.take(w, cdt)
+    Y = io.take(Y, cdt)
     F, T = Y.shape[-2], Y.shape[-1]
     lead = Y.shape[:-3]
     B = int(np.prod(lead)) if lead else 1
-    S = torch.empty((B, F, T), dtype=torch.complex64, device=Y.device)
-    _lib.check(_lib.load().avz_beamform_f32(_ptr(w), _ptr(Y), B, F, T, _ptr(S), _stream()), "avz_beamform_f32")
+    if w.numel() != B * F * 2:
+        raise ValueError(f"weights {tuple(w.shape)} do not match the spectrum {tuple(Y.shape)}")
+    S = torch.empty((B, F, T), dtype=cdt, device=Y.device)
+    if wide:
+        _lib.check(_lib.load().avz_beamform_f64(_ptr(w), _ptr(Y), B, F, T, _ptr(S), _stream()), "avz_beamform_f64")
+    else:
+        _lib.check(_lib.load().avz_beamform_f32(_ptr(w), _ptr(Y), B, F, T, _ptr(S), _stream()), "avz_beamform_f32")
     return io.give(S.reshape(*lead, F, T))
 
 
@@ -451,13 +515,25 @@ def ibm_exact_bits(tgt: torch.Tensor, itf: torch.Tensor, cfg: MvdrConfig) -> tor
 
 
 def wave_masked_covariance(mix: torch.Tensor, mask: torch.Tensor, cfg: MvdrConfig,
-                           spec: Optional[torch.Tensor] = None):
+                           spec: Optional[torch.Tensor] = None, wide: bool = False):
     """Learned-mask pass A (full_audio.../inference.py:90,102-108): mix [B,2,L], target-probability mask [B,F,T]
-    -> (R packed [B,F,4], msum [B,F]); noise weight = 1 - mask."""
+    -> (R packed [B,F,4], msum [B,F]); noise weight = 1 - mask.  `wide`: STFT and accumulation in float64 from the
+    same float32 inputs (R, msum float64) for ill-conditioned consumers; no kept spectrum in that mode."""
     lib = _lib.load()
     B, _, L = mix.shape
     F = cfg.n_freq
     dev = mix.device
+    T = num_frames(L, cfg.n_fft, cfg.hop)
+    if tuple(mask.shape) != (B, F, T) or mask.dtype != torch.float32 or not mask.is_contiguous():
+        raise ValueError(f"mask must be a contiguous float32 tensor of shape {(B, F, T)}, got {tuple(mask.shape)} {mask.dtype}")
+    if wide:
+        Rp = torch.empty((B, F, 4), dtype=torch.float64, device=dev)
+        ms = torch.empty((B, F), dtype=torch.float64, device=dev)
+        ws = torch.empty((int(lib.avz_wave_mask_cov_f64_ws_bytes(B, L, cfg.n_fft, cfg.hop)),), dtype=torch.uint8, device=dev)
+        _lib.check(lib.avz_wave_mask_cov_f64(_ptr(mix), _ptr(mask), B, L, cfg.n_fft, cfg.hop, float(cfg.sqrt_eps),
+                                             float(cfg.norm_eps), _ptr(Rp), _ptr(ms), _ptr(ws), _stream()),
+                   "avz_wave_mask_cov_f64")
+        return Rp, ms
     Rp = torch.empty((B, F, 4), dtype=torch.float32, device=dev)
     ms = torch.empty((B, F), dtype=torch.float32, device=dev)
     nws = lib.avz_ibm_cov_ws_bytes(B, L, cfg.n_fft, cfg.hop)

@@ -33,6 +33,11 @@ class MvdrStream:
         self.out = torch.empty((self.S, 128), dtype=torch.float32, device=device)
         _lib.check(self.lib.avz_init(512), "avz_init")
 
+    def reset(self) -> None:
+        """Forget everything: the next step() is hop 0 of a new set of streams."""
+        self.h = 0
+        self.state.zero_()
+
     def step(self, hop_in: torch.Tensor, noise_w: Optional[torch.Tensor] = None, t_end: int = INT_MAX) -> torch.Tensor:
         """hop_in [S,2,128] f32 (CUDA), noise_w [S,257] or None -> [S,128] output hop (valid from the 4th call on)."""
         _lib.check(self.lib.avz_stream_step_f32(_ptr(self.state), _ptr(hop_in), _ptr(noise_w), _ptr(self.d), self.S,
@@ -46,6 +51,7 @@ class MvdrStream:
         noise weights (T = L/128 + 1) -> [S, L]; equals `oracle.streaming_mvdr` on each stream."""
         S, _, L = mix.shape
         assert L % 128 == 0 and S == self.S
+        self.reset()                      # a recording starts from silence: frame index 0, empty covariance and tails
         H = L // 128
         T = H + 1
         out = torch.empty((S, L), dtype=torch.float32, device=mix.device)

@@ -1,0 +1,217 @@
+"""Memory-safety evidence without compute-sanitizer (closed on this pool): every output and workspace
+buffer of the fused kernels is carved out of a larger allocation with poisoned guard bands on both sides; after the
+kernels have run on ragged / odd / minimal shapes the bands must be untouched.  Plus argument checks of the C ABI."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BAND = 4096          # bytes on each side
+POISON = 0xA5
+
+
+@pytest.fixture(scope="module")
+def az():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import avzoom
+    avzoom._lib.load()
+    return avzoom
+
+
+class Guard:
+    """Hands out tensors that live between two poisoned bands and checks the bands afterwards."""
+
+    def __init__(self):
+        self.bufs = []
+
+    def like(self, t: torch.Tensor) -> torch.Tensor:
+        n = t.numel() * t.element_size()
+        pad = (-n) % 256
+        raw = torch.full((BAND + n + pad + BAND,), POISON, dtype=torch.uint8, device=t.device)
+        view = raw[BAND:BAND + n].view(t.dtype).view(t.shape)
+        self.bufs.append((raw, n))
+        return view
+
+    def empty(self, shape, dtype) -> torch.Tensor:
+        return self.like(torch.empty(shape, dtype=dtype, device="cuda"))
+
+    def check(self):
+        torch.cuda.synchronize()
+        for i, (raw, n) in enumerate(self.bufs):
+            lo, hi = raw[:BAND], raw[BAND + n:]
+            assert bool((lo == POISON).all()), f"buffer {i}: bytes before the buffer were written"
+            assert bool((hi == POISON).all()), f"buffer {i}: bytes after the buffer were written"
+
+
+@pytest.mark.parametrize("preset,B,L", [("baseline_oracle", 3, 12345), ("baseline_oracle", 1, 512), ("baseline_oracle", 2, 513),
+                                        ("oracle_debug", 3, 7001), ("oracle_debug", 2, 512), ("baseline_oracle", 37, 4000)])
+@pytest.mark.parametrize("keep", [True, False])
+def test_oracle_engine_stays_inside_its_buffers(az, preset, B, L, keep):
+    from avzoom import pipeline, synth
+    cfg = az.PRESETS[preset]
+    mix, tgt, itf = synth.make_batch(5, min(B, 4), L / 16000.0, 2)
+    rep = (B + mix.shape[0] - 1) // mix.shape[0]
+    mix, tgt, itf = (np.tile(a, (rep,) + (1,) * (a.ndim - 1))[:B, ..., :L].copy() for a in (mix, tgt, itf))
+    g = Guard()
+    mix_d, tgt_d, itf_d = (g.like(torch.from_numpy(a).cuda()) for a in (mix, tgt, itf))
+    mix_d.copy_(torch.from_numpy(mix)); tgt_d.copy_(torch.from_numpy(tgt)); itf_d.copy_(torch.from_numpy(itf))
+    e = pipeline.OracleMvdr(cfg, B, L, mix_d.device, keep_spectrum=keep)
+    ref = e.run(mix_d, tgt_d, itf_d).clone()
+    for name in ("bits", "R", "msum", "w", "out", "peak", "ws", "spec"):
+        t = getattr(e, name)
+        if t is not None:
+            setattr(e, name, g.like(t))
+    e.peak.zero_()
+    out = e.run(mix_d, tgt_d, itf_d)
+    g.check()
+    assert torch.equal(out, ref)                       # and the guarded run computes the same bits
+
+
+@pytest.mark.parametrize("n_fft,hop,B,L", [(1024, 512, 3, 32000), (1024, 512, 2, 1024), (1024, 512, 5, 1537), (512, 128, 3, 9999),
+                                           (512, 256, 2, 777), (256, 64, 2, 1000)])
+def test_learned_path_stays_inside_its_buffers(az, n_fft, hop, B, L):
+    import dataclasses
+    lib = az._lib.load()
+    cfg = dataclasses.replace(az.PRESETS["full_audio"], n_fft=n_fft, hop=hop)
+    rng = np.random.default_rng(0)
+    F, T = cfg.n_freq, az.num_frames(L, n_fft, hop)
+    g = Guard()
+    mix = g.empty((B, 2, L), torch.float32)
+    mix.copy_(torch.from_numpy(rng.standard_normal((B, 2, L)).astype(np.float32)))
+    mask = g.empty((B, F, T), torch.float32)
+    mask.copy_(torch.from_numpy(rng.uniform(0.05, 0.95, (B, F, T)).astype(np.float32)))
+    p, st = az.ops._ptr, az.ops._stream
+    X = g.empty((B, 2, F, T), torch.float32)
+    az._lib.check(lib.avz_wave_features_f32(p(mix), B, L, n_fft, hop, 0, p(X), st()), "features")
+    Xp = g.empty((B, F, T, 4), torch.float32)
+    az._lib.check(lib.avz_wave_features_f32(p(mix), B, L, n_fft, hop, 2, p(Xp), st()), "features(physics)")
+    Rp, ms = g.empty((B, F, 4), torch.float32), g.empty((B, F), torch.float32)
+    ws = g.empty((max(int(lib.avz_ibm_cov_ws_bytes(B, L, n_fft, hop)), 4),), torch.uint8)
+    nspec = int(lib.avz_spec_ws_bytes(B, L, n_fft, hop))
+    w = g.empty((B, F, 2), torch.complex64)
+    out, peak = g.empty((B, (T - 1) * hop), torch.float32), g.empty((B,), torch.float32)
+    cc = cfg.to_c()
+    d = az.steering_vectors(cfg, mix.device)
+    outs = []
+    for keep in ((True, False) if nspec > 0 else (False,)):
+        spec = g.empty((nspec,), torch.uint8) if keep else None
+        if keep:
+            az._lib.check(lib.avz_wave_mask_cov_keep_f32(p(mix), p(mask), B, L, n_fft, hop, 0.0, 1e-6, p(Rp), p(ms), p(ws),
+                                                         p(spec), st()), "cov keep")
+        else:
+            az._lib.check(lib.avz_wave_mask_cov_f32(p(mix), p(mask), B, L, n_fft, hop, 0.0, 1e-6, p(Rp), p(ms), p(ws), st()), "cov")
+        az._lib.check(lib.avz_mvdr_weights_f32(p(Rp), p(d), B, F, C.byref(cc), p(w), st()), "weights")
+        peak.zero_()
+        if keep:
+            az._lib.check(lib.avz_mvdr_apply_kept_f32(p(spec), p(w), p(None), p(mask), B, L, n_fft, hop, C.byref(cc), p(out),
+                                                      p(peak), st()), "apply kept")
+        else:
+            az._lib.check(lib.avz_mvdr_apply_f32(p(mix), p(w), p(None), p(mask), B, L, n_fft, hop, C.byref(cc), p(out), p(peak),
+                                                 st()), "apply")
+        outs.append(out.clone())
+    g.check()
+    assert bool(torch.isfinite(outs[0]).all())
+    if len(outs) == 2:
+        assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("R,Lrec", [(2, 40000), (3, 16001), (1, 70007)])
+def test_chunk_kernels_stay_inside_their_buffers(az, R, Lrec):
+    from avzoom.core import chunked
+    lib = az._lib.load()
+    cfg = az.PRESETS["full_audio"]
+    win, stride = 32000, 16000
+    n = chunked.n_windows(Lrec, win)
+    B, F, T = R * n, 513, 64
+    rng = np.random.default_rng(1)
+    g = Guard()
+    rec = g.empty((R, 2, Lrec), torch.float32)
+    rec.copy_(torch.from_numpy(rng.standard_normal((R, 2, Lrec)).astype(np.float32)))
+    mask = g.empty((B, F, T), torch.float32)
+    mask.copy_(torch.from_numpy(rng.uniform(0.05, 0.95, (B, F, T)).astype(np.float32)))
+    p, st = az.ops._ptr, az.ops._stream
+    cv = az._lib.AvzChunkView(Lrec, n, stride)
+    X = g.empty((B, 2, F, T), torch.float32)
+    az._lib.check(lib.avz_chunk_features_f32(p(rec), R, C.byref(cv), win, 1024, 512, 0, p(X), st()), "chunk features")
+    Rp, ms = g.empty((B, F, 4), torch.float32), g.empty((B, F), torch.float32)
+    ws = g.empty((max(int(lib.avz_ibm_cov_ws_bytes(B, win, 1024, 512)), 4),), torch.uint8)
+    spec = g.empty((int(lib.avz_spec_ws_bytes(B, win, 1024, 512)),), torch.uint8)
+    az._lib.check(lib.avz_chunk_mask_cov_f32(p(rec), p(mask), R, C.byref(cv), win, 1024, 512, 0.0, 1e-6, p(Rp), p(ms), p(ws),
+                                             p(spec), st()), "chunk cov")
+    R64, ms64 = g.empty((B, F, 4), torch.float64), g.empty((B, F), torch.float64)
+    ws64 = g.empty((int(lib.avz_wave_mask_cov_f64_ws_bytes(B, win, 1024, 512)),), torch.uint8)
+    az._lib.check(lib.avz_chunk_mask_cov_f64(p(rec), p(mask), R, C.byref(cv), win, 1024, 512, 0.0, 1e-6, p(R64), p(ms64),
+                                             p(ws64), st()), "chunk cov f64")
+    assert float((Rp.double() - R64).abs().max() / R64.abs().max()) < 1e-5
+    w = g.empty((B, F, 2), torch.complex64)
+    cc = cfg.to_c()
+    az._lib.check(lib.avz_mvdr_weights_f32(p(Rp), p(az.steering_vectors(cfg, rec.device)), B, F, C.byref(cc), p(w), st()), "w")
+    outs = g.empty((B, 32256), torch.float32)
+    res = []
+    for sp in (spec, None):
+        az._lib.check(lib.avz_chunk_mvdr_apply_f32(p(rec), p(sp), p(w), p(mask), R, C.byref(cv), win, 1024, 512, C.byref(cc),
+                                                   p(outs), p(None), st()), "chunk apply")
+        res.append(outs.clone())
+    assert torch.equal(res[0], res[1])
+    final, peak = g.empty((R, Lrec), torch.float32), g.empty((R,), torch.float32)
+    peak.zero_()
+    for use in (32000, 32256):
+        az._lib.check(lib.avz_chunk_ola_f32(p(outs), R, n, 32256, Lrec, stride, use, p(final), p(peak), st()), "chunk ola")
+    g.check()
+    assert bool(torch.isfinite(final).all()) and torch.allclose(peak, final.abs().amax(dim=1))
+
+
+def test_argument_checks(az):
+    """Errors are codes + messages, never a launch with bad geometry (include/avzoom.h conventions)."""
+    lib = az._lib.load()
+    x = torch.zeros((1, 1, 300), dtype=torch.float32, device="cuda")
+    Y = torch.zeros((1, 1, 257, 8), dtype=torch.complex64, device="cuda")
+    p, st = az.ops._ptr, az.ops._stream
+    # L < n_fft: scipy would shrink nperseg (the reference then indexes out of range) - rejected, with a message
+    assert lib.avz_stft_f32(p(x), 1, 1, 300, 512, 128, p(Y), st()) == -1
+    assert b"shorter than n_fft" in lib.avz_last_error()
+    with pytest.raises(az._lib.AvzError, match="shorter than n_fft"):
+        az.stft(np.zeros(300, np.float32), 512, 128)
+    with pytest.raises(az._lib.AvzError):
+        az.oracle_mask_mvdr(np.zeros((2, 300), np.float32), np.zeros(300, np.float32), np.zeros(300, np.float32))
+    assert lib.avz_stft_f32(p(x), 1, 1, 300, 500, 125, p(Y), st()) == -1          # n_fft not supported
+    assert lib.avz_stft_f32(p(x), 1, 1, 300, 256, 100, p(Y), st()) == -1          # hop does not divide n_fft
+    assert lib.avz_stft_f32(p(None), 1, 1, 300, 256, 64, p(Y), st()) == -1        # null pointer
+    assert lib.avz_ibm_cov_ws_bytes(70000, 4000, 512, 128) >= 0
+    z = torch.zeros(16, dtype=torch.float32, device="cuda")
+    assert lib.avz_ibm_cov_f32(p(z), p(z), p(z), 70000, 4000, 512, 128, 1e-6, p(z), p(z), p(z), p(z), st()) == -1   # B > 65535
+    # shape mismatches are caught in the Python wrappers before any launch
+    with pytest.raises(ValueError):
+        az.masked_covariance(torch.zeros((2, 257, 8), dtype=torch.complex64, device="cuda"),
+                             torch.zeros((257, 9), dtype=torch.float32, device="cuda"))
+    with pytest.raises(ValueError):
+        az.beamform(torch.zeros((100, 2), dtype=torch.complex64, device="cuda"),
+                    torch.zeros((2, 257, 8), dtype=torch.complex64, device="cuda"))
+    with pytest.raises(ValueError):
+        az.mvdr_weights(torch.zeros((257, 4), dtype=torch.float32, device="cuda"),
+                        torch.zeros((100, 2), dtype=torch.complex64, device="cuda"))
+
+
+def test_unfused_ops_at_baseline_batch_size(az):
+    """B * F exceeds 65535 (the limit of grid.y / grid.z) from B = 256 on: the unfused ops at B = 1024."""
+    rng = np.random.default_rng(2)
+    B, F, T = 1024, 257, 12
+    Y = torch.from_numpy((rng.standard_normal((B, 2, F, T)) + 1j * rng.standard_normal((B, 2, F, T))).astype(np.complex64)).cuda()
+    w = torch.from_numpy((rng.standard_normal((B, F, 2)) + 1j * rng.standard_normal((B, F, 2))).astype(np.complex64)).cuda()
+    S = az.beamform(w, Y)
+    want = (w[:, :, 0].conj()[:, :, None] * Y[:, 0] + w[:, :, 1].conj()[:, :, None] * Y[:, 1])
+    assert float((S - want).abs().max()) < 1e-5
+    m = az.geometric_mask(Y)
+    assert m.shape == (B, F, T) and set(np.unique(m.cpu().numpy()).tolist()) <= {np.float32(0.01), np.float32(1.0)}
+    X = az.logmag_ipd(Y)
+    assert X.shape == (B, 2, F, T) and bool(torch.isfinite(X).all())
+    assert torch.equal(X[1000], az.logmag_ipd(Y[1000]))
+    nw = torch.from_numpy(rng.random((B, F, T)).astype(np.float32)).cuda()
+    R = az.masked_covariance(Y, nw, packed=True)
+    assert torch.equal(R[777], az.masked_covariance(Y[777], nw[777], packed=True))
+    wts = az.mvdr_weights(R, az.steering_vectors(az.PRESETS["baseline_oracle"], Y.device), az.PRESETS["baseline_oracle"])
+    assert wts.shape == (B, F, 2) and bool(torch.isfinite(torch.view_as_real(wts)).all())

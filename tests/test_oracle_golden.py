@@ -149,3 +149,37 @@ def test_hybrid_hard_null(helpers):
                              helpers["asv_f_bins"])
     assert got.shape == (513, 64)
     assert rel_l2(got, helpers["hn_out"]) < 1e-12
+
+
+@pytest.fixture(scope="module")
+def drivers(golden_dir):
+    return np.load(os.path.join(golden_dir, "ref_chunk_drivers.npz"))
+
+
+def test_tflite_era_chunk_drivers(speech, learned, drivers):
+    """process_audio_file (tf_lite_version/inference.py:245-391) and enhance_audio (Final_pipeline/src/inference.py:
+    144-238), run unmodified with their TFLite interpreter replaced by a replay of seeded masks."""
+    L = int(learned["L"])
+    mix = _pcm(speech["mix_pcm"])[:L]
+    masks = learned["masks"]
+    for bf, key, kw in (("batch_mvdr", "process_audio_file_out", dict(mic_dist=0.04)),
+                        ("hybrid_null", "enhance_audio_out", dict(mic_dist=0.08))):
+        it = iter(masks)
+        got = O.chunked_enhance_clipped(mix, lambda lm, ipd: next(it), bf, **kw)
+        assert got.shape == (L,)
+        assert rel_l2(got, drivers[key + "_f64read"]) < 1e-9
+        it = iter(masks)
+        got32 = O.chunked_enhance_clipped(mix.astype(np.float32), lambda lm, ipd: next(it), bf, **kw)
+        assert rel_l2(got32, drivers[key + "_f32read"]) < 2e-5   # as shipped the reference's STFT and einsum are complex64
+
+
+def test_hybrid_hard_null_degenerate_bin(helpers, drivers):
+    """An interference covariance that is exactly zero above the bypass: the reference raises (np.linalg.cond of a NaN
+    matrix), and so does the restatement; without that bin both agree."""
+    Y = drivers["hn_nan_Y"].astype(np.complex128)
+    f = helpers["asv_f_bins"]
+    assert str(drivers["hn_nan_raised"]).startswith("LinAlgError")
+    with pytest.raises(np.linalg.LinAlgError), np.errstate(all="ignore"):
+        O.hybrid_hard_null(Y, drivers["hn_nan_mask"].astype(np.float64), f)
+    got = O.hybrid_hard_null(Y, drivers["hn_ok_mask"].astype(np.float64), f)
+    assert rel_l2(got, drivers["hn_ok_out"]) < 1e-12
