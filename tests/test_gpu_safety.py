@@ -51,11 +51,12 @@ class Guard:
                                         ("oracle_debug", 3, 7001), ("oracle_debug", 2, 512), ("baseline_oracle", 37, 4000)])
 @pytest.mark.parametrize("keep", [True, False])
 def test_oracle_engine_stays_inside_its_buffers(az, preset, B, L, keep):
-    from avzoom import pipeline, synth
+    from avzoom import pipeline
     cfg = az.PRESETS[preset]
-    mix, tgt, itf = synth.make_batch(5, min(B, 4), L / 16000.0, 2)
-    rep = (B + mix.shape[0] - 1) // mix.shape[0]
-    mix, tgt, itf = (np.tile(a, (rep,) + (1,) * (a.ndim - 1))[:B, ..., :L].copy() for a in (mix, tgt, itf))
+    rng = np.random.default_rng(B * 100003 + L)
+    tgt = rng.standard_normal((B, L)).astype(np.float32) * (rng.random((B, L)) < 0.6)      # gaps: a non-trivial IBM
+    itf = rng.standard_normal((B, L)).astype(np.float32) * (rng.random((B, L)) < 0.6)
+    mix = np.stack([tgt + itf, np.roll(tgt, 1, axis=1) + np.roll(itf, -1, axis=1)], axis=1).astype(np.float32)
     g = Guard()
     mix_d, tgt_d, itf_d = (g.like(torch.from_numpy(a).cuda()) for a in (mix, tgt, itf))
     mix_d.copy_(torch.from_numpy(mix)); tgt_d.copy_(torch.from_numpy(tgt)); itf_d.copy_(torch.from_numpy(itf))
@@ -68,7 +69,7 @@ def test_oracle_engine_stays_inside_its_buffers(az, preset, B, L, keep):
     e.peak.zero_()
     out = e.run(mix_d, tgt_d, itf_d)
     g.check()
-    assert torch.equal(out, ref)                       # and the guarded run computes the same bits
+    assert bool(torch.isfinite(ref).all()) and torch.equal(out, ref)     # and the guarded run computes the same bits
 
 
 @pytest.mark.parametrize("n_fft,hop,B,L", [(1024, 512, 3, 32000), (1024, 512, 2, 1024), (1024, 512, 5, 1537), (512, 128, 3, 9999),
