@@ -42,88 +42,103 @@ METRIC = "audio-sec/sec mask-MVDR (2-mic,16kHz)"
 UNIT = "audio-s/s"
 
 
-# ------------------------------------------------------------------------------------------ CPU baseline
-def _oracle_one(seed_args):
+# ------------------------------------------------------------------------------------------ workload / CPU baseline
+def workload_config():
+    """The `config` both arms print: BASELINE config 2, the configuration the metric is quoted on."""
+    return {"workload": "BASELINE config 2: 1024 synthetic 4 s 2-ch far-field mixtures per GPU, 1 target + 3 interferers, "
+                        "oracle IBM mask-MVDR, n_fft 512 hop 128",
+            "utterances_per_gpu_per_step": UTT_PER_GPU, "samples_per_utterance": int(DUR_S * FS), "n_fft": 512, "hop": 128,
+            "interferers": N_INTERF, "fs": FS}
+
+
+_G = {}          # inputs inherited by the forked CPU workers (copy-on-write: nothing is pickled per task)
+
+
+def _oracle_idx(u):
     import oracle as O
-    from avzoom import synth
-    mix, tgt, itf = synth.make_mixture(*seed_args)
     t0 = time.perf_counter()
-    O.oracle_mask_mvdr(mix, tgt, itf, O.PRESETS["baseline_oracle"])
+    O.oracle_mask_mvdr(_G["mix"][u], _G["tgt"][u], _G["itf"][u], O.PRESETS["baseline_oracle"])
     return time.perf_counter() - t0
 
 
-def cpu_baseline(n_utt: int | None = None):
-    """The reference's algorithm (oracle port of rt_av_zoom/core/oracle_debug.py:42-94, float64, per-bin python
-    loops as written) over a bounded sample of the workload, one process per host core."""
-    import multiprocessing as mp
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
-    os.environ.setdefault("MKL_NUM_THREADS", "1")
-    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
-    cores = os.cpu_count() or 1
-    if n_utt is None:
-        n_utt = UTT_PER_GPU                              # the whole config-2 batch: ~25-30 CPU-s of algorithm time
-    L = int(DUR_S * FS)
-    args = [(1_000_003 * CONFIG_ID + u, L, N_INTERF) for u in range(n_utt)]
-    with mp.get_context("fork").Pool(cores) as pool:
-        pool.map(_oracle_one, args[:cores])            # warm the workers (imports, FFT plans)
-        t0 = time.perf_counter()
-        per = pool.map(_oracle_one, args, chunksize=max(1, n_utt // (cores * 4)))
-        wall = time.perf_counter() - t0
-    # wall includes generating the inputs in the workers; the algorithm's own time is `per`
-    algo_cpu_s = float(sum(per))
-    eff_wall = algo_cpu_s / cores
-    return {
-        "value": n_utt * DUR_S / eff_wall,
-        "unit": UNIT,
-        "cores": cores,
-        "kind": "port",
-        "sample": f"{n_utt} utterances x {DUR_S:g} s of config 2, float64 numpy/scipy oracle, {cores} processes x 1 thread; "
-                  f"{algo_cpu_s:.1f} CPU-s of algorithm time (single core: {n_utt * DUR_S / algo_cpu_s:.1f} audio-s/s)",
-        "wall_s_incl_input_generation": wall,
-    }
-
-
-def run_reference(args):
-    """Reference arm: the oracle port (the reference's own algorithm, float64 numpy/scipy) on all host cores.  One
-    worker pool for the whole run; each of the K steps is a bounded sample of the config-2 workload, sized so that
-    W + K steps stay within ~3 batches (3072 utterances, ~80 CPU-s) in total."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def _cpu_pool(mix, tgt, itf):
     import multiprocessing as mp
     for v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
         os.environ.setdefault(v, "1")
+    _G.update(mix=mix, tgt=tgt, itf=itf)
+    cores = os.cpu_count() or 1
+    pool = mp.get_context("fork").Pool(cores)
+    pool.map(_oracle_idx, range(min(2 * cores, len(mix))))      # warm the workers (imports, FFT plans)
+    return pool, cores
+
+
+def _cpu_step(pool, cores, n_utt):
+    """One pass of the reference's algorithm over utterances 0..n_utt-1, inputs resident in host memory:
+    WALL-CLOCK seconds on all cores, and the summed per-utterance algorithm time."""
+    t0 = time.perf_counter()
+    per = pool.map(_oracle_idx, range(n_utt), chunksize=max(1, n_utt // (cores * 8)))
+    return time.perf_counter() - t0, float(sum(per))
+
+
+def cpu_baseline(mix, tgt, itf):
+    """The reference's algorithm (oracle port of rt_av_zoom/core/oracle_debug.py:42-94, float64, per-bin python loops as
+    written) over the whole config-2 batch, one process per host core, inputs already in host memory."""
+    pool, cores = _cpu_pool(mix, tgt, itf)
+    try:
+        n_utt = len(mix)
+        wall, cpu_s = _cpu_step(pool, cores, n_utt)
+    finally:
+        pool.close()
+    return {"value": n_utt * DUR_S / wall, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n_utt} utterances x {DUR_S:g} s of config 2 (the whole batch of one step), float64 numpy/scipy oracle, "
+                      f"{cores} processes x 1 thread, inputs resident in host memory; value = audio seconds / WALL-CLOCK "
+                      f"seconds ({wall:.2f} s)",
+            "wall_s": wall, "algorithm_cpu_s": cpu_s, "per_core_audio_s_per_s": n_utt * DUR_S / cpu_s,
+            "if_cores_scaled_perfectly": n_utt * DUR_S / (cpu_s / cores)}
+
+
+def run_reference(args):
+    """Reference arm: the oracle port (the reference's own algorithm, float64 numpy/scipy) on all host cores, on the
+    same config as our arm: every step is one pass over the 1024 utterances of the config-2 batch (wall-clock)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from avzoom import synth
     t_all = time.perf_counter()
     cores = os.cpu_count() or 1
     K, W = max(1, args.steps), max(0, args.warmup)
-    n_utt = max(cores, min(UTT_PER_GPU, 3 * UTT_PER_GPU // (K + W)))
-    L = int(DUR_S * FS)
-    vals, cpu_s = [], 0.0
-    with mp.get_context("fork").Pool(cores) as pool:
-        nxt = 0
+    mix, tgt, itf = synth.make_batch(CONFIG_ID, UTT_PER_GPU, DUR_S, N_INTERF, workers=max(1, min(32, cores)))
+    t_gen = time.perf_counter() - t_all
+    pool, cores = _cpu_pool(mix, tgt, itf)
+    # a step is ~25 CPU-s; keep the whole run within a few minutes on small hosts by shortening the step if needed
+    probe_wall, _ = _cpu_step(pool, cores, 4 * cores)
+    est_step = probe_wall * UTT_PER_GPU / (4 * cores)
+    n_utt = UTT_PER_GPU if est_step * (K + W) <= 240.0 else max(cores, int(UTT_PER_GPU * 240.0 / (est_step * (K + W))))
+    walls, cpu_s = [], 0.0
+    try:
         for step in range(W + K):
-            sample = [(1_000_003 * CONFIG_ID + (nxt + u) % UTT_PER_GPU, L, N_INTERF) for u in range(n_utt)]
-            nxt += n_utt
-            per = pool.map(_oracle_one, sample, chunksize=max(1, n_utt // (cores * 4)))
+            wall, cs = _cpu_step(pool, cores, n_utt)
             if step >= W:
-                algo = float(sum(per))
-                cpu_s += algo
-                vals.append(n_utt * DUR_S / (algo / cores))
-    v = statistics.median(vals)
+                walls.append(wall)
+                cpu_s += cs
+    finally:
+        pool.close()
+    total = float(sum(walls))
+    v = K * n_utt * DUR_S / total
+    cfg = workload_config()
+    if n_utt != UTT_PER_GPU:
+        cfg = dict(cfg, utterances_per_gpu_per_step=n_utt, note="step shortened to keep the run within a few minutes")
     base = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{K} steps x {n_utt} utterances x {DUR_S:g} s of config 2 (utterance index wraps at {UTT_PER_GPU}), float64 "
-                      f"numpy/scipy oracle, {cores} processes x 1 thread; {cpu_s:.1f} CPU-s of algorithm time in the timed steps; "
-                      "value = median over steps of utterance-seconds / (summed per-utterance algorithm time / cores)"}
+            "sample": f"{K} steps x {n_utt} utterances x {DUR_S:g} s of config 2, float64 numpy/scipy oracle, {cores} processes x "
+                      f"1 thread, inputs resident in host memory; value = audio seconds / wall-clock seconds of the timed steps",
+            "wall_s": total, "algorithm_cpu_s": cpu_s, "per_core_audio_s_per_s": K * n_utt * DUR_S / cpu_s}
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
-        "warmup": W, "ms_per_step": 1e3 * cpu_s / cores / K, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "BASELINE config 2 (bounded sample per step): 4 s 2-ch far-field mixtures, 1 target + 3 "
-                               "interferers, oracle IBM mask-MVDR, n_fft 512 hop 128", "utterances_per_step": n_utt,
-                   "utterance_s": DUR_S},
+        "warmup": W, "ms_per_step": 1e3 * total / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
         "cpu_baseline": base,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "total_s": time.perf_counter() - t_all,
+        "gpu_launches": 0, "input_generation_s": round(t_gen, 2), "total_s": time.perf_counter() - t_all,
     }
     print(json.dumps(line), flush=True)
 
@@ -186,6 +201,18 @@ def load_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _traffic_record():
+    """DRAM bytes and warp-instruction counts per launch from the committed ncu --set full capture (newest round first)."""
+    for name in ("r2_ncu_traffic.json", "r1_ncu_traffic.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            try:
+                return json.load(open(path)), "profiles/" + name
+            except Exception:
+                pass
+    return None, None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -245,8 +272,27 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def gather_floats(x: float):
+        if world == 1:
+            return [x]
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        out = torch.empty((world,), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(out, t)
+        return [float(v) for v in out.tolist()]
+
+    def timed_loop(n_steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(n_steps):
+            loop.submit(mix, tgt, itf)
+        loop.join()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
     # ---- device-resident throughput
-    for _ in range(args.warmup):
+    for _ in range(max(3, args.warmup)):
         enh.run(mix, tgt, itf)
         loop.submit(mix, tgt, itf)
     loop.join()
@@ -264,20 +310,16 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
-    e0.record()
-    for _ in range(args.steps):
-        loop.submit(mix, tgt, itf)
-    loop.join()
-    e1.record()
-    barrier()
-    t_wall1 = time.perf_counter()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    ms_total = timed_loop(args.steps)
     ms_per_step = ms_total / args.steps
     value = audio_s_per_step / (ms_per_step * 1e-3)
+    # the same loop for >= 1 s (the K steps above last tens of milliseconds): thermal / clock steady state, more clock samples
+    n_long = max(args.steps, int(1200.0 / max(ms_per_step, 1e-3)))
+    ms_long = timed_loop(n_long) / n_long
+    t_wall1 = time.perf_counter()
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    value_long = audio_s_per_step / (ms_long * 1e-3)
 
     # ---- per-kernel timing for the roofline (CUDA events on the launching stream, same resident inputs)
     ktimes = enh.time_each_kernel(mix, tgt, itf, iters=max(3, min(args.steps, 10)))
@@ -291,93 +333,140 @@ def run_ours(args):
             "k_peak_normalise": 8.0 * samples}
     dom = max(algo, key=lambda k: ktimes.get(k, 0.0))
     achieved = algo[dom] / (ktimes[dom] * 1e-3) / 1e9
-    traffic, traffic_src = None, None
-    issue = None
-    try:  # DRAM bytes per launch of that kernel from the committed ncu --set full capture of the same shape
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
-        traffic = tj["per_launch"][dom]["dram_read_bytes"] + tj["per_launch"][dom]["dram_write_bytes"]
-        traffic_src = "profiles/r1_ncu_traffic.json (" + tj["source"] + ")"
-        # what actually bounds the transform kernels: warp-instruction issue slots (4 schedulers per SM, one
-        # instruction per clock each).  Instruction counts from the same ncu capture, times live.
-        sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        clk_hz = 1e6 * (((clocks or {}).get("sm_mhz")) or 1965.0)
-        slots_per_s = sms * 4 * clk_hz
-        issue = {"unit": "fraction of warp-instruction issue slots", "peak_slots_per_s": slots_per_s, "kernels": {
-            k: (tj["per_launch"][k]["warp_instructions"] * B / 1024.0) / (ktimes[k] * 1e-3) / slots_per_s
-            for k in ("k512_ibm", "k512_cov", "k512_apply") if ktimes.get(k)},
-            "note": "instruction counts per launch from profiles/r1_ncu_traffic.json (ncu smsp__inst_executed.sum at "
-                    "B = 1024), divided by the CUDA-event kernel time measured in this run"}
-    except Exception:
-        pass
+    traffic, traffic_src, issue = None, None, None
+    tj, tj_name = _traffic_record()
+    if tj is not None:
+        try:
+            traffic = tj["per_launch"][dom]["dram_read_bytes"] + tj["per_launch"][dom]["dram_write_bytes"]
+            traffic_src = tj_name + " (" + tj["source"] + ")"
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            clk_hz = 1e6 * (((clocks or {}).get("sm_mhz")) or 1965.0)
+            slots_per_s = sms * 4 * clk_hz
+            issue = {"unit": "fraction of warp-instruction issue slots", "peak_slots_per_s": slots_per_s, "kernels": {
+                k: (tj["per_launch"][k]["warp_instructions"] * B / 1024.0) / (ktimes[k] * 1e-3) / slots_per_s
+                for k in ("k512_ibm", "k512_cov", "k512_apply") if ktimes.get(k)},
+                "dram_GBps": {k: (tj["per_launch"][k]["dram_read_bytes"] + tj["per_launch"][k]["dram_write_bytes"]) * (B / 1024.0)
+                              / (ktimes[k] * 1e-3) / 1e9 for k in ("k512_ibm", "k512_cov", "k512_apply", "k_peak_normalise")
+                              if ktimes.get(k)},
+                "note": "instruction and DRAM byte counts per launch from " + tj_name + " (ncu at B = 1024), divided by the "
+                        "CUDA-event kernel time measured in this run"}
+        except Exception:
+            pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                 "frac": achieved / peak_gbs, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo[dom], "kernel_ms": ktimes,
-                "note": "fp32-issue-bound path (DESIGN.md 3.1): ~2540 warp-instructions per frame set the time, not HBM",
+                "note": "the transforms make this path instruction-issue / FMA-pipe bound, not HBM-bound (DESIGN.md 3.1); the "
+                        "two passes around the kept spectrum also run at 70-80 % of the DRAM peak",
                 "path_achieved_GBps": (value / world) * FS * ALGO_BYTES_PER_SAMPLE / 1e9,
                 "path_frac_of_hbm_roofline": (value / world) * FS * ALGO_BYTES_PER_SAMPLE / (peak_gbs * 1e9),
                 "issue_slots": issue}
 
-    # ---- end to end through the public host-buffer API
-    e2e_steps = max(2, min(args.steps, 5))
+    # ---- end to end through the public host-buffer API: pinned host buffers in, enhanced waveforms + scores back in
+    # pinned host memory, every step; steps are submitted back to back (submit / wait), so step k+1's first copy
+    # overlaps step k's compute and drain - the steady state of a serving loop
+    e2e_steps = max(3, min(args.steps, 8))
+    h2d_bytes = int(mix_p.numel() + tgt_p.numel() + itf_p.numel()) * 4
+    out_len = enh.out_len
+
+    def e2e_leg(host, a, b_, c):
+        host.run(a, b_, c)                               # warm-up (allocates nothing afterwards)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        last = None
+        for _ in range(e2e_steps):
+            tk = host.submit(a, b_, c)
+            if last is not None:
+                host.wait(last)                          # the consumer takes step k while step k+1 is in flight
+            last = tk
+        res = host.wait(last)
+        host.join()
+        g1.record()
+        barrier()
+        return max_over_ranks(g0.elapsed_time(g1)) / e2e_steps, res
+
     host = pipeline.HostPipeline(enh, world)
-    host.run(mix_p, tgt_p, itf_p)                       # warm-up (allocates pinned result buffers)
-    barrier()
-    t0 = time.perf_counter()
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record()
-    for _ in range(e2e_steps):
-        out_h, scores_h = host.run(mix_p, tgt_p, itf_p)
-    g1.record()
-    barrier()
-    e2e_ms = max_over_ranks(g0.elapsed_time(g1)) / e2e_steps
-    e2e = {"value": audio_s_per_step / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-           "h2d_bytes_per_step": int(mix_p.numel() + tgt_p.numel() + itf_p.numel()) * 4,
-           "d2h_bytes_per_step": int(out_h.numel() + scores_h.numel()) * 4,
-           "api": "avzoom.pipeline.HostPipeline.run(pinned mix, tgt, itf) -> (enhanced waveforms, all-gathered scores)"}
+    e2e_ms, (out_h, scores_h) = e2e_leg(host, mix_p, tgt_p, itf_p)
+    d2h_bytes = int(out_h.numel() + scores_h.numel()) * 4
     sir_mean = float(scores_h[:, 1].mean())
-    # same leg with the reference's on-disk sample format (PCM16 WAV, oracle_debug.py:35-39,96) on the wire: int16 in
-    # both directions, converted on the device.  Informational: the headline e2e above moves float32.
     del host
+    # bare-copy ceiling of the link for exactly these bytes, all ranks at once
+    barrier()
+    cc = pipeline.copy_ceiling(h2d_bytes, d2h_bytes, dev)
+    barrier()
+    ceil_ms = max(cc["both_directions"]["h2d_ms"], cc["both_directions"]["d2h_ms"])
+    ceil_ms = max_over_ranks(ceil_ms)
+    e2e = {"value": audio_s_per_step / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+           "api": "avzoom.pipeline.HostPipeline.submit/wait(pinned mix, tgt, itf) -> (enhanced waveforms, all-gathered scores) "
+                  "in pinned host memory, float32 on the wire",
+           "copy_ceiling": {"what": "one bare pinned cudaMemcpyAsync per direction of exactly these bytes, both directions at "
+                                    "once, every rank at the same time, nothing else running",
+                            "h2d_GBps_alone": cc["alone"]["h2d_GBps"], "d2h_GBps_alone": cc["alone"]["d2h_GBps"],
+                            "h2d_GBps": cc["both_directions"]["h2d_GBps"], "d2h_GBps": cc["both_directions"]["d2h_GBps"],
+                            "ms_per_step_at_ceiling_max_over_ranks": ceil_ms,
+                            "per_rank_h2d_GBps": gather_floats(cc["both_directions"]["h2d_GBps"])},
+           "copy_ceiling_GBps": cc["both_directions"]["h2d_GBps"],
+           "frac_of_copy_ceiling": ceil_ms / e2e_ms}
+    # same leg with the reference's on-disk sample format (PCM16 WAV, oracle_debug.py:35-39,96) on the wire: int16 in
+    # both directions, converted on the device.
     to_pcm = lambda a: torch.from_numpy(np.clip(np.rint(a * 32767.0), -32768, 32767).astype(np.int16)).pin_memory()
     mix_w, tgt_w, itf_w = to_pcm(mix_h), to_pcm(tgt_h), to_pcm(itf_h)
     host_w = pipeline.HostPipeline(enh, world, wire="pcm16")
-    host_w.run(mix_w, tgt_w, itf_w)
-    barrier()
-    g0.record()
-    for _ in range(e2e_steps):
-        out_w, scores_w = host_w.run(mix_w, tgt_w, itf_w)
-    g1.record()
-    barrier()
-    w_ms = max_over_ranks(g0.elapsed_time(g1)) / e2e_steps
-    e2e["pcm16_wire"] = {"value": audio_s_per_step / (w_ms * 1e-3), "unit": UNIT, "ms_per_step": w_ms,
-                         "h2d_bytes_per_step": int(mix_w.numel() + tgt_w.numel() + itf_w.numel()) * 2,
-                         "d2h_bytes_per_step": int(out_w.numel()) * 2 + int(scores_w.numel()) * 4,
-                         "output_sir_mean": float(scores_w[:, 1].mean())}
+    w_ms, (out_w, scores_w) = e2e_leg(host_w, mix_w, tgt_w, itf_w)
+    e2e_pcm16 = {"value": audio_s_per_step / (w_ms * 1e-3), "unit": UNIT, "ms_per_step": w_ms,
+                 "h2d_bytes_per_step": int(mix_w.numel() + tgt_w.numel() + itf_w.numel()) * 2,
+                 "d2h_bytes_per_step": int(out_w.numel()) * 2 + int(scores_w.numel()) * 4,
+                 "output_sir_mean": float(scores_w[:, 1].mean()),
+                 "what": "the same leg with the reference's own I/O sample format on the wire (16 kHz PCM16, "
+                         "oracle_debug.py:35-39,96): int16 host buffers both ways, converted on the device"}
     del host_w, mix_w, tgt_w, itf_w
     sir_in = float(avzoom.sir_scores(mix[:, 0, :].contiguous(), tgt, itf)[:, 1].mean())
 
+    # ---- the other BASELINE configurations, compactly (tools/bench_configs.py)
+    extra = {}
+    if not args.no_extra_configs:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_configs as bc
+        del loop
+        torch.cuda.empty_cache()
+        try:
+            c5 = bc.config5(dev, rank, world, n_total=args.c5_utterances)
+            if rank == 0:
+                extra["config5"] = c5
+        except Exception as ex:  # noqa: BLE001 - a secondary block must not lose the headline line
+            extra["config5"] = {"error": repr(ex)}
+        if rank == 0:
+            for name, fn in (("config1", bc.config1), ("config4", bc.config4), ("config3", bc.config3)):
+                try:
+                    extra[name] = fn(dev)
+                except Exception as ex:  # noqa: BLE001
+                    extra[name] = {"error": repr(ex)}
+                torch.cuda.empty_cache()
+    barrier()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline()
+        cpu = cpu_baseline(mix_h, tgt_h, itf_h)
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE config 2: 1024 synthetic 4 s 2-ch far-field mixtures per GPU, 1 target + 3 "
-                                   "interferers, oracle IBM mask-MVDR, n_fft 512 hop 128",
-                       "utterances_per_gpu": B, "distinct_utterances_per_gpu": distinct, "samples_per_utterance": L,
-                       "l2_policy": "inputs (1.05 GB per GPU) larger than the 126 MB L2; no flush needed",
-                       "step_schedule": f"steps alternate between {DEPTH} engines on {DEPTH} CUDA streams (steady-state "
-                                        "serving loop); each step is one full pass of the 7 kernels over the whole batch",
-                       "ms_per_step_single_stream": ms_single,
-                       "input_generation_s": round(t_gen, 2),
-                       "host_cpus_bound_to_gpu_numa_node": len(numa_cpus) if numa_cpus else None},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(),
+            "value_long": {"value": value_long, "ms_per_step": ms_long, "steps": n_long,
+                           "what": "the same timed loop run for >= 1 s"},
+            "run_info": {"distinct_utterances_per_gpu": distinct,
+                         "l2_policy": "inputs (1.05 GB per GPU) larger than the 126 MB L2; no flush needed",
+                         "step_schedule": f"steps alternate between {DEPTH} engines on {DEPTH} CUDA streams (steady-state "
+                                          "serving loop); each step is one full pass of the 7 kernels over the whole batch",
+                         "ms_per_step_single_stream": ms_single, "input_generation_s": round(t_gen, 2),
+                         "host_cpus_bound_to_gpu_numa_node": len(numa_cpus) if numa_cpus else None},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_pcm16": e2e_pcm16,
             "gpu_launches": enh.launches_per_step * args.steps, "clocks": clocks,
             "dSIR_dB": {"output_sir_mean": sir_mean, "mic1_sir_mean": sir_in, "improvement": sir_mean - sir_in},
         }
+        line.update(extra)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -386,10 +475,12 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the config 1/3/4/5 blocks")
+    ap.add_argument("--c5-utterances", type=int, default=65536, help="size of the config-5 job (whole job, all ranks)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -397,7 +488,7 @@ def main():
         if args.gpus > 1 and "RANK" not in os.environ:
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                    "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__), "--gpus", str(args.gpus),
-                   "--steps", str(args.steps), "--warmup", str(args.warmup)]
+                   "--steps", str(args.steps), "--warmup", str(args.warmup)] + (["--no-extra-configs"] if args.no_extra_configs else [])
             sys.exit(subprocess.call(cmd))
         run_ours(args)
 

@@ -996,13 +996,15 @@ static const float* stage_mask(const float* mask, const void* spec, int B, int T
 }
 
 static float ibm_tol2() {
-  // (relative float32 FFT error bound)^2, relative to the rms bin magnitude of the frame.  5e-7 is 5x the level at
-  // which the first float32 decision errors appear; the choice is validated a posteriori by deciding
-  // EVERY bin of a full config-5 job (65 536 utterances, 8.4e9 bins) in float64 with avz_ibm_exact_f32 and comparing
-  // (profiles/r2_ibm_exact_c5.json: 0 mismatches).  Fixed at compile time: only builds with -DAVZ_EXPERIMENT read the
-  // AVZ_IBM_TOL environment variable (tools/ibm_tol_scan.py), so a stray variable cannot change results.
+  // (float32 FFT error bound of one bin)^2, relative to the rms bin magnitude of the frame.  The error of this
+  // transform is heavy-tailed, not Gaussian: deciding EVERY bin of a full config-5 job (65 536 utterances, 8.4e9 bins)
+  // in float64 (avz_ibm_exact_f32, tools/ibm_exact_c5.py) found 19 wrong float32 decisions outside a 5e-7 band (the
+  // round-1 value, chosen from 33 M bins) and none outside 1e-6, 2e-6 or 4e-6 (profiles/r2_ibm_exact_c5.json).  The
+  // shipped bound is 4e-6 - the generic path's value, 4-8x above the first observed failure - at +0.08 ms of fix-up per
+  // 1024 x 4 s.  Fixed at compile time: only builds with -DAVZ_EXPERIMENT read the AVZ_IBM_TOL environment variable
+  // (tools/ibm_tol_scan.py), so a stray variable cannot change results.
   static const float t2 = [] {
-    double tol = 5e-7;
+    double tol = 4e-6;
 #ifdef AVZ_EXPERIMENT
     if (const char* e = getenv("AVZ_IBM_TOL")) tol = atof(e);
 #endif

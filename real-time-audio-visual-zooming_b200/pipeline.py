@@ -185,11 +185,17 @@ class HostPipeline:
     sub-batches run on three streams so PCIe transfers overlap compute.  Scores (OSINR, OSIR, SDR, SIR per
     utterance) are all-gathered across ranks with NCCL when torch.distributed is initialised.
 
+    submit() enqueues a whole step and returns a ticket without waiting; wait(ticket) blocks until that step's results
+    are in pinned host memory.  Steps pipeline: the first host->device copy of step k+1 runs while step k is still
+    computing and draining, so in steady state the leg runs at the speed of its slowest resource (the host->device
+    link) with no fill/drain bubble per step.  Results live in `host_slots` rotating pinned buffers: a ticket's
+    buffers are reused `host_slots` submits later.  run() = submit + wait.
+
     wire="pcm16": the host buffers are int16 (what the reference's WAV files hold, oracle_debug.py:35-39,96); samples
     cross PCIe as int16 in both directions and are converted on the device (read = /32768 like soundfile, write =
     round(x*32767) like libsndfile), halving the transfer that bounds this leg."""
 
-    def __init__(self, engine: OracleMvdr, world: int = 1, sub_batches: int = 8, wire: str = "f32"):
+    def __init__(self, engine: OracleMvdr, world: int = 1, sub_batches: int = 8, wire: str = "f32", host_slots: int = 2):
         if wire not in ("f32", "pcm16"):
             raise ValueError("wire must be 'f32' or 'pcm16'")
         self.e = engine
@@ -205,31 +211,41 @@ class HostPipeline:
         self.d_tgt = [torch.empty((self.sb, engine.L), **f32) for _ in range(2)]
         self.d_itf = [torch.empty((self.sb, engine.L), **f32) for _ in range(2)]
         self.d_out = [torch.empty((self.sb, engine.out_len), **f32) for _ in range(2)]
-        self.scores = torch.empty((B, 4), **f32)
-        self.scores_all = torch.empty((B * world, 4), **f32)
+        self.host_slots = max(1, int(host_slots))
+        self.scores = [torch.empty((B, 4), **f32) for _ in range(self.host_slots)]
+        self.scores_all = [torch.empty((B * world, 4), **f32) for _ in range(self.host_slots)]
         if wire == "pcm16":
             i16 = dict(dtype=torch.int16, device=dev)
             self.w_mix = [torch.empty((self.sb, 2, engine.L), **i16) for _ in range(2)]
             self.w_tgt = [torch.empty((self.sb, engine.L), **i16) for _ in range(2)]
             self.w_itf = [torch.empty((self.sb, engine.L), **i16) for _ in range(2)]
             self.w_out = [torch.empty((self.sb, engine.out_len), **i16) for _ in range(2)]
-        self.h_out = torch.empty((B, engine.out_len), dtype=torch.int16 if wire == "pcm16" else torch.float32).pin_memory()
-        self.h_scores = torch.empty((B * world, 4), dtype=torch.float32).pin_memory()
+        odt = torch.int16 if wire == "pcm16" else torch.float32
+        self.h_out = [torch.empty((B, engine.out_len), dtype=odt).pin_memory() for _ in range(self.host_slots)]
+        self.h_scores = [torch.empty((B * world, 4), dtype=torch.float32).pin_memory() for _ in range(self.host_slots)]
         self.s_in, self.s_cmp, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        # events that order the reuse of the two device slots; they persist across steps so that steps pipeline
+        self.ev_in = [None, None]
+        self.ev_cmp = [None, None]
+        self.ev_out = [None, None]
+        self.done = [None] * self.host_slots
+        self.n_submitted = 0
 
-    def run(self, mix_h: torch.Tensor, tgt_h: torch.Tensor, itf_h: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    def submit(self, mix_h: torch.Tensor, tgt_h: torch.Tensor, itf_h: torch.Tensor) -> int:
         lib = _lib.load()
         pcm = self.wire == "pcm16"
         want = torch.int16 if pcm else torch.float32
         if mix_h.dtype != want or tgt_h.dtype != want or itf_h.dtype != want:
             raise _lib.AvzError(f"HostPipeline(wire={self.wire!r}) needs {want} host buffers")
+        ticket = self.n_submitted
+        hs = ticket % self.host_slots
+        self.n_submitted += 1
         i_mix, i_tgt, i_itf = (self.w_mix, self.w_tgt, self.w_itf) if pcm else (self.d_mix, self.d_tgt, self.d_itf)
         cur = torch.cuda.current_stream()
         for s in (self.s_in, self.s_cmp, self.s_out):
             s.wait_stream(cur)
-        ev_in = [None, None]
-        ev_cmp = [None, None]
-        ev_out = [None, None]
+        ev_in, ev_cmp, ev_out = self.ev_in, self.ev_cmp, self.ev_out
+        scores, h_out = self.scores[hs], self.h_out[hs]
         for c in range(self.nsub):
             slot = c & 1
             lo, hi = c * self.sb, (c + 1) * self.sb
@@ -247,25 +263,79 @@ class HostPipeline:
                 if pcm:
                     for w, d in ((i_mix[slot], self.d_mix[slot]), (i_tgt[slot], self.d_tgt[slot]), (i_itf[slot], self.d_itf[slot])):
                         _lib.check(lib.avz_pcm16_to_f32(_ptr(w), w.numel(), _ptr(d), _stream()), "avz_pcm16_to_f32")
-                out = self.sub.run(self.d_mix[slot], self.d_tgt[slot], self.d_itf[slot])
+                # the engine writes straight into the device slot the device->host copy reads (no staging copy)
+                out = self.sub.run(self.d_mix[slot], self.d_tgt[slot], self.d_itf[slot], out=self.d_out[slot])
                 _lib.check(lib.avz_sir_f32(_ptr(out), _ptr(self.d_tgt[slot]), _ptr(self.d_itf[slot]), self.sb,
-                                           self.sub.out_len, self.sub.L, _ptr(self.scores[lo:hi]), _stream()), "avz_sir_f32")
+                                           self.sub.out_len, self.sub.L, _ptr(scores[lo:hi]), _stream()), "avz_sir_f32")
                 if pcm:
                     _lib.check(lib.avz_f32_to_pcm16(_ptr(out), out.numel(), _ptr(self.w_out[slot]), _stream()), "avz_f32_to_pcm16")
-                else:
-                    self.d_out[slot].copy_(out, non_blocking=True)
                 ev_cmp[slot] = self.s_cmp.record_event()
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(ev_cmp[slot])
-                self.h_out[lo:hi].copy_((self.w_out if pcm else self.d_out)[slot], non_blocking=True)
+                h_out[lo:hi].copy_((self.w_out if pcm else self.d_out)[slot], non_blocking=True)
                 ev_out[slot] = self.s_out.record_event()
+        with torch.cuda.stream(self.s_cmp):
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_gather_into_tensor(self.scores_all[hs], scores)
+            else:
+                self.scores_all[hs].copy_(scores)
+            ev_sc = self.s_cmp.record_event()
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(ev_sc)
+            self.h_scores[hs].copy_(self.scores_all[hs], non_blocking=True)
+            self.done[hs] = self.s_out.record_event()
+        return ticket
+
+    def wait(self, ticket: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Block until step `ticket` is in pinned host memory -> (enhanced waveforms [B, n], all-gathered scores [B*world, 4])."""
+        if not (self.n_submitted - self.host_slots <= ticket < self.n_submitted):
+            raise _lib.AvzError("ticket is no longer (or not yet) held in a host slot")
+        hs = ticket % self.host_slots
+        self.done[hs].synchronize()
+        return self.h_out[hs], self.h_scores[hs]
+
+    def join(self) -> None:
+        """Make the caller's stream wait for everything submitted so far."""
+        cur = torch.cuda.current_stream()
         cur.wait_stream(self.s_cmp)
         cur.wait_stream(self.s_out)
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_gather_into_tensor(self.scores_all, self.scores)
-        else:
-            self.scores_all.copy_(self.scores)
-        self.h_scores.copy_(self.scores_all, non_blocking=True)
-        cur.synchronize()
-        return self.h_out, self.h_scores
+
+    def run(self, mix_h: torch.Tensor, tgt_h: torch.Tensor, itf_h: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        return self.wait(self.submit(mix_h, tgt_h, itf_h))
+
+
+def copy_ceiling(h2d_bytes: int, d2h_bytes: int, device, reps: int = 3) -> Dict[str, float]:
+    """Bare-copy ceiling of the host<->device link for the end-to-end leg: one pinned host->device cudaMemcpyAsync of
+    `h2d_bytes` and one device->host copy of `d2h_bytes` per step, both directions at once on two streams, nothing
+    else running (under torchrun every rank does this at the same time, which is what the leg has to share).
+    Returns GB/s per direction and the ms a step's copies take."""
+    h_in = torch.empty((h2d_bytes,), dtype=torch.uint8).pin_memory()
+    h_out = torch.empty((d2h_bytes,), dtype=torch.uint8).pin_memory()
+    d_in = torch.empty((h2d_bytes,), dtype=torch.uint8, device=device)
+    d_out = torch.empty((d2h_bytes,), dtype=torch.uint8, device=device)
+    s1, s2 = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    res = {}
+    for name, both in (("alone", False), ("both_directions", True)):
+        best = None
+        for _ in range(reps + 1):
+            torch.cuda.synchronize(device)
+            a1, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(s1):
+                a1.record()
+                d_in.copy_(h_in, non_blocking=True)
+                b1.record()
+            if not both:
+                torch.cuda.synchronize(device)
+            with torch.cuda.stream(s2):
+                a2.record()
+                h_out.copy_(d_out, non_blocking=True)
+                b2.record()
+            torch.cuda.synchronize(device)
+            t = (a1.elapsed_time(b1), a2.elapsed_time(b2))
+            if best is None or max(t) < max(best):
+                best = t
+        res[name] = {"h2d_GBps": h2d_bytes / (best[0] * 1e-3) / 1e9, "d2h_GBps": d2h_bytes / (best[1] * 1e-3) / 1e9,
+                     "h2d_ms": best[0], "d2h_ms": best[1]}
+    return res
