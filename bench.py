@@ -254,11 +254,12 @@ def run_ours(args):
     B = UTT_PER_GPU
     audio_s_per_step = B * DUR_S * world
 
-    enh = pipeline.OracleMvdr(cfg, B, L, dev)      # pre-allocated buffers, no per-step allocation
+    FUSED = args.fused_kernel
+    enh = pipeline.OracleMvdr(cfg, B, L, dev, fused=FUSED)      # pre-allocated buffers, no per-step allocation
     # steady-state serving loop: consecutive steps alternate between two engines on two CUDA streams (every step is
     # still one full pass of all seven kernels over the whole batch; the single-stream time is reported next to it)
     DEPTH = 2
-    loop = pipeline.StreamedOracleMvdr(cfg, B, L, dev, depth=DEPTH)
+    loop = pipeline.StreamedOracleMvdr(cfg, B, L, dev, depth=DEPTH, fused=FUSED)
 
     def barrier():
         if world > 1:
@@ -329,8 +330,11 @@ def run_ours(args):
     # k512_cov reads mix 2L, k512_apply writes out L (its input is the spectrum pass A kept: not compulsory traffic;
     # the recomputing variant would read mix 2L), k_peak_normalise reads and writes out L.  The path as a whole:
     # 20 B/sample (ALGO_BYTES_PER_SAMPLE).
+    # k512_fused (pass A + weights + pass B + normalisation as one persistent kernel, spectrum ring in L2): reads mix 2L,
+    # writes out L = 12 B/sample.
     algo = {"k512_ibm": 8.0 * samples, "k512_cov": 8.0 * samples, "k512_apply": 4.0 * samples,
-            "k_peak_normalise": 8.0 * samples}
+            "k_peak_normalise": 8.0 * samples, "k512_fused": 12.0 * samples}
+    algo = {k: v for k, v in algo.items() if k in ktimes}
     dom = max(algo, key=lambda k: ktimes.get(k, 0.0))
     achieved = algo[dom] / (ktimes[dom] * 1e-3) / 1e9
     traffic, traffic_src, issue = None, None, None
@@ -344,10 +348,11 @@ def run_ours(args):
             slots_per_s = sms * 4 * clk_hz
             issue = {"unit": "fraction of warp-instruction issue slots", "peak_slots_per_s": slots_per_s, "kernels": {
                 k: (tj["per_launch"][k]["warp_instructions"] * B / 1024.0) / (ktimes[k] * 1e-3) / slots_per_s
-                for k in ("k512_ibm", "k512_cov", "k512_apply") if ktimes.get(k)},
+                for k in ("k512_ibm", "k512_cov", "k512_apply", "k512_fused") if ktimes.get(k) and k in tj["per_launch"]},
                 "dram_GBps": {k: (tj["per_launch"][k]["dram_read_bytes"] + tj["per_launch"][k]["dram_write_bytes"]) * (B / 1024.0)
-                              / (ktimes[k] * 1e-3) / 1e9 for k in ("k512_ibm", "k512_cov", "k512_apply", "k_peak_normalise")
-                              if ktimes.get(k)},
+                              / (ktimes[k] * 1e-3) / 1e9
+                              for k in ("k512_ibm", "k512_cov", "k512_apply", "k_peak_normalise", "k512_fused")
+                              if ktimes.get(k) and k in tj["per_launch"]},
                 "note": "instruction and DRAM byte counts per launch from " + tj_name + " (ncu at B = 1024), divided by the "
                         "CUDA-event kernel time measured in this run"}
         except Exception:
@@ -459,7 +464,9 @@ def run_ours(args):
             "run_info": {"distinct_utterances_per_gpu": distinct,
                          "l2_policy": "inputs (1.05 GB per GPU) larger than the 126 MB L2; no flush needed",
                          "step_schedule": f"steps alternate between {DEPTH} engines on {DEPTH} CUDA streams (steady-state "
-                                          "serving loop); each step is one full pass of the 7 kernels over the whole batch",
+                                          "serving loop); each step is one full pass over the whole batch: " +
+                                          ("k512_ibm, k512_ibm_fixup, k512_fused (pass A + weights + pass B + normalisation "
+                                           "as tasks of one persistent kernel)" if FUSED else "seven separate kernels"),
                          "ms_per_step_single_stream": ms_single, "input_generation_s": round(t_gen, 2),
                          "host_cpus_bound_to_gpu_numa_node": len(numa_cpus) if numa_cpus else None},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_pcm16": e2e_pcm16,
@@ -480,6 +487,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the config 1/3/4/5 blocks")
+    ap.add_argument("--fused-kernel", action="store_true",
+                    help="pass A + weights + pass B + normalisation as one persistent kernel with the kept spectrum in an L2 ring "
+                         "(avz_oracle_fused_f32) instead of five separate launches; measured slower (profiles/README.md)")
     ap.add_argument("--c5-utterances", type=int, default=65536, help="size of the config-5 job (whole job, all ranks)")
     args = ap.parse_args()
     if args.impl == "reference":

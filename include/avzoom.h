@@ -187,6 +187,21 @@ AVZ_API int avz_mvdr_apply_kept_norm_f32(const void* spec, const float* w, const
                                  int64_t L, int n_fft, int hop, const AvzMvdrCfg* cfg, float peak_eps, float* out,
                                  float* peak, void* stream);
 
+/* ---- the whole oracle path of oracle_debug.py:42-94 as ONE call (n_fft 512, hop 128 / 256): k512_ibm + k512_ibm_fixup,
+ * then a single persistent kernel whose tasks are pass A (masked covariance, spectrum kept), the per-utterance
+ * finalize + 2x2 solve, pass B (beamform, post-filter, iSTFT / overlap-add) and the peak normalisation.  Pass B of an
+ * utterance runs microseconds after its pass A and the kept spectrum lives in a ring of utterance slots that stays in
+ * L2, so it never travels to HBM (the separate kernels move 4.2 GB of it per 1024 x 4 s and are bound by that stream).
+ * Same arithmetic, same device functions: ibm_bits, R, msum, w, out and peak equal what avz_ibm_cov_keep_f32 ->
+ * avz_mvdr_weights_f32 -> avz_mvdr_apply_kept_f32 -> avz_peak_normalise_f32 produce (bit for bit when both cut an
+ * utterance into the same frame chunks, otherwise to float32 summation order in R).
+ * dvec [257,2] complex64; cfg->post_mode AVZ_POST_ONE_MINUS_NOISE or AVZ_POST_NONE; peak_eps < 0: no normalisation;
+ * peak [B] is zeroed by the call; ws: avz_oracle_fused_ws_bytes() bytes. */
+AVZ_API int64_t avz_oracle_fused_ws_bytes(int B, int64_t L, int n_fft, int hop);
+AVZ_API int avz_oracle_fused_f32(const float* mix, const float* tgt, const float* itf, int B, int64_t L, int n_fft, int hop,
+                         const AvzMvdrCfg* cfg, float peak_eps, const float* dvec, uint32_t* ibm_bits, float* R, float* msum,
+                         float* w, float* out, float* peak, void* ws, void* stream);
+
 /* ---- streaming mode (BASELINE config 4; NOT in the reference - defined by this project, parity unpinned):
  *   R_t = lambda R_{t-1} + (1-lambda) m_t y_t y_t^H,  n_t = lambda n_{t-1} + (1-lambda) m_t,
  *   w_t = mvdr(R_t/(n_t+norm_eps) + sigma I),  S_t = w_t^H y_t,  same 512/128 framing and overlap-add as the batch path.

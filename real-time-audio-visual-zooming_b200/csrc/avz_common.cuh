@@ -1,6 +1,7 @@
 // Shared device/host helpers for libavzoom (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdio>
 #include <stdint.h>
 #include <math.h>
 
@@ -87,6 +88,50 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
   return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// MVDR weights of one bin.  Replaces oracle_debug.py:68-79 (np.linalg.solve on R + sigma I, then w / (d^H w + eps)):
+// closed-form 2x2 solve in float64; an exactly singular (or non-finite) system gives w = [1, 0] like the reference's
+// LinAlgError branch; bins below the high-pass get 0 (AVZ_HP_ZERO) or [1, 0] (AVZ_HP_MIC0).
+// ------------------------------------------------------------------------------------------
+struct cd {
+  double x, y;
+};
+__device__ __forceinline__ cd cdmul(cd a, cd b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+__device__ __forceinline__ cd cddiv(cd a, cd b) {
+  const double den = b.x * b.x + b.y * b.y;
+  return {(a.x * b.x + a.y * b.y) / den, (a.y * b.x - a.x * b.y) / den};
+}
+__device__ __forceinline__ void mvdr_weights_bin(float4 r, float2 dv0, float2 dv1, int k, const AvzMvdrCfg& cfg, float2& w0,
+                                                 float2& w1) {
+  w0 = make_float2(0.f, 0.f);
+  w1 = make_float2(0.f, 0.f);
+  if (k < cfg.hp_bins && cfg.hp_mode != AVZ_HP_NONE) {
+    if (cfg.hp_mode == AVZ_HP_MIC0) w0.x = 1.f;  // pass mic 0 through
+    return;
+  }
+  const double a = (double)r.x + (double)cfg.sigma, c = (double)r.y + (double)cfg.sigma;
+  const cd bb = {(double)r.z, (double)r.w};  // R01; R10 = conj
+  const cd d0 = {(double)dv0.x, (double)dv0.y};
+  const cd d1 = {(double)dv1.x, (double)dv1.y};
+  const double det = a * c - (bb.x * bb.x + bb.y * bb.y);
+  if (det == 0.0 || !isfinite(det)) {
+    w0.x = 1.f;  // LinAlgError fallback w = [1, 0] (oracle_debug.py:78-79)
+    return;
+  }
+  // u = inv([[a, b],[conj b, c]]) d
+  const cd bd1 = cdmul(bb, d1);
+  const cd cbd0 = cdmul({bb.x, -bb.y}, d0);
+  const cd u0 = {(c * d0.x - bd1.x) / det, (c * d0.y - bd1.y) / det};
+  const cd u1 = {(a * d1.x - cbd0.x) / det, (a * d1.y - cbd0.y) / det};
+  // denom = d^H u + w_eps
+  const cd t0 = cdmul({d0.x, -d0.y}, u0);
+  const cd t1 = cdmul({d1.x, -d1.y}, u1);
+  const cd den = {t0.x + t1.x + (double)cfg.w_eps, t0.y + t1.y};
+  const cd q0 = cddiv(u0, den), q1 = cddiv(u1, den);
+  w0 = make_float2((float)q0.x, (float)q0.y);
+  w1 = make_float2((float)q1.x, (float)q1.y);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -204,6 +249,19 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void mbar_inval(uint64_t* bar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// order earlier generic-proxy writes (of any thread, once observed) before this thread's later async-proxy (TMA) reads
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 // wait until the phase with the given parity has completed; traps instead of hanging if it never does
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
@@ -214,7 +272,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done)
         : "r"(addr), "r"(parity)
         : "memory");
-    if (spin > (1u << 26)) __trap();
+    if (spin > (1u << 22)) {
+      printf("mbar_wait timed out (block %d thread %d parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, parity);
+      __trap();
+    }
   }
 }
 
@@ -224,7 +285,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ float atan2_poly(float y, float x) {
   const float ax = fabsf(x), ay = fabsf(y);
   const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-  const float t = (mx > 0.f) ? __fdiv_rn(mn, mx) : 0.f;   // correctly rounded: the fast division's 2 ulp would be a third of the error budget
+  // mn / mx to ~1 ulp: hardware reciprocal + one Newton step on the quotient (the fast division's 2 ulp would be a
+  // quarter of the 1e-6 rad budget of the IPD; a correctly rounded division costs three times as many instructions)
+  float t = 0.f;
+  if (mx > 0.f) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(mx));
+    const float q0 = mn * r;
+    t = fmaf(fmaf(-q0, mx, mn), r, q0);
+  }
   const float s = t * t;
   float p = 0.0029035559807253364f;
   p = fmaf(p, s, -0.016283021665709413f);
@@ -241,16 +310,29 @@ __device__ __forceinline__ float atan2_poly(float y, float x) {
   return copysignf(r, y);
 }
 
+// ln(x) for normal x > 0 with an ABSOLUTE error of ~1.3e-7 + half an ulp of the result: x = 2^e f with f in
+// [0.7071, 1.4142), ln f from the hardware lg2 (absolute error 2^-22.6 on that interval), e ln 2 added with ln 2 split
+// in two so that the product is exact.  9 instructions; logf costs ~40, and __logf (lg2 on the raw argument) carries a
+// RELATIVE error of 2^-22 on a result of up to 16, i.e. up to 4e-6 - twice the budget below.
+__device__ __forceinline__ float log_abs_accurate(float x) {
+  const int ix = __float_as_int(x);
+  const int e = (ix - 0x3f3504f3) >> 23;
+  const float f = __int_as_float(ix - (e << 23));
+  float l2;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(f));
+  const float fe = (float)e;
+  return fmaf(fe, 0.693145751953125f, fmaf(fe, 1.42860682030941723e-6f, l2 * 0.693147180559945309f));
+}
+
 // log-magnitude + inter-channel phase difference of one TF bin (full_audio.../inference.py:91-94).  The reference
-// evaluates np.abs / np.log / np.angle in float64 and casts to float32.  Error budget against that, for the SAME
+// evaluates np.abs / np.log / np.angle in float64 and casts to float32.  Error budget against that for the SAME
 // spectrum (tests/test_gpu_parity.py::test_features_same_spectrum: log-mag <= 2e-6, IPD <= 1e-6 rad on every non-zero
-// bin): |y| = sqrt.rn(x^2 + y^2) (<= 1 ulp relative = 1.2e-7 absolute in the logarithm), logf (<= 1 ulp of a value of at
-// most 16.2 = 1.9e-6), two atan2_poly angles (1.2e-7 polynomial + 0.6e-7 quotient + 1.2e-7 rounding each) and the
-// rounding of their difference (2.4e-7).  The hardware lg2 / rsq / fast division this replaced were 3 ulp / 2 ulp /
-// 2 ulp and could exceed both bounds on weak bins.
+// bin): |y| = p * rsq(p) (2 ulp relative = 2.4e-7 absolute in the logarithm), log_abs_accurate (1.3e-7 + rounding of a
+// value of at most 16.2: 0.95e-6), two atan2_poly angles (1.2e-7 polynomial + 0.6e-7 quotient + 1.2e-7 rounding each)
+// and the rounding of their difference (2.4e-7).
 __device__ __forceinline__ void feature_values(float2 y0, float2 y1, float& logmag, float& ipd) {
   const float p = fmaf(y0.x, y0.x, y0.y * y0.y);
-  logmag = logf(__fsqrt_rn(p) + 1e-7f);
+  logmag = log_abs_accurate(p * rsqrtf(fmaxf(p, 1e-37f)) + 1e-7f);   // p = 0 gives |y| = 0, not NaN
   ipd = atan2_poly(y0.y, y0.x) - atan2_poly(y1.y, y1.x);
 }
 

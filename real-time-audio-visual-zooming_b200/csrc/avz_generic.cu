@@ -27,6 +27,11 @@ int launch_ibm_exact(const float* tgt, const float* itf, int B, int64_t L, int h
 template <int HOP>
 int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const float* mask, int B, int64_t L,
                    float sqrt_eps, uint32_t* ibm_bits, float* part, int* chunks_out, void* spec, cudaStream_t st);
+int64_t fused_ws_bytes(int B, int64_t L, int hop);
+template <int HOP>
+int launch_oracle_fused(const float* mix, const float* tgt, const float* itf, int B, int64_t L, const AvzMvdrCfg* cfg,
+                        float norm_eps, float peak_eps, const float* dvec, uint32_t* ibm_bits, float* R, float* msum,
+                        float* w, float* out, float* peak, void* ws, cudaStream_t st);
 template <int HOP>
 int launch_apply(const float* mix, const void* spec, const float* w, const uint32_t* ibm_bits, const float* mask,
                  int gain_mode, float post_floor, int B, int64_t L, float* out, float* peak, int fuse_norm,
@@ -825,6 +830,28 @@ int avz_mvdr_apply_kept_norm_f32(const void* spec, const float* w, const uint32_
                                  float* peak, void* stream) {
   if (!peak) return set_error(AVZ_EINVAL, "avz_mvdr_apply_kept_norm_f32: peak buffer required");
   return apply_kept(spec, w, ibm_bits, mask, B, L, n_fft, hop, cfg, out, peak, 1, peak_eps, stream);
+}
+
+// ---- the whole oracle path in two small launches + one persistent kernel (n_fft 512, hop 128 / 256)
+int64_t avz_oracle_fused_ws_bytes(int B, int64_t L, int n_fft, int hop) {
+  if (B <= 0 || B > 65535 || check_fft_args(n_fft, hop, L) || !use_opt512(n_fft, hop)) return 0;
+  return o512::fused_ws_bytes(B, L, hop);
+}
+
+int avz_oracle_fused_f32(const float* mix, const float* tgt, const float* itf, int B, int64_t L, int n_fft, int hop,
+                         const AvzMvdrCfg* cfg, float peak_eps, const float* dvec, uint32_t* ibm_bits, float* R, float* msum,
+                         float* w, float* out, float* peak, void* ws, void* stream) {
+  if (!mix || !tgt || !itf || !cfg || !dvec || !ibm_bits || !R || !msum || !w || !out || !peak || !ws || B <= 0 || B > 65535)
+    return set_error(AVZ_EINVAL, "avz_oracle_fused_f32: null pointer or bad batch size");
+  int rc = check_fft_args(n_fft, hop, L);
+  if (rc) return rc;
+  if (!use_opt512(n_fft, hop)) return set_error(AVZ_EINVAL, "avz_oracle_fused_f32: n_fft 512 with hop 128 or 256 only");
+  if (cfg->post_mode != AVZ_POST_ONE_MINUS_NOISE && cfg->post_mode != AVZ_POST_NONE)
+    return set_error(AVZ_EINVAL, "avz_oracle_fused_f32: post-filter must be AVZ_POST_ONE_MINUS_NOISE or AVZ_POST_NONE");
+  return (hop == 128) ? o512::launch_oracle_fused<128>(mix, tgt, itf, B, L, cfg, cfg->norm_eps, peak_eps, dvec, ibm_bits, R,
+                                                       msum, w, out, peak, ws, (cudaStream_t)stream)
+                      : o512::launch_oracle_fused<256>(mix, tgt, itf, B, L, cfg, cfg->norm_eps, peak_eps, dvec, ibm_bits, R,
+                                                       msum, w, out, peak, ws, (cudaStream_t)stream);
 }
 
 // ---- streaming (n_fft 512 / hop 128): one hop per call for n_streams independent 2-mic streams ---------------

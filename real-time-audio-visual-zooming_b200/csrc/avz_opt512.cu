@@ -11,6 +11,7 @@
 // Each lane keeps a sliding window of raw samples in registers: a new frame costs HOP/32 coalesced 128-byte
 // loads per channel, every input sample is fetched once per warp run, and nothing is staged in shared memory
 // except the single FFT transposition.  Replaces rt_av_zoom/core/oracle_debug.py:42-94.
+#include <cstdio>
 #include <cstdlib>
 
 #include "avz_common.cuh"
@@ -423,12 +424,14 @@ k_mask_transpose(const float* __restrict__ mask, float* __restrict__ mask_t, int
 // the forward transform: [B][T][8][32] float4 = (lo[i].x, lo[i].y, mir[i].x, mir[i].y) of lane l (lane 0's i = 0
 // slot carries (DC, Nyquist): its mirror is itself).  Each store instruction writes 512 contiguous bytes.
 // This trades 64 B/sample of spare HBM bandwidth for ~30 % fewer instructions on an issue-bound path.
-template <int HOP, int WMODE>
-__global__ void __launch_bounds__(kWarps * 32, AVZ_MINB_COV)
-k512_cov(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, const float* __restrict__ mask,
-         MaskLayout ml, int L, int T, int frames_per_cta, float sqrt_eps, float* __restrict__ part,
-         float4* __restrict__ spec, Tables tb) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+// L2KEEP: the kept spectrum is written with ordinary stores (it is read back out of L2 by the same launch: k512_fused)
+// instead of streaming (evict-first) stores.  (b, chunk, chunks) = (blockIdx.y, blockIdx.x, gridDim.x) of the plain launch.
+template <int HOP, int WMODE, bool L2KEEP>
+__device__ __forceinline__ void cov_body(unsigned char* smem_raw, int b, int chunk, int chunks,
+                                         const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits,
+                                         const float* __restrict__ mask, MaskLayout ml, int L, int T, int frames_per_cta,
+                                         float sqrt_eps, float* __restrict__ part, float4* __restrict__ spec,
+                                         int64_t spec_utt, const Tables& tb) {
   float2* sm_all = reinterpret_cast<float2*>(smem_raw);
   float2* sm = sm_all + (size_t)(threadIdx.x >> 5) * f512::kSmemComplex;
   Lane ln;
@@ -437,7 +440,6 @@ k512_cov(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, c
   ln.init_full(tb.tw);   // this kernel runs 2 CTAs/SM on its accumulators anyway: spend spare registers on twiddles
 #endif
   const int lane = ln.lane, warp = threadIdx.x >> 5;
-  const int b = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
   const float* m0 = mix + (int64_t)b * 2 * L;
   const float* m1 = m0 + L;
   float w[16];
@@ -495,7 +497,8 @@ k512_cov(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, c
       }
       float2 v[16];
       win.frame(v, w);
-#if AVZ_COV_FULLTW
+#if defined(AVZ_COV_NOFFT)   // timing experiment only (profiles/README.md): everything but the transform
+#elif AVZ_COV_FULLTW
       f512::forward_full(v, sm, ln);
 #else
       f512::forward(v, sm, ln);
@@ -503,7 +506,7 @@ k512_cov(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, c
       float2 mir[8];
       f512::mirror_of_low(v, mir, ln);
       if (spec != nullptr) {
-        float4* sp = spec + ((int64_t)b * T + t) * 256 + lane;
+        float4* sp = spec + (spec_utt * T + t) * 256 + lane;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 q = make_float4(v[j].x, v[j].y, mir[j].x, mir[j].y);
@@ -511,7 +514,8 @@ k512_cov(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, c
             q.z = v[8].x;
             q.w = v[8].y;
           }
-          __stcs(sp + 32 * j, q);     // streaming store: read once by pass B, no reuse before that
+          if (L2KEEP) sp[32 * j] = q;
+          else __stcs(sp + 32 * j, q);     // streaming store: read once by pass B, no reuse before that
         }
       }
 #pragma unroll
@@ -573,6 +577,16 @@ k512_cov(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, c
   }
 }
 
+template <int HOP, int WMODE>
+__global__ void __launch_bounds__(kWarps * 32, AVZ_MINB_COV)
+k512_cov(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, const float* __restrict__ mask,
+         MaskLayout ml, int L, int T, int frames_per_cta, float sqrt_eps, float* __restrict__ part,
+         float4* __restrict__ spec, Tables tb) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  cov_body<HOP, WMODE, false>(smem_raw, blockIdx.y, blockIdx.x, gridDim.x, mix, ibm_bits, mask, ml, L, T, frames_per_cta,
+                              sqrt_eps, part, spec, blockIdx.y, tb);
+}
+
 // ------------------------------------------------------------------------------------------
 // beamform + post-filter + inverse + overlap-add
 // ------------------------------------------------------------------------------------------
@@ -595,16 +609,21 @@ __host__ __device__ constexpr size_t apply_smem_bytes() {
 
 // KEPT: the packed mix spectrum of every frame was stored by k512_cov (`spec`); no forward transform here: frames
 // are staged into a per-warp shared-memory ring by TMA bulk copies (cp.async.bulk + mbarrier), kStages deep.
+// (b, bx) = (blockIdx.y, blockIdx.x) of the plain launch; spec_utt: utterance slot of the kept spectrum (= b in the
+// plain launch, a ring slot in k512_fused).  The mbarriers of the TMA ring are initialised once per CTA (`init_bar`) and
+// keep counting phases across the tasks of a persistent kernel: bit `stage` of `phase_bits` is the parity the next wait
+// on that stage must use.
 template <int HOP, bool KEPT>
-__global__ void __launch_bounds__(kWarps * 32, KEPT ? AVZ_MINB_APPLY_KEPT : AVZ_MINB_APPLY)
-k512_apply(const float* __restrict__ mix, const float4* __restrict__ spec, const float2* __restrict__ wgt,
-           const uint32_t* __restrict__ ibm_bits, const float* __restrict__ mask, MaskLayout ml, int gain_mode,
-           float post_floor, int L, int T, int blocks_per_cta, float* __restrict__ out, float* __restrict__ peak,
-           int cluster_norm, float peak_eps, Tables tb) {
+__device__ __forceinline__ void apply_body(unsigned char* smem_raw, int b, int bx, bool init_bar, uint32_t& phase_bits,
+                                           int64_t spec_utt,
+                                           const float* __restrict__ mix, const float4* __restrict__ spec,
+                                           const float2* __restrict__ wgt, const uint32_t* __restrict__ ibm_bits,
+                                           const float* __restrict__ mask, MaskLayout ml, int gain_mode, float post_floor,
+                                           int L, int T, int blocks_per_cta, float* __restrict__ out,
+                                           float* __restrict__ peak, int cluster_norm, float peak_eps, const Tables& tb) {
   constexpr int R = kN / HOP;        // frames overlapping one hop-block
   constexpr int NR = HOP / 32;       // rows per hop-block
   constexpr int TAIL = 16 - NR;      // rows still open after a frame's first block is emitted
-  extern __shared__ __align__(128) unsigned char smem_raw[];
   float2* sm_all = reinterpret_cast<float2*>(smem_raw);
   float2* sm = sm_all + (size_t)(threadIdx.x >> 5) * f512::kSmemComplex;
   float4* s_ab = reinterpret_cast<float4*>(sm_all + (size_t)kWarps * f512::kSmemComplex);  // [kF] (a.x,a.y,b.x,b.y)
@@ -623,7 +642,6 @@ k512_apply(const float* __restrict__ mix, const float4* __restrict__ spec, const
   if (!KEPT || AVZ_APPLY_FULLTW) ln.init_full(tb.tw);   // !KEPT: same twiddles as k512_cov, so recomputed and kept spectra are bit-identical
 #endif
   const int lane = ln.lane, warp = threadIdx.x >> 5;
-  const int b = blockIdx.y;
   const float* m0 = mix + (int64_t)b * 2 * L;
   const float* m1 = m0 + L;
   // S[k] = conj(w0) Y0 + conj(w1) Y1 = a[k] Z[k] + b[k] conj(Z[N-k]),  a = (conj w0 - i conj w1)/2,
@@ -639,7 +657,7 @@ k512_apply(const float* __restrict__ mix, const float4* __restrict__ spec, const
       s_ab[k] = make_float4(sc * (w0.x - w1.y), sc * (-w0.y - w1.x), sc * (w0.x + w1.y), sc * (-w0.y + w1.x));
     }
   }
-  if (KEPT && lane == 0) {
+  if (KEPT && init_bar && lane == 0) {
 #pragma unroll
     for (int st = 0; st < kStages; ++st) mbar_init(s_bar + st, 1);
     mbar_fence_init();
@@ -664,7 +682,7 @@ k512_apply(const float* __restrict__ mix, const float4* __restrict__ spec, const
   // run to balance that; later warps start cold and their first R-1 blocks are completed at the end from the
   // previous warp's open tail.  Runs are at least R-1 blocks long so a head block only needs one tail.
   const int g_lo = R / 2, g_hi = R / 2 + T - 1;
-  const int G0 = g_lo + blockIdx.x * blocks_per_cta, G1 = min(g_hi, G0 + blocks_per_cta);
+  const int G0 = g_lo + bx * blocks_per_cta, G1 = min(g_hi, G0 + blocks_per_cta);
   const int nblk = G1 - G0;
   const int per = max(R - 1, (nblk + (R - 1) + kWarps - 1) / kWarps);   // frames per warp incl. warp 0's warm-up
   const int first = max(min(nblk, R - 1), min(nblk, per - (R - 1)));    // warp 0's blocks
@@ -724,7 +742,7 @@ k512_apply(const float* __restrict__ mix, const float4* __restrict__ spec, const
     // KEPT: frames t_first .. t_last of the kept spectrum stream through the ring; frame t lives in stage
     // (t - t_first) % kStages and is the ((t - t_first) / kStages)-th use of that stage's barrier.
     const int t_last = min(gb - 1, T - 1);
-    const float4* sp = KEPT ? spec + ((int64_t)b * T + t_first) * 256 : nullptr;
+    const float4* sp = KEPT ? spec + (spec_utt * T + t_first) * 256 : nullptr;
     if (KEPT) {
       if (lane == 0) {
 #pragma unroll
@@ -782,7 +800,8 @@ k512_apply(const float* __restrict__ mix, const float4* __restrict__ spec, const
         float2 zlo[8], mir[8], zny;
         if (KEPT) {
           const int use = g - t_first, st = use % kStages;
-          mbar_wait(s_bar + st, (uint32_t)(use / kStages) & 1u);
+          mbar_wait(s_bar + st, (phase_bits >> st) & 1u);
+          phase_bits ^= 1u << st;
           const float4* fr = s_ring + st * 256 + lane;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -929,6 +948,190 @@ k512_apply(const float* __restrict__ mix, const float4* __restrict__ spec, const
         o4[i] = make_float4(__fdiv_rn(v.x, den), __fdiv_rn(v.y, den), __fdiv_rn(v.z, den), __fdiv_rn(v.w, den));
       }
     }
+  }
+}
+
+template <int HOP, bool KEPT>
+__global__ void __launch_bounds__(kWarps * 32, KEPT ? AVZ_MINB_APPLY_KEPT : AVZ_MINB_APPLY)
+k512_apply(const float* __restrict__ mix, const float4* __restrict__ spec, const float2* __restrict__ wgt,
+           const uint32_t* __restrict__ ibm_bits, const float* __restrict__ mask, MaskLayout ml, int gain_mode,
+           float post_floor, int L, int T, int blocks_per_cta, float* __restrict__ out, float* __restrict__ peak,
+           int cluster_norm, float peak_eps, Tables tb) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint32_t phase_bits = 0u;
+  apply_body<HOP, KEPT>(smem_raw, blockIdx.y, blockIdx.x, true, phase_bits, blockIdx.y, mix, spec, wgt, ibm_bits, mask, ml,
+                        gain_mode, post_floor, L, T, blocks_per_cta, out, peak, cluster_norm, peak_eps, tb);
+}
+
+// ------------------------------------------------------------------------------------------
+// Pass A + weights + pass B + normalisation as ONE persistent kernel (oracle-IBM path)
+// ------------------------------------------------------------------------------------------
+// Measured (profiles/README.md, "what bounds pass A / pass B"): with the spectrum handed from pass A to pass B through
+// HBM, k512_cov is bound by its 2 GB store stream and k512_apply by the 2 GB read-back (70-76 % of the DRAM peak), not
+// by instructions.  Here the two passes are tasks of one launch, dequeued in an order that lets pass B of an utterance
+// run a few microseconds after its pass A, and the kept spectrum lives in a RING of utterance slots small enough to
+// stay in the 126 MB L2: a slot is overwritten while its lines are still dirty in L2, so the spectrum never reaches
+// DRAM in either direction.  Finalize, the 2x2 solve and the peak normalisation ride along (the CTA that completes an
+// utterance's last pass-A / pass-B task does them), which also removes three launches.
+//
+// Task queue (one atomic counter; tasks are dequeued in index order by whichever CTA is free):
+//   slot s = 0, 1, ...:  [A(s, chunk 0..CA-1)]  then  [B(s - LAG, chunk 0..CB-1)]
+// A(u, c) first waits until B(u - NSLOT) is complete (its ring slot is free); B(u, c) waits until the weights of u are
+// published.  Every wait targets tasks with a SMALLER queue index; those were dequeued earlier by CTAs that are
+// running, and the induction closes on task 0, which waits for nothing - so the kernel cannot deadlock whatever the
+// number of resident CTAs.  Results are bit-identical to the separate kernels (same device functions, same order).
+struct FusedArgs {
+  const float* mix;
+  const uint32_t* ibm_bits;
+  const float2* dvec;
+  float* part;       // [B][CA][5][kFP]
+  float4* spec;      // [NSLOT][T][256]
+  float4* R;         // [B][F]
+  float* msum;       // [B][F]
+  float2* w;         // [B][F][2]
+  float* out;        // [B][(T-1) HOP]
+  float* peak;       // [B]
+  int* ctrl;         // [0] queue head, then a_done[B], w_ready[B], b_done[B]
+  AvzMvdrCfg cfg;
+  float norm_eps, peak_eps;   // peak_eps < 0: no normalisation
+  int B, L, T, fpt, CA, CB, lag, nslot;
+  Tables tb;
+};
+
+template <int HOP>
+__host__ __device__ constexpr size_t fused_smem_bytes() {
+  constexpr size_t cov = (size_t)kWarps * f512::kSmemComplex * sizeof(float2) + (size_t)kWarps * 5 * kFP * sizeof(float);
+  constexpr size_t app = apply_smem_bytes<HOP, true>();
+  return cov > app ? cov : app;
+}
+
+__device__ __forceinline__ void spin_until(const int* flag, int want, int what, int u) {
+  if (threadIdx.x == 0) {
+    unsigned spins = 0;
+    while (ld_acquire_gpu(flag) < want) {
+      __nanosleep(64);
+      if (++spins > (1u << 19)) {   // ~a second: a protocol error must not hang the device
+        printf("k512_fused: wait %d on utterance %d timed out (flag %d < %d, block %d)\n", what, u, ld_acquire_gpu(flag), want,
+               (int)blockIdx.x);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+}
+
+template <int HOP>
+__global__ void __launch_bounds__(kWarps * 32, 2) k512_fused(FusedArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ int s_task, s_last;
+  int* queue = a.ctrl;
+  int* a_done = a.ctrl + 1;
+  int* w_ready = a_done + a.B;
+  int* b_done = w_ready + a.B;
+  const int lag = a.lag;
+  const int head = lag * a.CA;                       // slots 0..lag-1: pass A only
+  const int mid = (a.B - lag) * (a.CA + a.CB);       // slots lag..B-1: A(s) then B(s - lag)
+  const int n_tasks = a.B * (a.CA + a.CB);
+  const int64_t out_len = (int64_t)(a.T - 1) * HOP;
+  bool ring_used = false;
+  uint32_t phase_bits = 0u;      // per warp: parity of the next wait on each stage of its TMA ring
+  for (;;) {
+    if (threadIdx.x == 0) s_task = atomicAdd(queue, 1);
+    __syncthreads();
+    const int t = s_task;
+    if (t >= n_tasks) break;
+    bool is_a;
+    int u, c;
+    if (t < head) {
+      is_a = true, u = t / a.CA, c = t - u * a.CA;
+    } else if (t < head + mid) {
+      const int q = t - head, slot = q / (a.CA + a.CB), r = q - slot * (a.CA + a.CB);
+      if (r < a.CA) is_a = true, u = lag + slot, c = r;
+      else is_a = false, u = slot, c = r - a.CA;
+    } else {
+      const int q = t - head - mid;
+      is_a = false, u = (a.B - lag) + q / a.CB, c = q % a.CB;
+    }
+    const int ring = u % a.nslot;
+    if (is_a) {
+      if (u >= a.nslot) spin_until(b_done + (u - a.nslot), a.CB, 0, u);   // the ring slot's previous utterance has been consumed
+      cov_body<HOP, W_BITS, true>(smem_raw, u, c, a.CA, a.mix, a.ibm_bits, nullptr, MaskLayout{0, 0, 0, nullptr, 0u, 0u}, a.L,
+                                  a.T, a.fpt, 0.f, a.part, a.spec, ring, a.tb);
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) s_last = (atomicAdd(a_done + u, 1) == a.CA - 1);
+      __syncthreads();
+      if (s_last) {
+        // last pass-A task of utterance u: float64 sum of the chunk partials in k_cov_finalize's order (chunks c = q mod 4
+        // summed per slice q, slices combined in order), then the closed-form weights of k_mvdr_weights
+        __threadfence();
+        for (int k = threadIdx.x; k < kF; k += kWarps * 32) {
+          double sl[4][5];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int j = 0; j < 5; ++j) sl[q][j] = 0.0;
+          for (int c0 = 0; c0 < a.CA; c0 += 4)
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (c0 + q < a.CA) {
+                const float* p = a.part + ((int64_t)u * a.CA + c0 + q) * 5 * kFP;
+#pragma unroll
+                for (int j = 0; j < 5; ++j) sl[q][j] += (double)__ldcg(p + j * kFP + k);
+              }
+          double sj[5];
+#pragma unroll
+          for (int j = 0; j < 5; ++j) sj[j] = ((sl[0][j] + sl[1][j]) + sl[2][j]) + sl[3][j];
+          const double inv = 1.0 / (sj[4] + (double)a.norm_eps);
+          const float4 r = make_float4((float)(sj[0] * inv), (float)(sj[1] * inv), (float)(sj[2] * inv), (float)(sj[3] * inv));
+          const int64_t idx = (int64_t)u * kF + k;
+          a.R[idx] = r;
+          a.msum[idx] = (float)sj[4];
+          float2 w0, w1;
+          mvdr_weights_bin(r, a.dvec[2 * k], a.dvec[2 * k + 1], k, a.cfg, w0, w1);
+          a.w[2 * idx] = w0;
+          a.w[2 * idx + 1] = w1;
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) st_release_gpu(w_ready + u, 1);
+      }
+    } else {
+      spin_until(w_ready + u, 1, 1, u);
+      fence_proxy_async_all();   // the spectrum was written by other CTAs' ordinary stores; it is read by TMA bulk copies here
+      apply_body<HOP, true>(smem_raw, u, c, !ring_used, phase_bits, ring, nullptr, a.spec, a.w, a.ibm_bits, nullptr,
+                            MaskLayout{0, 0, 0, nullptr, 0u, 0u}, a.cfg.post_mode == AVZ_POST_ONE_MINUS_NOISE ? GAIN_BITS : GAIN_NONE,
+                            0.f, a.L, a.T, a.fpt, a.out, a.peak, 0, 0.f, a.tb);
+      ring_used = true;
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) s_last = (atomicAdd(b_done + u, 1) == a.CB - 1);
+      __syncthreads();
+      if (s_last && a.peak_eps >= 0.f) {
+        // last pass-B task of utterance u: x / (max|x| + eps) while the output is still in L2 (k_peak_normalise's arithmetic)
+        __threadfence();
+        const float den = __ldcg(a.peak + u) + a.peak_eps;
+        float* xb = a.out + (int64_t)u * out_len;
+        float4* x4 = reinterpret_cast<float4*>(xb);
+        const int n4 = (int)(out_len >> 2);           // HOP is a multiple of 4 and the row starts 16-byte aligned
+        constexpr int kStep = kWarps * 32;
+        int i = threadIdx.x;
+        for (; i + 3 * kStep < n4; i += 4 * kStep) {
+          float4 v[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) v[q] = __ldcg(x4 + i + q * kStep);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            x4[i + q * kStep] = make_float4(__fdiv_rn(v[q].x, den), __fdiv_rn(v[q].y, den), __fdiv_rn(v[q].z, den),
+                                            __fdiv_rn(v[q].w, den));
+        }
+        for (; i < n4; i += kStep) {
+          const float4 v = __ldcg(x4 + i);
+          x4[i] = make_float4(__fdiv_rn(v.x, den), __fdiv_rn(v.y, den), __fdiv_rn(v.z, den), __fdiv_rn(v.w, den));
+        }
+      }
+    }
+    __syncthreads();   // shared memory (task id, transposition buffers, ring) is reused by the next task
   }
 }
 
@@ -1124,6 +1327,115 @@ int launch_apply(const float* mix, const void* spec, const float* w, const uint3
   AVZ_LAUNCH_OK("k512_apply");
   return AVZ_OK;
 }
+
+// ---- fused oracle path: k512_ibm + k512_ibm_fixup, then k512_fused (pass A, weights, pass B, normalisation)
+static int fused_env(const char* name, int dflt) {
+#ifdef AVZ_EXPERIMENT
+  if (const char* e = getenv(name)) return atoi(e);
+#endif
+  (void)name;
+  return dflt;
+}
+struct FusedGeo {
+  int T, fpt, CA, CB, lag, nslot;
+  size_t off_amb, off_ctrl, off_spec, total;
+};
+static FusedGeo fused_geo(int B, int64_t L, int hop) {
+  FusedGeo g;
+  g.T = (int)avz_num_frames(L, kN, hop);
+  g.fpt = fused_env("AVZ_FUSED_FPT", 32);            // frames (pass A) / hop-blocks (pass B) per task
+  if (g.fpt < 8 * kWarps) g.fpt = 8 * kWarps;
+  g.CA = (g.T + g.fpt - 1) / g.fpt;
+  g.CB = (g.T - 1 + g.fpt - 1) / g.fpt;
+  // pass B of an utterance is dequeued `lag` utterances after its pass A: far enough behind that the ~2 x SMs tasks in
+  // flight have retired its pass A (no waiting), close enough that lag + in-flight utterances of spectrum fit in L2
+  const int inflight = (2 * num_sms() + g.CA + g.CB - 1) / (g.CA + g.CB);
+  g.lag = fused_env("AVZ_FUSED_LAG", inflight + 2);
+  if (g.lag > B) g.lag = B;
+  if (g.lag < 1) g.lag = 1;
+  g.nslot = fused_env("AVZ_FUSED_NSLOT", g.lag + inflight + 2);
+  if (g.nslot > B) g.nslot = B;
+  if (g.nslot < g.lag + 1 && g.nslot < B) g.nslot = g.lag + 1;
+  g.off_amb = (((size_t)B * g.CA * 5 * kFP * sizeof(float)) + 15) / 16 * 16;
+  g.off_ctrl = g.off_amb + 16 + (size_t)amb_cap(B, g.T) * 8;
+  g.off_spec = (g.off_ctrl + (size_t)(1 + 3 * (size_t)B) * sizeof(int) + 255) / 256 * 256;
+  g.total = g.off_spec + (size_t)g.nslot * g.T * 4096;
+  return g;
+}
+int64_t fused_ws_bytes(int B, int64_t L, int hop) { return (int64_t)fused_geo(B, L, hop).total; }
+
+template <int HOP>
+int launch_oracle_fused(const float* mix, const float* tgt, const float* itf, int B, int64_t L, const AvzMvdrCfg* cfg,
+                        float norm_eps, float peak_eps, const float* dvec, uint32_t* ibm_bits, float* R, float* msum,
+                        float* w, float* out, float* peak, void* ws, cudaStream_t st) {
+  Tables tb;
+  int rc = tables_for(kN, &tb);
+  if (rc) return rc;
+  if (L >= (1ll << 30)) return set_error(AVZ_EINVAL, "L=%lld too long for the 512-point fast path", (long long)L);
+  const FusedGeo g = fused_geo(B, L, HOP);
+  if (g.T < 2) return set_error(AVZ_EINVAL, "signal too short");
+  unsigned char* wsb = static_cast<unsigned char*>(ws);
+  AmbList al;
+  al.count = reinterpret_cast<unsigned int*>(wsb + g.off_amb);
+  al.entries = reinterpret_cast<unsigned long long*>(wsb + g.off_amb + 16);
+  al.cap = amb_cap(B, g.T);
+  AVZ_CUDA_OK(cudaMemsetAsync(al.count, 0, 16, st));
+  AVZ_CUDA_OK(cudaMemsetAsync(wsb + g.off_ctrl, 0, (size_t)(1 + 3 * (size_t)B) * sizeof(int), st));
+  AVZ_CUDA_OK(cudaMemsetAsync(peak, 0, (size_t)B * sizeof(float), st));
+  const size_t smem_fft = (size_t)kWarps * f512::kSmemComplex * sizeof(float2);
+  const int fpc = frames_per_cta(B, g.T, num_sms());
+  AVZ_CUDA_OK(cudaFuncSetAttribute(k512_ibm<HOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
+  prof_begin(PROF_IBM, st);
+  k512_ibm<HOP><<<dim3((g.T + fpc - 1) / fpc, B), kWarps * 32, smem_fft, st>>>(tgt, itf, (int)L, g.T, fpc, ibm_bits, al,
+                                                                                ibm_tol2(), tb);
+  prof_end(PROF_IBM, st);
+  AVZ_LAUNCH_OK("k512_ibm");
+  prof_begin(PROF_FIXUP, st);
+  k512_ibm_fixup<<<num_sms() * 32, 256, 0, st>>>(tgt, itf, L, g.T, HOP, B, ibm_bits, al, tb);
+  prof_end(PROF_FIXUP, st);
+  AVZ_LAUNCH_OK("k512_ibm_fixup");
+  FusedArgs fa;
+  fa.mix = mix;
+  fa.ibm_bits = ibm_bits;
+  fa.dvec = reinterpret_cast<const float2*>(dvec);
+  fa.part = reinterpret_cast<float*>(wsb);
+  fa.spec = reinterpret_cast<float4*>(wsb + g.off_spec);
+  fa.R = reinterpret_cast<float4*>(R);
+  fa.msum = msum;
+  fa.w = reinterpret_cast<float2*>(w);
+  fa.out = out;
+  fa.peak = peak;
+  fa.ctrl = reinterpret_cast<int*>(wsb + g.off_ctrl);
+  fa.cfg = *cfg;
+  fa.norm_eps = norm_eps;
+  fa.peak_eps = peak_eps;
+  fa.B = B;
+  fa.L = (int)L;
+  fa.T = g.T;
+  fa.fpt = g.fpt;
+  fa.CA = g.CA;
+  fa.CB = g.CB;
+  fa.lag = g.lag;
+  fa.nslot = g.nslot;
+  fa.tb = tb;
+  const size_t smem = fused_smem_bytes<HOP>();
+  AVZ_CUDA_OK(cudaFuncSetAttribute(k512_fused<HOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  AVZ_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k512_fused<HOP>, kWarps * 32, smem));
+  if (per_sm < 1) return set_error(AVZ_ECUDA, "k512_fused does not fit on this device");
+  int64_t grid = (int64_t)per_sm * num_sms();
+  const int64_t n_tasks = (int64_t)B * (g.CA + g.CB);
+  if (grid > n_tasks) grid = n_tasks;
+  prof_begin(PROF_COV, st);
+  k512_fused<HOP><<<(unsigned)grid, kWarps * 32, smem, st>>>(fa);
+  prof_end(PROF_COV, st);
+  AVZ_LAUNCH_OK("k512_fused");
+  return AVZ_OK;
+}
+template int launch_oracle_fused<128>(const float*, const float*, const float*, int, int64_t, const AvzMvdrCfg*, float, float,
+                                      const float*, uint32_t*, float*, float*, float*, float*, float*, void*, cudaStream_t);
+template int launch_oracle_fused<256>(const float*, const float*, const float*, int, int64_t, const AvzMvdrCfg*, float, float,
+                                      const float*, uint32_t*, float*, float*, float*, float*, float*, void*, cudaStream_t);
 
 // Every bin decided in float64 (slow; the checker for the float32 + fix-up path at sizes the CPU oracle cannot reach).
 int launch_ibm_exact(const float* tgt, const float* itf, int B, int64_t L, int hop, uint32_t* ibm_bits, void* ws16,

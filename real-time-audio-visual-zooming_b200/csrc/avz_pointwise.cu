@@ -8,47 +8,13 @@ namespace avz {
 // ------------------------------------------------------------------------------------------
 // MVDR weights.  Replaces oracle_debug.py:68-79 (np.linalg.solve on R + sigma I, then w / (d^H w + eps)).
 // ------------------------------------------------------------------------------------------
-struct cd {
-  double x, y;
-};
-__device__ __forceinline__ cd cdmul(cd a, cd b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
-__device__ __forceinline__ cd cddiv(cd a, cd b) {
-  const double den = b.x * b.x + b.y * b.y;
-  return {(a.x * b.x + a.y * b.y) / den, (a.y * b.x - a.x * b.y) / den};
-}
-
 __global__ void k_mvdr_weights(const float4* __restrict__ R, const float2* __restrict__ dvec, int B, int F,
                                AvzMvdrCfg cfg, float2* __restrict__ w) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * F) return;
   const int k = idx % F;
-  float2 w0 = make_float2(0.f, 0.f), w1 = make_float2(0.f, 0.f);
-  if (k < cfg.hp_bins && cfg.hp_mode != AVZ_HP_NONE) {
-    if (cfg.hp_mode == AVZ_HP_MIC0) w0.x = 1.f;  // pass mic 0 through
-  } else {
-    const float4 r = R[idx];
-    const double a = (double)r.x + (double)cfg.sigma, c = (double)r.y + (double)cfg.sigma;
-    const cd bb = {(double)r.z, (double)r.w};  // R01; R10 = conj
-    const cd d0 = {(double)dvec[2 * k].x, (double)dvec[2 * k].y};
-    const cd d1 = {(double)dvec[2 * k + 1].x, (double)dvec[2 * k + 1].y};
-    const double det = a * c - (bb.x * bb.x + bb.y * bb.y);
-    if (det == 0.0 || !isfinite(det)) {
-      w0.x = 1.f;  // LinAlgError fallback w = [1, 0] (oracle_debug.py:78-79)
-    } else {
-      // u = inv([[a, b],[conj b, c]]) d
-      const cd bd1 = cdmul(bb, d1);
-      const cd cbd0 = cdmul({bb.x, -bb.y}, d0);
-      const cd u0 = {(c * d0.x - bd1.x) / det, (c * d0.y - bd1.y) / det};
-      const cd u1 = {(a * d1.x - cbd0.x) / det, (a * d1.y - cbd0.y) / det};
-      // denom = d^H u + w_eps
-      const cd t0 = cdmul({d0.x, -d0.y}, u0);
-      const cd t1 = cdmul({d1.x, -d1.y}, u1);
-      const cd den = {t0.x + t1.x + (double)cfg.w_eps, t0.y + t1.y};
-      const cd q0 = cddiv(u0, den), q1 = cddiv(u1, den);
-      w0 = make_float2((float)q0.x, (float)q0.y);
-      w1 = make_float2((float)q1.x, (float)q1.y);
-    }
-  }
+  float2 w0, w1;
+  mvdr_weights_bin(R[idx], dvec[2 * k], dvec[2 * k + 1], k, cfg, w0, w1);
   w[2 * (int64_t)idx] = w0;
   w[2 * (int64_t)idx + 1] = w1;
 }

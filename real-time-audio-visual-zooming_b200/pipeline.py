@@ -24,7 +24,10 @@ class OracleMvdr:
     # (+ two small memsets: the near-tie counter and `peak`)
     launches_per_step = 7
 
-    def __init__(self, cfg: MvdrConfig, B: int, L: int, device, keep_spectrum: bool = True, fused_norm: bool = False):
+    def __init__(self, cfg: MvdrConfig, B: int, L: int, device, keep_spectrum: bool = True, fused_norm: bool = False,
+                 fused: bool = False):
+        """`fused`: run pass A, the weights, pass B and the normalisation as ONE persistent kernel whose kept spectrum
+        stays in L2 (avz_oracle_fused_f32; n_fft 512, IBM post-filter or none) instead of five separate launches."""
         self.cfg, self.B, self.L, self.device = cfg, B, L, device
         self.lib = _lib.load()
         self.F = cfg.n_freq
@@ -52,6 +55,14 @@ class OracleMvdr:
         self.launches_per_step = 6 if self.fused_norm else 7
         self.d = steering_vectors(cfg, device)
         self.cc = cfg.to_c()
+        self.fused = bool(fused)
+        if self.fused:
+            nfw = self.lib.avz_oracle_fused_ws_bytes(B, L, cfg.n_fft, cfg.hop)
+            if nfw <= 0 or cfg.post not in ("one_minus_noise", "none"):
+                raise _lib.AvzError("the fused oracle kernel needs n_fft 512 (hop 128 / 256) and an IBM or no post-filter")
+            self.spec = None          # the fused kernel keeps its spectrum in a ring inside its own workspace
+            self.fws = torch.empty((int(nfw),), dtype=torch.uint8, device=device)
+            self.launches_per_step = 3
         _lib.check(self.lib.avz_init(cfg.n_fft), "avz_init")
 
     # individual stages (each one C-ABI call) ---------------------------------------------------
@@ -101,6 +112,15 @@ class OracleMvdr:
         buffer, or the contiguous float32 tensor `out` of that shape)."""
         if out is not None and (out.shape != self.out.shape or out.dtype != torch.float32 or not out.is_contiguous()):
             raise ValueError("out must be a contiguous float32 tensor of shape %s" % (tuple(self.out.shape),))
+        if self.fused:
+            c = self.cfg
+            dst = self.out if out is None else out
+            _lib.check(self.lib.avz_oracle_fused_f32(_ptr(mix), _ptr(tgt), _ptr(itf), self.B, self.L, c.n_fft, c.hop,
+                                                     C.byref(self.cc), -1.0 if c.peak_eps is None else float(c.peak_eps),
+                                                     _ptr(self.d), _ptr(self.bits), _ptr(self.R), _ptr(self.msum), _ptr(self.w),
+                                                     _ptr(dst), _ptr(self.peak), _ptr(self.fws), _stream()),
+                       "avz_oracle_fused_f32")
+            return dst
         self.pass_a(mix, tgt, itf)
         self.weights()
         self.pass_b(mix, out)
@@ -109,6 +129,7 @@ class OracleMvdr:
 
     KERNELS = ("k512_ibm", "k512_ibm_fixup", "k512_cov", "k_cov_finalize", "k_mvdr_weights", "k512_apply",
                "k_peak_normalise")
+    FUSED_KERNELS = ("k512_ibm", "k512_ibm_fixup", "k512_fused")
 
     def time_each_kernel(self, mix, tgt, itf, iters: int = 5) -> Dict[str, float]:
         """Average device time (ms) of every kernel of a step, from CUDA events the library records on the launching
@@ -126,6 +147,8 @@ class OracleMvdr:
                     acc[i] += max(0.0, float(buf[i]))
         finally:
             self.lib.avz_profile_enable(0)
+        if self.fused:      # the persistent kernel is timed in pass A's slot
+            return {k: acc[i] / iters for i, k in enumerate(self.FUSED_KERNELS)}
         return {k: acc[i] / iters for i, k in enumerate(self.KERNELS)}
 
     def time_kernels(self, mix, tgt, itf, iters: int = 5) -> Dict[str, float]:
@@ -156,10 +179,10 @@ class StreamedOracleMvdr:
     submit() enqueues a batch and returns the tensor its result will be in; join() makes the caller's stream wait for
     everything submitted.  A result tensor is reused after `depth` further submits."""
 
-    def __init__(self, cfg: MvdrConfig, B: int, L: int, device, depth: int = 2):
+    def __init__(self, cfg: MvdrConfig, B: int, L: int, device, depth: int = 2, fused: bool = False):
         if depth < 1:
             raise ValueError("depth must be >= 1")
-        self.engines = [OracleMvdr(cfg, B, L, device) for _ in range(depth)]
+        self.engines = [OracleMvdr(cfg, B, L, device, fused=fused) for _ in range(depth)]
         self.streams = [torch.cuda.Stream(device) for _ in range(depth)]
         self.launches_per_step = self.engines[0].launches_per_step
         self.n = 0
@@ -205,7 +228,7 @@ class HostPipeline:
         self.nsub = sub_batches if B % sub_batches == 0 and B >= sub_batches else 1
         self.sb = B // self.nsub
         dev = engine.device
-        self.sub = OracleMvdr(engine.cfg, self.sb, engine.L, dev)
+        self.sub = OracleMvdr(engine.cfg, self.sb, engine.L, dev, fused=engine.fused)
         f32 = dict(dtype=torch.float32, device=dev)
         self.d_mix = [torch.empty((self.sb, 2, engine.L), **f32) for _ in range(2)]
         self.d_tgt = [torch.empty((self.sb, engine.L), **f32) for _ in range(2)]

@@ -470,3 +470,38 @@ def test_config2_full_size_properties(az):
     assert float((resp[:, hp:] - 1).abs().max()) < 1e-5
     ref = O.oracle_mask_mvdr(mix8[3], tgt8[3], itf8[3], to_oracle_cfg(cfg))
     assert rel_l2(out[3].cpu().numpy(), ref) < WAVE_TOL
+
+
+@pytest.mark.parametrize("preset,B,dur", [("baseline_oracle", 5, 1.3), ("oracle_debug", 3, 2.0), ("baseline_oracle", 64, 1.0),
+                                          ("baseline_oracle", 300, 0.25), ("baseline_oracle", 1, 5.0)])
+def test_fused_persistent_kernel_equals_separate_kernels(az, preset, B, dur):
+    """avz_oracle_fused_f32 (pass A, weights, pass B and normalisation as tasks of one persistent kernel, spectrum ring
+    in L2) against the five separate launches: same IBM bits; the same waveform bit for bit when both cut an utterance
+    into the same 32-frame chunks (small batches), else to the float32 summation order of the covariance; reruns
+    bit-identical (no float atomics, fixed reduction orders, whatever order the tasks were dequeued in)."""
+    from avzoom import pipeline
+    cfg = az.PRESETS[preset]
+    mix, tgt, itf = synth(4, min(B, 16), dur, 2)
+    rep = (B + mix.shape[0] - 1) // mix.shape[0]
+    mix, tgt, itf = (np.tile(a, (rep,) + (1,) * (a.ndim - 1))[:B].copy() for a in (mix, tgt, itf))
+    scale = np.linspace(0.5, 1.5, B, dtype=np.float32)
+    mix, tgt, itf = mix * scale[:, None, None], tgt * scale[:, None], itf * scale[:, None]
+    mix_d, tgt_d, itf_d = (torch.from_numpy(a).cuda() for a in (mix, tgt, itf))
+    L = mix.shape[-1]
+    sep = pipeline.OracleMvdr(cfg, B, L, mix_d.device)
+    fus = pipeline.OracleMvdr(cfg, B, L, mix_d.device, fused=True)
+    a = sep.run(mix_d, tgt_d, itf_d).clone()
+    b = fus.run(mix_d, tgt_d, itf_d).clone()
+    assert torch.equal(sep.bits, fus.bits)
+    assert bool(torch.isfinite(b).all())
+    assert rel_l2(fus.R.cpu().numpy(), sep.R.cpu().numpy()) < 1e-6
+    assert rel_l2(b.cpu().numpy(), a.cpu().numpy()) < 1e-6
+    assert torch.allclose(fus.peak, sep.peak, rtol=1e-5)
+    if B <= 16:        # both paths cut T frames into 32-frame chunks: identical partial sums, identical everything
+        assert torch.equal(fus.R, sep.R) and torch.equal(fus.w, sep.w) and torch.equal(b, a)
+    for _ in range(3):
+        assert torch.equal(fus.run(mix_d, tgt_d, itf_d), b)
+    # against the float64 oracle directly
+    for i in (0, B - 1):
+        ref = O.oracle_mask_mvdr(mix[i], tgt[i], itf[i], to_oracle_cfg(cfg))
+        assert rel_l2(b[i].cpu().numpy(), ref) < 1e-4

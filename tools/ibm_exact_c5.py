@@ -48,7 +48,7 @@ def main():
         mism += int((diff != 0).sum().item()) if bool((diff != 0).any()) else 0
     res = {"config": "BASELINE config 5: %d synthetic 4 s mixtures (1 target + 3 interferers), n_fft 512 hop 128" % n_total,
            "utterances": n_total, "frames_per_utterance": T, "bins_checked": n_total * T * F,
-           "words_with_a_mismatch": mism, "tolerance": 5e-7,
+           "words_with_a_mismatch": mism, "tolerance": "compiled into the library (4e-6; AVZ_IBM_TOL only in -DAVZ_EXPERIMENT builds)",
            "fused_pass_a_ms_total": t_fused, "all_float64_ibm_ms_total": t_exact, "wall_s": time.perf_counter() - t0,
            "what": "k512_ibm (float32) + k512_ibm_fixup (float64 on near ties) vs avz_ibm_exact_f32 (every bin float64)"}
     os.makedirs("gpurun_out", exist_ok=True)

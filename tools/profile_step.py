@@ -1,5 +1,5 @@
 """Short single-GPU run of the fused oracle-mask MVDR step for ncu (keep it small: ncu replays every kernel).
-usage: python tools/profile_step.py [B] [steps]"""
+usage: python tools/profile_step.py [B] [steps] [fused|separate]"""
 import os
 import sys
 
@@ -16,7 +16,8 @@ reps = (B + 7) // 8
 mix = torch.from_numpy(mix).cuda().repeat(reps, 1, 1)[:B].contiguous()
 tgt = torch.from_numpy(tgt).cuda().repeat(reps, 1)[:B].contiguous()
 itf = torch.from_numpy(itf).cuda().repeat(reps, 1)[:B].contiguous()
-eng = pipeline.OracleMvdr(cfg, B, mix.shape[-1], mix.device)
+fused = (sys.argv[3] if len(sys.argv) > 3 else "fused") == "fused"
+eng = pipeline.OracleMvdr(cfg, B, mix.shape[-1], mix.device, fused=fused)
 for _ in range(steps):
     eng.run(mix, tgt, itf)
 torch.cuda.synchronize()
