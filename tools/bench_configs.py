@@ -79,6 +79,20 @@ def config3(dev, B: int = 256, unet_iters: int = 2):
             return torch.cat([net(X[i:i + sub]) for i in range(0, B, sub)]).float().contiguous()
 
     t_net, mask = _timed(unet, unet_iters)
+    # the same network in bf16 autocast + channels-last (the mask model is outside the path's scope - SURVEY 8-A lists it
+    # as the consumer of the features; reported so that the split of a config-3 step is visible)
+    net_cl = net.to(memory_format=torch.channels_last)
+
+    def unet_bf16():
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            return torch.cat([net_cl(X[i:i + sub].contiguous(memory_format=torch.channels_last)) for i in range(0, B, sub)]).float().contiguous()
+
+    try:
+        t_net16, mask16 = _timed(unet_bf16, unet_iters)
+        mask_err = float((mask16 - mask).abs().max())
+        del mask16
+    except Exception as ex:  # noqa: BLE001
+        t_net16, mask_err = None, repr(ex)
     t_mvdr, out = _timed(lambda: avzoom.learned_mask_mvdr(mix, mask, cfg), 10)
     del X, mask
     # the reference's own deployment form: 2 s windows at 50 % overlap, n_fft 1024 / hop 512, count-averaged chunk OLA
@@ -91,6 +105,7 @@ def config3(dev, B: int = 256, unet_iters: int = 2):
     return {"workload": f"{B} x 4 s: log-mag + IPD features -> FreqPreservingUNet (random init, eval, torch fp32) -> "
                         "learned-mask MVDR (sigma 1e-5, post-filter max(M, 0.05)), n_fft 512 hop 128",
             "features_ms": round(t_feat, 4), "mask_mvdr_ms": round(t_mvdr, 4), "unet_ms": round(t_net, 2),
+            "unet_bf16_channels_last_ms": None if t_net16 is None else round(t_net16, 2), "unet_bf16_max_mask_diff": mask_err,
             "hot_path_audio_s_per_s": round(audio_s / ((t_feat + t_mvdr) * 1e-3)),
             "with_unet_audio_s_per_s": round(audio_s / ((t_feat + t_net + t_mvdr) * 1e-3)),
             "finite": bool(torch.isfinite(out).all()),
