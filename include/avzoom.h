@@ -187,6 +187,15 @@ AVZ_API int avz_mvdr_apply_kept_norm_f32(const void* spec, const float* w, const
                                  int64_t L, int n_fft, int hop, const AvzMvdrCfg* cfg, float peak_eps, float* out,
                                  float* peak, void* stream);
 
+/* ---- pass A with its per-utterance tail folded in (n_fft 512, hop 128 / 256): as avz_ibm_cov_keep_f32 (spec may be
+ * NULL: no kept spectrum), and the block that finishes an utterance's last frame chunk also sums the chunk partials
+ * (oracle_debug.py:60-64) and solves the 257 2x2 systems (oracle_debug.py:68-79) - R, msum and w come out of the one
+ * launch, bit-identical to avz_ibm_cov_keep_f32 + avz_mvdr_weights_f32.  Two launches fewer per step: a single utterance
+ * (BASELINE config 1) is a chain of dependent launches of a few microseconds each.  dvec [257,2] complex64. */
+AVZ_API int avz_ibm_cov_weights_keep_f32(const float* mix, const float* tgt, const float* itf, int B, int64_t L, int n_fft,
+                                 int hop, const AvzMvdrCfg* cfg, const float* dvec, uint32_t* ibm_bits, float* R,
+                                 float* msum, float* w, void* ws, void* spec, void* stream);
+
 /* ---- the whole oracle path of oracle_debug.py:42-94 as ONE call (n_fft 512, hop 128 / 256): k512_ibm + k512_ibm_fixup,
  * then a single persistent kernel whose tasks are pass A (masked covariance, spectrum kept), the per-utterance
  * finalize + 2x2 solve, pass B (beamform, post-filter, iSTFT / overlap-add) and the peak normalisation.  Pass B of an

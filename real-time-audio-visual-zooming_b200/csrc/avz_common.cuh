@@ -20,6 +20,16 @@ struct Tables {
   const double* win_d;  // [n]
 };
 
+// what pass A needs to also finalize the covariance and solve for the weights (k512_cov_w)
+struct CovTailArgs {
+  const float* dvec;
+  float* R;
+  float* msum;
+  float* w;
+  const AvzMvdrCfg* cfg;
+  float norm_eps;
+};
+
 int set_error(int code, const char* fmt, ...);
 int tables_for(int n_fft, Tables* out);
 int check_fft_args(int n_fft, int hop, int64_t L);

@@ -26,7 +26,8 @@ int launch_ibm_exact(const float* tgt, const float* itf, int B, int64_t L, int h
                      cudaStream_t st);
 template <int HOP>
 int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const float* mask, int B, int64_t L,
-                   float sqrt_eps, uint32_t* ibm_bits, float* part, int* chunks_out, void* spec, cudaStream_t st);
+                   float sqrt_eps, uint32_t* ibm_bits, float* part, int* chunks_out, void* spec, cudaStream_t st,
+                   const CovTailArgs* tail = nullptr);
 int64_t fused_ws_bytes(int B, int64_t L, int hop);
 template <int HOP>
 int launch_oracle_fused(const float* mix, const float* tgt, const float* itf, int B, int64_t L, const AvzMvdrCfg* cfg,
@@ -830,6 +831,24 @@ int avz_mvdr_apply_kept_norm_f32(const void* spec, const float* w, const uint32_
                                  float* peak, void* stream) {
   if (!peak) return set_error(AVZ_EINVAL, "avz_mvdr_apply_kept_norm_f32: peak buffer required");
   return apply_kept(spec, w, ibm_bits, mask, B, L, n_fft, hop, cfg, out, peak, 1, peak_eps, stream);
+}
+
+// ---- pass A with finalize + weights folded into its last block per utterance (n_fft 512 fast path)
+int avz_ibm_cov_weights_keep_f32(const float* mix, const float* tgt, const float* itf, int B, int64_t L, int n_fft, int hop,
+                                 const AvzMvdrCfg* cfg, const float* dvec, uint32_t* ibm_bits, float* R, float* msum,
+                                 float* w, void* ws, void* spec, void* stream) {
+  if (!mix || !tgt || !itf || !cfg || !dvec || !ibm_bits || !R || !msum || !w || !ws || B <= 0 || B > 65535)
+    return set_error(AVZ_EINVAL, "avz_ibm_cov_weights_keep_f32: null pointer or bad batch size");
+  int rc = check_fft_args(n_fft, hop, L);
+  if (rc) return rc;
+  if (!use_opt512(n_fft, hop))
+    return set_error(AVZ_EINVAL, "avz_ibm_cov_weights_keep_f32: n_fft 512 with hop 128 or 256 only");
+  CovTailArgs tail{dvec, R, msum, w, cfg, cfg->norm_eps};
+  int chunks = 0;
+  return (hop == 128) ? o512::launch_ibm_cov<128>(mix, tgt, itf, nullptr, B, L, 0.f, ibm_bits, (float*)ws, &chunks, spec,
+                                                  (cudaStream_t)stream, &tail)
+                      : o512::launch_ibm_cov<256>(mix, tgt, itf, nullptr, B, L, 0.f, ibm_bits, (float*)ws, &chunks, spec,
+                                                  (cudaStream_t)stream, &tail);
 }
 
 // ---- the whole oracle path in two small launches + one persistent kernel (n_fft 512, hop 128 / 256)

@@ -577,6 +577,69 @@ __device__ __forceinline__ void cov_body(unsigned char* smem_raw, int b, int chu
   }
 }
 
+// The last pass-A block of utterance u: float64 sum of the chunk partials in k_cov_finalize's order (chunks c = q mod 4
+// summed per slice q, slices combined in order) and the closed-form weights of k_mvdr_weights - same arithmetic, same bits.
+__device__ __forceinline__ void finalize_weights_utt(const float* __restrict__ part, int u, int chunks, float norm_eps,
+                                                     const float2* __restrict__ dvec, const AvzMvdrCfg& cfg,
+                                                     float4* __restrict__ R, float* __restrict__ msum, float2* __restrict__ w) {
+  for (int k = threadIdx.x; k < kF; k += kWarps * 32) {
+    double sl[4][5];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int j = 0; j < 5; ++j) sl[q][j] = 0.0;
+    for (int c0 = 0; c0 < chunks; c0 += 4)
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (c0 + q < chunks) {
+          const float* p = part + ((int64_t)u * chunks + c0 + q) * 5 * kFP;
+#pragma unroll
+          for (int j = 0; j < 5; ++j) sl[q][j] += (double)__ldcg(p + j * kFP + k);
+        }
+    double sj[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) sj[j] = ((sl[0][j] + sl[1][j]) + sl[2][j]) + sl[3][j];
+    const double inv = 1.0 / (sj[4] + (double)norm_eps);
+    const float4 r = make_float4((float)(sj[0] * inv), (float)(sj[1] * inv), (float)(sj[2] * inv), (float)(sj[3] * inv));
+    const int64_t idx = (int64_t)u * kF + k;
+    R[idx] = r;
+    msum[idx] = (float)sj[4];
+    float2 w0, w1;
+    mvdr_weights_bin(r, dvec[2 * k], dvec[2 * k + 1], k, cfg, w0, w1);
+    w[2 * idx] = w0;
+    w[2 * idx + 1] = w1;
+  }
+}
+
+// Pass A with the per-utterance tail folded in: the block that completes an utterance's last chunk (a counter per
+// utterance) sums the partials and solves the 257 2x2 systems - two launches fewer per step, which is what a single
+// utterance (BASELINE config 1: a chain of dependent launches of a few microseconds each) is made of.
+struct CovTail {
+  int* done;               // [B] zeroed by the launcher
+  const float2* dvec;
+  float4* R;
+  float* msum;
+  float2* w;
+  AvzMvdrCfg cfg;
+  float norm_eps;
+};
+template <int HOP>
+__global__ void __launch_bounds__(kWarps * 32, AVZ_MINB_COV)
+k512_cov_w(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, int L, int T, int frames_per_cta,
+           float* __restrict__ part, float4* __restrict__ spec, CovTail tail, Tables tb) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ int s_last;
+  cov_body<HOP, W_BITS, false>(smem_raw, blockIdx.y, blockIdx.x, gridDim.x, mix, ibm_bits, nullptr,
+                               MaskLayout{0, 0, 0, nullptr, 0u, 0u}, L, T, frames_per_cta, 0.f, part, spec, blockIdx.y, tb);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(tail.done + blockIdx.y, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  finalize_weights_utt(part, blockIdx.y, gridDim.x, tail.norm_eps, tail.dvec, tail.cfg, tail.R, tail.msum, tail.w);
+}
+
 template <int HOP, int WMODE>
 __global__ void __launch_bounds__(kWarps * 32, AVZ_MINB_COV)
 k512_cov(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, const float* __restrict__ mask,
@@ -1065,33 +1128,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) k512_fused(FusedArgs a) {
         // last pass-A task of utterance u: float64 sum of the chunk partials in k_cov_finalize's order (chunks c = q mod 4
         // summed per slice q, slices combined in order), then the closed-form weights of k_mvdr_weights
         __threadfence();
-        for (int k = threadIdx.x; k < kF; k += kWarps * 32) {
-          double sl[4][5];
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-#pragma unroll
-            for (int j = 0; j < 5; ++j) sl[q][j] = 0.0;
-          for (int c0 = 0; c0 < a.CA; c0 += 4)
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (c0 + q < a.CA) {
-                const float* p = a.part + ((int64_t)u * a.CA + c0 + q) * 5 * kFP;
-#pragma unroll
-                for (int j = 0; j < 5; ++j) sl[q][j] += (double)__ldcg(p + j * kFP + k);
-              }
-          double sj[5];
-#pragma unroll
-          for (int j = 0; j < 5; ++j) sj[j] = ((sl[0][j] + sl[1][j]) + sl[2][j]) + sl[3][j];
-          const double inv = 1.0 / (sj[4] + (double)a.norm_eps);
-          const float4 r = make_float4((float)(sj[0] * inv), (float)(sj[1] * inv), (float)(sj[2] * inv), (float)(sj[3] * inv));
-          const int64_t idx = (int64_t)u * kF + k;
-          a.R[idx] = r;
-          a.msum[idx] = (float)sj[4];
-          float2 w0, w1;
-          mvdr_weights_bin(r, a.dvec[2 * k], a.dvec[2 * k + 1], k, a.cfg, w0, w1);
-          a.w[2 * idx] = w0;
-          a.w[2 * idx + 1] = w1;
-        }
+        finalize_weights_utt(a.part, u, a.CA, a.norm_eps, a.dvec, a.cfg, a.R, a.msum, a.w);
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) st_release_gpu(w_ready + u, 1);
@@ -1170,8 +1207,8 @@ static unsigned amb_cap(int B, int T) {
   const unsigned long long c = (unsigned long long)B * T * 8ull;   // 8 near-ties per frame on average
   return (unsigned)(c > (1ull << 26) ? (1ull << 26) : c);
 }
-int64_t ws_bytes512(int B, int T) {
-  return (int64_t)(part_bytes(B, cov_chunks512(B, T)) + 16 + (size_t)amb_cap(B, T) * 8);
+int64_t ws_bytes512(int B, int T) {   // partials, near-tie counter + list, per-utterance completion counters (k512_cov_w)
+  return (int64_t)(part_bytes(B, cov_chunks512(B, T)) + 16 + (size_t)amb_cap(B, T) * 8 + (size_t)B * sizeof(int));
 }
 
 // kept-spectrum buffer: [B*T frames x 4096 B][per-utterance completion counters, padded to 256 B][transposed mask]
@@ -1216,9 +1253,12 @@ static float ibm_tol2() {
   return t2;
 }
 
+// tail (optional, IBM path only): fold k_cov_finalize + k_mvdr_weights into pass A (k512_cov_w); its counters live behind
+// the near-tie list in the workspace
 template <int HOP>
 int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const float* mask, int B, int64_t L,
-                   float sqrt_eps, uint32_t* ibm_bits, float* part, int* chunks_out, void* spec, cudaStream_t st) {
+                   float sqrt_eps, uint32_t* ibm_bits, float* part, int* chunks_out, void* spec, cudaStream_t st,
+                   const CovTailArgs* tail) {
   Tables tb;
   int rc = tables_for(kN, &tb);
   if (rc) return rc;
@@ -1236,6 +1276,7 @@ int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const f
     al.entries = reinterpret_cast<unsigned long long*>(wsb + 16);
     al.cap = amb_cap(B, T);
     AVZ_CUDA_OK(cudaMemsetAsync(al.count, 0, 16, st));
+    if (tail != nullptr) AVZ_CUDA_OK(cudaMemsetAsync(wsb + 16 + (size_t)al.cap * 8, 0, (size_t)B * sizeof(int), st));
     if (spec != nullptr)   // this pass A stages no mask: a header left by an earlier learned-mask call must not survive
       AVZ_CUDA_OK(cudaMemsetAsync(spec_hdr(spec, B, T), 0, 16, st));
     AVZ_CUDA_OK(cudaFuncSetAttribute(k512_ibm<HOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
@@ -1250,7 +1291,20 @@ int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const f
   }
   const size_t smem_cov = smem_fft + (size_t)kWarps * 5 * kFP * sizeof(float);
   prof_begin(PROF_COV, st);
-  if (mask == nullptr) {
+  if (mask == nullptr && tail != nullptr) {
+    unsigned char* wsb = reinterpret_cast<unsigned char*>(part) + part_bytes(B, chunks);
+    CovTail ct;
+    ct.done = reinterpret_cast<int*>(wsb + 16 + (size_t)amb_cap(B, T) * 8);
+    ct.dvec = reinterpret_cast<const float2*>(tail->dvec);
+    ct.R = reinterpret_cast<float4*>(tail->R);
+    ct.msum = tail->msum;
+    ct.w = reinterpret_cast<float2*>(tail->w);
+    ct.cfg = *tail->cfg;
+    ct.norm_eps = tail->norm_eps;
+    AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov_w<HOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
+    k512_cov_w<HOP><<<grid, kWarps * 32, smem_cov, st>>>(mix, ibm_bits, (int)L, T, fpc, part, reinterpret_cast<float4*>(spec),
+                                                         ct, tb);
+  } else if (mask == nullptr) {
     AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov<HOP, W_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
     k512_cov<HOP, W_BITS><<<grid, kWarps * 32, smem_cov, st>>>(mix, ibm_bits, nullptr, MaskLayout{0, 0, 0, nullptr, 0u, 0u}, (int)L, T, fpc,
                                                                0.f, part, reinterpret_cast<float4*>(spec), tb);
@@ -1456,9 +1510,9 @@ int launch_ibm_exact(const float* tgt, const float* itf, int B, int64_t L, int h
 }
 
 template int launch_ibm_cov<128>(const float*, const float*, const float*, const float*, int, int64_t, float, uint32_t*,
-                                 float*, int*, void*, cudaStream_t);
+                                 float*, int*, void*, cudaStream_t, const CovTailArgs*);
 template int launch_ibm_cov<256>(const float*, const float*, const float*, const float*, int, int64_t, float, uint32_t*,
-                                 float*, int*, void*, cudaStream_t);
+                                 float*, int*, void*, cudaStream_t, const CovTailArgs*);
 template int launch_apply<128>(const float*, const void*, const float*, const uint32_t*, const float*, int, float, int,
                                int64_t, float*, float*, int, float, int, cudaStream_t);
 template int launch_apply<256>(const float*, const void*, const float*, const uint32_t*, const float*, int, float, int,

@@ -390,6 +390,8 @@ def sir_scores(est, tgt, itf):
     itf = io.take(itf, torch.float32)
     lead = est.shape[:-1]
     B = int(np.prod(lead)) if lead else 1
+    if tgt.shape != itf.shape or tgt.shape[:-1] != lead:
+        raise ValueError(f"references {tuple(tgt.shape)} / {tuple(itf.shape)} do not match the estimate {tuple(est.shape)}")
     sc = torch.empty((B, 4), dtype=torch.float32, device=est.device)
     _lib.check(_lib.load().avz_sir_f32(_ptr(est), _ptr(tgt), _ptr(itf), B, est.shape[-1], tgt.shape[-1], _ptr(sc),
                                        _stream()), "avz_sir_f32")
@@ -483,6 +485,8 @@ def ibm_covariance(mix: torch.Tensor, tgt: torch.Tensor, itf: torch.Tensor, cfg:
     mix [B,2,L], tgt [B,L], itf [B,L] -> (ibm_bits [B,T,ceil(F/32)] int32, R packed [B,F,4], msum [B,F])."""
     lib = _lib.load()
     B, _, L = mix.shape
+    if tuple(tgt.shape) != (B, L) or tuple(itf.shape) != (B, L) or mix.shape[1] != 2:
+        raise ValueError(f"mix {tuple(mix.shape)}, tgt {tuple(tgt.shape)}, itf {tuple(itf.shape)}: need (B,2,L), (B,L), (B,L)")
     F, T = cfg.n_freq, num_frames(L, cfg.n_fft, cfg.hop)
     dev = mix.device
     bits = torch.empty((B, T, (F + 31) // 32), dtype=torch.int32, device=dev)
@@ -557,9 +561,16 @@ def mvdr_apply(mix: torch.Tensor, w: torch.Tensor, cfg: MvdrConfig, ibm_bits: Op
     `mask_staged`: `mask` is the one `wave_masked_covariance(..., spec)` has just been given - at n_fft 512 pass B then
     reuses the transposed copy that call left in `spec` instead of re-laying the mask a second time."""
     B, _, L = mix.shape
+    T = num_frames(L, cfg.n_fft, cfg.hop)
+    F = cfg.n_freq
+    if tuple(w.shape) != (B, F, 2) or w.dtype != torch.complex64 or not w.is_contiguous():
+        raise ValueError(f"w must be a contiguous complex64 tensor of shape {(B, F, 2)}, got {tuple(w.shape)} {w.dtype}")
+    if ibm_bits is not None and (tuple(ibm_bits.shape) != (B, T, (F + 31) // 32) or ibm_bits.dtype != torch.int32):
+        raise ValueError(f"ibm_bits must be int32 of shape {(B, T, (F + 31) // 32)}, got {tuple(ibm_bits.shape)}")
+    if mask is not None and (tuple(mask.shape) != (B, F, T) or mask.dtype != torch.float32 or not mask.is_contiguous()):
+        raise ValueError(f"mask must be a contiguous float32 tensor of shape {(B, F, T)}, got {tuple(mask.shape)}")
     if mask_staged and spec is not None and cfg.n_fft == 512 and cfg.post in ("floor", "mask"):
         mask = None
-    T = num_frames(L, cfg.n_fft, cfg.hop)
     out = torch.empty((B, (T - 1) * cfg.hop), dtype=torch.float32, device=mix.device)
     peak = torch.zeros((B,), dtype=torch.float32, device=mix.device)
     cc = cfg.to_c()

@@ -25,7 +25,7 @@ class OracleMvdr:
     launches_per_step = 7
 
     def __init__(self, cfg: MvdrConfig, B: int, L: int, device, keep_spectrum: bool = True, fused_norm: bool = False,
-                 fused: bool = False):
+                 fused: bool = False, fold_weights: bool = False):
         """`fused`: run pass A, the weights, pass B and the normalisation as ONE persistent kernel whose kept spectrum
         stays in L2 (avz_oracle_fused_f32; n_fft 512, IBM post-filter or none) instead of five separate launches."""
         self.cfg, self.B, self.L, self.device = cfg, B, L, device
@@ -56,6 +56,13 @@ class OracleMvdr:
         self.d = steering_vectors(cfg, device)
         self.cc = cfg.to_c()
         self.fused = bool(fused)
+        # n_fft 512 fast path: finalize + weights folded into pass A's last block per utterance (two launches fewer,
+        # bit-identical).  Measured on B200 it does not pay: a single block per utterance is slower at the tail than the
+        # two small parallel kernels it replaces (config 2: 1.699 vs 1.696 ms per step; one 5 s utterance as a CUDA
+        # graph: 59.5 vs 53.3 us).  Off by default.
+        self.fold_weights = bool(fold_weights) and cfg.n_fft == 512 and cfg.hop in (128, 256) and not self.fused
+        if self.fold_weights:
+            self.launches_per_step -= 2
         if self.fused:
             nfw = self.lib.avz_oracle_fused_ws_bytes(B, L, cfg.n_fft, cfg.hop)
             if nfw <= 0 or cfg.post not in ("one_minus_noise", "none"):
@@ -68,6 +75,13 @@ class OracleMvdr:
     # individual stages (each one C-ABI call) ---------------------------------------------------
     def pass_a(self, mix, tgt, itf):
         c = self.cfg
+        if self.fold_weights:
+            # finalize + 2x2 solve ride on pass A's last block per utterance: R, msum and w come out of this one call
+            _lib.check(self.lib.avz_ibm_cov_weights_keep_f32(_ptr(mix), _ptr(tgt), _ptr(itf), self.B, self.L, c.n_fft, c.hop,
+                                                             C.byref(self.cc), _ptr(self.d), _ptr(self.bits), _ptr(self.R),
+                                                             _ptr(self.msum), _ptr(self.w), _ptr(self.ws), _ptr(self.spec),
+                                                             _stream()), "avz_ibm_cov_weights_keep_f32")
+            return
         if self.spec is not None:
             _lib.check(self.lib.avz_ibm_cov_keep_f32(_ptr(mix), _ptr(tgt), _ptr(itf), self.B, self.L, c.n_fft, c.hop,
                                                      float(c.norm_eps), _ptr(self.bits), _ptr(self.R), _ptr(self.msum),
@@ -78,6 +92,8 @@ class OracleMvdr:
                                             _ptr(self.ws), _stream()), "avz_ibm_cov_f32")
 
     def weights(self):
+        if self.fold_weights:
+            return                      # done by pass_a
         _lib.check(self.lib.avz_mvdr_weights_f32(_ptr(self.R), _ptr(self.d), self.B, self.F, C.byref(self.cc),
                                                  _ptr(self.w), _stream()), "avz_mvdr_weights_f32")
 
@@ -328,37 +344,40 @@ class HostPipeline:
         return self.wait(self.submit(mix_h, tgt_h, itf_h))
 
 
-def copy_ceiling(h2d_bytes: int, d2h_bytes: int, device, reps: int = 3) -> Dict[str, float]:
-    """Bare-copy ceiling of the host<->device link for the end-to-end leg: one pinned host->device cudaMemcpyAsync of
-    `h2d_bytes` and one device->host copy of `d2h_bytes` per step, both directions at once on two streams, nothing
-    else running (under torchrun every rank does this at the same time, which is what the leg has to share).
-    Returns GB/s per direction and the ms a step's copies take."""
+def copy_ceiling(h2d_bytes: int, d2h_bytes: int, device, reps: int = 6) -> Dict[str, float]:
+    """Bare-copy ceiling of the host<->device link for the end-to-end leg: per step one pinned host->device
+    cudaMemcpyAsync of `h2d_bytes` and one device->host copy of `d2h_bytes`, nothing else running; `reps` steps back to
+    back (sustained, like the leg itself - a single burst overstates what a shared host fabric holds when every rank
+    copies at once: under torchrun all ranks run this at the same time).  Returns GB/s per direction, each direction
+    alone and both at once, from the total time of the back-to-back steps."""
     h_in = torch.empty((h2d_bytes,), dtype=torch.uint8).pin_memory()
     h_out = torch.empty((d2h_bytes,), dtype=torch.uint8).pin_memory()
     d_in = torch.empty((h2d_bytes,), dtype=torch.uint8, device=device)
     d_out = torch.empty((d2h_bytes,), dtype=torch.uint8, device=device)
     s1, s2 = torch.cuda.Stream(device), torch.cuda.Stream(device)
-    res = {}
-    for name, both in (("alone", False), ("both_directions", True)):
-        best = None
-        for _ in range(reps + 1):
-            torch.cuda.synchronize(device)
-            a1, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            with torch.cuda.stream(s1):
-                a1.record()
+
+    def run(h2d: bool, d2h: bool):
+        torch.cuda.synchronize(device)
+        a1, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(s1):
+            a1.record()
+            for _ in range(reps if h2d else 0):
                 d_in.copy_(h_in, non_blocking=True)
-                b1.record()
-            if not both:
-                torch.cuda.synchronize(device)
-            with torch.cuda.stream(s2):
-                a2.record()
+            b1.record()
+        with torch.cuda.stream(s2):
+            a2.record()
+            for _ in range(reps if d2h else 0):
                 h_out.copy_(d_out, non_blocking=True)
-                b2.record()
-            torch.cuda.synchronize(device)
-            t = (a1.elapsed_time(b1), a2.elapsed_time(b2))
-            if best is None or max(t) < max(best):
-                best = t
-        res[name] = {"h2d_GBps": h2d_bytes / (best[0] * 1e-3) / 1e9, "d2h_GBps": d2h_bytes / (best[1] * 1e-3) / 1e9,
-                     "h2d_ms": best[0], "d2h_ms": best[1]}
-    return res
+            b2.record()
+        torch.cuda.synchronize(device)
+        return a1.elapsed_time(b1) / reps, a2.elapsed_time(b2) / reps
+
+    run(True, True)                                   # warm-up (first touch of the pinned pages)
+    h_alone, _ = run(True, False)
+    _, d_alone = run(False, True)
+    h_both, d_both = run(True, True)
+    return {"alone": {"h2d_GBps": h2d_bytes / (h_alone * 1e-3) / 1e9, "d2h_GBps": d2h_bytes / (d_alone * 1e-3) / 1e9,
+                      "h2d_ms": h_alone, "d2h_ms": d_alone},
+            "both_directions": {"h2d_GBps": h2d_bytes / (h_both * 1e-3) / 1e9, "d2h_GBps": d2h_bytes / (d_both * 1e-3) / 1e9,
+                                "h2d_ms": h_both, "d2h_ms": d_both}}

@@ -505,3 +505,19 @@ def test_fused_persistent_kernel_equals_separate_kernels(az, preset, B, dur):
     for i in (0, B - 1):
         ref = O.oracle_mask_mvdr(mix[i], tgt[i], itf[i], to_oracle_cfg(cfg))
         assert rel_l2(b[i].cpu().numpy(), ref) < 1e-4
+
+
+def test_pass_a_with_folded_weights_is_bit_identical(az):
+    """avz_ibm_cov_weights_keep_f32 (finalize + 2x2 solve done by the block that completes an utterance's last chunk)
+    against avz_ibm_cov_keep_f32 + avz_mvdr_weights_f32: same R, msum, w and waveform, bit for bit."""
+    from avzoom import pipeline
+    for preset, B, dur in (("baseline_oracle", 1, 5.0), ("baseline_oracle", 40, 1.1), ("oracle_debug", 3, 2.0)):
+        cfg = az.PRESETS[preset]
+        mix, tgt, itf = synth(6, min(B, 8), dur, 2)
+        rep = (B + mix.shape[0] - 1) // mix.shape[0]
+        mix_d, tgt_d, itf_d = (torch.from_numpy(np.tile(a, (rep,) + (1,) * (a.ndim - 1))[:B].copy()).cuda() for a in (mix, tgt, itf))
+        a = pipeline.OracleMvdr(cfg, B, mix.shape[-1], mix_d.device)
+        b = pipeline.OracleMvdr(cfg, B, mix.shape[-1], mix_d.device, fold_weights=True)
+        assert b.fold_weights and not a.fold_weights
+        xa, xb = a.run(mix_d, tgt_d, itf_d), b.run(mix_d, tgt_d, itf_d)
+        assert torch.equal(a.R, b.R) and torch.equal(a.msum, b.msum) and torch.equal(a.w, b.w) and torch.equal(xa, xb)
