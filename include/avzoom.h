@@ -178,6 +178,19 @@ AVZ_API int avz_wave_mask_cov_keep_f32(const float* mix, const float* mask, int 
 AVZ_API int avz_mvdr_apply_kept_f32(const void* spec, const float* w, const uint32_t* ibm_bits, const float* mask, int B,
                             int64_t L, int n_fft, int hop, const AvzMvdrCfg* cfg, float* out, float* peak, void* stream);
 
+/* Sparse kept spectrum for the oracle path (post-filter AVZ_POST_ONE_MINUS_NOISE, oracle_debug.py:84-90): pass B
+ * multiplies every TF bin whose noise bit is set by zero, so pass A keeps only the bins with a clear bit, compacted to
+ * the front of each frame's block in an order both passes derive from the same ibm_bits.  On speech-like mixtures two
+ * thirds of the bins are noise-dominated: two thirds of the kept-spectrum traffic - what bounds pass A and pass B -
+ * disappears; the waveform is bit-identical to the dense pair.  `spec` is sized by avz_spec_ws_bytes() as before.  A
+ * sparse spectrum read by avz_mvdr_apply_kept_f32 (or a dense one read here) is detected on the device (a header word
+ * in `spec`) and poisons the output with NaN instead of producing garbage. */
+AVZ_API int avz_ibm_cov_keep_sparse_f32(const float* mix, const float* tgt, const float* itf, int B, int64_t L, int n_fft,
+                                int hop, float norm_eps, uint32_t* ibm_bits, float* R, float* msum, void* ws, void* spec,
+                                void* stream);
+AVZ_API int avz_mvdr_apply_kept_sparse_f32(const void* spec, const float* w, const uint32_t* ibm_bits, int B, int64_t L,
+                                   int n_fft, int hop, const AvzMvdrCfg* cfg, float* out, float* peak, void* stream);
+
 /* Same as avz_mvdr_apply_kept_f32 plus the peak normalisation of oracle_debug.py:94 fused in: the thread blocks of an
  * utterance run as one cluster, agree on max|x| through distributed shared memory and divide their own output range
  * by (peak + peak_eps) while it is still in L2 (more than 8 blocks per utterance: a separate pass follows instead).
@@ -190,11 +203,12 @@ AVZ_API int avz_mvdr_apply_kept_norm_f32(const void* spec, const float* w, const
 /* ---- pass A with its per-utterance tail folded in (n_fft 512, hop 128 / 256): as avz_ibm_cov_keep_f32 (spec may be
  * NULL: no kept spectrum), and the block that finishes an utterance's last frame chunk also sums the chunk partials
  * (oracle_debug.py:60-64) and solves the 257 2x2 systems (oracle_debug.py:68-79) - R, msum and w come out of the one
- * launch, bit-identical to avz_ibm_cov_keep_f32 + avz_mvdr_weights_f32.  Two launches fewer per step: a single utterance
- * (BASELINE config 1) is a chain of dependent launches of a few microseconds each.  dvec [257,2] complex64. */
+ * launch, bit-identical to avz_ibm_cov_keep_f32 + avz_mvdr_weights_f32.  Two launches fewer per step (measured: no gain,
+ * profiles/README.md).  dvec [257,2] complex64; sparse != 0: the kept spectrum is sparse (see
+ * avz_ibm_cov_keep_sparse_f32). */
 AVZ_API int avz_ibm_cov_weights_keep_f32(const float* mix, const float* tgt, const float* itf, int B, int64_t L, int n_fft,
                                  int hop, const AvzMvdrCfg* cfg, const float* dvec, uint32_t* ibm_bits, float* R,
-                                 float* msum, float* w, void* ws, void* spec, void* stream);
+                                 float* msum, float* w, void* ws, void* spec, int sparse, void* stream);
 
 /* ---- the whole oracle path of oracle_debug.py:42-94 as ONE call (n_fft 512, hop 128 / 256): k512_ibm + k512_ibm_fixup,
  * then a single persistent kernel whose tasks are pass A (masked covariance, spectrum kept), the per-utterance

@@ -71,7 +71,9 @@ SIGNATURES = {
     "avz_wave_mask_cov_keep_f32": (_i, [_p, _p, _i, _l, _i, _i, _f, _f, _p, _p, _p, _p, _p]),
     "avz_mvdr_apply_kept_f32": (_i, [_p, _p, _p, _p, _i, _l, _i, _i, C.POINTER(AvzMvdrCfg), _p, _p, _p]),
     "avz_mvdr_apply_kept_norm_f32": (_i, [_p, _p, _p, _p, _i, _l, _i, _i, C.POINTER(AvzMvdrCfg), _f, _p, _p, _p]),
-    "avz_ibm_cov_weights_keep_f32": (_i, [_p, _p, _p, _i, _l, _i, _i, C.POINTER(AvzMvdrCfg), _p, _p, _p, _p, _p, _p, _p, _p]),
+    "avz_ibm_cov_weights_keep_f32": (_i, [_p, _p, _p, _i, _l, _i, _i, C.POINTER(AvzMvdrCfg), _p, _p, _p, _p, _p, _p, _p, _i, _p]),
+    "avz_ibm_cov_keep_sparse_f32": (_i, [_p, _p, _p, _i, _l, _i, _i, _f, _p, _p, _p, _p, _p, _p]),
+    "avz_mvdr_apply_kept_sparse_f32": (_i, [_p, _p, _p, _i, _l, _i, _i, C.POINTER(AvzMvdrCfg), _p, _p, _p]),
     "avz_oracle_fused_ws_bytes": (_l, [_i, _l, _i, _i]),
     "avz_oracle_fused_f32": (_i, [_p, _p, _p, _i, _l, _i, _i, C.POINTER(AvzMvdrCfg), _f, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "avz_stream_state_bytes": (_l, [_i]),

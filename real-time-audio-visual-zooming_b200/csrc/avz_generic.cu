@@ -27,7 +27,7 @@ int launch_ibm_exact(const float* tgt, const float* itf, int B, int64_t L, int h
 template <int HOP>
 int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const float* mask, int B, int64_t L,
                    float sqrt_eps, uint32_t* ibm_bits, float* part, int* chunks_out, void* spec, cudaStream_t st,
-                   const CovTailArgs* tail = nullptr);
+                   const CovTailArgs* tail = nullptr, int sparse = 0);
 int64_t fused_ws_bytes(int B, int64_t L, int hop);
 template <int HOP>
 int launch_oracle_fused(const float* mix, const float* tgt, const float* itf, int B, int64_t L, const AvzMvdrCfg* cfg,
@@ -36,7 +36,7 @@ int launch_oracle_fused(const float* mix, const float* tgt, const float* itf, in
 template <int HOP>
 int launch_apply(const float* mix, const void* spec, const float* w, const uint32_t* ibm_bits, const float* mask,
                  int gain_mode, float post_floor, int B, int64_t L, float* out, float* peak, int fuse_norm,
-                 float peak_eps, int mask_staged, cudaStream_t st);
+                 float peak_eps, int mask_staged, cudaStream_t st, int sparse = 0);
 }  // namespace o512
 
 // n_fft = 1024 / hop 512 fast path (avz_opt1024.cu)
@@ -586,11 +586,12 @@ static int launch_cov(const float* mix, const float* tgt, const float* itf, cons
 // fast path: IBM + covariance (or mask covariance) for n_fft 512, then the shared finalize kernel
 static int launch_cov512(const float* mix, const float* tgt, const float* itf, const float* mask, int B, int64_t L,
                          int hop, float sqrt_eps, float norm_eps, uint32_t* ibm_bits, float* R, float* msum, void* ws,
-                         void* spec, cudaStream_t st) {
+                         void* spec, cudaStream_t st, int sparse = 0) {
   int chunks = 0;
-  int rc = (hop == 128)
-               ? o512::launch_ibm_cov<128>(mix, tgt, itf, mask, B, L, sqrt_eps, ibm_bits, (float*)ws, &chunks, spec, st)
-               : o512::launch_ibm_cov<256>(mix, tgt, itf, mask, B, L, sqrt_eps, ibm_bits, (float*)ws, &chunks, spec, st);
+  int rc = (hop == 128) ? o512::launch_ibm_cov<128>(mix, tgt, itf, mask, B, L, sqrt_eps, ibm_bits, (float*)ws, &chunks, spec,
+                                                    st, nullptr, sparse)
+                        : o512::launch_ibm_cov<256>(mix, tgt, itf, mask, B, L, sqrt_eps, ibm_bits, (float*)ws, &chunks, spec,
+                                                    st, nullptr, sparse);
   if (rc) return rc;
   const int F = 257;
   prof_begin(PROF_FINALIZE, st);
@@ -758,6 +759,17 @@ int avz_ibm_cov_keep_f32(const float* mix, const float* tgt, const float* itf, i
                        (cudaStream_t)stream);
 }
 
+int avz_ibm_cov_keep_sparse_f32(const float* mix, const float* tgt, const float* itf, int B, int64_t L, int n_fft, int hop,
+                                float norm_eps, uint32_t* ibm_bits, float* R, float* msum, void* ws, void* spec, void* stream) {
+  if (!mix || !tgt || !itf || !ibm_bits || !R || !msum || !ws || !spec || B <= 0 || B > 65535)
+    return set_error(AVZ_EINVAL, "avz_ibm_cov_keep_sparse_f32: null pointer or empty batch");
+  int rc = check_fft_args(n_fft, hop, L);
+  if (rc) return rc;
+  if (!use_opt512(n_fft, hop)) return set_error(AVZ_EINVAL, "avz_ibm_cov_keep_sparse_f32: n_fft 512, hop 128/256 only");
+  return launch_cov512(mix, tgt, itf, nullptr, B, L, hop, 0.f, norm_eps, ibm_bits, R, msum, ws, spec,
+                       (cudaStream_t)stream, 1);
+}
+
 int avz_wave_mask_cov_keep_f32(const float* mix, const float* mask, int B, int64_t L, int n_fft, int hop, float sqrt_eps,
                                float norm_eps, float* R, float* msum, void* ws, void* spec, void* stream) {
   if (!mix || !mask || !R || !msum || !ws || !spec || B <= 0 || B > 65535)
@@ -791,7 +803,7 @@ static int gain_mode_of(const AvzMvdrCfg* cfg, const uint32_t* ibm_bits, const f
 
 static int apply_kept(const void* spec, const float* w, const uint32_t* ibm_bits, const float* mask, int B, int64_t L,
                       int n_fft, int hop, const AvzMvdrCfg* cfg, float* out, float* peak, int fuse_norm, float peak_eps,
-                      void* stream) {
+                      void* stream, int sparse = 0) {
   if (!spec || !w || !cfg || !out || B <= 0 || B > 65535)
     return set_error(AVZ_EINVAL, "avz_mvdr_apply_kept_f32: null pointer or empty batch");
   int rc = check_fft_args(n_fft, hop, L);
@@ -815,10 +827,17 @@ static int apply_kept(const void* spec, const float* w, const uint32_t* ibm_bits
       return set_error(AVZ_EINVAL, "avz_mvdr_apply_kept_f32: n_fft 1024 takes float masks only, no fused normalisation");
     return o1024::launch_apply(nullptr, spec, w, mask, gain, cfg->post_floor, B, L, out, peak, (cudaStream_t)stream);
   }
+  if (sparse && (fast1024 || gain != GAIN_BITS))
+    return set_error(AVZ_EINVAL, "a sparse kept spectrum goes with AVZ_POST_ONE_MINUS_NOISE and its ibm_bits (n_fft 512)");
   return (hop == 128) ? o512::launch_apply<128>(nullptr, spec, w, ibm_bits, mask, gain, cfg->post_floor, B, L, out, peak,
-                                                fuse_norm, peak_eps, staged, (cudaStream_t)stream)
+                                                fuse_norm, peak_eps, staged, (cudaStream_t)stream, sparse)
                       : o512::launch_apply<256>(nullptr, spec, w, ibm_bits, mask, gain, cfg->post_floor, B, L, out, peak,
-                                                fuse_norm, peak_eps, staged, (cudaStream_t)stream);
+                                                fuse_norm, peak_eps, staged, (cudaStream_t)stream, sparse);
+}
+
+int avz_mvdr_apply_kept_sparse_f32(const void* spec, const float* w, const uint32_t* ibm_bits, int B, int64_t L, int n_fft,
+                                   int hop, const AvzMvdrCfg* cfg, float* out, float* peak, void* stream) {
+  return apply_kept(spec, w, ibm_bits, nullptr, B, L, n_fft, hop, cfg, out, peak, 0, 0.f, stream, 1);
 }
 
 int avz_mvdr_apply_kept_f32(const void* spec, const float* w, const uint32_t* ibm_bits, const float* mask, int B,
@@ -836,7 +855,7 @@ int avz_mvdr_apply_kept_norm_f32(const void* spec, const float* w, const uint32_
 // ---- pass A with finalize + weights folded into its last block per utterance (n_fft 512 fast path)
 int avz_ibm_cov_weights_keep_f32(const float* mix, const float* tgt, const float* itf, int B, int64_t L, int n_fft, int hop,
                                  const AvzMvdrCfg* cfg, const float* dvec, uint32_t* ibm_bits, float* R, float* msum,
-                                 float* w, void* ws, void* spec, void* stream) {
+                                 float* w, void* ws, void* spec, int sparse, void* stream) {
   if (!mix || !tgt || !itf || !cfg || !dvec || !ibm_bits || !R || !msum || !w || !ws || B <= 0 || B > 65535)
     return set_error(AVZ_EINVAL, "avz_ibm_cov_weights_keep_f32: null pointer or bad batch size");
   int rc = check_fft_args(n_fft, hop, L);
@@ -846,9 +865,9 @@ int avz_ibm_cov_weights_keep_f32(const float* mix, const float* tgt, const float
   CovTailArgs tail{dvec, R, msum, w, cfg, cfg->norm_eps};
   int chunks = 0;
   return (hop == 128) ? o512::launch_ibm_cov<128>(mix, tgt, itf, nullptr, B, L, 0.f, ibm_bits, (float*)ws, &chunks, spec,
-                                                  (cudaStream_t)stream, &tail)
+                                                  (cudaStream_t)stream, &tail, sparse ? 1 : 0)
                       : o512::launch_ibm_cov<256>(mix, tgt, itf, nullptr, B, L, 0.f, ibm_bits, (float*)ws, &chunks, spec,
-                                                  (cudaStream_t)stream, &tail);
+                                                  (cudaStream_t)stream, &tail, sparse ? 1 : 0);
 }
 
 // ---- the whole oracle path in two small launches + one persistent kernel (n_fft 512, hop 128 / 256)

@@ -431,7 +431,7 @@ __device__ __forceinline__ void cov_body(unsigned char* smem_raw, int b, int chu
                                          const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits,
                                          const float* __restrict__ mask, MaskLayout ml, int L, int T, int frames_per_cta,
                                          float sqrt_eps, float* __restrict__ part, float4* __restrict__ spec,
-                                         int64_t spec_utt, const Tables& tb) {
+                                         int64_t spec_utt, int sparse, const Tables& tb) {
   float2* sm_all = reinterpret_cast<float2*>(smem_raw);
   float2* sm = sm_all + (size_t)(threadIdx.x >> 5) * f512::kSmemComplex;
   Lane ln;
@@ -506,7 +506,13 @@ __device__ __forceinline__ void cov_body(unsigned char* smem_raw, int b, int chu
       float2 mir[8];
       f512::mirror_of_low(v, mir, ln);
       if (spec != nullptr) {
-        float4* sp = spec + (spec_utt * T + t) * 256 + lane;
+        // `sparse` (oracle path, post-filter 1 - noise mask): pass B multiplies every bin whose noise bit is set by zero,
+        // so only the bins with a clear bit are kept - compacted to the front of the frame's 4096-byte block in
+        // (slot j, lane) order, which both passes derive from the same IBM bits.  About two thirds of the kept-spectrum
+        // traffic, which is what bounds this kernel and pass B, disappears.
+        float4* sp = spec + (spec_utt * T + t) * 256;
+        const unsigned lt = (1u << lane) - 1u;
+        int base = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 q = make_float4(v[j].x, v[j].y, mir[j].x, mir[j].y);
@@ -514,8 +520,18 @@ __device__ __forceinline__ void cov_body(unsigned char* smem_raw, int b, int chu
             q.z = v[8].x;
             q.w = v[8].y;
           }
-          if (L2KEEP) sp[32 * j] = q;
-          else __stcs(sp + 32 * j, q);     // streaming store: read once by pass B, no reuse before that
+          bool keep = true;
+          unsigned bal = kFull;
+          if (sparse) {
+            keep = (mw[j] == 0.f) || (j == 0 && lane == 0 && mny == 0.f);
+            bal = __ballot_sync(kFull, keep);
+          }
+          float4* dst = sp + base + __popc(bal & lt);
+          base += __popc(bal);
+          if (keep) {
+            if (L2KEEP) *dst = q;
+            else __stcs(dst, q);     // streaming store: read once by pass B, no reuse before that
+          }
         }
       }
 #pragma unroll
@@ -622,6 +638,8 @@ struct CovTail {
   float2* w;
   AvzMvdrCfg cfg;
   float norm_eps;
+  uint32_t* shdr;          // header of the kept-spectrum buffer: word 3 records whether the spectrum is sparse
+  int sparse;
 };
 template <int HOP>
 __global__ void __launch_bounds__(kWarps * 32, AVZ_MINB_COV)
@@ -629,8 +647,10 @@ k512_cov_w(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits,
            float* __restrict__ part, float4* __restrict__ spec, CovTail tail, Tables tb) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ int s_last;
+  if (tail.shdr != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) tail.shdr[3] = (uint32_t)tail.sparse;
   cov_body<HOP, W_BITS, false>(smem_raw, blockIdx.y, blockIdx.x, gridDim.x, mix, ibm_bits, nullptr,
-                               MaskLayout{0, 0, 0, nullptr, 0u, 0u}, L, T, frames_per_cta, 0.f, part, spec, blockIdx.y, tb);
+                               MaskLayout{0, 0, 0, nullptr, 0u, 0u}, L, T, frames_per_cta, 0.f, part, spec, blockIdx.y,
+                               tail.sparse, tb);
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicAdd(tail.done + blockIdx.y, 1) == (int)gridDim.x - 1);
@@ -644,10 +664,11 @@ template <int HOP, int WMODE>
 __global__ void __launch_bounds__(kWarps * 32, AVZ_MINB_COV)
 k512_cov(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, const float* __restrict__ mask,
          MaskLayout ml, int L, int T, int frames_per_cta, float sqrt_eps, float* __restrict__ part,
-         float4* __restrict__ spec, Tables tb) {
+         float4* __restrict__ spec, uint32_t* __restrict__ shdr, int sparse, Tables tb) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  if (WMODE == W_BITS && shdr != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) shdr[3] = (uint32_t)sparse;
   cov_body<HOP, WMODE, false>(smem_raw, blockIdx.y, blockIdx.x, gridDim.x, mix, ibm_bits, mask, ml, L, T, frames_per_cta,
-                              sqrt_eps, part, spec, blockIdx.y, tb);
+                              sqrt_eps, part, spec, blockIdx.y, WMODE == W_BITS ? sparse : 0, tb);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -683,7 +704,8 @@ __device__ __forceinline__ void apply_body(unsigned char* smem_raw, int b, int b
                                            const float2* __restrict__ wgt, const uint32_t* __restrict__ ibm_bits,
                                            const float* __restrict__ mask, MaskLayout ml, int gain_mode, float post_floor,
                                            int L, int T, int blocks_per_cta, float* __restrict__ out,
-                                           float* __restrict__ peak, int cluster_norm, float peak_eps, const Tables& tb) {
+                                           float* __restrict__ peak, int cluster_norm, float peak_eps,
+                                           const uint32_t* __restrict__ shdr, int sparse, const Tables& tb) {
   constexpr int R = kN / HOP;        // frames overlapping one hop-block
   constexpr int NR = HOP / 32;       // rows per hop-block
   constexpr int TAIL = 16 - NR;      // rows still open after a frame's first block is emitted
@@ -712,7 +734,9 @@ __device__ __forceinline__ void apply_body(unsigned char* smem_raw, int b, int b
   // factor (irfft's 1/N times sum(w) = N/2, i.e. 1/2) are folded into a and b: overall 1/N.
   {
     // a staged mask copy that is not there (header mismatch) poisons the weights: the output is NaN, not garbage
-    const bool staged_ok = ml.hdr == nullptr || (ml.hdr[0] == kMaskMagic && ml.hdr[1] == ml.B && ml.hdr[2] == ml.T);
+    // ... and so does a kept spectrum whose layout (dense / sparse) is not the one this call was told to read
+    const bool staged_ok = (ml.hdr == nullptr || (ml.hdr[0] == kMaskMagic && ml.hdr[1] == ml.B && ml.hdr[2] == ml.T)) &&
+                           (!KEPT || shdr == nullptr || shdr[3] == (uint32_t)sparse);
     const float sc = staged_ok ? 0.5f / (float)kN : __int_as_float(0x7fc00000);
     for (int k = threadIdx.x; k < kF; k += kWarps * 32) {
       const float2 w0 = wgt[((int64_t)b * kF + k) * 2 + 0];
@@ -806,15 +830,33 @@ __device__ __forceinline__ void apply_body(unsigned char* smem_raw, int b, int b
     // (t - t_first) % kStages and is the ((t - t_first) / kStages)-th use of that stage's barrier.
     const int t_last = min(gb - 1, T - 1);
     const float4* sp = KEPT ? spec + (spec_utt * T + t_first) * 256 : nullptr;
+    // sparse kept spectrum: a frame's block holds only the slots whose noise bit is clear, n_t of them, compacted; n_t
+    // comes from the frame's 9 IBM words (lanes 0..8 hold one word each), fetched one frame before its copy is issued
+    const uint32_t* bits_b = ibm_bits + (int64_t)b * T * kFW;
+    auto load_word = [&](int f) -> uint32_t { return (sparse && lane < kFW && f <= t_last) ? __ldg(bits_b + (int64_t)f * kFW + lane) : 0u; };
+    auto count_of = [&](uint32_t wd) -> int {
+      if (!sparse) return 256;
+      int c = (lane < 8) ? __popc(wd) : 0;
+      c = __reduce_add_sync(kFull, c);
+      const uint32_t b0 = __shfl_sync(kFull, wd, 0) & 1u, b256 = __shfl_sync(kFull, wd, 8) & 1u;
+      return 256 - c + (int)(b0 & (b256 ^ 1u));   // slot (0, lane 0) carries DC and Nyquist: kept if either is
+    };
+    int n_stage[kStages];
+    uint32_t wq = 0u;
     if (KEPT) {
-      if (lane == 0) {
 #pragma unroll
-        for (int st = 0; st < kStages; ++st)
-          if (t_first + st <= t_last) {
-            mbar_arrive_expect_tx(s_bar + st, 4096);
-            tma_load_1d(s_ring + st * 256, sp + (size_t)st * 256, 4096, s_bar + st);
+      for (int st = 0; st < kStages; ++st) {
+        n_stage[st] = 0;
+        if (t_first + st <= t_last) {
+          const int n = count_of(load_word(t_first + st));
+          n_stage[st] = n;
+          if (lane == 0 && n > 0) {
+            mbar_arrive_expect_tx(s_bar + st, 16u * n);
+            tma_load_1d(s_ring + st * 256, sp + (size_t)st * 256, 16u * n, s_bar + st);
           }
+        }
       }
+      wq = load_word(t_first + kStages);
     } else if (t_first <= T - 1) {
       win.load_all(m0, m1, L, t_first, lane);
     }
@@ -863,22 +905,43 @@ __device__ __forceinline__ void apply_body(unsigned char* smem_raw, int b, int b
         float2 zlo[8], mir[8], zny;
         if (KEPT) {
           const int use = g - t_first, st = use % kStages;
-          mbar_wait(s_bar + st, (phase_bits >> st) & 1u);
-          phase_bits ^= 1u << st;
-          const float4* fr = s_ring + st * 256 + lane;
+          int n_here = 0;
+#pragma unroll
+          for (int q = 0; q < kStages; ++q) n_here = (q == st) ? n_stage[q] : n_here;
+          if (n_here > 0) {
+            mbar_wait(s_bar + st, (phase_bits >> st) & 1u);
+            phase_bits ^= 1u << st;
+          }
+          const float4* fr = s_ring + st * 256;
+          const unsigned lt = (1u << lane) - 1u;
+          int base = 0;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 q = fr[32 * j];
+            bool keep = true;
+            unsigned bal = kFull;
+            if (sparse) {
+              keep = (gj[j] != 0.f) || (j == 0 && lane == 0 && gny != 0.f);
+              bal = __ballot_sync(kFull, keep);
+            }
+            const int pos = base + __popc(bal & lt);
+            base += __popc(bal);
+            const float4 q = keep ? fr[pos] : make_float4(0.f, 0.f, 0.f, 0.f);
             zlo[j] = make_float2(q.x, q.y);
             mir[j] = make_float2(q.z, q.w);
           }
           zny = mir[0];                       // lane 0: slot (0).zw is the Nyquist bin ...
           if (lane == 0) mir[0] = zlo[0];     // ... and DC is its own mirror
           __syncwarp();                       // every lane has read the stage: refill it with frame g + kStages
-          if (lane == 0 && g + kStages <= t_last) {
-            fence_proxy_async();
-            mbar_arrive_expect_tx(s_bar + st, 4096);
-            tma_load_1d(s_ring + st * 256, sp + (size_t)(use + kStages) * 256, 4096, s_bar + st);
+          if (g + kStages <= t_last) {
+            const int n = count_of(wq);
+#pragma unroll
+            for (int q = 0; q < kStages; ++q) n_stage[q] = (q == st) ? n : n_stage[q];
+            if (lane == 0 && n > 0) {
+              fence_proxy_async();
+              mbar_arrive_expect_tx(s_bar + st, 16u * n);
+              tma_load_1d(s_ring + st * 256, sp + (size_t)(use + kStages) * 256, 16u * n, s_bar + st);
+            }
+            wq = load_word(g + kStages + 1);
           }
           if (g + 1 <= T - 1) {
             bw += kFW;
@@ -1019,11 +1082,12 @@ __global__ void __launch_bounds__(kWarps * 32, KEPT ? AVZ_MINB_APPLY_KEPT : AVZ_
 k512_apply(const float* __restrict__ mix, const float4* __restrict__ spec, const float2* __restrict__ wgt,
            const uint32_t* __restrict__ ibm_bits, const float* __restrict__ mask, MaskLayout ml, int gain_mode,
            float post_floor, int L, int T, int blocks_per_cta, float* __restrict__ out, float* __restrict__ peak,
-           int cluster_norm, float peak_eps, Tables tb) {
+           int cluster_norm, float peak_eps, const uint32_t* __restrict__ shdr, int sparse, Tables tb) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint32_t phase_bits = 0u;
   apply_body<HOP, KEPT>(smem_raw, blockIdx.y, blockIdx.x, true, phase_bits, blockIdx.y, mix, spec, wgt, ibm_bits, mask, ml,
-                        gain_mode, post_floor, L, T, blocks_per_cta, out, peak, cluster_norm, peak_eps, tb);
+                        gain_mode, post_floor, L, T, blocks_per_cta, out, peak, cluster_norm, peak_eps, shdr,
+                        (KEPT && gain_mode == GAIN_BITS) ? sparse : 0, tb);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1057,7 +1121,7 @@ struct FusedArgs {
   int* ctrl;         // [0] queue head, then a_done[B], w_ready[B], b_done[B]
   AvzMvdrCfg cfg;
   float norm_eps, peak_eps;   // peak_eps < 0: no normalisation
-  int B, L, T, fpt, CA, CB, lag, nslot;
+  int B, L, T, fpt, CA, CB, lag, nslot, sparse;
   Tables tb;
 };
 
@@ -1119,7 +1183,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) k512_fused(FusedArgs a) {
     if (is_a) {
       if (u >= a.nslot) spin_until(b_done + (u - a.nslot), a.CB, 0, u);   // the ring slot's previous utterance has been consumed
       cov_body<HOP, W_BITS, true>(smem_raw, u, c, a.CA, a.mix, a.ibm_bits, nullptr, MaskLayout{0, 0, 0, nullptr, 0u, 0u}, a.L,
-                                  a.T, a.fpt, 0.f, a.part, a.spec, ring, a.tb);
+                                  a.T, a.fpt, 0.f, a.part, a.spec, ring, a.sparse, a.tb);
       __threadfence();
       __syncthreads();
       if (threadIdx.x == 0) s_last = (atomicAdd(a_done + u, 1) == a.CA - 1);
@@ -1138,7 +1202,8 @@ __global__ void __launch_bounds__(kWarps * 32, 2) k512_fused(FusedArgs a) {
       fence_proxy_async_all();   // the spectrum was written by other CTAs' ordinary stores; it is read by TMA bulk copies here
       apply_body<HOP, true>(smem_raw, u, c, !ring_used, phase_bits, ring, nullptr, a.spec, a.w, a.ibm_bits, nullptr,
                             MaskLayout{0, 0, 0, nullptr, 0u, 0u}, a.cfg.post_mode == AVZ_POST_ONE_MINUS_NOISE ? GAIN_BITS : GAIN_NONE,
-                            0.f, a.L, a.T, a.fpt, a.out, a.peak, 0, 0.f, a.tb);
+                            0.f, a.L, a.T, a.fpt, a.out, a.peak, 0, 0.f, nullptr,
+                            a.cfg.post_mode == AVZ_POST_ONE_MINUS_NOISE ? a.sparse : 0, a.tb);
       ring_used = true;
       __threadfence();
       __syncthreads();
@@ -1258,7 +1323,7 @@ static float ibm_tol2() {
 template <int HOP>
 int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const float* mask, int B, int64_t L,
                    float sqrt_eps, uint32_t* ibm_bits, float* part, int* chunks_out, void* spec, cudaStream_t st,
-                   const CovTailArgs* tail) {
+                   const CovTailArgs* tail, int sparse) {
   Tables tb;
   int rc = tables_for(kN, &tb);
   if (rc) return rc;
@@ -1301,20 +1366,23 @@ int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const f
     ct.w = reinterpret_cast<float2*>(tail->w);
     ct.cfg = *tail->cfg;
     ct.norm_eps = tail->norm_eps;
+    ct.shdr = spec ? spec_hdr(spec, B, T) : nullptr;
+    ct.sparse = spec ? sparse : 0;
     AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov_w<HOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
     k512_cov_w<HOP><<<grid, kWarps * 32, smem_cov, st>>>(mix, ibm_bits, (int)L, T, fpc, part, reinterpret_cast<float4*>(spec),
                                                          ct, tb);
   } else if (mask == nullptr) {
     AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov<HOP, W_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
     k512_cov<HOP, W_BITS><<<grid, kWarps * 32, smem_cov, st>>>(mix, ibm_bits, nullptr, MaskLayout{0, 0, 0, nullptr, 0u, 0u}, (int)L, T, fpc,
-                                                               0.f, part, reinterpret_cast<float4*>(spec), tb);
+                                                               0.f, part, reinterpret_cast<float4*>(spec),
+                                                               spec ? spec_hdr(spec, B, T) : nullptr, spec ? sparse : 0, tb);
   } else {
     AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov<HOP, W_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
     MaskLayout ml;
     const float* mptr = stage_mask(mask, spec, B, T, &ml, st);
     AVZ_LAUNCH_OK("k_mask_transpose");
     k512_cov<HOP, W_MASK><<<grid, kWarps * 32, smem_cov, st>>>(mix, nullptr, mptr, ml, (int)L, T, fpc, sqrt_eps, part,
-                                                               reinterpret_cast<float4*>(spec), tb);
+                                                               reinterpret_cast<float4*>(spec), nullptr, 0, tb);
   }
   prof_end(PROF_COV, st);
   AVZ_LAUNCH_OK("k512_cov");
@@ -1324,7 +1392,7 @@ int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const f
 template <int HOP>
 int launch_apply(const float* mix, const void* spec, const float* w, const uint32_t* ibm_bits, const float* mask,
                  int gain_mode, float post_floor, int B, int64_t L, float* out, float* peak, int fuse_norm,
-                 float peak_eps, int mask_staged, cudaStream_t st) {
+                 float peak_eps, int mask_staged, cudaStream_t st, int sparse) {
   Tables tb;
   int rc = tables_for(kN, &tb);
   if (rc) return rc;
@@ -1365,7 +1433,7 @@ int launch_apply(const float* mix, const void* spec, const float* w, const uint3
     lc.numAttrs = 1;
     AVZ_CUDA_OK(cudaLaunchKernelEx(&lc, k512_apply<HOP, true>, (const float*)nullptr, reinterpret_cast<const float4*>(spec),
                                    reinterpret_cast<const float2*>(w), ibm_bits, mptr, ml, gain_mode, post_floor, (int)L, T,
-                                   bpc, out, peak, cluster_norm, peak_eps, tb));
+                                   bpc, out, peak, cluster_norm, peak_eps, (const uint32_t*)spec_hdr(spec, B, T), sparse, tb));
     if (fuse_norm && !cluster_norm) {   // too many chunks per utterance for a cluster: separate pass
       prof_end(PROF_APPLY, st);
       AVZ_LAUNCH_OK("k512_apply");
@@ -1375,7 +1443,7 @@ int launch_apply(const float* mix, const void* spec, const float* w, const uint3
     AVZ_CUDA_OK(cudaFuncSetAttribute(k512_apply<HOP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k512_apply<HOP, false><<<grid, kWarps * 32, smem, st>>>(mix, nullptr, reinterpret_cast<const float2*>(w), ibm_bits,
                                                             mptr, ml, gain_mode, post_floor, (int)L, T, bpc, out, peak,
-                                                            0, 0.f, tb);
+                                                            0, 0.f, (const uint32_t*)nullptr, 0, tb);
   }
   prof_end(PROF_APPLY, st);
   AVZ_LAUNCH_OK("k512_apply");
@@ -1471,6 +1539,7 @@ int launch_oracle_fused(const float* mix, const float* tgt, const float* itf, in
   fa.CB = g.CB;
   fa.lag = g.lag;
   fa.nslot = g.nslot;
+  fa.sparse = (cfg->post_mode == AVZ_POST_ONE_MINUS_NOISE) ? 1 : 0;
   fa.tb = tb;
   const size_t smem = fused_smem_bytes<HOP>();
   AVZ_CUDA_OK(cudaFuncSetAttribute(k512_fused<HOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1510,13 +1579,13 @@ int launch_ibm_exact(const float* tgt, const float* itf, int B, int64_t L, int h
 }
 
 template int launch_ibm_cov<128>(const float*, const float*, const float*, const float*, int, int64_t, float, uint32_t*,
-                                 float*, int*, void*, cudaStream_t, const CovTailArgs*);
+                                 float*, int*, void*, cudaStream_t, const CovTailArgs*, int);
 template int launch_ibm_cov<256>(const float*, const float*, const float*, const float*, int, int64_t, float, uint32_t*,
-                                 float*, int*, void*, cudaStream_t, const CovTailArgs*);
+                                 float*, int*, void*, cudaStream_t, const CovTailArgs*, int);
 template int launch_apply<128>(const float*, const void*, const float*, const uint32_t*, const float*, int, float, int,
-                               int64_t, float*, float*, int, float, int, cudaStream_t);
+                               int64_t, float*, float*, int, float, int, cudaStream_t, int);
 template int launch_apply<256>(const float*, const void*, const float*, const uint32_t*, const float*, int, float, int,
-                               int64_t, float*, float*, int, float, int, cudaStream_t);
+                               int64_t, float*, float*, int, float, int, cudaStream_t, int);
 
 }  // namespace o512
 }  // namespace avz

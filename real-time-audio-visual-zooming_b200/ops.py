@@ -479,7 +479,7 @@ def alloc_kept_spectrum(mix: torch.Tensor, cfg: MvdrConfig, ibm: bool = False) -
 
 
 def ibm_covariance(mix: torch.Tensor, tgt: torch.Tensor, itf: torch.Tensor, cfg: MvdrConfig,
-                   spec: Optional[torch.Tensor] = None):
+                   spec: Optional[torch.Tensor] = None, sparse: bool = False):
     """Pass A (oracle_debug.py:42-64) without storing any spectrum - or, with `spec` (alloc_kept_spectrum), keeping
     the packed mix spectrum so that pass B can skip its forward transform.
     mix [B,2,L], tgt [B,L], itf [B,L] -> (ibm_bits [B,T,ceil(F/32)] int32, R packed [B,F,4], msum [B,F])."""
@@ -496,7 +496,12 @@ def ibm_covariance(mix: torch.Tensor, tgt: torch.Tensor, itf: torch.Tensor, cfg:
     if nws < 0:
         _lib.check(-1, "avz_ibm_cov_ws_bytes")
     ws = torch.empty((max(int(nws), 4),), dtype=torch.uint8, device=dev)
-    if spec is not None:
+    if spec is not None and sparse:
+        # only the bins the post-filter 1 - noise mask lets through are kept (read back with mvdr_apply(..., sparse=True))
+        _lib.check(lib.avz_ibm_cov_keep_sparse_f32(_ptr(mix), _ptr(tgt), _ptr(itf), B, L, cfg.n_fft, cfg.hop,
+                                                   float(cfg.norm_eps), _ptr(bits), _ptr(Rp), _ptr(ms), _ptr(ws), _ptr(spec),
+                                                   _stream()), "avz_ibm_cov_keep_sparse_f32")
+    elif spec is not None:
         _lib.check(lib.avz_ibm_cov_keep_f32(_ptr(mix), _ptr(tgt), _ptr(itf), B, L, cfg.n_fft, cfg.hop,
                                             float(cfg.norm_eps), _ptr(bits), _ptr(Rp), _ptr(ms), _ptr(ws), _ptr(spec),
                                             _stream()), "avz_ibm_cov_keep_f32")
@@ -555,7 +560,7 @@ def wave_masked_covariance(mix: torch.Tensor, mask: torch.Tensor, cfg: MvdrConfi
 
 def mvdr_apply(mix: torch.Tensor, w: torch.Tensor, cfg: MvdrConfig, ibm_bits: Optional[torch.Tensor] = None,
                mask: Optional[torch.Tensor] = None, spec: Optional[torch.Tensor] = None,
-               mask_staged: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+               mask_staged: bool = False, sparse: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
     """Pass B (oracle_debug.py:80-93): STFT(mix) (or the spectrum pass A kept in `spec`) -> w^H y -> post-filter ->
     iSTFT/OLA.  -> (out [B,(T-1)*hop] un-normalised, peak [B]).
     `mask_staged`: `mask` is the one `wave_masked_covariance(..., spec)` has just been given - at n_fft 512 pass B then
@@ -574,7 +579,11 @@ def mvdr_apply(mix: torch.Tensor, w: torch.Tensor, cfg: MvdrConfig, ibm_bits: Op
     out = torch.empty((B, (T - 1) * cfg.hop), dtype=torch.float32, device=mix.device)
     peak = torch.zeros((B,), dtype=torch.float32, device=mix.device)
     cc = cfg.to_c()
-    if spec is not None:
+    if spec is not None and sparse:
+        _lib.check(_lib.load().avz_mvdr_apply_kept_sparse_f32(_ptr(spec), _ptr(w), _ptr(ibm_bits), B, L, cfg.n_fft, cfg.hop,
+                                                              C.byref(cc), _ptr(out), _ptr(peak), _stream()),
+                   "avz_mvdr_apply_kept_sparse_f32")
+    elif spec is not None:
         _lib.check(_lib.load().avz_mvdr_apply_kept_f32(_ptr(spec), _ptr(w), _ptr(ibm_bits), _ptr(mask), B, L, cfg.n_fft,
                                                        cfg.hop, C.byref(cc), _ptr(out), _ptr(peak), _stream()),
                    "avz_mvdr_apply_kept_f32")
@@ -602,9 +611,10 @@ def oracle_mask_mvdr(mix, tgt, itf, cfg: MvdrConfig = PRESETS["baseline_oracle"]
     io = _Io()
     mix, tgt, itf, single = _batchify(mix, tgt, itf, io)
     spec = alloc_kept_spectrum(mix, cfg, ibm=True)
-    bits, Rp, ms = ibm_covariance(mix, tgt, itf, cfg, spec)
+    sparse = False      # the sparse kept spectrum saves 60 % of the traffic but costs more than it saves (pipeline.OracleMvdr)
+    bits, Rp, ms = ibm_covariance(mix, tgt, itf, cfg, spec, sparse=sparse)
     w = mvdr_weights(Rp, steering_vectors(cfg, mix.device), cfg)
-    out, peak = mvdr_apply(mix, w, cfg, ibm_bits=bits if cfg.post == "one_minus_noise" else None, spec=spec)
+    out, peak = mvdr_apply(mix, w, cfg, ibm_bits=bits if cfg.post == "one_minus_noise" else None, spec=spec, sparse=sparse)
     parts = None
     if return_parts:
         parts = {"ibm_bits": bits, "R": Rp, "msum": ms, "w": w, "x_raw": out.clone(), "peak": peak}

@@ -25,7 +25,7 @@ class OracleMvdr:
     launches_per_step = 7
 
     def __init__(self, cfg: MvdrConfig, B: int, L: int, device, keep_spectrum: bool = True, fused_norm: bool = False,
-                 fused: bool = False, fold_weights: bool = False):
+                 fused: bool = False, fold_weights: bool = False, sparse_spectrum: bool = False):
         """`fused`: run pass A, the weights, pass B and the normalisation as ONE persistent kernel whose kept spectrum
         stays in L2 (avz_oracle_fused_f32; n_fft 512, IBM post-filter or none) instead of five separate launches."""
         self.cfg, self.B, self.L, self.device = cfg, B, L, device
@@ -56,6 +56,12 @@ class OracleMvdr:
         self.d = steering_vectors(cfg, device)
         self.cc = cfg.to_c()
         self.fused = bool(fused)
+        # oracle post-filter (1 - noise mask): pass B zeroes every noise-dominated bin, so pass A can keep only the others
+        # (avz_ibm_cov_keep_sparse_f32 / avz_mvdr_apply_kept_sparse_f32): the kept-spectrum traffic of the two passes
+        # falls from 5.05 to 1.9 GB per 1024 x 4 s with the same bits out - but the compaction costs ~120 / ~200 more
+        # instructions per frame, and both kernels are then issue-bound: 0.64 + 0.69 ms against 0.57 + 0.47 dense
+        # (profiles/README.md).  Off by default.
+        self.sparse = bool(sparse_spectrum) and self.spec is not None and cfg.post == "one_minus_noise" and not self.fused_norm
         # n_fft 512 fast path: finalize + weights folded into pass A's last block per utterance (two launches fewer,
         # bit-identical).  Measured on B200 it does not pay: a single block per utterance is slower at the tail than the
         # two small parallel kernels it replaces (config 2: 1.699 vs 1.696 ms per step; one 5 s utterance as a CUDA
@@ -80,7 +86,13 @@ class OracleMvdr:
             _lib.check(self.lib.avz_ibm_cov_weights_keep_f32(_ptr(mix), _ptr(tgt), _ptr(itf), self.B, self.L, c.n_fft, c.hop,
                                                              C.byref(self.cc), _ptr(self.d), _ptr(self.bits), _ptr(self.R),
                                                              _ptr(self.msum), _ptr(self.w), _ptr(self.ws), _ptr(self.spec),
-                                                             _stream()), "avz_ibm_cov_weights_keep_f32")
+                                                             int(self.sparse), _stream()), "avz_ibm_cov_weights_keep_f32")
+            return
+        if self.spec is not None and self.sparse:
+            _lib.check(self.lib.avz_ibm_cov_keep_sparse_f32(_ptr(mix), _ptr(tgt), _ptr(itf), self.B, self.L, c.n_fft, c.hop,
+                                                            float(c.norm_eps), _ptr(self.bits), _ptr(self.R), _ptr(self.msum),
+                                                            _ptr(self.ws), _ptr(self.spec), _stream()),
+                       "avz_ibm_cov_keep_sparse_f32")
             return
         if self.spec is not None:
             _lib.check(self.lib.avz_ibm_cov_keep_f32(_ptr(mix), _ptr(tgt), _ptr(itf), self.B, self.L, c.n_fft, c.hop,
@@ -108,6 +120,11 @@ class OracleMvdr:
                                                              self.B, self.L, c.n_fft, c.hop, C.byref(self.cc),
                                                              float(c.peak_eps), _ptr(out_t), _ptr(self.peak),
                                                              _stream()), "avz_mvdr_apply_kept_norm_f32")
+            return
+        if self.spec is not None and self.sparse:
+            _lib.check(self.lib.avz_mvdr_apply_kept_sparse_f32(_ptr(self.spec), _ptr(self.w), _ptr(bits), self.B, self.L,
+                                                               c.n_fft, c.hop, C.byref(self.cc), _ptr(out_t), _ptr(self.peak),
+                                                               _stream()), "avz_mvdr_apply_kept_sparse_f32")
             return
         if self.spec is not None:
             _lib.check(self.lib.avz_mvdr_apply_kept_f32(_ptr(self.spec), _ptr(self.w), _ptr(bits), _ptr(None), self.B,

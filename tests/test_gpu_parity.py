@@ -521,3 +521,42 @@ def test_pass_a_with_folded_weights_is_bit_identical(az):
         assert b.fold_weights and not a.fold_weights
         xa, xb = a.run(mix_d, tgt_d, itf_d), b.run(mix_d, tgt_d, itf_d)
         assert torch.equal(a.R, b.R) and torch.equal(a.msum, b.msum) and torch.equal(a.w, b.w) and torch.equal(xa, xb)
+
+
+def test_sparse_kept_spectrum_is_bit_identical_and_mismatch_is_loud(az):
+    """Oracle post-filter: pass A keeps only the bins whose noise bit is clear (compacted), pass B reads them back:
+    same waveform bit for bit as the dense kept spectrum and as the recomputing pass B; a dense spectrum read as sparse
+    (or the reverse) gives NaN, not garbage."""
+    from avzoom import pipeline
+    for preset, B, dur in (("baseline_oracle", 6, 1.3), ("oracle_debug", 3, 2.0), ("baseline_oracle", 70, 0.6), ("baseline_oracle", 1, 5.0)):
+        cfg = az.PRESETS[preset]
+        mix, tgt, itf = synth(8, min(B, 8), dur, 3)
+        rep = (B + mix.shape[0] - 1) // mix.shape[0]
+        mix, tgt, itf = (np.tile(a, (rep,) + (1,) * (a.ndim - 1))[:B].copy() for a in (mix, tgt, itf))
+        tgt[0, :4000] = 0.0                               # a stretch where every bin is noise-dominated: empty frames
+        itf[-1, -4000:] = 0.0                             # ... and one where none is: full frames
+        mix_d, tgt_d, itf_d = (torch.from_numpy(a).cuda() for a in (mix, tgt, itf))
+        L = mix.shape[-1]
+        dense = pipeline.OracleMvdr(cfg, B, L, mix_d.device)
+        sparse = pipeline.OracleMvdr(cfg, B, L, mix_d.device, sparse_spectrum=True)
+        reco = pipeline.OracleMvdr(cfg, B, L, mix_d.device, keep_spectrum=False)
+        assert sparse.sparse and not dense.sparse
+        a = dense.run(mix_d, tgt_d, itf_d).clone()
+        b = sparse.run(mix_d, tgt_d, itf_d).clone()
+        c = reco.run(mix_d, tgt_d, itf_d).clone()
+        assert bool(torch.isfinite(a).all()) and torch.equal(a, b) and torch.equal(a, c)
+        assert torch.equal(dense.R, sparse.R) and torch.equal(dense.bits, sparse.bits) and torch.equal(dense.peak, sparse.peak)
+        # the ops-level pair
+        spec = az.alloc_kept_spectrum(mix_d, cfg, ibm=True)
+        bits, Rp, _ = az.ibm_covariance(mix_d, tgt_d, itf_d, cfg, spec, sparse=True)
+        wts = az.mvdr_weights(Rp, az.steering_vectors(cfg, mix_d.device), cfg)
+        x, pk = az.mvdr_apply(mix_d, wts, cfg, ibm_bits=bits, spec=spec, sparse=True)
+        if cfg.peak_eps is not None:
+            az.peak_normalise(x, pk, cfg.peak_eps)
+        assert torch.equal(x, a)
+        # layout mismatch: sparse pass A, dense pass B
+        sparse.pass_a(mix_d, tgt_d, itf_d)
+        sparse.weights()
+        sparse.sparse = False
+        sparse.pass_b(mix_d)
+        assert bool(torch.isnan(sparse.out).all())
