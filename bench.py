@@ -258,7 +258,7 @@ def run_ours(args):
     enh = pipeline.OracleMvdr(cfg, B, L, dev, fused=FUSED)      # pre-allocated buffers, no per-step allocation
     # steady-state serving loop: consecutive steps alternate between two engines on two CUDA streams (every step is
     # still one full pass of all seven kernels over the whole batch; the single-stream time is reported next to it)
-    DEPTH = 2
+    DEPTH = max(1, args.depth)
     loop = pipeline.StreamedOracleMvdr(cfg, B, L, dev, depth=DEPTH, fused=FUSED)
 
     def barrier():
@@ -487,6 +487,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the config 1/3/4/5 blocks")
+    ap.add_argument("--depth", type=int, default=2, help="engines / CUDA streams the steady-state loop alternates between")
     ap.add_argument("--e2e-sub-batches", type=int, default=8, help="sub-batches per step of the host-buffer pipeline")
     ap.add_argument("--fused-kernel", action="store_true",
                     help="pass A + weights + pass B + normalisation as one persistent kernel with the kept spectrum in an L2 ring "

@@ -426,12 +426,12 @@ k_mask_transpose(const float* __restrict__ mask, float* __restrict__ mask_t, int
 // This trades 64 B/sample of spare HBM bandwidth for ~30 % fewer instructions on an issue-bound path.
 // L2KEEP: the kept spectrum is written with ordinary stores (it is read back out of L2 by the same launch: k512_fused)
 // instead of streaming (evict-first) stores.  (b, chunk, chunks) = (blockIdx.y, blockIdx.x, gridDim.x) of the plain launch.
-template <int HOP, int WMODE, bool L2KEEP>
+template <int HOP, int WMODE, bool L2KEEP, bool SPARSE>
 __device__ __forceinline__ void cov_body(unsigned char* smem_raw, int b, int chunk, int chunks,
                                          const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits,
                                          const float* __restrict__ mask, MaskLayout ml, int L, int T, int frames_per_cta,
                                          float sqrt_eps, float* __restrict__ part, float4* __restrict__ spec,
-                                         int64_t spec_utt, int sparse, const Tables& tb) {
+                                         int64_t spec_utt, const Tables& tb) {
   float2* sm_all = reinterpret_cast<float2*>(smem_raw);
   float2* sm = sm_all + (size_t)(threadIdx.x >> 5) * f512::kSmemComplex;
   Lane ln;
@@ -522,11 +522,11 @@ __device__ __forceinline__ void cov_body(unsigned char* smem_raw, int b, int chu
           }
           bool keep = true;
           unsigned bal = kFull;
-          if (sparse) {
+          if (SPARSE) {
             keep = (mw[j] == 0.f) || (j == 0 && lane == 0 && mny == 0.f);
             bal = __ballot_sync(kFull, keep);
           }
-          float4* dst = sp + base + __popc(bal & lt);
+          float4* dst = SPARSE ? sp + base + __popc(bal & lt) : sp + 32 * j + lane;
           base += __popc(bal);
           if (keep) {
             if (L2KEEP) *dst = q;
@@ -641,16 +641,15 @@ struct CovTail {
   uint32_t* shdr;          // header of the kept-spectrum buffer: word 3 records whether the spectrum is sparse
   int sparse;
 };
-template <int HOP>
+template <int HOP, bool SPARSE>
 __global__ void __launch_bounds__(kWarps * 32, AVZ_MINB_COV)
 k512_cov_w(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, int L, int T, int frames_per_cta,
            float* __restrict__ part, float4* __restrict__ spec, CovTail tail, Tables tb) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ int s_last;
-  if (tail.shdr != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) tail.shdr[3] = (uint32_t)tail.sparse;
-  cov_body<HOP, W_BITS, false>(smem_raw, blockIdx.y, blockIdx.x, gridDim.x, mix, ibm_bits, nullptr,
-                               MaskLayout{0, 0, 0, nullptr, 0u, 0u}, L, T, frames_per_cta, 0.f, part, spec, blockIdx.y,
-                               tail.sparse, tb);
+  if (tail.shdr != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) tail.shdr[3] = SPARSE ? 1u : 0u;
+  cov_body<HOP, W_BITS, false, SPARSE>(smem_raw, blockIdx.y, blockIdx.x, gridDim.x, mix, ibm_bits, nullptr,
+                                       MaskLayout{0, 0, 0, nullptr, 0u, 0u}, L, T, frames_per_cta, 0.f, part, spec, blockIdx.y, tb);
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicAdd(tail.done + blockIdx.y, 1) == (int)gridDim.x - 1);
@@ -660,15 +659,15 @@ k512_cov_w(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits,
   finalize_weights_utt(part, blockIdx.y, gridDim.x, tail.norm_eps, tail.dvec, tail.cfg, tail.R, tail.msum, tail.w);
 }
 
-template <int HOP, int WMODE>
+template <int HOP, int WMODE, bool SPARSE>
 __global__ void __launch_bounds__(kWarps * 32, AVZ_MINB_COV)
 k512_cov(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, const float* __restrict__ mask,
          MaskLayout ml, int L, int T, int frames_per_cta, float sqrt_eps, float* __restrict__ part,
-         float4* __restrict__ spec, uint32_t* __restrict__ shdr, int sparse, Tables tb) {
+         float4* __restrict__ spec, uint32_t* __restrict__ shdr, Tables tb) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  if (WMODE == W_BITS && shdr != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) shdr[3] = (uint32_t)sparse;
-  cov_body<HOP, WMODE, false>(smem_raw, blockIdx.y, blockIdx.x, gridDim.x, mix, ibm_bits, mask, ml, L, T, frames_per_cta,
-                              sqrt_eps, part, spec, blockIdx.y, WMODE == W_BITS ? sparse : 0, tb);
+  if (WMODE == W_BITS && shdr != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) shdr[3] = SPARSE ? 1u : 0u;
+  cov_body<HOP, WMODE, false, SPARSE>(smem_raw, blockIdx.y, blockIdx.x, gridDim.x, mix, ibm_bits, mask, ml, L, T, frames_per_cta,
+                                      sqrt_eps, part, spec, blockIdx.y, tb);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -697,7 +696,7 @@ __host__ __device__ constexpr size_t apply_smem_bytes() {
 // plain launch, a ring slot in k512_fused).  The mbarriers of the TMA ring are initialised once per CTA (`init_bar`) and
 // keep counting phases across the tasks of a persistent kernel: bit `stage` of `phase_bits` is the parity the next wait
 // on that stage must use.
-template <int HOP, bool KEPT>
+template <int HOP, bool KEPT, bool SPARSE>
 __device__ __forceinline__ void apply_body(unsigned char* smem_raw, int b, int bx, bool init_bar, uint32_t& phase_bits,
                                            int64_t spec_utt,
                                            const float* __restrict__ mix, const float4* __restrict__ spec,
@@ -705,7 +704,7 @@ __device__ __forceinline__ void apply_body(unsigned char* smem_raw, int b, int b
                                            const float* __restrict__ mask, MaskLayout ml, int gain_mode, float post_floor,
                                            int L, int T, int blocks_per_cta, float* __restrict__ out,
                                            float* __restrict__ peak, int cluster_norm, float peak_eps,
-                                           const uint32_t* __restrict__ shdr, int sparse, const Tables& tb) {
+                                           const uint32_t* __restrict__ shdr, const Tables& tb) {
   constexpr int R = kN / HOP;        // frames overlapping one hop-block
   constexpr int NR = HOP / 32;       // rows per hop-block
   constexpr int TAIL = 16 - NR;      // rows still open after a frame's first block is emitted
@@ -736,7 +735,7 @@ __device__ __forceinline__ void apply_body(unsigned char* smem_raw, int b, int b
     // a staged mask copy that is not there (header mismatch) poisons the weights: the output is NaN, not garbage
     // ... and so does a kept spectrum whose layout (dense / sparse) is not the one this call was told to read
     const bool staged_ok = (ml.hdr == nullptr || (ml.hdr[0] == kMaskMagic && ml.hdr[1] == ml.B && ml.hdr[2] == ml.T)) &&
-                           (!KEPT || shdr == nullptr || shdr[3] == (uint32_t)sparse);
+                           (!KEPT || shdr == nullptr || shdr[3] == (SPARSE ? 1u : 0u));
     const float sc = staged_ok ? 0.5f / (float)kN : __int_as_float(0x7fc00000);
     for (int k = threadIdx.x; k < kF; k += kWarps * 32) {
       const float2 w0 = wgt[((int64_t)b * kF + k) * 2 + 0];
@@ -833,9 +832,9 @@ __device__ __forceinline__ void apply_body(unsigned char* smem_raw, int b, int b
     // sparse kept spectrum: a frame's block holds only the slots whose noise bit is clear, n_t of them, compacted; n_t
     // comes from the frame's 9 IBM words (lanes 0..8 hold one word each), fetched one frame before its copy is issued
     const uint32_t* bits_b = ibm_bits + (int64_t)b * T * kFW;
-    auto load_word = [&](int f) -> uint32_t { return (sparse && lane < kFW && f <= t_last) ? __ldg(bits_b + (int64_t)f * kFW + lane) : 0u; };
+    auto load_word = [&](int f) -> uint32_t { return (SPARSE && lane < kFW && f <= t_last) ? __ldg(bits_b + (int64_t)f * kFW + lane) : 0u; };
     auto count_of = [&](uint32_t wd) -> int {
-      if (!sparse) return 256;
+      if (!SPARSE) return 256;
       int c = (lane < 8) ? __popc(wd) : 0;
       c = __reduce_add_sync(kFull, c);
       const uint32_t b0 = __shfl_sync(kFull, wd, 0) & 1u, b256 = __shfl_sync(kFull, wd, 8) & 1u;
@@ -908,7 +907,7 @@ __device__ __forceinline__ void apply_body(unsigned char* smem_raw, int b, int b
           int n_here = 0;
 #pragma unroll
           for (int q = 0; q < kStages; ++q) n_here = (q == st) ? n_stage[q] : n_here;
-          if (n_here > 0) {
+          if (!SPARSE || n_here > 0) {
             mbar_wait(s_bar + st, (phase_bits >> st) & 1u);
             phase_bits ^= 1u << st;
           }
@@ -919,11 +918,11 @@ __device__ __forceinline__ void apply_body(unsigned char* smem_raw, int b, int b
           for (int j = 0; j < 8; ++j) {
             bool keep = true;
             unsigned bal = kFull;
-            if (sparse) {
+            if (SPARSE) {
               keep = (gj[j] != 0.f) || (j == 0 && lane == 0 && gny != 0.f);
               bal = __ballot_sync(kFull, keep);
             }
-            const int pos = base + __popc(bal & lt);
+            const int pos = SPARSE ? base + __popc(bal & lt) : 32 * j + lane;
             base += __popc(bal);
             const float4 q = keep ? fr[pos] : make_float4(0.f, 0.f, 0.f, 0.f);
             zlo[j] = make_float2(q.x, q.y);
@@ -1077,17 +1076,16 @@ __device__ __forceinline__ void apply_body(unsigned char* smem_raw, int b, int b
   }
 }
 
-template <int HOP, bool KEPT>
+template <int HOP, bool KEPT, bool SPARSE>
 __global__ void __launch_bounds__(kWarps * 32, KEPT ? AVZ_MINB_APPLY_KEPT : AVZ_MINB_APPLY)
 k512_apply(const float* __restrict__ mix, const float4* __restrict__ spec, const float2* __restrict__ wgt,
            const uint32_t* __restrict__ ibm_bits, const float* __restrict__ mask, MaskLayout ml, int gain_mode,
            float post_floor, int L, int T, int blocks_per_cta, float* __restrict__ out, float* __restrict__ peak,
-           int cluster_norm, float peak_eps, const uint32_t* __restrict__ shdr, int sparse, Tables tb) {
+           int cluster_norm, float peak_eps, const uint32_t* __restrict__ shdr, Tables tb) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint32_t phase_bits = 0u;
-  apply_body<HOP, KEPT>(smem_raw, blockIdx.y, blockIdx.x, true, phase_bits, blockIdx.y, mix, spec, wgt, ibm_bits, mask, ml,
-                        gain_mode, post_floor, L, T, blocks_per_cta, out, peak, cluster_norm, peak_eps, shdr,
-                        (KEPT && gain_mode == GAIN_BITS) ? sparse : 0, tb);
+  apply_body<HOP, KEPT, SPARSE>(smem_raw, blockIdx.y, blockIdx.x, true, phase_bits, blockIdx.y, mix, spec, wgt, ibm_bits, mask,
+                                ml, gain_mode, post_floor, L, T, blocks_per_cta, out, peak, cluster_norm, peak_eps, shdr, tb);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1121,7 +1119,7 @@ struct FusedArgs {
   int* ctrl;         // [0] queue head, then a_done[B], w_ready[B], b_done[B]
   AvzMvdrCfg cfg;
   float norm_eps, peak_eps;   // peak_eps < 0: no normalisation
-  int B, L, T, fpt, CA, CB, lag, nslot, sparse;
+  int B, L, T, fpt, CA, CB, lag, nslot;
   Tables tb;
 };
 
@@ -1182,8 +1180,8 @@ __global__ void __launch_bounds__(kWarps * 32, 2) k512_fused(FusedArgs a) {
     const int ring = u % a.nslot;
     if (is_a) {
       if (u >= a.nslot) spin_until(b_done + (u - a.nslot), a.CB, 0, u);   // the ring slot's previous utterance has been consumed
-      cov_body<HOP, W_BITS, true>(smem_raw, u, c, a.CA, a.mix, a.ibm_bits, nullptr, MaskLayout{0, 0, 0, nullptr, 0u, 0u}, a.L,
-                                  a.T, a.fpt, 0.f, a.part, a.spec, ring, a.sparse, a.tb);
+      cov_body<HOP, W_BITS, true, false>(smem_raw, u, c, a.CA, a.mix, a.ibm_bits, nullptr, MaskLayout{0, 0, 0, nullptr, 0u, 0u},
+                                         a.L, a.T, a.fpt, 0.f, a.part, a.spec, ring, a.tb);
       __threadfence();
       __syncthreads();
       if (threadIdx.x == 0) s_last = (atomicAdd(a_done + u, 1) == a.CA - 1);
@@ -1200,10 +1198,9 @@ __global__ void __launch_bounds__(kWarps * 32, 2) k512_fused(FusedArgs a) {
     } else {
       spin_until(w_ready + u, 1, 1, u);
       fence_proxy_async_all();   // the spectrum was written by other CTAs' ordinary stores; it is read by TMA bulk copies here
-      apply_body<HOP, true>(smem_raw, u, c, !ring_used, phase_bits, ring, nullptr, a.spec, a.w, a.ibm_bits, nullptr,
+      apply_body<HOP, true, false>(smem_raw, u, c, !ring_used, phase_bits, ring, nullptr, a.spec, a.w, a.ibm_bits, nullptr,
                             MaskLayout{0, 0, 0, nullptr, 0u, 0u}, a.cfg.post_mode == AVZ_POST_ONE_MINUS_NOISE ? GAIN_BITS : GAIN_NONE,
-                            0.f, a.L, a.T, a.fpt, a.out, a.peak, 0, 0.f, nullptr,
-                            a.cfg.post_mode == AVZ_POST_ONE_MINUS_NOISE ? a.sparse : 0, a.tb);
+                            0.f, a.L, a.T, a.fpt, a.out, a.peak, 0, 0.f, nullptr, a.tb);
       ring_used = true;
       __threadfence();
       __syncthreads();
@@ -1367,22 +1364,36 @@ int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const f
     ct.cfg = *tail->cfg;
     ct.norm_eps = tail->norm_eps;
     ct.shdr = spec ? spec_hdr(spec, B, T) : nullptr;
-    ct.sparse = spec ? sparse : 0;
-    AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov_w<HOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
-    k512_cov_w<HOP><<<grid, kWarps * 32, smem_cov, st>>>(mix, ibm_bits, (int)L, T, fpc, part, reinterpret_cast<float4*>(spec),
-                                                         ct, tb);
+    ct.sparse = (spec && sparse) ? 1 : 0;
+    if (ct.sparse) {
+      AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov_w<HOP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
+      k512_cov_w<HOP, true><<<grid, kWarps * 32, smem_cov, st>>>(mix, ibm_bits, (int)L, T, fpc, part,
+                                                                 reinterpret_cast<float4*>(spec), ct, tb);
+    } else {
+      AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov_w<HOP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
+      k512_cov_w<HOP, false><<<grid, kWarps * 32, smem_cov, st>>>(mix, ibm_bits, (int)L, T, fpc, part,
+                                                                  reinterpret_cast<float4*>(spec), ct, tb);
+    }
   } else if (mask == nullptr) {
-    AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov<HOP, W_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
-    k512_cov<HOP, W_BITS><<<grid, kWarps * 32, smem_cov, st>>>(mix, ibm_bits, nullptr, MaskLayout{0, 0, 0, nullptr, 0u, 0u}, (int)L, T, fpc,
-                                                               0.f, part, reinterpret_cast<float4*>(spec),
-                                                               spec ? spec_hdr(spec, B, T) : nullptr, spec ? sparse : 0, tb);
+    uint32_t* shdr = spec ? spec_hdr(spec, B, T) : nullptr;
+    if (spec && sparse) {
+      AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov<HOP, W_BITS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
+      k512_cov<HOP, W_BITS, true><<<grid, kWarps * 32, smem_cov, st>>>(mix, ibm_bits, nullptr, MaskLayout{0, 0, 0, nullptr, 0u, 0u},
+                                                                       (int)L, T, fpc, 0.f, part, reinterpret_cast<float4*>(spec),
+                                                                       shdr, tb);
+    } else {
+      AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov<HOP, W_BITS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
+      k512_cov<HOP, W_BITS, false><<<grid, kWarps * 32, smem_cov, st>>>(mix, ibm_bits, nullptr, MaskLayout{0, 0, 0, nullptr, 0u, 0u},
+                                                                        (int)L, T, fpc, 0.f, part, reinterpret_cast<float4*>(spec),
+                                                                        shdr, tb);
+    }
   } else {
-    AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov<HOP, W_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
+    AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov<HOP, W_MASK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
     MaskLayout ml;
     const float* mptr = stage_mask(mask, spec, B, T, &ml, st);
     AVZ_LAUNCH_OK("k_mask_transpose");
-    k512_cov<HOP, W_MASK><<<grid, kWarps * 32, smem_cov, st>>>(mix, nullptr, mptr, ml, (int)L, T, fpc, sqrt_eps, part,
-                                                               reinterpret_cast<float4*>(spec), nullptr, 0, tb);
+    k512_cov<HOP, W_MASK, false><<<grid, kWarps * 32, smem_cov, st>>>(mix, nullptr, mptr, ml, (int)L, T, fpc, sqrt_eps, part,
+                                                                      reinterpret_cast<float4*>(spec), nullptr, tb);
   }
   prof_end(PROF_COV, st);
   AVZ_LAUNCH_OK("k512_cov");
@@ -1416,7 +1427,9 @@ int launch_apply(const float* mix, const void* spec, const float* w, const uint3
   }
   prof_begin(PROF_APPLY, st);
   if (spec != nullptr) {
-    AVZ_CUDA_OK(cudaFuncSetAttribute(k512_apply<HOP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool sp_on = sparse && gain_mode == GAIN_BITS;
+    auto kern = sp_on ? k512_apply<HOP, true, true> : k512_apply<HOP, true, false>;
+    AVZ_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // fused normalisation: the CTAs of an utterance run as one thread-block cluster (portable size limit 8)
     const int cluster_norm = (fuse_norm && peak != nullptr && chunks <= 8) ? 1 : 0;
     cudaLaunchConfig_t lc = {};
@@ -1431,19 +1444,22 @@ int launch_apply(const float* mix, const void* spec, const float* w, const uint3
     at[0].val.clusterDim.z = 1;
     lc.attrs = at;
     lc.numAttrs = 1;
-    AVZ_CUDA_OK(cudaLaunchKernelEx(&lc, k512_apply<HOP, true>, (const float*)nullptr, reinterpret_cast<const float4*>(spec),
+    // the header word that records the layout is written by the IBM pass A only: a float-mask pass B does not look at it
+    const uint32_t* shdr = (gain_mode == GAIN_BITS || gain_mode == GAIN_NONE) && !mask_staged ? spec_hdr(spec, B, T) : nullptr;
+    if (gain_mode == GAIN_NONE) shdr = nullptr;   // AVZ_POST_NONE may follow either pass A
+    AVZ_CUDA_OK(cudaLaunchKernelEx(&lc, kern, (const float*)nullptr, reinterpret_cast<const float4*>(spec),
                                    reinterpret_cast<const float2*>(w), ibm_bits, mptr, ml, gain_mode, post_floor, (int)L, T,
-                                   bpc, out, peak, cluster_norm, peak_eps, (const uint32_t*)spec_hdr(spec, B, T), sparse, tb));
+                                   bpc, out, peak, cluster_norm, peak_eps, shdr, tb));
     if (fuse_norm && !cluster_norm) {   // too many chunks per utterance for a cluster: separate pass
       prof_end(PROF_APPLY, st);
       AVZ_LAUNCH_OK("k512_apply");
       return avz_peak_normalise_f32(out, B, (int64_t)(T - 1) * HOP, peak, peak_eps, st);
     }
   } else {
-    AVZ_CUDA_OK(cudaFuncSetAttribute(k512_apply<HOP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k512_apply<HOP, false><<<grid, kWarps * 32, smem, st>>>(mix, nullptr, reinterpret_cast<const float2*>(w), ibm_bits,
-                                                            mptr, ml, gain_mode, post_floor, (int)L, T, bpc, out, peak,
-                                                            0, 0.f, (const uint32_t*)nullptr, 0, tb);
+    AVZ_CUDA_OK(cudaFuncSetAttribute(k512_apply<HOP, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k512_apply<HOP, false, false><<<grid, kWarps * 32, smem, st>>>(mix, nullptr, reinterpret_cast<const float2*>(w), ibm_bits,
+                                                                   mptr, ml, gain_mode, post_floor, (int)L, T, bpc, out, peak,
+                                                                   0, 0.f, (const uint32_t*)nullptr, tb);
   }
   prof_end(PROF_APPLY, st);
   AVZ_LAUNCH_OK("k512_apply");
@@ -1539,7 +1555,6 @@ int launch_oracle_fused(const float* mix, const float* tgt, const float* itf, in
   fa.CB = g.CB;
   fa.lag = g.lag;
   fa.nslot = g.nslot;
-  fa.sparse = (cfg->post_mode == AVZ_POST_ONE_MINUS_NOISE) ? 1 : 0;
   fa.tb = tb;
   const size_t smem = fused_smem_bytes<HOP>();
   AVZ_CUDA_OK(cudaFuncSetAttribute(k512_fused<HOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
