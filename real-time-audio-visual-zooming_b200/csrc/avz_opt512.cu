@@ -148,6 +148,22 @@ struct FrameBits {
   __device__ __forceinline__ bool bit(int j, int k1) const { return (w[j >> 1] >> (k1 + 16 * (j & 1))) & 1u; }
 };
 
+// The same bits in (slot j, lane) order: word j of a frame is the warp ballot of slot j, i.e. bit `lane` of word j is the
+// noise bit of bin k1 + 16 j + 128 h.  k512_ibm writes this copy next to the k-ordered one when the sparse kept spectrum
+// is in use: a slot's keep mask over the lanes (what the compaction needs) is then ~word[j], no ballot or bit shuffling.
+struct LaneBits {
+  uint32_t w[8], ny;
+  __device__ __forceinline__ void load(const uint32_t* __restrict__ lane_bits_t, const uint32_t* __restrict__ bits_t) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(lane_bits_t));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(lane_bits_t) + 1);
+    w[0] = a.x, w[1] = a.y, w[2] = a.z, w[3] = a.w, w[4] = b.x, w[5] = b.y, w[6] = b.z, w[7] = b.w;
+    ny = __ldg(bits_t + 8);
+  }
+  __device__ __forceinline__ bool bit(int j, int lane) const { return (w[j] >> lane) & 1u; }
+  // lanes of slot j whose bin is kept (noise bit clear); slot (0, lane 0) carries DC and Nyquist: kept if either is
+  __device__ __forceinline__ uint32_t keep(int j) const { return ~w[j] | ((j == 0) ? (~ny & 1u) : 0u); }
+};
+
 // ------------------------------------------------------------------------------------------
 // IBM bits
 // ------------------------------------------------------------------------------------------
@@ -202,7 +218,7 @@ __device__ __forceinline__ void ibm_decide(float2 z, float2 m, float d2, bool li
 template <int HOP>
 __global__ void __launch_bounds__(kWarps * 32, AVZ_MINB_IBM)
 k512_ibm(const float* __restrict__ tgt, const float* __restrict__ itf, int L, int T, int frames_per_cta,
-         uint32_t* __restrict__ ibm_bits, AmbList amb_list, float tol2, Tables tb) {
+         uint32_t* __restrict__ ibm_bits, uint32_t* __restrict__ lane_bits, AmbList amb_list, float tol2, Tables tb) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float2* sm = reinterpret_cast<float2*>(smem_raw) + (size_t)(threadIdx.x >> 5) * f512::kSmemComplex;
   Lane ln;
@@ -287,6 +303,11 @@ k512_ibm(const float* __restrict__ tgt, const float* __restrict__ itf, int L, in
         o[4 + wd] = (ballots[2 * wd] >> 16) | (ballots[2 * wd + 1] & 0xffff0000u);
       }
       o[8] = ny;
+      if (lane_bits != nullptr) {   // the ballots themselves: (slot, lane) order for the sparse kept spectrum
+        uint4* lb = reinterpret_cast<uint4*>(lane_bits + ((int64_t)b * T + t) * 8);
+        lb[0] = make_uint4(ballots[0], ballots[1], ballots[2], ballots[3]);
+        lb[1] = make_uint4(ballots[4], ballots[5], ballots[6], ballots[7]);
+      }
     }
     if (t + 1 < tb_) win.advance();
   }
@@ -301,7 +322,7 @@ constexpr int kFixBlock = 2;   // short blocks + many warps: the kernel is a lat
 
 __global__ void __launch_bounds__(256)
 k512_ibm_fixup(const float* __restrict__ tgt, const float* __restrict__ itf, int64_t L, int T, int hop, int B,
-               uint32_t* __restrict__ ibm_bits, AmbList amb_list, Tables tb) {
+               uint32_t* __restrict__ ibm_bits, uint32_t* __restrict__ lane_bits, AmbList amb_list, Tables tb) {
   const int lane = threadIdx.x & 31;
   const unsigned long long gw = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const unsigned long long nw = (unsigned long long)gridDim.x * (blockDim.x >> 5);
@@ -365,7 +386,11 @@ k512_ibm_fixup(const float* __restrict__ tgt, const float* __restrict__ itf, int
       if (lane == 0) {
         uint32_t* wp = ibm_bits + ((int64_t)b * T + t) * kFW + (k >> 5);
         const bool cur = ((*wp) >> (k & 31)) & 1u;
-        if (cur != exact) atomicXor(wp, 1u << (k & 31));
+        if (cur != exact) {
+          atomicXor(wp, 1u << (k & 31));
+          if (lane_bits != nullptr && k < 256)   // bin k = k1 + 16 j + 128 h sits at bit k1 + 16 h of word j
+            atomicXor(lane_bits + ((int64_t)b * T + t) * 8 + ((k & 127) >> 4), 1u << ((k & 15) + 16 * (k >> 7)));
+        }
       }
     }
   }
@@ -431,7 +456,7 @@ __device__ __forceinline__ void cov_body(unsigned char* smem_raw, int b, int chu
                                          const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits,
                                          const float* __restrict__ mask, MaskLayout ml, int L, int T, int frames_per_cta,
                                          float sqrt_eps, float* __restrict__ part, float4* __restrict__ spec,
-                                         int64_t spec_utt, const Tables& tb) {
+                                         int64_t spec_utt, const uint32_t* __restrict__ lane_bits, const Tables& tb) {
   float2* sm_all = reinterpret_cast<float2*>(smem_raw);
   float2* sm = sm_all + (size_t)(threadIdx.x >> 5) * f512::kSmemComplex;
   Lane ln;
@@ -461,10 +486,14 @@ __device__ __forceinline__ void cov_body(unsigned char* smem_raw, int b, int chu
     win.load_all(m0, m1, L, ta, lane);
     // noise weights of this lane's bins, fetched one frame ahead
     FrameBits nb;
+    LaneBits lq;      // SPARSE: the same bits in (slot, lane) order
     float nmask[9];
     const uint32_t* bw = (WMODE == W_BITS) ? ibm_bits + ((int64_t)b * T + ta) * kFW : nullptr;
+    const uint32_t* lw = SPARSE ? lane_bits + ((int64_t)b * T + ta) * 8 : nullptr;
     const float* mk = (WMODE == W_MASK) ? mask + (int64_t)b * ml.sb + (int64_t)ta * ml.st : nullptr;
-    if (WMODE == W_BITS) {
+    if (SPARSE) {
+      lq.load(lw, bw);
+    } else if (WMODE == W_BITS) {
       nb.load(bw, ln.h);
     } else {
 #pragma unroll
@@ -474,7 +503,11 @@ __device__ __forceinline__ void cov_body(unsigned char* smem_raw, int b, int chu
 #pragma unroll 1
     for (int t = ta; t < tb_; ++t) {
       float mw[8], mny;
-      if (WMODE == W_BITS) {
+      if (SPARSE) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mw[j] = lq.bit(j, lane) ? 1.f : 0.f;
+        mny = (lq.ny & 1u) ? 1.f : 0.f;
+      } else if (WMODE == W_BITS) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) mw[j] = nb.bit(j, ln.k1) ? 1.f : 0.f;
         mny = (nb.ny & 1u) ? 1.f : 0.f;
@@ -485,7 +518,9 @@ __device__ __forceinline__ void cov_body(unsigned char* smem_raw, int b, int chu
       }
       if (t + 1 < tb_) {
         win.prefetch(m0, m1, L, t + 1, lane);
-        if (WMODE == W_BITS) {
+        if (SPARSE) {
+          // the next frame's bits are fetched after this frame's keep masks have been used (below)
+        } else if (WMODE == W_BITS) {
           bw += kFW;
           nb.load(bw, ln.h);
         } else {
@@ -520,12 +555,8 @@ __device__ __forceinline__ void cov_body(unsigned char* smem_raw, int b, int chu
             q.z = v[8].x;
             q.w = v[8].y;
           }
-          bool keep = true;
-          unsigned bal = kFull;
-          if (SPARSE) {
-            keep = (mw[j] == 0.f) || (j == 0 && lane == 0 && mny == 0.f);
-            bal = __ballot_sync(kFull, keep);
-          }
+          const unsigned bal = SPARSE ? lq.keep(j) : kFull;    // lanes of this slot that are kept
+          const bool keep = (bal >> lane) & 1u;
           float4* dst = SPARSE ? sp + base + __popc(bal & lt) : sp + 32 * j + lane;
           base += __popc(bal);
           if (keep) {
@@ -533,6 +564,11 @@ __device__ __forceinline__ void cov_body(unsigned char* smem_raw, int b, int chu
             else __stcs(dst, q);     // streaming store: read once by pass B, no reuse before that
           }
         }
+      }
+      if (SPARSE && t + 1 < tb_) {
+        bw += kFW;
+        lw += 8;
+        lq.load(lw, bw);
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -640,6 +676,7 @@ struct CovTail {
   float norm_eps;
   uint32_t* shdr;          // header of the kept-spectrum buffer: word 3 records whether the spectrum is sparse
   int sparse;
+  const uint32_t* lane_bits;
 };
 template <int HOP, bool SPARSE>
 __global__ void __launch_bounds__(kWarps * 32, AVZ_MINB_COV)
@@ -649,7 +686,8 @@ k512_cov_w(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits,
   __shared__ int s_last;
   if (tail.shdr != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) tail.shdr[3] = SPARSE ? 1u : 0u;
   cov_body<HOP, W_BITS, false, SPARSE>(smem_raw, blockIdx.y, blockIdx.x, gridDim.x, mix, ibm_bits, nullptr,
-                                       MaskLayout{0, 0, 0, nullptr, 0u, 0u}, L, T, frames_per_cta, 0.f, part, spec, blockIdx.y, tb);
+                                       MaskLayout{0, 0, 0, nullptr, 0u, 0u}, L, T, frames_per_cta, 0.f, part, spec, blockIdx.y,
+                                       tail.lane_bits, tb);
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicAdd(tail.done + blockIdx.y, 1) == (int)gridDim.x - 1);
@@ -663,11 +701,11 @@ template <int HOP, int WMODE, bool SPARSE>
 __global__ void __launch_bounds__(kWarps * 32, AVZ_MINB_COV)
 k512_cov(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, const float* __restrict__ mask,
          MaskLayout ml, int L, int T, int frames_per_cta, float sqrt_eps, float* __restrict__ part,
-         float4* __restrict__ spec, uint32_t* __restrict__ shdr, Tables tb) {
+         float4* __restrict__ spec, uint32_t* __restrict__ shdr, const uint32_t* __restrict__ lane_bits, Tables tb) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   if (WMODE == W_BITS && shdr != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) shdr[3] = SPARSE ? 1u : 0u;
   cov_body<HOP, WMODE, false, SPARSE>(smem_raw, blockIdx.y, blockIdx.x, gridDim.x, mix, ibm_bits, mask, ml, L, T, frames_per_cta,
-                                      sqrt_eps, part, spec, blockIdx.y, tb);
+                                      sqrt_eps, part, spec, blockIdx.y, lane_bits, tb);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -704,7 +742,8 @@ __device__ __forceinline__ void apply_body(unsigned char* smem_raw, int b, int b
                                            const float* __restrict__ mask, MaskLayout ml, int gain_mode, float post_floor,
                                            int L, int T, int blocks_per_cta, float* __restrict__ out,
                                            float* __restrict__ peak, int cluster_norm, float peak_eps,
-                                           const uint32_t* __restrict__ shdr, const Tables& tb) {
+                                           const uint32_t* __restrict__ shdr, const uint32_t* __restrict__ lane_bits,
+                                           const Tables& tb) {
   constexpr int R = kN / HOP;        // frames overlapping one hop-block
   constexpr int NR = HOP / 32;       // rows per hop-block
   constexpr int TAIL = 16 - NR;      // rows still open after a frame's first block is emitted
@@ -831,8 +870,13 @@ __device__ __forceinline__ void apply_body(unsigned char* smem_raw, int b, int b
     const float4* sp = KEPT ? spec + (spec_utt * T + t_first) * 256 : nullptr;
     // sparse kept spectrum: a frame's block holds only the slots whose noise bit is clear, n_t of them, compacted; n_t
     // comes from the frame's 9 IBM words (lanes 0..8 hold one word each), fetched one frame before its copy is issued
+    // (lanes 0..7 hold the frame's 8 ballot words, lane 8 the k-ordered word with the Nyquist bit)
     const uint32_t* bits_b = ibm_bits + (int64_t)b * T * kFW;
-    auto load_word = [&](int f) -> uint32_t { return (SPARSE && lane < kFW && f <= t_last) ? __ldg(bits_b + (int64_t)f * kFW + lane) : 0u; };
+    const uint32_t* lane_b = SPARSE ? lane_bits + (int64_t)b * T * 8 : nullptr;
+    auto load_word = [&](int f) -> uint32_t {
+      if (!SPARSE || f > t_last || lane > 8) return 0u;
+      return (lane < 8) ? __ldg(lane_b + (int64_t)f * 8 + lane) : __ldg(bits_b + (int64_t)f * kFW + 8);
+    };
     auto count_of = [&](uint32_t wd) -> int {
       if (!SPARSE) return 256;
       int c = (lane < 8) ? __popc(wd) : 0;
@@ -861,11 +905,15 @@ __device__ __forceinline__ void apply_body(unsigned char* smem_raw, int b, int b
     }
     // post-filter gains of the frame about to be analysed, fetched one frame ahead
     FrameBits nb;
+    LaneBits lq;      // SPARSE: the same bits in (slot, lane) order
     float nmask[9];
     const uint32_t* bw = ibm_bits + ((int64_t)b * T + t_first) * kFW;
+    const uint32_t* lw = SPARSE ? lane_bits + ((int64_t)b * T + t_first) * 8 : nullptr;
     const float* mk = mask + (int64_t)b * ml.sb + (int64_t)t_first * ml.st;
     auto fetch_gain = [&]() {
-      if (gain_mode == GAIN_BITS) {
+      if (SPARSE) {
+        lq.load(lw, bw);
+      } else if (gain_mode == GAIN_BITS) {
         nb.load(bw, ln.h);
       } else if (gain_mode != GAIN_NONE) {
 #pragma unroll
@@ -888,7 +936,11 @@ __device__ __forceinline__ void apply_body(unsigned char* smem_raw, int b, int b
       if (g <= T - 1) {
         // ---- frame g: forward transform, beamform, post-filter -> S at this lane's low bins (+ Nyquist, lane 0)
         float gj[8], gny;
-        if (gain_mode == GAIN_BITS) {
+        if (SPARSE) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gj[j] = lq.bit(j, lane) ? 0.f : 1.f;   // 1 - noise mask
+          gny = (lq.ny & 1u) ? 0.f : 1.f;
+        } else if (gain_mode == GAIN_BITS) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) gj[j] = nb.bit(j, ln.k1) ? 0.f : 1.f;   // 1 - noise mask
           gny = (nb.ny & 1u) ? 0.f : 1.f;
@@ -916,12 +968,8 @@ __device__ __forceinline__ void apply_body(unsigned char* smem_raw, int b, int b
           int base = 0;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            bool keep = true;
-            unsigned bal = kFull;
-            if (SPARSE) {
-              keep = (gj[j] != 0.f) || (j == 0 && lane == 0 && gny != 0.f);
-              bal = __ballot_sync(kFull, keep);
-            }
+            const unsigned bal = SPARSE ? lq.keep(j) : kFull;
+            const bool keep = (bal >> lane) & 1u;
             const int pos = SPARSE ? base + __popc(bal & lt) : 32 * j + lane;
             base += __popc(bal);
             const float4 q = keep ? fr[pos] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -945,6 +993,7 @@ __device__ __forceinline__ void apply_body(unsigned char* smem_raw, int b, int b
           if (g + 1 <= T - 1) {
             bw += kFW;
             mk += ml.st;
+            if (SPARSE) lw += 8;
             fetch_gain();
           }
         } else {
@@ -1081,11 +1130,13 @@ __global__ void __launch_bounds__(kWarps * 32, KEPT ? AVZ_MINB_APPLY_KEPT : AVZ_
 k512_apply(const float* __restrict__ mix, const float4* __restrict__ spec, const float2* __restrict__ wgt,
            const uint32_t* __restrict__ ibm_bits, const float* __restrict__ mask, MaskLayout ml, int gain_mode,
            float post_floor, int L, int T, int blocks_per_cta, float* __restrict__ out, float* __restrict__ peak,
-           int cluster_norm, float peak_eps, const uint32_t* __restrict__ shdr, Tables tb) {
+           int cluster_norm, float peak_eps, const uint32_t* __restrict__ shdr, const uint32_t* __restrict__ lane_bits,
+           Tables tb) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint32_t phase_bits = 0u;
   apply_body<HOP, KEPT, SPARSE>(smem_raw, blockIdx.y, blockIdx.x, true, phase_bits, blockIdx.y, mix, spec, wgt, ibm_bits, mask,
-                                ml, gain_mode, post_floor, L, T, blocks_per_cta, out, peak, cluster_norm, peak_eps, shdr, tb);
+                                ml, gain_mode, post_floor, L, T, blocks_per_cta, out, peak, cluster_norm, peak_eps, shdr,
+                                lane_bits, tb);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1181,7 +1232,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) k512_fused(FusedArgs a) {
     if (is_a) {
       if (u >= a.nslot) spin_until(b_done + (u - a.nslot), a.CB, 0, u);   // the ring slot's previous utterance has been consumed
       cov_body<HOP, W_BITS, true, false>(smem_raw, u, c, a.CA, a.mix, a.ibm_bits, nullptr, MaskLayout{0, 0, 0, nullptr, 0u, 0u},
-                                         a.L, a.T, a.fpt, 0.f, a.part, a.spec, ring, a.tb);
+                                         a.L, a.T, a.fpt, 0.f, a.part, a.spec, ring, nullptr, a.tb);
       __threadfence();
       __syncthreads();
       if (threadIdx.x == 0) s_last = (atomicAdd(a_done + u, 1) == a.CA - 1);
@@ -1200,7 +1251,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) k512_fused(FusedArgs a) {
       fence_proxy_async_all();   // the spectrum was written by other CTAs' ordinary stores; it is read by TMA bulk copies here
       apply_body<HOP, true, false>(smem_raw, u, c, !ring_used, phase_bits, ring, nullptr, a.spec, a.w, a.ibm_bits, nullptr,
                             MaskLayout{0, 0, 0, nullptr, 0u, 0u}, a.cfg.post_mode == AVZ_POST_ONE_MINUS_NOISE ? GAIN_BITS : GAIN_NONE,
-                            0.f, a.L, a.T, a.fpt, a.out, a.peak, 0, 0.f, nullptr, a.tb);
+                            0.f, a.L, a.T, a.fpt, a.out, a.peak, 0, 0.f, nullptr, nullptr, a.tb);
       ring_used = true;
       __threadfence();
       __syncthreads();
@@ -1343,14 +1394,20 @@ int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const f
       AVZ_CUDA_OK(cudaMemsetAsync(spec_hdr(spec, B, T), 0, 16, st));
     AVZ_CUDA_OK(cudaFuncSetAttribute(k512_ibm<HOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
     prof_begin(PROF_IBM, st);
-    k512_ibm<HOP><<<grid, kWarps * 32, smem_fft, st>>>(tgt, itf, (int)L, T, fpc, ibm_bits, al, ibm_tol2(), tb);
+    // sparse kept spectrum: the bits are also kept in (slot, lane) order, in the (unused) mask region of `spec`
+    uint32_t* lane_bits = (spec && sparse) ? reinterpret_cast<uint32_t*>(static_cast<unsigned char*>(spec) + spec_mask_offset(B, T))
+                                           : nullptr;
+    k512_ibm<HOP><<<grid, kWarps * 32, smem_fft, st>>>(tgt, itf, (int)L, T, fpc, ibm_bits, lane_bits, al, ibm_tol2(), tb);
     prof_end(PROF_IBM, st);
     AVZ_LAUNCH_OK("k512_ibm");
     prof_begin(PROF_FIXUP, st);
-    k512_ibm_fixup<<<num_sms() * 32, 256, 0, st>>>(tgt, itf, L, T, HOP, B, ibm_bits, al, tb);
+    k512_ibm_fixup<<<num_sms() * 32, 256, 0, st>>>(tgt, itf, L, T, HOP, B, ibm_bits, lane_bits, al, tb);
     prof_end(PROF_FIXUP, st);
     AVZ_LAUNCH_OK("k512_ibm_fixup");
   }
+  const uint32_t* lane_bits_c = (spec && sparse && mask == nullptr)
+                                    ? reinterpret_cast<const uint32_t*>(static_cast<unsigned char*>(spec) + spec_mask_offset(B, T))
+                                    : nullptr;
   const size_t smem_cov = smem_fft + (size_t)kWarps * 5 * kFP * sizeof(float);
   prof_begin(PROF_COV, st);
   if (mask == nullptr && tail != nullptr) {
@@ -1365,6 +1422,7 @@ int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const f
     ct.norm_eps = tail->norm_eps;
     ct.shdr = spec ? spec_hdr(spec, B, T) : nullptr;
     ct.sparse = (spec && sparse) ? 1 : 0;
+    ct.lane_bits = lane_bits_c;
     if (ct.sparse) {
       AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov_w<HOP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
       k512_cov_w<HOP, true><<<grid, kWarps * 32, smem_cov, st>>>(mix, ibm_bits, (int)L, T, fpc, part,
@@ -1380,12 +1438,12 @@ int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const f
       AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov<HOP, W_BITS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
       k512_cov<HOP, W_BITS, true><<<grid, kWarps * 32, smem_cov, st>>>(mix, ibm_bits, nullptr, MaskLayout{0, 0, 0, nullptr, 0u, 0u},
                                                                        (int)L, T, fpc, 0.f, part, reinterpret_cast<float4*>(spec),
-                                                                       shdr, tb);
+                                                                       shdr, lane_bits_c, tb);
     } else {
       AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov<HOP, W_BITS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
       k512_cov<HOP, W_BITS, false><<<grid, kWarps * 32, smem_cov, st>>>(mix, ibm_bits, nullptr, MaskLayout{0, 0, 0, nullptr, 0u, 0u},
                                                                         (int)L, T, fpc, 0.f, part, reinterpret_cast<float4*>(spec),
-                                                                        shdr, tb);
+                                                                        shdr, nullptr, tb);
     }
   } else {
     AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov<HOP, W_MASK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
@@ -1393,7 +1451,7 @@ int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const f
     const float* mptr = stage_mask(mask, spec, B, T, &ml, st);
     AVZ_LAUNCH_OK("k_mask_transpose");
     k512_cov<HOP, W_MASK, false><<<grid, kWarps * 32, smem_cov, st>>>(mix, nullptr, mptr, ml, (int)L, T, fpc, sqrt_eps, part,
-                                                                      reinterpret_cast<float4*>(spec), nullptr, tb);
+                                                                      reinterpret_cast<float4*>(spec), nullptr, nullptr, tb);
   }
   prof_end(PROF_COV, st);
   AVZ_LAUNCH_OK("k512_cov");
@@ -1449,7 +1507,11 @@ int launch_apply(const float* mix, const void* spec, const float* w, const uint3
     if (gain_mode == GAIN_NONE) shdr = nullptr;   // AVZ_POST_NONE may follow either pass A
     AVZ_CUDA_OK(cudaLaunchKernelEx(&lc, kern, (const float*)nullptr, reinterpret_cast<const float4*>(spec),
                                    reinterpret_cast<const float2*>(w), ibm_bits, mptr, ml, gain_mode, post_floor, (int)L, T,
-                                   bpc, out, peak, cluster_norm, peak_eps, shdr, tb));
+                                   bpc, out, peak, cluster_norm, peak_eps, shdr,
+                                   sp_on ? reinterpret_cast<const uint32_t*>(static_cast<const unsigned char*>(spec) +
+                                                                             spec_mask_offset(B, T))
+                                         : (const uint32_t*)nullptr,
+                                   tb));
     if (fuse_norm && !cluster_norm) {   // too many chunks per utterance for a cluster: separate pass
       prof_end(PROF_APPLY, st);
       AVZ_LAUNCH_OK("k512_apply");
@@ -1459,7 +1521,7 @@ int launch_apply(const float* mix, const void* spec, const float* w, const uint3
     AVZ_CUDA_OK(cudaFuncSetAttribute(k512_apply<HOP, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k512_apply<HOP, false, false><<<grid, kWarps * 32, smem, st>>>(mix, nullptr, reinterpret_cast<const float2*>(w), ibm_bits,
                                                                    mptr, ml, gain_mode, post_floor, (int)L, T, bpc, out, peak,
-                                                                   0, 0.f, (const uint32_t*)nullptr, tb);
+                                                                   0, 0.f, (const uint32_t*)nullptr, (const uint32_t*)nullptr, tb);
   }
   prof_end(PROF_APPLY, st);
   AVZ_LAUNCH_OK("k512_apply");
@@ -1524,12 +1586,12 @@ int launch_oracle_fused(const float* mix, const float* tgt, const float* itf, in
   const int fpc = frames_per_cta(B, g.T, num_sms());
   AVZ_CUDA_OK(cudaFuncSetAttribute(k512_ibm<HOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
   prof_begin(PROF_IBM, st);
-  k512_ibm<HOP><<<dim3((g.T + fpc - 1) / fpc, B), kWarps * 32, smem_fft, st>>>(tgt, itf, (int)L, g.T, fpc, ibm_bits, al,
+  k512_ibm<HOP><<<dim3((g.T + fpc - 1) / fpc, B), kWarps * 32, smem_fft, st>>>(tgt, itf, (int)L, g.T, fpc, ibm_bits, nullptr, al,
                                                                                 ibm_tol2(), tb);
   prof_end(PROF_IBM, st);
   AVZ_LAUNCH_OK("k512_ibm");
   prof_begin(PROF_FIXUP, st);
-  k512_ibm_fixup<<<num_sms() * 32, 256, 0, st>>>(tgt, itf, L, g.T, HOP, B, ibm_bits, al, tb);
+  k512_ibm_fixup<<<num_sms() * 32, 256, 0, st>>>(tgt, itf, L, g.T, HOP, B, ibm_bits, nullptr, al, tb);
   prof_end(PROF_FIXUP, st);
   AVZ_LAUNCH_OK("k512_ibm_fixup");
   FusedArgs fa;
@@ -1588,7 +1650,7 @@ int launch_ibm_exact(const float* tgt, const float* itf, int B, int64_t L, int h
   al.count = reinterpret_cast<unsigned int*>(ws16);
   al.entries = nullptr;
   al.cap = 0;
-  k512_ibm_fixup<<<num_sms() * 8, 256, 0, st>>>(tgt, itf, L, T, hop, B, ibm_bits, al, tb);
+  k512_ibm_fixup<<<num_sms() * 8, 256, 0, st>>>(tgt, itf, L, T, hop, B, ibm_bits, nullptr, al, tb);
   AVZ_LAUNCH_OK("k512_ibm_fixup(exact)");
   return AVZ_OK;
 }
