@@ -22,7 +22,9 @@ FS = 16000
 
 
 def _timed(fn, iters):
-    fn()
+    r = None
+    for _ in range(3):        # warm-up: kernels, and the two output buffers the loop below alternates between
+        r = fn()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
