@@ -191,6 +191,18 @@ AVZ_API int avz_ibm_cov_keep_sparse_f32(const float* mix, const float* tgt, cons
 AVZ_API int avz_mvdr_apply_kept_sparse_f32(const void* spec, const float* w, const uint32_t* ibm_bits, int B, int64_t L,
                                    int n_fft, int hop, const AvzMvdrCfg* cfg, float* out, float* peak, void* stream);
 
+/* Pass A for a pass B that applies AVZ_POST_ONE_MINUS_NOISE with these same ibm_bits (the oracle path): dense layout
+ * as avz_ibm_cov_keep_f32, but a 32-byte sector of the kept spectrum (the slots of two adjacent bins) whose two bins are
+ * both noise-dominated is not written - pass B multiplies whatever sits there by the gain 0.  `spec` must therefore hold
+ * finite values before its first use (zero it ONCE after allocating it; later calls find the previous call's finite
+ * spectra there) - a NaN / Inf left in it would surface as NaN in the output, loudly, never as a wrong number.  Read back
+ * with avz_mvdr_apply_kept_f32 (post-filter AVZ_POST_ONE_MINUS_NOISE only: any other post-filter on such a buffer is
+ * detected on the device and yields NaN).  Same bits out; about 45 % of pass A's store stream - which is what bounds it -
+ * is never sent to HBM. */
+AVZ_API int avz_ibm_cov_keep_postmask_f32(const float* mix, const float* tgt, const float* itf, int B, int64_t L, int n_fft,
+                                  int hop, float norm_eps, uint32_t* ibm_bits, float* R, float* msum, void* ws, void* spec,
+                                  void* stream);
+
 /* Same as avz_mvdr_apply_kept_f32 plus the peak normalisation of oracle_debug.py:94 fused in: the thread blocks of an
  * utterance run as one cluster, agree on max|x| through distributed shared memory and divide their own output range
  * by (peak + peak_eps) while it is still in L2 (more than 8 blocks per utterance: a separate pass follows instead).
@@ -204,8 +216,8 @@ AVZ_API int avz_mvdr_apply_kept_norm_f32(const void* spec, const float* w, const
  * NULL: no kept spectrum), and the block that finishes an utterance's last frame chunk also sums the chunk partials
  * (oracle_debug.py:60-64) and solves the 257 2x2 systems (oracle_debug.py:68-79) - R, msum and w come out of the one
  * launch, bit-identical to avz_ibm_cov_keep_f32 + avz_mvdr_weights_f32.  Two launches fewer per step (measured: no gain,
- * profiles/README.md).  dvec [257,2] complex64; sparse != 0: the kept spectrum is sparse (see
- * avz_ibm_cov_keep_sparse_f32). */
+ * profiles/README.md).  dvec [257,2] complex64; sparse: 0 dense kept spectrum, 1 as avz_ibm_cov_keep_sparse_f32,
+ * 2 as avz_ibm_cov_keep_postmask_f32. */
 AVZ_API int avz_ibm_cov_weights_keep_f32(const float* mix, const float* tgt, const float* itf, int B, int64_t L, int n_fft,
                                  int hop, const AvzMvdrCfg* cfg, const float* dvec, uint32_t* ibm_bits, float* R,
                                  float* msum, float* w, void* ws, void* spec, int sparse, void* stream);

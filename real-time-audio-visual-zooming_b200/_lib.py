@@ -72,6 +72,7 @@ SIGNATURES = {
     "avz_mvdr_apply_kept_f32": (_i, [_p, _p, _p, _p, _i, _l, _i, _i, C.POINTER(AvzMvdrCfg), _p, _p, _p]),
     "avz_mvdr_apply_kept_norm_f32": (_i, [_p, _p, _p, _p, _i, _l, _i, _i, C.POINTER(AvzMvdrCfg), _f, _p, _p, _p]),
     "avz_ibm_cov_weights_keep_f32": (_i, [_p, _p, _p, _i, _l, _i, _i, C.POINTER(AvzMvdrCfg), _p, _p, _p, _p, _p, _p, _p, _i, _p]),
+    "avz_ibm_cov_keep_postmask_f32": (_i, [_p, _p, _p, _i, _l, _i, _i, _f, _p, _p, _p, _p, _p, _p]),
     "avz_ibm_cov_keep_sparse_f32": (_i, [_p, _p, _p, _i, _l, _i, _i, _f, _p, _p, _p, _p, _p, _p]),
     "avz_mvdr_apply_kept_sparse_f32": (_i, [_p, _p, _p, _i, _l, _i, _i, C.POINTER(AvzMvdrCfg), _p, _p, _p]),
     "avz_oracle_fused_ws_bytes": (_l, [_i, _l, _i, _i]),

@@ -770,6 +770,18 @@ int avz_ibm_cov_keep_sparse_f32(const float* mix, const float* tgt, const float*
                        (cudaStream_t)stream, 1);
 }
 
+int avz_ibm_cov_keep_postmask_f32(const float* mix, const float* tgt, const float* itf, int B, int64_t L, int n_fft, int hop,
+                                  float norm_eps, uint32_t* ibm_bits, float* R, float* msum, void* ws, void* spec,
+                                  void* stream) {
+  if (!mix || !tgt || !itf || !ibm_bits || !R || !msum || !ws || !spec || B <= 0 || B > 65535)
+    return set_error(AVZ_EINVAL, "avz_ibm_cov_keep_postmask_f32: null pointer or empty batch");
+  int rc = check_fft_args(n_fft, hop, L);
+  if (rc) return rc;
+  if (!use_opt512(n_fft, hop)) return set_error(AVZ_EINVAL, "avz_ibm_cov_keep_postmask_f32: n_fft 512, hop 128/256 only");
+  return launch_cov512(mix, tgt, itf, nullptr, B, L, hop, 0.f, norm_eps, ibm_bits, R, msum, ws, spec,
+                       (cudaStream_t)stream, 2);
+}
+
 int avz_wave_mask_cov_keep_f32(const float* mix, const float* mask, int B, int64_t L, int n_fft, int hop, float sqrt_eps,
                                float norm_eps, float* R, float* msum, void* ws, void* spec, void* stream) {
   if (!mix || !mask || !R || !msum || !ws || !spec || B <= 0 || B > 65535)
@@ -862,12 +874,13 @@ int avz_ibm_cov_weights_keep_f32(const float* mix, const float* tgt, const float
   if (rc) return rc;
   if (!use_opt512(n_fft, hop))
     return set_error(AVZ_EINVAL, "avz_ibm_cov_weights_keep_f32: n_fft 512 with hop 128 or 256 only");
+  if (sparse < 0 || sparse > 2) return set_error(AVZ_EINVAL, "avz_ibm_cov_weights_keep_f32: sparse must be 0, 1 or 2");
   CovTailArgs tail{dvec, R, msum, w, cfg, cfg->norm_eps};
   int chunks = 0;
   return (hop == 128) ? o512::launch_ibm_cov<128>(mix, tgt, itf, nullptr, B, L, 0.f, ibm_bits, (float*)ws, &chunks, spec,
-                                                  (cudaStream_t)stream, &tail, sparse ? 1 : 0)
+                                                  (cudaStream_t)stream, &tail, sparse)
                       : o512::launch_ibm_cov<256>(mix, tgt, itf, nullptr, B, L, 0.f, ibm_bits, (float*)ws, &chunks, spec,
-                                                  (cudaStream_t)stream, &tail, sparse ? 1 : 0);
+                                                  (cudaStream_t)stream, &tail, sparse);
 }
 
 // ---- the whole oracle path in two small launches + one persistent kernel (n_fft 512, hop 128 / 256)

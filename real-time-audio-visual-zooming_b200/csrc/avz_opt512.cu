@@ -451,7 +451,12 @@ k_mask_transpose(const float* __restrict__ mask, float* __restrict__ mask_t, int
 // This trades 64 B/sample of spare HBM bandwidth for ~30 % fewer instructions on an issue-bound path.
 // L2KEEP: the kept spectrum is written with ordinary stores (it is read back out of L2 by the same launch: k512_fused)
 // instead of streaming (evict-first) stores.  (b, chunk, chunks) = (blockIdx.y, blockIdx.x, gridDim.x) of the plain launch.
-template <int HOP, int WMODE, bool L2KEEP, bool SPARSE>
+// KMODE (how the spectrum is kept, W_BITS only): 0 every slot; 1 sparse (compacted, see below); 2 dense layout, but a
+// 32-byte sector (the slots of two adjacent lanes) whose two bins are both noise-dominated is not written - pass B, which
+// must then apply the post-filter 1 - noise mask with the same bits, multiplies whatever sits there by zero: the buffer has
+// to hold finite values from the start (zero it once; a NaN left in it would surface in the output, loudly).
+enum { KEEP_ALL = 0, KEEP_SPARSE = 1, KEEP_SKIP = 2 };
+template <int HOP, int WMODE, bool L2KEEP, int KMODE>
 __device__ __forceinline__ void cov_body(unsigned char* smem_raw, int b, int chunk, int chunks,
                                          const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits,
                                          const float* __restrict__ mask, MaskLayout ml, int L, int T, int frames_per_cta,
@@ -486,12 +491,13 @@ __device__ __forceinline__ void cov_body(unsigned char* smem_raw, int b, int chu
     win.load_all(m0, m1, L, ta, lane);
     // noise weights of this lane's bins, fetched one frame ahead
     FrameBits nb;
-    LaneBits lq;      // SPARSE: the same bits in (slot, lane) order
+    unsigned pairkeep = 0xffu;
+    LaneBits lq;      // (KMODE == KEEP_SPARSE): the same bits in (slot, lane) order
     float nmask[9];
     const uint32_t* bw = (WMODE == W_BITS) ? ibm_bits + ((int64_t)b * T + ta) * kFW : nullptr;
-    const uint32_t* lw = SPARSE ? lane_bits + ((int64_t)b * T + ta) * 8 : nullptr;
+    const uint32_t* lw = (KMODE == KEEP_SPARSE) ? lane_bits + ((int64_t)b * T + ta) * 8 : nullptr;
     const float* mk = (WMODE == W_MASK) ? mask + (int64_t)b * ml.sb + (int64_t)ta * ml.st : nullptr;
-    if (SPARSE) {
+    if ((KMODE == KEEP_SPARSE)) {
       lq.load(lw, bw);
     } else if (WMODE == W_BITS) {
       nb.load(bw, ln.h);
@@ -503,7 +509,7 @@ __device__ __forceinline__ void cov_body(unsigned char* smem_raw, int b, int chu
 #pragma unroll 1
     for (int t = ta; t < tb_; ++t) {
       float mw[8], mny;
-      if (SPARSE) {
+      if ((KMODE == KEEP_SPARSE)) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) mw[j] = lq.bit(j, lane) ? 1.f : 0.f;
         mny = (lq.ny & 1u) ? 1.f : 0.f;
@@ -511,6 +517,13 @@ __device__ __forceinline__ void cov_body(unsigned char* smem_raw, int b, int chu
 #pragma unroll
         for (int j = 0; j < 8; ++j) mw[j] = nb.bit(j, ln.k1) ? 1.f : 0.f;
         mny = (nb.ny & 1u) ? 1.f : 0.f;
+        if (KMODE == KEEP_SKIP) {   // bit j: the sector of lanes (k1 & ~1, k1 | 1) of slot j has a bin pass B will use
+          pairkeep = 0u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            pairkeep |= ((((nb.w[j >> 1] >> ((ln.k1 & ~1) + 16 * (j & 1))) & 3u) != 3u) ? 1u : 0u) << j;
+          if (lane < 2 && !(nb.ny & 1u)) pairkeep |= 1u;   // slot (0, lane 0) also carries the Nyquist bin
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) mw[j] = 1.f - nmask[j];
@@ -518,7 +531,7 @@ __device__ __forceinline__ void cov_body(unsigned char* smem_raw, int b, int chu
       }
       if (t + 1 < tb_) {
         win.prefetch(m0, m1, L, t + 1, lane);
-        if (SPARSE) {
+        if ((KMODE == KEEP_SPARSE)) {
           // the next frame's bits are fetched after this frame's keep masks have been used (below)
         } else if (WMODE == W_BITS) {
           bw += kFW;
@@ -555,9 +568,9 @@ __device__ __forceinline__ void cov_body(unsigned char* smem_raw, int b, int chu
             q.z = v[8].x;
             q.w = v[8].y;
           }
-          const unsigned bal = SPARSE ? lq.keep(j) : kFull;    // lanes of this slot that are kept
-          const bool keep = (bal >> lane) & 1u;
-          float4* dst = SPARSE ? sp + base + __popc(bal & lt) : sp + 32 * j + lane;
+          const unsigned bal = (KMODE == KEEP_SPARSE) ? lq.keep(j) : kFull;    // lanes of this slot that are kept
+          const bool keep = (KMODE == KEEP_SKIP) ? ((pairkeep >> j) & 1u) : ((bal >> lane) & 1u);
+          float4* dst = (KMODE == KEEP_SPARSE) ? sp + base + __popc(bal & lt) : sp + 32 * j + lane;
           base += __popc(bal);
           if (keep) {
             if (L2KEEP) *dst = q;
@@ -565,7 +578,7 @@ __device__ __forceinline__ void cov_body(unsigned char* smem_raw, int b, int chu
           }
         }
       }
-      if (SPARSE && t + 1 < tb_) {
+      if ((KMODE == KEEP_SPARSE) && t + 1 < tb_) {
         bw += kFW;
         lw += 8;
         lq.load(lw, bw);
@@ -678,14 +691,14 @@ struct CovTail {
   int sparse;
   const uint32_t* lane_bits;
 };
-template <int HOP, bool SPARSE>
+template <int HOP, int KMODE>
 __global__ void __launch_bounds__(kWarps * 32, AVZ_MINB_COV)
 k512_cov_w(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, int L, int T, int frames_per_cta,
            float* __restrict__ part, float4* __restrict__ spec, CovTail tail, Tables tb) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ int s_last;
-  if (tail.shdr != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) tail.shdr[3] = SPARSE ? 1u : 0u;
-  cov_body<HOP, W_BITS, false, SPARSE>(smem_raw, blockIdx.y, blockIdx.x, gridDim.x, mix, ibm_bits, nullptr,
+  if (tail.shdr != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) tail.shdr[3] = (uint32_t)KMODE;
+  cov_body<HOP, W_BITS, false, KMODE>(smem_raw, blockIdx.y, blockIdx.x, gridDim.x, mix, ibm_bits, nullptr,
                                        MaskLayout{0, 0, 0, nullptr, 0u, 0u}, L, T, frames_per_cta, 0.f, part, spec, blockIdx.y,
                                        tail.lane_bits, tb);
   __threadfence();
@@ -697,14 +710,14 @@ k512_cov_w(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits,
   finalize_weights_utt(part, blockIdx.y, gridDim.x, tail.norm_eps, tail.dvec, tail.cfg, tail.R, tail.msum, tail.w);
 }
 
-template <int HOP, int WMODE, bool SPARSE>
+template <int HOP, int WMODE, int KMODE>
 __global__ void __launch_bounds__(kWarps * 32, AVZ_MINB_COV)
 k512_cov(const float* __restrict__ mix, const uint32_t* __restrict__ ibm_bits, const float* __restrict__ mask,
          MaskLayout ml, int L, int T, int frames_per_cta, float sqrt_eps, float* __restrict__ part,
          float4* __restrict__ spec, uint32_t* __restrict__ shdr, const uint32_t* __restrict__ lane_bits, Tables tb) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  if (WMODE == W_BITS && shdr != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) shdr[3] = SPARSE ? 1u : 0u;
-  cov_body<HOP, WMODE, false, SPARSE>(smem_raw, blockIdx.y, blockIdx.x, gridDim.x, mix, ibm_bits, mask, ml, L, T, frames_per_cta,
+  if (WMODE == W_BITS && shdr != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) shdr[3] = (uint32_t)KMODE;
+  cov_body<HOP, WMODE, false, KMODE>(smem_raw, blockIdx.y, blockIdx.x, gridDim.x, mix, ibm_bits, mask, ml, L, T, frames_per_cta,
                                       sqrt_eps, part, spec, blockIdx.y, lane_bits, tb);
 }
 
@@ -774,7 +787,8 @@ __device__ __forceinline__ void apply_body(unsigned char* smem_raw, int b, int b
     // a staged mask copy that is not there (header mismatch) poisons the weights: the output is NaN, not garbage
     // ... and so does a kept spectrum whose layout (dense / sparse) is not the one this call was told to read
     const bool staged_ok = (ml.hdr == nullptr || (ml.hdr[0] == kMaskMagic && ml.hdr[1] == ml.B && ml.hdr[2] == ml.T)) &&
-                           (!KEPT || shdr == nullptr || shdr[3] == (SPARSE ? 1u : 0u));
+                           (!KEPT || shdr == nullptr ||
+                            (SPARSE ? shdr[3] == 1u : (shdr[3] == 0u || (gain_mode == GAIN_BITS && shdr[3] == 2u))));
     const float sc = staged_ok ? 0.5f / (float)kN : __int_as_float(0x7fc00000);
     for (int k = threadIdx.x; k < kF; k += kWarps * 32) {
       const float2 w0 = wgt[((int64_t)b * kF + k) * 2 + 0];
@@ -1024,6 +1038,7 @@ __device__ __forceinline__ void apply_body(unsigned char* smem_raw, int b, int b
           s2 = fma2(pk2(-zlo[j].y, zlo[j].x), pk2(ab.y, ab.y), s2);
           s2 = fma2(pk2(ab.z, ab.w), pk2(mir[j].x, mir[j].x), s2);
           s2 = fma2(pk2(ab.w, -ab.z), pk2(mir[j].y, mir[j].y), s2);
+          // (a sector pass A did not write - KEEP_SKIP - holds whatever finite value sat there: times gain 0)
           S[j] = up2(mul2(s2, pk2(gj[j], gj[j])));
         }
         const float4 abn = s_ab[256];
@@ -1231,7 +1246,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) k512_fused(FusedArgs a) {
     const int ring = u % a.nslot;
     if (is_a) {
       if (u >= a.nslot) spin_until(b_done + (u - a.nslot), a.CB, 0, u);   // the ring slot's previous utterance has been consumed
-      cov_body<HOP, W_BITS, true, false>(smem_raw, u, c, a.CA, a.mix, a.ibm_bits, nullptr, MaskLayout{0, 0, 0, nullptr, 0u, 0u},
+      cov_body<HOP, W_BITS, true, KEEP_ALL>(smem_raw, u, c, a.CA, a.mix, a.ibm_bits, nullptr, MaskLayout{0, 0, 0, nullptr, 0u, 0u},
                                          a.L, a.T, a.fpt, 0.f, a.part, a.spec, ring, nullptr, a.tb);
       __threadfence();
       __syncthreads();
@@ -1395,7 +1410,7 @@ int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const f
     AVZ_CUDA_OK(cudaFuncSetAttribute(k512_ibm<HOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
     prof_begin(PROF_IBM, st);
     // sparse kept spectrum: the bits are also kept in (slot, lane) order, in the (unused) mask region of `spec`
-    uint32_t* lane_bits = (spec && sparse) ? reinterpret_cast<uint32_t*>(static_cast<unsigned char*>(spec) + spec_mask_offset(B, T))
+    uint32_t* lane_bits = (spec && sparse == KEEP_SPARSE) ? reinterpret_cast<uint32_t*>(static_cast<unsigned char*>(spec) + spec_mask_offset(B, T))
                                            : nullptr;
     k512_ibm<HOP><<<grid, kWarps * 32, smem_fft, st>>>(tgt, itf, (int)L, T, fpc, ibm_bits, lane_bits, al, ibm_tol2(), tb);
     prof_end(PROF_IBM, st);
@@ -1405,7 +1420,7 @@ int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const f
     prof_end(PROF_FIXUP, st);
     AVZ_LAUNCH_OK("k512_ibm_fixup");
   }
-  const uint32_t* lane_bits_c = (spec && sparse && mask == nullptr)
+  const uint32_t* lane_bits_c = (spec && sparse == KEEP_SPARSE && mask == nullptr)
                                     ? reinterpret_cast<const uint32_t*>(static_cast<unsigned char*>(spec) + spec_mask_offset(B, T))
                                     : nullptr;
   const size_t smem_cov = smem_fft + (size_t)kWarps * 5 * kFP * sizeof(float);
@@ -1421,36 +1436,26 @@ int launch_ibm_cov(const float* mix, const float* tgt, const float* itf, const f
     ct.cfg = *tail->cfg;
     ct.norm_eps = tail->norm_eps;
     ct.shdr = spec ? spec_hdr(spec, B, T) : nullptr;
-    ct.sparse = (spec && sparse) ? 1 : 0;
+    ct.sparse = spec ? sparse : 0;
     ct.lane_bits = lane_bits_c;
-    if (ct.sparse) {
-      AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov_w<HOP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
-      k512_cov_w<HOP, true><<<grid, kWarps * 32, smem_cov, st>>>(mix, ibm_bits, (int)L, T, fpc, part,
-                                                                 reinterpret_cast<float4*>(spec), ct, tb);
-    } else {
-      AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov_w<HOP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
-      k512_cov_w<HOP, false><<<grid, kWarps * 32, smem_cov, st>>>(mix, ibm_bits, (int)L, T, fpc, part,
-                                                                  reinterpret_cast<float4*>(spec), ct, tb);
-    }
+    auto kern = (ct.sparse == KEEP_SPARSE) ? k512_cov_w<HOP, KEEP_SPARSE>
+              : (ct.sparse == KEEP_SKIP)   ? k512_cov_w<HOP, KEEP_SKIP> : k512_cov_w<HOP, KEEP_ALL>;
+    AVZ_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
+    kern<<<grid, kWarps * 32, smem_cov, st>>>(mix, ibm_bits, (int)L, T, fpc, part, reinterpret_cast<float4*>(spec), ct, tb);
   } else if (mask == nullptr) {
     uint32_t* shdr = spec ? spec_hdr(spec, B, T) : nullptr;
-    if (spec && sparse) {
-      AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov<HOP, W_BITS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
-      k512_cov<HOP, W_BITS, true><<<grid, kWarps * 32, smem_cov, st>>>(mix, ibm_bits, nullptr, MaskLayout{0, 0, 0, nullptr, 0u, 0u},
-                                                                       (int)L, T, fpc, 0.f, part, reinterpret_cast<float4*>(spec),
-                                                                       shdr, lane_bits_c, tb);
-    } else {
-      AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov<HOP, W_BITS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
-      k512_cov<HOP, W_BITS, false><<<grid, kWarps * 32, smem_cov, st>>>(mix, ibm_bits, nullptr, MaskLayout{0, 0, 0, nullptr, 0u, 0u},
-                                                                        (int)L, T, fpc, 0.f, part, reinterpret_cast<float4*>(spec),
-                                                                        shdr, nullptr, tb);
-    }
+    const int km = spec ? sparse : 0;
+    auto kern = (km == KEEP_SPARSE) ? k512_cov<HOP, W_BITS, KEEP_SPARSE>
+              : (km == KEEP_SKIP)   ? k512_cov<HOP, W_BITS, KEEP_SKIP> : k512_cov<HOP, W_BITS, KEEP_ALL>;
+    AVZ_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
+    kern<<<grid, kWarps * 32, smem_cov, st>>>(mix, ibm_bits, nullptr, MaskLayout{0, 0, 0, nullptr, 0u, 0u}, (int)L, T, fpc, 0.f,
+                                              part, reinterpret_cast<float4*>(spec), shdr, lane_bits_c, tb);
   } else {
-    AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov<HOP, W_MASK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
+    AVZ_CUDA_OK(cudaFuncSetAttribute(k512_cov<HOP, W_MASK, KEEP_ALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cov));
     MaskLayout ml;
     const float* mptr = stage_mask(mask, spec, B, T, &ml, st);
     AVZ_LAUNCH_OK("k_mask_transpose");
-    k512_cov<HOP, W_MASK, false><<<grid, kWarps * 32, smem_cov, st>>>(mix, nullptr, mptr, ml, (int)L, T, fpc, sqrt_eps, part,
+    k512_cov<HOP, W_MASK, KEEP_ALL><<<grid, kWarps * 32, smem_cov, st>>>(mix, nullptr, mptr, ml, (int)L, T, fpc, sqrt_eps, part,
                                                                       reinterpret_cast<float4*>(spec), nullptr, nullptr, tb);
   }
   prof_end(PROF_COV, st);
@@ -1485,7 +1490,7 @@ int launch_apply(const float* mix, const void* spec, const float* w, const uint3
   }
   prof_begin(PROF_APPLY, st);
   if (spec != nullptr) {
-    const bool sp_on = sparse && gain_mode == GAIN_BITS;
+    const bool sp_on = sparse == KEEP_SPARSE && gain_mode == GAIN_BITS;
     auto kern = sp_on ? k512_apply<HOP, true, true> : k512_apply<HOP, true, false>;
     AVZ_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // fused normalisation: the CTAs of an utterance run as one thread-block cluster (portable size limit 8)
@@ -1503,8 +1508,7 @@ int launch_apply(const float* mix, const void* spec, const float* w, const uint3
     lc.attrs = at;
     lc.numAttrs = 1;
     // the header word that records the layout is written by the IBM pass A only: a float-mask pass B does not look at it
-    const uint32_t* shdr = (gain_mode == GAIN_BITS || gain_mode == GAIN_NONE) && !mask_staged ? spec_hdr(spec, B, T) : nullptr;
-    if (gain_mode == GAIN_NONE) shdr = nullptr;   // AVZ_POST_NONE may follow either pass A
+    const uint32_t* shdr = spec_hdr(spec, B, T);
     AVZ_CUDA_OK(cudaLaunchKernelEx(&lc, kern, (const float*)nullptr, reinterpret_cast<const float4*>(spec),
                                    reinterpret_cast<const float2*>(w), ibm_bits, mptr, ml, gain_mode, post_floor, (int)L, T,
                                    bpc, out, peak, cluster_norm, peak_eps, shdr,

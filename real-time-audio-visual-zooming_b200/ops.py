@@ -479,7 +479,7 @@ def alloc_kept_spectrum(mix: torch.Tensor, cfg: MvdrConfig, ibm: bool = False) -
 
 
 def ibm_covariance(mix: torch.Tensor, tgt: torch.Tensor, itf: torch.Tensor, cfg: MvdrConfig,
-                   spec: Optional[torch.Tensor] = None, sparse: bool = False):
+                   spec: Optional[torch.Tensor] = None, sparse: bool = False, postmask: bool = False):
     """Pass A (oracle_debug.py:42-64) without storing any spectrum - or, with `spec` (alloc_kept_spectrum), keeping
     the packed mix spectrum so that pass B can skip its forward transform.
     mix [B,2,L], tgt [B,L], itf [B,L] -> (ibm_bits [B,T,ceil(F/32)] int32, R packed [B,F,4], msum [B,F])."""
@@ -501,6 +501,12 @@ def ibm_covariance(mix: torch.Tensor, tgt: torch.Tensor, itf: torch.Tensor, cfg:
         _lib.check(lib.avz_ibm_cov_keep_sparse_f32(_ptr(mix), _ptr(tgt), _ptr(itf), B, L, cfg.n_fft, cfg.hop,
                                                    float(cfg.norm_eps), _ptr(bits), _ptr(Rp), _ptr(ms), _ptr(ws), _ptr(spec),
                                                    _stream()), "avz_ibm_cov_keep_sparse_f32")
+    elif spec is not None and postmask:
+        # pass B will apply 1 - noise mask with these bits: sectors it zeroes anyway are not written (mvdr_apply as usual);
+        # `spec` must have been zeroed once (pipeline.OracleMvdr does) - see avz_ibm_cov_keep_postmask_f32
+        _lib.check(lib.avz_ibm_cov_keep_postmask_f32(_ptr(mix), _ptr(tgt), _ptr(itf), B, L, cfg.n_fft, cfg.hop,
+                                                     float(cfg.norm_eps), _ptr(bits), _ptr(Rp), _ptr(ms), _ptr(ws), _ptr(spec),
+                                                     _stream()), "avz_ibm_cov_keep_postmask_f32")
     elif spec is not None:
         _lib.check(lib.avz_ibm_cov_keep_f32(_ptr(mix), _ptr(tgt), _ptr(itf), B, L, cfg.n_fft, cfg.hop,
                                             float(cfg.norm_eps), _ptr(bits), _ptr(Rp), _ptr(ms), _ptr(ws), _ptr(spec),
@@ -612,7 +618,7 @@ def oracle_mask_mvdr(mix, tgt, itf, cfg: MvdrConfig = PRESETS["baseline_oracle"]
     mix, tgt, itf, single = _batchify(mix, tgt, itf, io)
     spec = alloc_kept_spectrum(mix, cfg, ibm=True)
     sparse = False      # the sparse kept spectrum saves 60 % of the traffic but costs more than it saves (pipeline.OracleMvdr)
-    bits, Rp, ms = ibm_covariance(mix, tgt, itf, cfg, spec, sparse=sparse)
+    bits, Rp, ms = ibm_covariance(mix, tgt, itf, cfg, spec, sparse=sparse)   # (spec is fresh, uninitialised memory: no postmask)
     w = mvdr_weights(Rp, steering_vectors(cfg, mix.device), cfg)
     out, peak = mvdr_apply(mix, w, cfg, ibm_bits=bits if cfg.post == "one_minus_noise" else None, spec=spec, sparse=sparse)
     parts = None

@@ -25,7 +25,8 @@ class OracleMvdr:
     launches_per_step = 7
 
     def __init__(self, cfg: MvdrConfig, B: int, L: int, device, keep_spectrum: bool = True, fused_norm: bool = False,
-                 fused: bool = False, fold_weights: bool = False, sparse_spectrum: bool = False):
+                 fused: bool = False, fold_weights: bool = False, sparse_spectrum: bool = False,
+                 skip_masked_stores: bool = True):
         """`fused`: run pass A, the weights, pass B and the normalisation as ONE persistent kernel whose kept spectrum
         stays in L2 (avz_oracle_fused_f32; n_fft 512, IBM post-filter or none) instead of five separate launches."""
         self.cfg, self.B, self.L, self.device = cfg, B, L, device
@@ -46,7 +47,8 @@ class OracleMvdr:
         self.ws = torch.empty((max(int(nws), 4),), dtype=torch.uint8, device=device)
         # pass A may keep the packed mix spectrum so that pass B skips its forward transform (fast path only)
         nspec = self.lib.avz_spec_ws_bytes(B, L, cfg.n_fft, cfg.hop) if keep_spectrum and cfg.n_fft == 512 else 0
-        self.spec = torch.empty((int(nspec),), dtype=torch.uint8, device=device) if nspec > 0 else None
+        # zeroed once: the store-skipping pass A (below) leaves sectors unwritten that pass B multiplies by a gain of 0
+        self.spec = torch.zeros((int(nspec),), dtype=torch.uint8, device=device) if nspec > 0 else None
         # fused_norm: the thread blocks of an utterance run as one cluster, exchange their maxima through distributed
         # shared memory and each rescales the range it has just written while it is still in L2 (one launch less,
         # bit-identical output).  Measured on B200 at config 2 it LOSES: pass B 0.50 -> 0.68 ms against the 0.09 ms of
@@ -62,6 +64,10 @@ class OracleMvdr:
         # instructions per frame, and both kernels are then issue-bound: 0.64 + 0.69 ms against 0.57 + 0.47 dense
         # (profiles/README.md).  Off by default.
         self.sparse = bool(sparse_spectrum) and self.spec is not None and cfg.post == "one_minus_noise" and not self.fused_norm
+        # ... what does pay: the dense layout with the stores of sectors pass B will zero anyway left out
+        # (avz_ibm_cov_keep_postmask_f32): about half of pass A's store stream never goes to HBM
+        self.skip = (bool(skip_masked_stores) and self.spec is not None and cfg.post == "one_minus_noise"
+                     and cfg.n_fft == 512 and not self.sparse)
         # n_fft 512 fast path: finalize + weights folded into pass A's last block per utterance (two launches fewer,
         # bit-identical).  Measured on B200 it does not pay: a single block per utterance is slower at the tail than the
         # two small parallel kernels it replaces (config 2: 1.699 vs 1.696 ms per step; one 5 s utterance as a CUDA
@@ -86,13 +92,20 @@ class OracleMvdr:
             _lib.check(self.lib.avz_ibm_cov_weights_keep_f32(_ptr(mix), _ptr(tgt), _ptr(itf), self.B, self.L, c.n_fft, c.hop,
                                                              C.byref(self.cc), _ptr(self.d), _ptr(self.bits), _ptr(self.R),
                                                              _ptr(self.msum), _ptr(self.w), _ptr(self.ws), _ptr(self.spec),
-                                                             int(self.sparse), _stream()), "avz_ibm_cov_weights_keep_f32")
+                                                             1 if self.sparse else (2 if self.skip else 0), _stream()),
+                       "avz_ibm_cov_weights_keep_f32")
             return
         if self.spec is not None and self.sparse:
             _lib.check(self.lib.avz_ibm_cov_keep_sparse_f32(_ptr(mix), _ptr(tgt), _ptr(itf), self.B, self.L, c.n_fft, c.hop,
                                                             float(c.norm_eps), _ptr(self.bits), _ptr(self.R), _ptr(self.msum),
                                                             _ptr(self.ws), _ptr(self.spec), _stream()),
                        "avz_ibm_cov_keep_sparse_f32")
+            return
+        if self.spec is not None and self.skip:
+            _lib.check(self.lib.avz_ibm_cov_keep_postmask_f32(_ptr(mix), _ptr(tgt), _ptr(itf), self.B, self.L, c.n_fft, c.hop,
+                                                              float(c.norm_eps), _ptr(self.bits), _ptr(self.R), _ptr(self.msum),
+                                                              _ptr(self.ws), _ptr(self.spec), _stream()),
+                       "avz_ibm_cov_keep_postmask_f32")
             return
         if self.spec is not None:
             _lib.check(self.lib.avz_ibm_cov_keep_f32(_ptr(mix), _ptr(tgt), _ptr(itf), self.B, self.L, c.n_fft, c.hop,

@@ -560,3 +560,38 @@ def test_sparse_kept_spectrum_is_bit_identical_and_mismatch_is_loud(az):
         sparse.sparse = False
         sparse.pass_b(mix_d)
         assert bool(torch.isnan(sparse.out).all())
+
+
+def test_postmask_store_skipping_is_bit_identical_and_guarded(az):
+    """avz_ibm_cov_keep_postmask_f32 leaves out the stores of kept-spectrum sectors whose two bins pass B will zero:
+    same waveform bit for bit as the fully written spectrum and as the recomputing pass B, whatever finite values the
+    buffer held before; a pass B without the 1 - noise-mask post-filter on such a buffer gives NaN."""
+    import ctypes as C
+    import dataclasses
+    from avzoom import pipeline
+    for preset, B, dur in (("baseline_oracle", 6, 1.3), ("oracle_debug", 3, 2.0), ("baseline_oracle", 70, 0.6)):
+        cfg = az.PRESETS[preset]
+        mix, tgt, itf = synth(9, min(B, 8), dur, 3)
+        rep = (B + mix.shape[0] - 1) // mix.shape[0]
+        mix_d, tgt_d, itf_d = (torch.from_numpy(np.tile(a, (rep,) + (1,) * (a.ndim - 1))[:B].copy()).cuda() for a in (mix, tgt, itf))
+        L = mix.shape[-1]
+        full = pipeline.OracleMvdr(cfg, B, L, mix_d.device, skip_masked_stores=False)
+        skip = pipeline.OracleMvdr(cfg, B, L, mix_d.device)
+        reco = pipeline.OracleMvdr(cfg, B, L, mix_d.device, keep_spectrum=False)
+        assert skip.skip and not full.skip
+        # whatever finite values the buffer held before must not matter
+        skip.spec.view(torch.float32)[: (skip.spec.numel() // 4)].copy_(
+            (torch.rand(skip.spec.numel() // 4, device="cuda") - 0.5) * 1e30)
+        a, b, c = (e.run(mix_d, tgt_d, itf_d).clone() for e in (full, skip, reco))
+        assert bool(torch.isfinite(a).all()) and torch.equal(a, b) and torch.equal(a, c)
+        assert torch.equal(skip.run(mix_d, tgt_d, itf_d), a)        # and again on its own leftovers
+        assert torch.equal(az.oracle_mask_mvdr(mix_d, tgt_d, itf_d, cfg), a)
+        # the guard: the same buffer read by a pass B with no post-filter
+        skip.pass_a(mix_d, tgt_d, itf_d)
+        skip.weights()
+        none_cfg = dataclasses.replace(cfg, post="none").to_c()
+        out = torch.empty_like(skip.out)
+        az._lib.check(skip.lib.avz_mvdr_apply_kept_f32(az.ops._ptr(skip.spec), az.ops._ptr(skip.w), az.ops._ptr(None),
+                                                       az.ops._ptr(None), B, L, cfg.n_fft, cfg.hop, C.byref(none_cfg),
+                                                       az.ops._ptr(out), az.ops._ptr(None), az.ops._stream()), "apply")
+        assert bool(torch.isnan(out).all())
