@@ -354,10 +354,18 @@ AVZ_API int avz_sir_f32(const float* est, const float* tgt, const float* itf, in
  * (64000 = 512*125, 80000 = 128*625) runs the two-factor transform directly; every other length up to 262144 samples
  * (primes, odd lengths, ...) runs the same passes as a chirp-z (Bluestein) convolution of length M >= 2L-1 (one plan
  * per (device, L), built on the first call, which synchronises `stream` once).  Longer non-factorable lengths return
- * AVZ_EINVAL.  1 <= S <= 8.  ws: avz_farfield_mix_ws_bytes(B,S,L) bytes of device scratch (0 = unsupported shape). */
+ * AVZ_EINVAL.  1 <= S <= 8.  ws: avz_farfield_mix_ws_bytes(B,S,L) bytes of device scratch (0 = unsupported shape).
+ * S <= 4 and L = 4 * M with M <= 25600 a product of 2, 3, 5, 7 (64000, 80000, 16000, 4096 ...): ONE kernel, one 8-CTA
+ * thread-block cluster per utterance - the two complex planes stay in the cluster's shared memory from the load of the
+ * sources to the store of the normalised signals (in-place mixed-radix FFT whose first radix-4 stage runs across the
+ * CTAs through distributed shared memory); `ws` is not touched.  avz_farfield_mix_passes_f32 is the same operator
+ * always on the multi-pass path (what S > 4 and all other lengths use): same arguments, results equal to float32
+ * rounding of two different transform factorisations. */
 AVZ_API int64_t avz_farfield_mix_ws_bytes(int B, int S, int64_t L);
 AVZ_API int avz_farfield_mix_f32(const float* src, const double* delays_host, int B, int S, int64_t L, double fs,
                          float peak_eps, float* mix, float* tgt, float* itf, void* ws, void* stream);
+AVZ_API int avz_farfield_mix_passes_f32(const float* src, const double* delays_host, int B, int S, int64_t L, double fs,
+                                float peak_eps, float* mix, float* tgt, float* itf, void* ws, void* stream);
 
 /* ---- PCM16 wire format (soundfile semantics, oracle_debug.py:35-39,96): read = int16 / 32768 (exact in float32);
  * write = libsndfile's default PCM_16 conversion, round-half-even(x * 32767) (0x7FFF), clipped to [-32768, 32767].

@@ -88,6 +88,7 @@ SIGNATURES = {
     "avz_sir_f32": (_i, [_p, _p, _p, _i, _l, _l, _p, _p]),
     "avz_farfield_mix_ws_bytes": (_l, [_i, _i, _l]),
     "avz_farfield_mix_f32": (_i, [_p, C.POINTER(C.c_double), _i, _i, _l, C.c_double, _f, _p, _p, _p, _p, _p]),
+    "avz_farfield_mix_passes_f32": (_i, [_p, C.POINTER(C.c_double), _i, _i, _l, C.c_double, _f, _p, _p, _p, _p, _p]),
     "avz_chunk_features_f32": (_i, [_p, _i, C.POINTER(AvzChunkView), _l, _i, _i, _i, _p, _p]),
     "avz_chunk_mask_cov_f32": (_i, [_p, _p, _i, C.POINTER(AvzChunkView), _l, _i, _i, _f, _f, _p, _p, _p, _p, _p]),
     "avz_chunk_mvdr_apply_f32": (_i, [_p, _p, _p, _p, _i, C.POINTER(AvzChunkView), _l, _i, _i, C.POINTER(AvzMvdrCfg), _p, _p, _p]),

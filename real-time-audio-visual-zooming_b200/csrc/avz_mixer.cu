@@ -813,6 +813,15 @@ int blue_plan_for(int64_t L, const Split& sp, cudaStream_t st, const BluePlan** 
 }  // namespace
 }  // namespace avz
 
+#include "avz_mixer_cluster.cuh"   // k_mix_cluster: the whole mixer of one utterance inside one 8-CTA cluster
+
+namespace avz {
+namespace {
+int farfield_mix(const float* src, const double* delays_host, int B, int S, int64_t L, double fs, float peak_eps, float* mix,
+                 float* tgt, float* itf, void* ws, void* stream, bool allow_cluster);
+}  // namespace
+}  // namespace avz
+
 extern "C" {
 
 int64_t avz_farfield_mix_ws_bytes(int B, int S, int64_t L) {
@@ -827,7 +836,20 @@ int64_t avz_farfield_mix_ws_bytes(int B, int S, int64_t L) {
 
 int avz_farfield_mix_f32(const float* src, const double* delays_host, int B, int S, int64_t L, double fs,
                          float peak_eps, float* mix, float* tgt, float* itf, void* ws, void* stream) {
-  using namespace avz;
+  return avz::farfield_mix(src, delays_host, B, S, L, fs, peak_eps, mix, tgt, itf, ws, stream, true);
+}
+
+int avz_farfield_mix_passes_f32(const float* src, const double* delays_host, int B, int S, int64_t L, double fs,
+                                float peak_eps, float* mix, float* tgt, float* itf, void* ws, void* stream) {
+  return avz::farfield_mix(src, delays_host, B, S, L, fs, peak_eps, mix, tgt, itf, ws, stream, false);
+}
+
+}  // extern "C"
+
+namespace avz {
+namespace {
+int farfield_mix(const float* src, const double* delays_host, int B, int S, int64_t L, double fs, float peak_eps, float* mix,
+                 float* tgt, float* itf, void* ws, void* stream, bool allow_cluster) {
   if (!src || !delays_host || !mix || !tgt || !itf || !ws) return set_error(AVZ_EINVAL, "avz_farfield_mix_f32: null pointer");
   if (S < 1 || S > kMaxSrc) return set_error(AVZ_EINVAL, "avz_farfield_mix_f32: S=%d out of range (1..%d)", S, kMaxSrc);
   if (!(fs > 0.0)) return set_error(AVZ_EINVAL, "avz_farfield_mix_f32: fs must be positive");
@@ -836,6 +858,21 @@ int avz_farfield_mix_f32(const float* src, const double* delays_host, int B, int
   const int PP = P > 2 ? P : 2;
   if (B <= 0 || (int64_t)B * PP > 65535)
     return set_error(AVZ_EINVAL, "avz_farfield_mix_f32: B=%d out of range (B * max(2, ceil(S/2)) <= 65535)", B);
+  MixParams prm;
+  prm.S = S;
+  for (int s = 0; s < kMaxSrc; ++s) {
+    prm.c1[s] = s < S ? delays_host[2 * s] * fs / (double)L : 0.0;
+    prm.c2[s] = s < S ? delays_host[2 * s + 1] * fs / (double)L : 0.0;
+    // symmetric pair (far-field delays +-(d/2) cos(theta) / c; numpy's cos(theta - pi) and -cos(theta) differ in the last
+    // bit): the phase difference of treating them as exact negatives is < 1e-11 rad at any bin, far below float32
+    prm.sym[s] = (fabs(prm.c2[s] + prm.c1[s]) <= 1e-12 * fabs(prm.c1[s])) ? 1 : 0;
+  }
+  if (allow_cluster && S <= 4) {   // two complex planes: what one cluster holds on chip
+    const ClusterPlan* cp = nullptr;
+    const int rc = cluster_plan_for(L, &cp);
+    if (rc != AVZ_OK) return rc;
+    if (cp != nullptr) return launch_mix_cluster(cp, src, B, S, prm, peak_eps, mix, tgt, itf, st);
+  }
   Split sp;
   const bool native = split_length(L, &sp.N1, &sp.lg, &sp.N2);
   const BluePlan* bp = nullptr;
@@ -854,15 +891,6 @@ int avz_farfield_mix_f32(const float* src, const double* delays_host, int B, int
   float2* Z = (float2*)ws;                                   // [B][PP][M]
   float2* SP = native ? Z : Z + (int64_t)B * PP * M;         // Bluestein: spectra [B][PP][L] in natural bin order
   unsigned* peak = (unsigned*)((char*)ws + (int64_t)B * PP * (native ? L : M + L) * (int64_t)sizeof(float2));
-  MixParams prm;
-  prm.S = S;
-  for (int s = 0; s < kMaxSrc; ++s) {
-    prm.c1[s] = s < S ? delays_host[2 * s] * fs / (double)L : 0.0;
-    prm.c2[s] = s < S ? delays_host[2 * s + 1] * fs / (double)L : 0.0;
-    // symmetric pair (far-field delays +-(d/2) cos(theta) / c; numpy's cos(theta - pi) and -cos(theta) differ in the last
-    // bit): the phase difference of treating them as exact negatives is < 1e-11 rad at any bin, far below float32
-    prm.sym[s] = (fabs(prm.c2[s] + prm.c1[s]) <= 1e-12 * fabs(prm.c1[s])) ? 1 : 0;
-  }
   rc = set_mix_attrs(sp);
   if (rc != AVZ_OK) return rc;
   const size_t col_smem = sp.col_smem();
@@ -907,6 +935,10 @@ int avz_farfield_mix_f32(const float* src, const double* delays_host, int B, int
   }
   return AVZ_OK;
 }
+}  // namespace
+}  // namespace avz
+
+extern "C" {
 
 int avz_pcm16_to_f32(const int16_t* pcm, int64_t n, float* out, void* stream) {
   using namespace avz;

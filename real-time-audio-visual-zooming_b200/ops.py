@@ -399,12 +399,14 @@ def sir_scores(est, tgt, itf):
 
 
 # ------------------------------------------------------------------------------------------ mixer / wire format
-def far_field_mix(sources, delays_s, fs: float = 16000.0, peak_eps: Optional[float] = 1e-9):
+def far_field_mix(sources, delays_s, fs: float = 16000.0, peak_eps: Optional[float] = 1e-9, multi_pass: bool = False):
     """Far-field 2-mic mixtures on the device (tf_lite_version/world_building.py:61-93 without the file I/O).
 
     sources (B,S,L) or (S,L) float32, source 0 = target; delays_s (S,2) seconds per source and microphone
     (`world_building.calculate_far_field_delays`).  -> mix (B,2,L), tgt (B,L), itf (B,L) float32, all divided by
-    max|mix| + peak_eps per utterance (peak_eps=None: no division)."""
+    max|mix| + peak_eps per utterance (peak_eps=None: no division).
+    Up to 4 sources of a length L = 4 * (2, 3, 5, 7-smooth) <= 102 400 are mixed by one cluster-resident kernel (spectra
+    never leave the chip); anything else - or `multi_pass=True` - by the multi-pass transform through HBM."""
     io = _Io()
     src = io.take(sources, torch.float32)
     single = src.dim() == 2
@@ -420,9 +422,10 @@ def far_field_mix(sources, delays_s, fs: float = 16000.0, peak_eps: Optional[flo
     mix = torch.empty((B, 2, L), dtype=torch.float32, device=src.device)
     tgt = torch.empty((B, L), dtype=torch.float32, device=src.device)
     itf = torch.empty((B, L), dtype=torch.float32, device=src.device)
-    _lib.check(lib.avz_farfield_mix_f32(_ptr(src), dl.ctypes.data_as(C.POINTER(C.c_double)), B, S, L, float(fs),
-                                        -1.0 if peak_eps is None else float(peak_eps), _ptr(mix), _ptr(tgt), _ptr(itf),
-                                        _ptr(ws), _stream()), "avz_farfield_mix_f32")
+    fn = lib.avz_farfield_mix_passes_f32 if multi_pass else lib.avz_farfield_mix_f32
+    _lib.check(fn(_ptr(src), dl.ctypes.data_as(C.POINTER(C.c_double)), B, S, L, float(fs),
+                  -1.0 if peak_eps is None else float(peak_eps), _ptr(mix), _ptr(tgt), _ptr(itf), _ptr(ws), _stream()),
+               "avz_farfield_mix_f32")
     if single:
         mix, tgt, itf = mix[0], tgt[0], itf[0]
     return io.give(mix), io.give(tgt), io.give(itf)

@@ -185,3 +185,35 @@ def test_host_pipeline_pcm16_wire(az):
     assert np.allclose(sc.numpy(), ref_sc, atol=1e-3)
     with pytest.raises(az._lib.AvzError):
         hp.run(pin(mix), pin(tgt), pin(itf))                # float buffers on the int16 wire
+
+
+@pytest.mark.parametrize("B,S,L", [(5, 4, 64000), (2, 3, 80000), (3, 1, 16000), (2, 2, 4096), (1, 4, 96), (3, 3, 840),
+                                     (40, 4, 16000), (1, 4, 8), (2, 4, 96000)])
+def test_cluster_resident_mixer_against_oracle_and_multi_pass(az, B, S, L):
+    """The one-kernel mixer (8-CTA cluster per utterance, spectra on chip) and the multi-pass one are two float32
+    factorisations of the same transform: both within MIX_TOL of the float64 oracle, and of each other; more utterances
+    than clusters (B = 40) exercises the persistent loop; reruns are bit-identical."""
+    rng = np.random.default_rng(7 * S + L % 991)
+    src = rng.standard_normal((B, S, L)).astype(np.float32)
+    src[:, :, : L // 3] *= 0.05
+    delays = [O.far_field_delays(a, 0.04, 343.0) for a in ANGLES[:S]]
+    x = torch.from_numpy(src).cuda()
+    one = az.ops.far_field_mix(x, delays, 16000.0)
+    many = az.ops.far_field_mix(x, delays, 16000.0, multi_pass=True)
+    again = az.ops.far_field_mix(x, delays, 16000.0)
+    for u, v, w in zip(one, many, again):
+        assert torch.equal(u, w)
+        assert rel_l2(u.cpu().numpy(), v.cpu().numpy()) < MIX_TOL or float(v.abs().max()) < 1e-6
+    for b in sorted({0, B // 2, B - 1}):
+        rm, rt, ri = O.mix_far_field(list(src[b].astype(np.float64)), ANGLES[:S], 0.04, 343.0, 16000.0)
+        assert rel_l2(one[0][b].cpu().numpy(), rm) < MIX_TOL
+        assert rel_l2(one[1][b].cpu().numpy(), rt) < MIX_TOL
+        if S > 1:
+            assert rel_l2(one[2][b].cpu().numpy(), ri) < MIX_TOL
+        else:
+            assert float(one[2][b].abs().max()) < 1e-6
+        assert abs(float(one[0][b].abs().max()) - 1.0) < 1e-6
+    # no normalisation: plain delays (apply_frac_delay's use of the operator)
+    raw = az.ops.far_field_mix(x[:1], delays, 16000.0, peak_eps=None)
+    raw2 = az.ops.far_field_mix(x[:1], delays, 16000.0, peak_eps=None, multi_pass=True)
+    assert rel_l2(raw[0].cpu().numpy(), raw2[0].cpu().numpy()) < MIX_TOL
