@@ -42,10 +42,38 @@ struct ClStages {
   int tw_off[kClMaxStages];   // offset of the stage's twiddles [u-1][pos] in the table (stages with q == 1 have none)
   int pair_off[kClSize + 1];  // CTA r combines pairs [pair_off[r], pair_off[r + 1]) of the pair list
   int n_hi;                   // entries of a ramp table's coarse half: (L / 2 >> 8) + 1
+  int tw_sm[kClMaxStages];    // offset of the stage's twiddles in the shared-memory copy, -1: read from global memory
+  int tw_sm_n;                // entries of that copy (the small tables of the late stages)
 };
+constexpr int kTwSmemMax = 2560;   // 20 KB
+#ifndef AVZ_CL_CROSSU
+#define AVZ_CL_CROSSU 1
+#endif
+#ifndef AVZ_CL_PAIRU
+#define AVZ_CL_PAIRU 1
+#endif
+#ifndef AVZ_CL_U_SMALL
+#define AVZ_CL_U_SMALL 1
+#endif
+#ifndef AVZ_CL_U_8
+#define AVZ_CL_U_8 1
+#endif
+constexpr int kCrossU = AVZ_CL_CROSSU;    // cross-CTA butterflies a thread has in flight
+constexpr int kPairU = AVZ_CL_PAIRU;      // pairs of the combine step a thread has in flight
 constexpr int kRampLo = 256;  // exp(-2 pi i k c) = hi[k >> 8] * lo[k & 255]
 __host__ __device__ inline size_t cl_ramp_bytes(int n_hi) { return (size_t)2 * 4 * (kRampLo + n_hi) * sizeof(float2); }
 
+// Cluster barrier with release / acquire at cluster scope: what the phases need (a CTA's shared-memory writes visible
+// to its peers afterwards).  cooperative_groups' cluster.sync() adds a MEMBAR.ALL.GPU in front, 3-4 % of this kernel.
+__device__ __forceinline__ void cl_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// x / d for a loop-invariant d: r = RN(1 / d) once, then q = RN(x r), q' = RN(q + RN(x - q d) r) - Markstein's
+// correction step: the correctly rounded quotient (what __fdiv_rn gives) for three multiply-adds instead of a divide.
+__device__ __forceinline__ float div_by(float x, float d, float r) {
+  const float q = x * r;
+  return fmaf(fmaf(-q, d, x), r, q);
+}
 template <bool INV>
 __device__ __forceinline__ float2 mul_mi(float2 a) {   // * (-i) forward, * (+i) inverse
   return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
@@ -159,45 +187,83 @@ __device__ __forceinline__ void bfly(float2 (&v)[R]) {
   }
 }
 
-// One stage on a CTA's own M elements: butterflies over x[blk R q + pos + q t], t < R.
-template <int R, bool INV>
+// One stage on a CTA's own M elements: butterflies over x[blk R q + pos + q t], t < R.  A thread works on U butterflies
+// at a time - all their loads are issued before the first store (the transform is in place, and the compiler cannot
+// know that two butterflies never share an element): with four warps per scheduler it is memory-level parallelism
+// inside a thread, not occupancy, that hides the shared-memory and twiddle latencies.
+template <int R, bool INV, int U>
 __device__ __forceinline__ void cl_local_stage(float2* __restrict__ sm, int M, int q, const float2* __restrict__ tw) {
   const int nbf = M / R;
-  for (int idx = threadIdx.x; idx < nbf; idx += kClThreads) {
-    int blk = idx, pos = 0;
-    if (q > 1) {
-      blk = idx / q;
-      pos = idx - blk * q;
+  for (int i0 = threadIdx.x; i0 < nbf; i0 += U * kClThreads) {
+    float2 v[U][R];
+    float2* x[U];
+    int pos[U];
+#pragma unroll
+    for (int b = 0; b < U; ++b) {
+      int idx = i0 + b * kClThreads;
+      idx = idx < nbf ? idx : i0;          // a batch's missing tail repeats its first butterfly (loads only)
+      int blk = idx;
+      pos[b] = 0;
+      if (q > 1) {
+        blk = idx / q;
+        pos[b] = idx - blk * q;
+      }
+      x[b] = sm + blk * (R * q) + pos[b];
+#pragma unroll
+      for (int t = 0; t < R; ++t) v[b][t] = x[b][t * q];
     }
-    float2* x = sm + blk * (R * q) + pos;
-    float2 v[R];
 #pragma unroll
-    for (int t = 0; t < R; ++t) v[t] = x[t * q];
-    if (INV && q > 1) {
+    for (int b = 0; b < U; ++b) {
+      float2 w[R];
+      if (q > 1) {
+        if constexpr (R == 16) {
+          // W^{pos (4 u2 + u1)} = W^{4 pos u2} W^{pos u1}: six loads and nine products instead of fifteen loads
+          float2 w1[4], w4[4];
 #pragma unroll
-      for (int t = 1; t < R; ++t) v[t] = cmulc(v[t], __ldg(tw + (t - 1) * q + pos));
+          for (int j = 1; j < 4; ++j) {
+            w1[j] = tw[(j - 1) * q + pos[b]];
+            w4[j] = tw[(4 * j - 1) * q + pos[b]];
+          }
+#pragma unroll
+          for (int u = 1; u < 16; ++u) {
+            const int u1 = u & 3, u2 = u >> 2;
+            w[u] = (u2 == 0) ? w1[u1] : (u1 == 0 ? w4[u2] : cmul(w4[u2], w1[u1]));
+          }
+        } else {
+#pragma unroll
+          for (int u = 1; u < R; ++u) w[u] = tw[(u - 1) * q + pos[b]];
+        }
+      }
+      if (INV && q > 1) {
+#pragma unroll
+        for (int t = 1; t < R; ++t) v[b][t] = cmulc(v[b][t], w[t]);
+      }
+      bfly<R, INV>(v[b]);
+      if (!INV && q > 1) {
+#pragma unroll
+        for (int u = 1; u < R; ++u) v[b][u] = cmul(v[b][u], w[u]);
+      }
     }
-    bfly<R, INV>(v);
-    if (!INV && q > 1) {
 #pragma unroll
-      for (int u = 1; u < R; ++u) v[u] = cmul(v[u], __ldg(tw + (u - 1) * q + pos));
+    for (int b = 0; b < U; ++b) {
+      if (i0 + b * kClThreads < nbf) {
+#pragma unroll
+        for (int u = 0; u < R; ++u) x[b][u * q] = v[b][u];
+      }
     }
-#pragma unroll
-    for (int u = 0; u < R; ++u) x[u * q] = v[u];
   }
 }
 
 template <bool INV>
-__device__ __forceinline__ void cl_local_dispatch(float2* sm, const ClStages& pl, int s, const float2* __restrict__ tw) {
-  const float2* t = tw + pl.tw_off[s];
+__device__ __forceinline__ void cl_local_dispatch(float2* sm, const ClStages& pl, int s, const float2* __restrict__ t) {
   switch (pl.radix[s]) {
-    case 16: cl_local_stage<16, INV>(sm, pl.M, pl.q[s], t); break;
-    case 8: cl_local_stage<8, INV>(sm, pl.M, pl.q[s], t); break;
-    case 4: cl_local_stage<4, INV>(sm, pl.M, pl.q[s], t); break;
-    case 2: cl_local_stage<2, INV>(sm, pl.M, pl.q[s], t); break;
-    case 3: cl_local_stage<3, INV>(sm, pl.M, pl.q[s], t); break;
-    case 5: cl_local_stage<5, INV>(sm, pl.M, pl.q[s], t); break;
-    default: cl_local_stage<7, INV>(sm, pl.M, pl.q[s], t); break;
+    case 16: cl_local_stage<16, INV, 1>(sm, pl.M, pl.q[s], t); break;
+    case 8: cl_local_stage<8, INV, AVZ_CL_U_8>(sm, pl.M, pl.q[s], t); break;
+    case 4: cl_local_stage<4, INV, AVZ_CL_U_SMALL>(sm, pl.M, pl.q[s], t); break;
+    case 2: cl_local_stage<2, INV, AVZ_CL_U_SMALL>(sm, pl.M, pl.q[s], t); break;
+    case 3: cl_local_stage<3, INV, AVZ_CL_U_SMALL>(sm, pl.M, pl.q[s], t); break;
+    case 5: cl_local_stage<5, INV, AVZ_CL_U_SMALL>(sm, pl.M, pl.q[s], t); break;
+    default: cl_local_stage<7, INV, AVZ_CL_U_8>(sm, pl.M, pl.q[s], t); break;
   }
 }
 
@@ -210,6 +276,7 @@ k_mix_cluster(const float* __restrict__ src, int B, int S, ClStages pl, const fl
   extern __shared__ __align__(16) unsigned char cl_smem[];
   float2* sm = reinterpret_cast<float2*>(cl_smem);   // this CTA's quarter of its plane: M complex values
   float2* s_ramp = sm + pl.M;                        // [2 (mic)][4 (source)][kRampLo + n_hi] phase-ramp factors
+  float2* s_tw = s_ramp + 2 * 4 * (kRampLo + pl.n_hi);   // twiddles of the late local stages
   __shared__ float s_red[kClThreads / 32];
   __shared__ float s_peak;
   cgx::cluster_group cl = cgx::this_cluster();
@@ -240,8 +307,13 @@ k_mix_cluster(const float* __restrict__ src, int B, int S, ClStages pl, const fl
       sincospi(ph, &sn, &cs);
       s_ramp[(mic * 4 + sc) * tl + e] = make_float2((float)cs, (float)-sn);
     }
+    for (int s = 1; s < pl.n; ++s)
+      if (pl.tw_sm[s] >= 0)
+        for (int i = threadIdx.x; i < (pl.radix[s] - 1) * pl.q[s]; i += kClThreads)
+          s_tw[pl.tw_sm[s] + i] = __ldg(tw + pl.tw_off[s] + i);
     __syncthreads();
   }
+  auto stage_tw = [&](int s) -> const float2* { return pl.tw_sm[s] >= 0 ? s_tw + pl.tw_sm[s] : tw + pl.tw_off[s]; };
 
   for (int b = cid; b < B; b += n_clusters) {
     // ---- load: two real sources -> re + i im, this CTA's quarter
@@ -261,101 +333,156 @@ k_mix_cluster(const float* __restrict__ src, int B, int S, ClStages pl, const fl
         for (int i = threadIdx.x; i < M; i += kClThreads) sm[i] = make_float2(__ldcs(sa + i), has_b ? __ldcs(sb + i) : 0.f);
       }
     }
-    cl.sync();
+    cl_barrier();
     // ---- forward stage 0 (radix 4, stride M): across the four CTAs of the plane, in place
     if (active && (dbg == 0 || dbg >= 2)) {
-      for (int m = mlo + threadIdx.x; m < mhi; m += kClThreads) {
-        float2 v[4];
+      for (int m0 = mlo + threadIdx.x; m0 < mhi; m0 += kCrossU * kClThreads) {
+        float2 v[kCrossU][4], w[kCrossU][4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = peer[u][m];
-        bfly4<false>(v[0], v[1], v[2], v[3]);
+        for (int c = 0; c < kCrossU; ++c) {
+          const int m = min(m0 + c * kClThreads, mhi - 1);
 #pragma unroll
-        for (int u = 1; u < 4; ++u) v[u] = cmul(v[u], __ldg(tw0 + (u - 1) * M + m));
+          for (int u = 0; u < 4; ++u) v[c][u] = peer[u][m];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) peer[u][m] = v[u];
-      }
-    }
-    cl.sync();
-    // ---- forward local stages
-    if (active && (dbg == 0 || dbg >= 3)) {
-      for (int s = 1; s < pl.n; ++s) {
-        cl_local_dispatch<false>(sm, pl, s, tw);
-        __syncthreads();
-      }
-    }
-    cl.sync();
-    // ---- combine: unpack the sources at bins (k, L-k), ramps, sums, re-pack - in place on both planes
-    // (the pair list gives every CTA an equal share of the L/2 + 1 pairs, sorted by the local position of the smaller
-    // bin, which lies in this CTA's quarter - of this plane or of the other one)
-    float2* own0 = cl.map_shared_rank(sm, a);
-    float2* own1 = cl.map_shared_rank(sm, 4 + a);
-    const int rtl = kRampLo + pl.n_hi;
-    for (int i = pl.pair_off[rank] + threadIdx.x; i < ((dbg == 0 || dbg >= 4) ? pl.pair_off[rank + 1] : 0); i += kClThreads) {
-      const int4 e = __ldg(pairs + i);
-      const int jo = e.x, qm = e.y >> 16, jm = e.y & 0xffff, kk = e.z;
-      const bool self = e.w != 0;
-      float2* z0o = own0 + jo;
-      float2* z1o = own1 + jo;
-      float2* z0m = cl.map_shared_rank(sm, qm) + jm;
-      float2* z1m = cl.map_shared_rank(sm, 4 + qm) + jm;
-      float2 m1 = make_float2(0.f, 0.f), m2 = m1, tg = m1;
-      for (int pp = 0; pp < P; ++pp) {
-        const float2 zk = pp ? *z1o : *z0o;
-        const float2 zm = pp ? *z1m : *z0m;
-        const float2 av = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
-        const float2 bv = make_float2(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x));
+          for (int u = 1; u < 4; ++u) w[c][u] = __ldg(tw0 + (u - 1) * M + m);
+        }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int s = 2 * pp + h;
-          if (s < S) {
-            const float2 v = h ? bv : av;
-            const float2* t1 = s_ramp + s * rtl;
-            const float2 r1 = cmul(t1[kRampLo + (kk >> 8)], t1[kk & (kRampLo - 1)]);
-            float2 r2 = make_float2(r1.x, -r1.y);
-            if (!prm.sym[s]) {
-              const float2* t2 = s_ramp + (4 + s) * rtl;
-              r2 = cmul(t2[kRampLo + (kk >> 8)], t2[kk & (kRampLo - 1)]);
-            }
-            const float2 d1 = cmul(v, r1);
-            const float2 d2 = cmul(v, r2);
-            m1 = cadd(m1, d1);
-            m2 = cadd(m2, d2);
-            if (s == 0) tg = d1;
+        for (int c = 0; c < kCrossU; ++c) {
+          bfly4<false>(v[c][0], v[c][1], v[c][2], v[c][3]);
+#pragma unroll
+          for (int u = 1; u < 4; ++u) v[c][u] = cmul(v[c][u], w[c][u]);
+        }
+#pragma unroll
+        for (int c = 0; c < kCrossU; ++c) {
+          const int m = m0 + c * kClThreads;
+          if (m < mhi) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) peer[u][m] = v[c][u];
           }
         }
       }
-      float2 in = csub(m1, tg);
-      if (self) {  // DC and Nyquist: the real inverse transform ignores the imaginary part
-        m1.y = 0.f; m2.y = 0.f; tg.y = 0.f; in.y = 0.f;
-      }
-      *z0o = make_float2(m1.x - m2.y, m1.y + m2.x);
-      *z1o = make_float2(tg.x - in.y, tg.y + in.x);
-      if (!self) {
-        *z0m = make_float2(m1.x + m2.y, m2.x - m1.y);
-        *z1m = make_float2(tg.x + in.y, in.x - tg.y);
+    }
+    // the next utterance's sources: ask L2 for them now, the load at the top of the loop then does not wait for HBM
+    if (active && b + n_clusters < B) {
+      const char* nx = reinterpret_cast<const char*>(src + ((int64_t)(b + n_clusters) * S + 2 * p) * L + (int64_t)a * M);
+      const int n_src = (2 * p + 1 < S) ? 2 : 1;
+      const int lines = (int)(((size_t)M * sizeof(float) + 127) / 128);
+      for (int i = threadIdx.x; i < n_src * lines; i += kClThreads) {
+        const int which = i / lines, ln = i - which * lines;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)which * L * sizeof(float) + (size_t)ln * 128));
       }
     }
-    cl.sync();
+    cl_barrier();
+    // ---- forward local stages
+    if (active && (dbg == 0 || dbg >= 3)) {
+      for (int s = 1; s < pl.n; ++s) {
+        cl_local_dispatch<false>(sm, pl, s, stage_tw(s));
+        __syncthreads();
+      }
+    }
+    cl_barrier();
+    // ---- combine: unpack the sources at bins (k, L-k), ramps, sums, re-pack - in place on both planes
+    // (the pair list gives every CTA an equal share of the L/2 + 1 pairs, sorted by the local position of the smaller
+    // bin, which lies in this CTA's quarter - of this plane or of the other one)
+    float2* own0 = (p == 0) ? sm : cl.map_shared_rank(sm, a);
+    float2* own1 = (p == 1) ? sm : cl.map_shared_rank(sm, 4 + a);
+    const int rtl = kRampLo + pl.n_hi;
+    const int pr_end = (dbg == 0 || dbg >= 4) ? pl.pair_off[rank + 1] : 0;
+    for (int i0 = pl.pair_off[rank] + threadIdx.x; i0 < pr_end; i0 += kPairU * kClThreads) {
+      int4 e[kPairU];
+      float2 zk[kPairU][2], zm[kPairU][2];
+#pragma unroll
+      for (int c = 0; c < kPairU; ++c) e[c] = __ldg(pairs + min(i0 + c * kClThreads, pr_end - 1));
+#pragma unroll
+      for (int c = 0; c < kPairU; ++c) {   // all loads of the batch before its first store (in place, see cl_local_stage)
+        const int jo = e[c].x, qm = e[c].y >> 16, jm = e[c].y & 0xffff;
+        zk[c][0] = own0[jo];
+        zm[c][0] = cl.map_shared_rank(sm, qm)[jm];
+        if (P > 1) {
+          zk[c][1] = own1[jo];
+          zm[c][1] = cl.map_shared_rank(sm, 4 + qm)[jm];
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < kPairU; ++c) {
+        if (i0 + c * kClThreads >= pr_end) continue;
+        const int jo = e[c].x, qm = e[c].y >> 16, jm = e[c].y & 0xffff, kk = e[c].z;
+        const bool self = e[c].w != 0;
+        float2 m1 = make_float2(0.f, 0.f), m2 = m1, tg = m1;
+#pragma unroll
+        for (int pp = 0; pp < 2; ++pp) {
+          if (pp < P) {
+            const float2 av = make_float2(0.5f * (zk[c][pp].x + zm[c][pp].x), 0.5f * (zk[c][pp].y - zm[c][pp].y));
+            const float2 bv = make_float2(0.5f * (zk[c][pp].y + zm[c][pp].y), 0.5f * (zm[c][pp].x - zk[c][pp].x));
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int s = 2 * pp + h;
+              if (s < S) {
+                const float2 v = h ? bv : av;
+                const float2* t1 = s_ramp + s * rtl;
+                const float2 r1 = cmul(t1[kRampLo + (kk >> 8)], t1[kk & (kRampLo - 1)]);
+                float2 r2 = make_float2(r1.x, -r1.y);
+                if (!prm.sym[s]) {
+                  const float2* t2 = s_ramp + (4 + s) * rtl;
+                  r2 = cmul(t2[kRampLo + (kk >> 8)], t2[kk & (kRampLo - 1)]);
+                }
+                const float2 d1 = cmul(v, r1);
+                const float2 d2 = cmul(v, r2);
+                m1 = cadd(m1, d1);
+                m2 = cadd(m2, d2);
+                if (s == 0) tg = d1;
+              }
+            }
+          }
+        }
+        float2 in = csub(m1, tg);
+        if (self) {  // DC and Nyquist: the real inverse transform ignores the imaginary part
+          m1.y = 0.f; m2.y = 0.f; tg.y = 0.f; in.y = 0.f;
+        }
+        own0[jo] = make_float2(m1.x - m2.y, m1.y + m2.x);
+        own1[jo] = make_float2(tg.x - in.y, tg.y + in.x);
+        if (!self) {
+          cl.map_shared_rank(sm, qm)[jm] = make_float2(m1.x + m2.y, m2.x - m1.y);
+          cl.map_shared_rank(sm, 4 + qm)[jm] = make_float2(tg.x + in.y, in.x - tg.y);
+        }
+      }
+    }
+    cl_barrier();
     // ---- inverse local stages, backwards
     for (int s = pl.n - 1; s >= ((dbg == 0 || dbg >= 5) ? 1 : pl.n); --s) {
-      cl_local_dispatch<true>(sm, pl, s, tw);
+      cl_local_dispatch<true>(sm, pl, s, stage_tw(s));
       __syncthreads();
     }
-    cl.sync();
+    cl_barrier();
     // ---- inverse stage 0 across the CTAs, 1/L, max|mix|
     float mx = 0.f;
-    for (int m = mlo + threadIdx.x; m < (dbg == 0 ? mhi : 0); m += kClThreads) {
-      float2 v[4];
+    for (int m0 = mlo + threadIdx.x; m0 < (dbg == 0 ? mhi : 0); m0 += kCrossU * kClThreads) {
+      float2 v[kCrossU][4], w[kCrossU][4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = peer[u][m];
+      for (int c = 0; c < kCrossU; ++c) {
+        const int m = min(m0 + c * kClThreads, mhi - 1);
 #pragma unroll
-      for (int u = 1; u < 4; ++u) v[u] = cmulc(v[u], __ldg(tw0 + (u - 1) * M + m));
-      bfly4<true>(v[0], v[1], v[2], v[3]);
+        for (int u = 0; u < 4; ++u) v[c][u] = peer[u][m];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        v[u] = make_float2(v[u].x * inv_n, v[u].y * inv_n);
-        mx = fmaxf(mx, fmaxf(fabsf(v[u].x), fabsf(v[u].y)));
-        peer[u][m] = v[u];
+        for (int u = 1; u < 4; ++u) w[c][u] = __ldg(tw0 + (u - 1) * M + m);
+      }
+#pragma unroll
+      for (int c = 0; c < kCrossU; ++c) {
+#pragma unroll
+        for (int u = 1; u < 4; ++u) v[c][u] = cmulc(v[c][u], w[c][u]);
+        bfly4<true>(v[c][0], v[c][1], v[c][2], v[c][3]);
+      }
+#pragma unroll
+      for (int c = 0; c < kCrossU; ++c) {
+        const int m = m0 + c * kClThreads;
+        if (m < mhi) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float2 o = make_float2(v[c][u].x * inv_n, v[c][u].y * inv_n);
+            mx = fmaxf(mx, fmaxf(fabsf(o.x), fabsf(o.y)));
+            peer[u][m] = o;
+          }
+        }
       }
     }
     mx = warp_max(mx);
@@ -365,7 +492,7 @@ k_mix_cluster(const float* __restrict__ src, int B, int S, ClStages pl, const fl
       for (int w = 1; w < kClThreads / 32; ++w) mx = fmaxf(mx, s_red[w]);
       s_peak = mx;
     }
-    cl.sync();
+    cl_barrier();
     // ---- store: / (max|mix| + eps) (world_building.py:86-91), contiguous quarter of each of the two signals
     float den = 1.f;
     const bool norm = peak_eps >= 0.f;
@@ -375,6 +502,7 @@ k_mix_cluster(const float* __restrict__ src, int B, int S, ClStages pl, const fl
       for (int u = 0; u < 4; ++u) pk = fmaxf(pk, *cl.map_shared_rank(&s_peak, u));
       den = pk + peak_eps;
     }
+    const float rden = __frcp_rn(den);
     float* o_re = (p == 0 ? mix + (int64_t)b * 2 * L : tgt + (int64_t)b * L) + (int64_t)a * M;
     float* o_im = (p == 0 ? mix + ((int64_t)b * 2 + 1) * L : itf + (int64_t)b * L) + (int64_t)a * M;
     if (vec) {
@@ -383,8 +511,8 @@ k_mix_cluster(const float* __restrict__ src, int B, int S, ClStages pl, const fl
         const float4 lo = s4[2 * i], hi = s4[2 * i + 1];
         float4 re = make_float4(lo.x, lo.z, hi.x, hi.z), im = make_float4(lo.y, lo.w, hi.y, hi.w);
         if (norm) {
-          re = make_float4(__fdiv_rn(re.x, den), __fdiv_rn(re.y, den), __fdiv_rn(re.z, den), __fdiv_rn(re.w, den));
-          im = make_float4(__fdiv_rn(im.x, den), __fdiv_rn(im.y, den), __fdiv_rn(im.z, den), __fdiv_rn(im.w, den));
+          re = make_float4(div_by(re.x, den, rden), div_by(re.y, den, rden), div_by(re.z, den, rden), div_by(re.w, den, rden));
+          im = make_float4(div_by(im.x, den, rden), div_by(im.y, den, rden), div_by(im.z, den, rden), div_by(im.w, den, rden));
         }
         __stcs(reinterpret_cast<float4*>(o_re) + i, re);
         __stcs(reinterpret_cast<float4*>(o_im) + i, im);
@@ -392,13 +520,13 @@ k_mix_cluster(const float* __restrict__ src, int B, int S, ClStages pl, const fl
     } else {
       for (int i = threadIdx.x; i < M; i += kClThreads) {
         const float2 v = sm[i];
-        o_re[i] = norm ? __fdiv_rn(v.x, den) : v.x;
-        o_im[i] = norm ? __fdiv_rn(v.y, den) : v.y;
+        o_re[i] = norm ? div_by(v.x, den, rden) : v.x;
+        o_im[i] = norm ? div_by(v.y, den, rden) : v.y;
       }
     }
     __syncthreads();   // everyone has read its quarter before the next utterance's load overwrites it
   }
-  cl.sync();   // nobody leaves while a peer may still be reading its s_peak
+  cl_barrier();   // nobody leaves while a peer may still be reading its s_peak
 }
 
 // ---- host side: plan (radices, twiddle tables, bin / mirror-position table) per signal length and device ----
@@ -417,7 +545,7 @@ std::vector<ClusterPlan*> g_cl_plans;
 bool cluster_radices(int64_t L, ClStages* st) {
   if (L < 8 || (L & 3) != 0 || L / 4 > kClMaxLocal) return false;
   st->n_hi = (int)((L / 2) >> 8) + 1;
-  if ((size_t)(L / 4) * sizeof(float2) + cl_ramp_bytes(st->n_hi) > (size_t)225 * 1024) return false;
+  if ((size_t)(L / 4) * sizeof(float2) + cl_ramp_bytes(st->n_hi) + kTwSmemMax * sizeof(float2) > (size_t)225 * 1024) return false;
   int m = (int)(L / 4), n = 0;
   st->L = (int)L;
   st->M = m;
@@ -465,6 +593,16 @@ int cluster_plan_for(int64_t L, const ClusterPlan** out) {
       }
   }
   if (tw.empty()) tw.push_back(make_float2(1.f, 0.f));
+  // the late stages' tables are small and read by every butterfly of every utterance: they get a copy in shared memory
+  st.tw_sm_n = 0;
+  for (int s = 0; s < kClMaxStages; ++s) st.tw_sm[s] = -1;
+  for (int s = st.n - 1; s >= 1; --s) {
+    const int n = (st.radix[s] - 1) * st.q[s];
+    if (st.q[s] == 1) continue;
+    if (st.tw_sm_n + n > kTwSmemMax) break;
+    st.tw_sm[s] = st.tw_sm_n;
+    st.tw_sm_n += n;
+  }
   // bin of every position (digits reversed) and the position of its mirror bin, packed as (quarter << 16 | local index)
   const int Li = (int)L, M = st.M;
   std::vector<int> bin_of((size_t)Li), pos_of((size_t)Li);
@@ -506,7 +644,7 @@ int cluster_plan_for(int64_t L, const ClusterPlan** out) {
   AVZ_CUDA_OK(cudaMemcpy(dtw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
   AVZ_CUDA_OK(cudaMemcpy(dkp, pairs.data(), pairs.size() * sizeof(int4), cudaMemcpyHostToDevice));
   ClusterPlan* p = new ClusterPlan{dev, L, st, (const float2*)dtw, (const int4*)dkp, 0,
-                                   (size_t)M * sizeof(float2) + cl_ramp_bytes(st.n_hi)};
+                                   (size_t)M * sizeof(float2) + cl_ramp_bytes(st.n_hi) + (size_t)st.tw_sm_n * sizeof(float2)};
   // how many such clusters the device runs at once (0: it cannot - the caller falls back to the multi-pass path)
   if (cudaFuncSetAttribute(k_mix_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem) == cudaSuccess) {
     cudaLaunchConfig_t cfg = {};
