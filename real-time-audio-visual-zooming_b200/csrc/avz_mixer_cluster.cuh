@@ -1,26 +1,26 @@
 // Cluster-resident far-field mixer: one thread-block cluster of 8 CTAs mixes one utterance with its spectra never
-// leaving the chip.  Included by avz_mixer.cu (same translation unit: MixParams, ramp(), kMaxSrc live there).
+// leaving the chip.  Included by avz_mixer.cu (same translation unit: MixParams, kMaxSrc live there).
 //
 // Reference: rt_av_zoom/core/tf_lite_version/world_building.py:46-52 (apply_frac_delay) and :61-93 (mix_and_save) -
 // the same arithmetic as the multi-pass path of avz_mixer.cu (pack two real sources per complex transform, per-bin
 // ramps, Hermitian re-pack, two inverse transforms, peak normalisation), with a different transform:
 //
 //   * the two complex planes of an utterance (sources 0+1 and 2+3 on the way in, mic1 + i mic2 and target + i interferer
-//     on the way out) live in the shared memory of 2 x 4 CTAs: CTA (p, a) holds the contiguous quarter
-//     x[a M .. (a+1) M) of plane p, M = L / 4 (64 000 samples: 125 KB per CTA) - loads and stores are plain contiguous
-//     runs, every sample crosses HBM once in and once out;
-//   * the length-L transform is ONE in-place mixed-radix decimation-in-frequency FFT, L = 4 * r1 * r2 * ...: the first
-//     radix-4 stage has stride M, i.e. its butterflies take one element from each CTA of the plane - it runs over
-//     distributed shared memory (every CTA does the butterflies of a quarter of the positions, reads and writes its
-//     three peers in place); all later stages have strides < M and are local to a CTA (radix 16 / 8 / 4 / 2 / 3 / 5 / 7
-//     butterflies in registers, one shared-memory round trip per stage);
-//   * in-place DIF leaves bin k = d0 + R0 (d1 + R1 (d2 + ...)) at position d0 q0 + d1 q1 + ... (digits reversed); the
-//     combine step needs bin k next to bin L - k: a table gives every position its bin and the position of its mirror
-//     (quarter u of a plane holds the bins k = u mod 4, so quarters 1 and 3 mirror each other, 0 and 2 themselves);
-//     pairs are dealt out evenly over the 8 CTAs, each pair is read and written in place through DSMEM by one thread;
-//   * the inverse is the exact reverse (conjugate twiddle on the way in, conjugate butterfly, stages backwards:
-//     decimation in time) and lands in natural order; max|mix| is exchanged through DSMEM, the division by it happens
-//     on the way out - no scale pass, no atomics.
+//     on the way out) live in the shared memory of 2 x 4 CTAs: CTA (p, a) holds the decimated sequence x[4 m + a],
+//     m < M = L / 4, of plane p (64 000 samples: 125 KB per CTA);
+//   * length-L transform = radix-4 decimation in time: four independent length-M transforms, one per CTA, entirely in
+//     its own shared memory (in-place mixed-radix decimation in frequency: radix 16 / 8 / 4 / 2 / 3 / 7 / 5 / 25
+//     butterflies in registers, one shared-memory round trip per stage, spectrum left in digit-reversed order), then
+//     ONE radix-4 butterfly across the four CTAs per bin: X[k' + M u] = sum_a W4^{a u} W_L^{a k'} Y_a[k'];
+//   * that cross-CTA butterfly is not a pass of its own: the thread that owns local bins k' and M - k' reads the 2 x 8
+//     values of both planes through distributed shared memory, forms the eight bins k' + M u, (M - k') + M u - a set
+//     closed under k -> L - k - does the Hermitian unpack / ramps / re-pack of the four mirror pairs on them, applies
+//     the inverse cross-CTA butterfly and writes the 16 values back in place.  Forward cross stage, combine and
+//     inverse cross stage cost one DSMEM round trip (DSMEM moves ~17 B/clk per SM - it is what bounds this kernel's
+//     exchange steps, so each value crosses it once in and once out);
+//   * the inverse local transforms are the exact reverse (conjugate twiddle on the way in, conjugate butterfly, stages
+//     backwards: decimation in time) and land in natural order; max|mix| is exchanged through DSMEM, the division by
+//     it happens on the way out - no scale pass, no atomics.
 //
 // Index algebra validated in tools/mixer_cluster_model.py before this was written.
 #pragma once
@@ -36,11 +36,11 @@ constexpr int kClMaxStages = 12;
 constexpr int kClMaxLocal = 25600;    // complex elements per CTA (200 KB)
 
 struct ClStages {
-  int L, M, n;
+  int L, M, n;                // n local stages on the M elements of a CTA
   int radix[kClMaxStages];
   int q[kClMaxStages];        // butterfly stride of the stage (block length radix * q)
   int tw_off[kClMaxStages];   // offset of the stage's twiddles [u-1][pos] in the table (stages with q == 1 have none)
-  int pair_off[kClSize + 1];  // CTA r combines pairs [pair_off[r], pair_off[r + 1]) of the pair list
+  int task_off[kClSize + 1];  // CTA r does tasks [task_off[r], task_off[r + 1]) of the exchange step
   int n_hi;                   // entries of a ramp table's coarse half: (L / 2 >> 8) + 1
   int tw_sm[kClMaxStages];    // offset of the stage's twiddles in the shared-memory copy, -1: read from global memory
   int tw_sm_n;                // entries of that copy (the small tables of the late stages)
@@ -187,33 +187,84 @@ __device__ __forceinline__ void bfly(float2 (&v)[R]) {
   }
 }
 
-// One stage on a CTA's own M elements: butterflies over x[blk R q + pos + q t], t < R.  A thread works on U butterflies
-// at a time - all their loads are issued before the first store (the transform is in place, and the compiler cannot
-// know that two butterflies never share an element): with four warps per scheduler it is memory-level parallelism
-// inside a thread, not occupancy, that hides the shared-memory and twiddle latencies.
-template <int R, bool INV, int U>
-__device__ __forceinline__ void cl_local_stage(float2* __restrict__ sm, int M, int q, const float2* __restrict__ tw) {
-  const int nbf = M / R;
-  for (int i0 = threadIdx.x; i0 < nbf; i0 += U * kClThreads) {
-    float2 v[U][R];
-    float2* x[U];
-    int pos[U];
+
+__device__ constexpr float kW25c[17] = {1.f, 0.96858316112863108f, 0.87630668004386358f, 0.72896862742141155f,
+                                        0.53582679497899655f, 0.30901699437494745f, 0.062790519529313527f,
+                                        -0.1873813145857246f, -0.42577929156507272f, -0.63742398974868975f,
+                                        -0.80901699437494734f, -0.92977648588825135f, -0.99211470131447776f,
+                                        -0.99211470131447788f, -0.92977648588825146f, -0.80901699437494778f,
+                                        -0.63742398974868952f};
+__device__ constexpr float kW25s[17] = {0.f, 0.24868988716485479f, 0.48175367410171532f, 0.68454710592868862f,
+                                        0.84432792550201508f, 0.95105651629515353f, 0.99802672842827156f,
+                                        0.98228725072868872f, 0.90482705246601947f, 0.77051324277578925f,
+                                        0.58778525229247325f, 0.36812455268467814f, 0.12533323356430454f,
+                                        -0.12533323356430429f, -0.36812455268467792f, -0.58778525229247269f,
+                                        -0.77051324277578936f};
+
+// Two radix-5 stages on 25 consecutive elements in registers (the last two stages of a transform whose length ends in
+// 5 x 5): stage q = 5 (inputs v[pos + 5 t]), twiddles W25^{pos u} (constants), stage q = 1 (blocks of five).  The
+// inverse runs them backwards with conjugates.  One shared-memory round trip and no twiddle loads for two stages.
+template <bool INV>
+__device__ __forceinline__ void bfly25(float2 (&v)[25]) {
+  if (!INV) {
 #pragma unroll
-    for (int b = 0; b < U; ++b) {
-      int idx = i0 + b * kClThreads;
-      idx = idx < nbf ? idx : i0;          // a batch's missing tail repeats its first butterfly (loads only)
-      int blk = idx;
-      pos[b] = 0;
-      if (q > 1) {
-        blk = idx / q;
-        pos[b] = idx - blk * q;
-      }
-      x[b] = sm + blk * (R * q) + pos[b];
+    for (int pos = 0; pos < 5; ++pos) {
+      float2 w[5] = {v[pos], v[pos + 5], v[pos + 10], v[pos + 15], v[pos + 20]};
+      bfly<5, false>(w);
 #pragma unroll
-      for (int t = 0; t < R; ++t) v[b][t] = x[b][t * q];
+      for (int u = 0; u < 5; ++u)
+        v[pos + 5 * u] = (pos * u == 0) ? w[u] : mul_w<false>(w[u], kW25c[pos * u], kW25s[pos * u]);
     }
 #pragma unroll
-    for (int b = 0; b < U; ++b) {
+    for (int blk = 0; blk < 5; ++blk) {
+      float2 w[5] = {v[5 * blk], v[5 * blk + 1], v[5 * blk + 2], v[5 * blk + 3], v[5 * blk + 4]};
+      bfly<5, false>(w);
+#pragma unroll
+      for (int u = 0; u < 5; ++u) v[5 * blk + u] = w[u];
+    }
+  } else {
+#pragma unroll
+    for (int blk = 0; blk < 5; ++blk) {
+      float2 w[5] = {v[5 * blk], v[5 * blk + 1], v[5 * blk + 2], v[5 * blk + 3], v[5 * blk + 4]};
+      bfly<5, true>(w);
+#pragma unroll
+      for (int u = 0; u < 5; ++u) v[5 * blk + u] = w[u];
+    }
+#pragma unroll
+    for (int pos = 0; pos < 5; ++pos) {
+      float2 w[5];
+#pragma unroll
+      for (int t = 0; t < 5; ++t)
+        w[t] = (pos * t == 0) ? v[pos + 5 * t] : mul_w<true>(v[pos + 5 * t], kW25c[pos * t], kW25s[pos * t]);
+      bfly<5, true>(w);
+#pragma unroll
+      for (int u = 0; u < 5; ++u) v[pos + 5 * u] = w[u];
+    }
+  }
+}
+
+// One stage on a CTA's own M elements: butterflies over x[blk R q + pos + q t], t < R.  QC > 0: the stride is a
+// compile-time constant (the stages of the 64 000-sample plan) - every offset becomes an immediate of the load / store
+// and the (blk, pos) split a multiply-shift; QC == 0: run-time stride, (blk, pos) advanced incrementally.
+// R == 25 stands for the fused pair of radix-5 stages at q = 5 and q = 1 (bfly25).
+template <int R, bool INV, int QC>
+__device__ __forceinline__ void cl_local_stage(float2* __restrict__ sm, int M, int q_rt, const float2* __restrict__ tw) {
+  const int q = QC > 0 ? QC : q_rt;
+  const int nbf = M / R;
+  int blk = (int)threadIdx.x / q, pos = (int)threadIdx.x - blk * q;
+  const int dblk = kClThreads / q, dpos = kClThreads - dblk * q;
+  for (int idx = threadIdx.x; idx < nbf; idx += kClThreads) {
+    if constexpr (QC > 0) {
+      blk = idx / QC;
+      pos = idx - blk * QC;
+    }
+    float2* x = sm + blk * (R * q) + pos;
+    float2 v[R];
+#pragma unroll
+    for (int t = 0; t < R; ++t) v[t] = x[t * q];
+    if constexpr (R == 25) {
+      bfly25<INV>(v);
+    } else {
       float2 w[R];
       if (q > 1) {
         if constexpr (R == 16) {
@@ -221,8 +272,8 @@ __device__ __forceinline__ void cl_local_stage(float2* __restrict__ sm, int M, i
           float2 w1[4], w4[4];
 #pragma unroll
           for (int j = 1; j < 4; ++j) {
-            w1[j] = tw[(j - 1) * q + pos[b]];
-            w4[j] = tw[(4 * j - 1) * q + pos[b]];
+            w1[j] = tw[(j - 1) * q + pos];
+            w4[j] = tw[(4 * j - 1) * q + pos];
           }
 #pragma unroll
           for (int u = 1; u < 16; ++u) {
@@ -231,24 +282,27 @@ __device__ __forceinline__ void cl_local_stage(float2* __restrict__ sm, int M, i
           }
         } else {
 #pragma unroll
-          for (int u = 1; u < R; ++u) w[u] = tw[(u - 1) * q + pos[b]];
+          for (int u = 1; u < R; ++u) w[u] = tw[(u - 1) * q + pos];
         }
       }
       if (INV && q > 1) {
 #pragma unroll
-        for (int t = 1; t < R; ++t) v[b][t] = cmulc(v[b][t], w[t]);
+        for (int t = 1; t < R; ++t) v[t] = cmulc(v[t], w[t]);
       }
-      bfly<R, INV>(v[b]);
+      bfly<R, INV>(v);
       if (!INV && q > 1) {
 #pragma unroll
-        for (int u = 1; u < R; ++u) v[b][u] = cmul(v[b][u], w[u]);
+        for (int u = 1; u < R; ++u) v[u] = cmul(v[u], w[u]);
       }
     }
 #pragma unroll
-    for (int b = 0; b < U; ++b) {
-      if (i0 + b * kClThreads < nbf) {
-#pragma unroll
-        for (int u = 0; u < R; ++u) x[b][u * q] = v[b][u];
+    for (int u = 0; u < R; ++u) x[u * q] = v[u];
+    if (QC == 0) {
+      blk += dblk;
+      pos += dpos;
+      if (pos >= q) {
+        pos -= q;
+        ++blk;
       }
     }
   }
@@ -256,29 +310,82 @@ __device__ __forceinline__ void cl_local_stage(float2* __restrict__ sm, int M, i
 
 template <bool INV>
 __device__ __forceinline__ void cl_local_dispatch(float2* sm, const ClStages& pl, int s, const float2* __restrict__ t) {
-  switch (pl.radix[s]) {
-    case 16: cl_local_stage<16, INV, 1>(sm, pl.M, pl.q[s], t); break;
-    case 8: cl_local_stage<8, INV, AVZ_CL_U_8>(sm, pl.M, pl.q[s], t); break;
-    case 4: cl_local_stage<4, INV, AVZ_CL_U_SMALL>(sm, pl.M, pl.q[s], t); break;
-    case 2: cl_local_stage<2, INV, AVZ_CL_U_SMALL>(sm, pl.M, pl.q[s], t); break;
-    case 3: cl_local_stage<3, INV, AVZ_CL_U_SMALL>(sm, pl.M, pl.q[s], t); break;
-    case 5: cl_local_stage<5, INV, AVZ_CL_U_SMALL>(sm, pl.M, pl.q[s], t); break;
-    default: cl_local_stage<7, INV, AVZ_CL_U_8>(sm, pl.M, pl.q[s], t); break;
+  const int R = pl.radix[s], q = pl.q[s], M = pl.M;
+  // the 64 000-sample plan (M = 16 000 = 16 x 8 x 5 x 25) with compile-time strides
+  if (R == 16 && q == 1000) return cl_local_stage<16, INV, 1000>(sm, M, q, t);
+  if (R == 8 && q == 125) return cl_local_stage<8, INV, 125>(sm, M, q, t);
+  if (R == 5 && q == 25) return cl_local_stage<5, INV, 25>(sm, M, q, t);
+  if (R == 25) return cl_local_stage<25, INV, 1>(sm, M, q, t);
+  switch (R) {
+    case 16: cl_local_stage<16, INV, 0>(sm, M, q, t); break;
+    case 8: cl_local_stage<8, INV, 0>(sm, M, q, t); break;
+    case 4: cl_local_stage<4, INV, 0>(sm, M, q, t); break;
+    case 2: cl_local_stage<2, INV, 0>(sm, M, q, t); break;
+    case 3: cl_local_stage<3, INV, 0>(sm, M, q, t); break;
+    case 5: cl_local_stage<5, INV, 0>(sm, M, q, t); break;
+    default: cl_local_stage<7, INV, 0>(sm, M, q, t); break;
   }
 }
 
+// Hermitian unpack / ramps / re-pack of one mirror pair (k, L - k), k = kk <= L / 2, on both planes, in registers:
+// zk[p] = plane p at bin k, zm[p] = plane p at bin L - k (self: the same bin, k = 0 or L / 2).
+struct ClCombine {
+  const float2* s_ramp;
+  int rtl, S, P;
+  const int* sym;
+  __device__ __forceinline__ void operator()(float2 (&zk)[2], float2 (&zm)[2], int kk, bool self) const {
+    float2 m1 = make_float2(0.f, 0.f), m2 = m1, tg = m1;
+#pragma unroll
+    for (int pp = 0; pp < 2; ++pp) {
+      if (pp < P) {
+        const float2 av = make_float2(0.5f * (zk[pp].x + zm[pp].x), 0.5f * (zk[pp].y - zm[pp].y));
+        const float2 bv = make_float2(0.5f * (zk[pp].y + zm[pp].y), 0.5f * (zm[pp].x - zk[pp].x));
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int s = 2 * pp + h;
+          if (s < S) {
+            const float2 v = h ? bv : av;
+            const float2* t1 = s_ramp + s * rtl;
+            const float2 r1 = cmul(t1[kRampLo + (kk >> 8)], t1[kk & (kRampLo - 1)]);
+            float2 r2 = make_float2(r1.x, -r1.y);
+            if (!sym[s]) {
+              const float2* t2 = s_ramp + (4 + s) * rtl;
+              r2 = cmul(t2[kRampLo + (kk >> 8)], t2[kk & (kRampLo - 1)]);
+            }
+            const float2 d1 = cmul(v, r1);
+            const float2 d2 = cmul(v, r2);
+            m1 = cadd(m1, d1);
+            m2 = cadd(m2, d2);
+            if (s == 0) tg = d1;
+          }
+        }
+      }
+    }
+    float2 in = csub(m1, tg);
+    if (self) {  // DC and Nyquist: the real inverse transform ignores the imaginary part
+      m1.y = 0.f; m2.y = 0.f; tg.y = 0.f; in.y = 0.f;
+    }
+    // x + i y for two real signals x, y: bin k holds X + iY, bin L-k holds conj(X) + i conj(Y)
+    zk[0] = make_float2(m1.x - m2.y, m1.y + m2.x);
+    zk[1] = make_float2(tg.x - in.y, tg.y + in.x);
+    zm[0] = make_float2(m1.x + m2.y, m2.x - m1.y);
+    zm[1] = make_float2(tg.x + in.y, in.x - tg.y);
+  }
+};
+
 __global__ void __launch_bounds__(kClThreads, 1)
 k_mix_cluster(const float* __restrict__ src, int B, int S, ClStages pl, const float2* __restrict__ tw,
-              const int4* __restrict__ pairs, MixParams prm, float peak_eps, int vec, int dbg, float* __restrict__ mix,
+              const int4* __restrict__ tasks, MixParams prm, float peak_eps, int dbg, float* __restrict__ mix,
               float* __restrict__ tgt, float* __restrict__ itf) {
   // dbg (AVZ_EXPERIMENT builds only, 0 otherwise): stop after phase `dbg` and store the planes as they are
-  // (1 load, 2 forward stage 0, 3 forward local stages, 4 combine, 5 inverse local stages)
+  // (1 load, 2 forward local stages, 3 exchange step)
   extern __shared__ __align__(16) unsigned char cl_smem[];
-  float2* sm = reinterpret_cast<float2*>(cl_smem);   // this CTA's quarter of its plane: M complex values
+  float2* sm = reinterpret_cast<float2*>(cl_smem);   // Y_a / x_a of this CTA: M complex values
   float2* s_ramp = sm + pl.M;                        // [2 (mic)][4 (source)][kRampLo + n_hi] phase-ramp factors
   float2* s_tw = s_ramp + 2 * 4 * (kRampLo + pl.n_hi);   // twiddles of the late local stages
   __shared__ float s_red[kClThreads / 32];
   __shared__ float s_peak;
+  __shared__ int s_sym[kMaxSrc];
   cgx::cluster_group cl = cgx::this_cluster();
   const int rank = (int)cl.block_rank(), p = rank >> 2, a = rank & 3;
   const int n_clusters = gridDim.x / kClSize, cid = blockIdx.x / kClSize;
@@ -286,11 +393,7 @@ k_mix_cluster(const float* __restrict__ src, int B, int S, ClStages pl, const fl
   const int P = (S + 1) / 2;
   const bool active = 2 * p < S;            // S <= 2: plane 1 has nothing to transform on the way in
   const float inv_n = (float)(1.0 / (double)L);
-  float2* peer[4];
-#pragma unroll
-  for (int u = 0; u < 4; ++u) peer[u] = cl.map_shared_rank(sm, (p << 2) + u);
-  const float2* tw0 = tw + pl.tw_off[0];    // [3][M]: W_L^{m u}
-  const int per = (M + 3) / 4, mlo = a * per, mhi = min(M, mlo + per);   // this CTA's share of the cross-CTA butterflies
+  const float2* twx = tw + pl.tw_off[kClMaxStages - 1];    // [3][M]: W_L^{a k'(j)}, position order
   // Phase ramps exp(-2 pi i k c), c = tau fs / L per source and microphone (the delays are per call, not per utterance):
   // k = 256 kh + kl, one table per factor, from a float64 phase reduced to [0, 2) - a ramp then costs two shared-memory
   // loads and one complex multiply instead of a sincospif, at the same ~1e-7 accuracy.
@@ -307,195 +410,150 @@ k_mix_cluster(const float* __restrict__ src, int B, int S, ClStages pl, const fl
       sincospi(ph, &sn, &cs);
       s_ramp[(mic * 4 + sc) * tl + e] = make_float2((float)cs, (float)-sn);
     }
-    for (int s = 1; s < pl.n; ++s)
+    for (int s = 0; s < pl.n; ++s)
       if (pl.tw_sm[s] >= 0)
         for (int i = threadIdx.x; i < (pl.radix[s] - 1) * pl.q[s]; i += kClThreads)
           s_tw[pl.tw_sm[s] + i] = __ldg(tw + pl.tw_off[s] + i);
+    if (threadIdx.x < kMaxSrc) s_sym[threadIdx.x] = prm.sym[threadIdx.x];
     __syncthreads();
   }
   auto stage_tw = [&](int s) -> const float2* { return pl.tw_sm[s] >= 0 ? s_tw + pl.tw_sm[s] : tw + pl.tw_off[s]; };
+  const ClCombine combine{s_ramp, kRampLo + pl.n_hi, S, P, s_sym};
 
   for (int b = cid; b < B; b += n_clusters) {
-    // ---- load: two real sources -> re + i im, this CTA's quarter
+    // ---- load: two real sources -> re + i im, every fourth sample (x[4 m + a]): 16-byte stride, whole sectors are
+    //      shared with the three peer CTAs through L2
     if (active) {
-      const float* sa = src + ((int64_t)b * S + 2 * p) * L + (int64_t)a * M;
+      const float* sa = src + ((int64_t)b * S + 2 * p) * L + a;
       const bool has_b = 2 * p + 1 < S;
       const float* sb = sa + L;
-      if (vec) {
-        float4* s4 = reinterpret_cast<float4*>(sm);
-        for (int i = threadIdx.x; i < M / 4; i += kClThreads) {
-          const float4 xa = __ldcs(reinterpret_cast<const float4*>(sa) + i);
-          const float4 xb = has_b ? __ldcs(reinterpret_cast<const float4*>(sb) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-          s4[2 * i] = make_float4(xa.x, xb.x, xa.y, xb.y);
-          s4[2 * i + 1] = make_float4(xa.z, xb.z, xa.w, xb.w);
-        }
-      } else {
-        for (int i = threadIdx.x; i < M; i += kClThreads) sm[i] = make_float2(__ldcs(sa + i), has_b ? __ldcs(sb + i) : 0.f);
-      }
+      for (int m = threadIdx.x; m < M; m += kClThreads)
+        sm[m] = make_float2(__ldg(sa + 4 * m), has_b ? __ldg(sb + 4 * m) : 0.f);
     }
-    cl_barrier();
-    // ---- forward stage 0 (radix 4, stride M): across the four CTAs of the plane, in place
+    __syncthreads();
+    // ---- forward local stages: Y_a = DFT_M(x_a), digit-reversed order
     if (active && (dbg == 0 || dbg >= 2)) {
-      for (int m0 = mlo + threadIdx.x; m0 < mhi; m0 += kCrossU * kClThreads) {
-        float2 v[kCrossU][4], w[kCrossU][4];
-#pragma unroll
-        for (int c = 0; c < kCrossU; ++c) {
-          const int m = min(m0 + c * kClThreads, mhi - 1);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) v[c][u] = peer[u][m];
-#pragma unroll
-          for (int u = 1; u < 4; ++u) w[c][u] = __ldg(tw0 + (u - 1) * M + m);
-        }
-#pragma unroll
-        for (int c = 0; c < kCrossU; ++c) {
-          bfly4<false>(v[c][0], v[c][1], v[c][2], v[c][3]);
-#pragma unroll
-          for (int u = 1; u < 4; ++u) v[c][u] = cmul(v[c][u], w[c][u]);
-        }
-#pragma unroll
-        for (int c = 0; c < kCrossU; ++c) {
-          const int m = m0 + c * kClThreads;
-          if (m < mhi) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) peer[u][m] = v[c][u];
-          }
-        }
-      }
-    }
-    // the next utterance's sources: ask L2 for them now, the load at the top of the loop then does not wait for HBM
-    if (active && b + n_clusters < B) {
-      const char* nx = reinterpret_cast<const char*>(src + ((int64_t)(b + n_clusters) * S + 2 * p) * L + (int64_t)a * M);
-      const int n_src = (2 * p + 1 < S) ? 2 : 1;
-      const int lines = (int)(((size_t)M * sizeof(float) + 127) / 128);
-      for (int i = threadIdx.x; i < n_src * lines; i += kClThreads) {
-        const int which = i / lines, ln = i - which * lines;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)which * L * sizeof(float) + (size_t)ln * 128));
-      }
-    }
-    cl_barrier();
-    // ---- forward local stages
-    if (active && (dbg == 0 || dbg >= 3)) {
-      for (int s = 1; s < pl.n; ++s) {
+      for (int s = 0; s < pl.n; ++s) {
         cl_local_dispatch<false>(sm, pl, s, stage_tw(s));
         __syncthreads();
       }
     }
+    // the next utterance's sources: ask L2 for them now, the load at the top of the loop then does not wait for HBM
+    if (active && a == 0 && b + n_clusters < B) {
+      const char* nx = reinterpret_cast<const char*>(src + ((int64_t)(b + n_clusters) * S + 2 * p) * L);
+      const int n_src = (2 * p + 1 < S) ? 2 : 1;
+      const int lines = (int)(((size_t)L * sizeof(float) + 127) / 128);
+      for (int i = threadIdx.x; i < n_src * lines; i += kClThreads)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)i * 128));
+    }
     cl_barrier();
-    // ---- combine: unpack the sources at bins (k, L-k), ramps, sums, re-pack - in place on both planes
-    // (the pair list gives every CTA an equal share of the L/2 + 1 pairs, sorted by the local position of the smaller
-    // bin, which lies in this CTA's quarter - of this plane or of the other one)
-    float2* own0 = (p == 0) ? sm : cl.map_shared_rank(sm, a);
-    float2* own1 = (p == 1) ? sm : cl.map_shared_rank(sm, 4 + a);
-    const int rtl = kRampLo + pl.n_hi;
-    const int pr_end = (dbg == 0 || dbg >= 4) ? pl.pair_off[rank + 1] : 0;
-    for (int i0 = pl.pair_off[rank] + threadIdx.x; i0 < pr_end; i0 += kPairU * kClThreads) {
-      int4 e[kPairU];
-      float2 zk[kPairU][2], zm[kPairU][2];
+    // ---- exchange step: cross-CTA radix-4 butterfly, combine, inverse cross-CTA butterfly - one DSMEM round trip
+    const int t_end = (dbg == 0 || dbg >= 3) ? pl.task_off[rank + 1] : 0;
+    for (int i = pl.task_off[rank] + threadIdx.x; i < t_end; i += kClThreads) {
+      const int4 e = __ldg(tasks + i);
+      const int jA = e.x, jB = e.y, kA = e.z;
+      const bool two = jA != jB;
+      float2 XA[2][4], XB[2][4], wA[4], wB[4];
 #pragma unroll
-      for (int c = 0; c < kPairU; ++c) e[c] = __ldg(pairs + min(i0 + c * kClThreads, pr_end - 1));
-#pragma unroll
-      for (int c = 0; c < kPairU; ++c) {   // all loads of the batch before its first store (in place, see cl_local_stage)
-        const int jo = e[c].x, qm = e[c].y >> 16, jm = e[c].y & 0xffff;
-        zk[c][0] = own0[jo];
-        zm[c][0] = cl.map_shared_rank(sm, qm)[jm];
-        if (P > 1) {
-          zk[c][1] = own1[jo];
-          zm[c][1] = cl.map_shared_rank(sm, 4 + qm)[jm];
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < kPairU; ++c) {
-        if (i0 + c * kClThreads >= pr_end) continue;
-        const int jo = e[c].x, qm = e[c].y >> 16, jm = e[c].y & 0xffff, kk = e[c].z;
-        const bool self = e[c].w != 0;
-        float2 m1 = make_float2(0.f, 0.f), m2 = m1, tg = m1;
+      for (int u = 0; u < 4; ++u) {
 #pragma unroll
         for (int pp = 0; pp < 2; ++pp) {
+          XA[pp][u] = make_float2(0.f, 0.f);
+          XB[pp][u] = make_float2(0.f, 0.f);
           if (pp < P) {
-            const float2 av = make_float2(0.5f * (zk[c][pp].x + zm[c][pp].x), 0.5f * (zk[c][pp].y - zm[c][pp].y));
-            const float2 bv = make_float2(0.5f * (zk[c][pp].y + zm[c][pp].y), 0.5f * (zm[c][pp].x - zk[c][pp].x));
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int s = 2 * pp + h;
-              if (s < S) {
-                const float2 v = h ? bv : av;
-                const float2* t1 = s_ramp + s * rtl;
-                const float2 r1 = cmul(t1[kRampLo + (kk >> 8)], t1[kk & (kRampLo - 1)]);
-                float2 r2 = make_float2(r1.x, -r1.y);
-                if (!prm.sym[s]) {
-                  const float2* t2 = s_ramp + (4 + s) * rtl;
-                  r2 = cmul(t2[kRampLo + (kk >> 8)], t2[kk & (kRampLo - 1)]);
-                }
-                const float2 d1 = cmul(v, r1);
-                const float2 d2 = cmul(v, r2);
-                m1 = cadd(m1, d1);
-                m2 = cadd(m2, d2);
-                if (s == 0) tg = d1;
-              }
-            }
+            const float2* peer = cl.map_shared_rank(sm, 4 * pp + u);
+            XA[pp][u] = peer[jA];
+            if (two) XB[pp][u] = peer[jB];
           }
         }
-        float2 in = csub(m1, tg);
-        if (self) {  // DC and Nyquist: the real inverse transform ignores the imaginary part
-          m1.y = 0.f; m2.y = 0.f; tg.y = 0.f; in.y = 0.f;
+        if (u > 0) {
+          wA[u] = __ldg(twx + (u - 1) * M + jA);
+          wB[u] = __ldg(twx + (u - 1) * M + jB);
         }
-        own0[jo] = make_float2(m1.x - m2.y, m1.y + m2.x);
-        own1[jo] = make_float2(tg.x - in.y, tg.y + in.x);
+      }
+#pragma unroll
+      for (int pp = 0; pp < 2; ++pp) {
+        if (pp < P) {
+#pragma unroll
+          for (int u = 1; u < 4; ++u) {
+            XA[pp][u] = cmul(XA[pp][u], wA[u]);
+            XB[pp][u] = cmul(XB[pp][u], wB[u]);
+          }
+          bfly4<false>(XA[pp][0], XA[pp][1], XA[pp][2], XA[pp][3]);
+          bfly4<false>(XB[pp][0], XB[pp][1], XB[pp][2], XB[pp][3]);
+        }
+      }
+      // XA[.][u] = bin kA + M u, XB[.][u] = bin kB + M u, kB = M - kA; mirror of (kA, u) is (kB, 3 - u)
+      auto pair = [&](float2 (&X)[2][4], int u, float2 (&Y)[2][4], int v, int kk, bool self) {
+        float2 zk[2] = {X[0][u], X[1][u]}, zm[2] = {Y[0][v], Y[1][v]};
+        combine(zk, zm, kk, self);
         if (!self) {
-          cl.map_shared_rank(sm, qm)[jm] = make_float2(m1.x + m2.y, m2.x - m1.y);
-          cl.map_shared_rank(sm, 4 + qm)[jm] = make_float2(tg.x + in.y, in.x - tg.y);
+          Y[0][v] = zm[0];
+          Y[1][v] = zm[1];
         }
-      }
-    }
-    cl_barrier();
-    // ---- inverse local stages, backwards
-    for (int s = pl.n - 1; s >= ((dbg == 0 || dbg >= 5) ? 1 : pl.n); --s) {
-      cl_local_dispatch<true>(sm, pl, s, stage_tw(s));
-      __syncthreads();
-    }
-    cl_barrier();
-    // ---- inverse stage 0 across the CTAs, 1/L, max|mix|
-    float mx = 0.f;
-    for (int m0 = mlo + threadIdx.x; m0 < (dbg == 0 ? mhi : 0); m0 += kCrossU * kClThreads) {
-      float2 v[kCrossU][4], w[kCrossU][4];
-#pragma unroll
-      for (int c = 0; c < kCrossU; ++c) {
-        const int m = min(m0 + c * kClThreads, mhi - 1);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) v[c][u] = peer[u][m];
-#pragma unroll
-        for (int u = 1; u < 4; ++u) w[c][u] = __ldg(tw0 + (u - 1) * M + m);
+        X[0][u] = zk[0];
+        X[1][u] = zk[1];
+      };
+      if (two) {
+        const int kB = M - kA;
+        pair(XA, 0, XB, 3, kA, false);
+        pair(XA, 1, XB, 2, kA + M, false);
+        pair(XB, 0, XA, 3, kB, false);
+        pair(XB, 1, XA, 2, kB + M, false);
+      } else if (kA == 0) {
+        pair(XA, 0, XA, 0, 0, true);
+        pair(XA, 2, XA, 2, 2 * M, true);
+        pair(XA, 1, XA, 3, M, false);
+      } else {   // kA == M / 2
+        pair(XA, 0, XA, 3, kA, false);
+        pair(XA, 1, XA, 2, kA + M, false);
       }
 #pragma unroll
-      for (int c = 0; c < kCrossU; ++c) {
+      for (int pp = 0; pp < 2; ++pp) {
+        bfly4<true>(XA[pp][0], XA[pp][1], XA[pp][2], XA[pp][3]);
+        if (two) bfly4<true>(XB[pp][0], XB[pp][1], XB[pp][2], XB[pp][3]);
 #pragma unroll
-        for (int u = 1; u < 4; ++u) v[c][u] = cmulc(v[c][u], w[c][u]);
-        bfly4<true>(v[c][0], v[c][1], v[c][2], v[c][3]);
-      }
-#pragma unroll
-      for (int c = 0; c < kCrossU; ++c) {
-        const int m = m0 + c * kClThreads;
-        if (m < mhi) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float2 o = make_float2(v[c][u].x * inv_n, v[c][u].y * inv_n);
-            mx = fmaxf(mx, fmaxf(fabsf(o.x), fabsf(o.y)));
-            peer[u][m] = o;
+        for (int u = 0; u < 4; ++u) {
+          float2 za = XA[pp][u], zb = XB[pp][u];
+          if (u > 0) {
+            za = cmulc(za, wA[u]);
+            zb = cmulc(zb, wB[u]);
           }
+          float2* peer = cl.map_shared_rank(sm, 4 * pp + u);
+          peer[jA] = make_float2(za.x * inv_n, za.y * inv_n);
+          if (two) peer[jB] = make_float2(zb.x * inv_n, zb.y * inv_n);
         }
       }
     }
-    mx = warp_max(mx);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int w = 1; w < kClThreads / 32; ++w) mx = fmaxf(mx, s_red[w]);
-      s_peak = mx;
-    }
     cl_barrier();
-    // ---- store: / (max|mix| + eps) (world_building.py:86-91), contiguous quarter of each of the two signals
+    // ---- inverse local stages, backwards: x_a in natural order, already times 1 / L
+    if (dbg == 0) {
+      for (int s = pl.n - 1; s >= 0; --s) {
+        cl_local_dispatch<true>(sm, pl, s, stage_tw(s));
+        __syncthreads();
+      }
+    }
+    // ---- max|mix| over the four CTAs of plane 0
+    const bool norm = peak_eps >= 0.f && dbg == 0;
+    if (norm) {
+      float mx = 0.f;
+      if (p == 0) {
+        for (int m = threadIdx.x; m < M; m += kClThreads) {
+          const float2 v = sm[m];
+          mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y)));
+        }
+        mx = warp_max(mx);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          for (int w = 1; w < kClThreads / 32; ++w) mx = fmaxf(mx, s_red[w]);
+          s_peak = mx;
+        }
+      }
+      cl_barrier();
+    }
+    // ---- store: / (max|mix| + eps) (world_building.py:86-91), every fourth sample of each of the two signals
     float den = 1.f;
-    const bool norm = peak_eps >= 0.f;
     if (norm) {
       float pk = 0.f;
 #pragma unroll
@@ -503,39 +561,25 @@ k_mix_cluster(const float* __restrict__ src, int B, int S, ClStages pl, const fl
       den = pk + peak_eps;
     }
     const float rden = __frcp_rn(den);
-    float* o_re = (p == 0 ? mix + (int64_t)b * 2 * L : tgt + (int64_t)b * L) + (int64_t)a * M;
-    float* o_im = (p == 0 ? mix + ((int64_t)b * 2 + 1) * L : itf + (int64_t)b * L) + (int64_t)a * M;
-    if (vec) {
-      const float4* s4 = reinterpret_cast<const float4*>(sm);
-      for (int i = threadIdx.x; i < M / 4; i += kClThreads) {
-        const float4 lo = s4[2 * i], hi = s4[2 * i + 1];
-        float4 re = make_float4(lo.x, lo.z, hi.x, hi.z), im = make_float4(lo.y, lo.w, hi.y, hi.w);
-        if (norm) {
-          re = make_float4(div_by(re.x, den, rden), div_by(re.y, den, rden), div_by(re.z, den, rden), div_by(re.w, den, rden));
-          im = make_float4(div_by(im.x, den, rden), div_by(im.y, den, rden), div_by(im.z, den, rden), div_by(im.w, den, rden));
-        }
-        __stcs(reinterpret_cast<float4*>(o_re) + i, re);
-        __stcs(reinterpret_cast<float4*>(o_im) + i, im);
-      }
-    } else {
-      for (int i = threadIdx.x; i < M; i += kClThreads) {
-        const float2 v = sm[i];
-        o_re[i] = norm ? div_by(v.x, den, rden) : v.x;
-        o_im[i] = norm ? div_by(v.y, den, rden) : v.y;
-      }
+    float* o_re = (p == 0 ? mix + (int64_t)b * 2 * L : tgt + (int64_t)b * L) + a;
+    float* o_im = (p == 0 ? mix + ((int64_t)b * 2 + 1) * L : itf + (int64_t)b * L) + a;
+    for (int m = threadIdx.x; m < M; m += kClThreads) {
+      const float2 v = sm[m];
+      o_re[4 * m] = norm ? div_by(v.x, den, rden) : v.x;
+      o_im[4 * m] = norm ? div_by(v.y, den, rden) : v.y;
     }
-    __syncthreads();   // everyone has read its quarter before the next utterance's load overwrites it
+    __syncthreads();   // everyone has read its sequence before the next utterance's load overwrites it
   }
   cl_barrier();   // nobody leaves while a peer may still be reading its s_peak
 }
 
-// ---- host side: plan (radices, twiddle tables, bin / mirror-position table) per signal length and device ----
+// ---- host side: plan (radices, twiddle tables, task list of the exchange step) per signal length and device ----
 struct ClusterPlan {
   int device;
   int64_t L;
   ClStages st;
   const float2* tw;
-  const int4* pairs;
+  const int4* tasks;
   int max_clusters;
   size_t smem;
 };
@@ -549,15 +593,18 @@ bool cluster_radices(int64_t L, ClStages* st) {
   int m = (int)(L / 4), n = 0;
   st->L = (int)L;
   st->M = m;
-  st->radix[n++] = 4;
-  while (m % 16 == 0 && n < kClMaxStages) { st->radix[n++] = 16; m /= 16; }
+  while (m % 16 == 0 && n < kClMaxStages - 1) { st->radix[n++] = 16; m /= 16; }
   for (int r : {8, 4, 2})
-    if (m % r == 0 && n < kClMaxStages) { st->radix[n++] = r; m /= r; }
-  for (int r : {3, 5, 7})
-    while (m % r == 0 && n < kClMaxStages) { st->radix[n++] = r; m /= r; }
-  if (m != 1) return false;
+    if (m % r == 0 && n < kClMaxStages - 1) { st->radix[n++] = r; m /= r; }
+  for (int r : {3, 7, 5})
+    while (m % r == 0 && n < kClMaxStages - 1) { st->radix[n++] = r; m /= r; }
+  if (m != 1 || n == 0) return false;
+  if (n >= 2 && st->radix[n - 1] == 5 && st->radix[n - 2] == 5) {   // ... x 5 x 5: one in-register radix-25 stage
+    st->radix[n - 2] = 25;
+    --n;
+  }
   st->n = n;
-  int len = (int)L;
+  int len = st->M;
   for (int s = 0; s < n; ++s) {
     len /= st->radix[s];
     st->q[s] = len;
@@ -580,6 +627,7 @@ int cluster_plan_for(int64_t L, const ClusterPlan** out) {
       return AVZ_OK;
     }
   const double two_pi = 6.283185307179586476925286766559;
+  const int Li = (int)L, M = st.M;
   std::vector<float2> tw;
   for (int s = 0; s < st.n; ++s) {
     st.tw_off[s] = (int)tw.size();
@@ -592,58 +640,55 @@ int cluster_plan_for(int64_t L, const ClusterPlan** out) {
         tw.push_back(make_float2((float)cos(ang), (float)-sin(ang)));
       }
   }
-  if (tw.empty()) tw.push_back(make_float2(1.f, 0.f));
   // the late stages' tables are small and read by every butterfly of every utterance: they get a copy in shared memory
   st.tw_sm_n = 0;
   for (int s = 0; s < kClMaxStages; ++s) st.tw_sm[s] = -1;
-  for (int s = st.n - 1; s >= 1; --s) {
+  for (int s = st.n - 1; s >= 0; --s) {
     const int n = (st.radix[s] - 1) * st.q[s];
     if (st.q[s] == 1) continue;
     if (st.tw_sm_n + n > kTwSmemMax) break;
     st.tw_sm[s] = st.tw_sm_n;
     st.tw_sm_n += n;
   }
-  // bin of every position (digits reversed) and the position of its mirror bin, packed as (quarter << 16 | local index)
-  const int Li = (int)L, M = st.M;
-  std::vector<int> bin_of((size_t)Li), pos_of((size_t)Li);
-  for (int pos = 0; pos < Li; ++pos) {
+  // local bin of every position (digits reversed; a radix-25 stage is the digit pair of its two radix-5 stages)
+  std::vector<int> bin_of((size_t)M), pos_of((size_t)M);
+  for (int pos = 0; pos < M; ++pos) {
     int k = 0, mult = 1;
     for (int s = 0; s < st.n; ++s) {
-      k += ((pos / st.q[s]) % st.radix[s]) * mult;
+      const int d = (pos / st.q[s]) % st.radix[s];
+      if (st.radix[s] == 25) {
+        k += ((d / 5) + 5 * (d % 5)) * mult;   // position digit pair (d1, d2) = (d / 5, d % 5) -> bin digits d1 + 5 d2
+      } else {
+        k += d * mult;
+      }
       mult *= st.radix[s];
     }
     bin_of[(size_t)pos] = k;
     pos_of[(size_t)k] = pos;
   }
-  // pairs (k, L - k), k <= L / 2, grouped by the quarter that holds bin k, sorted by its local position there; each
-  // quarter's list is halved between its plane-0 and its plane-1 CTA
-  std::vector<int4> pairs;
-  {
-    std::vector<std::vector<int4>> by_q(4);
-    for (int pos = 0; pos < Li; ++pos) {
-      const int k = bin_of[(size_t)pos];
-      const int km = (Li - k) % Li;
-      if (k > km) continue;
-      const int mp = pos_of[(size_t)km];
-      by_q[(size_t)(pos / M)].push_back(make_int4(pos % M, ((mp / M) << 16) | (mp % M), k, mp == pos ? 1 : 0));
+  // cross-CTA twiddles W_L^{a k'} in position order
+  st.tw_off[kClMaxStages - 1] = (int)tw.size();
+  for (int a = 1; a < 4; ++a)
+    for (int pos = 0; pos < M; ++pos) {
+      const double ang = two_pi * (double)(((int64_t)a * bin_of[(size_t)pos]) % Li) / (double)Li;
+      tw.push_back(make_float2((float)cos(ang), (float)-sin(ang)));
     }
-    std::vector<std::vector<int4>> by_rank(kClSize);
-    for (int a = 0; a < 4; ++a) {
-      const size_t half = (by_q[(size_t)a].size() + 1) / 2;
-      for (size_t i = 0; i < by_q[(size_t)a].size(); ++i) by_rank[(size_t)(i < half ? a : 4 + a)].push_back(by_q[(size_t)a][i]);
-    }
-    for (int r = 0; r < kClSize; ++r) {
-      st.pair_off[r] = (int)pairs.size();
-      pairs.insert(pairs.end(), by_rank[(size_t)r].begin(), by_rank[(size_t)r].end());
-    }
-    st.pair_off[kClSize] = (int)pairs.size();
+  // tasks of the exchange step: local bins (k', M - k'), k' <= M / 2, as positions, sorted by the first position; each
+  // CTA of the cluster takes an eighth
+  std::vector<int4> tasks;
+  for (int pos = 0; pos < M; ++pos) {
+    const int k = bin_of[(size_t)pos];
+    const int kb = (M - k) % M;
+    if (k > kb) continue;
+    tasks.push_back(make_int4(pos, pos_of[(size_t)kb], k, 0));
   }
-  void *dtw = nullptr, *dkp = nullptr;
+  for (int r = 0; r <= kClSize; ++r) st.task_off[r] = (int)((int64_t)tasks.size() * r / kClSize);
+  void *dtw = nullptr, *dts = nullptr;
   AVZ_CUDA_OK(cudaMalloc(&dtw, tw.size() * sizeof(float2)));
-  AVZ_CUDA_OK(cudaMalloc(&dkp, pairs.size() * sizeof(int4)));
+  AVZ_CUDA_OK(cudaMalloc(&dts, tasks.size() * sizeof(int4)));
   AVZ_CUDA_OK(cudaMemcpy(dtw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
-  AVZ_CUDA_OK(cudaMemcpy(dkp, pairs.data(), pairs.size() * sizeof(int4), cudaMemcpyHostToDevice));
-  ClusterPlan* p = new ClusterPlan{dev, L, st, (const float2*)dtw, (const int4*)dkp, 0,
+  AVZ_CUDA_OK(cudaMemcpy(dts, tasks.data(), tasks.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  ClusterPlan* p = new ClusterPlan{dev, L, st, (const float2*)dtw, (const int4*)dts, 0,
                                    (size_t)M * sizeof(float2) + cl_ramp_bytes(st.n_hi) + (size_t)st.tw_sm_n * sizeof(float2)};
   // how many such clusters the device runs at once (0: it cannot - the caller falls back to the multi-pass path)
   if (cudaFuncSetAttribute(k_mix_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem) == cudaSuccess) {
@@ -675,8 +720,6 @@ int launch_mix_cluster(const ClusterPlan* cp, const float* src, int B, int S, co
     AVZ_CUDA_OK(cudaFuncSetAttribute(k_mix_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cp->smem));
   }
   const int n_clusters = B < cp->max_clusters ? B : cp->max_clusters;
-  const bool aligned = (((uintptr_t)src | (uintptr_t)mix | (uintptr_t)tgt | (uintptr_t)itf) & 15u) == 0;
-  const int vec = (aligned && (cp->st.M & 3) == 0) ? 1 : 0;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(n_clusters * kClSize));
   cfg.blockDim = dim3(kClThreads);
@@ -693,7 +736,7 @@ int launch_mix_cluster(const ClusterPlan* cp, const float* src, int B, int S, co
 #ifdef AVZ_EXPERIMENT
   if (const char* e = getenv("AVZ_MIX_DBG")) dbg = atoi(e);
 #endif
-  AVZ_CUDA_OK(cudaLaunchKernelEx(&cfg, k_mix_cluster, src, B, S, cp->st, cp->tw, cp->pairs, prm, peak_eps, vec, dbg, mix, tgt, itf));
+  AVZ_CUDA_OK(cudaLaunchKernelEx(&cfg, k_mix_cluster, src, B, S, cp->st, cp->tw, cp->tasks, prm, peak_eps, dbg, mix, tgt, itf));
   return AVZ_OK;
 }
 
