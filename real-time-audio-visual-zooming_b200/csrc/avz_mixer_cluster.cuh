@@ -260,11 +260,20 @@ __device__ __forceinline__ void cl_local_stage(float2* __restrict__ sm, int M, i
     }
     float2* x = sm + blk * (R * q) + pos;
     float2 v[R];
-#pragma unroll
-    for (int t = 0; t < R; ++t) v[t] = x[t * q];
     if constexpr (R == 25) {
+      // The block of 25 is kept in NATURAL order of its bin digit (register d = 5 d1 + d2 holds bin digit d1 + 5 d2:
+      // a compile-time transposition).  This digit is the most significant one of the local bin, so the lower half of
+      // a mirror pair (k', M - k') always sits in the first 12-13 positions of a block and its partner in the last
+      // 12-13 of the mirror block: the exchange step then touches runs of ~100 contiguous bytes of a peer's shared
+      // memory instead of isolated pairs (DSMEM moves 32-byte sectors: 2.2x -> 1.25x the payload).
+#pragma unroll
+      for (int t = 0; t < 25; ++t) v[t] = INV ? x[(t / 5) + 5 * (t % 5)] : x[t];
       bfly25<INV>(v);
+#pragma unroll
+      for (int u = 0; u < 25; ++u) x[INV ? u : (u / 5) + 5 * (u % 5)] = v[u];
     } else {
+#pragma unroll
+      for (int t = 0; t < R; ++t) v[t] = x[t * q];
       float2 w[R];
       if (q > 1) {
         if constexpr (R == 16) {
@@ -294,9 +303,9 @@ __device__ __forceinline__ void cl_local_stage(float2* __restrict__ sm, int M, i
 #pragma unroll
         for (int u = 1; u < R; ++u) v[u] = cmul(v[u], w[u]);
       }
-    }
 #pragma unroll
-    for (int u = 0; u < R; ++u) x[u * q] = v[u];
+      for (int u = 0; u < R; ++u) x[u * q] = v[u];
+    }
     if (QC == 0) {
       blk += dblk;
       pos += dpos;
@@ -373,6 +382,9 @@ struct ClCombine {
   }
 };
 
+// XIO: the 4-way de-interleave between global memory and the decimated sequences runs over DSMEM (below); false: every
+// CTA reads / writes its own every-fourth samples directly (4-byte accesses at a 16-byte stride: any alignment).
+template <bool XIO>
 __global__ void __launch_bounds__(kClThreads, 1)
 k_mix_cluster(const float* __restrict__ src, int B, int S, ClStages pl, const float2* __restrict__ tw,
               const int4* __restrict__ tasks, MixParams prm, float peak_eps, int dbg, float* __restrict__ mix,
@@ -420,17 +432,45 @@ k_mix_cluster(const float* __restrict__ src, int B, int S, ClStages pl, const fl
   auto stage_tw = [&](int s) -> const float2* { return pl.tw_sm[s] >= 0 ? s_tw + pl.tw_sm[s] : tw + pl.tw_off[s]; };
   const ClCombine combine{s_ramp, kRampLo + pl.n_hi, S, P, s_sym};
 
+  // Global memory <-> decimated sequences.  A CTA's sequence x[4 m + a] is every fourth sample: read directly that is a
+  // 4-byte access per 16 bytes, and the four CTAs of a plane each pull every sector of both sources through L2 -> SM
+  // (and write quarter sectors on the way out).  XIO: CTA a of a plane instead moves the CONTIGUOUS quarter
+  // m in [m_lo, m_hi) of all four sequences - float4 = x[4 m .. 4 m + 3] per source, coalesced, every sector once - and
+  // the de-interleave happens over DSMEM: sample j of the vector goes to / comes from CTA j's sm[m] as an 8-byte
+  // (re, im) pair, 256 contiguous bytes per warp.  Position m of every peer is touched by exactly one thread of the
+  // cluster, so the store of utterance b and the load of utterance b + n_clusters share one loop without a barrier
+  // between them.
+  const int m_lo = (int)((int64_t)M * a / 4), m_hi = (int)((int64_t)M * (a + 1) / 4);
+  float2* pl_sm[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) pl_sm[j] = cl.map_shared_rank(sm, 4 * p + j);
+  auto load_x = [&](int b, int m) {
+    const float* sa = src + ((int64_t)b * S + 2 * p) * L + 4 * m;
+    const float4 va = __ldg(reinterpret_cast<const float4*>(sa));
+    const float4 vb = (2 * p + 1 < S) ? __ldg(reinterpret_cast<const float4*>(sa + L)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    pl_sm[0][m] = make_float2(va.x, vb.x);
+    pl_sm[1][m] = make_float2(va.y, vb.y);
+    pl_sm[2][m] = make_float2(va.z, vb.z);
+    pl_sm[3][m] = make_float2(va.w, vb.w);
+  };
+  if constexpr (XIO) {
+    if (active && cid < B)
+      for (int m = m_lo + threadIdx.x; m < m_hi; m += kClThreads) load_x(cid, m);
+    cl_barrier();
+  }
   for (int b = cid; b < B; b += n_clusters) {
-    // ---- load: two real sources -> re + i im, every fourth sample (x[4 m + a]): 16-byte stride, whole sectors are
-    //      shared with the three peer CTAs through L2
-    if (active) {
-      const float* sa = src + ((int64_t)b * S + 2 * p) * L + a;
-      const bool has_b = 2 * p + 1 < S;
-      const float* sb = sa + L;
-      for (int m = threadIdx.x; m < M; m += kClThreads)
-        sm[m] = make_float2(__ldg(sa + 4 * m), has_b ? __ldg(sb + 4 * m) : 0.f);
+    // ---- load: two real sources -> re + i im
+    if constexpr (!XIO) {
+      if (active) {
+        const float* sa = src + ((int64_t)b * S + 2 * p) * L + a;
+        const bool has_b = 2 * p + 1 < S;
+        const float* sb = sa + L;
+#pragma unroll 4
+        for (int m = threadIdx.x; m < M; m += kClThreads)
+          sm[m] = make_float2(__ldg(sa + 4 * m), has_b ? __ldg(sb + 4 * m) : 0.f);
+      }
+      __syncthreads();
     }
-    __syncthreads();
     // ---- forward local stages: Y_a = DFT_M(x_a), digit-reversed order
     if (active && (dbg == 0 || dbg >= 2)) {
       for (int s = 0; s < pl.n; ++s) {
@@ -535,24 +575,22 @@ k_mix_cluster(const float* __restrict__ src, int B, int S, ClStages pl, const fl
     }
     // ---- max|mix| over the four CTAs of plane 0
     const bool norm = peak_eps >= 0.f && dbg == 0;
-    if (norm) {
+    if (norm && p == 0) {
       float mx = 0.f;
-      if (p == 0) {
-        for (int m = threadIdx.x; m < M; m += kClThreads) {
-          const float2 v = sm[m];
-          mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y)));
-        }
-        mx = warp_max(mx);
-        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-          for (int w = 1; w < kClThreads / 32; ++w) mx = fmaxf(mx, s_red[w]);
-          s_peak = mx;
-        }
+      for (int m = threadIdx.x; m < M; m += kClThreads) {
+        const float2 v = sm[m];
+        mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y)));
       }
-      cl_barrier();
+      mx = warp_max(mx);
+      if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        for (int w = 1; w < kClThreads / 32; ++w) mx = fmaxf(mx, s_red[w]);
+        s_peak = mx;
+      }
     }
-    // ---- store: / (max|mix| + eps) (world_building.py:86-91), every fourth sample of each of the two signals
+    if (norm || XIO) cl_barrier();   // s_peak of plane 0 (and, XIO, every peer's finished sequence) visible
+    // ---- store: / (max|mix| + eps) (world_building.py:86-91)
     float den = 1.f;
     if (norm) {
       float pk = 0.f;
@@ -561,14 +599,37 @@ k_mix_cluster(const float* __restrict__ src, int B, int S, ClStages pl, const fl
       den = pk + peak_eps;
     }
     const float rden = __frcp_rn(den);
-    float* o_re = (p == 0 ? mix + (int64_t)b * 2 * L : tgt + (int64_t)b * L) + a;
-    float* o_im = (p == 0 ? mix + ((int64_t)b * 2 + 1) * L : itf + (int64_t)b * L) + a;
-    for (int m = threadIdx.x; m < M; m += kClThreads) {
-      const float2 v = sm[m];
-      o_re[4 * m] = norm ? div_by(v.x, den, rden) : v.x;
-      o_im[4 * m] = norm ? div_by(v.y, den, rden) : v.y;
+    float* o_re = (p == 0 ? mix + (int64_t)b * 2 * L : tgt + (int64_t)b * L);
+    float* o_im = (p == 0 ? mix + ((int64_t)b * 2 + 1) * L : itf + (int64_t)b * L);
+    if constexpr (XIO) {
+      const int bn = b + n_clusters;
+      const bool more = active && bn < B;
+#pragma unroll 2
+      for (int m = m_lo + threadIdx.x; m < m_hi; m += kClThreads) {
+        float2 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = pl_sm[j][m];
+        float4 re = make_float4(v[0].x, v[1].x, v[2].x, v[3].x), im = make_float4(v[0].y, v[1].y, v[2].y, v[3].y);
+        if (norm) {
+          re = make_float4(div_by(re.x, den, rden), div_by(re.y, den, rden), div_by(re.z, den, rden), div_by(re.w, den, rden));
+          im = make_float4(div_by(im.x, den, rden), div_by(im.y, den, rden), div_by(im.z, den, rden), div_by(im.w, den, rden));
+        }
+        *reinterpret_cast<float4*>(o_re + 4 * m) = re;
+        *reinterpret_cast<float4*>(o_im + 4 * m) = im;
+        if (more) load_x(bn, m);   // the next utterance moves in behind the store
+      }
+      cl_barrier();   // sequences of the next utterance complete everywhere (and s_peak no longer needed)
+    } else {
+      o_re += a;
+      o_im += a;
+#pragma unroll 4
+      for (int m = threadIdx.x; m < M; m += kClThreads) {
+        const float2 v = sm[m];
+        o_re[4 * m] = norm ? div_by(v.x, den, rden) : v.x;
+        o_im[4 * m] = norm ? div_by(v.y, den, rden) : v.y;
+      }
+      __syncthreads();   // everyone has read its sequence before the next utterance's load overwrites it
     }
-    __syncthreads();   // everyone has read its sequence before the next utterance's load overwrites it
   }
   cl_barrier();   // nobody leaves while a peer may still be reading its s_peak
 }
@@ -656,11 +717,7 @@ int cluster_plan_for(int64_t L, const ClusterPlan** out) {
     int k = 0, mult = 1;
     for (int s = 0; s < st.n; ++s) {
       const int d = (pos / st.q[s]) % st.radix[s];
-      if (st.radix[s] == 25) {
-        k += ((d / 5) + 5 * (d % 5)) * mult;   // position digit pair (d1, d2) = (d / 5, d % 5) -> bin digits d1 + 5 d2
-      } else {
-        k += d * mult;
-      }
+      k += d * mult;   // (a radix-25 block is stored in natural order of its digit - cl_local_stage)
       mult *= st.radix[s];
     }
     bin_of[(size_t)pos] = k;
@@ -691,7 +748,8 @@ int cluster_plan_for(int64_t L, const ClusterPlan** out) {
   ClusterPlan* p = new ClusterPlan{dev, L, st, (const float2*)dtw, (const int4*)dts, 0,
                                    (size_t)M * sizeof(float2) + cl_ramp_bytes(st.n_hi) + (size_t)st.tw_sm_n * sizeof(float2)};
   // how many such clusters the device runs at once (0: it cannot - the caller falls back to the multi-pass path)
-  if (cudaFuncSetAttribute(k_mix_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem) == cudaSuccess) {
+  if (cudaFuncSetAttribute(k_mix_cluster<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem) == cudaSuccess &&
+      cudaFuncSetAttribute(k_mix_cluster<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem) == cudaSuccess) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(kClSize);
     cfg.blockDim = dim3(kClThreads);
@@ -704,7 +762,10 @@ int cluster_plan_for(int64_t L, const ClusterPlan** out) {
     cfg.attrs = at;
     cfg.numAttrs = 1;
     int nc = 0;
-    if (cudaOccupancyMaxActiveClusters(&nc, k_mix_cluster, &cfg) == cudaSuccess) p->max_clusters = nc;
+    int nc2 = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, k_mix_cluster<true>, &cfg) == cudaSuccess &&
+        cudaOccupancyMaxActiveClusters(&nc2, k_mix_cluster<false>, &cfg) == cudaSuccess)
+      p->max_clusters = nc < nc2 ? nc : nc2;
   }
   (void)cudaGetLastError();
   g_cl_plans.push_back(p);
@@ -717,7 +778,8 @@ int launch_mix_cluster(const ClusterPlan* cp, const float* src, int B, int S, co
   {
     static std::mutex mu;
     std::lock_guard<std::mutex> lk(mu);
-    AVZ_CUDA_OK(cudaFuncSetAttribute(k_mix_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cp->smem));
+    AVZ_CUDA_OK(cudaFuncSetAttribute(k_mix_cluster<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cp->smem));
+    AVZ_CUDA_OK(cudaFuncSetAttribute(k_mix_cluster<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cp->smem));
   }
   const int n_clusters = B < cp->max_clusters ? B : cp->max_clusters;
   cudaLaunchConfig_t cfg = {};
@@ -736,7 +798,16 @@ int launch_mix_cluster(const ClusterPlan* cp, const float* src, int B, int S, co
 #ifdef AVZ_EXPERIMENT
   if (const char* e = getenv("AVZ_MIX_DBG")) dbg = atoi(e);
 #endif
-  AVZ_CUDA_OK(cudaLaunchKernelEx(&cfg, k_mix_cluster, src, B, S, cp->st, cp->tw, cp->tasks, prm, peak_eps, dbg, mix, tgt, itf));
+  // float4 traffic needs 16-byte aligned signals (L is a multiple of 4 here, so every utterance then is)
+  bool xio = (((uintptr_t)src | (uintptr_t)mix | (uintptr_t)tgt | (uintptr_t)itf) & 15) == 0;
+#ifdef AVZ_EXPERIMENT
+  if (const char* e = getenv("AVZ_MIX_XIO")) xio = xio && atoi(e) != 0;
+#endif
+  if (xio) {
+    AVZ_CUDA_OK(cudaLaunchKernelEx(&cfg, k_mix_cluster<true>, src, B, S, cp->st, cp->tw, cp->tasks, prm, peak_eps, dbg, mix, tgt, itf));
+  } else {
+    AVZ_CUDA_OK(cudaLaunchKernelEx(&cfg, k_mix_cluster<false>, src, B, S, cp->st, cp->tw, cp->tasks, prm, peak_eps, dbg, mix, tgt, itf));
+  }
   return AVZ_OK;
 }
 
