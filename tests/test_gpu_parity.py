@@ -448,6 +448,124 @@ def test_ibm_bit_exact_at_scale(az):
 
 # --------------------------------------------------------------------------------------------- full-size properties
 def test_config2_full_size_properties(az):
+    """BASELINE config 2 at full size - 1024 DISTINCT 4 s utterances through the fused path: shape, per-utterance peak
+    == 1, distortionless weights, permutation equivariance (utterances are independent - the sharding invariant: a
+    shuffled batch gives the shuffled output bit for bit), and utterances spread over the batch against the float64
+    oracle (IBM bit-exact, waveform, SIR)."""
+    B = 1024
+    from avzoom import synth as S
+    mix_h, tgt_h, itf_h = S.make_batch(2, B, 4.0, 3, workers=max(1, min(16, os.cpu_count() or 1)))
+    mix, tgt, itf = (torch.from_numpy(a).cuda() for a in (mix_h, tgt_h, itf_h))
+    cfg = az.PRESETS["baseline_oracle"]
+    out, parts = az.oracle_mask_mvdr(mix, tgt, itf, cfg, return_parts=True)
+    assert out.shape == (B, 64000)
+    assert torch.all(out.abs().amax(dim=1) == 1.0)
+    perm = torch.from_numpy(np.random.default_rng(5).permutation(B)).cuda()
+    out_p, parts_p = az.oracle_mask_mvdr(mix[perm].contiguous(), tgt[perm].contiguous(), itf[perm].contiguous(), cfg,
+                                         return_parts=True)
+    assert torch.equal(out_p, out[perm])
+    assert torch.equal(parts_p["ibm_bits"], parts["ibm_bits"][perm])
+    # d^H w = 1 above the high-pass (MVDR distortionless constraint), w = 0 below it
+    d = az.steering_vectors(cfg, mix.device)
+    resp = (d.conj()[None] * parts["w"]).sum(-1)
+    hp = cfg.hp_bins()
+    assert torch.all(parts["w"][:, :hp] == 0)
+    assert float((resp[:, hp:] - 1).abs().max()) < 1e-5
+    ocfg = to_oracle_cfg(cfg)
+    picks = [0, 147, 148, 511, 777, 1023]          # first / last utterance, both sides of a wave of 148 SMs, the middle
+    masks = az.unpack_ibm(parts["ibm_bits"][picks], cfg.n_freq).cpu().numpy()
+    for i, b in enumerate(picks):
+        ref, rp = O.oracle_mask_mvdr(mix_h[b], tgt_h[b], itf_h[b], ocfg, return_parts=True)
+        assert np.array_equal(masks[i], rp["mask_noise"].astype(np.float32))
+        got = out[b].cpu().numpy()
+        assert rel_l2(got, ref) < WAVE_TOL
+        n = min(len(ref), tgt_h.shape[1])
+        assert abs(O.osinr_osir(ref[:n], tgt_h[b, :n], itf_h[b, :n])[1] - O.osinr_osir(got[:n], tgt_h[b, :n], itf_h[b, :n])[1]) < SIR_TOL_DB
+
+
+@pytest.mark.parametrize("preset,B,dur", [("baseline_oracle", 5, 1.3), ("oracle_debug", 3, 2.0), ("baseline_oracle", 300, 0.25)])
+def test_engine_kept_spectrum_equals_recompute(az, preset, B, dur):
+    """The pre-allocated engine in its two modes - pass A keeps the packed mix spectrum and pass B streams it back
+    through a TMA ring, or pass B recomputes the forward transform - must agree bit for bit, and with the ops path."""
+    from avzoom import pipeline
+    cfg = az.PRESETS[preset]
+    mix, tgt, itf = synth(4, B, dur, 2)
+    mix_d, tgt_d, itf_d = (torch.from_numpy(a).cuda() for a in (mix, tgt, itf))
+    e_keep = pipeline.OracleMvdr(cfg, B, mix.shape[-1], mix_d.device, keep_spectrum=True)
+    e_reco = pipeline.OracleMvdr(cfg, B, mix.shape[-1], mix_d.device, keep_spectrum=False)
+    e_sep = pipeline.OracleMvdr(cfg, B, mix.shape[-1], mix_d.device, keep_spectrum=True, fused_norm=True)
+    assert e_keep.spec is not None and e_reco.spec is None and not e_keep.fused_norm and e_sep.fused_norm
+    def same(x, y):
+        # an all-silent output is 0 / 0 = NaN after peak normalisation (as `s_out /= np.max(np.abs(s_out))` gives in
+        # the reference); NaN patterns must agree, everything else bit for bit
+        return torch.equal(torch.isnan(x), torch.isnan(y)) and torch.equal(torch.nan_to_num(x), torch.nan_to_num(y))
+
+    a = e_keep.run(mix_d, tgt_d, itf_d).clone()
+    b = e_reco.run(mix_d, tgt_d, itf_d).clone()
+    assert same(a, b)
+    assert same(a, e_sep.run(mix_d, tgt_d, itf_d))          # fused vs separate peak normalisation
+    assert torch.equal(e_keep.bits, e_reco.bits) and torch.equal(e_keep.R, e_reco.R)
+    assert torch.equal(e_keep.peak, e_reco.peak)
+    c = az.oracle_mask_mvdr(mix_d, tgt_d, itf_d, cfg)
+    assert same(a, c)
+    assert same(e_keep.run(mix_d, tgt_d, itf_d), a)      # reruns are bit-stable
+    ref = O.oracle_mask_mvdr(mix[0], tgt[0], itf[0], to_oracle_cfg(cfg))
+    assert rel_l2(a[0].cpu().numpy(), ref) < WAVE_TOL
+
+
+def test_streamed_engine_equals_single_engine(az):
+    """StreamedOracleMvdr (consecutive batches on alternating CUDA streams / workspaces) returns, for every batch,
+    exactly what one OracleMvdr returns; results stay valid until `depth` further submits."""
+    from avzoom import pipeline
+    cfg = az.PRESETS["baseline_oracle"]
+    batches = []
+    for i in range(5):
+        mix, tgt, itf = synth(2, 6, 0.9, 3, start=10 * i)
+        batches.append(tuple(torch.from_numpy(a).cuda() for a in (mix, tgt, itf)))
+    L = batches[0][0].shape[-1]
+    single = pipeline.OracleMvdr(cfg, 6, L, batches[0][0].device)
+    want = [single.run(*b).clone() for b in batches]
+    loop = pipeline.StreamedOracleMvdr(cfg, 6, L, batches[0][0].device, depth=2)
+    got = []
+    for k, b in enumerate(batches):
+        out = loop.submit(*b)
+        if k >= 1:                       # the previous result is still intact while this one is being computed
+            loop.join()
+            got.append(prev.clone())
+        prev = out
+    loop.join()
+    got.append(prev.clone())
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        pipeline.StreamedOracleMvdr(cfg, 6, L, batches[0][0].device, depth=0)
+
+
+def test_ibm_bit_exact_at_scale(az):
+    """IBM of the fused float32 path (near ties re-decided in float64) against the all-float64 GPU reference over
+    ~16 M bins, the latter pinned to the CPU oracle on one utterance; plus degenerate inputs (identical references:
+    every bin is an exact tie -> all zeros; the near-tie list overflows and the full recheck must still be right)."""
+    cfg = az.PRESETS["baseline_oracle"]
+    mix, tgt, itf = synth(2, 128, 4.0, 3, start=5000)
+    mix_d, tgt_d, itf_d = (torch.from_numpy(a).cuda() for a in (mix, tgt, itf))
+    bits, _, _ = az.ibm_covariance(mix_d, tgt_d, itf_d, cfg)
+    ref_bits = az.ibm_exact_bits(tgt_d, itf_d, cfg)
+    assert torch.equal(bits, ref_bits), f"{int((bits != ref_bits).sum())} IBM words differ"
+    m = az.unpack_ibm(ref_bits[:1], cfg.n_freq).cpu().numpy()[0]
+    mo = O.ibm_noise_mask(O.stft_scipy(tgt[0], 512, 128), O.stft_scipy(itf[0], 512, 128))
+    assert np.array_equal(m, mo.astype(np.float32))
+    # identical references
+    bits2, _, _ = az.ibm_covariance(mix_d[:4], tgt_d[:4], tgt_d[:4].clone(), cfg)
+    assert int(bits2.abs().sum()) == 0
+    # scaled copy: |S_int| = 1.0000001 |S_tgt| everywhere they are non-zero -> all ones except exact-zero bins
+    it2 = (tgt_d[:2].double() * 1.0000001).float()
+    b3, _, _ = az.ibm_covariance(mix_d[:2], tgt_d[:2], it2, cfg)
+    assert torch.equal(b3, az.ibm_exact_bits(tgt_d[:2], it2, cfg))
+
+
+# --------------------------------------------------------------------------------------------- full-size properties
+def test_config2_full_size_properties(az):
     """1024 x 4 s through the fused path: shape, per-utterance peak == 1, distortionless weights, and
     permutation equivariance (utterances are independent - the sharding invariant)."""
     B = 1024
