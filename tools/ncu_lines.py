@@ -1,5 +1,5 @@
 """Per-source-line stall samples of one kernel from an ncu report (needs -lineinfo):
-python tools/ncu_lines.py report.ncu-rep [top N]  - aggregates `ncu --page source --print-source cuda,sass --csv`."""
+python tools/ncu_lines.py report.ncu-rep [top N] [kernel regex]  - aggregates `ncu --page source --print-source cuda,sass --csv`."""
 import csv
 import io
 import subprocess
@@ -9,8 +9,10 @@ import sys
 def main():
     rep = sys.argv[1]
     top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
-                         capture_output=True, text=True).stdout
+    cmd = ["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"]
+    if len(sys.argv) > 3:
+        cmd += ["-k", "regex:" + sys.argv[3]]
+    txt = subprocess.run(cmd, capture_output=True, text=True).stdout
     cur, hdr, agg = None, None, {}
     for r in csv.reader(io.StringIO(txt)):
         if len(r) == 2 and r[0] == "File Path":
