@@ -360,8 +360,9 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                 "frac": achieved / peak_gbs, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo[dom], "kernel_ms": ktimes,
-                "note": "the transforms make this path instruction-issue / FMA-pipe bound, not HBM-bound (DESIGN.md 3.1); the "
-                        "two passes around the kept spectrum also run at 70-80 % of the DRAM peak",
+                "note": "the transforms make this path bound by dependent-issue latency with the FMA pipe half busy, not by "
+                        "HBM (DESIGN.md 3.1, profiles/r2_ncu_pipes.json); pass B (kept-spectrum read-back) also runs at 76 % "
+                        "of the DRAM peak, pass A with store skipping at 34 %",
                 "path_achieved_GBps": (value / world) * FS * ALGO_BYTES_PER_SAMPLE / 1e9,
                 "path_frac_of_hbm_roofline": (value / world) * FS * ALGO_BYTES_PER_SAMPLE / (peak_gbs * 1e9),
                 "issue_slots": issue}
