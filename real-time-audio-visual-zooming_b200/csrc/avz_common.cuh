@@ -12,6 +12,13 @@ namespace avz {
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
 
+// Warp index of this thread within its CTA, in a form the compiler's uniformity analysis accepts as warp-uniform
+// (a broadcast from lane 0).  `threadIdx.x >> 5` is just as uniform but the compiler does not know it: every branch and
+// loop bound derived from it counts as divergent, and each __shfl_sync / __ballot_sync inside such a region is then
+// wrapped in WARPSYNC.COLLECTIVE ... ENDCOLLECTIVE with its operands moved through fixed registers (5 instructions
+// and a serialising register dependency per shuffle instead of 1 instruction).
+__device__ __forceinline__ int warp_id_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 // Per-(device, n_fft) constant tables, created once by tables_for().
 struct Tables {
   const float2* tw;     // [n]  exp(-2 pi i k / n), rounded from float64
@@ -272,16 +279,20 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 __device__ __forceinline__ void st_release_gpu(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// wait until the phase with the given parity has completed; traps instead of hanging if it never does
+// wait until the phase with the given parity has completed; traps instead of hanging if it never does.
+// Called by all 32 lanes of a converged warp: the loop exit is a warp vote, so the compiler sees a warp-uniform branch
+// and the code behind the wait stays "converged" in its analysis (a per-lane exit made it wrap every later shuffle of
+// the frame loop in WARPSYNC.COLLECTIVE - see warp_id_uniform()).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
-  for (uint32_t spin = 0; !done; ++spin) {
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t done;
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
         : "r"(addr), "r"(parity)
         : "memory");
+    if (__all_sync(kFull, done != 0u)) break;
     if (spin > (1u << 22)) {
       printf("mbar_wait timed out (block %d thread %d parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, parity);
       __trap();

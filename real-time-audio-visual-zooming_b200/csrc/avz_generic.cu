@@ -105,7 +105,7 @@ k_stft(const float* __restrict__ x, int C, int64_t L, int T, int hop, float2* __
     s_win[i] = tb.win[i];
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
   const int b = blockIdx.z, c0 = 2 * blockIdx.y;
   const bool has_b = (c0 + 1) < C;
   const float* sa = x + ((int64_t)b * C + c0) * L;
@@ -147,7 +147,7 @@ k_wave_features(const float* __restrict__ mix, int64_t L, int T, int hop, int mo
     s_win[i] = tb.win[i];
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   const float* m0 = mix + (int64_t)b * 2 * L;
   const float* m1 = m0 + L;
@@ -222,7 +222,7 @@ k_cov(const float* __restrict__ mix, const float* __restrict__ tgt, const float*
   }
   for (int i = threadIdx.x; i < WARPS * 5 * FP; i += WARPS * 32) s_acc[i] = 0.f;
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
   const int b = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
   const float* m0 = mix + (int64_t)b * 2 * L;
   const float* m1 = m0 + L;
@@ -389,7 +389,7 @@ k_synth(const float* __restrict__ mix, const float2* __restrict__ spec, const fl
   }
   __syncthreads();
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_id_uniform(), lane = threadIdx.x & 31;
   float2* b0 = bufs + (size_t)warp * 2 * N;
   float2* b1 = b0 + N;
   const float* m0 = (SRC == SRC_MIX) ? mix + (int64_t)b * 2 * L : nullptr;

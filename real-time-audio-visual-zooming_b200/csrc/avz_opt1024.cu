@@ -218,7 +218,7 @@ k1024_features(const float* __restrict__ mix, WaveView vw, int L, int T, int B, 
   __syncthreads();
   Ctx cx;
   cx.init(tb512.tw, tb.tw);
-  const int lane = cx.ln.lane, warp = threadIdx.x >> 5;
+  const int lane = cx.ln.lane, warp = warp_id_uniform();
   float2* sm = s_fft + (size_t)warp * f512::kSmemComplex;
   float2* Y0 = s_y + (size_t)warp * 2 * kYP;
   float2* Y1 = Y0 + kYP;
@@ -308,7 +308,7 @@ k1024_cov(const float* __restrict__ mix, WaveView vw, const float* __restrict__ 
   __syncthreads();
   Ctx cx;
   cx.init(tb512.tw, tb.tw);
-  const int lane = cx.ln.lane, warp = threadIdx.x >> 5;
+  const int lane = cx.ln.lane, warp = warp_id_uniform();
   float2* sm = s_fft + (size_t)warp * f512::kSmemComplex;
   float2* Y0 = s_y + (size_t)warp * 2 * kYP;
   float2* Y1 = Y0 + kYP;
@@ -420,7 +420,7 @@ k1024_apply(const float* __restrict__ mix, WaveView vw, const float2* __restrict
   __syncthreads();
   Ctx cx;
   cx.init(tb512.tw, tb.tw);
-  const int lane = cx.ln.lane, warp = threadIdx.x >> 5;
+  const int lane = cx.ln.lane, warp = warp_id_uniform();
   float2* sm = s_fft + (size_t)warp * f512::kSmemComplex;
   float2* Y0 = s_y + (size_t)warp * 2 * kYP;
   float2* Y1 = Y0 + kYP;

@@ -226,7 +226,7 @@ k512_ibm(const float* __restrict__ tgt, const float* __restrict__ itf, int L, in
 #if AVZ_IBM_FULLTW
   ln.init_full(tb.tw);
 #endif
-  const int lane = ln.lane, warp = threadIdx.x >> 5;
+  const int lane = ln.lane, warp = warp_id_uniform();
   const int b = blockIdx.y;
   const float* tg = tgt + (int64_t)b * L;
   const float* it = itf + (int64_t)b * L;
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(256)
 k512_ibm_fixup(const float* __restrict__ tgt, const float* __restrict__ itf, int64_t L, int T, int hop, int B,
                uint32_t* __restrict__ ibm_bits, uint32_t* __restrict__ lane_bits, AmbList amb_list, Tables tb) {
   const int lane = threadIdx.x & 31;
-  const unsigned long long gw = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const unsigned long long gw = (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (unsigned)warp_id_uniform();
   const unsigned long long nw = (unsigned long long)gridDim.x * (blockDim.x >> 5);
   const unsigned int n = *amb_list.count;
   const bool overflow = n > amb_list.cap;
@@ -469,7 +469,7 @@ __device__ __forceinline__ void cov_body(unsigned char* smem_raw, int b, int chu
 #if AVZ_COV_FULLTW
   ln.init_full(tb.tw);   // this kernel runs 2 CTAs/SM on its accumulators anyway: spend spare registers on twiddles
 #endif
-  const int lane = ln.lane, warp = threadIdx.x >> 5;
+  const int lane = ln.lane, warp = warp_id_uniform();
   const float* m0 = mix + (int64_t)b * 2 * L;
   const float* m1 = m0 + L;
   float w[16];
@@ -777,7 +777,7 @@ __device__ __forceinline__ void apply_body(unsigned char* smem_raw, int b, int b
 #if AVZ_COV_FULLTW
   if (!KEPT || AVZ_APPLY_FULLTW) ln.init_full(tb.tw);   // !KEPT: same twiddles as k512_cov, so recomputed and kept spectra are bit-identical
 #endif
-  const int lane = ln.lane, warp = threadIdx.x >> 5;
+  const int lane = ln.lane, warp = warp_id_uniform();
   const float* m0 = mix + (int64_t)b * 2 * L;
   const float* m1 = m0 + L;
   // S[k] = conj(w0) Y0 + conj(w1) Y1 = a[k] Z[k] + b[k] conj(Z[N-k]),  a = (conj w0 - i conj w1)/2,
@@ -1724,7 +1724,7 @@ k512_stream_step(float* __restrict__ state, const float* __restrict__ hop_in, co
                  const float2* __restrict__ dvec, int n_streams, int t, int t_end, float lam, AvzMvdrCfg cfg,
                  float* __restrict__ hop_out, Tables tb) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_id_uniform();
   float* stage = reinterpret_cast<float*>(smem_raw) + (size_t)warp * kStreamStageFloats;
   float2* sm = reinterpret_cast<float2*>(stage);   // reused once hop, history and tail are in registers
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kWarps * kStreamStageFloats * sizeof(float)) + warp;
@@ -1909,7 +1909,7 @@ k512_features(const float* __restrict__ mix, int L, int T, int wrapped, float* _
   float* tile = reinterpret_cast<float*>(reinterpret_cast<float2*>(smem_raw) + (size_t)kFeatWarps * f512::kSmemComplex);
   Lane ln;
   ln.init(tb.tw);
-  const int lane = ln.lane, warp = threadIdx.x >> 5;
+  const int lane = ln.lane, warp = warp_id_uniform();
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * kFeatTile;
   const float* m0 = mix + (int64_t)b * 2 * L;
