@@ -208,11 +208,12 @@ struct AmbList {
 // "too close to call" is  c^2 <= delta^2 (4 (|Z[k]|^2 + |Z[N-k]|^2) + 2 delta^2).  Only a frame whose INPUT is
 // exactly zero (`live` false) is a true tie everywhere (bit 0, nothing to recheck); a bin that merely comes out
 // as 0 + 0i in float32 (cancellation at the rounding floor) is as uncertain as any other small value.
-__device__ __forceinline__ void ibm_decide(float2 z, float2 m, float d2, bool live, bool& bit, bool& amb) {
+// (k1, k2) = (4 d2, 2 d2^2) for a live frame, (-1, -1) for an all-zero one (the test then never fires).
+__device__ __forceinline__ void ibm_decide(float2 z, float2 m, float k1, float k2, bool& bit, bool& amb) {
   const float c = fmaf(z.x, m.x, -z.y * m.y);
   const float s = fmaf(z.x, z.x, fmaf(z.y, z.y, fmaf(m.x, m.x, m.y * m.y)));
   bit = c < 0.f;
-  amb = live && (c * c <= d2 * fmaf(4.f, s, 2.f * d2));
+  amb = c * c <= fmaf(k1, s, k2);
 }
 
 template <int HOP>
@@ -260,18 +261,19 @@ k512_ibm(const float* __restrict__ tgt, const float* __restrict__ itf, int L, in
     // and sqrt(e2) is the rms bin magnitude; the spectrum here is unscaled).
     const float d2 = tol2 * e2;
     const bool live = e2 > 0.f;   // any non-zero input sample in either reference
+    const float k1 = live ? 4.f * d2 : -1.f, k2 = live ? 2.f * d2 * d2 : -1.f;
     unsigned ballots[8];
     unsigned my_amb = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       bool bit, amb;
-      ibm_decide(v[j], mir[j], d2, live, bit, amb);
+      ibm_decide(v[j], mir[j], k1, k2, bit, amb);
       ballots[j] = __ballot_sync(kFull, bit);
       my_amb |= amb ? (1u << j) : 0u;
     }
     // Nyquist bin 256 = hi[0] of lane 0, its own mirror: same formula with m = z
     bool ny_bit, ny_a;
-    ibm_decide(v[8], v[8], d2, live, ny_bit, ny_a);
+    ibm_decide(v[8], v[8], k1, k2, ny_bit, ny_a);
     const unsigned ny = __ballot_sync(kFull, ny_bit) & 1u;
     if (lane == 0 && ny_a) my_amb |= 1u << 8;
     if (__any_sync(kFull, my_amb != 0u)) {  // warp-uniform, taken for a minority of frames
@@ -299,8 +301,8 @@ k512_ibm(const float* __restrict__ tgt, const float* __restrict__ itf, int L, in
       uint32_t* o = ibm_bits + ((int64_t)b * T + t) * kFW;
 #pragma unroll
       for (int wd = 0; wd < 4; ++wd) {
-        o[wd] = (ballots[2 * wd] & 0xffffu) | (ballots[2 * wd + 1] << 16);
-        o[4 + wd] = (ballots[2 * wd] >> 16) | (ballots[2 * wd + 1] & 0xffff0000u);
+        o[wd] = __byte_perm(ballots[2 * wd], ballots[2 * wd + 1], 0x5410);       // low halves:  (x & 0xffff) | (y << 16)
+        o[4 + wd] = __byte_perm(ballots[2 * wd], ballots[2 * wd + 1], 0x7632);   // high halves: (x >> 16) | (y & 0xffff0000)
       }
       o[8] = ny;
       if (lane_bits != nullptr) {   // the ballots themselves: (slot, lane) order for the sparse kept spectrum
