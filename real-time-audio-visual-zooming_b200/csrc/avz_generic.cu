@@ -50,23 +50,23 @@ int launch_apply(const float* mix, const void* spec, const float* w, const float
                  int B, int64_t L, float* out, float* peak, cudaStream_t st, const AvzChunkView* cv = nullptr);
 }  // namespace o1024
 
-// The register-resident 512-point path serves n_fft 512 with hop 128 / 256 unless AVZ_FORCE_GENERIC=1
-// (kept for A/B checks of the two implementations against each other).
-static bool use_opt512(int n_fft, int hop) {
+// The register-resident 512-point path serves n_fft 512 with hop 128 / 256.  Experiment builds (-DAVZ_EXPERIMENT,
+// tools/build_exp.sh) can force the generic kernels with AVZ_FORCE_GENERIC=1 for A/B checks of the two implementations
+// against each other; the release library reads no environment variable - its results depend on its arguments only.
+static bool force_generic() {
+#ifdef AVZ_EXPERIMENT
   static const bool forced = [] {
     const char* e = getenv("AVZ_FORCE_GENERIC");
     return e && e[0] == '1';
   }();
-  return !forced && n_fft == 512 && (hop == 128 || hop == 256);
+  return forced;
+#else
+  return false;
+#endif
 }
+static bool use_opt512(int n_fft, int hop) { return !force_generic() && n_fft == 512 && (hop == 128 || hop == 256); }
 // ... and n_fft 1024 / hop 512 (the learned pipelines' shape) on the same 512-point transform (even/odd split).
-static bool use_opt1024(int n_fft, int hop) {
-  static const bool forced = [] {
-    const char* e = getenv("AVZ_FORCE_GENERIC");
-    return e && e[0] == '1';
-  }();
-  return !forced && n_fft == 1024 && hop == 512;
-}
+static bool use_opt1024(int n_fft, int hop) { return !force_generic() && n_fft == 1024 && hop == 512; }
 
 template <int N>
 struct Geo {

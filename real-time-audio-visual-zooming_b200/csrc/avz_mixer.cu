@@ -705,10 +705,14 @@ template <bool INV>
 int launch_rows(float2* Z, const float2* W, const float2* mul, const Split& sp, int B, int used, int PP, cudaStream_t st) {
   if (sp.N2 <= 1) return AVZ_OK;
   RowFftPlan plan;
+#ifdef AVZ_EXPERIMENT
   static const bool direct_only = [] {
     const char* e = getenv("AVZ_MIXER_DIRECT_ROWS");   // A/B: force the two-level direct DFT
     return e && e[0] == '1';
   }();
+#else
+  constexpr bool direct_only = false;
+#endif
   if (!direct_only && row_fft_plan(sp.N2, &plan)) {
     const int64_t M = sp.len();
     // 32 rows per block when they fit in ~72 KB (3 blocks of 512 threads per SM = 48 warps: the pass is latency-bound,

@@ -1307,12 +1307,18 @@ __global__ void __launch_bounds__(kWarps * 32, 2) k512_fused(FusedArgs a) {
 // ------------------------------------------------------------------------------------------
 static int ctas_per_sm_target() {
   // CTAs per SM a launch should have at least, so that the tail of the last wave is short (AVZ_CTAS_PER_SM overrides)
+  // (it decides how an utterance is cut into chunks, i.e. the summation order of the covariance partials: fixed in
+  // the release library, so that results depend on the arguments only)
+#ifdef AVZ_EXPERIMENT
   static const int v = [] {
     int t = 20;
     if (const char* e = getenv("AVZ_CTAS_PER_SM")) t = atoi(e);
     return t < 1 ? 1 : t;
   }();
   return v;
+#else
+  return 20;
+#endif
 }
 
 static int frames_per_cta(int B, int T, int sms) {
