@@ -559,8 +559,9 @@ k_mix_scale(float* __restrict__ mix, float* __restrict__ tgt, float* __restrict_
             const unsigned* __restrict__ peak_bits, float peak_eps, int64_t N) {
   const int b = blockIdx.y;
   const float den = __uint_as_float(peak_bits[b]) + peak_eps;
-  // the four signals of an utterance, float4 at a time when N allows it (each signal then starts 16-byte aligned)
-  if ((N & 3) == 0) {
+  // the four signals of an utterance, float4 at a time when N and the caller's pointers allow it (each signal then
+  // starts 16-byte aligned); a shifted view of a larger buffer takes the scalar loop
+  if ((N & 3) == 0 && ((reinterpret_cast<uintptr_t>(mix) | reinterpret_cast<uintptr_t>(tgt) | reinterpret_cast<uintptr_t>(itf)) & 15) == 0) {
     const int64_t n4 = N >> 2;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < 4 * n4; i += (int64_t)gridDim.x * blockDim.x) {
       float4* p = i < 2 * n4 ? reinterpret_cast<float4*>(mix + (int64_t)b * 2 * N) + i

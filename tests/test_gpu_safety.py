@@ -216,3 +216,37 @@ def test_unfused_ops_at_baseline_batch_size(az):
     assert torch.equal(R[777], az.masked_covariance(Y[777], nw[777], packed=True))
     wts = az.mvdr_weights(R, az.steering_vectors(az.PRESETS["baseline_oracle"], Y.device), az.PRESETS["baseline_oracle"])
     assert wts.shape == (B, F, 2) and bool(torch.isfinite(torch.view_as_real(wts)).all())
+
+
+@pytest.mark.parametrize("B,S,L", [(3, 4, 64000), (20, 3, 840), (2, 1, 96), (17, 4, 4096), (2, 2, 8)])
+@pytest.mark.parametrize("misalign", [0, 1])
+def test_far_field_mixer_stays_inside_its_buffers(az, B, S, L, misalign):
+    """The cluster-resident mixer (float4 traffic when every signal is 16-byte aligned, 4-byte accesses otherwise:
+    `misalign` shifts the sources and the outputs by one float) and the multi-pass mixer write nothing outside
+    mix / tgt / itf / ws, and agree with each other."""
+    from avzoom import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(B + 7 * S + L)
+    src = torch.from_numpy(rng.standard_normal((B * S * L + 4,)).astype(np.float32)).cuda()[misalign:misalign + B * S * L]
+    th = np.deg2rad([90.0, 40.0, 130.0, 65.0][:S])
+    delays = np.ascontiguousarray(np.stack([0.02 * np.cos(th) / 343.0, 0.02 * np.cos(th - np.pi) / 343.0], axis=1))
+    dp = delays.ctypes.data_as(C.POINTER(C.c_double))
+    outs = {}
+    for name, fn in (("cluster", lib.avz_farfield_mix_f32), ("passes", lib.avz_farfield_mix_passes_f32)):
+        g = Guard()
+        mix = g.empty((B * 2 * L + 4,), torch.float32)[misalign:misalign + B * 2 * L]
+        tgt = g.empty((B * L + 4,), torch.float32)[misalign:misalign + B * L]
+        itf = g.empty((B * L + 4,), torch.float32)[misalign:misalign + B * L]
+        ws = g.empty((int(lib.avz_farfield_mix_ws_bytes(B, S, L)),), torch.uint8)
+        _lib.check(fn(src.data_ptr(), dp, B, S, L, 16000.0, 1e-9, mix.data_ptr(), tgt.data_ptr(), itf.data_ptr(),
+                      ws.data_ptr(), torch.cuda.current_stream().cuda_stream), name)
+        g.check()
+        # the slack floats around a shifted output are part of the allocation but not of the signal: untouched too
+        for (raw, _), n in zip(g.bufs[:3], (B * 2 * L, B * L, B * L)):
+            body = raw[BAND:BAND + 4 * (n + 4)].view(torch.float32)
+            assert bool((body[:misalign].view(torch.uint8) == POISON).all())
+            assert bool((body[misalign + n:].view(torch.uint8) == POISON).all())
+        outs[name] = (mix.clone(), tgt.clone(), itf.clone())
+        assert torch.isfinite(mix).all() and abs(float(mix.abs().max()) - 1.0) < 1e-5
+    for u, v in zip(outs["cluster"], outs["passes"]):
+        assert float((u - v).norm() / (v.norm() + 1e-30)) < 5e-6 or float(v.abs().max()) < 1e-6
