@@ -250,3 +250,69 @@ def test_far_field_mixer_stays_inside_its_buffers(az, B, S, L, misalign):
         assert torch.isfinite(mix).all() and abs(float(mix.abs().max()) - 1.0) < 1e-5
     for u, v in zip(outs["cluster"], outs["passes"]):
         assert float((u - v).norm() / (v.norm() + 1e-30)) < 5e-6 or float(v.abs().max()) < 1e-6
+
+
+def _shifted(t: torch.Tensor) -> torch.Tensor:
+    """The same values in a contiguous view that starts one element (4 or 8 bytes) into a larger allocation."""
+    big = torch.empty((t.numel() + 8,), dtype=t.dtype, device=t.device)
+    v = big[1:1 + t.numel()].view(t.shape)
+    v.copy_(t)
+    return v
+
+
+def test_ops_accept_buffers_that_are_only_element_aligned(az):
+    """numpy hands the reference arrays of any alignment; a contiguous view that starts one element into a larger
+    CUDA allocation must give the operators the same results as an aligned tensor (vector loads may only be used where
+    the pointer allows them) - never a misaligned-address fault."""
+    from avzoom import synth as S
+    mix_h, tgt_h, itf_h = S.make_batch(11, 3, 0.5, 2)
+    mix, tgt, itf = (torch.from_numpy(a).cuda() for a in (mix_h, tgt_h, itf_h))
+    smix, stgt, sitf = _shifted(mix), _shifted(tgt), _shifted(itf)
+    assert smix.data_ptr() % 16 != 0 and smix.is_contiguous()
+    for preset in ("baseline_oracle", "oracle_debug"):
+        cfg = az.PRESETS[preset]
+        a = az.oracle_mask_mvdr(mix, tgt, itf, cfg)
+        b = az.oracle_mask_mvdr(smix, stgt, sitf, cfg)
+        assert torch.equal(a, b)
+    T = az.num_frames(mix.shape[-1], 512, 128)
+    mask = torch.rand((3, 257, T), device="cuda")
+    a = az.learned_mask_mvdr(mix, mask, az.PRESETS["baseline_learned"])
+    b = az.learned_mask_mvdr(smix, _shifted(mask), az.PRESETS["baseline_learned"])
+    assert torch.equal(a, b)
+    for n_fft, hop in ((512, 128), (1024, 512), (256, 64)):
+        assert torch.equal(az.wave_features(mix, n_fft, hop), az.wave_features(smix, n_fft, hop))
+        Y = az.stft(mix, n_fft, hop)
+        assert torch.equal(Y, az.stft(smix, n_fft, hop))
+        assert torch.equal(az.istft(Y[:, 0], n_fft, hop), az.istft(_shifted(Y[:, 0].contiguous()), n_fft, hop))
+        assert torch.equal(az.logmag_ipd(Y), az.logmag_ipd(_shifted(Y)))
+    T2 = az.num_frames(mix.shape[-1], 1024, 512)
+    mask2 = torch.rand((3, 513, T2), device="cuda")
+    cfg2 = az.PRESETS["full_audio"]
+    assert torch.equal(az.learned_mask_mvdr(mix, mask2, cfg2), az.learned_mask_mvdr(smix, _shifted(mask2), cfg2))
+    n = min(a.shape[-1], tgt.shape[-1])
+    est = a[:, :n].contiguous()
+    assert torch.equal(az.sir_scores(est, tgt[:, :n].contiguous(), itf[:, :n].contiguous()),
+                       az.sir_scores(_shifted(est), _shifted(tgt[:, :n].contiguous()), _shifted(itf[:, :n].contiguous())))
+    pcm = az.ops.float_to_pcm16(est)
+    assert torch.equal(az.ops.pcm16_to_float(pcm), (pcm.float() / 32768.0))
+
+
+def test_engine_and_chunk_driver_accept_element_aligned_buffers(az):
+    """The same for the engine writing into a caller's shifted output buffer and for the chunk driver reading shifted
+    recordings (the 1024 / 512 kernels load float2 pairs: a recording that is only 4-byte aligned must still work)."""
+    from avzoom import pipeline, synth as S
+    from avzoom.core import chunked
+    mix_h, tgt_h, itf_h = S.make_batch(12, 2, 0.7, 3)
+    mix, tgt, itf = (torch.from_numpy(a).cuda() for a in (mix_h, tgt_h, itf_h))
+    cfg = az.PRESETS["baseline_oracle"]
+    eng = pipeline.OracleMvdr(cfg, 2, mix.shape[-1], mix.device)
+    ref = eng.run(mix, tgt, itf).clone()
+    out = _shifted(torch.zeros_like(ref))
+    got = eng.run(_shifted(mix), _shifted(tgt), _shifted(itf), out=out)
+    assert torch.equal(got, ref)
+    rec = torch.from_numpy(np.random.default_rng(3).standard_normal((3, 2, 40001)).astype(np.float32)).cuda() * 0.1
+    model = lambda X: torch.sigmoid(X[:, 0] - X[:, 0].mean())          # noqa: E731  (pointwise stand-in mask model)
+    enh = chunked.ChunkedEnhancer(az.PRESETS["full_audio"])
+    a = enh(rec, model)
+    b = enh(_shifted(rec), model)
+    assert torch.equal(a, b)
