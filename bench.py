@@ -43,6 +43,15 @@ UNIT = "audio-s/s"
 
 
 # ------------------------------------------------------------------------------------------ workload / CPU baseline
+def _build_info():
+    """What libavzoom.so says about its own build (release / experiment, compiler); never fatal."""
+    try:
+        from avzoom import _lib
+        return _lib.load().avz_build_info().decode()
+    except Exception as e:   # an older library without the symbol
+        return f"unknown ({type(e).__name__})"
+
+
 def workload_config():
     """The `config` both arms print: BASELINE config 2, the configuration the metric is quoted on."""
     return {"workload": "BASELINE config 2: 1024 synthetic 4 s 2-ch far-field mixtures per GPU, 1 target + 3 interferers, "
@@ -469,7 +478,8 @@ def run_ours(args):
                                           ("k512_ibm, k512_ibm_fixup, k512_fused (pass A + weights + pass B + normalisation "
                                            "as tasks of one persistent kernel)" if FUSED else "seven separate kernels"),
                          "ms_per_step_single_stream": ms_single, "input_generation_s": round(t_gen, 2),
-                         "host_cpus_bound_to_gpu_numa_node": len(numa_cpus) if numa_cpus else None},
+                         "host_cpus_bound_to_gpu_numa_node": len(numa_cpus) if numa_cpus else None,
+                         "library": _build_info()},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_pcm16": e2e_pcm16,
             "gpu_launches": enh.launches_per_step * args.steps, "clocks": clocks,
             "dSIR_dB": {"output_sir_mean": sir_mean, "mic1_sir_mean": sir_in, "improvement": sir_mean - sir_in},

@@ -75,6 +75,9 @@ typedef struct AvzMvdrCfg {
 
 AVZ_API int avz_version(void);
 AVZ_API const char* avz_last_error(void);
+/* How this binary was built: target architecture, compiler, "release" (reads no environment variable) or "experiment"
+ * (-DAVZ_EXPERIMENT: tuning knobs from the environment, tools/build_exp.sh).  Static string; bench.py records it. */
+AVZ_API const char* avz_build_info(void);
 
 /* Create the per-device constant tables (window, twiddles) for n_fft ahead of time (optional;
  * otherwise done on first use).  Do this before capturing calls into a CUDA graph. */

@@ -50,6 +50,7 @@ _d = C.c_double
 SIGNATURES = {
     "avz_version": (_i, []),
     "avz_last_error": (C.c_char_p, []),
+    "avz_build_info": (C.c_char_p, []),
     "avz_init": (_i, [_i]),
     "avz_profile_enable": (_i, [_i]),
     "avz_profile_get": (_i, [C.POINTER(C.c_float), _i]),

@@ -118,6 +118,18 @@ int avz_version(void) { return AVZ_VERSION; }
 
 const char* avz_last_error(void) { return avz::g_err; }
 
+#define AVZ_STR2(x) #x
+#define AVZ_STR(x) AVZ_STR2(x)
+const char* avz_build_info(void) {
+  return "libavzoom " AVZ_STR(AVZ_VERSION) " sm_100a nvcc " AVZ_STR(__CUDACC_VER_MAJOR__) "." AVZ_STR(__CUDACC_VER_MINOR__) "." AVZ_STR(
+      __CUDACC_VER_BUILD__) " -O3 -lineinfo "
+#ifdef AVZ_EXPERIMENT
+         "experiment (environment knobs enabled)";
+#else
+         "release (no environment reads)";
+#endif
+}
+
 int avz_init(int n_fft) {
   if (n_fft != 256 && n_fft != 512 && n_fft != 1024) return avz::set_error(AVZ_EINVAL, "n_fft=%d unsupported", n_fft);
   avz::Tables t;

@@ -29,6 +29,8 @@ def test_library_exports_every_declared_symbol(az):
         assert hasattr(lib, name), f"{name} declared in avzoom.h but not exported"
     assert declared == set(az._lib.SIGNATURES), "ctypes table and header disagree"
     assert az._lib.load().avz_version() == 100
+    info = az._lib.load().avz_build_info().decode()
+    assert "sm_100a" in info and "release" in info      # the in-tree library is the release build
 
 
 def test_cfg_struct_matches_header(az):

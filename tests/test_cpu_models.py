@@ -20,3 +20,14 @@ def _load(name):
 def test_model_runs(name, capsys):
     _load(name).main()
     assert "ok" in capsys.readouterr().out
+
+
+def test_cluster_mixer_model(capsys):
+    """The cluster-resident mixer as shipped (decimated sequences per CTA, fused exchange step, natural-order radix-25
+    block, quarter-wise I/O) against numpy's FFT and the float64 oracle mixer (the model asserts), and the sector
+    efficiency of its exchange step that the natural-order block buys."""
+    _load("mixer_cluster_model").main()
+    out = capsys.readouterr().out
+    assert "mixer err" in out
+    ratio = float(out.strip().splitlines()[-1].split(":")[-1])
+    assert ratio < 1.5
