@@ -87,3 +87,23 @@ def test_synthetic_mixer_follows_world_building(az):
     # deterministic and batchable
     b1 = synth.make_batch(2, 3, 1.0, 3, start=5)
     assert np.array_equal(b1[0][0], mix[:, :16000])
+
+
+def test_release_library_reads_no_environment_variable():
+    """Every getenv in csrc/ sits behind #ifdef AVZ_EXPERIMENT (tools/build_exp.sh): the results of the release library
+    depend on its arguments only (a stray AVZ_IBM_TOL must not change IBM bits)."""
+    csrc = os.path.join(ROOT, "real-time-audio-visual-zooming_b200", "csrc")
+    for name in sorted(os.listdir(csrc)):
+        if not name.endswith((".cu", ".cuh")):
+            continue
+        depth_exp, stack = 0, []
+        for ln, line in enumerate(open(os.path.join(csrc, name)), 1):
+            t = line.strip()
+            if t.startswith("#if"):
+                stack.append("AVZ_EXPERIMENT" in t and not t.startswith("#ifndef"))
+            elif t.startswith("#else") and stack:
+                stack[-1] = False
+            elif t.startswith("#endif") and stack:
+                stack.pop()
+            if "getenv(" in t and not t.startswith("//"):
+                assert any(stack), f"{name}:{ln}: getenv outside #ifdef AVZ_EXPERIMENT"
